@@ -1,0 +1,73 @@
+"""ctypes binding of ``libd3roma_b200.so`` (the C ABI declared in ``include/d3roma_b200.h``).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, an exception
+is raised.  The product path never routes through ``oracle/`` or a PyTorch re-implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "libd3roma_b200.so"
+
+
+class D3Error(RuntimeError):
+    pass
+
+
+class ConvParams(C.Structure):
+    """Mirror of ``d3_conv_params`` (include/d3roma_b200.h)."""
+
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("Cin", C.c_int32), ("x_pitch", C.c_int32),
+        ("ksize", C.c_int32), ("stride", C.c_int32),
+        ("w", C.c_void_p),
+        ("Cout", C.c_int32),
+        ("sc1", C.c_void_p), ("C1", C.c_int32), ("sc1_pitch", C.c_int32),
+        ("sc2", C.c_void_p), ("C2", C.c_int32), ("sc2_pitch", C.c_int32),
+        ("bias", C.c_void_p), ("bias_bstride", C.c_int32),
+        ("residual", C.c_void_p), ("res_pitch", C.c_int32),
+        ("out", C.c_void_p), ("out_pitch", C.c_int32),
+        ("stats", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def _declare(lib: C.CDLL) -> None:
+    vp, i32, i64, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
+    sigs = {
+        "d3_last_error": (C.c_char_p, []),
+        "d3_version": (i32, []),
+        "d3_launch_count": (i64, []),
+        "d3_reset_launch_count": (None, []),
+        "d3_conv2d_igemm": (i32, [C.POINTER(ConvParams), vp]),
+    }
+    for name, (res, args) in sigs.items():
+        if not hasattr(lib, name):
+            continue
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+
+
+def lib() -> C.CDLL:
+    """Return the loaded library; raise loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise D3Error(
+                f"{LIB_PATH} is missing: build it with `python -m d3roma_b200.build` "
+                "(there is no CPU / PyTorch fallback for the CUDA path)")
+        _lib = C.CDLL(str(LIB_PATH))
+        _declare(_lib)
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().d3_last_error()
+        raise D3Error(f"d3roma_b200 error {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,42 @@
+// Library-level C-ABI entry points: error text, version, launch counter.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "internal.h"
+
+namespace d3 {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  }
+  return n;
+}
+
+}  // namespace d3
+
+extern "C" {
+
+const char* d3_last_error(void) { return d3::g_err; }
+int d3_version(void) { return 100; }
+int64_t d3_launch_count(void) { return d3::g_launches.load(std::memory_order_relaxed); }
+void d3_reset_launch_count(void) { d3::g_launches.store(0, std::memory_order_relaxed); }
+
+}  // extern "C"

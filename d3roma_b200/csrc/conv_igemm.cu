@@ -1,0 +1,482 @@
+// Implicit-GEMM convolution for sm_100a: TMA-fed tcgen05.mma with TMEM accumulators.
+//
+// GEMM view: M = output pixels (B*Ho*Wo), N = Cout, K = taps*Cin (+ folded 1x1
+// shortcut channels). Activations are bf16 NHWC, so one K-block (64 channels of one filter tap) of the
+// A operand for a TH x TW pixel tile is a single 4-D TMA box [64c, TW, TH, 1] whose start coordinate is
+// shifted by the tap offset; out-of-image coordinates are zero-filled by TMA, which *is* the conv zero
+// padding. Weights are pre-packed [Cout][Ktot] (K-major) so the B operand is a 2-D box [64k, BN].
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0   TMA producer (one lane)          smem ring: STAGES x {A 16 KB, B BN*128 B}, SWIZZLE_128B
+//   warp 1   tcgen05.mma issuer (one lane)    accumulators: 2 x [128 lanes x BN cols] fp32 in TMEM
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue: tcgen05.ld -> +bias(+temb) (+identity residual) -> bf16 -> swizzled smem -> TMA store,
+//            plus per-(sample, channel-quad) sum / sum-of-squares of the rounded outputs for the next GroupNorm.
+//
+// Replaces aten::conv2d (cuDNN) for every 3x3 / 1x1 conv with Cin % 64 == 0 and Cout % 128 == 0
+// (reference call sites: diffusers ResnetBlock2D / Downsample2D / Upsample2D / Attention linears, built at
+// /root/reference/train.py:788-810).
+#include "common.cuh"
+#include "internal.h"
+#include "tensormap.h"
+
+namespace d3 {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTileM = 128;
+constexpr uint32_t kATileBytes = kTileM * 64 * 2;  // 16 KB
+constexpr uint32_t kStagingBytes = kTileM * 128;   // one 64-channel chunk of the output tile
+
+struct ConvKArgs {
+  int B, Ho, Wo, Cout;
+  int TH, TW, tilesH, tilesW, nTilesN, numTiles;
+  int ksize, stride, pad;
+  int Cin, cbMain;
+  int kbMain, kbSc1, kbSc2, kbTotal;
+  int sc_off2;  // channel offset of the second half-res parity plane (stride 2 only): x_pitch
+  const float* bias;
+  int bias_bstride;
+  const __nv_bfloat16* residual;
+  int res_pitch;
+  double* stats;
+  uint32_t a_bytes;
+};
+
+struct TileCoord {
+  int b, h0, w0, n0;
+};
+
+D3_DEVINL TileCoord decode_tile(const ConvKArgs& a, int tile, int BN) {
+  TileCoord t;
+  int nt = tile % a.nTilesN;
+  int p = tile / a.nTilesN;
+  int tw = p % a.tilesW;
+  p /= a.tilesW;
+  int th = p % a.tilesH;
+  t.b = p / a.tilesH;
+  t.h0 = th * a.TH;
+  t.w0 = tw * a.TW;
+  t.n0 = nt * BN;
+  return t;
+}
+
+// Butterfly transpose-reduce: on entry every lane holds 32 partial values v[0..31]; on exit lane l holds
+// sum over all 32 lanes of the original v[l]. 31 shuffles.
+D3_DEVINL float warp_transpose_reduce32(float (&v)[32], uint32_t lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      float send = upper ? v[i] : v[i + off];
+      float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+
+// Epilogue math for 32 accumulator columns (half of a 64-channel chunk): + bias (+ residual), round to bf16,
+// write the swizzled staging row, and collect per-quad sum / sum-of-squares of the rounded values.
+template <int HALF>
+D3_DEVINL void epi_process32(const uint32_t (&v)[32], float (&sums)[32], const float4* bp, const uint4* rp,
+                             bool valid, uint8_t* sbuf, uint32_t r) {
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {  // 8 channels per iteration -> one 16 B smem store
+    const int j8 = HALF * 4 + jj;
+    float x[8];
+    const float4 b0 = __ldg(bp + 2 * j8), b1 = __ldg(bp + 2 * j8 + 1);
+    x[0] = __uint_as_float(v[8 * jj + 0]) + b0.x;
+    x[1] = __uint_as_float(v[8 * jj + 1]) + b0.y;
+    x[2] = __uint_as_float(v[8 * jj + 2]) + b0.z;
+    x[3] = __uint_as_float(v[8 * jj + 3]) + b0.w;
+    x[4] = __uint_as_float(v[8 * jj + 4]) + b1.x;
+    x[5] = __uint_as_float(v[8 * jj + 5]) + b1.y;
+    x[6] = __uint_as_float(v[8 * jj + 6]) + b1.z;
+    x[7] = __uint_as_float(v[8 * jj + 7]) + b1.w;
+    if (rp != nullptr) {
+      const uint4 rv = __ldg(rp + j8);
+      float2 f;
+      f = unpack_bf16x2(rv.x); x[0] += f.x; x[1] += f.y;
+      f = unpack_bf16x2(rv.y); x[2] += f.x; x[3] += f.y;
+      f = unpack_bf16x2(rv.z); x[4] += f.x; x[5] += f.y;
+      f = unpack_bf16x2(rv.w); x[6] += f.x; x[7] += f.y;
+    }
+    uint4 pk;
+    pk.x = pack_bf16x2(x[0], x[1]);
+    pk.y = pack_bf16x2(x[2], x[3]);
+    pk.z = pack_bf16x2(x[4], x[5]);
+    pk.w = pack_bf16x2(x[6], x[7]);
+    // statistics of the values as stored (bf16-rounded), masked to in-image pixels
+    const float2 f0 = unpack_bf16x2(pk.x), f1 = unpack_bf16x2(pk.y);
+    const float2 f2 = unpack_bf16x2(pk.z), f3 = unpack_bf16x2(pk.w);
+    const float s0 = (f0.x + f0.y) + (f1.x + f1.y);
+    const float q0 = (f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y);
+    const float s1 = (f2.x + f2.y) + (f3.x + f3.y);
+    const float q1 = (f2.x * f2.x + f2.y * f2.y) + (f3.x * f3.x + f3.y * f3.y);
+    sums[2 * j8] = valid ? s0 : 0.f;
+    sums[2 * j8 + 1] = valid ? s1 : 0.f;
+    sums[16 + 2 * j8] = valid ? q0 : 0.f;
+    sums[16 + 2 * j8 + 1] = valid ? q1 : 0.f;
+    // SWIZZLE_128B: 16-byte chunk index XOR (row % 8)
+    *reinterpret_cast<uint4*>(sbuf + r * 128 + ((j8 ^ (r & 7)) << 4)) = pk;
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS1,
+                  const __grid_constant__ CUtensorMap tmS2, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmO, const ConvKArgs a) {
+  constexpr uint32_t kBBytes = BN * 128;
+  constexpr uint32_t kStageBytes = kATileBytes + kBBytes;
+  constexpr uint32_t kTmemCols = 2 * BN;  // 256 or 512 (power of two)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + STAGES * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* spart = reinterpret_cast<float*>(tmem_ptr + 4);  // [4][32]
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    if (a.kbSc1) tma_prefetch_desc(&tmS1);
+    if (a.kbSc2) tma_prefetch_desc(&tmS2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(a, tile, BN);
+        for (int kb = 0; kb < a.kbTotal; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * kStageBytes;
+          uint8_t* sB = sA + kATileBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], a.a_bytes + kBBytes);
+          if (kb < a.kbMain) {
+            const int tap = kb / a.cbMain;
+            const int cb = kb - tap * a.cbMain;
+            const int kh = tap / a.ksize;
+            const int kw = tap - kh * a.ksize;
+            if (a.stride == 1) {
+              tma_load_4d(sA, &tmA, &full_bar[stage], cb * 64, t.w0 + kw - a.pad, t.h0 + kh - a.pad, t.b);
+            } else {
+              // input pixel (2*ho + kh - 1, 2*wo + kw - 1) in the parity-split 5-D view
+              const int dh = kh - 1, dw = kw - 1;
+              const int hh = t.h0 + (dh < 0 ? -1 : 0), ph = (dh == 0) ? 0 : 1;
+              const int ww = t.w0 + (dw < 0 ? -1 : 0), pw = (dw == 0) ? 0 : 1;
+              tma_load_5d(sA, &tmA, &full_bar[stage], pw * a.sc_off2 + cb * 64, ww, ph, hh, t.b);
+            }
+          } else if (kb < a.kbMain + a.kbSc1) {
+            tma_load_4d(sA, &tmS1, &full_bar[stage], (kb - a.kbMain) * 64, t.w0, t.h0, t.b);
+          } else {
+            tma_load_4d(sA, &tmS2, &full_bar[stage], (kb - a.kbMain - a.kbSc1) * 64, t.w0, t.h0, t.b);
+          }
+          tma_load_2d(sB, &tmB, &full_bar[stage], kb * 64, t.n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < a.kbTotal; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * kStageBytes);
+          const uint64_t adesc = make_sw128_kmajor_desc(sA);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sA + kATileBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const uint32_t q = warp - 4;
+    const uint32_t et = threadIdx.x - 128;
+    const uint32_t r = q * 32 + lane;  // accumulator row == pixel index inside the tile
+    const int th = r / a.TW;
+    const int tw = r - th * a.TW;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(a, tile, BN);
+      const int h = t.h0 + th, w = t.w0 + tw;
+      const bool valid = (th < a.TH) && (h < a.Ho) && (w < a.Wo);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        uint32_t v0[32], v1[32];
+        {
+          const uint32_t taddr = tmem_base + ((q * 32) << 16) + acc * BN + c * 64;
+          tmem_ld_32x32b_x32(taddr, v0);
+          tmem_ld_32x32b_x32(taddr + 32, v1);
+          tmem_ld_wait();
+        }
+        if (c == BN / 64 - 1) {
+          // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        uint8_t* sbuf = staging + (chunk_ctr & 1) * kStagingBytes;
+        if (et == 0) tma_store_wait_read<1>();  // the store that last used this buffer has drained
+        named_bar_sync(1, 128);
+
+        const int n_base = t.n0 + c * 64;
+        const float4* bp = reinterpret_cast<const float4*>(a.bias + (size_t)t.b * a.bias_bstride + n_base);
+        const uint4* rp = nullptr;
+        if (a.residual != nullptr && valid) {
+          rp = reinterpret_cast<const uint4*>(a.residual + ((size_t)(t.b * a.Ho + h) * a.Wo + w) * a.res_pitch +
+                                              n_base);
+        }
+        float sums[32];  // [0..15] quad sums, [16..31] quad sums of squares
+        epi_process32<0>(v0, sums, bp, rp, valid, sbuf, r);
+        epi_process32<1>(v1, sums, bp, rp, valid, sbuf, r);
+        if (a.stats != nullptr) {
+          const float tot = warp_transpose_reduce32(sums, lane);
+          spart[q * 32 + lane] = tot;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (et == 0) {
+          tma_store_4d(&tmO, sbuf, n_base, t.w0, t.h0, t.b);
+          tma_store_commit();
+        }
+        if (a.stats != nullptr && et < 32) {
+          const float tot = spart[et] + spart[32 + et] + spart[64 + et] + spart[96 + et];
+          const int quad = (n_base >> 2) + (et & 15);
+          atomicAdd(a.stats + ((size_t)t.b * (a.Cout >> 2) + quad) * 2 + (et >> 4), static_cast<double>(tot));
+        }
+        ++chunk_ctr;
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int BN, int STAGES>
+constexpr size_t conv_smem_bytes() {
+  return 1024 + STAGES * (kATileBytes + BN * 128) + 2 * kStagingBytes + (2 * STAGES + 4) * 8 + 16 + 4 * 32 * 4;
+}
+
+// Pick the pixel tile TH x TW (TH*TW <= 128) that wastes the fewest MMA rows.
+void choose_tile(int Ho, int Wo, int* TH, int* TW) {
+  double best = -1.0;
+  int bh = 1, bw = 1;
+  for (int tw = 1; tw <= 128 && tw <= Wo; ++tw) {
+    int th = 128 / tw;
+    if (th > Ho) th = Ho;
+    if (th < 1) continue;
+    if (th > 256 || tw > 256) continue;
+    const double tiles = double(ceil_div(Ho, th)) * ceil_div(Wo, tw);
+    const double eff = double(Ho) * Wo / (tiles * 128.0);
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > bw)) {
+      best = eff;
+      bh = th;
+      bw = tw;
+    }
+  }
+  *TH = bh;
+  *TW = bw;
+}
+
+}  // namespace
+
+}  // namespace d3
+
+extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
+  using namespace d3;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  D3_REQUIRE(p != nullptr, "conv: null params");
+  D3_REQUIRE(p->ksize == 3 || p->ksize == 1, "conv: ksize must be 1 or 3 (got %d)", p->ksize);
+  D3_REQUIRE(p->stride == 1 || (p->stride == 2 && p->ksize == 3), "conv: unsupported stride %d", p->stride);
+  D3_REQUIRE(p->Cin > 0 && p->Cin % 64 == 0, "conv: Cin must be a multiple of 64 (got %d)", p->Cin);
+  D3_REQUIRE(p->Cout > 0 && p->Cout % 128 == 0, "conv: Cout must be a multiple of 128 (got %d)", p->Cout);
+  D3_REQUIRE(p->C1 % 64 == 0 && p->C2 % 64 == 0, "conv: shortcut channels must be multiples of 64");
+  D3_REQUIRE(p->x_pitch % 8 == 0 && p->out_pitch % 8 == 0, "conv: pitches must be multiples of 8");
+  D3_REQUIRE(p->x && p->w && p->out && p->bias, "conv: null pointer");
+  if (p->stride == 2) {
+    D3_REQUIRE(p->H % 2 == 0 && p->W % 2 == 0, "conv: stride 2 needs even H, W");
+    D3_REQUIRE(p->C1 == 0 && p->C2 == 0, "conv: stride 2 with shortcut not supported");
+  }
+  const int Ho = p->H / p->stride, Wo = p->W / p->stride;
+  const int taps = p->ksize * p->ksize;
+  const int Ktot = taps * p->Cin + p->C1 + p->C2;
+
+  ConvKArgs a{};
+  a.B = p->B;
+  a.Ho = Ho;
+  a.Wo = Wo;
+  a.Cout = p->Cout;
+  choose_tile(Ho, Wo, &a.TH, &a.TW);
+  a.tilesH = ceil_div(Ho, a.TH);
+  a.tilesW = ceil_div(Wo, a.TW);
+  const int pixTiles = p->B * a.tilesH * a.tilesW;
+  int BN = (p->Cout % 256 == 0) ? 256 : 128;
+  if (BN == 256 && pixTiles * (p->Cout / 256) < num_sms()) BN = 128;  // more CTAs for tiny layers
+  a.nTilesN = p->Cout / BN;
+  a.numTiles = pixTiles * a.nTilesN;
+  a.ksize = p->ksize;
+  a.stride = p->stride;
+  a.pad = p->ksize / 2;
+  a.Cin = p->Cin;
+  a.cbMain = p->Cin / 64;
+  a.kbMain = taps * a.cbMain;
+  a.kbSc1 = p->sc1 ? p->C1 / 64 : 0;
+  a.kbSc2 = p->sc2 ? p->C2 / 64 : 0;
+  a.kbTotal = a.kbMain + a.kbSc1 + a.kbSc2;
+  a.sc_off2 = p->x_pitch;
+  a.bias = p->bias;
+  a.bias_bstride = p->bias_bstride;
+  a.residual = static_cast<const __nv_bfloat16*>(p->residual);
+  a.res_pitch = p->res_pitch;
+  a.stats = p->stats;
+  a.a_bytes = static_cast<uint32_t>(a.TH * a.TW * 128);
+  D3_REQUIRE((p->sc1 ? p->C1 : 0) + (p->sc2 ? p->C2 : 0) == p->C1 + p->C2, "conv: C1/C2 set without pointers");
+
+  CUtensorMap tmA, tmS1, tmS2, tmB, tmO;
+  int rc = 0;
+  if (p->stride == 1) {
+    uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
+    uint64_t str[3] = {(uint64_t)p->x_pitch * 2, (uint64_t)p->W * p->x_pitch * 2,
+                       (uint64_t)p->H * p->W * p->x_pitch * 2};
+    uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
+    rc = make_tmap_bf16(&tmA, p->x, 4, dims, str, box);
+  } else {
+    // parity-split view: (pw*pitch + c, w/2, h parity, h/2, b)
+    uint64_t dims[5] = {(uint64_t)p->x_pitch + p->Cin, (uint64_t)p->W / 2, 2, (uint64_t)p->H / 2, (uint64_t)p->B};
+    uint64_t str[4] = {(uint64_t)p->x_pitch * 4, (uint64_t)p->W * p->x_pitch * 2,
+                       (uint64_t)p->W * p->x_pitch * 4, (uint64_t)p->H * p->W * p->x_pitch * 2};
+    uint32_t box[5] = {64, (uint32_t)a.TW, 1, (uint32_t)a.TH, 1};
+    rc = make_tmap_bf16(&tmA, p->x, 5, dims, str, box);
+  }
+  if (rc) return set_error(D3_ERR_CUDA, "conv: tensor map A encode failed (%d)", rc);
+  tmS1 = tmA;
+  tmS2 = tmA;
+  if (a.kbSc1) {
+    uint64_t dims[4] = {(uint64_t)p->C1, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)p->B};
+    uint64_t str[3] = {(uint64_t)p->sc1_pitch * 2, (uint64_t)Wo * p->sc1_pitch * 2,
+                       (uint64_t)Ho * Wo * p->sc1_pitch * 2};
+    uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
+    if ((rc = make_tmap_bf16(&tmS1, p->sc1, 4, dims, str, box)))
+      return set_error(D3_ERR_CUDA, "conv: tensor map S1 encode failed (%d)", rc);
+  }
+  if (a.kbSc2) {
+    uint64_t dims[4] = {(uint64_t)p->C2, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)p->B};
+    uint64_t str[3] = {(uint64_t)p->sc2_pitch * 2, (uint64_t)Wo * p->sc2_pitch * 2,
+                       (uint64_t)Ho * Wo * p->sc2_pitch * 2};
+    uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
+    if ((rc = make_tmap_bf16(&tmS2, p->sc2, 4, dims, str, box)))
+      return set_error(D3_ERR_CUDA, "conv: tensor map S2 encode failed (%d)", rc);
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)p->Cout};
+    uint64_t str[1] = {(uint64_t)Ktot * 2};
+    uint32_t box[2] = {64, (uint32_t)BN};
+    if ((rc = make_tmap_bf16(&tmB, p->w, 2, dims, str, box)))
+      return set_error(D3_ERR_CUDA, "conv: tensor map B encode failed (%d)", rc);
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)p->Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)p->B};
+    uint64_t str[3] = {(uint64_t)p->out_pitch * 2, (uint64_t)Wo * p->out_pitch * 2,
+                       (uint64_t)Ho * Wo * p->out_pitch * 2};
+    uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
+    if ((rc = make_tmap_bf16(&tmO, p->out, 4, dims, str, box)))
+      return set_error(D3_ERR_CUDA, "conv: tensor map O encode failed (%d)", rc);
+  }
+
+  const int grid = a.numTiles < num_sms() ? a.numTiles : num_sms();
+  if (BN == 128) {
+    constexpr int S = 5;
+    constexpr size_t smem = conv_smem_bytes<128, S>();
+    static bool attr_set = false;
+    if (!attr_set) {
+      D3_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<128, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+      attr_set = true;
+    }
+    conv_igemm_kernel<128, S><<<grid, kThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, a);
+  } else {
+    constexpr int S = 4;
+    constexpr size_t smem = conv_smem_bytes<256, S>();
+    static bool attr_set = false;
+    if (!attr_set) {
+      D3_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<256, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+      attr_set = true;
+    }
+    conv_igemm_kernel<256, S><<<grid, kThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, a);
+  }
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}

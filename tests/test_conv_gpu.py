@@ -1,0 +1,65 @@
+"""Parity of the tcgen05 implicit-GEMM conv (d3_conv2d_igemm) against a plain PyTorch fp32 conv2d
+evaluated on the same bf16-rounded operands (floating-point kernel -> torch fp32 reference)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # B, H, W, Cin, Cout, k, stride, C1, C2, residual
+    (1, 16, 128, 64, 128, 3, 1, 0, 0, False),
+    (2, 24, 40, 128, 128, 3, 1, 0, 0, True),      # TW=40,TH=3 tile, identity residual
+    (1, 12, 20, 512, 512, 3, 1, 0, 0, True),      # tiny map, N tiles
+    (2, 48, 80, 256, 256, 3, 1, 0, 0, False),     # BN=256
+    (1, 96, 160, 384, 256, 3, 1, 256, 128, False),  # virtual-concat 1x1 shortcut folded in
+    (2, 32, 64, 128, 128, 3, 2, 0, 0, False),     # stride-2 downsample
+    (1, 34, 60, 256, 256, 3, 2, 0, 0, False),     # stride-2, ragged tiles (544x960 family)
+    (2, 24, 40, 512, 1536, 1, 1, 0, 0, False),    # 1x1 (attention QKV linear)
+    (1, 17, 30, 512, 512, 1, 1, 0, 0, True),      # 1x1 + residual (attention out-proj), odd sizes
+    (1, 384, 640, 128, 128, 3, 1, 0, 0, False),   # the dominant shape
+]
+
+
+def _ref(x, w, b, stride, sc, wsc, res):
+    xf = x.float().permute(0, 3, 1, 2)
+    k = w.shape[-1]
+    y = F.conv2d(xf, w.float(), b, stride=stride, padding=k // 2)
+    if sc is not None:
+        y = y + F.conv2d(sc.float().permute(0, 3, 1, 2), wsc.float()[:, :, None, None])
+    if res is not None:
+        y = y + res.float().permute(0, 3, 1, 2)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_conv_igemm_matches_torch(case):
+    from d3roma_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, H, W, Cin, Cout, k, stride, C1, C2, use_res = case
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    dev = "cuda"
+    x = torch.randn(B, H, W, Cin, device=dev, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, k, k, device=dev, generator=g) / (Cin * k * k) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(B, Cout, device=dev, generator=g)
+    Ho, Wo = H // stride, W // stride
+    sc1 = sc2 = sc = wsc = None
+    if C1:
+        sc1 = torch.randn(B, Ho, Wo, C1, device=dev, generator=g).to(torch.bfloat16)
+        sc2 = torch.randn(B, Ho, Wo, C2, device=dev, generator=g).to(torch.bfloat16)
+        sc = torch.cat([sc1, sc2], dim=3)
+        wsc = (torch.randn(Cout, C1 + C2, device=dev, generator=g) / (C1 + C2) ** 0.5).to(torch.bfloat16)
+    res = torch.randn(B, Ho, Wo, Cout, device=dev, generator=g).to(torch.bfloat16) if use_res else None
+    wp = ops.pack_conv_weight(w, wsc)
+    stats = torch.zeros(B, Cout // 4, 2, dtype=torch.float64, device=dev)
+    out = ops.conv2d_igemm(x, wp, bias, ksize=k, stride=stride, sc1=sc1, sc2=sc2, residual=res, stats=stats)
+    torch.cuda.synchronize()
+    ref = _ref(x, w, None, stride, sc, wsc, res) + bias[:, None, None, :]
+    err = (out.float() - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 2e-2
+    assert bool((err <= tol).all()), f"max err {err.max().item():.4g} (ref max {ref.abs().max().item():.3g})"
+    # statistics are those of the stored (rounded) output
+    o = out.double().reshape(B, Ho * Wo, Cout // 4, 4)
+    s_ref = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
+    torch.testing.assert_close(stats, s_ref, rtol=1e-5, atol=1e-3)
