@@ -1,0 +1,298 @@
+"""ORACLE tooling: generate the golden vectors under ``tests/golden/`` by running the REFERENCE's own
+Python (``/root/reference/core/*.py`` and ``utils_d3roma/*.py``, imported unmodified behind
+``oracle/diffusers_stub.py``) in this container.  The reference tree does not exist on the GPU box,
+so the vectors are committed as small ``.npz`` fixtures; this script is what made them.
+
+    python oracle/gen_golden.py            # rewrites tests/golden/*.npz
+
+What is pinned:
+  * ddim.npz / ddpm.npz   - ``MyDDIMScheduler`` / ``MyDDPMScheduler`` tables, timesteps and full multi-step
+                            trajectories of ``step()`` for every prediction type / spacing / variance type used
+                            (core/scheduler_ddim.py:346-498, core/scheduler_ddpm.py:403-526), plus ``add_noise`` /
+                            ``get_velocity``.
+  * prepost.npz           - ``Normalizer.normalize/denormalize`` (utils_d3roma/utils.py:171-273),
+                            ``InputPadder.pad/unpad`` (:297-325), ``normalize_disp/unnormalize_disp`` known
+                            answers (utils_d3roma/camera.py:1027-1044) and the sim camera scalars
+                            (``Realsense.default_sim``: fxb, min_disp, max_disp).
+  * guidance.npz          - the stereo photometric-guidance gradient: the arithmetic of
+                            ``FlowGuidance.grad`` (core/guidance.py:298-323) evaluated with the reference's own
+                            ``SSIM`` module, ``camera.unnormalize_disp`` and autograd (the function as written
+                            cannot return - SURVEY §0.4 - so its body is replayed line by line here).
+  * pipeline.npz          - ``GuidedDiffusionPipeline.__call__`` (core/custom_pipelines.py:97-205) driving the
+                            restated UNet (oracle/unet_ref.py, seed 0) on a small seeded input: per-step model
+                            outputs and the returned ``images`` for DDIM-10 and DDPM-8.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = Path(__file__).resolve().parents[1]
+REF = Path("/root/reference")
+sys.path.insert(0, str(ROOT))
+from oracle import diffusers_stub  # noqa: E402
+
+diffusers_stub.install()
+sys.path.insert(0, str(REF))
+
+from core.scheduler_ddim import MyDDIMScheduler  # noqa: E402
+from core.scheduler_ddpm import MyDDPMScheduler  # noqa: E402
+from core.custom_pipelines import GuidedDiffusionPipeline  # noqa: E402
+from core.guidance import SSIM, FlowGuidance  # noqa: E402
+from utils_d3roma.utils import InputPadder, Normalizer  # noqa: E402
+from utils_d3roma import camera as ref_camera  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+
+DDIM_CONFIGS = {
+    # the BASELINE / SURVEY C.1 configuration (conf/task/train_sceneflow.yaml + config.py:204-208)
+    "cos128_sample": dict(num_train_timesteps=128, beta_schedule="squaredcos_cap_v2", prediction_type="sample",
+                          clip_sample=True, set_alpha_to_one=False, steps_offset=1),
+    "cos128_epsilon": dict(num_train_timesteps=128, beta_schedule="squaredcos_cap_v2", prediction_type="epsilon",
+                           clip_sample=True, set_alpha_to_one=False, steps_offset=1),
+    "cos128_v": dict(num_train_timesteps=128, beta_schedule="squaredcos_cap_v2", prediction_type="v_prediction",
+                     clip_sample=True, set_alpha_to_one=False, steps_offset=1),
+    "cos128_sample_thresh": dict(num_train_timesteps=128, beta_schedule="squaredcos_cap_v2",
+                                 prediction_type="sample", thresholding=True, set_alpha_to_one=False,
+                                 steps_offset=1),
+    # LDM family constants
+    "sl1000_epsilon": dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012,
+                           beta_schedule="scaled_linear", prediction_type="epsilon", clip_sample=False,
+                           set_alpha_to_one=False, steps_offset=1),
+    "lin1000_v_trailing": dict(num_train_timesteps=1000, beta_schedule="linear", prediction_type="v_prediction",
+                               clip_sample=True, set_alpha_to_one=True, timestep_spacing="trailing"),
+    "lin1000_eps_linspace": dict(num_train_timesteps=1000, beta_schedule="linear", prediction_type="epsilon",
+                                 clip_sample=True, clip_sample_range=0.8, timestep_spacing="linspace"),
+}
+
+DDPM_CONFIGS = {
+    "cos128_sample_thresh": dict(num_train_timesteps=128, beta_schedule="squaredcos_cap_v2",
+                                 prediction_type="sample", thresholding=True, clip_sample=True),
+    "cos128_epsilon": dict(num_train_timesteps=128, beta_schedule="squaredcos_cap_v2", prediction_type="epsilon",
+                           clip_sample=True),
+    "cos128_v_log": dict(num_train_timesteps=128, beta_schedule="squaredcos_cap_v2", prediction_type="v_prediction",
+                         clip_sample=True, variance_type="fixed_small_log"),
+    "lin1000_eps_large": dict(num_train_timesteps=1000, beta_schedule="linear", prediction_type="epsilon",
+                              clip_sample=False, variance_type="fixed_large"),
+    "sig200_sample": dict(num_train_timesteps=200, beta_schedule="sigmoid", prediction_type="sample",
+                          clip_sample=True),
+}
+
+
+def _np(t):
+    return t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+
+
+def gen_ddim(store):
+    shape = (2, 1, 4, 6)
+    for name, cfg in DDIM_CONFIGS.items():
+        for n_steps, eta in ((10, 0.0), (8, 0.5)):
+            sch = MyDDIMScheduler.from_config(cfg)
+            sch.set_timesteps(n_steps)
+            g = torch.Generator().manual_seed(7)
+            x = torch.randn(shape, generator=g) * 1.3
+            key = f"{name}/n{n_steps}_eta{eta}"
+            store[f"{key}/timesteps"] = _np(sch.timesteps)
+            store[f"{key}/alphas_cumprod"] = _np(sch.alphas_cumprod)
+            store[f"{key}/final_alpha_cumprod"] = _np(sch.final_alpha_cumprod)
+            store[f"{key}/x0"] = _np(x)
+            for i, t in enumerate(sch.timesteps):
+                m = torch.randn(shape, generator=g) * 0.9
+                noise = torch.randn(shape, generator=g) if eta > 0 else None
+                out = sch.step(m, t, x, eta=eta, variance_noise=noise)
+                store[f"{key}/m{i}"] = _np(m)
+                if noise is not None:
+                    store[f"{key}/noise{i}"] = _np(noise)
+                store[f"{key}/prev{i}"] = _np(out.prev_sample)
+                store[f"{key}/orig{i}"] = _np(out.pred_original_sample)
+                x = out.prev_sample
+        # add_noise / get_velocity
+        sch = MyDDIMScheduler.from_config(cfg)
+        g = torch.Generator().manual_seed(11)
+        a, b = torch.randn(3, 1, 4, 6, generator=g), torch.randn(3, 1, 4, 6, generator=g)
+        ts = torch.tensor([0, sch.config.num_train_timesteps // 2, sch.config.num_train_timesteps - 1])
+        store[f"{name}/an_a"], store[f"{name}/an_b"], store[f"{name}/an_t"] = _np(a), _np(b), _np(ts)
+        store[f"{name}/add_noise"] = _np(sch.add_noise(a, b, ts))
+        store[f"{name}/velocity"] = _np(sch.get_velocity(a, b, ts))
+
+
+def gen_ddpm(store):
+    shape = (2, 1, 4, 6)
+    for name, cfg in DDPM_CONFIGS.items():
+        for n_steps in (8, 100):
+            sch = MyDDPMScheduler.from_config(cfg)
+            sch.set_timesteps(n_steps)
+            g = torch.Generator().manual_seed(5)
+            x = torch.randn(shape, generator=g) * 1.2
+            key = f"{name}/n{n_steps}"
+            store[f"{key}/timesteps"] = _np(sch.timesteps)
+            store[f"{key}/x0"] = _np(x)
+            steps = list(enumerate(sch.timesteps))
+            if n_steps == 100:
+                steps = steps[:4] + steps[-3:]
+            store[f"{key}/step_ids"] = np.array([i for i, _ in steps])
+            for i, t in steps:
+                m = torch.randn(shape, generator=g) * 0.8
+                out = sch.step(m, t, x, generator=torch.Generator().manual_seed(1000 + i))
+                store[f"{key}/m{i}"] = _np(m)
+                store[f"{key}/x{i}"] = _np(x)
+                store[f"{key}/prev{i}"] = _np(out.prev_sample)
+                store[f"{key}/orig{i}"] = _np(out.pred_original_sample)
+                store[f"{key}/mean{i}"] = _np(out.images_pred_prev)
+                x = out.prev_sample
+        sch = MyDDPMScheduler.from_config(cfg)
+        store[f"{name}/betas"] = _np(sch.betas)
+        store[f"{name}/alphas_cumprod"] = _np(sch.alphas_cumprod)
+        store[f"{name}/posterior_variance"] = _np(sch.posterior_variance)
+        g = torch.Generator().manual_seed(13)
+        a, b = torch.randn(3, 1, 4, 6, generator=g), torch.randn(3, 1, 4, 6, generator=g)
+        ts = torch.tensor([0, sch.config.num_train_timesteps // 2, sch.config.num_train_timesteps - 1])
+        store[f"{name}/an_a"], store[f"{name}/an_b"], store[f"{name}/an_t"] = _np(a), _np(b), _np(ts)
+        store[f"{name}/add_noise"] = _np(sch.add_noise(a, b, ts))
+        store[f"{name}/velocity"] = _np(sch.get_velocity(a, b, ts))
+        pm, _ = sch.posterior_mean_variance(a, b, ts)
+        store[f"{name}/posterior_mean"] = _np(pm)
+
+
+def gen_prepost(store):
+    g = torch.Generator().manual_seed(3)
+    disp = torch.rand(1, 20, 36, generator=g) * 150.0  # some values above the 128 bound -> clamp path
+    disp[0, :3, :5] = 0.0
+    for tag, kw in (("avg1", dict(ssi=False, mode="average", num_chs=1, ch_bounds=[128.], ch_gammas=[1.], t=0.5, s=2.)),
+                    ("avg3", dict(ssi=False, mode="average", num_chs=3, ch_bounds=[128.], ch_gammas=[1.], t=0.5, s=2.)),
+                    ("avg1g", dict(ssi=False, mode="average", num_chs=1, ch_bounds=[64.], ch_gammas=[0.5], t=0.5, s=2.))):
+        n = Normalizer(**kw)
+        y = n.normalize(disp.clone())[0]
+        store[f"norm/{tag}/in"] = _np(disp)
+        store[f"norm/{tag}/out"] = _np(y)
+        pred = (torch.rand(2, 2 * kw["num_chs"], 20, 36, generator=g) * 2 - 1)
+        store[f"norm/{tag}/den_in"] = _np(pred)
+        store[f"norm/{tag}/den_out"] = _np(n.denormalize(pred.clone()))
+    for hw in ((360, 640), (540, 960), (37, 50), (64, 96)):
+        x = torch.randn(2, 3, *hw, generator=g)
+        p = InputPadder(x.shape, divis_by=32)
+        y = p.pad(x)[0]
+        store[f"pad/{hw[0]}x{hw[1]}/pad"] = np.array(p._pad)
+        if hw[0] < 100:
+            store[f"pad/{hw[0]}x{hw[1]}/in"] = _np(x)
+            store[f"pad/{hw[0]}x{hw[1]}/out"] = _np(y)
+        assert torch.equal(p.unpad(y), x)
+        store[f"pad/{hw[0]}x{hw[1]}/shape"] = np.array(y.shape)
+    # known answers asserted by the reference's own __main__ (utils_d3roma/camera.py:1027-1044)
+    ka_in = [(20, 20, 120, 0), (120, 20, 120, 0), (30, 20, 120, 0), (70, 20, 120, 0), (0, 20, 120, 0),
+             (20, 20, 120, 0.2), (0, 20, 120, 0.2), (120, 20, 120, 0.2)]
+    store["camera/normalize_in"] = np.array(ka_in, dtype=np.float64)
+    store["camera/normalize_out"] = np.array([ref_camera.normalize_disp(d, a, b, s) for d, a, b, s in ka_in])
+    ku_in = [(0, 20, 120, 0), (1, 20, 120, 0), (0.5, 20, 120, 0), (0.2, 20, 120, 0.2), (1.2, 20, 120, 0.2),
+             (0.7, 20, 120, 0.2)]
+    store["camera/unnormalize_in"] = np.array(ku_in, dtype=np.float64)
+    store["camera/unnormalize_out"] = np.array([ref_camera.unnormalize_disp(d, a, b, s) for d, a, b, s in ku_in])
+    cam = ref_camera.Realsense.default_sim()
+    cam.change_resolution("640x360") if hasattr(cam, "change_resolution") else None
+    store["camera/sim"] = np.array([cam.fxb_depth, cam.min_disp, cam.max_disp, cam.config["shift"]], dtype=np.float64)
+    # depth <-> disparity (inference.py:128-131, 246-249)
+    depth = torch.rand(1, 20, 36, generator=g) * 2.0
+    depth[depth < 0.3] = 0.0
+    d2 = torch.zeros_like(depth)
+    v = depth > 0
+    d2[v] = float(cam.fxb_depth) / depth[v]
+    store["camera/depth_in"] = _np(depth)
+    store["camera/disp_out"] = _np(d2)
+
+
+def _guidance_grad_reference(fg, ssim, cam, disp_raw, left_images, right_images, use_ssim=True):
+    """core/guidance.py:298-323 replayed with the reference's own modules (the function cannot return)."""
+    disp_raw = disp_raw.squeeze(1).clone()
+    B, H, W = disp_raw.shape
+    device = disp_raw.device
+    with torch.enable_grad():
+        w = 0.95
+        disp_raw.requires_grad_(True)
+        disp = cam.unnormalize_disp(disp_raw)
+        margin_left = right_images.shape[-1] - W
+        xx, yy = torch.meshgrid(torch.arange(W), torch.arange(H), indexing='xy')
+        xx = xx[None, ...].repeat(B, 1, 1).to(device)
+        yy = yy[None, ...].repeat(B, 1, 1).to(device)
+        xx = (xx - disp + margin_left) / ((W + margin_left - 1) / 2.) - 1
+        yy = yy / ((H - 1) / 2.) - 1
+        grid = torch.stack([xx, yy], dim=-1)
+        warp_left_image = F.grid_sample(right_images, grid, align_corners=True, mode="bilinear",
+                                        padding_mode="border")
+        loss = F.l1_loss(left_images[..., margin_left:], warp_left_image, reduction='sum')
+        if use_ssim:
+            ssim_loss = ssim(left_images[..., margin_left:], warp_left_image).sum()
+            loss = w * ssim_loss + (1 - w) * loss
+        grads = torch.autograd.grad(loss, disp_raw)[0]
+    return grads.unsqueeze(1), warp_left_image.detach()
+
+
+def gen_guidance(store):
+    cam = ref_camera.Realsense.default_sim()
+    ssim = SSIM()
+    fg = FlowGuidance(flow_guidance_weight=1.0)
+    g = torch.Generator().manual_seed(21)
+    for tag, (B, H, W) in (("a", (2, 16, 72)), ("b", (1, 20, 96))):
+        left = torch.rand(B, 3, H, W, generator=g) * 2 - 1
+        right = torch.rand(B, 3, H, W, generator=g) * 2 - 1
+        # smooth-ish images so that SSIM is not saturated everywhere
+        left = F.avg_pool2d(F.pad(left, (1, 1, 1, 1), mode="replicate"), 3, 1)
+        right = F.avg_pool2d(F.pad(right, (1, 1, 1, 1), mode="replicate"), 3, 1)
+        dn = torch.rand(B, 1, H, W, generator=g) * 0.2 - 0.03  # normalised disparity, some below 0 (clip)
+        grad, warp = _guidance_grad_reference(fg, ssim, cam, dn, left, right)
+        store[f"{tag}/left"], store[f"{tag}/right"], store[f"{tag}/disp"] = _np(left), _np(right), _np(dn)
+        store[f"{tag}/grad"], store[f"{tag}/warp"] = _np(grad), _np(warp)
+    store["cam"] = np.array([cam.min_disp, cam.max_disp, cam.config["shift"]], dtype=np.float64)
+
+
+def gen_pipeline(store):
+    from oracle.unet_ref import make_unet
+    H, W = 32, 64
+    g = torch.Generator().manual_seed(1234)
+    left = torch.rand(1, 3, H, W, generator=g) * 2 - 1
+    right = torch.rand(1, 3, H, W, generator=g) * 2 - 1
+    raw = torch.rand(1, 1, H, W, generator=g) * 2 - 1
+    store["left"], store["right"], store["raw"] = _np(left), _np(right), _np(raw)
+    unet = make_unet(8, 1, seed=0, sample_size=(H, W))
+
+    class Rec(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m, self.outs, self.sample_size = m, [], m.sample_size
+
+        def forward(self, x, t):
+            o = self.m(x, t)
+            self.outs.append(o.sample.clone())
+            return o
+
+    for tag, sch, n in (
+            ("ddim10", MyDDIMScheduler.from_config(DDIM_CONFIGS["cos128_sample"]), 10),
+            ("ddpm8", MyDDPMScheduler.from_config(DDPM_CONFIGS["cos128_sample_thresh"]), 8)):
+        rec = Rec(unet)
+        pipe = GuidedDiffusionPipeline(rec, sch, FlowGuidance(flow_guidance_weight=0.0))
+        torch.manual_seed(99)  # DDPM variance noise comes from the default generator
+        out = pipe(None, left, right, raw, None, None, num_inference_steps=n, num_intermediate_images=2,
+                   depth_channels=1, cond_channels="left+right+raw",
+                   generator=torch.Generator().manual_seed(42))
+        store[f"{tag}/images"] = _np(out.images)
+        store[f"{tag}/intermediate"] = _np(out.images_pred_orig)
+        store[f"{tag}/model_outputs"] = np.stack([_np(o) for o in rec.outs])
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(8)
+    for name, fn in (("ddim", gen_ddim), ("ddpm", gen_ddpm), ("prepost", gen_prepost), ("guidance", gen_guidance),
+                     ("pipeline", gen_pipeline)):
+        store = {}
+        with torch.no_grad():
+            fn(store)
+        np.savez_compressed(OUT / f"{name}.npz", **store)
+        print(f"{name}.npz: {len(store)} arrays, {(OUT / (name + '.npz')).stat().st_size / 1024:.1f} KiB")
+
+
+if __name__ == "__main__":
+    main()
