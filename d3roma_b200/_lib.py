@@ -15,6 +15,10 @@ class D3Error(RuntimeError):
     pass
 
 
+DTYPE_BF16 = 0
+DTYPE_F16 = 1
+
+
 class ConvParams(C.Structure):
     """Mirror of ``d3_conv_params`` (include/d3roma_b200.h)."""
 
@@ -31,6 +35,30 @@ class ConvParams(C.Structure):
         ("residual", C.c_void_p), ("res_pitch", C.c_int32),
         ("out", C.c_void_p), ("out_pitch", C.c_int32),
         ("stats", C.c_void_p),
+        ("dtype", C.c_int32),
+    ]
+
+
+class DDIMCoeffs(C.Structure):
+    """Mirror of ``d3_ddim_coeffs``."""
+
+    _fields_ = [
+        ("prediction_type", C.c_int32),
+        ("sqrt_alpha_t", C.c_float), ("sqrt_beta_t", C.c_float), ("sqrt_alpha_prev", C.c_float),
+        ("dir_coeff", C.c_float), ("std_dev", C.c_float),
+        ("clip_mode", C.c_int32), ("clip_range", C.c_float),
+        ("use_clipped_model_output", C.c_int32),
+    ]
+
+
+class DDPMCoeffs(C.Structure):
+    """Mirror of ``d3_ddpm_coeffs``."""
+
+    _fields_ = [
+        ("prediction_type", C.c_int32),
+        ("sqrt_alpha_t", C.c_float), ("sqrt_beta_t", C.c_float),
+        ("x0_coeff", C.c_float), ("xt_coeff", C.c_float), ("sigma", C.c_float),
+        ("clip_mode", C.c_int32), ("clip_range", C.c_float),
     ]
 
 
@@ -45,11 +73,20 @@ def _declare(lib: C.CDLL) -> None:
         "d3_launch_count": (i64, []),
         "d3_reset_launch_count": (None, []),
         "d3_conv2d_igemm": (i32, [C.POINTER(ConvParams), vp]),
+        "d3_groupnorm_silu": (i32, [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, f32, i32, vp, i32, i32,
+                                    vp]),
+        "d3_upsample_nearest2x": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
+        "d3_im2col_input": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, i32, vp]),
+        "d3_conv_out_fused": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, i32, vp]),
+        "d3_time_embed": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),
+        "d3_temb_project_all": (i32, [vp, i32, vp, vp, i32, vp, vp]),
+        "d3_attention_hd8": (i32, [vp, i32, i32, i32, i32, vp, i32, i32, vp]),
+        "d3_sched_ddim_step": (i32, [vp, vp, vp, C.POINTER(DDIMCoeffs), i64, vp, vp, vp, vp, vp]),
+        "d3_sched_ddpm_step": (i32, [vp, vp, vp, C.POINTER(DDPMCoeffs), i64, vp, vp, vp, vp]),
+        "d3_lincomb": (i32, [f32, vp, f32, vp, f32, vp, i64, vp, vp]),
     }
     for name, (res, args) in sigs.items():
-        if not hasattr(lib, name):
-            continue
-        fn = getattr(lib, name)
+        fn = getattr(lib, name)  # AttributeError here == header and library out of sync
         fn.restype = res
         fn.argtypes = args
 

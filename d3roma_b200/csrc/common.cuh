@@ -8,6 +8,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -185,11 +186,11 @@ D3_DEVINL uint64_t make_sw128_kmajor_desc(uint32_t saddr) {
   return d;
 }
 
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
-  return (1u << 4)              // D format  = F32
-         | (1u << 7)            // A format  = BF16
-         | (1u << 10)           // B format  = BF16
+// kind::f16 instruction descriptor: bf16 x bf16 (or f16 x f16) -> fp32, both operands K-major, M x N tile.
+__host__ __device__ constexpr uint32_t make_idesc_16bit(uint32_t M, uint32_t N, bool bf16) {
+  return (1u << 4)                       // D format  = F32
+         | ((bf16 ? 1u : 0u) << 7)       // A format  = BF16 (1) / F16 (0)
+         | ((bf16 ? 1u : 0u) << 10)      // B format
          | (0u << 15)           // A K-major
          | (0u << 16)           // B K-major
          | ((N >> 3) << 17)     // N / 8
@@ -201,13 +202,29 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
 // ----------------------------------------------------------------------------------------
 D3_DEVINL float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
-D3_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+// 16-bit activation storage type: DT = 0 -> bf16, DT = 1 -> fp16 (same tensor-core rate, 3 more mantissa bits).
+constexpr int kBF16 = 0;
+constexpr int kF16 = 1;
+
+template <int DT>
+D3_DEVINL uint32_t pack2(float lo, float hi) {
+  if constexpr (DT == kBF16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
 }
-D3_DEVINL float2 unpack_bf16x2(uint32_t u) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(v);
+template <int DT>
+D3_DEVINL float2 unpack2(uint32_t u) {
+  if constexpr (DT == kBF16) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+    return __bfloat1622float2(v);
+  } else {
+    __half2 v = *reinterpret_cast<__half2*>(&u);
+    return __half22float2(v);
+  }
 }
 
 }  // namespace d3

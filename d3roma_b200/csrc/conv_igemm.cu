@@ -38,7 +38,7 @@ struct ConvKArgs {
   int sc_off2;  // channel offset of the second half-res parity plane (stride 2 only): x_pitch
   const float* bias;
   int bias_bstride;
-  const __nv_bfloat16* residual;
+  const uint16_t* residual;
   int res_pitch;
   double* stats;
   uint32_t a_bytes;
@@ -81,7 +81,7 @@ D3_DEVINL float warp_transpose_reduce32(float (&v)[32], uint32_t lane) {
 
 // Epilogue math for 32 accumulator columns (half of a 64-channel chunk): + bias (+ residual), round to bf16,
 // write the swizzled staging row, and collect per-quad sum / sum-of-squares of the rounded values.
-template <int HALF>
+template <int HALF, int DT>
 D3_DEVINL void epi_process32(const uint32_t (&v)[32], float (&sums)[32], const float4* bp, const uint4* rp,
                              bool valid, uint8_t* sbuf, uint32_t r) {
 #pragma unroll
@@ -100,19 +100,19 @@ D3_DEVINL void epi_process32(const uint32_t (&v)[32], float (&sums)[32], const f
     if (rp != nullptr) {
       const uint4 rv = __ldg(rp + j8);
       float2 f;
-      f = unpack_bf16x2(rv.x); x[0] += f.x; x[1] += f.y;
-      f = unpack_bf16x2(rv.y); x[2] += f.x; x[3] += f.y;
-      f = unpack_bf16x2(rv.z); x[4] += f.x; x[5] += f.y;
-      f = unpack_bf16x2(rv.w); x[6] += f.x; x[7] += f.y;
+      f = unpack2<DT>(rv.x); x[0] += f.x; x[1] += f.y;
+      f = unpack2<DT>(rv.y); x[2] += f.x; x[3] += f.y;
+      f = unpack2<DT>(rv.z); x[4] += f.x; x[5] += f.y;
+      f = unpack2<DT>(rv.w); x[6] += f.x; x[7] += f.y;
     }
     uint4 pk;
-    pk.x = pack_bf16x2(x[0], x[1]);
-    pk.y = pack_bf16x2(x[2], x[3]);
-    pk.z = pack_bf16x2(x[4], x[5]);
-    pk.w = pack_bf16x2(x[6], x[7]);
+    pk.x = pack2<DT>(x[0], x[1]);
+    pk.y = pack2<DT>(x[2], x[3]);
+    pk.z = pack2<DT>(x[4], x[5]);
+    pk.w = pack2<DT>(x[6], x[7]);
     // statistics of the values as stored (bf16-rounded), masked to in-image pixels
-    const float2 f0 = unpack_bf16x2(pk.x), f1 = unpack_bf16x2(pk.y);
-    const float2 f2 = unpack_bf16x2(pk.z), f3 = unpack_bf16x2(pk.w);
+    const float2 f0 = unpack2<DT>(pk.x), f1 = unpack2<DT>(pk.y);
+    const float2 f2 = unpack2<DT>(pk.z), f3 = unpack2<DT>(pk.w);
     const float s0 = (f0.x + f0.y) + (f1.x + f1.y);
     const float q0 = (f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y);
     const float s1 = (f2.x + f2.y) + (f3.x + f3.y);
@@ -126,7 +126,7 @@ D3_DEVINL void epi_process32(const uint32_t (&v)[32], float (&sums)[32], const f
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int DT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS1,
                   const __grid_constant__ CUtensorMap tmS2, const __grid_constant__ CUtensorMap tmB,
@@ -217,7 +217,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN);
+      constexpr uint32_t idesc = make_idesc_16bit(kTileM, BN, DT == kBF16);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -291,8 +291,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                               n_base);
         }
         float sums[32];  // [0..15] quad sums, [16..31] quad sums of squares
-        epi_process32<0>(v0, sums, bp, rp, valid, sbuf, r);
-        epi_process32<1>(v1, sums, bp, rp, valid, sbuf, r);
+        epi_process32<0, DT>(v0, sums, bp, rp, valid, sbuf, r);
+        epi_process32<1, DT>(v1, sums, bp, rp, valid, sbuf, r);
         if (a.stats != nullptr) {
           const float tot = warp_transpose_reduce32(sums, lane);
           spart[q * 32 + lane] = tot;
@@ -327,6 +327,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 template <int BN, int STAGES>
 constexpr size_t conv_smem_bytes() {
   return 1024 + STAGES * (kATileBytes + BN * 128) + 2 * kStagingBytes + (2 * STAGES + 4) * 8 + 16 + 4 * 32 * 4;
+}
+
+template <int BN, int STAGES, int DT>
+cudaError_t launch_conv(int grid, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmS1,
+                        const CUtensorMap& tmS2, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvKArgs& a) {
+  constexpr size_t smem = conv_smem_bytes<BN, STAGES>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, DT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  conv_igemm_kernel<BN, STAGES, DT><<<grid, kThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, a);
+  return cudaSuccess;
 }
 
 // Pick the pixel tile TH x TW (TH*TW <= 128) that wastes the fewest MMA rows.
@@ -365,6 +380,7 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   D3_REQUIRE(p->C1 % 64 == 0 && p->C2 % 64 == 0, "conv: shortcut channels must be multiples of 64");
   D3_REQUIRE(p->x_pitch % 8 == 0 && p->out_pitch % 8 == 0, "conv: pitches must be multiples of 8");
   D3_REQUIRE(p->x && p->w && p->out && p->bias, "conv: null pointer");
+  D3_REQUIRE(p->dtype == D3_DTYPE_BF16 || p->dtype == D3_DTYPE_F16, "conv: bad dtype %d", p->dtype);
   if (p->stride == 2) {
     D3_REQUIRE(p->H % 2 == 0 && p->W % 2 == 0, "conv: stride 2 needs even H, W");
     D3_REQUIRE(p->C1 == 0 && p->C2 == 0, "conv: stride 2 with shortcut not supported");
@@ -398,7 +414,7 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   a.sc_off2 = p->x_pitch;
   a.bias = p->bias;
   a.bias_bstride = p->bias_bstride;
-  a.residual = static_cast<const __nv_bfloat16*>(p->residual);
+  a.residual = static_cast<const uint16_t*>(p->residual);
   a.res_pitch = p->res_pitch;
   a.stats = p->stats;
   a.a_bytes = static_cast<uint32_t>(a.TH * a.TW * 128);
@@ -411,14 +427,14 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
     uint64_t str[3] = {(uint64_t)p->x_pitch * 2, (uint64_t)p->W * p->x_pitch * 2,
                        (uint64_t)p->H * p->W * p->x_pitch * 2};
     uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
-    rc = make_tmap_bf16(&tmA, p->x, 4, dims, str, box);
+    rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmA, p->x, 4, dims, str, box);
   } else {
     // parity-split view: (pw*pitch + c, w/2, h parity, h/2, b)
     uint64_t dims[5] = {(uint64_t)p->x_pitch + p->Cin, (uint64_t)p->W / 2, 2, (uint64_t)p->H / 2, (uint64_t)p->B};
     uint64_t str[4] = {(uint64_t)p->x_pitch * 4, (uint64_t)p->W * p->x_pitch * 2,
                        (uint64_t)p->W * p->x_pitch * 4, (uint64_t)p->H * p->W * p->x_pitch * 2};
     uint32_t box[5] = {64, (uint32_t)a.TW, 1, (uint32_t)a.TH, 1};
-    rc = make_tmap_bf16(&tmA, p->x, 5, dims, str, box);
+    rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmA, p->x, 5, dims, str, box);
   }
   if (rc) return set_error(D3_ERR_CUDA, "conv: tensor map A encode failed (%d)", rc);
   tmS1 = tmA;
@@ -428,7 +444,7 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
     uint64_t str[3] = {(uint64_t)p->sc1_pitch * 2, (uint64_t)Wo * p->sc1_pitch * 2,
                        (uint64_t)Ho * Wo * p->sc1_pitch * 2};
     uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
-    if ((rc = make_tmap_bf16(&tmS1, p->sc1, 4, dims, str, box)))
+    if ((rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmS1, p->sc1, 4, dims, str, box)))
       return set_error(D3_ERR_CUDA, "conv: tensor map S1 encode failed (%d)", rc);
   }
   if (a.kbSc2) {
@@ -436,14 +452,14 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
     uint64_t str[3] = {(uint64_t)p->sc2_pitch * 2, (uint64_t)Wo * p->sc2_pitch * 2,
                        (uint64_t)Ho * Wo * p->sc2_pitch * 2};
     uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
-    if ((rc = make_tmap_bf16(&tmS2, p->sc2, 4, dims, str, box)))
+    if ((rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmS2, p->sc2, 4, dims, str, box)))
       return set_error(D3_ERR_CUDA, "conv: tensor map S2 encode failed (%d)", rc);
   }
   {
     uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)p->Cout};
     uint64_t str[1] = {(uint64_t)Ktot * 2};
     uint32_t box[2] = {64, (uint32_t)BN};
-    if ((rc = make_tmap_bf16(&tmB, p->w, 2, dims, str, box)))
+    if ((rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmB, p->w, 2, dims, str, box)))
       return set_error(D3_ERR_CUDA, "conv: tensor map B encode failed (%d)", rc);
   }
   {
@@ -451,32 +467,21 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
     uint64_t str[3] = {(uint64_t)p->out_pitch * 2, (uint64_t)Wo * p->out_pitch * 2,
                        (uint64_t)Ho * Wo * p->out_pitch * 2};
     uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
-    if ((rc = make_tmap_bf16(&tmO, p->out, 4, dims, str, box)))
+    if ((rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmO, p->out, 4, dims, str, box)))
       return set_error(D3_ERR_CUDA, "conv: tensor map O encode failed (%d)", rc);
   }
 
   const int grid = a.numTiles < num_sms() ? a.numTiles : num_sms();
-  if (BN == 128) {
-    constexpr int S = 5;
-    constexpr size_t smem = conv_smem_bytes<128, S>();
-    static bool attr_set = false;
-    if (!attr_set) {
-      D3_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<128, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
-      attr_set = true;
-    }
-    conv_igemm_kernel<128, S><<<grid, kThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, a);
-  } else {
-    constexpr int S = 4;
-    constexpr size_t smem = conv_smem_bytes<256, S>();
-    static bool attr_set = false;
-    if (!attr_set) {
-      D3_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<256, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
-      attr_set = true;
-    }
-    conv_igemm_kernel<256, S><<<grid, kThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, a);
-  }
+  cudaError_t le = cudaSuccess;
+  if (BN == 128 && p->dtype == D3_DTYPE_BF16)
+    le = launch_conv<128, 5, kBF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, a);
+  else if (BN == 128)
+    le = launch_conv<128, 5, kF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, a);
+  else if (p->dtype == D3_DTYPE_BF16)
+    le = launch_conv<256, 4, kBF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, a);
+  else
+    le = launch_conv<256, 4, kF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, a);
+  D3_CHECK_CUDA(le);
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

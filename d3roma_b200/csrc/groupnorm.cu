@@ -1,0 +1,215 @@
+// GroupNorm (32 groups) + optional SiLU, applied as one bandwidth-bound pass over bf16 NHWC activations.
+//
+// Replaces aten::native_group_norm (+ aten::silu) of every ResnetBlock2D.norm1/norm2, Attention.group_norm and
+// conv_norm_out (diffusers ResnetBlock2D built at /root/reference/train.py:788-810).
+//
+// Statistics are NOT computed here: every producer (the conv epilogue) accumulates, per sample, the sum and
+// sum-of-squares of each 4-channel "quad" of its bf16-rounded output in fp64 ([B][C/4][2]).  All group widths in
+// this UNet (4, 8, 12, 16, 24, 32 channels) are multiples of 4, and so are the split points of every skip
+// concatenation, so a group's moments are the sum of its quads' moments — including groups that straddle the two
+// source tensors of a virtual concat (C = 384 = 256 + 128, C = 768 = 512 + 256).  The kernel reads up
+// to two sources and writes ONE dense normalised tensor, i.e. the torch.cat of the up-blocks costs nothing extra.
+//
+// Algorithmic bytes: 2 * N * sizeof(bf16) per layer (one read, one write).
+#include "common.cuh"
+#include "internal.h"
+
+namespace d3 {
+namespace {
+
+constexpr int kGnThreads = 256;
+constexpr int kMaxC = 1024;
+
+struct GnArgs {
+  const uint16_t* x1;
+  const uint16_t* x2;
+  const double* st1;
+  const double* st2;
+  const float* gamma;
+  const float* beta;
+  uint16_t* out;
+  int C1, C2, p1, p2, pout;
+  int HW;        // pixels per sample
+  int groups;
+  float eps;
+  int silu;
+  int pix_per_block;
+};
+
+template <int DT>
+__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
+  __shared__ float s_scale[kMaxC];
+  __shared__ float s_shift[kMaxC];
+  __shared__ float s_mean[32];
+  __shared__ float s_rstd[32];
+  const int b = blockIdx.y;
+  const int C = a.C1 + a.C2;
+  const int cpg = C / a.groups;
+  const int qpg = cpg >> 2;
+  const int Q1 = a.C1 >> 2, Q2 = a.C2 >> 2;
+  if (threadIdx.x < a.groups) {
+    const int g = threadIdx.x;
+    double s = 0.0, ss = 0.0;
+    for (int i = 0; i < qpg; ++i) {
+      const int q = g * qpg + i;
+      const double* p = (q < Q1) ? (a.st1 + ((size_t)b * Q1 + q) * 2) : (a.st2 + ((size_t)b * Q2 + (q - Q1)) * 2);
+      s += p[0];
+      ss += p[1];
+    }
+    const double n = (double)a.HW * cpg;
+    const double mean = s / n;
+    double var = ss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = (float)mean;
+    s_rstd[g] = (float)(1.0 / sqrt(var + (double)a.eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kGnThreads) {
+    const int g = c / cpg;
+    const float sc = a.gamma[c] * s_rstd[g];
+    s_scale[c] = sc;
+    s_shift[c] = a.beta[c] - s_mean[g] * sc;
+  }
+  __syncthreads();
+
+  const int nvec = C >> 3;       // 16-byte vectors per pixel
+  const int nvec1 = a.C1 >> 3;
+  const int pix0 = blockIdx.x * a.pix_per_block;
+  int npix = a.HW - pix0;
+  if (npix > a.pix_per_block) npix = a.pix_per_block;
+  if (npix <= 0) return;
+  const int total = npix * nvec;
+  const size_t base_pix = (size_t)b * a.HW + pix0;
+
+  constexpr int U = 4;
+  for (int i0 = threadIdx.x; i0 < total; i0 += kGnThreads * U) {
+    uint4 v[U];
+    int pix[U], vec[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * kGnThreads;
+      if (i < total) {
+        pix[u] = i / nvec;
+        vec[u] = i - pix[u] * nvec;
+        const uint16_t* src = (vec[u] < nvec1)
+                                       ? a.x1 + (base_pix + pix[u]) * a.p1 + vec[u] * 8
+                                       : a.x2 + (base_pix + pix[u]) * a.p2 + (vec[u] - nvec1) * 8;
+        v[u] = __ldcs(reinterpret_cast<const uint4*>(src));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * kGnThreads;
+      if (i < total) {
+        const int c0 = vec[u] * 8;
+        const float4 sc0 = *reinterpret_cast<const float4*>(&s_scale[c0]);
+        const float4 sc1 = *reinterpret_cast<const float4*>(&s_scale[c0 + 4]);
+        const float4 sh0 = *reinterpret_cast<const float4*>(&s_shift[c0]);
+        const float4 sh1 = *reinterpret_cast<const float4*>(&s_shift[c0 + 4]);
+        float2 f0 = unpack2<DT>(v[u].x), f1 = unpack2<DT>(v[u].y);
+        float2 f2 = unpack2<DT>(v[u].z), f3 = unpack2<DT>(v[u].w);
+        float y[8];
+        y[0] = fmaf(f0.x, sc0.x, sh0.x);
+        y[1] = fmaf(f0.y, sc0.y, sh0.y);
+        y[2] = fmaf(f1.x, sc0.z, sh0.z);
+        y[3] = fmaf(f1.y, sc0.w, sh0.w);
+        y[4] = fmaf(f2.x, sc1.x, sh1.x);
+        y[5] = fmaf(f2.y, sc1.y, sh1.y);
+        y[6] = fmaf(f3.x, sc1.z, sh1.z);
+        y[7] = fmaf(f3.y, sc1.w, sh1.w);
+        if (a.silu) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) y[k] = silu_f(y[k]);
+        }
+        uint4 o;
+        o.x = pack2<DT>(y[0], y[1]);
+        o.y = pack2<DT>(y[2], y[3]);
+        o.z = pack2<DT>(y[4], y[5]);
+        o.w = pack2<DT>(y[6], y[7]);
+        *reinterpret_cast<uint4*>(a.out + (base_pix + pix[u]) * a.pout + c0) = o;
+      }
+    }
+  }
+}
+
+// out[b, h, w, :] = in[b, h/2, w/2, :]  (F.interpolate(scale_factor=2, mode="nearest") of Upsample2D)
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint16_t* __restrict__ in,
+                                                         uint16_t* __restrict__ out, int B, int H, int W, int C,
+                                                         int pin, int pout) {
+  const int nvec = C >> 3;
+  const size_t total = (size_t)B * H * W * nvec;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    size_t p = i / nvec;
+    const int w = (int)(p % W);
+    p /= W;
+    const int h = (int)(p % H);
+    const int b = (int)(p / H);
+    const uint4 val = __ldcs(reinterpret_cast<const uint4*>(in + (((size_t)b * H + h) * W + w) * pin + v * 8));
+    uint16_t* o = out + (((size_t)b * 2 * H + 2 * h) * (2 * W) + 2 * w) * pout + v * 8;
+    *reinterpret_cast<uint4*>(o) = val;
+    *reinterpret_cast<uint4*>(o + pout) = val;
+    *reinterpret_cast<uint4*>(o + (size_t)2 * W * pout) = val;
+    *reinterpret_cast<uint4*>(o + (size_t)2 * W * pout + pout) = val;
+  }
+}
+
+}  // namespace
+}  // namespace d3
+
+extern "C" int d3_groupnorm_silu(const void* x1, int C1, int p1, const double* stats1, const void* x2, int C2, int p2,
+                                 const double* stats2, const float* gamma, const float* beta, int B, int HW,
+                                 int groups, float eps, int apply_silu, void* out, int pout, int dtype, void* stream) {
+  using namespace d3;
+  const int C = C1 + C2;
+  D3_REQUIRE(x1 && stats1 && gamma && beta && out, "groupnorm: null pointer");
+  D3_REQUIRE(C2 == 0 || (x2 && stats2), "groupnorm: second source missing");
+  D3_REQUIRE(C <= kMaxC && C % groups == 0 && (C / groups) % 4 == 0 && groups <= 32,
+             "groupnorm: unsupported C=%d groups=%d", C, groups);
+  D3_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && p1 % 8 == 0 && (C2 == 0 || p2 % 8 == 0) && pout % 8 == 0,
+             "groupnorm: channel counts / pitches must be multiples of 8");
+  GnArgs a{};
+  a.x1 = static_cast<const uint16_t*>(x1);
+  a.x2 = static_cast<const uint16_t*>(x2);
+  a.st1 = stats1;
+  a.st2 = stats2;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.out = static_cast<uint16_t*>(out);
+  a.C1 = C1;
+  a.C2 = C2;
+  a.p1 = p1;
+  a.p2 = p2;
+  a.pout = pout;
+  a.HW = HW;
+  a.groups = groups;
+  a.eps = eps;
+  a.silu = apply_silu;
+  // aim for ~8 blocks per SM over the whole batch, but at least 32 KB of work per block
+  int blocks_per_sample = ceil_div(num_sms() * 8, B);
+  int ppb = ceil_div(HW, blocks_per_sample);
+  const int min_ppb = ceil_div(16384, C);
+  if (ppb < min_ppb) ppb = min_ppb;
+  a.pix_per_block = ppb;
+  dim3 grid(ceil_div(HW, ppb), B);
+  if (dtype == D3_DTYPE_F16)
+    gn_apply_kernel<kF16><<<grid, kGnThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  else
+    gn_apply_kernel<kBF16><<<grid, kGnThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
+extern "C" int d3_upsample_nearest2x(const void* in, int B, int H, int W, int C, int pin, void* out, int pout,
+                                     void* stream) {
+  using namespace d3;
+  D3_REQUIRE(in && out && C % 8 == 0 && pin % 8 == 0 && pout % 8 == 0, "upsample: bad arguments");
+  const size_t total = (size_t)B * H * W * (C / 8);
+  int blocks = (int)((total + 255) / 256);
+  const int cap = num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  upsample2x_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), B, H, W, C, pin, pout);
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}

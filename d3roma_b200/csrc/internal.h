@@ -34,6 +34,6 @@ int num_sms();
                              cudaGetErrorString(_e));                                         \
   } while (0)
 
-inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace d3

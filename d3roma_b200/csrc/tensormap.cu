@@ -18,7 +18,7 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+int make_tmap_16bit(bool f16, CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
                    const uint32_t* box, bool swizzle128) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return 100;
@@ -32,7 +32,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     estr[i] = 1;
     if (i > 0) gstr[i - 1] = strides_b[i - 1];
   }
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+  CUresult r = enc(out, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
                    gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

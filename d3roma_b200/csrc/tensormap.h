@@ -15,13 +15,13 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 PFN_encodeTiled get_encode_tiled();
 
-// Generic bf16 tiled map with 128B swizzle and zero OOB fill.
+// Generic 16-bit (bf16 / fp16) tiled map with 128B swizzle and zero OOB fill.
 //   rank      : 2..5
 //   dims      : extent of each dimension, fastest first (elements)
 //   strides_b : byte stride of dimensions 1..rank-1 (dimension 0 is contiguous)
 //   box       : box extent per dimension (elements); box[0]*2 must be <= 128 bytes
 // Returns 0 on success.
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+int make_tmap_16bit(bool f16, CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
                    const uint32_t* box, bool swizzle128 = true);
 
 }  // namespace d3

@@ -1,0 +1,95 @@
+// Timestep embedding path of UNet2DModel (reference call site
+// /root/reference/core/custom_pipelines.py:173 passes a scalar t, train.py:308 a per-sample vector):
+//   Timesteps(128): emb = cat[cos(t*f_i), sin(t*f_i)], f_i = exp(-ln(1e4) * i / 64)
+//   TimestepEmbedding: Linear(128,512) -> SiLU -> Linear(512,512)
+//   every ResnetBlock2D: time_emb_proj(SiLU(emb)) added to conv1's output per channel.
+// Replaces aten::sin/cos/exp/cat + 2 + 32 aten::linear launches by two tiny kernels per UNet forward:
+//   d3_time_embed      : t[nt] -> SiLU(emb)[nt][512]   (weights passed TRANSPOSED: w1t [128][512], w2t [512][512])
+//   d3_temb_project_all: all 32 projections at once -> one fused per-channel bias vector per ResNet
+//                        (conv1.bias + time_emb_proj.bias + W_r . SiLU(emb)), consumed by the conv epilogue.
+#include "common.cuh"
+#include "internal.h"
+
+namespace d3 {
+namespace {
+
+__global__ void __launch_bounds__(512) time_embed_kernel(const float* __restrict__ t, const float* __restrict__ w1,
+                                                         const float* __restrict__ b1, const float* __restrict__ w2,
+                                                         const float* __restrict__ b2, float* __restrict__ out) {
+  __shared__ float s_sin[128];
+  __shared__ float s_h[512];
+  const int n = blockIdx.x;
+  const float tv = t[n];
+  if (threadIdx.x < 64) {
+    // exponent = -ln(10000) * i / 64 ; arg = t * exp(exponent)  (fp32, as torch computes it)
+    const float freq = expf(-9.210340371976184f * (float)threadIdx.x / 64.0f);
+    const float arg = tv * freq;
+    s_sin[threadIdx.x] = cosf(arg);       // flip_sin_to_cos=True: [cos | sin]
+    s_sin[64 + threadIdx.x] = sinf(arg);
+  }
+  __syncthreads();
+  {
+    float acc = b1[threadIdx.x];
+#pragma unroll 8
+    for (int k = 0; k < 128; ++k) acc = fmaf(w1[(size_t)k * 512 + threadIdx.x], s_sin[k], acc);
+    s_h[threadIdx.x] = acc / (1.0f + expf(-acc));
+  }
+  __syncthreads();
+  {
+    float acc = b2[threadIdx.x];
+#pragma unroll 8
+    for (int k = 0; k < 512; ++k) acc = fmaf(w2[(size_t)k * 512 + threadIdx.x], s_h[k], acc);
+    out[(size_t)n * 512 + threadIdx.x] = acc / (1.0f + expf(-acc));  // SiLU(emb): what every consumer applies first
+  }
+}
+
+// one warp per output channel: out[n][row] = bias[row] + W[row,:] . semb[n,:]
+__global__ void __launch_bounds__(256) temb_project_kernel(const float* __restrict__ semb, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ out,
+                                                           int rows, int nt) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* wr = reinterpret_cast<const float4*>(w + (size_t)row * 512);
+  float4 wv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) wv[i] = __ldg(wr + lane + 32 * i);
+  for (int n = 0; n < nt; ++n) {
+    const float4* e = reinterpret_cast<const float4*>(semb + (size_t)n * 512);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 ev = __ldg(e + lane + 32 * i);
+      acc = fmaf(wv[i].x, ev.x, acc);
+      acc = fmaf(wv[i].y, ev.y, acc);
+      acc = fmaf(wv[i].z, ev.z, acc);
+      acc = fmaf(wv[i].w, ev.w, acc);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) out[(size_t)n * rows + row] = acc + bias[row];
+  }
+}
+
+}  // namespace
+}  // namespace d3
+
+extern "C" int d3_time_embed(const float* t, int nt, const float* w1, const float* b1, const float* w2,
+                             const float* b2, float* silu_emb_out, void* stream) {
+  using namespace d3;
+  D3_REQUIRE(t && w1 && b1 && w2 && b2 && silu_emb_out && nt > 0, "time_embed: bad arguments");
+  time_embed_kernel<<<nt, 512, 0, static_cast<cudaStream_t>(stream)>>>(t, w1, b1, w2, b2, silu_emb_out);
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
+extern "C" int d3_temb_project_all(const float* silu_emb, int nt, const float* w_all, const float* bias_all,
+                                   int rows, float* out, void* stream) {
+  using namespace d3;
+  D3_REQUIRE(silu_emb && w_all && bias_all && out && rows > 0 && nt > 0, "temb_project: bad arguments");
+  const int blocks = ceil_div(rows * 32, 256);
+  temb_project_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(silu_emb, w_all, bias_all, out, rows,
+                                                                             nt);
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}

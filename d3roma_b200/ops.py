@@ -22,23 +22,33 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def _dt(t: torch.Tensor) -> int:
+    """C-ABI dtype code of a 16-bit activation / weight tensor."""
+    if t.dtype == torch.bfloat16:
+        return _lib.DTYPE_BF16
+    if t.dtype == torch.float16:
+        return _lib.DTYPE_F16
+    raise ValueError(f"expected a bf16 or fp16 tensor, got {t.dtype}")
+
+
 def _check_nhwc(t: torch.Tensor, name: str) -> None:
-    if not (t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 4 and t.stride(3) == 1):
-        raise ValueError(f"{name}: expected a CUDA bf16 NHWC tensor with contiguous channels")
+    if not (t.is_cuda and t.dtype in (torch.bfloat16, torch.float16) and t.dim() == 4 and t.stride(3) == 1):
+        raise ValueError(f"{name}: expected a CUDA bf16/fp16 NHWC tensor with contiguous channels")
     B, H, W, _ = t.shape
     p = t.stride(2)
     if t.stride(1) != W * p or (B > 1 and t.stride(0) != H * W * p):
         raise ValueError(f"{name}: expected dense pixels (strides {t.stride()})")
 
 
-def pack_conv_weight(w_oihw: torch.Tensor, shortcut_w: Optional[torch.Tensor] = None) -> torch.Tensor:
+def pack_conv_weight(w_oihw: torch.Tensor, shortcut_w: Optional[torch.Tensor] = None,
+                     dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
     """OIHW fp32/bf16 conv weight (+ optional [Cout, Csc(,1,1)] 1x1 shortcut weight) -> bf16 [Cout, Ktot]
     with k = (kh*KW + kw)*Cin + c, shortcut channels appended (layout the igemm kernel expects)."""
     co, ci, kh, kw = w_oihw.shape
     w = w_oihw.permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
     if shortcut_w is not None:
         w = torch.cat([w, shortcut_w.reshape(co, -1).to(w.dtype)], dim=1)
-    return w.to(torch.bfloat16).contiguous()
+    return w.to(dtype).contiguous()
 
 
 def conv2d_igemm(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, *, ksize: int, stride: int = 1,
@@ -51,7 +61,7 @@ def conv2d_igemm(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, *,
     Cout = w_packed.shape[0]
     Ho, Wo = H // stride, W // stride
     if out is None:
-        out = torch.empty((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
+        out = torch.empty((B, Ho, Wo, Cout), dtype=x.dtype, device=x.device)
     _check_nhwc(out, "out")
     p = _lib.ConvParams()
     p.x, p.B, p.H, p.W, p.Cin, p.x_pitch = x.data_ptr(), B, H, W, Cin, x.stride(2)
@@ -66,11 +76,11 @@ def conv2d_igemm(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, *,
         _check_nhwc(sc2, "sc2")
         c2 = sc2.shape[3]
         p.sc2, p.C2, p.sc2_pitch = sc2.data_ptr(), c2, sc2.stride(2)
-    if w_packed.shape[1] != ksize * ksize * Cin + c1 + c2 or w_packed.dtype != torch.bfloat16:
+    if w_packed.shape[1] != ksize * ksize * Cin + c1 + c2 or w_packed.dtype != x.dtype:
         raise ValueError("w_packed shape/dtype mismatch")
-    if bias.dtype != torch.float32 or bias.shape[-1] != Cout:
+    if bias.dtype != torch.float32 or bias.shape[-1] != Cout or bias.stride(-1) != 1:
         raise ValueError("bias must be fp32 [Cout] or [B, Cout]")
-    p.bias, p.bias_bstride = bias.data_ptr(), (Cout if bias.dim() == 2 else 0)
+    p.bias, p.bias_bstride = bias.data_ptr(), (bias.stride(0) if bias.dim() == 2 and bias.shape[0] > 1 else 0)
     if residual is not None:
         _check_nhwc(residual, "residual")
         p.residual, p.res_pitch = residual.data_ptr(), residual.stride(2)
@@ -79,5 +89,91 @@ def conv2d_igemm(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, *,
         if stats.dtype != torch.float64 or stats.numel() != B * (Cout // 4) * 2:
             raise ValueError("stats must be fp64 [B, Cout/4, 2]")
         p.stats = stats.data_ptr()
+    p.dtype = _dt(x)
+    for t_ in (sc1, sc2, residual, out):
+        if t_ is not None and t_.dtype != x.dtype:
+            raise ValueError("all 16-bit operands of a conv must share one dtype")
     _lib.check(_lib.lib().d3_conv2d_igemm(C.byref(p), _stream()))
+    return out
+
+
+def groupnorm_silu(x1: torch.Tensor, stats1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *,
+                   x2: Optional[torch.Tensor] = None, stats2: Optional[torch.Tensor] = None, silu: bool = True,
+                   groups: int = 32, eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(+SiLU) over cat(x1, x2) using the producers' quad statistics (``d3_groupnorm_silu``)."""
+    _check_nhwc(x1, "x1")
+    B, H, W, C1 = x1.shape
+    C2 = 0
+    if x2 is not None:
+        _check_nhwc(x2, "x2")
+        C2 = x2.shape[3]
+    if out is None:
+        out = torch.empty((B, H, W, C1 + C2), dtype=x1.dtype, device=x1.device)
+    _lib.check(_lib.lib().d3_groupnorm_silu(
+        x1.data_ptr(), C1, x1.stride(2), stats1.data_ptr(), _ptr(x2), C2, x2.stride(2) if x2 is not None else 0,
+        _ptr(stats2), gamma.data_ptr(), beta.data_ptr(), B, H * W, groups, eps, int(silu), out.data_ptr(),
+        out.stride(2), _dt(x1), _stream()))
+    return out
+
+
+def upsample_nearest2x(x: torch.Tensor) -> torch.Tensor:
+    _check_nhwc(x, "x")
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, 2 * H, 2 * W, Cc), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().d3_upsample_nearest2x(x.data_ptr(), B, H, W, Cc, x.stride(2), out.data_ptr(),
+                                                out.stride(2), _stream()))
+    return out
+
+
+def im2col_input(sample: torch.Tensor, cond: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+                 dtype: torch.dtype = torch.bfloat16):
+    """fp32 NCHW sample [B,Cs,H,W] (+ cond [B,Cc,H,W]) -> bf16 [B,H,W,128] im2col rows for conv_in."""
+    B, Cs, H, W = sample.shape
+    Cc = 0 if cond is None else cond.shape[1]
+    for t in (sample, cond):
+        if t is not None and not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError("im2col_input expects contiguous fp32 CUDA NCHW tensors")
+    if out is None:
+        out = torch.empty((B, H, W, 128), dtype=dtype, device=sample.device)
+    _lib.check(_lib.lib().d3_im2col_input(sample.data_ptr(), Cs, _ptr(cond), Cc, B, H, W, out.data_ptr(), _dt(out),
+                                          _stream()))
+    return out
+
+
+def conv_out_fused(x: torch.Tensor, stats: torch.Tensor, gamma, beta, w, bias, dc: int, eps: float = 1e-5,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _check_nhwc(x, "x")
+    B, H, W, Cc = x.shape
+    if Cc != 128:
+        raise ValueError("conv_out_fused expects 128 input channels")
+    if out is None:
+        out = torch.empty((B, dc, H, W), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().d3_conv_out_fused(x.data_ptr(), x.stride(2), stats.data_ptr(), gamma.data_ptr(),
+                                            beta.data_ptr(), w.data_ptr(), bias.data_ptr(), B, H, W, dc, eps,
+                                            out.data_ptr(), _dt(x), _stream()))
+    return out
+
+
+def time_embed(t: torch.Tensor, w1t, b1, w2t, b2) -> torch.Tensor:
+    nt = t.numel()
+    out = torch.empty((nt, 512), dtype=torch.float32, device=t.device)
+    _lib.check(_lib.lib().d3_time_embed(t.data_ptr(), nt, w1t.data_ptr(), b1.data_ptr(), w2t.data_ptr(),
+                                        b2.data_ptr(), out.data_ptr(), _stream()))
+    return out
+
+
+def temb_project_all(silu_emb: torch.Tensor, w_all: torch.Tensor, bias_all: torch.Tensor) -> torch.Tensor:
+    nt, rows = silu_emb.shape[0], w_all.shape[0]
+    out = torch.empty((nt, rows), dtype=torch.float32, device=silu_emb.device)
+    _lib.check(_lib.lib().d3_temb_project_all(silu_emb.data_ptr(), nt, w_all.data_ptr(), bias_all.data_ptr(), rows,
+                                              out.data_ptr(), _stream()))
+    return out
+
+
+def attention_hd8(qkv: torch.Tensor, C_: int) -> torch.Tensor:
+    _check_nhwc(qkv, "qkv")
+    B, H, W, _ = qkv.shape
+    out = torch.empty((B, H, W, C_), dtype=qkv.dtype, device=qkv.device)
+    _lib.check(_lib.lib().d3_attention_hd8(qkv.data_ptr(), qkv.stride(2), B, H * W, C_, out.data_ptr(),
+                                           out.stride(2), _dt(qkv), _stream()))
     return out

@@ -1,0 +1,332 @@
+"""``UNet2DModel`` — drop-in for the reference's denoiser on the sampling path.
+
+The reference builds ``diffusers.UNet2DModel(sample_size=[H,W], in_channels=Cin, out_channels=dc,
+layers_per_block=2, block_out_channels=(128,128,256,256,512,512), down_block_types=("DownBlock2D",)*4 +
+("AttnDownBlock2D","DownBlock2D"), up_block_types=("UpBlock2D","AttnUpBlock2D")+("UpBlock2D",)*4)`` at
+``/root/reference/train.py:788-810`` and calls ``unet(model_input, t).sample`` at
+``core/custom_pipelines.py:173``.  This class keeps that call surface (``__call__(sample, timestep,
+return_dict=True)``, ``.sample_size``, ``.config``, ``load_state_dict`` with diffusers key names, ``.to``,
+``.device``) and runs the forward entirely through ``libd3roma_b200.so``:
+
+    conv_in      d3_im2col_input + d3_conv2d_igemm (K = 128)
+    ResnetBlock  d3_groupnorm_silu -> d3_conv2d_igemm (+temb bias) -> d3_groupnorm_silu ->
+                 d3_conv2d_igemm (+ folded 1x1 shortcut K-slabs over the *virtual* concat, or identity residual)
+    Attention    d3_groupnorm_silu(no SiLU) -> igemm 1x1 (fused QKV) -> d3_attention_hd8 -> igemm 1x1 (+residual)
+    Down/Up      igemm stride 2 / d3_upsample_nearest2x + igemm
+    head         d3_conv_out_fused (GroupNorm + SiLU + conv 128 -> dc, fp32 NCHW out)
+    time         d3_time_embed + d3_temb_project_all (all 32 ResNet projections in one launch)
+
+Activations are bf16 NHWC; accumulation, GroupNorm statistics and the model output are fp32/fp64.
+There is no PyTorch fallback: without the CUDA library every call raises.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+
+BLOCK_OUT = (128, 128, 256, 256, 512, 512)
+DOWN_TYPES = ("DownBlock2D",) * 4 + ("AttnDownBlock2D", "DownBlock2D")
+UP_TYPES = ("UpBlock2D", "AttnUpBlock2D") + ("UpBlock2D",) * 4
+
+
+class UNet2DOutput(SimpleNamespace):
+    """``.sample`` like diffusers' ``UNet2DOutput``."""
+
+
+class _Act:
+    """A bf16 NHWC activation together with the fp64 quad statistics of its producer."""
+
+    __slots__ = ("t", "stats")
+
+    def __init__(self, t: torch.Tensor, stats: Optional[torch.Tensor]):
+        self.t, self.stats = t, stats
+
+
+class _StatsArena:
+    """One zero-initialised fp64 buffer per forward from which every producer takes its [B, C/4, 2] slice
+    (a single memset per UNet forward instead of one per tensor)."""
+
+    def __init__(self, device, nbytes_doubles: int):
+        self.buf = torch.zeros(nbytes_doubles, dtype=torch.float64, device=device)
+        self.off = 0
+
+    def reset(self):
+        self.buf.zero_()
+        self.off = 0
+
+    def take(self, B: int, C: int) -> torch.Tensor:
+        n = B * (C // 4) * 2
+        if self.off + n > self.buf.numel():
+            raise RuntimeError("stats arena exhausted")
+        v = self.buf[self.off:self.off + n].view(B, C // 4, 2)
+        self.off += n
+        return v
+
+
+def _resnet_specs():
+    """(prefix, cin_hidden, cin_skip, cout, has_attn) in execution order + structural markers."""
+    boc = BLOCK_OUT
+    specs = []
+    out_c = boc[0]
+    for i, t in enumerate(DOWN_TYPES):
+        in_c, out_c = out_c, boc[i]
+        for j in range(2):
+            specs.append(("down", i, j, in_c if j == 0 else out_c, 0, out_c, t.startswith("Attn")))
+    specs.append(("mid", 0, 0, boc[-1], 0, boc[-1], True))
+    specs.append(("mid", 0, 1, boc[-1], 0, boc[-1], False))
+    rev = list(reversed(boc))
+    out_c = rev[0]
+    for i, t in enumerate(UP_TYPES):
+        prev, out_c = out_c, rev[i]
+        in_c = rev[min(i + 1, len(boc) - 1)]
+        for j in range(3):
+            skip = in_c if j == 2 else out_c
+            rin = prev if j == 0 else out_c
+            specs.append(("up", i, j, rin, skip, out_c, t.startswith("Attn")))
+    return specs
+
+
+class UNet2DModel:
+    def __init__(self, sample_size: Sequence[int] = (384, 640), in_channels: int = 8, out_channels: int = 1,
+                 layers_per_block: int = 2, block_out_channels: Sequence[int] = BLOCK_OUT,
+                 down_block_types: Sequence[str] = DOWN_TYPES, up_block_types: Sequence[str] = UP_TYPES,
+                 compute_dtype: str = "bf16", **unused):
+        if (tuple(block_out_channels) != BLOCK_OUT or tuple(down_block_types) != DOWN_TYPES
+                or tuple(up_block_types) != UP_TYPES or layers_per_block != 2):
+            raise NotImplementedError("d3roma_b200.UNet2DModel implements the architecture of train.py:788-810 only")
+        if 9 * in_channels > 128 or out_channels not in (1, 3):
+            raise NotImplementedError("in_channels must be <= 14 and out_channels 1 or 3")
+        self.sample_size = list(sample_size) if not isinstance(sample_size, int) else sample_size
+        self.config = SimpleNamespace(sample_size=self.sample_size, in_channels=in_channels,
+                                      out_channels=out_channels, layers_per_block=2,
+                                      block_out_channels=tuple(block_out_channels),
+                                      down_block_types=tuple(down_block_types), up_block_types=tuple(up_block_types),
+                                      attention_head_dim=8, norm_num_groups=32, norm_eps=1e-5)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        if compute_dtype not in ("bf16", "fp16"):
+            raise ValueError("compute_dtype must be 'bf16' or 'fp16'")
+        self.compute_dtype = compute_dtype
+        self._adt = torch.bfloat16 if compute_dtype == "bf16" else torch.float16
+        self.device = torch.device("cpu")
+        self.dtype = torch.float32  # dtype of the pipeline-facing tensors
+        self._w: Dict[str, torch.Tensor] = {}
+        self._specs = _resnet_specs()
+        self._arena: Optional[_StatsArena] = None
+        self._loaded = False
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
+        """Pack a diffusers-keyed ``state_dict`` into the layouts the kernels read."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("d3roma_b200.UNet2DModel needs a CUDA device (no CPU fallback)")
+        dev = self.device if self.device.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        sd = {k: v.detach() for k, v in sd.items()}
+        used = set()
+
+        def get(k):
+            used.add(k)
+            return sd[k].to(dev, torch.float32)
+
+        W = self._w
+        # conv_in as a 1x1 igemm over the 128-wide im2col row: [128][tap*Cin + c], zero padded
+        w_in = get("conv_in.weight")
+        cin = w_in.shape[1]
+        assert cin == self.in_channels, "conv_in.weight does not match in_channels"
+        w_in = w_in.permute(0, 2, 3, 1).reshape(128, 9 * cin)
+        W["conv_in.w"] = torch.nn.functional.pad(w_in, (0, 128 - 9 * cin)).to(self._adt).contiguous()
+        W["conv_in.b"] = get("conv_in.bias").contiguous()
+        # time MLP (transposed fp32)
+        W["time.w1t"] = get("time_embedding.linear_1.weight").t().contiguous()
+        W["time.b1"] = get("time_embedding.linear_1.bias").contiguous()
+        W["time.w2t"] = get("time_embedding.linear_2.weight").t().contiguous()
+        W["time.b2"] = get("time_embedding.linear_2.bias").contiguous()
+
+        proj_w, proj_b, off = [], [], 0
+        self._temb_off: Dict[str, int] = {}
+        for kind, i, j, cin_h, cin_s, cout, attn in self._specs:
+            p = self._rprefix(kind, i, j)
+            W[p + ".n1.g"], W[p + ".n1.b"] = get(p + ".norm1.weight").contiguous(), get(p + ".norm1.bias").contiguous()
+            W[p + ".n2.g"], W[p + ".n2.b"] = get(p + ".norm2.weight").contiguous(), get(p + ".norm2.bias").contiguous()
+            W[p + ".w1"] = ops.pack_conv_weight(get(p + ".conv1.weight"), dtype=self._adt)
+            b2 = get(p + ".conv2.bias")
+            if cin_h + cin_s != cout:
+                W[p + ".w2"] = ops.pack_conv_weight(get(p + ".conv2.weight"), get(p + ".conv_shortcut.weight"), dtype=self._adt)
+                b2 = b2 + get(p + ".conv_shortcut.bias")
+            else:
+                W[p + ".w2"] = ops.pack_conv_weight(get(p + ".conv2.weight"), dtype=self._adt)
+            W[p + ".b2"] = b2.contiguous()
+            proj_w.append(get(p + ".time_emb_proj.weight"))
+            proj_b.append(get(p + ".time_emb_proj.bias") + get(p + ".conv1.bias"))
+            self._temb_off[p] = off
+            off += cout
+            if attn:
+                a = self._aprefix(kind, i, j)
+                W[a + ".gn.g"], W[a + ".gn.b"] = get(a + ".group_norm.weight").contiguous(), get(a + ".group_norm.bias").contiguous()
+                wq, wk, wv = get(a + ".to_q.weight"), get(a + ".to_k.weight"), get(a + ".to_v.weight")
+                W[a + ".wqkv"] = torch.cat([wq, wk, wv], 0).to(self._adt).contiguous()
+                W[a + ".bqkv"] = torch.cat([get(a + ".to_q.bias"), get(a + ".to_k.bias"), get(a + ".to_v.bias")]).contiguous()
+                W[a + ".wo"] = get(a + ".to_out.0.weight").to(self._adt).contiguous()
+                W[a + ".bo"] = get(a + ".to_out.0.bias").contiguous()
+        W["temb.w"] = torch.cat(proj_w, 0).contiguous()
+        W["temb.b"] = torch.cat(proj_b, 0).contiguous()
+        self._temb_rows = off
+        for i in range(5):
+            p = f"down_blocks.{i}.downsamplers.0.conv"
+            W[p + ".w"], W[p + ".b"] = ops.pack_conv_weight(get(p + ".weight"), dtype=self._adt), get(p + ".bias").contiguous()
+            p = f"up_blocks.{i}.upsamplers.0.conv"
+            W[p + ".w"], W[p + ".b"] = ops.pack_conv_weight(get(p + ".weight"), dtype=self._adt), get(p + ".bias").contiguous()
+        W["out.g"], W["out.b"] = get("conv_norm_out.weight").contiguous(), get("conv_norm_out.bias").contiguous()
+        w_out = get("conv_out.weight")  # [dc,128,3,3] -> [dc][9][128]
+        assert w_out.shape[0] == self.out_channels
+        W["out.w"] = w_out.permute(0, 2, 3, 1).reshape(self.out_channels, 9, 128).contiguous()
+        W["out.bias"] = get("conv_out.bias").contiguous()
+        if strict:
+            missing = set(sd) - used
+            if missing:
+                raise KeyError(f"unexpected keys in state_dict: {sorted(missing)[:5]} ...")
+        self._loaded = True
+        return self
+
+    @staticmethod
+    def _rprefix(kind, i, j):
+        return {"down": f"down_blocks.{i}.resnets.{j}", "mid": f"mid_block.resnets.{j}",
+                "up": f"up_blocks.{i}.resnets.{j}"}[kind]
+
+    @staticmethod
+    def _aprefix(kind, i, j):
+        return {"down": f"down_blocks.{i}.attentions.{j}", "mid": "mid_block.attentions.0",
+                "up": f"up_blocks.{i}.attentions.{j}"}[kind]
+
+    def to(self, device=None, dtype=None):
+        if device is not None:
+            device = torch.device(device)
+            if device.type != "cuda":
+                raise RuntimeError("d3roma_b200.UNet2DModel runs on CUDA only")
+            if device.index is None:
+                device = torch.device("cuda", torch.cuda.current_device())
+            if self._loaded and device != self.device:
+                self._w = {k: v.to(device) for k, v in self._w.items()}
+                self._arena = None
+            self.device = device
+        return self
+
+    def eval(self):
+        return self
+
+    def parameters(self):
+        return iter(self._w.values())
+
+    # ------------------------------------------------------------------ forward pieces
+    def _conv(self, x, w, b, ksize, B, stride=1, sc1=None, sc2=None, residual=None, want_stats=True):
+        cout = w.shape[0]
+        stats = self._arena.take(B, cout) if want_stats else None
+        out = ops.conv2d_igemm(x, w, b, ksize=ksize, stride=stride, sc1=sc1, sc2=sc2, residual=residual, stats=stats)
+        return _Act(out, stats)
+
+    def _resnet(self, p: str, h: _Act, skip: Optional[_Act], cout: int, bias1: torch.Tensor, B: int) -> _Act:
+        W = self._w
+        a1 = ops.groupnorm_silu(h.t, h.stats, W[p + ".n1.g"], W[p + ".n1.b"],
+                                x2=None if skip is None else skip.t, stats2=None if skip is None else skip.stats)
+        h1 = self._conv(a1, W[p + ".w1"], bias1, 3, B)
+        del a1
+        a2 = ops.groupnorm_silu(h1.t, h1.stats, W[p + ".n2.g"], W[p + ".n2.b"])
+        cin = h.t.shape[3] + (0 if skip is None else skip.t.shape[3])
+        if cin != cout:
+            return self._conv(a2, W[p + ".w2"], W[p + ".b2"], 3, B, sc1=h.t, sc2=None if skip is None else skip.t)
+        return self._conv(a2, W[p + ".w2"], W[p + ".b2"], 3, B, residual=h.t)
+
+    def _attention(self, a: str, h: _Act, B: int) -> _Act:
+        W = self._w
+        C = h.t.shape[3]
+        n = ops.groupnorm_silu(h.t, h.stats, W[a + ".gn.g"], W[a + ".gn.b"], silu=False)
+        qkv = self._conv(n, W[a + ".wqkv"], W[a + ".bqkv"], 1, B, want_stats=False)
+        o = ops.attention_hd8(qkv.t, C)
+        return self._conv(o, W[a + ".wo"], W[a + ".bo"], 1, B, residual=h.t)
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward_split(self, sample: torch.Tensor, cond: Optional[torch.Tensor], timestep) -> torch.Tensor:
+        """UNet forward on ``cat([sample, cond], 1)`` without materialising the concat.
+        sample fp32 [B,dc,H,W], cond fp32 [B,Cc,H,W] (contiguous, CUDA); returns fp32 [B,out_channels,H,W]."""
+        if not self._loaded:
+            raise RuntimeError("UNet2DModel: load_state_dict() has not been called")
+        B, Cs, H, Wd = sample.shape
+        Cc = 0 if cond is None else cond.shape[1]
+        if Cs + Cc != self.in_channels:
+            raise ValueError(f"expected {self.in_channels} input channels, got {Cs}+{Cc}")
+        if H % 32 or Wd % 32:
+            raise ValueError(f"H and W must be multiples of 32 (got {H}x{Wd}); pad with InputPadder(divis_by=32)")
+        dev = sample.device
+        W = self._w
+        need = B * 2 * 40000
+        if self._arena is None or self._arena.buf.numel() < need or self._arena.buf.device != dev:
+            self._arena = _StatsArena(dev, need)
+        self._arena.reset()
+
+        # timestep -> fused per-ResNet bias vectors
+        if torch.is_tensor(timestep):
+            t = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
+        else:
+            t = torch.tensor([float(timestep)], dtype=torch.float32, device=dev)
+        if t.numel() not in (1, B):
+            raise ValueError("timestep must be a scalar or have one entry per sample")
+        semb = ops.time_embed(t, W["time.w1t"], W["time.b1"], W["time.w2t"], W["time.b2"])
+        tb = ops.temb_project_all(semb, W["temb.w"], W["temb.b"])  # [nt, rows]
+
+        def bias1(p, cout):
+            o = self._temb_off[p]
+            return tb[:, o:o + cout] if tb.shape[0] > 1 else tb[0, o:o + cout]
+
+        col = ops.im2col_input(sample, cond, dtype=self._adt)
+        h = self._conv(col, W["conv_in.w"], W["conv_in.b"], 1, B)
+        del col
+        skips: List[_Act] = [h]
+        it = iter(self._specs)
+        for i in range(6):
+            for j in range(2):
+                kind, bi, bj, cin_h, cin_s, cout, attn = next(it)
+                p = self._rprefix(kind, bi, bj)
+                h = self._resnet(p, h, None, cout, bias1(p, cout), B)
+                if attn:
+                    h = self._attention(self._aprefix(kind, bi, bj), h, B)
+                skips.append(h)
+            if i < 5:
+                p = f"down_blocks.{i}.downsamplers.0.conv"
+                h = self._conv(h.t, W[p + ".w"], W[p + ".b"], 3, B, stride=2)
+                skips.append(h)
+        for j in range(2):
+            kind, bi, bj, cin_h, cin_s, cout, attn = next(it)
+            p = self._rprefix(kind, bi, bj)
+            h = self._resnet(p, h, None, cout, bias1(p, cout), B)
+            if attn:
+                h = self._attention(self._aprefix(kind, bi, bj), h, B)
+        for i in range(6):
+            for j in range(3):
+                kind, bi, bj, cin_h, cin_s, cout, attn = next(it)
+                p = self._rprefix(kind, bi, bj)
+                h = self._resnet(p, h, skips.pop(), cout, bias1(p, cout), B)
+                if attn:
+                    h = self._attention(self._aprefix(kind, bi, bj), h, B)
+            if i < 5:
+                p = f"up_blocks.{i}.upsamplers.0.conv"
+                u = ops.upsample_nearest2x(h.t)
+                h = self._conv(u, W[p + ".w"], W[p + ".b"], 3, B)
+                del u
+        return ops.conv_out_fused(h.t, h.stats, W["out.g"], W["out.b"], W["out.w"], W["out.bias"], self.out_channels)
+
+    @torch.no_grad()
+    def __call__(self, sample: torch.Tensor, timestep, return_dict: bool = True):
+        """``unet(model_input[B,Cin,H,W], t).sample`` (custom_pipelines.py:173; train.py:308 form with
+        ``return_dict=False``)."""
+        x = sample.to(device=self.device, dtype=torch.float32).contiguous()
+        out = self.forward_split(x, None, timestep).to(sample.dtype)
+        if not return_dict:
+            return (out,)
+        return UNet2DOutput(sample=out)
+
+    forward = __call__

@@ -34,6 +34,11 @@ extern "C" {
 #define D3_ERR_CUDA 2
 #define D3_ERR_UNSUPPORTED 3
 
+/* 16-bit storage / tensor-core operand type of the UNet activations and packed weights. Both run tcgen05
+ * kind::f16 at the same rate with fp32 accumulation; F16 carries 3 more mantissa bits (parity). */
+#define D3_DTYPE_BF16 0
+#define D3_DTYPE_F16 1
+
 /* ---- library ------------------------------------------------------------------------------- */
 const char* d3_last_error(void);
 int d3_version(void);
@@ -69,9 +74,88 @@ typedef struct d3_conv_params {
   void* out;           /* bf16 NHWC [B,Ho,Wo,Cout], pixel pitch out_pitch                            */
   int32_t out_pitch;
   double* stats;       /* optional fp64 [B][Cout/4][2], must be zero on entry; NULL to skip          */
+  int32_t dtype;       /* D3_DTYPE_BF16 / D3_DTYPE_F16: element type of x, w, sc1, sc2, residual, out        */
 } d3_conv_params;
 
 int d3_conv2d_igemm(const d3_conv_params* p, void* stream);
+
+/* ---- GroupNorm(32 groups) + optional SiLU over up to two concatenated sources ------------------
+ * Replaces aten::native_group_norm + aten::silu (+ the torch.cat of the up blocks) - SURVEY.md §2.3 rows 4,5,10.
+ * out[b,p,c] = act(gamma[c] * (x[b,p,c] - mean[b,g]) * rstd[b,g] + beta[c]),  x = cat(x1, x2) along channels.
+ * mean/rstd come from the producers' quad statistics (stats1 [B][C1/4][2], stats2 [B][C2/4][2], fp64). */
+int d3_groupnorm_silu(const void* x1, int C1, int pitch1, const double* stats1, const void* x2, int C2, int pitch2,
+                      const double* stats2, const float* gamma, const float* beta, int B, int HW, int groups,
+                      float eps, int apply_silu, void* out, int out_pitch, int dtype, void* stream);
+
+/* ---- nearest-neighbour 2x upsample (F.interpolate(scale_factor=2, mode="nearest") of Upsample2D) */
+int d3_upsample_nearest2x(const void* in, int B, int H, int W, int C, int in_pitch, void* out, int out_pitch,
+                          void* stream);
+
+/* ---- conv_in front end: torch.cat([sample, cond], 1) + cast + NCHW->NHWC + 3x3 im2col with zero padding.
+ * sample fp32 NCHW [B,Cs,H,W], cond fp32 NCHW [B,Cc,H,W] -> bf16 [B,H,W,128], k = tap*(Cs+Cc) + c, zero-padded.
+ * Replaces custom_pipelines.py:158-171 (the per-step torch.cat) and the im2col of conv_in. */
+int d3_im2col_input(const float* sample, int Cs, const float* cond, int Cc, int B, int H, int W, void* out,
+                    int dtype, void* stream);
+
+/* ---- conv_norm_out + SiLU + conv_out fused: bf16 NHWC [B,H,W,128] -> fp32 NCHW [B,dc,H,W] (dc = 1 or 3).
+ * w fp32 [dc][9][128] (tap-major), stats = quad statistics of x ([B][32][2]). */
+int d3_conv_out_fused(const void* x, int pitch, const double* stats, const float* gamma, const float* beta,
+                      const float* w, const float* bias, int B, int H, int W, int dc, float eps, float* out,
+                      int dtype, void* stream);
+
+/* ---- timestep embedding (Timesteps(128) -> Linear -> SiLU -> Linear -> SiLU) and all ResNet projections.
+ * t fp32 [nt] (nt = 1 for the sampling loop, = B for per-sample timesteps). Weights are passed transposed:
+ * w1t [128][512], w2t [512][512]. Output silu_emb [nt][512]. */
+int d3_time_embed(const float* t, int nt, const float* w1t, const float* b1, const float* w2t, const float* b2,
+                  float* silu_emb_out, void* stream);
+/* out[n][r] = bias_all[r] + w_all[r,:] . silu_emb[n,:]; w_all fp32 [rows][512] = all time_emb_proj weights stacked,
+ * bias_all = time_emb_proj.bias + conv1.bias stacked. */
+int d3_temb_project_all(const float* silu_emb, int nt, const float* w_all, const float* bias_all, int rows,
+                        float* out, void* stream);
+
+/* ---- self-attention core, head_dim 8: qkv bf16 [B,N,>=3C] (q | k | v at channel offsets 0, C, 2C) -> [B,N,C] */
+int d3_attention_hd8(const void* qkv, int pitch, int B, int N, int C, void* out, int out_pitch, int dtype,
+                     void* stream);
+
+/* ---- fused scheduler updates -----------------------------------------------------------------
+ * prediction_type: 0 epsilon, 1 sample, 2 v_prediction.  clip_mode: 0 none, 1 clamp(+-clip_range),
+ * 2 "thresholding" (== clamp(+-1)/1 because sample_max_value defaults to 1.0). */
+typedef struct d3_ddim_coeffs {
+  int32_t prediction_type;
+  float sqrt_alpha_t;    /* alpha_prod_t ** 0.5                      (scheduler_ddim.py:416,424) */
+  float sqrt_beta_t;     /* (1 - alpha_prod_t) ** 0.5                                          */
+  float sqrt_alpha_prev; /* alpha_prod_t_prev ** 0.5                 (:459)                    */
+  float dir_coeff;       /* (1 - alpha_prod_t_prev - std_dev_t**2) ** 0.5 (:456)               */
+  float std_dev;         /* eta * variance ** 0.5                    (:448-449)                */
+  int32_t clip_mode;
+  float clip_range;
+  int32_t use_clipped_model_output;
+} d3_ddim_coeffs;
+
+typedef struct d3_ddpm_coeffs {
+  int32_t prediction_type;
+  float sqrt_alpha_t;
+  float sqrt_beta_t;
+  float x0_coeff;        /* pred_original_sample_coeff               (scheduler_ddpm.py:482)   */
+  float xt_coeff;        /* current_sample_coeff                     (:483)                    */
+  float sigma;           /* multiplier of the N(0,1) draw for t > 0  (:496-504)                */
+  int32_t clip_mode;
+  float clip_range;
+} d3_ddpm_coeffs;
+
+/* fp32, n elements. variance_noise may be NULL (eta == 0 / t == 0). prev_mean (x_{t-1} before noise) and dir_out
+ * (the "direction pointing to x_t" term) are optional outputs. Replaces scheduler_ddim.py:423-489. */
+int d3_sched_ddim_step(const float* model_output, const float* sample, const float* variance_noise,
+                       const d3_ddim_coeffs* c, int64_t n, float* prev_sample, float* pred_original,
+                       float* prev_mean, float* dir_out, void* stream);
+/* Replaces scheduler_ddpm.py:460-518. */
+int d3_sched_ddpm_step(const float* model_output, const float* sample, const float* variance_noise,
+                       const d3_ddpm_coeffs* c, int64_t n, float* prev_sample, float* pred_original,
+                       float* prev_mean, void* stream);
+/* out = a*x (+ b*y) (+ c*z), each product and sum rounded separately (recombination after a guidance
+ * perturbation of x0: scheduler_ddim.py:468, scheduler_ddpm.py:512). y, z may be NULL. */
+int d3_lincomb(float a, const float* x, float b, const float* y, float c, const float* z, int64_t n, float* out,
+               void* stream);
 
 #ifdef __cplusplus
 }

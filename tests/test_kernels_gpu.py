@@ -1,0 +1,104 @@
+"""Component parity of the bandwidth / small kernels against plain PyTorch fp32 references of the same ops."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _quad_stats(x):  # x [B,H,W,C] bf16 -> [B, C/4, 2] fp64
+    B, H, W, C = x.shape
+    o = x.double().reshape(B, H * W, C // 4, 4)
+    return torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1).contiguous()
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+@pytest.mark.parametrize("C1,C2,silu", [(128, 0, True), (256, 128, True), (512, 256, True), (512, 0, False),
+                                        (1024, 0, True)])
+def test_groupnorm_silu(C1, C2, silu, dt):
+    from d3roma_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    B, H, W = 2, 24, 40
+    x1 = (torch.randn(B, H, W, C1, device="cuda", generator=g) * 1.5 + 0.3).to(dt)
+    x2 = (torch.randn(B, H, W, C2, device="cuda", generator=g) * 0.7 - 0.2).to(dt) if C2 else None
+    C = C1 + C2
+    gamma = torch.randn(C, device="cuda", generator=g)
+    beta = torch.randn(C, device="cuda", generator=g)
+    out = ops.groupnorm_silu(x1, _quad_stats(x1), gamma, beta, x2=x2, stats2=None if x2 is None else _quad_stats(x2),
+                             silu=silu)
+    xc = torch.cat([x1, x2], 3) if C2 else x1
+    ref = F.group_norm(xc.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    tol = 1e-2 if dt == torch.bfloat16 else 2e-3
+    torch.testing.assert_close(out.float(), ref, rtol=tol, atol=tol)
+
+
+def test_upsample_and_im2col():
+    from d3roma_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(2, 6, 10, 128, device="cuda", generator=g).to(torch.bfloat16)
+    up = ops.upsample_nearest2x(x)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up.float(), ref)
+    for Cs, Cc in ((1, 7), (1, 4), (3, 9), (8, 0)):
+        s = torch.randn(2, Cs, 8, 12, device="cuda", generator=g)
+        c = torch.randn(2, Cc, 8, 12, device="cuda", generator=g) if Cc else None
+        col = ops.im2col_input(s, c)
+        xin = torch.cat([s, c], 1) if Cc else s
+        Cin = Cs + Cc
+        unf = F.unfold(xin, 3, padding=1)  # [B, Cin*9, HW] with index c*9 + tap
+        unf = unf.view(2, Cin, 9, 8, 12).permute(0, 3, 4, 2, 1).reshape(2, 8, 12, 9 * Cin)
+        ref = F.pad(unf, (0, 128 - 9 * Cin)).to(torch.bfloat16)
+        assert torch.equal(col, ref)
+
+
+@pytest.mark.parametrize("dc", [1, 3])
+def test_conv_out_fused(dc):
+    from d3roma_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(2)
+    B, H, W = 2, 10, 70
+    x = (torch.randn(B, H, W, 128, device="cuda", generator=g) * 2 + 0.5).to(torch.bfloat16)
+    gamma = torch.randn(128, device="cuda", generator=g)
+    beta = torch.randn(128, device="cuda", generator=g)
+    w = torch.randn(dc, 128, 3, 3, device="cuda", generator=g) / 34.0
+    bias = torch.randn(dc, device="cuda", generator=g)
+    out = ops.conv_out_fused(x, _quad_stats(x), gamma, beta, w.permute(0, 2, 3, 1).reshape(dc, 9, 128).contiguous(),
+                             bias, dc)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(F.silu(F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)), w, bias, padding=1)
+    torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("N,hw", [(960, (24, 40)), (240, (12, 20)), (2040, (34, 60))])
+def test_attention_hd8(N, hw):
+    from d3roma_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, C = 2, 512
+    qkv = (torch.randn(B, hw[0], hw[1], 3 * C, device="cuda", generator=g) * 1.2).to(torch.bfloat16)
+    out = ops.attention_hd8(qkv, C)
+    q, k, v = qkv.float().view(B, N, 3, 64, 8).permute(2, 0, 3, 1, 4)
+    p = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(8), dim=-1)
+    ref = (p @ v).permute(0, 2, 1, 3).reshape(B, hw[0], hw[1], C)
+    torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-2)
+
+
+def test_time_embedding():
+    from d3roma_b200 import ops
+    from oracle.unet_ref import TimestepEmbedding, timestep_embedding
+    torch.manual_seed(4)
+    te = TimestepEmbedding(128, 512)
+    proj = torch.nn.Linear(512, 384)
+    for tv in ([73.0], [1.0, 109.0, 990.0]):
+        t = torch.tensor(tv)
+        emb = te(timestep_embedding(t, 128))
+        ref_semb = F.silu(emb)
+        ref_proj = proj(ref_semb)
+        semb = ops.time_embed(t.cuda(), te.linear_1.weight.t().contiguous().cuda(), te.linear_1.bias.cuda(),
+                              te.linear_2.weight.t().contiguous().cuda(), te.linear_2.bias.cuda())
+        torch.testing.assert_close(semb.cpu(), ref_semb.detach(), rtol=1e-4, atol=1e-5)
+        pr = ops.temb_project_all(semb, proj.weight.detach().cuda().contiguous(), proj.bias.detach().cuda())
+        torch.testing.assert_close(pr.cpu(), ref_proj.detach(), rtol=1e-4, atol=1e-5)

@@ -1,0 +1,46 @@
+"""Whole-UNet parity: d3roma_b200.UNet2DModel (tcgen05 path) vs the oracle restatement (fp32 CPU) on the same
+random-init weights and inputs.
+
+Tolerances.  BASELINE.json's north_star asks for a per-step model-output max-abs error <= 1e-2 with 16-bit tensor-core
+operands.  ``tools/error_budget.py`` (run on a B200, profiles/r01_error_budget.txt) shows that on this 113 M-parameter
+random-init network the bf16 rounding of the conv operands alone (weights + activations, which ANY bf16 tensor-core
+implementation, cuDNN included, must perform) already yields a max-abs error of 0.85-0.92e-2 against fp32, and an ideal
+bf16 pipeline (operands + bf16 storage of activations) 1.1-1.3e-2.  We therefore test
+  * fp16 operands/storage (same tcgen05 rate, 3 more mantissa bits): max-abs <= 1e-2  - the north_star tolerance;
+  * bf16 operands/storage (the dtype BASELINE names): max-abs <= 2e-2 and rms <= 4e-3 - the bf16-inherent bound.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL_NORTH_STAR = 1e-2
+TOL_BF16_MAX, TOL_BF16_RMS = 2e-2, 4e-3
+
+
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+@pytest.mark.parametrize("cin,dc,hw,ts", [(8, 1, (64, 96), [109, 1]), (5, 1, (32, 64), [49]), (12, 3, (32, 32), [13])])
+def test_unet_matches_oracle(cin, dc, hw, ts, dtype):
+    from d3roma_b200.unet import UNet2DModel
+    from oracle.unet_ref import make_unet
+    torch.set_num_threads(8)
+    ref = make_unet(cin, dc, seed=0, sample_size=hw)
+    net = UNet2DModel(sample_size=hw, in_channels=cin, out_channels=dc, compute_dtype=dtype).to("cuda")
+    net.load_state_dict(ref.state_dict())
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, cin, *hw, generator=g)
+    for t in ts:
+        with torch.no_grad():
+            y_ref = ref(x, torch.tensor(t)).sample
+        y = net(x.cuda(), torch.tensor(t)).sample.cpu()
+        e = (y - y_ref).abs()
+        err, rms = e.max().item(), e.pow(2).mean().sqrt().item()
+        print(f"{dtype} cin={cin} dc={dc} hw={hw} t={t}: max-abs {err:.3e} rms {rms:.3e} "
+              f"(ref absmax {y_ref.abs().max():.3f})")
+        if dtype == "fp16":
+            assert err <= TOL_NORTH_STAR, err
+        else:
+            assert err <= TOL_BF16_MAX and rms <= TOL_BF16_RMS, (err, rms)
+    # split entry (sample + cond) is the same computation as the concatenated call
+    y2 = net.forward_split(x[:, :dc].contiguous().cuda(), x[:, dc:].contiguous().cuda(), ts[-1]).cpu()
+    assert torch.equal(y2, y)
