@@ -1,0 +1,14 @@
+"""d3roma_b200 — B200-native (sm_100a) implementation of D3RoMa's iterative disparity-denoising loop.
+
+Public surface mirrors the reference's classes for this path (jie0530/d3roma ``core/``):
+``GuidedDiffusionPipeline``, ``MyDDIMScheduler``, ``MyDDPMScheduler``, ``FlowGuidance``, ``UNet2DModel``,
+``Normalizer``, ``InputPadder``.  All arithmetic runs in ``libd3roma_b200.so`` (build: ``python -m d3roma_b200.build``).
+"""
+from .guidance import FlowGuidance  # noqa: F401
+from .pipelines import GuidedDiffusionPipeline, GuidedPipelineOutput  # noqa: F401
+from .prepost import SIM_CAMERA, Camera, InputPadder, Normalizer  # noqa: F401
+from .scheduler_ddim import DDIMSchedulerOutput, MyDDIMScheduler  # noqa: F401
+from .scheduler_ddpm import DDPMSchedulerOutput, MyDDPMScheduler  # noqa: F401
+from .unet import UNet2DModel  # noqa: F401
+
+__version__ = "0.1.0"

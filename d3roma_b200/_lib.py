@@ -84,6 +84,14 @@ def _declare(lib: C.CDLL) -> None:
         "d3_sched_ddim_step": (i32, [vp, vp, vp, C.POINTER(DDIMCoeffs), i64, vp, vp, vp, vp, vp]),
         "d3_sched_ddpm_step": (i32, [vp, vp, vp, C.POINTER(DDPMCoeffs), i64, vp, vp, vp, vp]),
         "d3_lincomb": (i32, [f32, vp, f32, vp, f32, vp, i64, vp, vp]),
+        "d3_guidance_grad": (i32, [vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, f32, vp, vp]),
+        "d3_depth_to_disp": (i32, [vp, f32, i64, vp, vp]),
+        "d3_disp_to_depth": (i32, [vp, f32, i64, vp, vp]),
+        "d3_normalize_disp": (i32, [vp, i64, i64, i32, f32, f32, f32, f32, vp, vp]),
+        "d3_denormalize_disp": (i32, [vp, i64, i64, i32, f32, f32, f32, f32, vp, vp]),
+        "d3_pad_replicate": (i32, [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]),
+        "d3_crop": (i32, [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]),
+        "d3_clamp_into": (i32, [vp, i64, i64, i64, i64, f32, f32, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here == header and library out of sync

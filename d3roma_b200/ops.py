@@ -177,3 +177,122 @@ def attention_hd8(qkv: torch.Tensor, C_: int) -> torch.Tensor:
     _lib.check(_lib.lib().d3_attention_hd8(qkv.data_ptr(), qkv.stride(2), B, H * W, C_, out.data_ptr(),
                                            out.stride(2), _dt(qkv), _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# scheduler / guidance / pre-post wrappers (fp32 NCHW tensors)
+# ------------------------------------------------------------------------------------------------
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise ValueError(f"{name}: expected an fp32 CUDA tensor (got {t.dtype} on {t.device}); "
+                         "the d3roma_b200 path has no CPU fallback")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def sched_ddim_step(model_output, sample, coeffs: "_lib.DDIMCoeffs", variance_noise=None, want_mean=False,
+                    want_dir=False):
+    m, s = _f32c(model_output, "model_output"), _f32c(sample, "sample")
+    noise = None if variance_noise is None else _f32c(variance_noise, "variance_noise")
+    prev, orig = torch.empty_like(s), torch.empty_like(s)
+    mean = torch.empty_like(s) if want_mean else None
+    dirv = torch.empty_like(s) if want_dir else None
+    _lib.check(_lib.lib().d3_sched_ddim_step(m.data_ptr(), s.data_ptr(), _ptr(noise), C.byref(coeffs), s.numel(),
+                                             prev.data_ptr(), orig.data_ptr(), _ptr(mean), _ptr(dirv), _stream()))
+    return prev, orig, mean, dirv
+
+
+def sched_ddpm_step(model_output, sample, coeffs: "_lib.DDPMCoeffs", variance_noise=None, want_mean=False):
+    m, s = _f32c(model_output, "model_output"), _f32c(sample, "sample")
+    noise = None if variance_noise is None else _f32c(variance_noise, "variance_noise")
+    prev, orig = torch.empty_like(s), torch.empty_like(s)
+    mean = torch.empty_like(s) if want_mean else None
+    _lib.check(_lib.lib().d3_sched_ddpm_step(m.data_ptr(), s.data_ptr(), _ptr(noise), C.byref(coeffs), s.numel(),
+                                             prev.data_ptr(), orig.data_ptr(), _ptr(mean), _stream()))
+    return prev, orig, mean
+
+
+def lincomb(a: float, x, b: float = 1.0, y=None, c: float = 0.0, z=None):
+    """a*x (+ b*y) (+ c*z) with every product / sum rounded separately."""
+    x = _f32c(x, "x")
+    y = None if y is None else _f32c(y, "y")
+    z = None if z is None else _f32c(z, "z")
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().d3_lincomb(a, x.data_ptr(), b, _ptr(y), c, _ptr(z), x.numel(), out.data_ptr(), _stream()))
+    return out
+
+
+def guidance_grad(disp_norm, left, right, min_disp: float, max_disp: float, shift: float = 0.0,
+                  w_ssim: float = 0.95):
+    d, l, r = _f32c(disp_norm, "disp_norm"), _f32c(left, "left"), _f32c(right, "right")
+    B, _, H, W = d.shape
+    margin = r.shape[-1] - W
+    if l.shape != r.shape or l.shape[1] != 3 or margin < 0:
+        raise ValueError("guidance_grad: left/right must be [B,3,H,W+margin]")
+    out = torch.empty_like(d)
+    _lib.check(_lib.lib().d3_guidance_grad(d.data_ptr(), l.data_ptr(), r.data_ptr(), B, H, W, margin, min_disp,
+                                           max_disp, shift, w_ssim, out.data_ptr(), _stream()))
+    return out
+
+
+def depth_to_disp(depth, fxb: float):
+    d = _f32c(depth, "depth")
+    out = torch.empty_like(d)
+    _lib.check(_lib.lib().d3_depth_to_disp(d.data_ptr(), fxb, d.numel(), out.data_ptr(), _stream()))
+    return out
+
+
+def disp_to_depth(disp, fxb: float):
+    d = _f32c(disp, "disp")
+    out = torch.empty_like(d)
+    _lib.check(_lib.lib().d3_disp_to_depth(d.data_ptr(), fxb, d.numel(), out.data_ptr(), _stream()))
+    return out
+
+
+def normalize_disp(disp, num_chs: int, bound: float, gamma: float, t: float, s: float):
+    """disp [..., H, W] with leading dims flattened to N -> [N*num_chs, H, W] (caller reshapes)."""
+    d = _f32c(disp, "disp")
+    H, W = d.shape[-2:]
+    N = d.numel() // (H * W)
+    out = torch.empty((N * num_chs, H, W), dtype=torch.float32, device=d.device)
+    _lib.check(_lib.lib().d3_normalize_disp(d.data_ptr(), N, H * W, num_chs, bound, gamma, t, s, out.data_ptr(),
+                                            _stream()))
+    return out
+
+
+def denormalize_disp(y, num_chs: int, bound: float, gamma: float, t: float, s: float):
+    """y [B, R*num_chs, H, W] -> [B, R, H, W]."""
+    y = _f32c(y, "y")
+    B, Cc, H, W = y.shape
+    R = Cc // num_chs
+    out = torch.empty((B, R, H, W), dtype=torch.float32, device=y.device)
+    _lib.check(_lib.lib().d3_denormalize_disp(y.data_ptr(), B * R, H * W, num_chs, bound, gamma, t, s,
+                                              out.data_ptr(), _stream()))
+    return out
+
+
+def pad_replicate(x, pads):
+    """x [B,C,H,W] fp32, pads = [left, right, top, bottom] (InputPadder._pad order)."""
+    x = _f32c(x, "x")
+    B, Cc, H, W = x.shape
+    l, r, t, b = pads
+    out = torch.empty((B, Cc, H + t + b, W + l + r), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().d3_pad_replicate(x.data_ptr(), B * Cc, H, W, l, r, t, b, out.data_ptr(), _stream()))
+    return out
+
+
+def crop(x, top: int, left: int, H: int, W: int):
+    x = _f32c(x, "x")
+    B, Cc, Hi, Wi = x.shape
+    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().d3_crop(x.data_ptr(), B * Cc, Hi, Wi, top, left, H, W, out.data_ptr(), _stream()))
+    return out
+
+
+def clamp_into(x, out, slot: int, lo: float = -1.0, hi: float = 1.0):
+    """out[:, slot*C:(slot+1)*C] = clamp(x, lo, hi) for x [B,C,H,W], out [B,C*T,H,W]."""
+    x = _f32c(x, "x")
+    B, Cc, H, W = x.shape
+    chw = Cc * H * W
+    _lib.check(_lib.lib().d3_clamp_into(x.data_ptr(), B, chw, out.stride(0), slot * chw, lo, hi, out.data_ptr(),
+                                        _stream()))
+    return out

@@ -1,0 +1,144 @@
+"""``GuidedDiffusionPipeline`` — drop-in for the reference's pixel-space denoising loop
+(``/root/reference/core/custom_pipelines.py:90-205``): same constructor, same ``__call__`` signature and positional
+order, same ``GuidedPipelineOutput`` fields, same RNG consumption (x_T drawn with ``randn_tensor`` on the
+generator's device then moved, :117-123), same assertions and ``NotImplementedError`` for unknown
+``cond_channels`` (:158-171).
+
+What differs is how the loop body executes:
+  * the conditioning channels are concatenated ONCE (they are constant across steps) and never concatenated with the
+    noisy sample — the conv_in front end gathers from both tensors (``d3_im2col_input``);
+  * ``unet(model_input, t)`` is one CUDA-graph replay of the sm_100a kernels (``UNet2DModel.forward_graphed``);
+  * ``scheduler.step`` is one fused kernel; the five intermediate-image stacks the reference fills with identical
+    ``image.clamp(-1, 1)`` copies (:176-182) are one tensor written in place and aliased five times.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Union
+
+import torch
+
+from . import ops
+from ._config import BaseOutput
+from .scheduler_ddim import randn_tensor
+
+COND_ORDER = {
+    "rgb": ("rgb",),
+    "rgb+raw": ("rgb", "raw"),
+    "rgb+right": ("left", "right"),          # sic: the reference concatenates left+right for this key (:162-163)
+    "left+right+raw": ("left", "right", "raw"),
+    "rgb+left+right": ("rgb", "left", "right"),
+    "rgb+left+right+raw": ("rgb", "left", "right", "raw"),
+}
+
+
+@dataclass
+class GuidedPipelineOutput(BaseOutput):
+    """custom_pipelines.py:63-85 (field names kept, including the reference's spelling)."""
+
+    images: torch.Tensor
+    images_pred_orig: Optional[torch.Tensor] = None
+    images_perturbed_orig: Optional[torch.Tensor] = None
+    images_pred_prev: Optional[torch.Tensor] = None
+    images_purturbed_pred_prev: Optional[torch.Tensor] = None
+    images_sampled_prev: Optional[torch.Tensor] = None
+
+
+class GuidedDiffusionPipeline:
+    def __init__(self, unet, scheduler, guidance):
+        self.register_modules(unet=unet, scheduler=scheduler, guidance=guidance)
+        self._progress_bar_config = {}
+        self.use_cuda_graph = True
+
+    # ---- DiffusionPipeline-ish plumbing used by the callers (inference.py:71-91,215; evaluate.py:314-317)
+    def register_modules(self, **kwargs):
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    @property
+    def device(self) -> torch.device:
+        return self.unet.device
+
+    def to(self, device):
+        self.unet.to(device)
+        return self
+
+    def set_progress_bar_config(self, **kwargs):
+        self._progress_bar_config = kwargs
+
+    def progress_bar(self, iterable):
+        if self._progress_bar_config.get("disable", True) and "desc" not in self._progress_bar_config:
+            return iterable
+        try:
+            from tqdm.auto import tqdm
+            return tqdm(iterable, **self._progress_bar_config)
+        except Exception:  # pragma: no cover
+            return iterable
+
+    # ---- the loop
+    @torch.no_grad()
+    def __call__(self, rgb_images=None, left_images=None, right_images=None, sim_disp=None, raw_depth=None, mask=None,
+                 num_inference_steps: int = 128, num_intermediate_images: int = 128, add_noise_rgb: bool = False,
+                 depth_channels: int = 1, cond_channels: str = "rgb", denorm: Callable = None,
+                 generator: Optional[Union[torch.Generator, List[torch.Generator]]] = None):
+        """ in & out images are preferably on the same device """
+        assert rgb_images is not None or left_images is not None
+        assert num_intermediate_images > 0 and num_inference_steps % num_intermediate_images == 0
+        plot_every = num_inference_steps // num_intermediate_images
+        image_shape = rgb_images.shape if rgb_images is not None else left_images.shape
+        batch_size = image_shape[0]
+        ss = self.unet.sample_size
+        if type(ss) == int:
+            shape = (batch_size, depth_channels, ss, ss)
+        elif type(ss) == tuple or type(ss) == list:
+            shape = (batch_size, depth_channels, image_shape[-2], image_shape[-1])
+        else:
+            raise ValueError("sample_size must be int or tuple of ints")
+        image = randn_tensor(shape, generator=generator)  # CPU draw (custom_pipelines.py:117-119)
+        dev = self.device
+        image = image.to(dev, torch.float32).contiguous()
+        srcs = {"rgb": rgb_images, "left": left_images, "right": right_images, "raw": sim_disp}
+        srcs = {k: (None if v is None else v.to(dev, torch.float32)) for k, v in srcs.items()}
+        if cond_channels not in COND_ORDER:
+            raise NotImplementedError
+        names = COND_ORDER[cond_channels]
+        if any(srcs[n] is None for n in names):
+            raise ValueError(f"cond_channels={cond_channels!r} needs {names}")
+
+        def build_cond(rgb_override=None):
+            parts = [(rgb_override if (n == "rgb" and rgb_override is not None) else srcs[n]) for n in names]
+            return torch.cat(parts, dim=1).contiguous() if len(parts) > 1 else parts[0].contiguous()
+
+        cond = None if add_noise_rgb else build_cond()
+        self.scheduler.set_timesteps(num_inference_steps)
+        guidance = self.guidance
+        guided = (guidance is not None and getattr(guidance, "flow_guidance_mode", None) == "stereo"
+                  and guidance.flow_guidance_weight > 0.0 and srcs["left"] is not None and srcs["right"] is not None)
+        if guided:
+            guidance.num_train_timesteps = self.scheduler.config.num_train_timesteps
+        n_plots = num_inference_steps // plot_every
+        stack = torch.empty((batch_size, depth_channels * n_plots, shape[2], shape[3]), dtype=torch.float32,
+                            device=dev)
+        fwd = self.unet.forward_graphed if self.use_cuda_graph else self.unet.forward_split
+        step = 0
+        for t in self.progress_bar(self.scheduler.timesteps):
+            if add_noise_rgb:
+                rgb = srcs["rgb"]
+                noise_rgb = torch.randn(rgb.shape).to(rgb.device)
+                timesteps = (t * torch.ones(rgb.shape[0]).to(rgb.device)).long()
+                noisy_rgb = self.scheduler.add_noise(rgb, noise_rgb, timesteps)
+                cond = build_cond(rgb * 0.5 + noisy_rgb * 0.5)
+            model_output = fwd(image, cond, t)
+            if guided:
+                g = self.scheduler.step(model_output, t, image, guidance=guidance, left_image=srcs["left"],
+                                        right_image=srcs["right"], raw_depth=raw_depth)
+            else:
+                g = self.scheduler.step(model_output, t, image)
+            image = g.prev_sample
+            if (step + 1) % plot_every == 0:
+                ops.clamp_into(image, stack, (step + 1) // plot_every - 1)
+            step += 1
+        image = ops.clamp_into(image, torch.empty_like(image), 0)
+        return GuidedPipelineOutput(images=image, images_pred_orig=stack, images_perturbed_orig=stack,
+                                    images_pred_prev=stack, images_purturbed_pred_prev=stack,
+                                    images_sampled_prev=stack)

@@ -117,6 +117,7 @@ class UNet2DModel:
         self._specs = _resnet_specs()
         self._arena: Optional[_StatsArena] = None
         self._loaded = False
+        self._graphs: Dict[tuple, dict] = {}
 
     # ------------------------------------------------------------------ weights
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
@@ -318,6 +319,43 @@ class UNet2DModel:
                 h = self._conv(u, W[p + ".w"], W[p + ".b"], 3, B)
                 del u
         return ops.conv_out_fused(h.t, h.stats, W["out.g"], W["out.b"], W["out.w"], W["out.bias"], self.out_channels)
+
+    @torch.no_grad()
+    def forward_graphed(self, sample: torch.Tensor, cond: Optional[torch.Tensor], timestep) -> torch.Tensor:
+        """Same as ``forward_split`` but replayed from a CUDA graph captured per (B, H, W, Cs, Cc): the ~430 kernel
+        launches of one UNet forward become a single graph launch.  ``timestep`` must be one scalar for the batch.
+        Returns a STATIC output buffer that the next call overwrites (the sampling loop consumes it immediately)."""
+        key = (tuple(sample.shape), None if cond is None else tuple(cond.shape), sample.device.index)
+        g = self._graphs.get(key)
+        tval = float(timestep)
+        if g is None:
+            g = {"x": torch.empty_like(sample), "c": None if cond is None else torch.empty_like(cond),
+                 "t": torch.zeros(1, dtype=torch.float32, device=sample.device)}
+            g["x"].copy_(sample)
+            if cond is not None:
+                g["c"].copy_(cond)
+            g["t"].fill_(tval)
+            side = torch.cuda.Stream(device=sample.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.forward_split(g["x"], g["c"], g["t"])  # warm-up: function attributes, arena, allocator
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g["y"] = self.forward_split(g["x"], g["c"], g["t"])
+            g["graph"] = graph
+            g["cond_src"] = None
+            self._graphs[key] = g
+        g["x"].copy_(sample)
+        if cond is not None and g["cond_src"] is not cond:
+            g["c"].copy_(cond)  # conditioning is constant across the steps of one sampling loop: copy once
+            g["cond_src"] = cond
+        g["t"].fill_(tval)
+        g["graph"].replay()
+        return g["y"]
+
+    def reset_graphs(self):
+        self._graphs.clear()
 
     @torch.no_grad()
     def __call__(self, sample: torch.Tensor, timestep, return_dict: bool = True):

@@ -67,7 +67,7 @@ typedef struct d3_conv_params {
   int32_t C1, sc1_pitch;
   const void* sc2;     /* optional second shortcut source (virtual concat)                           */
   int32_t C2, sc2_pitch;
-  const float* bias;   /* fp32 [Cout] (bias_bstride 0) or [B][Cout] (bias_bstride = Cout)            */
+  const float* bias;   /* fp32 [Cout] (bias_bstride 0) or [B][Cout] (bias_bstride = row stride in elements)            */
   int32_t bias_bstride;
   const void* residual; /* optional bf16 NHWC [B,Ho,Wo,Cout] identity residual                       */
   int32_t res_pitch;
@@ -156,6 +156,35 @@ int d3_sched_ddpm_step(const float* model_output, const float* sample, const flo
  * perturbation of x0: scheduler_ddim.py:468, scheduler_ddpm.py:512). y, z may be NULL. */
 int d3_lincomb(float a, const float* x, float b, const float* y, float c, const float* z, int64_t n, float* out,
                void* stream);
+
+/* ---- stereo photometric guidance gradient (FlowGuidance.grad stereo branch, core/guidance.py:298-323 + SSIM :28-42)
+ * grad[b,0,y,x] = d/d(disp_norm) [ w_ssim * sum SSIM_loss(left, warp) + (1 - w_ssim) * sum |left - warp| ],
+ * warp = right sampled at x - clip(min_disp + (disp_norm - shift) * (max_disp - min_disp)) (bilinear, border).
+ * disp_norm fp32 [B,1,H,W]; left, right fp32 [B,3,H,W+margin]. Replaces ~50 autograd launches by one kernel. */
+int d3_guidance_grad(const float* disp_norm, const float* left, const float* right, int B, int H, int W, int margin,
+                     float min_disp, float max_disp, float shift, float w_ssim, float* grad, void* stream);
+
+/* ---- pre/post-processing (fp32, elementwise) -------------------------------------------------
+ * inference.py:128-131 / 246-249: out = fxb / in where in > 0 else 0. */
+int d3_depth_to_disp(const float* depth, float fxb, int64_t n, float* disp, void* stream);
+int d3_disp_to_depth(const float* disp, float fxb, int64_t n, float* depth, void* stream);
+/* Normalizer (ssi=False, mode="average"; utils_d3roma/utils.py:183-196): disp [N][HW] -> out [N][num_chs][HW],
+ * ((min(x, bound) / bound) ** gamma - t) * s replicated over num_chs. */
+int d3_normalize_disp(const float* disp, int64_t N, int64_t HW, int num_chs, float bound, float gamma, float t,
+                      float s, float* out, void* stream);
+/* Normalizer.denormalize (utils.py:252-273): y [NR][num_chs][HW] -> out [NR][HW],
+ * sum_c (y_c / s + t) ** (1/gamma) * (bound / num_chs). */
+int d3_denormalize_disp(const float* y, int64_t NR, int64_t HW, int num_chs, float bound, float gamma, float t,
+                        float s, float* out, void* stream);
+/* InputPadder.pad (replicate) / unpad (utils.py:313-325) over `planes` = B*C planes of H x W. */
+int d3_pad_replicate(const float* in, int64_t planes, int H, int W, int left, int right, int top, int bottom,
+                     float* out, void* stream);
+int d3_crop(const float* in, int64_t planes, int Hin, int Win, int top, int left, int H, int W, float* out,
+            void* stream);
+/* out[b][out_off + i] = clamp(in[b][i], lo, hi), i < chw (custom_pipelines.py:176-182,196: image.clamp(-1,1) written
+ * straight into its slot of the intermediate-image stack). */
+int d3_clamp_into(const float* in, int64_t B, int64_t chw, int64_t out_bstride, int64_t out_off, float lo, float hi,
+                  float* out, void* stream);
 
 #ifdef __cplusplus
 }

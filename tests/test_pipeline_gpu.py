@@ -1,0 +1,116 @@
+"""End-to-end parity of the drop-in pipeline (GuidedDiffusionPipeline + UNet2DModel + schedulers on the CUDA path)
+against (a) golden outputs of the reference's own pipeline class (tests/golden/pipeline.npz) and (b) the oracle."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = Path(__file__).parent / "golden"
+
+DDIM_CFG = dict(num_train_timesteps=128, beta_schedule="squaredcos_cap_v2", prediction_type="sample",
+                clip_sample=True, set_alpha_to_one=False, steps_offset=1)
+DDPM_CFG = dict(num_train_timesteps=128, beta_schedule="squaredcos_cap_v2", prediction_type="sample",
+                thresholding=True, clip_sample=True)
+
+
+def _make(dtype, hw=(32, 64), cin=8, dc=1):
+    import d3roma_b200 as d
+    from oracle.unet_ref import make_unet
+    ref = make_unet(cin, dc, seed=0, sample_size=hw)
+    net = d.UNet2DModel(sample_size=hw, in_channels=cin, out_channels=dc, compute_dtype=dtype).to("cuda")
+    net.load_state_dict(ref.state_dict())
+    return d, ref, net
+
+
+@pytest.mark.parametrize("dtype,tol_step,tol_img", [("fp16", 1e-2, 1e-2), ("bf16", 2e-2, 3e-2)])
+@pytest.mark.parametrize("graph", [False, True])
+def test_ddim_pipeline_vs_reference_golden(dtype, tol_step, tol_img, graph):
+    d, ref, net = _make(dtype)
+    z = np.load(G / "pipeline.npz")
+    pipe = d.GuidedDiffusionPipeline(net, d.MyDDIMScheduler.from_config(DDIM_CFG), d.FlowGuidance(flow_guidance_weight=0.0))
+    pipe.use_cuda_graph = graph
+    left, right, raw = (torch.from_numpy(z[k]) for k in ("left", "right", "raw"))
+    out = pipe(None, left, right, raw, None, None, num_inference_steps=10, num_intermediate_images=2,
+               depth_channels=1, cond_channels="left+right+raw", generator=torch.Generator().manual_seed(42))
+    img = out.images.cpu().numpy()
+    err = np.abs(img - z["ddim10/images"]).max()
+    print(f"{dtype} graph={graph}: final-image max-abs err {err:.3e}")
+    assert err <= tol_img
+    assert out.images_pred_orig.shape == (1, 2, 32, 64) and out.images_sampled_prev is out.images_pred_orig
+    np.testing.assert_allclose(out.images_pred_orig.cpu().numpy()[:, 1:], img, atol=0)  # last slot == final image
+    assert np.abs(out.images_pred_orig.cpu().numpy() - z["ddim10/intermediate"]).max() <= tol_img
+    # per-step model output parity when fed the reference's own trajectory (teacher forcing)
+    sch = d.MyDDIMScheduler.from_config(DDIM_CFG)
+    sch.set_timesteps(10)
+    x = torch.randn((1, 1, 32, 64), generator=torch.Generator().manual_seed(42)).cuda()
+    cond = torch.cat([left, right, raw], 1).cuda()
+    worst = 0.0
+    for i, t in enumerate(sch.timesteps):
+        m = net.forward_split(x, cond, t)
+        worst = max(worst, float((m.cpu() - torch.from_numpy(z["ddim10/model_outputs"][i])).abs().max()))
+        x = sch.step(torch.from_numpy(z["ddim10/model_outputs"][i]).cuda(), t, x).prev_sample
+    print(f"{dtype}: worst per-step model-output max-abs err {worst:.3e}")
+    assert worst <= tol_step
+
+
+def test_ddpm_pipeline_vs_reference_golden():
+    d, ref, net = _make("fp16")
+    z = np.load(G / "pipeline.npz")
+    pipe = d.GuidedDiffusionPipeline(net, d.MyDDPMScheduler.from_config(DDPM_CFG), d.FlowGuidance(flow_guidance_weight=0.0))
+    left, right, raw = (torch.from_numpy(z[k]) for k in ("left", "right", "raw"))
+    # the reference draws the DDPM variance noise from the DEVICE default generator (CPU in the golden run); feed the
+    # same stream through a CPU generator list trick: seed the global CPU generator and draw on CPU per step.
+    import d3roma_b200.scheduler_ddpm as sd
+    torch.manual_seed(99)
+    orig = sd.randn_tensor
+    sd.randn_tensor = lambda shape, generator=None, device=None, dtype=None: torch.randn(tuple(shape), dtype=dtype).to(device)
+    try:
+        out = pipe(None, left, right, raw, None, None, num_inference_steps=8, num_intermediate_images=2,
+                   depth_channels=1, cond_channels="left+right+raw", generator=torch.Generator().manual_seed(42))
+    finally:
+        sd.randn_tensor = orig
+    err = np.abs(out.images.cpu().numpy() - z["ddpm8/images"]).max()
+    print(f"ddpm8 fp16: final-image max-abs err {err:.3e}")
+    assert err <= 1e-2
+
+
+def test_pipeline_contract_and_variants():
+    d, ref, net = _make("fp16", cin=5)
+    pipe = d.GuidedDiffusionPipeline(net, d.MyDDIMScheduler.from_config(DDIM_CFG), d.FlowGuidance(flow_guidance_weight=0.0))
+    g = torch.Generator().manual_seed(0)
+    rgb, raw = torch.rand(2, 3, 32, 64, generator=g) * 2 - 1, torch.rand(2, 1, 32, 64, generator=g) * 2 - 1
+    out = pipe(rgb, None, None, raw, None, None, num_inference_steps=4, num_intermediate_images=4,
+               cond_channels="rgb+raw", generator=torch.Generator().manual_seed(1))
+    assert out.images.shape == (2, 1, 32, 64) and out.images_pred_orig.shape == (2, 4, 32, 64)
+    assert float(out.images.abs().max()) <= 1.0 and out.images.is_cuda
+    # per-sample generators make the result independent of how the batch is sharded
+    gens = [torch.Generator().manual_seed(100 + i) for i in range(2)]
+    full = pipe(rgb, None, None, raw, None, None, num_inference_steps=4, num_intermediate_images=1,
+                cond_channels="rgb+raw", generator=gens).images
+    gens = [torch.Generator().manual_seed(100 + i) for i in range(2)]
+    parts = [pipe(rgb[i:i + 1], None, None, raw[i:i + 1], None, None, num_inference_steps=4, num_intermediate_images=1,
+                  cond_channels="rgb+raw", generator=[gens[i]]).images for i in range(2)]
+    assert torch.equal(full, torch.cat(parts))
+    with pytest.raises(NotImplementedError):
+        pipe(rgb, None, None, raw, cond_channels="bogus", num_inference_steps=4, num_intermediate_images=4)
+    with pytest.raises(AssertionError):
+        pipe(None, None, None, raw, num_inference_steps=4, num_intermediate_images=4)
+    with pytest.raises(AssertionError):
+        pipe(rgb, None, None, raw, num_inference_steps=10, num_intermediate_images=4)
+
+
+def test_guided_pipeline_runs_and_differs():
+    d, ref, net = _make("fp16")
+    g = torch.Generator().manual_seed(3)
+    left = torch.rand(1, 3, 32, 64, generator=g) * 2 - 1
+    right = torch.roll(left, -3, dims=-1)
+    raw = torch.rand(1, 1, 32, 64, generator=g) * 2 - 1
+    outs = []
+    for w in (0.0, 1e-3):
+        fg = d.FlowGuidance(flow_guidance_weight=w, flow_guidance_mode="stereo")
+        pipe = d.GuidedDiffusionPipeline(net, d.MyDDIMScheduler.from_config(DDIM_CFG), fg)
+        outs.append(pipe(None, left, right, raw, None, None, num_inference_steps=4, num_intermediate_images=1,
+                         cond_channels="left+right+raw", generator=torch.Generator().manual_seed(9)).images)
+    assert torch.isfinite(outs[1]).all() and not torch.equal(outs[0], outs[1])
