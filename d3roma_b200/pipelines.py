@@ -75,7 +75,53 @@ class GuidedDiffusionPipeline:
         except Exception:  # pragma: no cover
             return iterable
 
-    # ---- the loop
+    # ---- the loop body, on device-resident tensors
+    @torch.no_grad()
+    def _loop(self, image, cond, srcs, build_cond, num_inference_steps, plot_every, add_noise_rgb, raw_depth):
+        """custom_pipelines.py:134-196 for tensors already on the device. Returns (clamped image, intermediates)."""
+        dev = image.device
+        batch_size, depth_channels = image.shape[:2]
+        self.scheduler.set_timesteps(num_inference_steps)
+        guidance = self.guidance
+        guided = (guidance is not None and getattr(guidance, "flow_guidance_mode", None) == "stereo"
+                  and guidance.flow_guidance_weight > 0.0 and srcs.get("left") is not None
+                  and srcs.get("right") is not None)
+        if guided:
+            guidance.num_train_timesteps = self.scheduler.config.num_train_timesteps
+        n_plots = num_inference_steps // plot_every
+        stack = torch.empty((batch_size, depth_channels * n_plots, image.shape[2], image.shape[3]),
+                            dtype=torch.float32, device=dev)
+        fwd = self.unet.forward_graphed if self.use_cuda_graph else self.unet.forward_split
+        step = 0
+        for t in self.progress_bar(self.scheduler.timesteps):
+            if add_noise_rgb:
+                rgb = srcs["rgb"]
+                noise_rgb = torch.randn(rgb.shape).to(rgb.device)
+                timesteps = (t * torch.ones(rgb.shape[0]).to(rgb.device)).long()
+                noisy_rgb = self.scheduler.add_noise(rgb, noise_rgb, timesteps)
+                cond = build_cond(rgb * 0.5 + noisy_rgb * 0.5)
+            model_output = fwd(image, cond, t)
+            if guided:
+                g = self.scheduler.step(model_output, t, image, guidance=guidance, left_image=srcs["left"],
+                                        right_image=srcs["right"], raw_depth=raw_depth)
+            else:
+                g = self.scheduler.step(model_output, t, image)
+            image = g.prev_sample
+            if (step + 1) % plot_every == 0:
+                ops.clamp_into(image, stack, (step + 1) // plot_every - 1)
+            step += 1
+        image = ops.clamp_into(image, torch.empty_like(image), 0)
+        return image, stack
+
+    @torch.no_grad()
+    def sample_from(self, x_T: torch.Tensor, cond: torch.Tensor, num_inference_steps: int = 10,
+                    left_images=None, right_images=None) -> torch.Tensor:
+        """Device-resident entry: start noise ``x_T`` [B,dc,H,W] and pre-concatenated conditioning ``cond``
+        [B,Cc,H,W] already in HBM (fp32, contiguous). Returns the clamped final sample."""
+        srcs = {"left": left_images, "right": right_images}
+        image, _ = self._loop(x_T, cond, srcs, None, num_inference_steps, num_inference_steps, False, None)
+        return image
+
     @torch.no_grad()
     def __call__(self, rgb_images=None, left_images=None, right_images=None, sim_disp=None, raw_depth=None, mask=None,
                  num_inference_steps: int = 128, num_intermediate_images: int = 128, add_noise_rgb: bool = False,
@@ -110,35 +156,8 @@ class GuidedDiffusionPipeline:
             return torch.cat(parts, dim=1).contiguous() if len(parts) > 1 else parts[0].contiguous()
 
         cond = None if add_noise_rgb else build_cond()
-        self.scheduler.set_timesteps(num_inference_steps)
-        guidance = self.guidance
-        guided = (guidance is not None and getattr(guidance, "flow_guidance_mode", None) == "stereo"
-                  and guidance.flow_guidance_weight > 0.0 and srcs["left"] is not None and srcs["right"] is not None)
-        if guided:
-            guidance.num_train_timesteps = self.scheduler.config.num_train_timesteps
-        n_plots = num_inference_steps // plot_every
-        stack = torch.empty((batch_size, depth_channels * n_plots, shape[2], shape[3]), dtype=torch.float32,
-                            device=dev)
-        fwd = self.unet.forward_graphed if self.use_cuda_graph else self.unet.forward_split
-        step = 0
-        for t in self.progress_bar(self.scheduler.timesteps):
-            if add_noise_rgb:
-                rgb = srcs["rgb"]
-                noise_rgb = torch.randn(rgb.shape).to(rgb.device)
-                timesteps = (t * torch.ones(rgb.shape[0]).to(rgb.device)).long()
-                noisy_rgb = self.scheduler.add_noise(rgb, noise_rgb, timesteps)
-                cond = build_cond(rgb * 0.5 + noisy_rgb * 0.5)
-            model_output = fwd(image, cond, t)
-            if guided:
-                g = self.scheduler.step(model_output, t, image, guidance=guidance, left_image=srcs["left"],
-                                        right_image=srcs["right"], raw_depth=raw_depth)
-            else:
-                g = self.scheduler.step(model_output, t, image)
-            image = g.prev_sample
-            if (step + 1) % plot_every == 0:
-                ops.clamp_into(image, stack, (step + 1) // plot_every - 1)
-            step += 1
-        image = ops.clamp_into(image, torch.empty_like(image), 0)
+        image, stack = self._loop(image, cond, srcs, build_cond, num_inference_steps, plot_every, add_noise_rgb,
+                                  raw_depth)
         return GuidedPipelineOutput(images=image, images_pred_orig=stack, images_perturbed_orig=stack,
                                     images_pred_prev=stack, images_purturbed_pred_prev=stack,
                                     images_sampled_prev=stack)

@@ -118,6 +118,7 @@ class UNet2DModel:
         self._arena: Optional[_StatsArena] = None
         self._loaded = False
         self._graphs: Dict[tuple, dict] = {}
+        self.graph_kernel_launches = 0  # kernels executed through CUDA-graph replays (for launch accounting)
 
     # ------------------------------------------------------------------ weights
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
@@ -341,8 +342,11 @@ class UNet2DModel:
                 self.forward_split(g["x"], g["c"], g["t"])  # warm-up: function attributes, arena, allocator
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
+            from . import _lib
+            n0 = _lib.lib().d3_launch_count()
             with torch.cuda.graph(graph):
                 g["y"] = self.forward_split(g["x"], g["c"], g["t"])
+            g["n_kernels"] = int(_lib.lib().d3_launch_count() - n0)
             g["graph"] = graph
             g["cond_src"] = None
             self._graphs[key] = g
@@ -352,6 +356,7 @@ class UNet2DModel:
             g["cond_src"] = cond
         g["t"].fill_(tval)
         g["graph"].replay()
+        self.graph_kernel_launches += g["n_kernels"]
         return g["y"]
 
     def reset_graphs(self):
