@@ -16,6 +16,8 @@
 // Replaces aten::conv2d (cuDNN) for every 3x3 / 1x1 conv with Cin % 64 == 0 and Cout % 128 == 0
 // (reference call sites: diffusers ResnetBlock2D / Downsample2D / Upsample2D / Attention linears, built at
 // /root/reference/train.py:788-810).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "internal.h"
 #include "tensormap.h"
@@ -42,6 +44,7 @@ struct ConvKArgs {
   int res_pitch;
   double* stats;
   uint32_t a_bytes;
+  int debug_skip;  // developer experiment: bit0 = skip A loads, bit1 = skip B loads (results are garbage)
 };
 
 struct TileCoord {
@@ -186,6 +189,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * kStageBytes;
           uint8_t* sB = sA + kATileBytes;
+          if (a.debug_skip) {
+            const uint32_t bytes = ((a.debug_skip & 1) ? 0u : a.a_bytes) + ((a.debug_skip & 2) ? 0u : kBBytes);
+            if (bytes) mbar_arrive_expect_tx(&full_bar[stage], bytes); else mbar_arrive(&full_bar[stage]);
+            if (!(a.debug_skip & 1)) tma_load_4d(sA, &tmA, &full_bar[stage], 0, t.w0, t.h0, t.b);
+            if (!(a.debug_skip & 2)) tma_load_2d(sB, &tmB, &full_bar[stage], kb * 64, t.n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], a.a_bytes + kBBytes);
           if (kb < a.kbMain) {
             const int tap = kb / a.cbMain;
@@ -264,6 +275,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool valid = (th < a.TH) && (h < a.Ho) && (w < a.Wo);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (a.debug_skip & 4) {  // developer experiment: no epilogue work at all
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 64; ++c) {
         uint32_t v0[32], v1[32];
@@ -327,6 +346,322 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 template <int BN, int STAGES>
 constexpr size_t conv_smem_bytes() {
   return 1024 + STAGES * (kATileBytes + BN * 128) + 2 * kStagingBytes + (2 * STAGES + 4) * 8 + 16 + 4 * 32 * 4;
+}
+
+
+// =====================================================================================================================
+// "Pixels-as-N" variant for Cout tiles of exactly 128 channels (54 % of the UNet's FLOPs: every 128-channel layer).
+//
+// A single-CTA tcgen05.mma with N = 128 has to fetch 8 KB of smem operands every 64 clk (128 B/clk) and measures at
+// ~50 % of the N = 256 rate on B200 (profiles/r01_conv_experiments.txt).  Swapping the operand roles puts the WEIGHTS
+// on the M side (M = 128 output channels) and up to 256 PIXELS on the N side, so each instruction moves 12 KB per
+// 128 clk (96 B/clk) like the BN = 256 kernel.  The accumulator is then D[channel lane][pixel column]; the epilogue
+// transposes through the swizzled staging tile (2-byte stores, conflict-free) before the TMA store, and the per-channel
+// GroupNorm partial sums become per-thread running sums (no shuffles except the final quad combine).
+// =====================================================================================================================
+constexpr uint32_t kWTileBytes = 128 * 128;          // 128 output channels x 64 k
+constexpr uint32_t kPTileBytes = 256 * 128;          // up to 256 pixels x 64 k
+constexpr uint32_t kTStageBytes = kWTileBytes + kPTileBytes;
+constexpr uint32_t kTStagingBytes = 2 * kStagingBytes;  // 128 pixels x 128 channels (two 64-channel halves)
+
+
+// One 32-pixel chunk of the pixels-as-N epilogue for one channel (thread): + bias (+ residual read back from the
+// staging tile), round to 16 bit, store at [pixel row][channel] of the SWIZZLE_128B staging tile, accumulate the
+// channel's sum / sum-of-squares over in-image pixels.
+template <int DT, bool HAS_RES, int J = 0>
+D3_DEVINL void epi_t_chunk(const uint32_t (&v)[32], uint32_t sa, const uint32_t (&swz)[8], float bias, uint32_t vmask,
+                           float& s_sum, float& s_sq) {
+  if constexpr (J < 32) {
+    const uint32_t addr = sa + swz[J & 7];
+    float x = __uint_as_float(v[J]) + bias;
+    if constexpr (HAS_RES) x += unpack2<DT>(lds_u16<J * 128>(addr)).x;
+    const uint32_t pk = pack2<DT>(x, 0.f);
+    sts_u16<J * 128>(addr, pk);
+    const float xr = ((vmask >> J) & 1u) ? unpack2<DT>(pk & 0xFFFFu).x : 0.f;
+    s_sum += xr;
+    s_sq = fmaf(xr, xr, s_sq);
+    epi_t_chunk<DT, HAS_RES, J + 1>(v, sa, swz, bias, vmask, s_sum, s_sq);
+  }
+}
+
+template <int STAGES, int DT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS1,
+                    const __grid_constant__ CUtensorMap tmS2, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
+                    const ConvKArgs a) {
+  constexpr uint32_t kTmemCols = 512;  // 2 accumulator stages x 256 pixel columns
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + STAGES * kTStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kTStagingBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* res_bar = tempty_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 1);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const int NP = a.TH * a.TW;                 // pixels per tile (<= 256)
+  const uint32_t n_mma = (NP + 15) & ~15;     // MMA N (multiple of 16)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    mbar_init(res_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(a, tile, 128);
+        for (int kb = 0; kb < a.kbTotal; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sW = smem + stage * kTStageBytes;
+          uint8_t* sP = sW + kWTileBytes;
+          if (a.debug_skip & 3) {
+            const uint32_t bytes = ((a.debug_skip & 1) ? 0u : a.a_bytes) + ((a.debug_skip & 2) ? 0u : kWTileBytes);
+            if (bytes) mbar_arrive_expect_tx(&full_bar[stage], bytes); else mbar_arrive(&full_bar[stage]);
+            if (!(a.debug_skip & 1)) tma_load_4d(sP, &tmA, &full_bar[stage], 0, t.w0, t.h0, t.b);
+            if (!(a.debug_skip & 2)) tma_load_2d(sW, &tmB, &full_bar[stage], kb * 64, t.n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          mbar_arrive_expect_tx(&full_bar[stage], a.a_bytes + kWTileBytes);
+          if (kb < a.kbMain) {
+            const int tap = kb / a.cbMain;
+            const int cb = kb - tap * a.cbMain;
+            const int kh = tap / a.ksize;
+            const int kw = tap - kh * a.ksize;
+            if (a.stride == 1) {
+              tma_load_4d(sP, &tmA, &full_bar[stage], cb * 64, t.w0 + kw - a.pad, t.h0 + kh - a.pad, t.b);
+            } else {
+              const int dh = kh - 1, dw = kw - 1;
+              const int hh = t.h0 + (dh < 0 ? -1 : 0), ph = (dh == 0) ? 0 : 1;
+              const int ww = t.w0 + (dw < 0 ? -1 : 0), pw = (dw == 0) ? 0 : 1;
+              tma_load_5d(sP, &tmA, &full_bar[stage], pw * a.sc_off2 + cb * 64, ww, ph, hh, t.b);
+            }
+          } else if (kb < a.kbMain + a.kbSc1) {
+            tma_load_4d(sP, &tmS1, &full_bar[stage], (kb - a.kbMain) * 64, t.w0, t.h0, t.b);
+          } else {
+            tma_load_4d(sP, &tmS2, &full_bar[stage], (kb - a.kbMain - a.kbSc1) * 64, t.w0, t.h0, t.b);
+          }
+          tma_load_2d(sW, &tmB, &full_bar[stage], kb * 64, t.n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_16bit(kTileM, n_mma, DT == kBF16);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < a.kbTotal; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sW = smem_u32(smem + stage * kTStageBytes);
+          const uint64_t adesc = make_sw128_kmajor_desc(sW);                 // weights: M = 128 channels
+          const uint64_t bdesc = make_sw128_kmajor_desc(sW + kWTileBytes);   // pixels:  N = n_mma
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const uint32_t q = warp - 4;
+    const uint32_t et = threadIdx.x - 128;
+    const uint32_t ch = q * 32 + lane;          // channel inside the 128-channel tile == TMEM lane
+    const uint32_t half = ch >> 6;              // which 64-channel staging half
+    const uint32_t ch16 = (ch & 63) >> 3;       // 16-byte chunk of this channel inside the 128-byte row
+    const uint32_t chb = (ch & 7) * 2;          // byte inside the chunk
+    uint8_t* sbase = staging + half * kStagingBytes;
+    const uint32_t sbase_u32 = smem_u32(sbase) + chb;
+    uint32_t swz[8];  // swizzled 16-byte chunk offset of this channel for row (pixel) index % 8
+#pragma unroll
+    for (int i = 0; i < 8; ++i) swz[i] = (ch16 ^ (uint32_t)i) << 4;
+    const bool has_res = a.residual != nullptr;
+    const int passes = (a.TH % 2 == 0) ? 2 : 1;
+    const int pass_rows = a.TH / passes;
+    const int pass_px = pass_rows * a.TW;       // <= 128
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t res_phase = 0;
+    for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(a, tile, 128);
+      const float bias = a.bias[(size_t)t.b * a.bias_bstride + t.n0 + ch];
+      float s_sum = 0.f, s_sq = 0.f;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      if (a.debug_skip & 4) {  // developer experiment: no epilogue work at all
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
+      for (int ps = 0; ps < passes; ++ps) {
+        const int h_pass = t.h0 + ps * pass_rows;
+        // staging is free once the previous TMA store has finished READING it
+        if (et == 0) {
+          tma_store_wait_read<0>();
+          if (a.residual != nullptr) {
+            mbar_arrive_expect_tx(res_bar, 2u * (uint32_t)pass_px * 128u);
+            tma_load_4d(staging, &tmR, res_bar, t.n0, t.w0, h_pass, t.b);
+            tma_load_4d(staging + kStagingBytes, &tmR, res_bar, t.n0 + 64, t.w0, h_pass, t.b);
+          }
+        }
+        named_bar_sync(1, 128);
+        if (a.residual != nullptr) {
+          mbar_wait(res_bar, res_phase);
+          res_phase ^= 1;
+        }
+        for (int c0 = 0; c0 < pass_px; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * 256 + ps * pass_px + c0, v);
+          // validity of the 32 pixels of this chunk: one division per lane, shared through a ballot
+          uint32_t vmask;
+          {
+            const int px = c0 + (int)lane;
+            const int pr = px / a.TW;
+            const int pw = px - pr * a.TW;
+            vmask = __ballot_sync(0xffffffffu, (px < pass_px) && (h_pass + pr < a.Ho) && (t.w0 + pw < a.Wo));
+          }
+          // rows c0 .. c0+31 of the 128-row staging tile (rows beyond pass_px are written but never stored)
+          const uint32_t sa = sbase_u32 + (uint32_t)c0 * 128u;
+          tmem_ld_wait();
+          if (has_res) {
+            epi_t_chunk<DT, true>(v, sa, swz, bias, vmask, s_sum, s_sq);
+          } else {
+            epi_t_chunk<DT, false>(v, sa, swz, bias, vmask, s_sum, s_sq);
+          }
+        }
+        if (ps == passes - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (et == 0) {
+          tma_store_4d(&tmO, staging, t.n0, t.w0, h_pass, t.b);
+          tma_store_4d(&tmO, staging + kStagingBytes, t.n0 + 64, t.w0, h_pass, t.b);
+          tma_store_commit();
+        }
+      }
+      if (a.stats != nullptr) {
+        // quad = 4 consecutive channels = 4 consecutive lanes
+        s_sum += __shfl_xor_sync(0xffffffffu, s_sum, 1);
+        s_sq += __shfl_xor_sync(0xffffffffu, s_sq, 1);
+        s_sum += __shfl_xor_sync(0xffffffffu, s_sum, 2);
+        s_sq += __shfl_xor_sync(0xffffffffu, s_sq, 2);
+        if ((lane & 3) == 0 && t.b < a.B) {
+          double* dst = a.stats + ((size_t)t.b * (a.Cout >> 2) + ((t.n0 + ch) >> 2)) * 2;
+          atomicAdd(dst, (double)s_sum);
+          atomicAdd(dst + 1, (double)s_sq);
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int STAGES>
+constexpr size_t conv_t_smem_bytes() {
+  return 1024 + STAGES * kTStageBytes + kTStagingBytes + (2 * STAGES + 5) * 8 + 16;
+}
+
+template <int STAGES, int DT>
+cudaError_t launch_conv_t(int grid, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmS1,
+                          const CUtensorMap& tmS2, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                          const CUtensorMap& tmR, const ConvKArgs& a) {
+  constexpr size_t smem = conv_t_smem_bytes<STAGES>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_t_kernel<STAGES, DT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  conv_igemm_t_kernel<STAGES, DT><<<grid, kThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, tmR, a);
+  return cudaSuccess;
+}
+
+// Pixel tile for the pixels-as-N kernel: TH*TW <= 256, epilogue passes of <= 128 pixels (TH even, or TH == 1).
+void choose_tile_t(int Ho, int Wo, int* TH, int* TW) {
+  double best = -1.0;
+  int bh = 1, bw = 1;
+  for (int tw = 1; tw <= 256 && tw <= Wo; ++tw) {
+    int th = 256 / tw;
+    if (th > Ho) th = Ho;
+    if (th > 1 && (th & 1)) --th;
+    if (th < 1) continue;
+    const int pass_px = (th % 2 == 0) ? th * tw / 2 : th * tw;
+    if (pass_px > 128) continue;
+    const double tiles = double(ceil_div(Ho, th)) * ceil_div(Wo, tw);
+    const double eff = double(Ho) * Wo / (tiles * 256.0);
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > bw)) {
+      best = eff;
+      bh = th;
+      bw = tw;
+    }
+  }
+  *TH = bh;
+  *TW = bw;
 }
 
 template <int BN, int STAGES, int DT>
@@ -394,7 +729,11 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   a.Ho = Ho;
   a.Wo = Wo;
   a.Cout = p->Cout;
-  choose_tile(Ho, Wo, &a.TH, &a.TW);
+  // Cout == 128 layers run the pixels-as-N kernel (weights on the M side); see conv_igemm_t_kernel.
+  static int no_t = -1;
+  if (no_t < 0) { const char* e = getenv("D3_CONV_NO_T"); no_t = e ? atoi(e) : 0; }
+  const bool use_t = (p->Cout == 128) && !no_t;
+  if (use_t) choose_tile_t(Ho, Wo, &a.TH, &a.TW); else choose_tile(Ho, Wo, &a.TH, &a.TW);
   a.tilesH = ceil_div(Ho, a.TH);
   a.tilesW = ceil_div(Wo, a.TW);
   const int pixTiles = p->B * a.tilesH * a.tilesW;
@@ -418,10 +757,16 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   a.res_pitch = p->res_pitch;
   a.stats = p->stats;
   a.a_bytes = static_cast<uint32_t>(a.TH * a.TW * 128);
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("D3_CONV_DEBUG_SKIP"); dbg = e ? atoi(e) : 0; }
+    a.debug_skip = dbg;
+  }
   D3_REQUIRE((p->sc1 ? p->C1 : 0) + (p->sc2 ? p->C2 : 0) == p->C1 + p->C2, "conv: C1/C2 set without pointers");
 
-  CUtensorMap tmA, tmS1, tmS2, tmB, tmO;
+  CUtensorMap tmA, tmS1, tmS2, tmB, tmO, tmR;
   int rc = 0;
+  const int store_rows = use_t ? ((a.TH % 2 == 0) ? a.TH / 2 : a.TH) : a.TH;  // rows per TMA store box
   if (p->stride == 1) {
     uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
     uint64_t str[3] = {(uint64_t)p->x_pitch * 2, (uint64_t)p->W * p->x_pitch * 2,
@@ -466,14 +811,25 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
     uint64_t dims[4] = {(uint64_t)p->Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)p->B};
     uint64_t str[3] = {(uint64_t)p->out_pitch * 2, (uint64_t)Wo * p->out_pitch * 2,
                        (uint64_t)Ho * Wo * p->out_pitch * 2};
-    uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
+    uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)store_rows, 1};
     if ((rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmO, p->out, 4, dims, str, box)))
       return set_error(D3_ERR_CUDA, "conv: tensor map O encode failed (%d)", rc);
+    tmR = tmO;
+    if (use_t && p->residual) {
+      uint64_t rstr[3] = {(uint64_t)p->res_pitch * 2, (uint64_t)Wo * p->res_pitch * 2,
+                          (uint64_t)Ho * Wo * p->res_pitch * 2};
+      if ((rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmR, p->residual, 4, dims, rstr, box)))
+        return set_error(D3_ERR_CUDA, "conv: tensor map R encode failed (%d)", rc);
+    }
   }
 
   const int grid = a.numTiles < num_sms() ? a.numTiles : num_sms();
   cudaError_t le = cudaSuccess;
-  if (BN == 128 && p->dtype == D3_DTYPE_BF16)
+  if (use_t && p->dtype == D3_DTYPE_BF16)
+    le = launch_conv_t<4, kBF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, tmR, a);
+  else if (use_t)
+    le = launch_conv_t<4, kF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, tmR, a);
+  else if (BN == 128 && p->dtype == D3_DTYPE_BF16)
     le = launch_conv<128, 5, kBF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, a);
   else if (BN == 128)
     le = launch_conv<128, 5, kF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, a);

@@ -18,7 +18,7 @@ namespace d3 {
 namespace {
 
 constexpr int kGnThreads = 256;
-constexpr int kMaxC = 1024;
+constexpr int kMaxC = 1024;  // nvec = C/8 <= 128 threads per pixel
 
 struct GnArgs {
   const uint16_t* x1;
@@ -38,8 +38,8 @@ struct GnArgs {
 
 template <int DT>
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
-  __shared__ float s_scale[kMaxC];
-  __shared__ float s_shift[kMaxC];
+  // blockDim.x = nvec * k (nvec = C/8 16-byte vectors per pixel): every thread owns ONE channel vector for the whole
+  // block, so its 8 scale/shift pairs live in registers and the inner loop is load - 8 FMA - 8 SiLU - store.
   __shared__ float s_mean[32];
   __shared__ float s_rstd[32];
   const int b = blockIdx.y;
@@ -64,69 +64,60 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
     s_rstd[g] = (float)(1.0 / sqrt(var + (double)a.eps));
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += kGnThreads) {
-    const int g = c / cpg;
-    const float sc = a.gamma[c] * s_rstd[g];
-    s_scale[c] = sc;
-    s_shift[c] = a.beta[c] - s_mean[g] * sc;
-  }
-  __syncthreads();
-
-  const int nvec = C >> 3;       // 16-byte vectors per pixel
+  const int nvec = C >> 3;
   const int nvec1 = a.C1 >> 3;
+  const int vec = threadIdx.x % nvec;
+  const int prow = threadIdx.x / nvec;       // pixel slot of this thread inside one block iteration
+  const int pstride = blockDim.x / nvec;     // pixels per block iteration
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = vec * 8 + k;
+    const int g = c / cpg;
+    sc[k] = a.gamma[c] * s_rstd[g];
+    sh[k] = a.beta[c] - s_mean[g] * sc[k];
+  }
   const int pix0 = blockIdx.x * a.pix_per_block;
   int npix = a.HW - pix0;
   if (npix > a.pix_per_block) npix = a.pix_per_block;
-  if (npix <= 0) return;
-  const int total = npix * nvec;
   const size_t base_pix = (size_t)b * a.HW + pix0;
+  const uint16_t* src = (vec < nvec1) ? a.x1 + base_pix * a.p1 + vec * 8 : a.x2 + base_pix * a.p2 + (vec - nvec1) * 8;
+  const int sp = (vec < nvec1) ? a.p1 : a.p2;
+  uint16_t* dst = a.out + base_pix * a.pout + vec * 8;
 
   constexpr int U = 4;
-  for (int i0 = threadIdx.x; i0 < total; i0 += kGnThreads * U) {
+  for (int p0 = prow; p0 < npix; p0 += pstride * U) {
     uint4 v[U];
-    int pix[U], vec[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * kGnThreads;
-      if (i < total) {
-        pix[u] = i / nvec;
-        vec[u] = i - pix[u] * nvec;
-        const uint16_t* src = (vec[u] < nvec1)
-                                       ? a.x1 + (base_pix + pix[u]) * a.p1 + vec[u] * 8
-                                       : a.x2 + (base_pix + pix[u]) * a.p2 + (vec[u] - nvec1) * 8;
-        v[u] = __ldcs(reinterpret_cast<const uint4*>(src));
-      }
+      const int p = p0 + u * pstride;
+      if (p < npix) v[u] = __ldcs(reinterpret_cast<const uint4*>(src + (size_t)p * sp));
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * kGnThreads;
-      if (i < total) {
-        const int c0 = vec[u] * 8;
-        const float4 sc0 = *reinterpret_cast<const float4*>(&s_scale[c0]);
-        const float4 sc1 = *reinterpret_cast<const float4*>(&s_scale[c0 + 4]);
-        const float4 sh0 = *reinterpret_cast<const float4*>(&s_shift[c0]);
-        const float4 sh1 = *reinterpret_cast<const float4*>(&s_shift[c0 + 4]);
-        float2 f0 = unpack2<DT>(v[u].x), f1 = unpack2<DT>(v[u].y);
-        float2 f2 = unpack2<DT>(v[u].z), f3 = unpack2<DT>(v[u].w);
+      const int p = p0 + u * pstride;
+      if (p < npix) {
+        const float2 f0 = unpack2<DT>(v[u].x), f1 = unpack2<DT>(v[u].y);
+        const float2 f2 = unpack2<DT>(v[u].z), f3 = unpack2<DT>(v[u].w);
         float y[8];
-        y[0] = fmaf(f0.x, sc0.x, sh0.x);
-        y[1] = fmaf(f0.y, sc0.y, sh0.y);
-        y[2] = fmaf(f1.x, sc0.z, sh0.z);
-        y[3] = fmaf(f1.y, sc0.w, sh0.w);
-        y[4] = fmaf(f2.x, sc1.x, sh1.x);
-        y[5] = fmaf(f2.y, sc1.y, sh1.y);
-        y[6] = fmaf(f3.x, sc1.z, sh1.z);
-        y[7] = fmaf(f3.y, sc1.w, sh1.w);
+        y[0] = fmaf(f0.x, sc[0], sh[0]);
+        y[1] = fmaf(f0.y, sc[1], sh[1]);
+        y[2] = fmaf(f1.x, sc[2], sh[2]);
+        y[3] = fmaf(f1.y, sc[3], sh[3]);
+        y[4] = fmaf(f2.x, sc[4], sh[4]);
+        y[5] = fmaf(f2.y, sc[5], sh[5]);
+        y[6] = fmaf(f3.x, sc[6], sh[6]);
+        y[7] = fmaf(f3.y, sc[7], sh[7]);
         if (a.silu) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) y[k] = silu_f(y[k]);
+          for (int k = 0; k < 8; ++k) y[k] = silu_fast(y[k]);
         }
         uint4 o;
         o.x = pack2<DT>(y[0], y[1]);
         o.y = pack2<DT>(y[2], y[3]);
         o.z = pack2<DT>(y[4], y[5]);
         o.w = pack2<DT>(y[6], y[7]);
-        *reinterpret_cast<uint4*>(a.out + (base_pix + pix[u]) * a.pout + c0) = o;
+        *reinterpret_cast<uint4*>(dst + (size_t)p * a.pout) = o;
       }
     }
   }
@@ -192,10 +183,12 @@ extern "C" int d3_groupnorm_silu(const void* x1, int C1, int p1, const double* s
   if (ppb < min_ppb) ppb = min_ppb;
   a.pix_per_block = ppb;
   dim3 grid(ceil_div(HW, ppb), B);
+  const int nvec = C / 8;
+  const int threads = nvec * (kGnThreads / nvec > 0 ? kGnThreads / nvec : 1);  // multiple of nvec, <= 256 (nvec <= 128)
   if (dtype == D3_DTYPE_F16)
-    gn_apply_kernel<kF16><<<grid, kGnThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    gn_apply_kernel<kF16><<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   else
-    gn_apply_kernel<kBF16><<<grid, kGnThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    gn_apply_kernel<kBF16><<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

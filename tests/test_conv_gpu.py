@@ -18,6 +18,10 @@ CASES = [
     (2, 24, 40, 512, 1536, 1, 1, 0, 0, False),    # 1x1 (attention QKV linear)
     (1, 17, 30, 512, 512, 1, 1, 0, 0, True),      # 1x1 + residual (attention out-proj), odd sizes
     (1, 384, 640, 128, 128, 3, 1, 0, 0, False),   # the dominant shape
+    (1, 48, 64, 256, 128, 3, 1, 128, 128, False),  # Cout=128 with folded shortcut (up5 resnets), pixels-as-N kernel
+    (2, 33, 70, 64, 128, 3, 1, 0, 0, True),        # ragged tiles + residual, pixels-as-N kernel
+    (1, 1, 20, 128, 128, 1, 1, 0, 0, True),        # single-row image (TH = 1 path)
+    (3, 192, 320, 128, 128, 3, 1, 0, 0, True),     # TW=64, TH=4 tiles
 ]
 
 
