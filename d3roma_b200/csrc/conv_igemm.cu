@@ -44,6 +44,7 @@ struct ConvKArgs {
   int res_pitch;
   double* stats;
   uint32_t a_bytes;
+  int pass_w;      // pixels-as-N kernel: pixels per epilogue pass (divides TW, <= 64)
   int debug_skip;  // developer experiment: bit0 = skip A loads, bit1 = skip B loads (results are garbage)
 };
 
@@ -384,8 +385,10 @@ D3_DEVINL void epi_t_chunk(const uint32_t (&v)[32], uint32_t sa, const uint32_t 
   }
 }
 
+constexpr int kTThreads = 384;  // warps 0-3: producer / MMA / TMEM alloc / idle; warps 4-11: two epilogue groups
+
 template <int STAGES, int DT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kTThreads, 1)
 conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS1,
                     const __grid_constant__ CUtensorMap tmS2, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
@@ -418,7 +421,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 8);
     }
     mbar_init(res_bar, 1);
     fence_barrier_init();
@@ -513,24 +516,26 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
-    const uint32_t q = warp - 4;
+    const uint32_t q = (warp - 4) & 3;          // TMEM lane quarter this warp may access
+    const uint32_t grp = (warp - 4) >> 2;       // the two groups take the two 32-pixel chunks of a pass
     const uint32_t et = threadIdx.x - 128;
     const uint32_t ch = q * 32 + lane;          // channel inside the 128-channel tile == TMEM lane
     const uint32_t half = ch >> 6;              // which 64-channel staging half
     const uint32_t ch16 = (ch & 63) >> 3;       // 16-byte chunk of this channel inside the 128-byte row
     const uint32_t chb = (ch & 7) * 2;          // byte inside the chunk
-    uint8_t* sbase = staging + half * kStagingBytes;
-    const uint32_t sbase_u32 = smem_u32(sbase) + chb;
     uint32_t swz[8];  // swizzled 16-byte chunk offset of this channel for row (pixel) index % 8
 #pragma unroll
     for (int i = 0; i < 8; ++i) swz[i] = (ch16 ^ (uint32_t)i) << 4;
     const bool has_res = a.residual != nullptr;
-    const int passes = (a.TH % 2 == 0) ? 2 : 1;
-    const int pass_rows = a.TH / passes;
-    const int pass_px = pass_rows * a.TW;       // <= 128
+    // A pass = PW (<= 64) consecutive pixels of one tile row = a contiguous range of accumulator columns.  Staging is
+    // double-buffered by pass so the TMA store of pass p overlaps the math of pass p+1.
+    const int PW = a.pass_w;
+    const int segs = a.TW / PW;
+    const int passes = a.TH * segs;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t res_phase = 0;
+    uint32_t pass_ctr = 0;
     for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(a, tile, 128);
       const float bias = a.bias[(size_t)t.b * a.bias_bstride + t.n0 + ch];
@@ -545,35 +550,32 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (acc == 0) acc_phase ^= 1;
         continue;
       }
-      for (int ps = 0; ps < passes; ++ps) {
-        const int h_pass = t.h0 + ps * pass_rows;
-        // staging is free once the previous TMA store has finished READING it
+      for (int ps = 0; ps < passes; ++ps, ++pass_ctr) {
+        const int r = ps / segs;
+        const int sg = ps - r * segs;
+        const int h = t.h0 + r;
+        const int wpass = t.w0 + sg * PW;
+        uint8_t* sbuf = staging + (pass_ctr & 1) * kStagingBytes;  // two 64-channel halves of 64 rows each
         if (et == 0) {
-          tma_store_wait_read<0>();
-          if (a.residual != nullptr) {
-            mbar_arrive_expect_tx(res_bar, 2u * (uint32_t)pass_px * 128u);
-            tma_load_4d(staging, &tmR, res_bar, t.n0, t.w0, h_pass, t.b);
-            tma_load_4d(staging + kStagingBytes, &tmR, res_bar, t.n0 + 64, t.w0, h_pass, t.b);
+          tma_store_wait_read<1>();  // the store that used this buffer two passes ago has finished reading it
+          if (has_res) {
+            mbar_arrive_expect_tx(res_bar, 2u * (uint32_t)PW * 128u);
+            tma_load_4d(sbuf, &tmR, res_bar, t.n0, wpass, h, t.b);
+            tma_load_4d(sbuf + kStagingBytes / 2, &tmR, res_bar, t.n0 + 64, wpass, h, t.b);
           }
         }
-        named_bar_sync(1, 128);
-        if (a.residual != nullptr) {
+        named_bar_sync(1, 256);
+        if (has_res) {
           mbar_wait(res_bar, res_phase);
           res_phase ^= 1;
         }
-        for (int c0 = 0; c0 < pass_px; c0 += 32) {
+        const int c0 = (int)grp * 32;
+        if (c0 < PW) {
           uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * 256 + ps * pass_px + c0, v);
-          // validity of the 32 pixels of this chunk: one division per lane, shared through a ballot
-          uint32_t vmask;
-          {
-            const int px = c0 + (int)lane;
-            const int pr = px / a.TW;
-            const int pw = px - pr * a.TW;
-            vmask = __ballot_sync(0xffffffffu, (px < pass_px) && (h_pass + pr < a.Ho) && (t.w0 + pw < a.Wo));
-          }
-          // rows c0 .. c0+31 of the 128-row staging tile (rows beyond pass_px are written but never stored)
-          const uint32_t sa = sbase_u32 + (uint32_t)c0 * 128u;
+          tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * 256 + r * a.TW + sg * PW + c0, v);
+          const uint32_t vmask = __ballot_sync(
+              0xffffffffu, (c0 + (int)lane < PW) && (h < a.Ho) && (wpass + c0 + (int)lane < a.Wo));
+          const uint32_t sa = smem_u32(sbuf) + half * (kStagingBytes / 2) + (uint32_t)c0 * 128u + chb;
           tmem_ld_wait();
           if (has_res) {
             epi_t_chunk<DT, true>(v, sa, swz, bias, vmask, s_sum, s_sq);
@@ -587,10 +589,10 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
         fence_proxy_async_smem();
-        named_bar_sync(2, 128);
+        named_bar_sync(2, 256);
         if (et == 0) {
-          tma_store_4d(&tmO, staging, t.n0, t.w0, h_pass, t.b);
-          tma_store_4d(&tmO, staging + kStagingBytes, t.n0 + 64, t.w0, h_pass, t.b);
+          tma_store_4d(&tmO, sbuf, t.n0, wpass, h, t.b);
+          tma_store_4d(&tmO, sbuf + kStagingBytes / 2, t.n0 + 64, wpass, h, t.b);
           tma_store_commit();
         }
       }
@@ -600,7 +602,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         s_sq += __shfl_xor_sync(0xffffffffu, s_sq, 1);
         s_sum += __shfl_xor_sync(0xffffffffu, s_sum, 2);
         s_sq += __shfl_xor_sync(0xffffffffu, s_sq, 2);
-        if ((lane & 3) == 0 && t.b < a.B) {
+        if ((lane & 3) == 0) {
           double* dst = a.stats + ((size_t)t.b * (a.Cout >> 2) + ((t.n0 + ch) >> 2)) * 2;
           atomicAdd(dst, (double)s_sum);
           atomicAdd(dst + 1, (double)s_sq);
@@ -637,23 +639,30 @@ cudaError_t launch_conv_t(int grid, cudaStream_t stream, const CUtensorMap& tmA,
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  conv_igemm_t_kernel<STAGES, DT><<<grid, kThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, tmR, a);
+  conv_igemm_t_kernel<STAGES, DT><<<grid, kTThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, tmR, a);
   return cudaSuccess;
 }
 
-// Pixel tile for the pixels-as-N kernel: TH*TW <= 256, epilogue passes of <= 128 pixels (TH even, or TH == 1).
+// Pixel tile for the pixels-as-N kernel: TH*TW <= 256; the epilogue walks it in passes of PW pixels of one row,
+// PW = largest divisor of TW that is <= 64.
+int pass_width(int tw) {
+  for (int d = (tw < 64 ? tw : 64); d >= 1; --d)
+    if (tw % d == 0) return d;
+  return 1;
+}
+
 void choose_tile_t(int Ho, int Wo, int* TH, int* TW) {
   double best = -1.0;
   int bh = 1, bw = 1;
   for (int tw = 1; tw <= 256 && tw <= Wo; ++tw) {
     int th = 256 / tw;
     if (th > Ho) th = Ho;
-    if (th > 1 && (th & 1)) --th;
     if (th < 1) continue;
-    const int pass_px = (th % 2 == 0) ? th * tw / 2 : th * tw;
-    if (pass_px > 128) continue;
+    const int pw = pass_width(tw);
+    if (pw < 16 && tw > 16) continue;  // avoid degenerate pass widths (e.g. prime tile widths)
     const double tiles = double(ceil_div(Ho, th)) * ceil_div(Wo, tw);
-    const double eff = double(Ho) * Wo / (tiles * 256.0);
+    double eff = double(Ho) * Wo / (tiles * 256.0);
+    eff *= (pw >= 32 ? 1.0 : 0.98);    // prefer tiles whose passes fill both epilogue groups
     if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > bw)) {
       best = eff;
       bh = th;
@@ -766,7 +775,9 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
 
   CUtensorMap tmA, tmS1, tmS2, tmB, tmO, tmR;
   int rc = 0;
-  const int store_rows = use_t ? ((a.TH % 2 == 0) ? a.TH / 2 : a.TH) : a.TH;  // rows per TMA store box
+  a.pass_w = use_t ? pass_width(a.TW) : 0;
+  const int store_rows = use_t ? 1 : a.TH;               // rows per TMA store box
+  const int store_cols = use_t ? a.pass_w : a.TW;        // pixels per row of the TMA store box
   if (p->stride == 1) {
     uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
     uint64_t str[3] = {(uint64_t)p->x_pitch * 2, (uint64_t)p->W * p->x_pitch * 2,
@@ -811,7 +822,7 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
     uint64_t dims[4] = {(uint64_t)p->Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)p->B};
     uint64_t str[3] = {(uint64_t)p->out_pitch * 2, (uint64_t)Wo * p->out_pitch * 2,
                        (uint64_t)Ho * Wo * p->out_pitch * 2};
-    uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)store_rows, 1};
+    uint32_t box[4] = {64, (uint32_t)store_cols, (uint32_t)store_rows, 1};
     if ((rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmO, p->out, 4, dims, str, box)))
       return set_error(D3_ERR_CUDA, "conv: tensor map O encode failed (%d)", rc);
     tmR = tmO;
