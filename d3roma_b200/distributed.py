@@ -1,0 +1,82 @@
+"""Batch-sharded multi-GPU evaluation — the multi-GPU shape of the reference's ``distributed_evaluate.py``
+(/root/reference/distributed_evaluate.py:28-174): every rank holds a full pipeline replica (:63), the batch is split
+across ranks (:96, ``accelerator.prepare(val_dataloader)``), each rank denoises its shard independently (no
+collective inside the loop) and the results are all-gathered (:162-163, ``gather_for_metrics``).
+
+One process per GPU under ``torchrun``; ``torch.distributed`` (NCCL over NVLink on GPUs, gloo in the CPU tests) is
+the plumbing.  Differences from the reference, on purpose:
+  * the split is a deterministic contiguous index range per rank (the reference shuffles, distributed_evaluate.py:85-89),
+  * start noise is seeded PER SAMPLE (global index), so results do not depend on the number of ranks,
+  * the predicted disparity maps themselves are gathered (BASELINE config 5), not only metric rows.
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """Initialise the default process group from torchrun's env (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*).
+    Returns (rank, world, local_rank); a single-process run needs no process group."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local
+
+
+def shard_range(n: int, rank: int, world: int) -> range:
+    """Contiguous, balanced split of ``n`` samples: the first ``n % world`` ranks get one extra sample."""
+    base, extra = divmod(n, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def sample_generators(indices: Sequence[int], seed: int = 0) -> List[torch.Generator]:
+    """One CPU generator per GLOBAL sample index: x_T of a sample is the same on any number of ranks."""
+    return [torch.Generator().manual_seed(seed + int(i)) for i in indices]
+
+
+def all_gather_variable(local: torch.Tensor, n_total: int, rank: int, world: int) -> torch.Tensor:
+    """All-gather per-rank shards ``[n_r, ...]`` (n_r = len(shard_range(n_total, r, world))) into ``[n_total, ...]``
+    in global sample order.  Uses one ``all_gather_into_tensor`` on equal-size (padded) slots."""
+    if world == 1:
+        return local
+    per = (n_total + world - 1) // world
+    slot = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    slot[:local.shape[0]] = local
+    out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, slot)
+    parts = [out[r * per:r * per + len(shard_range(n_total, r, world))] for r in range(world)]
+    return torch.cat(parts, dim=0)
+
+
+def run_sharded(n_total: int, make_batch: Callable[[Sequence[int]], dict], denoise: Callable[..., torch.Tensor],
+                batch_size: int, seed: int = 0) -> torch.Tensor:
+    """Evaluate ``n_total`` samples: this rank's contiguous shard is processed in batches of ``batch_size`` through
+    ``denoise(**make_batch(indices), generator=[per-sample generators])`` and the per-sample outputs are gathered
+    on every rank in global order."""
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    mine = shard_range(n_total, rank, world)
+    outs = []
+    for s in range(mine.start, mine.stop, batch_size):
+        idx = list(range(s, min(s + batch_size, mine.stop)))
+        outs.append(denoise(**make_batch(idx), generator=sample_generators(idx, seed)))
+    if outs:
+        local = torch.cat(outs, dim=0)
+    else:  # a rank can be empty when n_total < world
+        probe = denoise(**make_batch([0]), generator=sample_generators([0], seed))
+        local = probe[:0]
+    return all_gather_variable(local, n_total, rank, world)
