@@ -36,6 +36,7 @@ class ConvParams(C.Structure):
         ("out", C.c_void_p), ("out_pitch", C.c_int32),
         ("stats", C.c_void_p),
         ("dtype", C.c_int32),
+        ("up2x_phase", C.c_int32),
     ]
 
 

@@ -35,6 +35,8 @@ struct ConvKArgs {
   int B, Ho, Wo, Cout;
   int TH, TW, tilesH, tilesW, nTilesN, numTiles;
   int ksize, stride, pad;
+  int ntaps;
+  signed char tap_dh[9], tap_dw[9];  // input offset of each filter tap (stride-1 path)
   int Cin, cbMain;
   int kbMain, kbSc1, kbSc2, kbTotal;
   int sc_off2;  // channel offset of the second half-res parity plane (stride 2 only): x_pitch
@@ -205,7 +207,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int kh = tap / a.ksize;
             const int kw = tap - kh * a.ksize;
             if (a.stride == 1) {
-              tma_load_4d(sA, &tmA, &full_bar[stage], cb * 64, t.w0 + kw - a.pad, t.h0 + kh - a.pad, t.b);
+              tma_load_4d(sA, &tmA, &full_bar[stage], cb * 64, t.w0 + a.tap_dw[tap], t.h0 + a.tap_dh[tap], t.b);
             } else {
               // input pixel (2*ho + kh - 1, 2*wo + kw - 1) in the parity-split 5-D view
               const int dh = kh - 1, dw = kw - 1;
@@ -461,7 +463,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int kh = tap / a.ksize;
             const int kw = tap - kh * a.ksize;
             if (a.stride == 1) {
-              tma_load_4d(sP, &tmA, &full_bar[stage], cb * 64, t.w0 + kw - a.pad, t.h0 + kh - a.pad, t.b);
+              tma_load_4d(sP, &tmA, &full_bar[stage], cb * 64, t.w0 + a.tap_dw[tap], t.h0 + a.tap_dh[tap], t.b);
             } else {
               const int dh = kh - 1, dw = kw - 1;
               const int hh = t.h0 + (dh < 0 ? -1 : 0), ph = (dh == 0) ? 0 : 1;
@@ -730,7 +732,11 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
     D3_REQUIRE(p->C1 == 0 && p->C2 == 0, "conv: stride 2 with shortcut not supported");
   }
   const int Ho = p->H / p->stride, Wo = p->W / p->stride;
-  const int taps = p->ksize * p->ksize;
+  const int phase = p->up2x_phase;  // 0: plain conv; 1..4: sub-pixel phase (py, px) = ((phase-1)/2, (phase-1)%2)
+  D3_REQUIRE(phase >= 0 && phase <= 4, "conv: bad up2x_phase %d", phase);
+  D3_REQUIRE(phase == 0 || (p->ksize == 3 && p->stride == 1 && !p->sc1 && !p->sc2 && !p->residual),
+             "conv: up2x_phase needs a plain 3x3 stride-1 conv");
+  const int taps = phase ? 4 : p->ksize * p->ksize;
   const int Ktot = taps * p->Cin + p->C1 + p->C2;
 
   ConvKArgs a{};
@@ -753,6 +759,21 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   a.ksize = p->ksize;
   a.stride = p->stride;
   a.pad = p->ksize / 2;
+  a.ntaps = taps;
+  if (phase) {
+    // nearest-2x upsample folded into the conv: output pixel (2i+py, 2j+px) reads input rows {i+py-1, i+py} and
+    // columns {j+px-1, j+px} with pre-summed weights (see ops.pack_upsample_weights)
+    const int py = (phase - 1) / 2, px = (phase - 1) % 2;
+    for (int t = 0; t < 4; ++t) {
+      a.tap_dh[t] = (signed char)(py - 1 + t / 2);
+      a.tap_dw[t] = (signed char)(px - 1 + t % 2);
+    }
+  } else {
+    for (int t = 0; t < taps; ++t) {
+      a.tap_dh[t] = (signed char)(t / p->ksize - a.pad);
+      a.tap_dw[t] = (signed char)(t % p->ksize - a.pad);
+    }
+  }
   a.Cin = p->Cin;
   a.cbMain = p->Cin / 64;
   a.kbMain = taps * a.cbMain;
@@ -822,8 +843,17 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
     uint64_t dims[4] = {(uint64_t)p->Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)p->B};
     uint64_t str[3] = {(uint64_t)p->out_pitch * 2, (uint64_t)Wo * p->out_pitch * 2,
                        (uint64_t)Ho * Wo * p->out_pitch * 2};
+    const void* obase = p->out;
+    if (phase) {
+      // strided view of the [B, 2H, 2W, Cout] output: every second pixel in both directions, offset (py, px)
+      const int py = (phase - 1) / 2, px = (phase - 1) % 2;
+      str[0] = (uint64_t)p->out_pitch * 4;
+      str[1] = (uint64_t)(2 * Wo) * p->out_pitch * 4;
+      str[2] = (uint64_t)(2 * Ho) * (2 * Wo) * p->out_pitch * 2;
+      obase = static_cast<const char*>(p->out) + ((size_t)py * (2 * Wo) + px) * p->out_pitch * 2;
+    }
     uint32_t box[4] = {64, (uint32_t)store_cols, (uint32_t)store_rows, 1};
-    if ((rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmO, p->out, 4, dims, str, box)))
+    if ((rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmO, obase, 4, dims, str, box)))
       return set_error(D3_ERR_CUDA, "conv: tensor map O encode failed (%d)", rc);
     tmR = tmO;
     if (use_t && p->residual) {

@@ -51,17 +51,38 @@ def pack_conv_weight(w_oihw: torch.Tensor, shortcut_w: Optional[torch.Tensor] = 
     return w.to(dtype).contiguous()
 
 
+def pack_upsample_weights(w_oihw: torch.Tensor, dtype: torch.dtype = torch.bfloat16):
+    """Weights of the 4 sub-pixel phases of ``conv3x3(nearest_upsample_2x(x))``: for output parity (py, px) the 3x3
+    kernel collapses onto a 2x2 input neighbourhood (rows {i+py-1, i+py}, cols {j+px-1, j+px}); taps that land on the
+    same input pixel are summed in fp32.  Returns [phase] -> [Cout, 4*Cin], tap-major (dy, dx)."""
+    w = w_oihw.float()
+    groups = {0: ([0], [1, 2]), 1: ([0, 1], [2])}  # parity -> (taps hitting the first input row/col, the second)
+    out = []
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = []
+            for rows in groups[py]:
+                for cols in groups[px]:
+                    taps.append(w[:, :, rows][:, :, :, cols].sum(dim=(2, 3)))   # [Cout, Cin]
+            out.append(torch.stack(taps, dim=1).reshape(w.shape[0], -1).to(dtype).contiguous())
+    return out
+
+
 def conv2d_igemm(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, *, ksize: int, stride: int = 1,
                  sc1: Optional[torch.Tensor] = None, sc2: Optional[torch.Tensor] = None,
                  residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                 stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 stats: Optional[torch.Tensor] = None, up2x_phase: int = 0) -> torch.Tensor:
     """tcgen05 implicit-GEMM conv (see ``d3_conv2d_igemm`` in include/d3roma_b200.h)."""
     _check_nhwc(x, "x")
     B, H, W, Cin = x.shape
     Cout = w_packed.shape[0]
     Ho, Wo = H // stride, W // stride
+    if up2x_phase:
+        Ho, Wo = 2 * H, 2 * W
     if out is None:
         out = torch.empty((B, Ho, Wo, Cout), dtype=x.dtype, device=x.device)
+    if tuple(out.shape) != (B, Ho, Wo, Cout):
+        raise ValueError(f"out has shape {tuple(out.shape)}, expected {(B, Ho, Wo, Cout)}")
     _check_nhwc(out, "out")
     p = _lib.ConvParams()
     p.x, p.B, p.H, p.W, p.Cin, p.x_pitch = x.data_ptr(), B, H, W, Cin, x.stride(2)
@@ -76,7 +97,8 @@ def conv2d_igemm(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, *,
         _check_nhwc(sc2, "sc2")
         c2 = sc2.shape[3]
         p.sc2, p.C2, p.sc2_pitch = sc2.data_ptr(), c2, sc2.stride(2)
-    if w_packed.shape[1] != ksize * ksize * Cin + c1 + c2 or w_packed.dtype != x.dtype:
+    ntaps = 4 if up2x_phase else ksize * ksize
+    if w_packed.shape[1] != ntaps * Cin + c1 + c2 or w_packed.dtype != x.dtype:
         raise ValueError("w_packed shape/dtype mismatch")
     if bias.dtype != torch.float32 or bias.shape[-1] != Cout or bias.stride(-1) != 1:
         raise ValueError("bias must be fp32 [Cout] or [B, Cout]")
@@ -90,6 +112,7 @@ def conv2d_igemm(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, *,
             raise ValueError("stats must be fp64 [B, Cout/4, 2]")
         p.stats = stats.data_ptr()
     p.dtype = _dt(x)
+    p.up2x_phase = int(up2x_phase)
     for t_ in (sc1, sc2, residual, out):
         if t_ is not None and t_.dtype != x.dtype:
             raise ValueError("all 16-bit operands of a conv must share one dtype")

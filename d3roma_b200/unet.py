@@ -181,7 +181,9 @@ class UNet2DModel:
             p = f"down_blocks.{i}.downsamplers.0.conv"
             W[p + ".w"], W[p + ".b"] = ops.pack_conv_weight(get(p + ".weight"), dtype=self._adt), get(p + ".bias").contiguous()
             p = f"up_blocks.{i}.upsamplers.0.conv"
-            W[p + ".w"], W[p + ".b"] = ops.pack_conv_weight(get(p + ".weight"), dtype=self._adt), get(p + ".bias").contiguous()
+            for ph, wp in enumerate(ops.pack_upsample_weights(get(p + ".weight"), dtype=self._adt)):
+                W[p + f".w{ph}"] = wp
+            W[p + ".b"] = get(p + ".bias").contiguous()
         W["out.g"], W["out.b"] = get("conv_norm_out.weight").contiguous(), get("conv_norm_out.bias").contiguous()
         w_out = get("conv_out.weight")  # [dc,128,3,3] -> [dc][9][128]
         assert w_out.shape[0] == self.out_channels
@@ -315,10 +317,15 @@ class UNet2DModel:
                 if attn:
                     h = self._attention(self._aprefix(kind, bi, bj), h, B)
             if i < 5:
+                # Upsample2D = nearest-2x + conv3x3, run as 4 sub-pixel phase convs on the low-res tensor
                 p = f"up_blocks.{i}.upsamplers.0.conv"
-                u = ops.upsample_nearest2x(h.t)
-                h = self._conv(u, W[p + ".w"], W[p + ".b"], 3, B)
-                del u
+                Bn, Hh, Ww, Cc = h.t.shape
+                up = torch.empty((Bn, 2 * Hh, 2 * Ww, Cc), dtype=h.t.dtype, device=h.t.device)
+                st = self._arena.take(B, Cc)
+                for ph in range(4):
+                    ops.conv2d_igemm(h.t, W[p + f".w{ph}"], W[p + ".b"], ksize=3, out=up, stats=st,
+                                     up2x_phase=ph + 1)
+                h = _Act(up, st)
         return ops.conv_out_fused(h.t, h.stats, W["out.g"], W["out.b"], W["out.w"], W["out.bias"], self.out_channels)
 
     @torch.no_grad()

@@ -75,6 +75,11 @@ typedef struct d3_conv_params {
   int32_t out_pitch;
   double* stats;       /* optional fp64 [B][Cout/4][2], must be zero on entry; NULL to skip          */
   int32_t dtype;       /* D3_DTYPE_BF16 / D3_DTYPE_F16: element type of x, w, sc1, sc2, residual, out        */
+  int32_t up2x_phase;  /* 0 = plain conv. 1..4 = sub-pixel phase of "nearest-2x upsample + 3x3 conv" (Upsample2D):
+                          x is the LOW-res tensor [B,H,W,Cin], out the HIGH-res tensor [B,2H,2W,Cout]; this launch
+                          writes output pixels (2i+py, 2j+px), (py,px) = ((phase-1)/2, (phase-1)%2), from the 2x2
+                          input neighbourhood with pre-summed weights w[Cout][4*Cin]. 4 launches = the whole layer
+                          at 4/9 of the FLOPs and without materialising the upsampled tensor.                   */
 } d3_conv_params;
 
 int d3_conv2d_igemm(const d3_conv_params* p, void* stream);

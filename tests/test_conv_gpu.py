@@ -68,3 +68,27 @@ def test_conv_igemm_matches_torch(case, dt):
     o = out.double().reshape(B, Ho * Wo, Cout // 4, 4)
     s_ref = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
     torch.testing.assert_close(stats, s_ref, rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+@pytest.mark.parametrize("B,H,W,C", [(2, 12, 20, 512), (1, 24, 40, 128), (2, 17, 30, 256), (1, 192, 320, 128)])
+def test_upsample_conv_subpixel_phases(B, H, W, C, dt):
+    """Upsample2D (nearest 2x + conv3x3) as 4 sub-pixel phase convs == conv over the materialised upsample."""
+    from d3roma_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).to(dt)
+    w = (torch.randn(C, C, 3, 3, device="cuda", generator=g) / (C * 9) ** 0.5)
+    bias = torch.randn(C, device="cuda", generator=g)
+    out = torch.empty(B, 2 * H, 2 * W, C, device="cuda", dtype=dt)
+    stats = torch.zeros(B, C // 4, 2, dtype=torch.float64, device="cuda")
+    for ph, wp in enumerate(ops.pack_upsample_weights(w, dtype=dt)):
+        ops.conv2d_igemm(x, wp, bias, ksize=3, out=out, stats=stats, up2x_phase=ph + 1)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w.to(dt).float(), bias, padding=1).permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs()
+    tol = (2.0 ** -7 if dt == torch.bfloat16 else 2.0 ** -10) * ref.abs() + (3e-2 if dt == torch.bfloat16 else 4e-3)
+    assert bool((err <= tol).all()), f"max err {err.max().item():.4g}"
+    o = out.double().reshape(B, 4 * H * W, C // 4, 4)
+    s_ref = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
+    torch.testing.assert_close(stats, s_ref, rtol=1e-5, atol=1e-3)
