@@ -34,6 +34,7 @@ constexpr uint32_t kStagingBytes = kTileM * 128;   // one 64-channel chunk of th
 struct ConvKArgs {
   int B, Ho, Wo, Cout;
   int TH, TW, tilesH, tilesW, nTilesN, numTiles;
+  int numPairs;  // cta_group::2 kernel: pairs of pixel tiles x nTilesN
   int ksize, stride, pad;
   int ntaps;
   signed char tap_dh[9], tap_dw[9];  // input offset of each filter tap (stride-1 path)
@@ -46,6 +47,9 @@ struct ConvKArgs {
   int res_pitch;
   double* stats;
   uint32_t a_bytes;
+  int t_direct;    // pixels-as-N kernel: epilogue stores straight to global (no staging / TMA store)
+  uint16_t* out;   // output base pointer + pitch for the direct epilogue
+  int out_pitch;
   int pass_w;      // pixels-as-N kernel: pixels per epilogue pass (divides TW, <= 64)
   int debug_skip;  // developer experiment: bit0 = skip A loads, bit1 = skip B loads (results are garbage)
 };
@@ -387,6 +391,25 @@ D3_DEVINL void epi_t_chunk(const uint32_t (&v)[32], uint32_t sa, const uint32_t 
   }
 }
 
+// Variant that writes straight to global memory (no staging tile, no TMA store): the warp's 32 lanes hold 32
+// consecutive channels of one pixel, i.e. each store instruction covers one contiguous 64-byte segment.
+template <int DT, bool HAS_RES, int J = 0>
+D3_DEVINL void epi_t_chunk_global(const uint32_t (&v)[32], uint16_t* gp, const uint16_t* rp, size_t pitch, float bias,
+                                  uint32_t vmask, float& s_sum, float& s_sq) {
+  if constexpr (J < 32) {
+    if ((vmask >> J) & 1u) {
+      float x = __uint_as_float(v[J]) + bias;
+      if constexpr (HAS_RES) x += unpack2<DT>((uint32_t)__ldg(rp + (size_t)J * pitch)).x;
+      const uint32_t pk = pack2<DT>(x, 0.f);
+      gp[(size_t)J * pitch] = (uint16_t)pk;
+      const float xr = unpack2<DT>(pk & 0xFFFFu).x;
+      s_sum += xr;
+      s_sq = fmaf(xr, xr, s_sq);
+    }
+    epi_t_chunk_global<DT, HAS_RES, J + 1>(v, gp, rp, pitch, bias, vmask, s_sum, s_sq);
+  }
+}
+
 constexpr int kTThreads = 384;  // warps 0-3: producer / MMA / TMEM alloc / idle; warps 4-11: two epilogue groups
 
 template <int STAGES, int DT>
@@ -552,6 +575,58 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (acc == 0) acc_phase ^= 1;
         continue;
       }
+      if (a.t_direct) {
+        // direct-to-global epilogue: 32-pixel chunks of the tile's accumulator columns, alternating between groups
+        const int NPx = a.TH * a.TW;
+        for (int c0 = (int)grp * 32; c0 < NPx; c0 += 64) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * 256 + c0, v);
+          const int px = c0 + (int)lane;
+          const int pr = px / a.TW;
+          const int pw = px - pr * a.TW;
+          const bool ok = (px < NPx) && (t.h0 + pr < a.Ho) && (t.w0 + pw < a.Wo);
+          const uint32_t vmask = __ballot_sync(0xffffffffu, ok);
+          // pixel offset (in pixels) of chunk element j relative to element 0: contiguous inside a tile row
+          const int r0 = c0 / a.TW, w0c = c0 - r0 * a.TW;
+          const size_t pix0 = ((size_t)(t.b * a.Ho + t.h0 + r0) * a.Wo + t.w0 + w0c);
+          tmem_ld_wait();
+          if (w0c + 32 <= a.TW) {  // the 32 pixels of this chunk lie in one tile row: constant pixel stride
+            uint16_t* gp = a.out + pix0 * a.out_pitch + t.n0 + ch;
+            if (has_res) {
+              const uint16_t* rp = a.residual + pix0 * a.res_pitch + t.n0 + ch;
+              if (a.res_pitch == a.out_pitch)
+                epi_t_chunk_global<DT, true>(v, gp, rp, (size_t)a.out_pitch, bias, vmask, s_sum, s_sq);
+              else
+                for (int j = 0; j < 32; ++j)
+                  if ((vmask >> j) & 1u) {
+                    const float x = __uint_as_float(v[j]) + bias + unpack2<DT>((uint32_t)rp[(size_t)j * a.res_pitch]).x;
+                    const uint32_t pk = pack2<DT>(x, 0.f);
+                    gp[(size_t)j * a.out_pitch] = (uint16_t)pk;
+                    const float xr = unpack2<DT>(pk & 0xFFFFu).x;
+                    s_sum += xr; s_sq = fmaf(xr, xr, s_sq);
+                  }
+            } else {
+              epi_t_chunk_global<DT, false>(v, gp, nullptr, (size_t)a.out_pitch, bias, vmask, s_sum, s_sq);
+            }
+          } else {  // chunk straddles tile rows (narrow tiles): generic addressing
+            for (int j = 0; j < 32; ++j) {
+              if ((vmask >> j) & 1u) {
+                const int pxj = c0 + j, prj = pxj / a.TW, pwj = pxj - prj * a.TW;
+                const size_t pix = ((size_t)(t.b * a.Ho + t.h0 + prj) * a.Wo + t.w0 + pwj);
+                float x = __uint_as_float(v[j]) + bias;
+                if (has_res) x += unpack2<DT>((uint32_t)a.residual[pix * a.res_pitch + t.n0 + ch]).x;
+                const uint32_t pk = pack2<DT>(x, 0.f);
+                a.out[pix * a.out_pitch + t.n0 + ch] = (uint16_t)pk;
+                const float xr = unpack2<DT>(pk & 0xFFFFu).x;
+                s_sum += xr; s_sq = fmaf(xr, xr, s_sq);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      } else
       for (int ps = 0; ps < passes; ++ps, ++pass_ctr) {
         const int r = ps / segs;
         const int sg = ps - r * segs;
@@ -673,6 +748,282 @@ void choose_tile_t(int Ho, int Wo, int* TH, int* TW) {
   }
   *TH = bh;
   *TW = bw;
+}
+
+
+// =====================================================================================================================
+// CTA-pair variant (cta_group::2) of the pixels-as-M kernel: two CTAs of a cluster own two adjacent pixel tiles
+// (M = 256 = 2 x 128 rows) and each keeps only HALF of the weight tile (BN/2 output channels) in shared memory; one
+// tcgen05.mma.cta_group::2 issued by the leader drives both SMs.  Per CTA the weight operand costs half the TMA
+// writes and half the operand reads of the single-CTA kernel, which is what the shared-memory port is short of
+// (profiles/r01_conv_experiments.txt).
+// =====================================================================================================================
+template <int BN, int STAGES, int DT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS1,
+                   const __grid_constant__ CUtensorMap tmS2, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmO, const ConvKArgs a) {
+  constexpr uint32_t kBHalfBytes = (BN / 2) * 128;
+  constexpr uint32_t kStageBytes = kATileBytes + kBHalfBytes;
+  constexpr uint32_t kTmemCols = 2 * BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + STAGES * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* spart = reinterpret_cast<float*>(tmem_ptr + 4);  // [4][32]
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();       // 0 = leader (issues the MMAs), 1 = peer
+  const int pair = blockIdx.x >> 1;
+  const int npairs_grid = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    if (a.kbSc1) tma_prefetch_desc(&tmS1);
+    if (a.kbSc2) tma_prefetch_desc(&tmS2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);   // leader's producer arrival (+ the bytes of both CTAs)
+      mbar_init(&empty_bar[i], 1);  // multicast commit from the leader's MMA lane
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);   // multicast commit
+      mbar_init(&tempty_bar[i], 8);  // 4 epilogue warps of each CTA (only the leader's copy is waited on)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc2(tmem_ptr, kTmemCols);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // pair-tile decode: pixel tiles 2*pp + rank share the weight tile nt
+  auto decode = [&](int tp, TileCoord& t) -> bool {
+    const int nt = tp % a.nTilesN;
+    const int pp = tp / a.nTilesN;
+    int p = 2 * pp + (int)rank;
+    const int pixTiles = a.B * a.tilesH * a.tilesW;
+    const bool real = p < pixTiles;
+    if (!real) p = pixTiles;  // decodes to b == B: every TMA coordinate out of range (zero fill / clipped store)
+    const int tw = p % a.tilesW;
+    const int q = p / a.tilesW;
+    const int th = q % a.tilesH;
+    t.b = q / a.tilesH;
+    t.h0 = th * a.TH;
+    t.w0 = tw * a.TW;
+    t.n0 = nt * BN;
+    return real;
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tp = pair; tp < a.numPairs; tp += npairs_grid) {
+        TileCoord t;
+        decode(tp, t);
+        for (int kb = 0; kb < a.kbTotal; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * kStageBytes;
+          uint8_t* sB = sA + kATileBytes;
+          if (a.debug_skip & 3) {
+            const uint32_t bytes = ((a.debug_skip & 1) ? 0u : a.a_bytes) + ((a.debug_skip & 2) ? 0u : kBHalfBytes);
+            if (rank == 0) { if (bytes) mbar_arrive_expect_tx(&full_bar[stage], 2u * bytes); else mbar_arrive(&full_bar[stage]); }
+            if (!(a.debug_skip & 1)) tma_load_4d_2cta(sA, &tmA, &full_bar[stage], 0, t.w0, t.h0, t.b);
+            if (!(a.debug_skip & 2)) tma_load_2d_2cta(sB, &tmB, &full_bar[stage], kb * 64, t.n0 + (int)rank * (BN / 2));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (a.a_bytes + kBHalfBytes));
+          if (kb < a.kbMain) {
+            const int tap = kb / a.cbMain;
+            const int cb = kb - tap * a.cbMain;
+            if (a.stride == 1) {
+              tma_load_4d_2cta(sA, &tmA, &full_bar[stage], cb * 64, t.w0 + a.tap_dw[tap], t.h0 + a.tap_dh[tap], t.b);
+            } else {
+              const int kh = tap / a.ksize;
+              const int kw = tap - kh * a.ksize;
+              const int dh = kh - 1, dw = kw - 1;
+              const int hh = t.h0 + (dh < 0 ? -1 : 0), ph = (dh == 0) ? 0 : 1;
+              const int ww = t.w0 + (dw < 0 ? -1 : 0), pw = (dw == 0) ? 0 : 1;
+              tma_load_5d_2cta(sA, &tmA, &full_bar[stage], pw * a.sc_off2 + cb * 64, ww, ph, hh, t.b);
+            }
+          } else if (kb < a.kbMain + a.kbSc1) {
+            tma_load_4d_2cta(sA, &tmS1, &full_bar[stage], (kb - a.kbMain) * 64, t.w0, t.h0, t.b);
+          } else {
+            tma_load_4d_2cta(sA, &tmS2, &full_bar[stage], (kb - a.kbMain - a.kbSc1) * 64, t.w0, t.h0, t.b);
+          }
+          // this CTA's half of the weight tile: output channels n0 + rank*BN/2 ...
+          tma_load_2d_2cta(sB, &tmB, &full_bar[stage], kb * 64, t.n0 + (int)rank * (BN / 2));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA only) ================================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_16bit(256, BN, DT == kBF16);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tp = pair; tp < a.numPairs; tp += npairs_grid) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < a.kbTotal; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * kStageBytes);
+          const uint64_t adesc = make_sw128_kmajor_desc(sA);
+          const uint64_t bdesc = make_sw128_kmajor_desc(sA + kATileBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2cta_mc(&empty_bar[stage], 0x3);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2cta_mc(&tfull_bar[acc], 0x3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue (both CTAs, own 128 rows) ================================
+    const uint32_t q = warp - 4;
+    const uint32_t et = threadIdx.x - 128;
+    const uint32_t r = q * 32 + lane;
+    const int th = r / a.TW;
+    const int tw = r - th * a.TW;
+    const uint32_t tempty_leader0 = mapa_u32(smem_u32(&tempty_bar[0]), 0);
+    const uint32_t tempty_leader1 = mapa_u32(smem_u32(&tempty_bar[1]), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t chunk_ctr = 0;
+    for (int tp = pair; tp < a.numPairs; tp += npairs_grid) {
+      TileCoord t;
+      const bool real = decode(tp, t);
+      const int h = t.h0 + th, w = t.w0 + tw;
+      const bool valid = real && (th < a.TH) && (h < a.Ho) && (w < a.Wo);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      if (a.debug_skip & 4) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        uint32_t v0[32], v1[32];
+        {
+          const uint32_t taddr = tmem_base + ((q * 32) << 16) + acc * BN + c * 64;
+          tmem_ld_32x32b_x32(taddr, v0);
+          tmem_ld_32x32b_x32(taddr + 32, v1);
+          tmem_ld_wait();
+        }
+        if (c == BN / 64 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+        }
+        uint8_t* sbuf = staging + (chunk_ctr & 1) * kStagingBytes;
+        if (et == 0) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        const int n_base = t.n0 + c * 64;
+        const int bb = real ? t.b : 0;
+        const float4* bp = reinterpret_cast<const float4*>(a.bias + (size_t)bb * a.bias_bstride + n_base);
+        const uint4* rp = nullptr;
+        if (a.residual != nullptr && valid) {
+          rp = reinterpret_cast<const uint4*>(a.residual + ((size_t)(t.b * a.Ho + h) * a.Wo + w) * a.res_pitch +
+                                              n_base);
+        }
+        float sums[32];
+        epi_process32<0, DT>(v0, sums, bp, rp, valid, sbuf, r);
+        epi_process32<1, DT>(v1, sums, bp, rp, valid, sbuf, r);
+        if (a.stats != nullptr) {
+          const float tot = warp_transpose_reduce32(sums, lane);
+          spart[q * 32 + lane] = tot;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (et == 0) {
+          tma_store_4d(&tmO, sbuf, n_base, t.w0, t.h0, t.b);
+          tma_store_commit();
+        }
+        if (a.stats != nullptr && et < 32 && real) {
+          const float tot = spart[et] + spart[32 + et] + spart[64 + et] + spart[96 + et];
+          const int quad = (n_base >> 2) + (et & 15);
+          atomicAdd(a.stats + ((size_t)t.b * (a.Cout >> 2) + quad) * 2 + (et >> 4), static_cast<double>(tot));
+        }
+        ++chunk_ctr;
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, kTmemCols);
+  }
+}
+
+template <int BN, int STAGES>
+constexpr size_t conv2_smem_bytes() {
+  return 1024 + STAGES * (kATileBytes + (BN / 2) * 128) + 2 * kStagingBytes + (2 * STAGES + 4) * 8 + 16 + 4 * 32 * 4;
+}
+
+template <int BN, int STAGES, int DT>
+cudaError_t launch_conv2(int npairs_grid, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmS1,
+                         const CUtensorMap& tmS2, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvKArgs& a) {
+  constexpr size_t smem = conv2_smem_bytes<BN, STAGES>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm2_kernel<BN, STAGES, DT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * npairs_grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<BN, STAGES, DT>, tmA, tmS1, tmS2, tmB, tmO, a);
 }
 
 template <int BN, int STAGES, int DT>
@@ -797,6 +1148,13 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   CUtensorMap tmA, tmS1, tmS2, tmB, tmO, tmR;
   int rc = 0;
   a.pass_w = use_t ? pass_width(a.TW) : 0;
+  {
+    static int td = -1;
+    if (td < 0) { const char* e = getenv("D3_CONV_T_DIRECT"); td = e ? atoi(e) : 0; }
+    a.t_direct = (use_t && phase == 0) ? td : 0;
+  }
+  a.out = static_cast<uint16_t*>(p->out);
+  a.out_pitch = p->out_pitch;
   const int store_rows = use_t ? 1 : a.TH;               // rows per TMA store box
   const int store_cols = use_t ? a.pass_w : a.TW;        // pixels per row of the TMA store box
   if (p->stride == 1) {
@@ -866,7 +1224,27 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
 
   const int grid = a.numTiles < num_sms() ? a.numTiles : num_sms();
   cudaError_t le = cudaSuccess;
-  if (use_t && p->dtype == D3_DTYPE_BF16)
+  static int use_2cta = -1;
+  if (use_2cta < 0) { const char* e = getenv("D3_CONV_2CTA"); use_2cta = e ? atoi(e) : 0; }
+  a.numPairs = ((pixTiles + 1) / 2) * a.nTilesN;
+  if (!use_t && use_2cta && a.numPairs >= 8) {
+    // B-operand box covers this CTA's half of the weight tile
+    uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)p->Cout};
+    uint64_t str[1] = {(uint64_t)Ktot * 2};
+    uint32_t box[2] = {64, (uint32_t)(BN / 2)};
+    if ((rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmB, p->w, 2, dims, str, box)))
+      return set_error(D3_ERR_CUDA, "conv: tensor map B(half) encode failed (%d)", rc);
+    const int max_pairs = num_sms() / 2;
+    const int npg = a.numPairs < max_pairs ? a.numPairs : max_pairs;
+    if (BN == 128 && p->dtype == D3_DTYPE_BF16)
+      le = launch_conv2<128, 6, kBF16>(npg, stream, tmA, tmS1, tmS2, tmB, tmO, a);
+    else if (BN == 128)
+      le = launch_conv2<128, 6, kF16>(npg, stream, tmA, tmS1, tmS2, tmB, tmO, a);
+    else if (p->dtype == D3_DTYPE_BF16)
+      le = launch_conv2<256, 5, kBF16>(npg, stream, tmA, tmS1, tmS2, tmB, tmO, a);
+    else
+      le = launch_conv2<256, 5, kF16>(npg, stream, tmA, tmS1, tmS2, tmB, tmO, a);
+  } else if (use_t && p->dtype == D3_DTYPE_BF16)
     le = launch_conv_t<4, kBF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, tmR, a);
   else if (use_t)
     le = launch_conv_t<4, kF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, tmR, a);
