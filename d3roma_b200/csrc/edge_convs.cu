@@ -18,54 +18,73 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // im2col gather for conv_in
 // ------------------------------------------------------------------------------------------------
+constexpr int kI2cPix = 64;     // pixels (of one image row) per block
+constexpr int kI2cPitchW = 65;  // smem words per pixel row (64 + 1 pad: conflict-free column writes AND row reads)
+
 template <int DT>
 __global__ void __launch_bounds__(256) im2col_input_kernel(const float* __restrict__ xs, int Cs,
                                                            const float* __restrict__ cond, int Cc, int B, int H,
-                                                           int W, uint16_t* __restrict__ out) {
-  // 16 lanes per pixel; lane j builds k = 8j .. 8j+7 of the 128-wide row.  The (tap, channel) of each of its 8
-  // elements does not depend on the pixel, so it is decoded once: plane base pointer offset + (dh, dw).
+                                                           int W, uint32_t* __restrict__ out) {
+  // Work item = 64 consecutive pixels of one image row.  Phase 1: for every pair of k = (tap, channel) the 64 pixel
+  // values are read with COALESCED loads along W (lanes = consecutive pixels) and dropped, packed, into a
+  // [pixel][k-pair] smem tile.  Phase 2: the tile is streamed out as full 256-byte rows (coalesced 4-byte words).
+  // The k -> (plane, dh, dw) decode is done once per block into a small table; blocks loop over work items.
+  __shared__ uint32_t tile[kI2cPix * kI2cPitchW];
+  __shared__ int s_chan[128];   // channel index (>= 0: sample plane c; < -1: cond plane -(v+2); -1: zero padding)
+  __shared__ int s_off[128];    // (dh + 1) * 3 + (dw + 1) = tap index
   const int Cin = Cs + Cc;
   const int K = 9 * Cin;
-  const size_t npix = (size_t)B * H * W;
-  const size_t HWs = (size_t)H * W;
-  const int j = threadIdx.x & 15;
-  int dh[8], dw[8], ch[8];  // ch < 0: zero padding column; ch < Cs: sample plane; else cond plane (ch - Cs)
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int k = 8 * j + e;
+  if (threadIdx.x < 128) {
+    const int k = threadIdx.x;
+    int chan = -1, code = 4;
     if (k < K) {
       const int tap = k / Cin;
-      ch[e] = k - tap * Cin;
-      dh[e] = tap / 3 - 1;
-      dw[e] = tap % 3 - 1;
-    } else {
-      ch[e] = -1;
-      dh[e] = dw[e] = 0;
+      const int c = k - tap * Cin;
+      chan = (c < Cs) ? c : -(c - Cs + 2);
+      code = tap;
     }
+    s_chan[k] = chan;
+    s_off[k] = code;
   }
-  for (size_t p = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4; p < npix;
-       p += ((size_t)gridDim.x * blockDim.x) >> 4) {
-    const int w = (int)(p % W);
-    const size_t t = p / W;
-    const int h = (int)(t % H);
-    const size_t b = t / H;
-    float v[8];
+  __syncthreads();
+  const int segs = (W + kI2cPix - 1) / kI2cPix;
+  const int items = B * H * segs;
+  const size_t HWs = (size_t)H * W;
+  const int px = threadIdx.x & 63;   // pixel inside the segment
+  const int kq = threadIdx.x >> 6;   // 4 k-pair lanes per pixel
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int seg = item % segs;
+    const int h = (item / segs) % H;
+    const size_t b = item / (segs * H);
+    const int w0 = seg * kI2cPix;
+    const int w = w0 + px;
+    const float* xb = xs + b * Cs * HWs;
+    const float* cb = cond + b * Cc * HWs;
+#pragma unroll 4
+    for (int kp = kq; kp < 64; kp += 4) {
+      float val[2];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int hh = h + dh[e], ww = w + dw[e];
-      float val = 0.f;
-      if (ch[e] >= 0 && hh >= 0 && hh < H && ww >= 0 && ww < W) {
-        const float* src = (ch[e] < Cs) ? xs + (b * Cs + ch[e]) * HWs : cond + (b * Cc + (ch[e] - Cs)) * HWs;
-        val = __ldg(src + (size_t)hh * W + ww);
+      for (int e = 0; e < 2; ++e) {
+        const int k = 2 * kp + e;
+        const int chan = s_chan[k];
+        const int code = s_off[k];
+        const int dh = (code >= 6 ? 1 : (code >= 3 ? 0 : -1)), dw = code - 3 * (dh + 1) - 1;
+        const int hh = h + dh, ww = w + dw;
+        float v = 0.f;
+        if (chan != -1 && hh >= 0 && hh < H && ww >= 0 && ww < W) {
+          const float* src = (chan >= 0) ? xb + (size_t)chan * HWs : cb + (size_t)(-chan - 2) * HWs;
+          v = __ldg(src + (size_t)hh * W + ww);
+        }
+        val[e] = v;
       }
-      v[e] = val;
+      tile[px * kI2cPitchW + kp] = pack2<DT>(val[0], val[1]);
     }
-    uint4 o;
-    o.x = pack2<DT>(v[0], v[1]);
-    o.y = pack2<DT>(v[2], v[3]);
-    o.z = pack2<DT>(v[4], v[5]);
-    o.w = pack2<DT>(v[6], v[7]);
-    __stcs(reinterpret_cast<uint4*>(out + p * 128 + 8 * j), o);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kI2cPix * 64; i += 256) {
+      const int p = i >> 6, wd = i & 63;
+      if (w0 + p < W) __stcs(out + ((b * H + h) * (size_t)W + w0 + p) * 64 + wd, tile[p * kI2cPitchW + wd]);
+    }
+    __syncthreads();
   }
 }
 
@@ -92,7 +111,27 @@ struct ConvOutArgs {
 
 template <int DC>
 constexpr size_t conv_out_smem() {
-  return (size_t)kCoRY * kCoRX * kCoPitch + (size_t)DC * 9 * 128 * 4 + 2 * 128 * 4;
+  return (size_t)kCoRY * kCoRX * kCoPitch + (size_t)9 * 8 * 8 * 16 * 2 + 2 * 128 * 4;
+}
+
+template <int DT>
+D3_DEVINL void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (DT == kBF16) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+}
+D3_DEVINL void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
 }
 
 template <int DC, int DT>
@@ -100,15 +139,20 @@ __global__ void __launch_bounds__(kCoThreads) conv_out_kernel(const ConvOutArgs 
   // Stage 1: the (8+2) x (32+2) x 128 input region is read ONCE from global (coalesced 16 B vectors), normalised,
   // SiLU'd, rounded to the 16-bit activation type (exactly what the separate GroupNorm pass would have stored) and
   // parked in shared memory; out-of-image pixels become the conv's zero padding.
-  // Stage 2: one output pixel per thread: 9 taps x 128 channels from smem against broadcast fp32 weights.
+  // Stage 2: warp w owns output row w of the tile (32 pixels = two 16-pixel MMA tiles); for every tap and 16-channel
+  // slab: ldmatrix the activation fragment, mma.m16n8k16 against the weight fragment (n = dc padded to 8).
   extern __shared__ __align__(16) uint8_t co_smem[];
   uint8_t* s_in = co_smem;
-  float* s_w = reinterpret_cast<float*>(co_smem + (size_t)kCoRY * kCoRX * kCoPitch);
-  float* s_sc = s_w + DC * 9 * 128;
+  uint16_t* s_w = reinterpret_cast<uint16_t*>(co_smem + (size_t)kCoRY * kCoRX * kCoPitch);  // [tap][ks][n=8][16]
+  float* s_sc = reinterpret_cast<float*>(s_w + 9 * 8 * 8 * 16);
   float* s_sh = s_sc + 128;
   const int b = blockIdx.z;
   const int y0 = blockIdx.y * kCoTY, x0 = blockIdx.x * kCoTX;
-  for (int i = threadIdx.x; i < DC * 9 * 128; i += kCoThreads) s_w[i] = a.w[i];
+  for (int i = threadIdx.x; i < 9 * 8 * 8 * 16; i += kCoThreads) {
+    const int c16 = i & 15, n = (i >> 4) & 7, ks = (i >> 7) & 7, tap = i >> 10;
+    const float wv = (n < DC) ? a.w[((size_t)n * 9 + tap) * 128 + ks * 16 + c16] : 0.f;
+    s_w[i] = (uint16_t)pack2<DT>(wv, 0.f);
+  }
   if (threadIdx.x < 128) {
     const int c = threadIdx.x, g = c >> 2;
     const double s = a.stats[((size_t)b * 32 + g) * 2], ss = a.stats[((size_t)b * 32 + g) * 2 + 1];
@@ -130,55 +174,80 @@ __global__ void __launch_bounds__(kCoThreads) conv_out_kernel(const ConvOutArgs 
       sc[k] = s_sc[vec * 8 + k];
       sh[k] = s_sh[vec * 8 + k];
     }
-    for (int pi = threadIdx.x >> 4; pi < kCoRY * kCoRX; pi += kCoThreads / 16) {
-      const int ry = pi / kCoRX, rx = pi - ry * kCoRX;
-      const int y = y0 - 1 + ry, x = x0 - 1 + rx;
-      uint4 o = make_uint4(0u, 0u, 0u, 0u);
-      if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(a.x + (((size_t)b * a.H + y) * a.W + x) * a.pitch +
-                                                               vec * 8));
-        const float2 f0 = unpack2<DT>(raw.x), f1 = unpack2<DT>(raw.y);
-        const float2 f2 = unpack2<DT>(raw.z), f3 = unpack2<DT>(raw.w);
-        o.x = pack2<DT>(silu_fast(fmaf(f0.x, sc[0], sh[0])), silu_fast(fmaf(f0.y, sc[1], sh[1])));
-        o.y = pack2<DT>(silu_fast(fmaf(f1.x, sc[2], sh[2])), silu_fast(fmaf(f1.y, sc[3], sh[3])));
-        o.z = pack2<DT>(silu_fast(fmaf(f2.x, sc[4], sh[4])), silu_fast(fmaf(f2.y, sc[5], sh[5])));
-        o.w = pack2<DT>(silu_fast(fmaf(f3.x, sc[6], sh[6])), silu_fast(fmaf(f3.y, sc[7], sh[7])));
+    constexpr int kPixPerIter = kCoThreads / 16;  // 16
+    constexpr int U = 4;
+    for (int p0 = threadIdx.x >> 4; p0 < kCoRY * kCoRX; p0 += kPixPerIter * U) {
+      uint4 raw[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pi = p0 + u * kPixPerIter;
+        const int ry = pi / kCoRX, rx = pi - ry * kCoRX;
+        const int y = y0 - 1 + ry, x = x0 - 1 + rx;
+        ok[u] = (pi < kCoRY * kCoRX) && y >= 0 && y < a.H && x >= 0 && x < a.W;
+        if (ok[u])
+          raw[u] = __ldg(reinterpret_cast<const uint4*>(a.x + (((size_t)b * a.H + y) * a.W + x) * a.pitch + vec * 8));
       }
-      *reinterpret_cast<uint4*>(s_in + (size_t)pi * kCoPitch + vec * 16) = o;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pi = p0 + u * kPixPerIter;
+        if (pi < kCoRY * kCoRX) {
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if (ok[u]) {
+            const float2 f0 = unpack2<DT>(raw[u].x), f1 = unpack2<DT>(raw[u].y);
+            const float2 f2 = unpack2<DT>(raw[u].z), f3 = unpack2<DT>(raw[u].w);
+            o.x = pack2<DT>(silu_fast(fmaf(f0.x, sc[0], sh[0])), silu_fast(fmaf(f0.y, sc[1], sh[1])));
+            o.y = pack2<DT>(silu_fast(fmaf(f1.x, sc[2], sh[2])), silu_fast(fmaf(f1.y, sc[3], sh[3])));
+            o.z = pack2<DT>(silu_fast(fmaf(f2.x, sc[4], sh[4])), silu_fast(fmaf(f2.y, sc[5], sh[5])));
+            o.w = pack2<DT>(silu_fast(fmaf(f3.x, sc[6], sh[6])), silu_fast(fmaf(f3.y, sc[7], sh[7])));
+          }
+          *reinterpret_cast<uint4*>(s_in + (size_t)pi * kCoPitch + vec * 16) = o;
+        }
+      }
     }
   }
   __syncthreads();
-  const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
-  float acc[DC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  float acc[2][4];
 #pragma unroll
-  for (int d = 0; d < DC; ++d) acc[d] = 0.f;
-#pragma unroll
+  for (int m = 0; m < 2; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+  // ldmatrix row address of this lane inside a 16x16 fragment: row = lane % 16, k-half = lane / 16
+  const uint32_t s_in_u32 = smem_u32(s_in);
+  const uint32_t lrow = (uint32_t)(lane & 15), lk = (uint32_t)(lane >> 4) * 16u;
+  const uint32_t* s_w32 = reinterpret_cast<const uint32_t*>(s_w);
+#pragma unroll 1
   for (int tap = 0; tap < 9; ++tap) {
-    const uint8_t* row = s_in + (size_t)((ty + tap / 3) * kCoRX + tx + tap % 3) * kCoPitch;
-#pragma unroll 4
-    for (int v = 0; v < 16; ++v) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(row + v * 16);
-      float f[8];
-      float2 t2;
-      t2 = unpack2<DT>(raw.x); f[0] = t2.x; f[1] = t2.y;
-      t2 = unpack2<DT>(raw.y); f[2] = t2.x; f[3] = t2.y;
-      t2 = unpack2<DT>(raw.z); f[4] = t2.x; f[5] = t2.y;
-      t2 = unpack2<DT>(raw.w); f[6] = t2.x; f[7] = t2.y;
+    const int kh = tap / 3, kw = tap - kh * 3;
+    const uint32_t rowbase = s_in_u32 + (uint32_t)((warp + kh) * kCoRX + kw) * kCoPitch + lrow * kCoPitch + lk;
 #pragma unroll
-      for (int d = 0; d < DC; ++d) {
-        const float4 w0 = *reinterpret_cast<const float4*>(s_w + (d * 9 + tap) * 128 + v * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(s_w + (d * 9 + tap) * 128 + v * 8 + 4);
-        acc[d] = fmaf(f[0], w0.x, acc[d]); acc[d] = fmaf(f[1], w0.y, acc[d]);
-        acc[d] = fmaf(f[2], w0.z, acc[d]); acc[d] = fmaf(f[3], w0.w, acc[d]);
-        acc[d] = fmaf(f[4], w1.x, acc[d]); acc[d] = fmaf(f[5], w1.y, acc[d]);
-        acc[d] = fmaf(f[6], w1.z, acc[d]); acc[d] = fmaf(f[7], w1.w, acc[d]);
-      }
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint32_t b0 = s_w32[((tap * 8 + ks) * 8 + g) * 8 + t];
+      const uint32_t b1 = s_w32[((tap * 8 + ks) * 8 + g) * 8 + 4 + t];
+      uint32_t af[4];
+      ldmatrix_x4(af, rowbase + ks * 32);
+      mma16816<DT>(acc[0], af, b0, b1);
+      ldmatrix_x4(af, rowbase + 16 * kCoPitch + ks * 32);
+      mma16816<DT>(acc[1], af, b0, b1);
     }
   }
-  const int y = y0 + ty, x = x0 + tx;
-  if (y < a.H && x < a.W) {
+  // C fragment: rows g / g+8 (pixels), columns 2t, 2t+1 (output channels)
+  const int y = y0 + warp;
+  if (y < a.H) {
 #pragma unroll
-    for (int d = 0; d < DC; ++d) a.out[(((size_t)b * DC + d) * a.H + y) * a.W + x] = acc[d] + a.bias[d];
+    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const int x = x0 + 16 * m + g + 8 * hrow;
+        if (x < a.W) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int d = 2 * t + e;
+            if (d < DC) a.out[(((size_t)b * DC + d) * a.H + y) * a.W + x] = acc[m][2 * hrow + e] + a.bias[d];
+          }
+        }
+      }
+    }
   }
 }
 
@@ -190,16 +259,14 @@ extern "C" int d3_im2col_input(const float* sample, int Cs, const float* cond, i
   using namespace d3;
   D3_REQUIRE(sample && out && (Cc == 0 || cond), "im2col: null pointer");
   D3_REQUIRE(9 * (Cs + Cc) <= 128, "im2col: 9*Cin = %d exceeds the 128-wide K slab", 9 * (Cs + Cc));
-  const size_t threads = (size_t)B * H * W * 16;
-  int blocks = (int)((threads + 255) / 256);
-  const int cap = num_sms() * 16;
-  if (blocks > cap) blocks = cap;
+  int blocks = B * H * ((W + kI2cPix - 1) / kI2cPix);
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   if (dtype == D3_DTYPE_F16)
     im2col_input_kernel<kF16><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        sample, Cs, cond, Cc, B, H, W, static_cast<uint16_t*>(out));
+        sample, Cs, cond, Cc, B, H, W, static_cast<uint32_t*>(out));
   else
     im2col_input_kernel<kBF16><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        sample, Cs, cond, Cc, B, H, W, static_cast<uint16_t*>(out));
+        sample, Cs, cond, Cc, B, H, W, static_cast<uint32_t*>(out));
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

@@ -72,7 +72,7 @@ def test_conv_out_fused(dc, dt):
     torch.backends.cudnn.allow_tf32 = False
     act = F.silu(F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5))
     # the kernel stages the normalised activation in the 16-bit activation type (like every other layer's GN pass)
-    ref16 = F.conv2d(act.to(dt).float(), w, bias, padding=1)
+    ref16 = F.conv2d(act.to(dt).float(), w.to(dt).float(), bias, padding=1)   # 16-bit operands, fp32 accumulate
     ref32 = F.conv2d(act, w, bias, padding=1)
     tol16 = 3e-3 if dt == torch.bfloat16 else 1e-3   # tanh.approx SiLU can flip a last-place rounding of `act`
     torch.testing.assert_close(out, ref16, rtol=tol16, atol=tol16)
