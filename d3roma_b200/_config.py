@@ -45,6 +45,24 @@ class ConfigMixin:
         return cls(**{k: v for k, v in cfg.items() if k in sig.parameters})
 
 
+def save_config(obj, path, filename):
+    """Write ``obj.config`` (+ ``_class_name``) as JSON, diffusers style."""
+    import json
+    import os
+    os.makedirs(path, exist_ok=True)
+    cfg = {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in dict(obj.config).items()}
+    cfg["_class_name"] = type(obj).__name__
+    with open(os.path.join(path, filename), "w") as f:
+        json.dump(cfg, f, indent=2)
+
+
+def load_config(path, filename):
+    import json
+    import os
+    with open(os.path.join(path, filename)) as f:
+        return json.load(f)
+
+
 class BaseOutput(OrderedDict):
     """Dataclass-style output: attribute access, tuple-style indexing, reassignable fields."""
 

@@ -49,6 +49,16 @@ D3_DEVINL void sts_u16(uint32_t saddr, uint32_t v) {
   asm volatile("st.shared.u16 [%0 + %2], %1;" ::"r"(saddr), "h"((unsigned short)v), "n"(IMM) : "memory");
 }
 template <int IMM>
+D3_DEVINL void sts_u32(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0 + %2], %1;" ::"r"(saddr), "r"(v), "n"(IMM) : "memory");
+}
+template <int IMM>
+D3_DEVINL uint32_t lds_u32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1 + %2];" : "=r"(v) : "r"(saddr), "n"(IMM) : "memory");
+  return v;
+}
+template <int IMM>
 D3_DEVINL uint32_t lds_u16(uint32_t saddr) {
   unsigned short v;
   asm volatile("ld.shared.u16 %0, [%1 + %2];" : "=h"(v) : "r"(saddr), "n"(IMM) : "memory");
@@ -117,6 +127,13 @@ D3_DEVINL void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c
       " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+// L2 prefetch of a tile (no shared-memory destination, no barrier)
+D3_DEVINL void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 D3_DEVINL void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
@@ -262,14 +279,16 @@ D3_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart).
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused for SW128 K-major)
 //   bits [32,46) stride byte offset >> 4   bits [46,48) version = 1
-//   bits [49,52) base offset               bits [61,64) layout type (2 = SWIZZLE_128B)
+//   bits [49,52) base offset (= 0)         bits [61,64) layout type (2 = SWIZZLE_128B)
 D3_DEVINL uint64_t make_sw128_kmajor_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>(1) << 16;            // LBO (ignored for swizzled K-major)
   d |= static_cast<uint64_t>(1024 >> 4) << 32;    // SBO = 8 rows * 128 B
   d |= static_cast<uint64_t>(1) << 46;            // version
-  d |= static_cast<uint64_t>((saddr >> 7) & 0x7) << 49;  // base offset (0 when 1024 B aligned)
+  // base offset (bits 49-51) stays 0: measured on B200, the 128B-swizzle XOR is taken from the absolute shared-memory
+  // address bits, so a start address shifted by whole 128 B rows (halo-strip windows) needs no phase correction
+  // (setting it to (addr >> 7) & 7 produces wrong operands).
   d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
   return d;
 }

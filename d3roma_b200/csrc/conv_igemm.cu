@@ -47,6 +47,8 @@ struct ConvKArgs {
   int res_pitch;
   double* stats;
   uint32_t a_bytes;
+  int l2_prefetch; // strips variant: producer prefetches the next tile's input rows into L2
+  int strip_slot;  // strips variant: bytes per strip ring slot ((TW+2)*128 rounded up to 1 KB)
   int t_direct;    // pixels-as-N kernel: epilogue stores straight to global (no staging / TMA store)
   uint16_t* out;   // output base pointer + pitch for the direct epilogue
   int out_pitch;
@@ -391,6 +393,41 @@ D3_DEVINL void epi_t_chunk(const uint32_t (&v)[32], uint32_t sa, const uint32_t 
   }
 }
 
+// Paired variant of the chunk epilogue: lanes 2k / 2k+1 (adjacent channels) exchange values so that the even lane
+// stores the 32-bit word {ch, ch+1} of pixel row j and the odd lane the word {ch-1, ch} of pixel row j+4.  Rows j and
+// j+4 sit in opposite halves of the swizzle pattern, so a warp's 32 word stores hit 32 distinct banks (the 16-bit
+// version measured 50 % bank conflicts).  Statistics: each lane sums both halves of the words it stores; the quad
+// total is the sum over the 4 lanes of a quad, which is all the caller needs.
+template <int DT, bool HAS_RES, int BASE = 0, int JJ = 0>
+D3_DEVINL void epi_t_chunk2(const uint32_t (&v)[32], uint32_t sa_lane, const uint32_t (&myswz)[4], float bias,
+                            uint32_t vmask, bool odd, float& s_sum, float& s_sq) {
+  if constexpr (BASE < 32) {
+    constexpr int J0 = BASE + JJ, J1 = J0 + 4;
+    const float x0 = __uint_as_float(v[J0]) + bias;   // own channel, pixel J0
+    const float x1 = __uint_as_float(v[J1]) + bias;   // own channel, pixel J1
+    const float recv = __shfl_xor_sync(0xffffffffu, odd ? x0 : x1, 1);
+    float lo = odd ? recv : x0;                       // even: {ch @J0, ch+1 @J0}; odd: {ch-1 @J1, ch @J1}
+    float hi = odd ? x1 : recv;
+    const uint32_t addr = sa_lane + myswz[JJ];
+    if constexpr (HAS_RES) {
+      const float2 r = unpack2<DT>(lds_u32<J0 * 128>(addr));
+      lo += r.x;
+      hi += r.y;
+    }
+    const uint32_t pk = pack2<DT>(lo, hi);
+    sts_u32<J0 * 128>(addr, pk);
+    const bool ok = ((vmask >> (odd ? J1 : J0)) & 1u) != 0;
+    const float2 xr = unpack2<DT>(pk);
+    const float a0 = ok ? xr.x : 0.f, a1 = ok ? xr.y : 0.f;
+    s_sum += a0 + a1;
+    s_sq = fmaf(a0, a0, fmaf(a1, a1, s_sq));
+    if constexpr (JJ < 3)
+      epi_t_chunk2<DT, HAS_RES, BASE, JJ + 1>(v, sa_lane, myswz, bias, vmask, odd, s_sum, s_sq);
+    else
+      epi_t_chunk2<DT, HAS_RES, BASE + 8, 0>(v, sa_lane, myswz, bias, vmask, odd, s_sum, s_sq);
+  }
+}
+
 // Variant that writes straight to global memory (no staging tile, no TMA store): the warp's 32 lanes hold 32
 // consecutive channels of one pixel, i.e. each store instruction covers one contiguous 64-byte segment.
 template <int DT, bool HAS_RES, int J = 0>
@@ -412,22 +449,38 @@ D3_DEVINL void epi_t_chunk_global(const uint32_t (&v)[32], uint16_t* gp, const u
 
 constexpr int kTThreads = 384;  // warps 0-3: producer / MMA / TMEM alloc / idle; warps 4-11: two epilogue groups
 
-template <int STAGES, int DT>
+constexpr int kNStrips = 3;   // halo-strip ring slots (strips variant)
+constexpr int kNWts = 6;      // weight-tile ring slots (strips variant)
+
+// STRIPS = true: 3x3 stride-1 convs on wide images.  The pixel operand of a tile (one image-row segment of TW pixels)
+// is loaded ONCE per (input row, 64-channel block) as a halo "strip" of TW+2 pixels and used by the three kw taps
+// through row-shifted UMMA descriptors (start address + kw*128 B; the swizzle follows the absolute address): the activation TMA
+// traffic drops 3x and the bytes that must be in flight to cover L2 latency with it.  Weights stream through their
+// own ring.  K-loop order: for cb: for kh: strip(h+kh-1, cb) -> for kw: weight tile (kh, kw, cb) -> 4 MMAs.
+template <int STAGES, int DT, bool STRIPS>
 __global__ void __launch_bounds__(kTThreads, 1)
 conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS1,
                     const __grid_constant__ CUtensorMap tmS2, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                     const ConvKArgs a) {
   constexpr uint32_t kTmemCols = 512;  // 2 accumulator stages x 256 pixel columns
+  constexpr int NBAR = STRIPS ? (kNStrips + kNWts) : STAGES;  // ring barriers (full + empty each)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* staging = smem + STAGES * kTStageBytes;
+  // STRIPS: [kNStrips strip slots of a.strip_slot bytes][kNWts weight tiles of 16 KB]; else STAGES x {16 KB W, 32 KB P}
+  uint8_t* wring = STRIPS ? smem + kNStrips * a.strip_slot : smem;
+  uint8_t* staging = STRIPS ? wring + kNWts * kWTileBytes : smem + STAGES * kTStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kTStagingBytes);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + NBAR;
+  uint64_t* tfull_bar = empty_bar + NBAR;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* res_bar = tempty_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 1);
+  // strips variant: barriers [0, kNStrips) belong to the strip ring, [kNStrips, NBAR) to the weight ring
+  uint64_t* sfull = full_bar;
+  uint64_t* sempty = empty_bar;
+  uint64_t* wfull = full_bar + kNStrips;
+  uint64_t* wempty = empty_bar + kNStrips;
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -440,7 +493,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmO);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < NBAR; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -462,7 +515,50 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    if (STRIPS && lane == 0) {
+      int ss = 0, ws = 0;
+      uint32_t sphase = 0, wphase = 0;
+      const uint32_t strip_bytes = (uint32_t)(a.TW + 2) * 128u;
+      const uint32_t plain_bytes = (uint32_t)a.TW * 128u;
+      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(a, tile, 128);
+        const int n_items = 3 * a.cbMain + a.kbSc1 + a.kbSc2;  // strip loads per tile
+        if (a.l2_prefetch && tile + (int)gridDim.x < a.numTiles) {
+          // pull the NEXT tile's input rows into L2 now, a whole tile ahead of the TMA loads that need them
+          const TileCoord tn = decode_tile(a, tile + gridDim.x, 128);
+          for (int cb = 0; cb < a.cbMain; ++cb)
+            for (int kh = 0; kh < 3; ++kh) tma_prefetch_4d(&tmA, cb * 64, tn.w0 - 1, tn.h0 + kh - 1, tn.b);
+          for (int j = 0; j < a.kbSc1; ++j) tma_prefetch_4d(&tmS1, j * 64, tn.w0, tn.h0, tn.b);
+          for (int j = 0; j < a.kbSc2; ++j) tma_prefetch_4d(&tmS2, j * 64, tn.w0, tn.h0, tn.b);
+        }
+        for (int it = 0; it < n_items; ++it) {
+          mbar_wait(&sempty[ss], sphase ^ 1);
+          uint8_t* sS = smem + ss * a.strip_slot;
+          int nkb, kb0;  // weight K-blocks served by this strip and the first one's K index (in 64-column units)
+          if (it < 3 * a.cbMain) {
+            const int cb = it / 3, kh = it - cb * 3;
+            mbar_arrive_expect_tx(&sfull[ss], strip_bytes);
+            tma_load_4d(sS, &tmA, &sfull[ss], cb * 64, t.w0 - 1, t.h0 + kh - 1, t.b);
+            nkb = 3;
+            kb0 = (kh * 3) * a.cbMain + cb;  // tap (kh, kw) -> K-block (kh*3 + kw) * cbMain + cb
+          } else {
+            const int j = it - 3 * a.cbMain;
+            mbar_arrive_expect_tx(&sfull[ss], plain_bytes);
+            if (j < a.kbSc1) tma_load_4d(sS, &tmS1, &sfull[ss], j * 64, t.w0, t.h0, t.b);
+            else tma_load_4d(sS, &tmS2, &sfull[ss], (j - a.kbSc1) * 64, t.w0, t.h0, t.b);
+            nkb = 1;
+            kb0 = a.kbMain + j;
+          }
+          if (++ss == kNStrips) { ss = 0; sphase ^= 1; }
+          for (int i = 0; i < nkb; ++i) {
+            mbar_wait(&wempty[ws], wphase ^ 1);
+            mbar_arrive_expect_tx(&wfull[ws], kWTileBytes);
+            tma_load_2d(wring + ws * kWTileBytes, &tmB, &wfull[ws], (kb0 + i * a.cbMain) * 64, t.n0);
+            if (++ws == kNWts) { ws = 0; wphase ^= 1; }
+          }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
@@ -508,7 +604,45 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    if (STRIPS && lane == 0) {
+      const uint32_t idesc = make_idesc_16bit(kTileM, n_mma, DT == kBF16);
+      int ss = 0, ws = 0;
+      uint32_t sphase = 0, wphase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        const int n_items = 3 * a.cbMain + a.kbSc1 + a.kbSc2;
+        uint32_t first = 1;
+        for (int it = 0; it < n_items; ++it) {
+          mbar_wait(&sfull[ss], sphase);
+          tc_fence_after();
+          const uint32_t sS = smem_u32(smem + ss * a.strip_slot);
+          const int nkb = (it < 3 * a.cbMain) ? 3 : 1;
+          for (int i = 0; i < nkb; ++i) {
+            mbar_wait(&wfull[ws], wphase);
+            tc_fence_after();
+            const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(wring + ws * kWTileBytes));
+            // pixel window of tap kw = i: rows i .. i+TW-1 of the strip
+            const uint64_t bdesc = make_sw128_kmajor_desc(sS + (uint32_t)i * 128u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+            }
+            first = 0;
+            umma_commit(&wempty[ws]);
+            if (++ws == kNWts) { ws = 0; wphase ^= 1; }
+          }
+          umma_commit(&sempty[ss]);
+          if (++ss == kNStrips) { ss = 0; sphase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    } else if (lane == 0) {
       const uint32_t idesc = make_idesc_16bit(kTileM, n_mma, DT == kBF16);
       int stage = 0;
       uint32_t phase = 0;
@@ -551,6 +685,10 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t swz[8];  // swizzled 16-byte chunk offset of this channel for row (pixel) index % 8
 #pragma unroll
     for (int i = 0; i < 8; ++i) swz[i] = (ch16 ^ (uint32_t)i) << 4;
+    const bool odd = (lane & 1u) != 0;
+    uint32_t myswz[4];  // swizzle offsets of the 4 pixel rows (mod 8) this lane stores: even lanes 0-3, odd lanes 4-7
+#pragma unroll
+    for (int i = 0; i < 4; ++i) myswz[i] = swz[i + (odd ? 4 : 0)];
     const bool has_res = a.residual != nullptr;
     // A pass = PW (<= 64) consecutive pixels of one tile row = a contiguous range of accumulator columns.  Staging is
     // double-buffered by pass so the TMA store of pass p overlaps the math of pass p+1.
@@ -652,12 +790,14 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * 256 + r * a.TW + sg * PW + c0, v);
           const uint32_t vmask = __ballot_sync(
               0xffffffffu, (c0 + (int)lane < PW) && (h < a.Ho) && (wpass + c0 + (int)lane < a.Wo));
-          const uint32_t sa = smem_u32(sbuf) + half * (kStagingBytes / 2) + (uint32_t)c0 * 128u + chb;
+          // word address of this lane's channel pair; odd lanes write 4 pixel rows further down (see epi_t_chunk2)
+          const uint32_t sa = smem_u32(sbuf) + half * (kStagingBytes / 2) + (uint32_t)c0 * 128u + (chb & ~3u) +
+                              (odd ? 512u : 0u);
           tmem_ld_wait();
           if (has_res) {
-            epi_t_chunk<DT, true>(v, sa, swz, bias, vmask, s_sum, s_sq);
+            epi_t_chunk2<DT, true>(v, sa, myswz, bias, vmask, odd, s_sum, s_sq);
           } else {
-            epi_t_chunk<DT, false>(v, sa, swz, bias, vmask, s_sum, s_sq);
+            epi_t_chunk2<DT, false>(v, sa, myswz, bias, vmask, odd, s_sum, s_sq);
           }
         }
         if (ps == passes - 1) {
@@ -703,20 +843,36 @@ template <int STAGES>
 constexpr size_t conv_t_smem_bytes() {
   return 1024 + STAGES * kTStageBytes + kTStagingBytes + (2 * STAGES + 5) * 8 + 16;
 }
+inline size_t conv_ts_smem_bytes(int strip_slot) {
+  return 1024 + (size_t)kNStrips * strip_slot + kNWts * kWTileBytes + kTStagingBytes +
+         (2 * (kNStrips + kNWts) + 5) * 8 + 16;
+}
 
 template <int STAGES, int DT>
 cudaError_t launch_conv_t(int grid, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmS1,
                           const CUtensorMap& tmS2, const CUtensorMap& tmB, const CUtensorMap& tmO,
-                          const CUtensorMap& tmR, const ConvKArgs& a) {
+                          const CUtensorMap& tmR, const ConvKArgs& a, bool strips) {
+  if (strips) {
+    const size_t smem = conv_ts_smem_bytes(a.strip_slot);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+      cudaError_t e = cudaFuncSetAttribute(conv_igemm_t_kernel<STAGES, DT, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr_smem = smem;
+    }
+    conv_igemm_t_kernel<STAGES, DT, true><<<grid, kTThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, tmR, a);
+    return cudaSuccess;
+  }
   constexpr size_t smem = conv_t_smem_bytes<STAGES>();
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_t_kernel<STAGES, DT>,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_t_kernel<STAGES, DT, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  conv_igemm_t_kernel<STAGES, DT><<<grid, kTThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, tmR, a);
+  conv_igemm_t_kernel<STAGES, DT, false><<<grid, kTThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, tmR, a);
   return cudaSuccess;
 }
 
@@ -1099,7 +1255,28 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   static int no_t = -1;
   if (no_t < 0) { const char* e = getenv("D3_CONV_NO_T"); no_t = e ? atoi(e) : 0; }
   const bool use_t = (p->Cout == 128) && !no_t;
-  if (use_t) choose_tile_t(Ho, Wo, &a.TH, &a.TW); else choose_tile(Ho, Wo, &a.TH, &a.TW);
+  // halo-strip variant: plain 3x3 stride-1 convs on images at least 160 pixels wide
+  // (correct and parity-tested, but measured no faster than per-tap tiles in round 1 - profiles/r01_conv_experiments.txt -
+  // so it is opt-in: D3_CONV_STRIPS=1)
+  static int want_strips = -1;
+  if (want_strips < 0) { const char* e = getenv("D3_CONV_STRIPS"); want_strips = e ? atoi(e) : 0; }
+  const bool use_strips = use_t && want_strips && p->ksize == 3 && p->stride == 1 && phase == 0 && Wo >= 160;
+  if (use_strips) {
+    // one image-row segment per tile; uniform width = smallest multiple of 16 that covers W in ceil(W/256) tiles
+    const int nseg = ceil_div(Wo, 256);
+    a.TH = 1;
+    a.TW = ((ceil_div(Wo, nseg) + 15) / 16) * 16;
+  } else if (use_t) {
+    choose_tile_t(Ho, Wo, &a.TH, &a.TW);
+  } else {
+    choose_tile(Ho, Wo, &a.TH, &a.TW);
+  }
+  {
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("D3_CONV_L2_PREFETCH"); pf = e ? atoi(e) : 0; }
+    a.l2_prefetch = pf;
+  }
+  a.strip_slot = use_strips ? (((a.TW + 2) * 128 + 1023) / 1024) * 1024 : 0;
   a.tilesH = ceil_div(Ho, a.TH);
   a.tilesW = ceil_div(Wo, a.TW);
   const int pixTiles = p->B * a.tilesH * a.tilesW;
@@ -1161,7 +1338,7 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
     uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
     uint64_t str[3] = {(uint64_t)p->x_pitch * 2, (uint64_t)p->W * p->x_pitch * 2,
                        (uint64_t)p->H * p->W * p->x_pitch * 2};
-    uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
+    uint32_t box[4] = {64, (uint32_t)(use_strips ? a.TW + 2 : a.TW), (uint32_t)a.TH, 1};
     rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmA, p->x, 4, dims, str, box);
   } else {
     // parity-split view: (pw*pitch + c, w/2, h parity, h/2, b)
@@ -1245,9 +1422,9 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
     else
       le = launch_conv2<256, 5, kF16>(npg, stream, tmA, tmS1, tmS2, tmB, tmO, a);
   } else if (use_t && p->dtype == D3_DTYPE_BF16)
-    le = launch_conv_t<4, kBF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, tmR, a);
+    le = launch_conv_t<4, kBF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, tmR, a, use_strips);
   else if (use_t)
-    le = launch_conv_t<4, kF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, tmR, a);
+    le = launch_conv_t<4, kF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, tmR, a, use_strips);
   else if (BN == 128 && p->dtype == D3_DTYPE_BF16)
     le = launch_conv<128, 5, kBF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, a);
   else if (BN == 128)

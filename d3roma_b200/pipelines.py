@@ -63,6 +63,42 @@ class GuidedDiffusionPipeline:
         self.unet.to(device)
         return self
 
+    def save_pretrained(self, path):
+        """diffusers directory layout: model_index.json, unet/, scheduler/, guidance/ (train.py:682, 701)."""
+        import json
+        import os
+        from ._config import save_config
+        os.makedirs(path, exist_ok=True)
+        self.unet.save_pretrained(os.path.join(path, "unet"))
+        save_config(self.scheduler, os.path.join(path, "scheduler"), "scheduler_config.json")
+        g = self.guidance
+        os.makedirs(os.path.join(path, "guidance"), exist_ok=True)
+        with open(os.path.join(path, "guidance", "config.json"), "w") as f:
+            json.dump({"_class_name": "FlowGuidance", "flow_guidance_weight": g.flow_guidance_weight,
+                       "perturb_start_ratio": g.perturb_start_ratio, "flow_guidance_mode": g.flow_guidance_mode}, f)
+        with open(os.path.join(path, "model_index.json"), "w") as f:
+            json.dump({"_class_name": "GuidedDiffusionPipeline", "unet": ["d3roma_b200", "UNet2DModel"],
+                       "scheduler": ["d3roma_b200", type(self.scheduler).__name__],
+                       "guidance": ["d3roma_b200", "FlowGuidance"]}, f, indent=2)
+
+    @classmethod
+    def from_pretrained(cls, path, compute_dtype=None, device="cuda"):
+        """evaluate.py:314 / inference.py:73: ``GuidedDiffusionPipeline.from_pretrained(path).to("cuda")``."""
+        import os
+        from ._config import load_config
+        from .guidance import FlowGuidance
+        from .scheduler_ddim import MyDDIMScheduler
+        from .scheduler_ddpm import MyDDPMScheduler
+        from .unet import UNet2DModel
+        unet = UNet2DModel.from_pretrained(os.path.join(path, "unet"), compute_dtype=compute_dtype, device=device)
+        scfg = load_config(os.path.join(path, "scheduler"), "scheduler_config.json")
+        sched_cls = MyDDPMScheduler if "DDPM" in scfg.get("_class_name", "DDIM") else MyDDIMScheduler
+        scheduler = sched_cls.from_config(scfg)
+        gpath = os.path.join(path, "guidance", "config.json")
+        gcfg = load_config(os.path.join(path, "guidance"), "config.json") if os.path.exists(gpath) else {}
+        gcfg.pop("_class_name", None)
+        return cls(unet, scheduler, FlowGuidance(**gcfg))
+
     def set_progress_bar_config(self, **kwargs):
         self._progress_bar_config = kwargs
 

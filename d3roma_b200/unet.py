@@ -117,6 +117,8 @@ class UNet2DModel:
         self._specs = _resnet_specs()
         self._arena: Optional[_StatsArena] = None
         self._loaded = False
+        self.keep_state_dict = True   # keep a host copy of the loaded fp32 state_dict (for save_pretrained)
+        self._sd_cpu = None
         self._graphs: Dict[tuple, dict] = {}
         self.graph_kernel_launches = 0  # kernels executed through CUDA-graph replays (for launch accounting)
 
@@ -194,7 +196,44 @@ class UNet2DModel:
             if missing:
                 raise KeyError(f"unexpected keys in state_dict: {sorted(missing)[:5]} ...")
         self._loaded = True
+        self._sd_cpu = {k: v.to("cpu") for k, v in sd.items()} if self.keep_state_dict else None
         return self
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """The diffusers-keyed fp32 state_dict this model was loaded from (kept on the host)."""
+        if self._sd_cpu is None:
+            raise RuntimeError("state_dict() needs keep_state_dict=True at load time")
+        return dict(self._sd_cpu)
+
+    # ---- diffusers-layout persistence (train.py:682,701 `pipeline.save_pretrained`, evaluate.py:314 `from_pretrained`)
+    def save_pretrained(self, path):
+        import json
+        import os
+        from safetensors.torch import save_file
+        os.makedirs(path, exist_ok=True)
+        cfg = dict(vars(self.config), _class_name="UNet2DModel", compute_dtype=self.compute_dtype)
+        with open(os.path.join(path, "config.json"), "w") as f:
+            json.dump(cfg, f, indent=2)
+        save_file({k: v.contiguous() for k, v in self.state_dict().items()},
+                  os.path.join(path, "diffusion_pytorch_model.safetensors"))
+
+    @classmethod
+    def from_pretrained(cls, path, compute_dtype: Optional[str] = None, device="cuda"):
+        import json
+        import os
+        with open(os.path.join(path, "config.json")) as f:
+            cfg = json.load(f)
+        cfg.pop("_class_name", None)
+        if compute_dtype is not None:
+            cfg["compute_dtype"] = compute_dtype
+        net = cls(**cfg).to(device)
+        st = os.path.join(path, "diffusion_pytorch_model.safetensors")
+        if os.path.exists(st):
+            from safetensors.torch import load_file
+            sd = load_file(st)
+        else:
+            sd = torch.load(os.path.join(path, "diffusion_pytorch_model.bin"), map_location="cpu")
+        return net.load_state_dict(sd)
 
     @staticmethod
     def _rprefix(kind, i, j):

@@ -114,3 +114,21 @@ def test_guided_pipeline_runs_and_differs():
         outs.append(pipe(None, left, right, raw, None, None, num_inference_steps=4, num_intermediate_images=1,
                          cond_channels="left+right+raw", generator=torch.Generator().manual_seed(9)).images)
     assert torch.isfinite(outs[1]).all() and not torch.equal(outs[0], outs[1])
+
+
+def test_save_and_from_pretrained_roundtrip(tmp_path):
+    d, ref, net = _make("fp16")
+    pipe = d.GuidedDiffusionPipeline(net, d.MyDDIMScheduler.from_config(DDIM_CFG),
+                                     d.FlowGuidance(flow_guidance_weight=0.0, flow_guidance_mode="stereo"))
+    pipe.save_pretrained(tmp_path)
+    for f in ("model_index.json", "unet/config.json", "unet/diffusion_pytorch_model.safetensors",
+              "scheduler/scheduler_config.json", "guidance/config.json"):
+        assert (tmp_path / f).exists(), f
+    pipe2 = d.GuidedDiffusionPipeline.from_pretrained(tmp_path)
+    assert pipe2.scheduler.config.prediction_type == "sample" and pipe2.guidance.flow_guidance_mode == "stereo"
+    g = torch.Generator().manual_seed(4)
+    left, right = torch.rand(1, 3, 32, 64, generator=g) * 2 - 1, torch.rand(1, 3, 32, 64, generator=g) * 2 - 1
+    raw = torch.rand(1, 1, 32, 64, generator=g) * 2 - 1
+    outs = [p(None, left, right, raw, None, None, num_inference_steps=2, num_intermediate_images=1,
+              cond_channels="left+right+raw", generator=torch.Generator().manual_seed(1)).images for p in (pipe, pipe2)]
+    assert torch.equal(outs[0], outs[1])
