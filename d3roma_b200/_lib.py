@@ -17,6 +17,7 @@ class D3Error(RuntimeError):
 
 DTYPE_BF16 = 0
 DTYPE_F16 = 1
+DTYPE_F32 = 2
 
 
 class ConvParams(C.Structure):

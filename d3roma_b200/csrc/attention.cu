@@ -175,6 +175,7 @@ extern "C" int d3_attention_hd8(const void* qkv, int pitch, int B, int N, int C,
   using namespace d3;
   D3_REQUIRE(qkv && out && C % 8 == 0 && pitch >= 3 * C && pitch % 8 == 0 && opitch % 2 == 0,
              "attention: bad arguments");
+  if (dtype == D3_DTYPE_F32) return attention_f32(qkv, pitch, B, N, C, out, opitch, static_cast<cudaStream_t>(stream));
   const int Npad = (N + kKeyBlock - 1) / kKeyBlock * kKeyBlock;
   const size_t smem = (size_t)Npad * 16 + (size_t)8 * (Npad + kVPad) * 2;
   D3_REQUIRE(smem <= 220 * 1024, "attention: N=%d tokens exceed the shared-memory K/V budget", N);

@@ -1228,6 +1228,11 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   D3_REQUIRE(p != nullptr, "conv: null params");
   D3_REQUIRE(p->ksize == 3 || p->ksize == 1, "conv: ksize must be 1 or 3 (got %d)", p->ksize);
   D3_REQUIRE(p->stride == 1 || (p->stride == 2 && p->ksize == 3), "conv: unsupported stride %d", p->stride);
+  if (p->dtype == D3_DTYPE_F32) {
+    D3_REQUIRE(p->x && p->w && p->out && p->bias, "conv: null pointer");
+    D3_REQUIRE(p->up2x_phase >= 0 && p->up2x_phase <= 4, "conv: bad up2x_phase");
+    return conv2d_f32(p, stream);
+  }
   D3_REQUIRE(p->Cin > 0 && p->Cin % 64 == 0, "conv: Cin must be a multiple of 64 (got %d)", p->Cin);
   D3_REQUIRE(p->Cout > 0 && p->Cout % 128 == 0, "conv: Cout must be a multiple of 128 (got %d)", p->Cout);
   D3_REQUIRE(p->C1 % 64 == 0 && p->C2 % 64 == 0, "conv: shortcut channels must be multiples of 64");

@@ -259,6 +259,7 @@ extern "C" int d3_im2col_input(const float* sample, int Cs, const float* cond, i
   using namespace d3;
   D3_REQUIRE(sample && out && (Cc == 0 || cond), "im2col: null pointer");
   D3_REQUIRE(9 * (Cs + Cc) <= 128, "im2col: 9*Cin = %d exceeds the 128-wide K slab", 9 * (Cs + Cc));
+  if (dtype == D3_DTYPE_F32) return im2col_f32(sample, Cs, cond, Cc, B, H, W, out, static_cast<cudaStream_t>(stream));
   int blocks = B * H * ((W + kI2cPix - 1) / kI2cPix);
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   if (dtype == D3_DTYPE_F16)
@@ -277,6 +278,8 @@ extern "C" int d3_conv_out_fused(const void* x, int pitch, const double* stats, 
   using namespace d3;
   D3_REQUIRE(x && stats && gamma && beta && w && bias && out, "conv_out: null pointer");
   D3_REQUIRE(dc == 1 || dc == 3, "conv_out: depth_channels must be 1 or 3 (got %d)", dc);
+  if (dtype == D3_DTYPE_F32)
+    return conv_out_f32(x, pitch, stats, gamma, beta, w, bias, B, H, W, dc, eps, out, static_cast<cudaStream_t>(stream));
   ConvOutArgs a{static_cast<const uint16_t*>(x), pitch, stats, gamma, beta, w, bias, out, B, H, W, eps};
   D3_REQUIRE(pitch % 8 == 0, "conv_out: pitch must be a multiple of 8");
   dim3 grid(ceil_div(W, kCoTX), ceil_div(H, kCoTY), B);

@@ -155,6 +155,9 @@ extern "C" int d3_groupnorm_silu(const void* x1, int C1, int p1, const double* s
   const int C = C1 + C2;
   D3_REQUIRE(x1 && stats1 && gamma && beta && out, "groupnorm: null pointer");
   D3_REQUIRE(C2 == 0 || (x2 && stats2), "groupnorm: second source missing");
+  if (dtype == D3_DTYPE_F32)
+    return groupnorm_f32(x1, C1, p1, stats1, x2, C2, p2, stats2, gamma, beta, B, HW, groups, eps, apply_silu, out, pout,
+                         static_cast<cudaStream_t>(stream));
   D3_REQUIRE(C <= kMaxC && C % groups == 0 && (C / groups) % 4 == 0 && groups <= 32,
              "groupnorm: unsupported C=%d groups=%d", C, groups);
   D3_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && p1 % 8 == 0 && (C2 == 0 || p2 % 8 == 0) && pout % 8 == 0,

@@ -34,6 +34,17 @@ int num_sms();
                              cudaGetErrorString(_e));                                         \
   } while (0)
 
+// fp32 reference-precision variants (fp32_path.cu), reached through the same C-ABI entry points with D3_DTYPE_F32
+int conv2d_f32(const d3_conv_params* p, cudaStream_t stream);
+int groupnorm_f32(const void* x1, int C1, int p1, const double* stats1, const void* x2, int C2, int p2,
+                  const double* stats2, const float* gamma, const float* beta, int B, int HW, int groups, float eps,
+                  int apply_silu, void* out, int pout, cudaStream_t stream);
+int attention_f32(const void* qkv, int pitch, int B, int N, int C, void* out, int opitch, cudaStream_t stream);
+int conv_out_f32(const void* x, int pitch, const double* stats, const float* gamma, const float* beta, const float* w,
+                 const float* bias, int B, int H, int W, int dc, float eps, float* out, cudaStream_t stream);
+int im2col_f32(const float* sample, int Cs, const float* cond, int Cc, int B, int H, int W, void* out,
+               cudaStream_t stream);
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace d3

@@ -28,12 +28,15 @@ def _dt(t: torch.Tensor) -> int:
         return _lib.DTYPE_BF16
     if t.dtype == torch.float16:
         return _lib.DTYPE_F16
-    raise ValueError(f"expected a bf16 or fp16 tensor, got {t.dtype}")
+    if t.dtype == torch.float32:
+        return _lib.DTYPE_F32
+    raise ValueError(f"expected a bf16, fp16 or fp32 tensor, got {t.dtype}")
 
 
 def _check_nhwc(t: torch.Tensor, name: str) -> None:
-    if not (t.is_cuda and t.dtype in (torch.bfloat16, torch.float16) and t.dim() == 4 and t.stride(3) == 1):
-        raise ValueError(f"{name}: expected a CUDA bf16/fp16 NHWC tensor with contiguous channels")
+    if not (t.is_cuda and t.dtype in (torch.bfloat16, torch.float16, torch.float32) and t.dim() == 4
+            and t.stride(3) == 1):
+        raise ValueError(f"{name}: expected a CUDA bf16/fp16/fp32 NHWC tensor with contiguous channels")
     B, H, W, _ = t.shape
     p = t.stride(2)
     if t.stride(1) != W * p or (B > 1 and t.stride(0) != H * W * p):

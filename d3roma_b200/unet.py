@@ -107,10 +107,11 @@ class UNet2DModel:
                                       down_block_types=tuple(down_block_types), up_block_types=tuple(up_block_types),
                                       attention_head_dim=8, norm_num_groups=32, norm_eps=1e-5)
         self.in_channels, self.out_channels = in_channels, out_channels
-        if compute_dtype not in ("bf16", "fp16"):
-            raise ValueError("compute_dtype must be 'bf16' or 'fp16'")
+        if compute_dtype not in ("bf16", "fp16", "fp32"):
+            raise ValueError("compute_dtype must be 'bf16', 'fp16' (tcgen05 tensor-core paths) or 'fp32' "
+                             "(CUDA-core reference-precision path)")
         self.compute_dtype = compute_dtype
-        self._adt = torch.bfloat16 if compute_dtype == "bf16" else torch.float16
+        self._adt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[compute_dtype]
         self.device = torch.device("cpu")
         self.dtype = torch.float32  # dtype of the pipeline-facing tensors
         self._w: Dict[str, torch.Tensor] = {}

@@ -38,6 +38,9 @@ extern "C" {
  * kind::f16 at the same rate with fp32 accumulation; F16 carries 3 more mantissa bits (parity). */
 #define D3_DTYPE_BF16 0
 #define D3_DTYPE_F16 1
+/* fp32 storage + CUDA-core FFMA arithmetic: the reference-precision path for the <= 1e-4 tolerance configuration
+ * (BASELINE configs[3]); accepted by every entry point that takes a dtype, ~40x slower than the tensor-core path. */
+#define D3_DTYPE_F32 2
 
 /* ---- library ------------------------------------------------------------------------------- */
 const char* d3_last_error(void);

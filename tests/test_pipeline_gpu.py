@@ -132,3 +132,53 @@ def test_save_and_from_pretrained_roundtrip(tmp_path):
     outs = [p(None, left, right, raw, None, None, num_inference_steps=2, num_intermediate_images=1,
               cond_channels="left+right+raw", generator=torch.Generator().manual_seed(1)).images for p in (pipe, pipe2)]
     assert torch.equal(outs[0], outs[1])
+
+
+def test_config4_style_ddpm100_fp32_tolerance():
+    """BASELINE configs[3] in miniature: SceneFlow variant (rgb+left+right cond, Cin=12, dc=3), DDPM 100 of 128 steps,
+    fp32 reference-precision path; per-step model-output and final-image max-abs <= 1e-4 vs the oracle loop."""
+    import d3roma_b200 as d
+    import d3roma_b200.scheduler_ddpm as sd
+    from oracle import pipeline_ref
+    from oracle.unet_ref import make_unet
+    hw = (32, 64)
+    ref = make_unet(12, 3, seed=0, sample_size=hw)
+    net = d.UNet2DModel(sample_size=hw, in_channels=12, out_channels=3, compute_dtype="fp32").to("cuda")
+    net.load_state_dict(ref.state_dict())
+    g = torch.Generator().manual_seed(8)
+    rgb, left, right = (torch.rand(1, 3, *hw, generator=g) * 2 - 1 for _ in range(3))
+    x_T = torch.randn((1, 3, *hw), generator=torch.Generator().manual_seed(42))
+    rec = []
+    torch.manual_seed(77)
+    want = pipeline_ref.run_pipeline(ref, x_T, {"rgb": rgb, "left": left, "right": right}, "rgb+left+right",
+                                     sampler="ddpm", num_inference_steps=100, steps_offset=0,
+                                     ddpm_noise=lambda i, shape: torch.randn(shape), record=rec)
+    pipe = d.GuidedDiffusionPipeline(net, d.MyDDPMScheduler.from_config(DDPM_CFG), d.FlowGuidance(flow_guidance_weight=0.0))
+    orig = sd.randn_tensor
+    sd.randn_tensor = lambda shape, generator=None, device=None, dtype=None: torch.randn(tuple(shape), dtype=dtype).to(device)
+    torch.manual_seed(77)
+    try:
+        out = pipe(rgb, left, right, None, None, None, num_inference_steps=100, num_intermediate_images=4,
+                   depth_channels=3, cond_channels="rgb+left+right", generator=torch.Generator().manual_seed(42))
+    finally:
+        sd.randn_tensor = orig
+    err = float((out.images.cpu() - want).abs().max())
+    print(f"DDPM-100 fp32: final-image max-abs err {err:.3e}")
+    assert err <= 1e-4
+    assert out.images_pred_orig.shape == (1, 12, 32, 64)
+    # per-step model output with teacher forcing on the oracle trajectory
+    sch = d.MyDDPMScheduler.from_config(DDPM_CFG)
+    sch.set_timesteps(100)
+    cond = torch.cat([rgb, left, right], 1).cuda()
+    from oracle import schedulers_ref as S
+    ac = torch.cumprod(1 - S.make_betas("squaredcos_cap_v2", 128), 0)
+    x = x_T.clone()
+    torch.manual_seed(77)
+    worst = 0.0
+    for i, t in enumerate(sch.timesteps.tolist()):
+        m = net.forward_split(x.cuda(), cond, t).cpu()
+        worst = max(worst, float((m - rec[i]).abs().max()))
+        noise = torch.randn(m.shape) if t > 0 else None
+        x, _, _ = S.ddpm_step(rec[i], t, x, ac, 128, 100, noise, prediction_type="sample", thresholding=True)
+    print(f"DDPM-100 fp32: worst per-step model-output max-abs err {worst:.3e}")
+    assert worst <= 1e-4
