@@ -10,5 +10,6 @@ from .prepost import SIM_CAMERA, Camera, InputPadder, Normalizer  # noqa: F401
 from .scheduler_ddim import DDIMSchedulerOutput, MyDDIMScheduler  # noqa: F401
 from .scheduler_ddpm import DDPMSchedulerOutput, MyDDPMScheduler  # noqa: F401
 from .unet import UNet2DModel  # noqa: F401
+from .metrics import compute_errors, compute_scale_and_shift, metrics_to_dict  # noqa: F401
 
 __version__ = "0.1.0"

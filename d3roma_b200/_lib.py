@@ -94,6 +94,11 @@ def _declare(lib: C.CDLL) -> None:
         "d3_pad_replicate": (i32, [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]),
         "d3_crop": (i32, [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]),
         "d3_clamp_into": (i32, [vp, i64, i64, i64, i64, f32, f32, vp, vp]),
+        "d3_disp_metrics": (i32, [vp, vp, vp, vp, i32, i32, i64, vp, vp]),
+        "d3_scale_shift_lsq": (i32, [vp, vp, vp, i32, i64, vp, vp]),
+        "d3_masked_minmax": (i32, [vp, vp, i32, i64, vp, vp]),
+        "d3_normalize_ssi": (i32, [vp, vp, vp, i32, i64, f32, f32, vp, vp]),
+        "d3_affine_rows": (i32, [vp, vp, i32, i64, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here == header and library out of sync

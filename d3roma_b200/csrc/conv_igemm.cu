@@ -398,7 +398,7 @@ D3_DEVINL void epi_t_chunk(const uint32_t (&v)[32], uint32_t sa, const uint32_t 
 // j+4 sit in opposite halves of the swizzle pattern, so a warp's 32 word stores hit 32 distinct banks (the 16-bit
 // version measured 50 % bank conflicts).  Statistics: each lane sums both halves of the words it stores; the quad
 // total is the sum over the 4 lanes of a quad, which is all the caller needs.
-template <int DT, bool HAS_RES, int BASE = 0, int JJ = 0>
+template <int DT, bool HAS_RES, int BASE = 0, int JJ = 0, bool NO_STORE = false>
 D3_DEVINL void epi_t_chunk2(const uint32_t (&v)[32], uint32_t sa_lane, const uint32_t (&myswz)[4], float bias,
                             uint32_t vmask, bool odd, float& s_sum, float& s_sq) {
   if constexpr (BASE < 32) {
@@ -415,16 +415,16 @@ D3_DEVINL void epi_t_chunk2(const uint32_t (&v)[32], uint32_t sa_lane, const uin
       hi += r.y;
     }
     const uint32_t pk = pack2<DT>(lo, hi);
-    sts_u32<J0 * 128>(addr, pk);
+    if (!NO_STORE) sts_u32<J0 * 128>(addr, pk);
     const bool ok = ((vmask >> (odd ? J1 : J0)) & 1u) != 0;
     const float2 xr = unpack2<DT>(pk);
     const float a0 = ok ? xr.x : 0.f, a1 = ok ? xr.y : 0.f;
     s_sum += a0 + a1;
     s_sq = fmaf(a0, a0, fmaf(a1, a1, s_sq));
     if constexpr (JJ < 3)
-      epi_t_chunk2<DT, HAS_RES, BASE, JJ + 1>(v, sa_lane, myswz, bias, vmask, odd, s_sum, s_sq);
+      epi_t_chunk2<DT, HAS_RES, BASE, JJ + 1, NO_STORE>(v, sa_lane, myswz, bias, vmask, odd, s_sum, s_sq);
     else
-      epi_t_chunk2<DT, HAS_RES, BASE + 8, 0>(v, sa_lane, myswz, bias, vmask, odd, s_sum, s_sq);
+      epi_t_chunk2<DT, HAS_RES, BASE + 8, 0, NO_STORE>(v, sa_lane, myswz, bias, vmask, odd, s_sum, s_sq);
   }
 }
 
@@ -794,7 +794,9 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t sa = smem_u32(sbuf) + half * (kStagingBytes / 2) + (uint32_t)c0 * 128u + (chb & ~3u) +
                               (odd ? 512u : 0u);
           tmem_ld_wait();
-          if (has_res) {
+          if (a.debug_skip & 8) {
+            epi_t_chunk2<DT, false, 0, 0, true>(v, sa, myswz, bias, vmask, odd, s_sum, s_sq);
+          } else if (has_res) {
             epi_t_chunk2<DT, true>(v, sa, myswz, bias, vmask, odd, s_sum, s_sq);
           } else {
             epi_t_chunk2<DT, false>(v, sa, myswz, bias, vmask, odd, s_sum, s_sq);
@@ -807,7 +809,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 256);
-        if (et == 0) {
+        if (et == 0 && !(a.debug_skip & 8)) {
           tma_store_4d(&tmO, sbuf, t.n0, wpass, h, t.b);
           tma_store_4d(&tmO, sbuf + kStagingBytes / 2, t.n0 + 64, wpass, h, t.b);
           tma_store_commit();

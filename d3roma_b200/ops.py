@@ -322,3 +322,61 @@ def clamp_into(x, out, slot: int, lo: float = -1.0, hi: float = 1.0):
     _lib.check(_lib.lib().d3_clamp_into(x.data_ptr(), B, chw, out.stride(0), slot * chw, lo, hi, out.data_ptr(),
                                         _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# evaluation post-processing (SURVEY §8f rank 2)
+# ------------------------------------------------------------------------------------------------
+def disp_metrics(gt_disp, pred_disp, mask, fxb=None) -> torch.Tensor:
+    """[B,H,W] fp32 disparities (pixels) + mask -> [B, 11] fp64: epe, d1, d2, d3, d5, a1, a2, a3, rmse, rel, mae."""
+    g, p = _f32c(gt_disp, "gt_disp"), _f32c(pred_disp, "pred_disp")
+    m = _f32c(mask.to(torch.float32), "mask")
+    B = g.shape[0]
+    HW = g.numel() // max(B, 1)
+    f = None
+    if fxb is not None:
+        f = torch.as_tensor(fxb, dtype=torch.float32, device=g.device).reshape(-1).contiguous()
+    out = torch.empty((B, 11), dtype=torch.float64, device=g.device)
+    _lib.check(_lib.lib().d3_disp_metrics(g.data_ptr(), p.data_ptr(), m.data_ptr(), _ptr(f), 0 if f is None else f.numel(),
+                                          B, HW, out.data_ptr(), _stream()))
+    return out
+
+
+def scale_shift_lsq(pred, target, mask) -> torch.Tensor:
+    """[R, HW] rows -> [R, 2] (scale, shift) of the masked least-squares fit pred * s + t ~ target."""
+    p, t = _f32c(pred, "pred"), _f32c(target, "target")
+    m = _f32c(mask.to(torch.float32), "mask")
+    R = p.shape[0]
+    out = torch.empty((R, 2), dtype=torch.float32, device=p.device)
+    _lib.check(_lib.lib().d3_scale_shift_lsq(p.data_ptr(), t.data_ptr(), m.data_ptr(), R, p.numel() // max(R, 1),
+                                             out.data_ptr(), _stream()))
+    return out
+
+
+def masked_minmax(x, mask=None) -> torch.Tensor:
+    x = _f32c(x, "x")
+    m = None if mask is None else _f32c(mask.to(torch.float32), "mask")
+    R = x.shape[0]
+    out = torch.empty((R, 2), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().d3_masked_minmax(x.data_ptr(), _ptr(m), R, x.numel() // max(R, 1), out.data_ptr(), _stream()))
+    return out
+
+
+def normalize_ssi(x, mask, low_up, t: float, s: float) -> torch.Tensor:
+    x = _f32c(x, "x")
+    m = None if mask is None else _f32c(mask.to(torch.float32), "mask")
+    lu = _f32c(low_up, "low_up")
+    R = x.shape[0]
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().d3_normalize_ssi(x.data_ptr(), _ptr(m), lu.data_ptr(), R, x.numel() // max(R, 1), t, s,
+                                           out.data_ptr(), _stream()))
+    return out
+
+
+def affine_rows(y, scale_shift) -> torch.Tensor:
+    y = _f32c(y, "y")
+    st = _f32c(scale_shift, "scale_shift")
+    R = st.shape[0]
+    out = torch.empty_like(y)
+    _lib.check(_lib.lib().d3_affine_rows(y.data_ptr(), st.data_ptr(), R, y.numel() // max(R, 1), out.data_ptr(), _stream()))
+    return out

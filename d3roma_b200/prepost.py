@@ -5,8 +5,9 @@
 * ``Camera`` scalars + ``depth_to_disp`` / ``disp_to_depth`` — utils_d3roma/camera.py:115-125, 599-602, 771-780;
   inference.py:128-131, 246-249
 
-Every tensor op runs in ``libd3roma_b200.so`` (one fused pass each).  SSI / RANSAC scale-shift alignment and the
-piecewise multi-channel mode are evaluation-time post-processing outside the hot path.
+Every tensor op runs in ``libd3roma_b200.so`` (one fused pass each).  ``ssi=True`` (DREDS / ClearPose configs) is
+supported with the direct least-squares alignment (``safe_ssi=False``); the RANSAC variant and the piecewise
+multi-channel mode are not implemented.
 """
 from __future__ import annotations
 
@@ -89,8 +90,7 @@ class Normalizer:
 
     def _check(self):
         if self.ssi:
-            raise NotImplementedError("scale-shift-invariant (SSI / RANSAC) alignment is evaluation post-processing "
-                                      "outside the B200 hot path (SURVEY.md §8f rank 2)")
+            return
         if self.mode != "average":
             raise NotImplementedError("only normalize_mode='average' (the pixel-space configs) is implemented")
         assert len(self.ch_bounds) == len(self.ch_gammas) == 1, "inconsistent params"
@@ -99,6 +99,17 @@ class Normalizer:
         """[1,H,W] raw disparity -> ([num_chs,H,W] in [-1,1], None, None)   (utils.py:171-196)."""
         self._check()
         assert len(x.shape) == 3
+        if self.ssi:
+            # utils.py:172-180: low/up = the 0- and 1-quantiles (min / max) of the valid pixels, unless given
+            m = None if mask is None else mask.to(torch.float32)
+            if low is None and up is None:
+                lu = ops.masked_minmax(x.reshape(1, -1), None if m is None else m.reshape(1, -1))
+            else:
+                lu = torch.stack([torch.as_tensor(low, dtype=torch.float32, device=x.device).reshape(()),
+                                  torch.as_tensor(up, dtype=torch.float32, device=x.device).reshape(())]).view(1, 2)
+            y = ops.normalize_ssi(x.reshape(1, -1), None if m is None else m.reshape(1, -1), lu, float(self.t),
+                                  float(self.s)).view_as(x)
+            return y, lu[0, 0], lu[0, 1]
         y = ops.normalize_disp(x, self.num_chs, float(self.ch_bounds[0]), float(self.ch_gammas[0]), float(self.t),
                                float(self.s))
         return y.view(x.shape[0] * self.num_chs, *x.shape[1:]), None, None
@@ -107,6 +118,18 @@ class Normalizer:
         """[B, R*num_chs, H, W] -> [B, R, H, W] disparity in pixels (utils.py:231-273)."""
         self._check()
         assert len(y.shape) == 4, "should be of shape B,C,H,W"
+        if self.ssi:
+            # utils.py:232-251: per (sample, round) least-squares scale/shift against the raw disparity
+            assert raw_disp is not None and mask is not None
+            if self.safe_ssi:
+                raise NotImplementedError("safe_ssi (RANSAC, utils_d3roma/ransac.py) is not implemented; "
+                                          "use safe_ssi=False for the direct least-squares alignment")
+            B, R, H, W = y.shape
+            pred = y.reshape(B * R, H * W)
+            gt = raw_disp.to(torch.float32).repeat(1, R, 1, 1).reshape(B * R, H * W)
+            mk = mask.to(torch.float32).repeat(1, R, 1, 1).reshape(B * R, H * W)
+            st = ops.scale_shift_lsq(pred, gt, mk)
+            return ops.affine_rows(pred, st).view(B, R, H, W)
         return ops.denormalize_disp(y, self.num_chs, float(self.ch_bounds[0]), float(self.ch_gammas[0]),
                                     float(self.t), float(self.s))
 

@@ -194,6 +194,22 @@ int d3_crop(const float* in, int64_t planes, int Hin, int Win, int top, int left
 int d3_clamp_into(const float* in, int64_t B, int64_t chw, int64_t out_bstride, int64_t out_off, float lo, float hi,
                   float* out, void* stream);
 
+/* ---- evaluation post-processing on the device ----------------------------------------------
+ * compute_errors(space="disp") of utils_d3roma/utils.py:554-653: per sample, over mask != 0 pixels,
+ * out[b] = {EPE, D1, D2, D3, D5 (thresholds scaled by n_valid/480 as the reference does), a1(1.05), a2(1.10), a3(1.25),
+ * RMSE, REL, MAE of depth = fxb / disp}. fxb: fxb_n = 0 (1/disp), 1 (shared) or B (per sample) entries. */
+int d3_disp_metrics(const float* gt_disp, const float* pred_disp, const float* mask, const float* fxb, int fxb_n, int B,
+                    int64_t HW, double* out, void* stream);
+/* compute_scale_and_shift (utils.py:488-528): per row least squares pred*s + t ~ target over mask; out [rows][2]. */
+int d3_scale_shift_lsq(const float* pred, const float* target, const float* mask, int rows, int64_t HW,
+                       float* scale_shift, void* stream);
+/* Normalizer ssi=True (utils.py:171-182): per-row min/max over the mask, then (clamp((x-low)/(up-low),0,1)-t)*s on the
+ * mask and 0 elsewhere; and the inverse affine `y*s + t` per row (utils.py:250-251). mask may be NULL (all valid). */
+int d3_masked_minmax(const float* x, const float* mask, int rows, int64_t HW, float* low_up, void* stream);
+int d3_normalize_ssi(const float* x, const float* mask, const float* low_up, int rows, int64_t HW, float t, float s,
+                     float* out, void* stream);
+int d3_affine_rows(const float* y, const float* scale_shift, int rows, int64_t HW, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

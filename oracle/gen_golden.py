@@ -18,6 +18,8 @@ What is pinned:
                             ``FlowGuidance.grad`` (core/guidance.py:298-323) evaluated with the reference's own
                             ``SSIM`` module, ``camera.unnormalize_disp`` and autograd (the function as written
                             cannot return - SURVEY §0.4 - so its body is replayed line by line here).
+  * postproc.npz          - ``compute_errors`` (utils_d3roma/utils.py:554-653), ``compute_scale_and_shift`` (:488-528)
+                            and ``Normalizer(ssi=True).normalize/denormalize`` (:171-182, 231-251) outputs.
   * pipeline.npz          - ``GuidedDiffusionPipeline.__call__`` (core/custom_pipelines.py:97-205) driving the
                             restated UNet (oracle/unet_ref.py, seed 0) on a small seeded input: per-step model
                             outputs and the returned ``images`` for DDIM-10 and DDPM-8.
@@ -43,7 +45,7 @@ from core.scheduler_ddim import MyDDIMScheduler  # noqa: E402
 from core.scheduler_ddpm import MyDDPMScheduler  # noqa: E402
 from core.custom_pipelines import GuidedDiffusionPipeline  # noqa: E402
 from core.guidance import SSIM, FlowGuidance  # noqa: E402
-from utils_d3roma.utils import InputPadder, Normalizer  # noqa: E402
+from utils_d3roma.utils import InputPadder, Normalizer, compute_errors, compute_scale_and_shift  # noqa: E402
 from utils_d3roma import camera as ref_camera  # noqa: E402
 
 OUT = ROOT / "tests" / "golden"
@@ -282,11 +284,43 @@ def gen_pipeline(store):
         store[f"{tag}/model_outputs"] = np.stack([_np(o) for o in rec.outs])
 
 
+def gen_postproc(store):
+    """compute_errors / compute_scale_and_shift / Normalizer(ssi=True) of the reference (utils_d3roma/utils.py)."""
+    g = torch.Generator().manual_seed(31)
+    B, H, W = 3, 24, 40
+    gt = torch.rand(B, H, W, generator=g) * 60 + 5
+    gt[torch.rand(B, H, W, generator=g) < 0.25] = 0.0           # invalid pixels
+    pred = gt + torch.randn(B, H, W, generator=g) * 1.5
+    pred[1, :2, :3] = -0.5                                       # non-positive predictions -> clip branch (sample 1)
+    mask = gt > 0
+    md, mz = compute_errors(gt.numpy(), pred.numpy(), "disp", mask.numpy(), [24.5471958] * B)
+    store["err/gt"], store["err/pred"], store["err/mask"] = _np(gt), _np(pred), _np(mask)
+    store["err/disp"], store["err/depth"] = md, mz
+    md2, mz2 = compute_errors(gt.numpy(), np.where(mask.numpy(), np.abs(pred.numpy()) + 0.1, 0).astype(np.float32),
+                              "disp", None, None)
+    store["err/disp_nofxb"], store["err/depth_nofxb"] = md2, mz2
+    p2 = torch.rand(4, H * W, generator=g) * 2 - 1
+    t2 = p2 * 37.5 + 20.0 + torch.randn(4, H * W, generator=g) * 0.3
+    m2 = torch.rand(4, H * W, generator=g) > 0.3
+    store["ssi/pred"], store["ssi/target"], store["ssi/mask"] = _np(p2), _np(t2), _np(m2)
+    store["ssi/st"] = _np(compute_scale_and_shift(p2, t2, m2.float()))
+    n = Normalizer(ssi=True, mode="average", num_chs=1, ch_bounds=[128.], ch_gammas=[1.], t=0.5, s=2.0, safe_ssi=False)
+    x = gt[:1].clone()
+    y, low, up = n.normalize(x, mask[:1])
+    store["ssi/norm_in"], store["ssi/norm_mask"], store["ssi/norm_out"] = _np(x), _np(mask[:1]), _np(y)
+    store["ssi/low_up"] = np.array([float(low), float(up)], dtype=np.float32)
+    yb = (torch.rand(2, 2, H, W, generator=g) * 2 - 1)
+    raw = torch.rand(2, 1, H, W, generator=g) * 60 + 5
+    mk = torch.rand(2, 1, H, W, generator=g) > 0.2
+    store["ssi/den_in"], store["ssi/den_raw"], store["ssi/den_mask"] = _np(yb), _np(raw), _np(mk)
+    store["ssi/den_out"] = _np(n.denormalize(yb, raw, mk.float()))
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
     for name, fn in (("ddim", gen_ddim), ("ddpm", gen_ddpm), ("prepost", gen_prepost), ("guidance", gen_guidance),
-                     ("pipeline", gen_pipeline)):
+                     ("pipeline", gen_pipeline), ("postproc", gen_postproc)):
         store = {}
         with torch.no_grad():
             fn(store)

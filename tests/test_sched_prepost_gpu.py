@@ -126,9 +126,8 @@ def test_prepost_bit_exact_vs_reference():
     depth = torch.rand(4, 1, 360, 640, device="cuda") * 1.7 + 0.3
     back = prepost.disp_to_depth(prepost.depth_to_disp(depth, fxb), fxb)
     torch.testing.assert_close(back, depth, rtol=3e-7, atol=0)
-    ssi = Normalizer(ssi=True, mode="average", num_chs=1, ch_bounds=[128.], ch_gammas=[1.])
-    with pytest.raises(NotImplementedError):
-        ssi.normalize(torch.zeros(1, 4, 4, device="cuda"))
+    with pytest.raises(NotImplementedError):   # piecewise multi-channel mode is not implemented
+        Normalizer(ssi=False, mode="piecewise").normalize(torch.zeros(1, 4, 4, device="cuda"))
 
 
 def test_guidance_gradient_vs_reference_and_oracle():
