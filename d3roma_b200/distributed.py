@@ -80,3 +80,29 @@ def run_sharded(n_total: int, make_batch: Callable[[Sequence[int]], dict], denoi
         probe = denoise(**make_batch([0]), generator=sample_generators([0], seed))
         local = probe[:0]
     return all_gather_variable(local, n_total, rank, world)
+
+
+def run_distributed_eval(config, pipeline, n_total: int, batch_size: int, make_batch_fn=None, seed: int = 0,
+                         eval_fn=None, device=None):
+    """The loop of /root/reference/distributed_evaluate.py:96-172 on synthetic batches: this rank evaluates its
+    contiguous shard with ``evaluate.eval_batch`` and the per-sample metric rows (fp64 [n, 11]: the reference's
+    ``disp_err`` [n,5] + ``depth_err`` [n,6], :153-163) are all-gathered in global order.  Returns the metric dict of
+    ``metrics_to_dict`` (:172)."""
+    from . import evaluate, metrics, synthetic
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    make_batch_fn = make_batch_fn or synthetic.make_batch
+    eval_fn = eval_fn or evaluate.eval_batch          # injectable so the gloo CPU tests can exercise the gather
+    device = device if device is not None else pipeline.device
+    mine = shard_range(n_total, rank, world)
+    rows = []
+    for s in range(mine.start, mine.stop, batch_size):
+        idx = list(range(s, min(s + batch_size, mine.stop)))
+        batch = make_batch_fn(idx)
+        keys = ("fxb", "normalized_rgb", "raw_disp", "mask", "left_image", "right_image", "sim_disp", "raw_depth")
+        _, r, _, _, _ = eval_fn(config, pipeline, True, generator=sample_generators(idx, seed), as_numpy=False,
+                                **{k: batch[k] for k in keys})
+        rows.append(r)
+    local = torch.cat(rows) if rows else torch.zeros((0, 11), dtype=torch.float64, device=device)
+    allrows = all_gather_variable(local, n_total, rank, world).cpu().numpy()
+    return metrics.metrics_to_dict(allrows[:, :5], allrows[:, 5:]), allrows

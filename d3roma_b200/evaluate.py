@@ -9,7 +9,77 @@ from typing import Optional
 
 import torch
 
+from types import SimpleNamespace
+
+import numpy as np
+
+from . import metrics as M
 from .prepost import InputPadder, Normalizer
+
+
+def default_config(**overrides) -> SimpleNamespace:
+    """The fields of the reference's ``TrainingConfig`` (config.py:36-136) that ``eval_batch`` reads, with the
+    pixel-space SceneFlow defaults (conf/task/train_sceneflow.yaml, eval_sceneflow.yaml)."""
+    cfg = dict(divis_by=32, num_inference_rounds=1, num_inference_timesteps=10, num_intermediate_images=1,
+               noise_rgb=False, depth_channels=1, cond_channels="left+right+raw", ssi=False, normalize_mode="average",
+               num_chs=1, ch_bounds=[128.], ch_gammas=[1.], norm_t=0.5, norm_s=2.0, safe_ssi=False,
+               ransac_error_threshold=0.6, ensemble=False, eval_dataset=["synthetic"], camera_resolution="640x360",
+               prediction_space="disp")
+    cfg.update(overrides)
+    return SimpleNamespace(**cfg)
+
+
+def denormalize(config, pred_disps, raw_disp=None, mask=None):
+    """inference.py:8-35 / evaluate.py:44-64: SSI scale-shift alignment or Normalizer.denormalize."""
+    return Normalizer.from_config(config).denormalize(pred_disps, raw_disp, mask)
+
+
+@torch.no_grad()
+def eval_batch(config, pipeline, disable_bar=True, fxb=None, normalized_rgb=None, raw_disp=None, mask=None,
+               left_image=None, right_image=None, sim_disp=None, raw_depth=None, generator=None, as_numpy=True,
+               **kwargs):
+    """``eval_batch`` of /root/reference/evaluate.py:66-148 with the same signature and return tuple
+    ``(pred_disps_unnormalized, metrics, uncertainties, error_map, out)``: pad -> R rounds of the pipeline -> unpad ->
+    denormalise -> mean over rounds -> metrics.  Everything runs on the device; with ``as_numpy=False`` the maps stay
+    CUDA tensors and only the [B, 11] metric rows are computed (no D2H sync of full-resolution maps)."""
+    dev = pipeline.device
+    up = lambda t: None if t is None else t.to(dev, torch.float32)  # noqa: E731
+    normalized_rgb, left_image, right_image, sim_disp, raw_depth, raw_disp, mask = map(
+        up, (normalized_rgb, left_image, right_image, sim_disp, raw_depth, raw_disp, mask))
+    image_shape = normalized_rgb.shape if normalized_rgb is not None else left_image.shape
+    padder = InputPadder(image_shape, divis_by=config.divis_by)
+    p_rgb, p_left, p_right, p_sim, p_raw = padder.pad(normalized_rgb, left_image, right_image, sim_disp, raw_depth)
+    assert config.num_inference_rounds > 0, "num_inference_rounds should be greater than 0"
+    if getattr(config, "ensemble", False):
+        raise NotImplementedError("ensemble_depths (scipy optimisation, utils.py:346-460) is not implemented")
+    preds, out = [], None
+    for r in range(config.num_inference_rounds):
+        pipeline.set_progress_bar_config(desc=f"Denoising, round={r}", disable=disable_bar)
+        out = pipeline(p_rgb, p_left, p_right, p_sim, p_raw, mask, num_inference_steps=config.num_inference_timesteps,
+                       num_intermediate_images=config.num_intermediate_images, add_noise_rgb=config.noise_rgb,
+                       depth_channels=config.depth_channels, cond_channels=config.cond_channels, generator=generator)
+        out.images = padder.unpad(out.images)
+        preds.append(out.images)
+    pred_disps = torch.cat(preds, dim=1)                                       # [B, R*dc, H, W]
+    pred_un = denormalize(config, pred_disps, raw_disp, mask).mean(dim=1)      # [B, H, W]
+    gt = raw_disp.squeeze(1)
+    if config.eval_dataset[0] == "SceneFlow":                                  # evaluate.py:126-130
+        scale = 960. / float(config.camera_resolution.split("x")[0])
+        lo, hi = 0.5 / scale, 192.0 / scale
+        m = (gt >= lo) & (gt < hi)
+        pred_un = pred_un.clamp(lo, hi)
+    else:
+        m = mask.squeeze(1) > 0
+    rows = M.compute_errors_device(gt, pred_un, m, fxb)                        # [B, 11] fp64 on the device
+    mf = m.to(pred_un.dtype)
+    n_rounds = pred_disps.shape[1] // config.depth_channels
+    unc = pred_disps.std(dim=1, unbiased=False) * mf if n_rounds > 1 else None  # np.std over rounds (:140-142)
+    err = (gt - pred_un).abs() * mf
+    if as_numpy:
+        rows_h = rows.cpu().numpy()
+        return (pred_un.cpu().numpy(), (rows_h[:, :5], rows_h[:, 5:]), None if unc is None else unc.cpu().numpy(),
+                err.cpu().numpy(), out)
+    return pred_un, rows, unc, err, out
 
 
 @torch.no_grad()

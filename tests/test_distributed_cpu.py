@@ -73,3 +73,64 @@ def test_shard_range_partitions_exactly():
             assert got == list(range(n))
             sizes = [len(shard_range(n, r, world)) for r in range(world)]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _fake_eval(config, pipeline, disable_bar, generator=None, as_numpy=False, raw_disp=None, fxb=None, **kw):
+    """Stand-in for evaluate.eval_batch on CPU: 11 fp64 'metrics' per sample that depend on the sample's own data and on
+    its own start-noise generator only."""
+    noise = torch.stack([torch.randn((), generator=g, dtype=torch.float64) for g in generator])
+    base = raw_disp.double().flatten(1).mean(1) + fxb.double()
+    rows = base[:, None] * torch.arange(1, 12, dtype=torch.float64)[None] + noise[:, None]
+    return None, rows, None, None, None
+
+
+def _eval_worker(rank, world, port, n, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from d3roma_b200 import distributed as D, synthetic
+    if world > 1:
+        D.init_from_env("gloo")
+    mk = lambda idx: synthetic.make_batch(idx, h=8, w=12)  # noqa: E731
+    mdict, rows = D.run_distributed_eval(None, None, n, 2, make_batch_fn=mk, seed=3, eval_fn=_fake_eval, device="cpu")
+    q.put((rank, rows, sorted(mdict)))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def test_distributed_eval_metric_rows_independent_of_world_size():
+    """distributed_evaluate.py:153-163: the gathered [N, 5] + [N, 6] fp64 metric rows come back in global sample order and
+    are the same at world_size 1 and 2."""
+    import numpy as np
+    ctx = mp.get_context("spawn")
+    got = {}
+    for world in (1, 2):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_eval_worker, args=(r, world, port, 5, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=120) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        for _, rows, keys in res:
+            assert rows.shape == (5, 11) and rows.dtype == np.float64 and keys == ["depth", "disp"]
+        got[world] = res
+    for _, rows, _ in got[2]:
+        assert np.array_equal(rows, got[1][0][1])
+
+
+def test_synthetic_batch_keys_and_determinism():
+    """stereo_datasets.py:520-544 batch keys; a sample depends only on (seed, global index), not on its batch."""
+    from d3roma_b200 import synthetic
+    a = synthetic.make_batch([0, 1, 2], h=8, w=12)
+    b = synthetic.make_batch([2], h=8, w=12)
+    for k in ("raw_disp", "normalized_disp", "sim_disp", "sim_mask", "normalized_rgb", "left_image", "right_image", "mask",
+              "depth", "raw_depth", "fxb"):
+        assert k in a
+        assert torch.equal(a[k][2:3], b[k]), k
+    assert a["normalized_rgb"].shape == (3, 3, 8, 12) and a["raw_disp"].shape == (3, 1, 8, 12) and a["fxb"].shape == (3,)
+    assert a["normalized_rgb"].abs().max() <= 1 and a["normalized_disp"].abs().max() <= 1
+    assert ((a["sim_disp"] == -1.0) == (a["sim_mask"] == 0)).all()      # holes normalise to -1 (disp 0)

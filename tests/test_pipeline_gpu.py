@@ -182,3 +182,29 @@ def test_config4_style_ddpm100_fp32_tolerance():
         x, _, _ = S.ddpm_step(rec[i], t, x, ac, 128, 100, noise, prediction_type="sample", thresholding=True)
     print(f"DDPM-100 fp32: worst per-step model-output max-abs err {worst:.3e}")
     assert worst <= 1e-4
+
+
+def test_eval_batch_contract_and_metrics():
+    """eval_batch (evaluate.py:66-148 signature): pad -> rounds -> unpad -> denormalise -> metrics, on a synthetic batch
+    with the reference's dataset keys; the metric rows must agree with the oracle's compute_errors on the same maps."""
+    import d3roma_b200 as d
+    from d3roma_b200 import evaluate, synthetic
+    from oracle import postproc_ref as P
+    _, ref, net = _make("fp16", hw=(64, 96))
+    pipe = d.GuidedDiffusionPipeline(net, d.MyDDIMScheduler.from_config(DDIM_CFG), d.FlowGuidance(flow_guidance_weight=0.0))
+    cfg = evaluate.default_config(num_inference_timesteps=2, num_inference_rounds=2)
+    batch = synthetic.make_batch([0, 1], h=60, w=90)      # padded to 64 x 96 by InputPadder(divis_by=32)
+    keys = ("fxb", "normalized_rgb", "raw_disp", "mask", "left_image", "right_image", "sim_disp", "raw_depth")
+    pred, (md, mz), unc, err, out = evaluate.eval_batch(cfg, pipe, True, **{k: batch[k] for k in keys})
+    assert pred.shape == (2, 60, 90) and md.shape == (2, 5) and mz.shape == (2, 6) and unc.shape == (2, 60, 90)
+    assert out.images.shape == (2, 1, 60, 90)
+    rmd, rmz = P.compute_errors_disp(batch["raw_disp"].squeeze(1).numpy(), pred, batch["mask"].squeeze(1).numpy() > 0,
+                                     batch["fxb"].numpy())
+    np.testing.assert_allclose(md, rmd, rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(mz, rmz, rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(err, np.abs(batch["raw_disp"].squeeze(1).numpy() - pred), rtol=1e-6, atol=1e-6)
+    # single-process distributed eval = same rows in global order
+    from d3roma_b200 import distributed
+    mdict, rows = distributed.run_distributed_eval(evaluate.default_config(num_inference_timesteps=2), pipe, 3, 2,
+                                                   make_batch_fn=lambda idx: synthetic.make_batch(idx, h=60, w=90))
+    assert rows.shape == (3, 11) and set(mdict) == {"disp", "depth"} and np.isfinite(rows).all()
