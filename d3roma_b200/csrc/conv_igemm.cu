@@ -47,8 +47,9 @@ struct ConvKArgs {
   int res_pitch;
   double* stats;
   uint32_t a_bytes;
-  int l2_prefetch; // strips variant: producer prefetches the next tile's input rows into L2
-  int strip_slot;  // strips variant: bytes per strip ring slot ((TW+2)*128 rounded up to 1 KB)
+  int blk_slot;    // halo-block variant: bytes per block ring slot ((TH+2)*TW*128)
+  int n_blk, n_wts;  // halo-block variant: ring depths (<= kMaxBlk, kMaxWts)
+  int pass_h;      // pixels-as-N kernel: tile rows per epilogue pass (1 unless TW < 64)
   int t_direct;    // pixels-as-N kernel: epilogue stores straight to global (no staging / TMA store)
   uint16_t* out;   // output base pointer + pitch for the direct epilogue
   int out_pitch;
@@ -59,6 +60,11 @@ struct ConvKArgs {
 struct TileCoord {
   int b, h0, w0, n0;
 };
+
+// developer profiling (D3_CONV_DEBUG_SKIP bit 256): clock cycles summed over CTAs
+//   [0] MMA thread total, [1] waiting for a free accumulator, [2] waiting for pixel blocks, [3] waiting for weights,
+//   [4] epilogue thread total, [5] waiting for a full accumulator, [6] inside passes, [7] tiles
+__device__ unsigned long long g_conv_prof[8];
 
 D3_DEVINL TileCoord decode_tile(const ConvKArgs& a, int tile, int BN) {
   TileCoord t;
@@ -428,6 +434,49 @@ D3_DEVINL void epi_t_chunk2(const uint32_t (&v)[32], uint32_t sa_lane, const uin
   }
 }
 
+// Packed fp32x2 accumulate (Blackwell FADD2 / FFMA2): acc += x, sq += x * x on two lanes of a register pair.
+D3_DEVINL void stats_acc2(float2& s, float2& q, float2 x) {
+  asm("{\n\t.reg .b64 s, q, x;\n\t"
+      "mov.b64 s, {%0, %1};\n\tmov.b64 q, {%2, %3};\n\tmov.b64 x, {%4, %5};\n\t"
+      "add.rn.f32x2 s, s, x;\n\tfma.rn.f32x2 q, x, x, q;\n\t"
+      "mov.b64 {%0, %1}, s;\n\tmov.b64 {%2, %3}, q;\n\t}"
+      : "+f"(s.x), "+f"(s.y), "+f"(q.x), "+f"(q.y)
+      : "f"(x.x), "f"(x.y));
+}
+
+// Lean chunk epilogue (default): each lane rounds ITS OWN channel at pixels J0 and J0+4 into one packed word, swaps it
+// with the neighbouring channel's lane and assembles the 32-bit staging word with one PRMT (even lane: {ch, ch+1} at
+// pixel J0; odd lane: {ch-1, ch} at pixel J0+4 - the same conflict-free store pattern as epi_t_chunk2, without its
+// selects).  Statistics are per own channel on the rounded values, accumulated with packed fp32x2 ops; the MASKED
+// instantiation (tiles that overhang the image) zeroes out-of-image pixels first.
+template <int DT, bool HAS_RES, bool MASKED, int BASE = 0, int JJ = 0, bool NOSHFL = false>
+D3_DEVINL void epi_t_chunk3(const uint32_t (&v)[32], uint32_t sa_lane, const uint32_t (&myswz)[4], uint32_t sa_own,
+                            const uint32_t (&swz)[8], float bias, uint32_t vmask, uint32_t prmt_sel, float2& s2,
+                            float2& q2) {
+  if constexpr (BASE < 32) {
+    constexpr int J0 = BASE + JJ, J1 = J0 + 4;
+    float x0 = __uint_as_float(v[J0]) + bias;
+    float x1 = __uint_as_float(v[J1]) + bias;
+    if constexpr (HAS_RES) {
+      x0 += unpack2<DT>(lds_u16<J0 * 128>(sa_own + swz[J0 & 7])).x;
+      x1 += unpack2<DT>(lds_u16<J1 * 128>(sa_own + swz[J1 & 7])).x;
+    }
+    const uint32_t pk = pack2<DT>(x0, x1);
+    const uint32_t other = NOSHFL ? pk : __shfl_xor_sync(0xffffffffu, pk, 1);
+    sts_u32<J0 * 128>(sa_lane + myswz[JJ], __byte_perm(pk, other, prmt_sel));
+    float2 xr = unpack2<DT>(pk);
+    if constexpr (MASKED) {
+      xr.x = ((vmask >> J0) & 1u) ? xr.x : 0.f;
+      xr.y = ((vmask >> J1) & 1u) ? xr.y : 0.f;
+    }
+    stats_acc2(s2, q2, xr);
+    if constexpr (JJ < 3)
+      epi_t_chunk3<DT, HAS_RES, MASKED, BASE, JJ + 1, NOSHFL>(v, sa_lane, myswz, sa_own, swz, bias, vmask, prmt_sel, s2, q2);
+    else
+      epi_t_chunk3<DT, HAS_RES, MASKED, BASE + 8, 0, NOSHFL>(v, sa_lane, myswz, sa_own, swz, bias, vmask, prmt_sel, s2, q2);
+  }
+}
+
 // Variant that writes straight to global memory (no staging tile, no TMA store): the warp's 32 lanes hold 32
 // consecutive channels of one pixel, i.e. each store instruction covers one contiguous 64-byte segment.
 template <int DT, bool HAS_RES, int J = 0>
@@ -449,14 +498,16 @@ D3_DEVINL void epi_t_chunk_global(const uint32_t (&v)[32], uint16_t* gp, const u
 
 constexpr int kTThreads = 384;  // warps 0-3: producer / MMA / TMEM alloc / idle; warps 4-11: two epilogue groups
 
-constexpr int kNStrips = 3;   // halo-strip ring slots (strips variant)
-constexpr int kNWts = 6;      // weight-tile ring slots (strips variant)
+constexpr int kMaxBlk = 3;    // halo-block ring slots (halo-block variant)
+constexpr int kMaxWts = 8;    // weight-tile ring slots (halo-block variant)
 
-// STRIPS = true: 3x3 stride-1 convs on wide images.  The pixel operand of a tile (one image-row segment of TW pixels)
-// is loaded ONCE per (input row, 64-channel block) as a halo "strip" of TW+2 pixels and used by the three kw taps
-// through row-shifted UMMA descriptors (start address + kw*128 B; the swizzle follows the absolute address): the activation TMA
-// traffic drops 3x and the bytes that must be in flight to cover L2 latency with it.  Weights stream through their
-// own ring.  K-loop order: for cb: for kh: strip(h+kh-1, cb) -> for kw: weight tile (kh, kw, cb) -> 4 MMAs.
+// STRIPS = true ("halo blocks"): 3x3 stride-1 convs.  The pixel operand of a TH x TW tile (TW a multiple of 8, so one
+// tile row = TW*128 B is a whole number of 1024 B swizzle atoms) is loaded ONCE per (kw, 64-channel block) as a block of
+// TH+2 rows starting one row above the tile, and the three kh taps read it through UMMA descriptors whose start
+// address is advanced by whole tile rows - atom-aligned, unlike a kw (single-pixel) shift, which measured ~25 % slower
+// in the MMA itself (profiles/r01_conv_experiments.txt).  Activation TMA traffic drops by 3*TH/(TH+2).  Weights stream
+// through their own ring, fed by a second producer lane (warp 3).
+// K-loop order: for cb: for kw: block(kw, cb) -> for kh: weight tile (kh, kw, cb) -> 4 MMAs.
 template <int STAGES, int DT, bool STRIPS>
 __global__ void __launch_bounds__(kTThreads, 1)
 conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS1,
@@ -464,23 +515,23 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                     const ConvKArgs a) {
   constexpr uint32_t kTmemCols = 512;  // 2 accumulator stages x 256 pixel columns
-  constexpr int NBAR = STRIPS ? (kNStrips + kNWts) : STAGES;  // ring barriers (full + empty each)
+  constexpr int NBAR = STRIPS ? (kMaxBlk + kMaxWts) : STAGES;  // ring barriers (full + empty each)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // STRIPS: [kNStrips strip slots of a.strip_slot bytes][kNWts weight tiles of 16 KB]; else STAGES x {16 KB W, 32 KB P}
-  uint8_t* wring = STRIPS ? smem + kNStrips * a.strip_slot : smem;
-  uint8_t* staging = STRIPS ? wring + kNWts * kWTileBytes : smem + STAGES * kTStageBytes;
+  // STRIPS: [n_blk block slots of a.blk_slot bytes][n_wts weight tiles of 16 KB]; else STAGES x {16 KB W, 32 KB P}
+  uint8_t* wring = STRIPS ? smem + a.n_blk * a.blk_slot : smem;
+  uint8_t* staging = STRIPS ? wring + a.n_wts * kWTileBytes : smem + STAGES * kTStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kTStagingBytes);
   uint64_t* empty_bar = full_bar + NBAR;
   uint64_t* tfull_bar = empty_bar + NBAR;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* res_bar = tempty_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 1);
-  // strips variant: barriers [0, kNStrips) belong to the strip ring, [kNStrips, NBAR) to the weight ring
+  // halo-block variant: barriers [0, kMaxBlk) belong to the block ring, [kMaxBlk, NBAR) to the weight ring
   uint64_t* sfull = full_bar;
   uint64_t* sempty = empty_bar;
-  uint64_t* wfull = full_bar + kNStrips;
-  uint64_t* wempty = empty_bar + kNStrips;
+  uint64_t* wfull = full_bar + kMaxBlk;
+  uint64_t* wempty = empty_bar + kMaxBlk;
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -516,46 +567,29 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (STRIPS && lane == 0) {
-      int ss = 0, ws = 0;
-      uint32_t sphase = 0, wphase = 0;
-      const uint32_t strip_bytes = (uint32_t)(a.TW + 2) * 128u;
-      const uint32_t plain_bytes = (uint32_t)a.TW * 128u;
+      int ss = 0;
+      uint32_t sphase = 0;
+      const uint32_t blk_bytes = (uint32_t)(a.TH + 2) * a.TW * 128u;
+      const uint32_t plain_bytes = (uint32_t)a.TH * a.TW * 128u;
+      const int n_items = 3 * a.cbMain + a.kbSc1 + a.kbSc2;  // block loads per tile
       for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(a, tile, 128);
-        const int n_items = 3 * a.cbMain + a.kbSc1 + a.kbSc2;  // strip loads per tile
-        if (a.l2_prefetch && tile + (int)gridDim.x < a.numTiles) {
-          // pull the NEXT tile's input rows into L2 now, a whole tile ahead of the TMA loads that need them
-          const TileCoord tn = decode_tile(a, tile + gridDim.x, 128);
-          for (int cb = 0; cb < a.cbMain; ++cb)
-            for (int kh = 0; kh < 3; ++kh) tma_prefetch_4d(&tmA, cb * 64, tn.w0 - 1, tn.h0 + kh - 1, tn.b);
-          for (int j = 0; j < a.kbSc1; ++j) tma_prefetch_4d(&tmS1, j * 64, tn.w0, tn.h0, tn.b);
-          for (int j = 0; j < a.kbSc2; ++j) tma_prefetch_4d(&tmS2, j * 64, tn.w0, tn.h0, tn.b);
-        }
         for (int it = 0; it < n_items; ++it) {
           mbar_wait(&sempty[ss], sphase ^ 1);
-          uint8_t* sS = smem + ss * a.strip_slot;
-          int nkb, kb0;  // weight K-blocks served by this strip and the first one's K index (in 64-column units)
-          if (it < 3 * a.cbMain) {
-            const int cb = it / 3, kh = it - cb * 3;
-            mbar_arrive_expect_tx(&sfull[ss], strip_bytes);
-            tma_load_4d(sS, &tmA, &sfull[ss], cb * 64, t.w0 - 1, t.h0 + kh - 1, t.b);
-            nkb = 3;
-            kb0 = (kh * 3) * a.cbMain + cb;  // tap (kh, kw) -> K-block (kh*3 + kw) * cbMain + cb
+          uint8_t* sS = smem + ss * a.blk_slot;
+          if (a.debug_skip & 1) {  // developer experiment: no activation loads
+            mbar_arrive(&sfull[ss]);
+          } else if (it < 3 * a.cbMain) {
+            const int cb = it / 3, kw = it - cb * 3;
+            mbar_arrive_expect_tx(&sfull[ss], blk_bytes);
+            tma_load_4d(sS, &tmA, &sfull[ss], cb * 64, t.w0 + kw - 1, t.h0 - 1, t.b);
           } else {
             const int j = it - 3 * a.cbMain;
             mbar_arrive_expect_tx(&sfull[ss], plain_bytes);
             if (j < a.kbSc1) tma_load_4d(sS, &tmS1, &sfull[ss], j * 64, t.w0, t.h0, t.b);
             else tma_load_4d(sS, &tmS2, &sfull[ss], (j - a.kbSc1) * 64, t.w0, t.h0, t.b);
-            nkb = 1;
-            kb0 = a.kbMain + j;
           }
-          if (++ss == kNStrips) { ss = 0; sphase ^= 1; }
-          for (int i = 0; i < nkb; ++i) {
-            mbar_wait(&wempty[ws], wphase ^ 1);
-            mbar_arrive_expect_tx(&wfull[ws], kWTileBytes);
-            tma_load_2d(wring + ws * kWTileBytes, &tmB, &wfull[ws], (kb0 + i * a.cbMain) * 64, t.n0);
-            if (++ws == kNWts) { ws = 0; wphase ^= 1; }
-          }
+          if (++ss == a.n_blk) { ss = 0; sphase ^= 1; }
         }
       }
     } else if (lane == 0) {
@@ -610,37 +644,52 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t sphase = 0, wphase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t row_bytes = (uint32_t)a.TW * 128u;
+      const int n_items = 3 * a.cbMain + a.kbSc1 + a.kbSc2;
+      const bool prof = (a.debug_skip & 256) != 0;
+      long long p_t0 = prof ? clock64() : 0, p_acc = 0, p_blk = 0, p_wts = 0, p_c = 0;
       for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+        if (prof) p_c = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        if (prof) p_acc += clock64() - p_c;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        const int n_items = 3 * a.cbMain + a.kbSc1 + a.kbSc2;
         uint32_t first = 1;
         for (int it = 0; it < n_items; ++it) {
+          if (prof) p_c = clock64();
           mbar_wait(&sfull[ss], sphase);
+          if (prof) p_blk += clock64() - p_c;
           tc_fence_after();
-          const uint32_t sS = smem_u32(smem + ss * a.strip_slot);
+          const uint32_t sS = smem_u32(smem + ss * a.blk_slot);
           const int nkb = (it < 3 * a.cbMain) ? 3 : 1;
           for (int i = 0; i < nkb; ++i) {
+            if (prof) p_c = clock64();
             mbar_wait(&wfull[ws], wphase);
+            if (prof) p_wts += clock64() - p_c;
             tc_fence_after();
             const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(wring + ws * kWTileBytes));
-            // pixel window of tap kw = i: rows i .. i+TW-1 of the strip
-            const uint64_t bdesc = make_sw128_kmajor_desc(sS + (uint32_t)i * 128u);
+            // pixel window of tap kh = i: tile rows i .. i+TH-1 of the block (whole swizzle atoms further down)
+            const uint64_t bdesc = make_sw128_kmajor_desc(sS + (uint32_t)i * row_bytes);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
             }
             first = 0;
             umma_commit(&wempty[ws]);
-            if (++ws == kNWts) { ws = 0; wphase ^= 1; }
+            if (++ws == a.n_wts) { ws = 0; wphase ^= 1; }
           }
           umma_commit(&sempty[ss]);
-          if (++ss == kNStrips) { ss = 0; sphase ^= 1; }
+          if (++ss == a.n_blk) { ss = 0; sphase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+      }
+      if (prof) {
+        atomicAdd(&g_conv_prof[0], (unsigned long long)(clock64() - p_t0));
+        atomicAdd(&g_conv_prof[1], (unsigned long long)p_acc);
+        atomicAdd(&g_conv_prof[2], (unsigned long long)p_blk);
+        atomicAdd(&g_conv_prof[3], (unsigned long long)p_wts);
       }
     } else if (lane == 0) {
       const uint32_t idesc = make_idesc_16bit(kTileM, n_mma, DT == kBF16);
@@ -673,6 +722,34 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (acc == 0) acc_phase ^= 1;
       }
     }
+  } else if (warp == 3) {
+    // ================================ weight producer (halo-block variant) ================================
+    if (STRIPS && lane == 0) {
+      int ws = 0;
+      uint32_t wphase = 0;
+      const int n_items = 3 * a.cbMain + a.kbSc1 + a.kbSc2;
+      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(a, tile, 128);
+        for (int it = 0; it < n_items; ++it) {
+          int nkb = 1, kb0 = a.kbMain + (it - 3 * a.cbMain);
+          if (it < 3 * a.cbMain) {
+            const int cb = it / 3, kw = it - cb * 3;
+            nkb = 3;
+            kb0 = kw * a.cbMain + cb;  // tap (kh, kw) -> K-block (kh*3 + kw) * cbMain + cb
+          }
+          for (int i = 0; i < nkb; ++i) {
+            mbar_wait(&wempty[ws], wphase ^ 1);
+            if (a.debug_skip & 2) {
+              mbar_arrive(&wfull[ws]);
+            } else {
+              mbar_arrive_expect_tx(&wfull[ws], kWTileBytes);
+              tma_load_2d(wring + ws * kWTileBytes, &tmB, &wfull[ws], (kb0 + i * 3 * a.cbMain) * 64, t.n0);
+            }
+            if (++ws == a.n_wts) { ws = 0; wphase ^= 1; }
+          }
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
     const uint32_t q = (warp - 4) & 3;          // TMEM lane quarter this warp may access
@@ -689,21 +766,28 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t myswz[4];  // swizzle offsets of the 4 pixel rows (mod 8) this lane stores: even lanes 0-3, odd lanes 4-7
 #pragma unroll
     for (int i = 0; i < 4; ++i) myswz[i] = swz[i + (odd ? 4 : 0)];
+    const uint32_t prmt_sel = odd ? 0x3276u : 0x5410u;  // see epi_t_chunk3
     const bool has_res = a.residual != nullptr;
     // A pass = PW (<= 64) consecutive pixels of one tile row = a contiguous range of accumulator columns.  Staging is
     // double-buffered by pass so the TMA store of pass p overlaps the math of pass p+1.
     const int PW = a.pass_w;
+    const int PH = a.pass_h;                    // > 1 only for narrow tiles (TW < 64): a pass = PH whole tile rows
+    const int PN = PW * PH;                     // pixels (accumulator columns) per pass
     const int segs = a.TW / PW;
-    const int passes = a.TH * segs;
+    const int passes = (a.TH / PH) * segs;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t res_phase = 0;
     uint32_t pass_ctr = 0;
+    const bool prof = (a.debug_skip & 256) != 0 && et == 0;
+    long long p_t0 = prof ? clock64() : 0, p_wait = 0, p_pass = 0, p_c = 0, p_tiles = 0;
     for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(a, tile, 128);
       const float bias = a.bias[(size_t)t.b * a.bias_bstride + t.n0 + ch];
       float s_sum = 0.f, s_sq = 0.f;
+      if (prof) p_c = clock64();
       mbar_wait(&tfull_bar[acc], acc_phase);
+      if (prof) { const long long n = clock64(); p_wait += n - p_c; p_c = n; ++p_tiles; }
       tc_fence_after();
       if (a.debug_skip & 4) {  // developer experiment: no epilogue work at all
         tc_fence_before();
@@ -766,15 +850,15 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       } else
       for (int ps = 0; ps < passes; ++ps, ++pass_ctr) {
-        const int r = ps / segs;
-        const int sg = ps - r * segs;
+        const int r = (ps / segs) * PH;
+        const int sg = ps - (ps / segs) * segs;
         const int h = t.h0 + r;
         const int wpass = t.w0 + sg * PW;
         uint8_t* sbuf = staging + (pass_ctr & 1) * kStagingBytes;  // two 64-channel halves of 64 rows each
         if (et == 0) {
           tma_store_wait_read<1>();  // the store that used this buffer two passes ago has finished reading it
           if (has_res) {
-            mbar_arrive_expect_tx(res_bar, 2u * (uint32_t)PW * 128u);
+            mbar_arrive_expect_tx(res_bar, 2u * (uint32_t)PN * 128u);
             tma_load_4d(sbuf, &tmR, res_bar, t.n0, wpass, h, t.b);
             tma_load_4d(sbuf + kStagingBytes / 2, &tmR, res_bar, t.n0 + 64, wpass, h, t.b);
           }
@@ -785,21 +869,41 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           res_phase ^= 1;
         }
         const int c0 = (int)grp * 32;
-        if (c0 < PW) {
+        if (c0 < PN) {
           uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * 256 + r * a.TW + sg * PW + c0, v);
+          if (!(a.debug_skip & 64))
+            tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * 256 + r * a.TW + sg * PW + c0, v);
+          const int pc = c0 + (int)lane;          // pixel of the pass; row pc / PW, column pc % PW (PH == 1: row 0)
+          const int prow = (PH > 1) ? pc / PW : 0;
+          const int pcol = pc - prow * PW;
           const uint32_t vmask = __ballot_sync(
-              0xffffffffu, (c0 + (int)lane < PW) && (h < a.Ho) && (wpass + c0 + (int)lane < a.Wo));
+              0xffffffffu, (pc < PN) && (h + prow < a.Ho) && (wpass + pcol < a.Wo));
           // word address of this lane's channel pair; odd lanes write 4 pixel rows further down (see epi_t_chunk2)
           const uint32_t sa = smem_u32(sbuf) + half * (kStagingBytes / 2) + (uint32_t)c0 * 128u + (chb & ~3u) +
                               (odd ? 512u : 0u);
+          // byte address of this lane's own channel at pixel row 0 of the chunk (residual read-back)
+          const uint32_t sa_own = smem_u32(sbuf) + half * (kStagingBytes / 2) + (uint32_t)c0 * 128u + chb;
           tmem_ld_wait();
-          if (a.debug_skip & 8) {
+          if (a.debug_skip & 32) {  // developer experiment: no epilogue math
+          } else if (a.debug_skip & 8) {
             epi_t_chunk2<DT, false, 0, 0, true>(v, sa, myswz, bias, vmask, odd, s_sum, s_sq);
-          } else if (has_res) {
-            epi_t_chunk2<DT, true>(v, sa, myswz, bias, vmask, odd, s_sum, s_sq);
+          } else if (a.debug_skip & 16) {  // previous (select-based) epilogue, kept for A/B timing
+            if (has_res) epi_t_chunk2<DT, true>(v, sa, myswz, bias, vmask, odd, s_sum, s_sq);
+            else epi_t_chunk2<DT, false>(v, sa, myswz, bias, vmask, odd, s_sum, s_sq);
           } else {
-            epi_t_chunk2<DT, false>(v, sa, myswz, bias, vmask, odd, s_sum, s_sq);
+            float2 s2 = make_float2(s_sum, 0.f), q2 = make_float2(s_sq, 0.f);
+            const bool full = (vmask == 0xffffffffu);
+            if (a.debug_skip & 128) {  // developer experiment: no lane exchange (wrong results)
+              epi_t_chunk3<DT, false, false, 0, 0, true>(v, sa, myswz, sa_own, swz, bias, vmask, prmt_sel, s2, q2);
+            } else if (has_res) {
+              if (full) epi_t_chunk3<DT, true, false>(v, sa, myswz, sa_own, swz, bias, vmask, prmt_sel, s2, q2);
+              else epi_t_chunk3<DT, true, true>(v, sa, myswz, sa_own, swz, bias, vmask, prmt_sel, s2, q2);
+            } else {
+              if (full) epi_t_chunk3<DT, false, false>(v, sa, myswz, sa_own, swz, bias, vmask, prmt_sel, s2, q2);
+              else epi_t_chunk3<DT, false, true>(v, sa, myswz, sa_own, swz, bias, vmask, prmt_sel, s2, q2);
+            }
+            s_sum = s2.x + s2.y;
+            s_sq = q2.x + q2.y;
           }
         }
         if (ps == passes - 1) {
@@ -815,6 +919,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tma_store_commit();
         }
       }
+      if (prof) p_pass += clock64() - p_c;
       if (a.stats != nullptr) {
         // quad = 4 consecutive channels = 4 consecutive lanes
         s_sum += __shfl_xor_sync(0xffffffffu, s_sum, 1);
@@ -831,6 +936,12 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (acc == 0) acc_phase ^= 1;
     }
     if (et == 0) tma_store_wait_all<0>();
+    if (prof) {
+      atomicAdd(&g_conv_prof[4], (unsigned long long)(clock64() - p_t0));
+      atomicAdd(&g_conv_prof[5], (unsigned long long)p_wait);
+      atomicAdd(&g_conv_prof[6], (unsigned long long)p_pass);
+      atomicAdd(&g_conv_prof[7], (unsigned long long)p_tiles);
+    }
   }
 
   tc_fence_before();
@@ -845,9 +956,9 @@ template <int STAGES>
 constexpr size_t conv_t_smem_bytes() {
   return 1024 + STAGES * kTStageBytes + kTStagingBytes + (2 * STAGES + 5) * 8 + 16;
 }
-inline size_t conv_ts_smem_bytes(int strip_slot) {
-  return 1024 + (size_t)kNStrips * strip_slot + kNWts * kWTileBytes + kTStagingBytes +
-         (2 * (kNStrips + kNWts) + 5) * 8 + 16;
+inline size_t conv_ts_smem_bytes(const ConvKArgs& a) {
+  return 1024 + (size_t)a.n_blk * a.blk_slot + (size_t)a.n_wts * kWTileBytes + kTStagingBytes +
+         (2 * (kMaxBlk + kMaxWts) + 5) * 8 + 16;
 }
 
 template <int STAGES, int DT>
@@ -855,7 +966,7 @@ cudaError_t launch_conv_t(int grid, cudaStream_t stream, const CUtensorMap& tmA,
                           const CUtensorMap& tmS2, const CUtensorMap& tmB, const CUtensorMap& tmO,
                           const CUtensorMap& tmR, const ConvKArgs& a, bool strips) {
   if (strips) {
-    const size_t smem = conv_ts_smem_bytes(a.strip_slot);
+    const size_t smem = conv_ts_smem_bytes(a);
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
       cudaError_t e = cudaFuncSetAttribute(conv_igemm_t_kernel<STAGES, DT, true>,
@@ -1224,6 +1335,17 @@ void choose_tile(int Ho, int Wo, int* TH, int* TW) {
 
 }  // namespace d3
 
+// Developer hook (not part of include/d3roma_b200.h): read (and optionally clear) the cycle counters collected while
+// D3_CONV_DEBUG_SKIP has bit 256 set.
+extern "C" int d3_debug_conv_profile(unsigned long long* out8, int reset) {
+  if (out8 && cudaMemcpyFromSymbol(out8, d3::g_conv_prof, sizeof(d3::g_conv_prof)) != cudaSuccess) return 1;
+  if (reset) {
+    unsigned long long z[8] = {};
+    if (cudaMemcpyToSymbol(d3::g_conv_prof, z, sizeof(z)) != cudaSuccess) return 1;
+  }
+  return 0;
+}
+
 extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   using namespace d3;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -1262,28 +1384,40 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   static int no_t = -1;
   if (no_t < 0) { const char* e = getenv("D3_CONV_NO_T"); no_t = e ? atoi(e) : 0; }
   const bool use_t = (p->Cout == 128) && !no_t;
-  // halo-strip variant: plain 3x3 stride-1 convs on images at least 160 pixels wide
-  // (correct and parity-tested, but measured no faster than per-tap tiles in round 1 - profiles/r01_conv_experiments.txt -
-  // so it is opt-in: D3_CONV_STRIPS=1)
-  static int want_strips = -1;
-  if (want_strips < 0) { const char* e = getenv("D3_CONV_STRIPS"); want_strips = e ? atoi(e) : 0; }
-  const bool use_strips = use_t && want_strips && p->ksize == 3 && p->stride == 1 && phase == 0 && Wo >= 160;
+  // halo-block variant: plain 3x3 stride-1 convs whose output is covered well by TH x TW = 256-pixel tiles with TW a
+  // multiple of 8 (D3_CONV_VB: 0 = off, 1 = pick TW automatically, 8/16/32/64 = force that tile width)
+  static int want_vb = -1;
+  if (want_vb < 0) { const char* e = getenv("D3_CONV_VB"); want_vb = e ? atoi(e) : 1; }
+  bool use_strips = false;
+  if (use_t && want_vb && p->ksize == 3 && p->stride == 1 && phase == 0) {
+    double best = 0.0;
+    for (int tw = (want_vb == 8 ? 8 : 16); tw <= 64; tw *= 2) {
+      if (want_vb > 1 && tw != want_vb) continue;
+      const int th = 256 / tw;
+      const double eff = double(Ho) * Wo / (double(ceil_div(Ho, th)) * th * ceil_div(Wo, tw) * tw);
+      // activation bytes per K-block relative to per-tap tiles: (th + 2) / (3 * th); prefer the smaller unless it wastes MMAs
+      const double score = eff * (1.0 - 0.15 * double(th + 2) / (3.0 * th));
+      if ((eff >= 0.85 || want_vb > 1) && score > best) { best = score; a.TH = th; a.TW = tw; use_strips = true; }
+    }
+  }
   if (use_strips) {
-    // one image-row segment per tile; uniform width = smallest multiple of 16 that covers W in ceil(W/256) tiles
-    const int nseg = ceil_div(Wo, 256);
-    a.TH = 1;
-    a.TW = ((ceil_div(Wo, nseg) + 15) / 16) * 16;
+    a.blk_slot = (a.TH + 2) * a.TW * 128;
+    // ring depths: 32 KB staging + barriers leave ~193 KB
+    a.n_blk = (a.TW == 64) ? 2 : 3;
+    a.n_wts = (193 * 1024 - a.n_blk * a.blk_slot) / (int)kWTileBytes;
+    if (a.n_wts > kMaxWts) a.n_wts = kMaxWts;
+    static int nb = -1;
+    if (nb < 0) { const char* e = getenv("D3_CONV_VB_NBLK"); nb = e ? atoi(e) : 0; }
+    if (nb >= 2 && nb <= kMaxBlk && (193 * 1024 - nb * a.blk_slot) / (int)kWTileBytes >= 3) {
+      a.n_blk = nb;
+      a.n_wts = (193 * 1024 - nb * a.blk_slot) / (int)kWTileBytes;
+      if (a.n_wts > kMaxWts) a.n_wts = kMaxWts;
+    }
   } else if (use_t) {
     choose_tile_t(Ho, Wo, &a.TH, &a.TW);
   } else {
     choose_tile(Ho, Wo, &a.TH, &a.TW);
   }
-  {
-    static int pf = -1;
-    if (pf < 0) { const char* e = getenv("D3_CONV_L2_PREFETCH"); pf = e ? atoi(e) : 0; }
-    a.l2_prefetch = pf;
-  }
-  a.strip_slot = use_strips ? (((a.TW + 2) * 128 + 1023) / 1024) * 1024 : 0;
   a.tilesH = ceil_div(Ho, a.TH);
   a.tilesW = ceil_div(Wo, a.TW);
   const int pixTiles = p->B * a.tilesH * a.tilesW;
@@ -1332,6 +1466,7 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   CUtensorMap tmA, tmS1, tmS2, tmB, tmO, tmR;
   int rc = 0;
   a.pass_w = use_t ? pass_width(a.TW) : 0;
+  a.pass_h = (use_strips && a.TW < 64) ? 64 / a.TW : 1;
   {
     static int td = -1;
     if (td < 0) { const char* e = getenv("D3_CONV_T_DIRECT"); td = e ? atoi(e) : 0; }
@@ -1339,13 +1474,13 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   }
   a.out = static_cast<uint16_t*>(p->out);
   a.out_pitch = p->out_pitch;
-  const int store_rows = use_t ? 1 : a.TH;               // rows per TMA store box
+  const int store_rows = use_t ? a.pass_h : a.TH;        // rows per TMA store box
   const int store_cols = use_t ? a.pass_w : a.TW;        // pixels per row of the TMA store box
   if (p->stride == 1) {
     uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
     uint64_t str[3] = {(uint64_t)p->x_pitch * 2, (uint64_t)p->W * p->x_pitch * 2,
                        (uint64_t)p->H * p->W * p->x_pitch * 2};
-    uint32_t box[4] = {64, (uint32_t)(use_strips ? a.TW + 2 : a.TW), (uint32_t)a.TH, 1};
+    uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)(use_strips ? a.TH + 2 : a.TH), 1};
     rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmA, p->x, 4, dims, str, box);
   } else {
     // parity-split view: (pw*pitch + c, w/2, h parity, h/2, b)

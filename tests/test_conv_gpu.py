@@ -21,10 +21,10 @@ CASES = [
     (1, 48, 64, 256, 128, 3, 1, 128, 128, False),  # Cout=128 with folded shortcut (up5 resnets), pixels-as-N kernel
     (2, 33, 70, 64, 128, 3, 1, 0, 0, True),        # ragged tiles + residual, pixels-as-N kernel
     (1, 1, 20, 128, 128, 1, 1, 0, 0, True),        # single-row image (TH = 1 path)
-    (3, 192, 320, 128, 128, 3, 1, 0, 0, True),     # halo-strip variant, TW=160, identity residual
-    (1, 8, 320, 256, 128, 3, 1, 128, 128, False),  # halo-strip variant with folded 1x1 shortcut slabs
-    (2, 5, 200, 64, 128, 3, 1, 0, 0, True),        # halo-strip variant, ragged width (TW=208 > W)
-    (1, 6, 960, 128, 128, 3, 1, 0, 0, False),      # halo-strip variant, 544x960 family (TW=240)
+    (3, 192, 320, 128, 128, 3, 1, 0, 0, True),     # halo-block variant, identity residual
+    (1, 8, 320, 256, 128, 3, 1, 128, 128, False),  # halo-block variant with folded 1x1 shortcut slabs
+    (2, 5, 200, 64, 128, 3, 1, 0, 0, True),        # ragged width
+    (1, 6, 960, 128, 128, 3, 1, 0, 0, False),      # 544x960 family
 ]
 
 
@@ -97,27 +97,16 @@ def test_upsample_conv_subpixel_phases(B, H, W, C, dt):
     torch.testing.assert_close(stats, s_ref, rtol=1e-5, atol=1e-3)
 
 
-def test_opt_in_kernel_variants_match(monkeypatch):
-    """The experimental variants (halo strips, cta_group::2 pairs, direct-store epilogue) are selected through
-    environment variables read once per process; run them in a subprocess on a few shapes."""
+def test_kernel_variants_match():
+    """Kernel variants (halo blocks with each tile width, per-tap tiles, cta_group::2 pairs, direct-store epilogue,
+    pixels-as-M only) are selected through environment variables read once per process; run every variant in a
+    subprocess over shapes with ragged tiles, residuals, folded shortcuts and statistics (tests/_conv_variant_check.py)."""
     import os, subprocess, sys
-    code = (
-        "import torch, torch.nn.functional as F, sys; sys.path.insert(0, '.');"
-        "from d3roma_b200 import ops;"
-        "torch.backends.cudnn.allow_tf32=False;"
-        "g=torch.Generator(device='cuda').manual_seed(3);"
-        "shapes=[(2,6,320,128,128),(1,4,640,64,128),(2,24,40,256,256),(1,48,80,256,512)];"
-        "ok=True\n"
-        "for (B,H,W,Ci,Co) in shapes:\n"
-        "    x=torch.randn(B,H,W,Ci,device='cuda',generator=g).to(torch.bfloat16)\n"
-        "    w=(torch.randn(Co,Ci,3,3,device='cuda',generator=g)/(Ci*9)**0.5).to(torch.bfloat16)\n"
-        "    b=torch.randn(Co,device='cuda',generator=g)\n"
-        "    out=ops.conv2d_igemm(x,ops.pack_conv_weight(w),b,ksize=3)\n"
-        "    ref=F.conv2d(x.float().permute(0,3,1,2),w.float(),b,padding=1).permute(0,2,3,1)\n"
-        "    ok=ok and bool(((out.float()-ref).abs()<=2**-7*ref.abs()+2e-2).all())\n"
-        "print('VARIANT_OK' if ok else 'VARIANT_BAD')\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for env in ({"D3_CONV_STRIPS": "1"}, {"D3_CONV_2CTA": "1"}, {"D3_CONV_T_DIRECT": "1"}, {"D3_CONV_NO_T": "1"}):
+    script = os.path.join(root, "tests", "_conv_variant_check.py")
+    for env in ({"D3_CONV_VB": "0"}, {"D3_CONV_VB": "8"}, {"D3_CONV_VB": "16"}, {"D3_CONV_VB": "32"},
+                {"D3_CONV_VB": "64"}, {"D3_CONV_VB": "64", "D3_CONV_VB_NBLK": "3"}, {"D3_CONV_2CTA": "1"},
+                {"D3_CONV_T_DIRECT": "1"}, {"D3_CONV_NO_T": "1"}):
         e = dict(os.environ, **env)
-        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=e, capture_output=True, text=True, timeout=300)
-        assert "VARIANT_OK" in r.stdout, (env, r.stdout[-500:], r.stderr[-500:])
+        r = subprocess.run([sys.executable, script], cwd=root, env=e, capture_output=True, text=True, timeout=300)
+        assert "VARIANT_OK" in r.stdout, (env, r.stdout[-800:], r.stderr[-800:])
