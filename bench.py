@@ -201,16 +201,16 @@ def time_dominant_kernels(dtype, peaks):
     flops = 2.0 * B * HP * WP * 128 * 1152
     t_gn = timeit(lambda: ops.groupnorm_silu(x, stats, gamma, beta, out=out))
     gn_bytes = 2.0 * x.numel() * 2
-    roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<128,5> 3x3 128->128 @16x384x640",
+    roof = {"bound": "tensor", "kernel": "conv_igemm_t_kernel (pixels-as-N, 16x16 halo blocks) 3x3 128->128 @16x384x640",
             "achieved": flops / t_conv / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
             "frac": flops / t_conv / 1e12 / peaks["tf_burst"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r01_ncu_full_summary.csv)
-            "traffic": 1.007701e9 + 0.965439e9, "algorithmic_bytes": 2.0 * x.numel() * 2,
-            "ncu_tensor_pipe_active_pct": 63.5,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r01b_ncu_full_summary.csv)
+            "traffic": 1.014290e9 + 0.964388e9, "algorithmic_bytes": 2.0 * x.numel() * 2,
+            "ncu_tensor_pipe_active_pct": 69.5,
             "flops_per_launch": flops, "ms_per_launch": t_conv * 1e3, "peak_source": peaks["src"] + " burst"}
     roof_hbm = {"bound": "hbm", "kernel": "gn_apply_kernel 128ch @16x384x640 (GroupNorm+SiLU)",
                 "achieved": gn_bytes / t_gn / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                "frac": gn_bytes / t_gn / 1e9 / peaks["hbm"], "traffic": 1.006668e9 + 0.950813e9,
+                "frac": gn_bytes / t_gn / 1e9 / peaks["hbm"], "traffic": 1.006704e9 + 0.950754e9,
                 "bytes_per_launch": gn_bytes,
                 "ms_per_launch": t_gn * 1e3, "peak_source": peaks["src"]}
     return roof, roof_hbm
