@@ -89,6 +89,147 @@ __global__ void __launch_bounds__(256) im2col_input_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// direct conv_in (split form): conv_in(cat[x, cond]) = conv(x; W[:, :Cs]) + {conv(cond; W[:, Cs:]) + bias}.  The braces
+// depend only on the conditioning images, which are constant over the steps of one sampling loop
+// (custom_pipelines.py:158-171 rebuilds the same cat every step), so they are computed ONCE per loop into an fp32
+// NHWC "base" tensor (OUT32 mode) and every step only adds the 9*Cs taps of the noisy sample (OUT16 mode: + base,
+// round to the 16-bit activation type, GroupNorm quad statistics of the rounded values).  All arithmetic is fp32 with
+// fp32 weights - the model input is never rounded to 16 bit.
+// Per step algorithmic bytes: (4 (base) + 2 (out)) * 128 * P + 4 * Cs * P per sample.
+// Thread = 4 consecutive pixels of a row x 8 output channels; block = 64 pixels x 128 channels; weights in smem.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCiPx = 4;          // pixels per thread
+constexpr int kCiSeg = 16 * kCiPx;  // pixels per block iteration
+
+struct ConvInArgs {
+  const float* planes;  // [B, C, H, W] fp32
+  int C;
+  const float* wT;      // [C*9][128] fp32, k = c*9 + tap
+  const float* base;    // [B,H,W,128] fp32 or nullptr
+  const float* bias;    // [128] or nullptr (added when base == nullptr)
+  float* out32;         // OUT32 mode
+  uint16_t* out16;      // OUT16 mode
+  double* stats;        // OUT16 mode: [B][32][2]
+  int B, H, W;
+};
+
+template <int DT, bool OUT32>
+__global__ void __launch_bounds__(256, 2) conv_in_direct_kernel(const ConvInArgs a) {
+  extern __shared__ __align__(16) float ci_w[];  // [C*9][128]
+  __shared__ float s_part[8][64];
+  const int K = a.C * 9;
+  for (int i = threadIdx.x; i < K * 128; i += 256) ci_w[i] = a.wT[i];
+  __syncthreads();
+  const int oct = threadIdx.x & 15, pg = threadIdx.x >> 4;
+  const int b = blockIdx.y;
+  const int segs = (a.W + kCiSeg - 1) / kCiSeg;
+  const int items = a.H * segs;
+  const size_t HW = (size_t)a.H * a.W;
+  float bias8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bias8[j] = (a.base == nullptr && a.bias != nullptr) ? a.bias[oct * 8 + j] : 0.f;
+  float st[4] = {0.f, 0.f, 0.f, 0.f};  // quad 2*oct: sum, sq; quad 2*oct+1: sum, sq
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int h = item / segs, seg = item - h * segs;
+    const int w0 = seg * kCiSeg + pg * kCiPx;
+    if (w0 >= a.W) continue;
+    float acc[kCiPx][8];
+#pragma unroll
+    for (int p = 0; p < kCiPx; ++p)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[p][j] = bias8[j];
+    // issue the loads of the per-loop term first so that they are in flight during the tap arithmetic
+    float4 bv[kCiPx][2];
+    if (a.base != nullptr) {
+      const float* bp = a.base + (((size_t)b * a.H + h) * a.W + w0) * 128 + oct * 8;
+#pragma unroll
+      for (int p = 0; p < kCiPx; ++p) {
+        if (w0 + p < a.W) {
+          bv[p][0] = __ldcs(reinterpret_cast<const float4*>(bp + (size_t)p * 128));
+          bv[p][1] = __ldcs(reinterpret_cast<const float4*>(bp + (size_t)p * 128 + 4));
+        } else {
+          bv[p][0] = bv[p][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+    for (int c = 0; c < a.C; ++c) {
+      const float* pl = a.planes + ((size_t)b * a.C + c) * HW;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int hh = h + kh - 1;
+        float xv[kCiPx + 2];
+#pragma unroll
+        for (int i = 0; i < kCiPx + 2; ++i) {
+          const int ww = w0 - 1 + i;
+          xv[i] = (hh >= 0 && hh < a.H && ww >= 0 && ww < a.W) ? __ldg(pl + (size_t)hh * a.W + ww) : 0.f;
+        }
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float4 wa = *reinterpret_cast<const float4*>(ci_w + (c * 9 + kh * 3 + kw) * 128 + oct * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(ci_w + (c * 9 + kh * 3 + kw) * 128 + oct * 8 + 4);
+#pragma unroll
+          for (int p = 0; p < kCiPx; ++p) {
+            const float x = xv[p + kw];
+            acc[p][0] = fmaf(x, wa.x, acc[p][0]); acc[p][1] = fmaf(x, wa.y, acc[p][1]);
+            acc[p][2] = fmaf(x, wa.z, acc[p][2]); acc[p][3] = fmaf(x, wa.w, acc[p][3]);
+            acc[p][4] = fmaf(x, wb.x, acc[p][4]); acc[p][5] = fmaf(x, wb.y, acc[p][5]);
+            acc[p][6] = fmaf(x, wb.z, acc[p][6]); acc[p][7] = fmaf(x, wb.w, acc[p][7]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < kCiPx; ++p) {
+      const int w = w0 + p;
+      if (w >= a.W) break;
+      const size_t pix = ((size_t)b * a.H + h) * a.W + w;
+      if (a.base != nullptr) {
+        const float4 ba = bv[p][0], bb = bv[p][1];
+        acc[p][0] += ba.x; acc[p][1] += ba.y; acc[p][2] += ba.z; acc[p][3] += ba.w;
+        acc[p][4] += bb.x; acc[p][5] += bb.y; acc[p][6] += bb.z; acc[p][7] += bb.w;
+      }
+      if constexpr (OUT32) {
+        float4* o = reinterpret_cast<float4*>(a.out32 + pix * 128 + oct * 8);
+        o[0] = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+        o[1] = make_float4(acc[p][4], acc[p][5], acc[p][6], acc[p][7]);
+      } else {
+        uint4 pk;
+        pk.x = pack2<DT>(acc[p][0], acc[p][1]);
+        pk.y = pack2<DT>(acc[p][2], acc[p][3]);
+        pk.z = pack2<DT>(acc[p][4], acc[p][5]);
+        pk.w = pack2<DT>(acc[p][6], acc[p][7]);
+        *reinterpret_cast<uint4*>(a.out16 + pix * 128 + oct * 8) = pk;
+        const float2 f0 = unpack2<DT>(pk.x), f1 = unpack2<DT>(pk.y), f2 = unpack2<DT>(pk.z), f3 = unpack2<DT>(pk.w);
+        st[0] += (f0.x + f0.y) + (f1.x + f1.y);
+        st[1] += (f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y);
+        st[2] += (f2.x + f2.y) + (f3.x + f3.y);
+        st[3] += (f2.x * f2.x + f2.y * f2.y) + (f3.x * f3.x + f3.y * f3.y);
+      }
+    }
+  }
+  if constexpr (!OUT32) {
+    if (a.stats != nullptr) {
+      // lanes l and l+16 of a warp share the octet: combine, park per warp, then a fixed-order sum over the 8 warps
+      // (deterministic: no floating-point atomics before the fp64 stage)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) st[i] += __shfl_xor_sync(0xffffffffu, st[i], 16);
+      if ((threadIdx.x & 31) < 16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s_part[threadIdx.x >> 5][oct * 4 + i] = st[i];
+      }
+      __syncthreads();
+      if (threadIdx.x < 64) {
+        // s_part column oct*4 + {0,1,2,3} = quad 2*oct {sum, sq}, quad 2*oct+1 {sum, sq} = stats[b][quad][2] flattened
+        double t = 0.0;
+#pragma unroll
+        for (int wi = 0; wi < 8; ++wi) t += (double)s_part[wi][threadIdx.x];
+        atomicAdd(a.stats + (size_t)b * 64 + threadIdx.x, t);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // fused GroupNorm + SiLU + conv3x3 (128 -> DC) -> fp32 NCHW
 // ------------------------------------------------------------------------------------------------
 constexpr int kCoTY = 8, kCoTX = 32;                 // output tile: 256 pixels, one per thread
@@ -300,6 +441,38 @@ extern "C" int d3_conv_out_fused(const void* x, int pitch, const double* stats, 
   else if (dc == 1) conv_out_kernel<1, kF16><<<grid, kCoThreads, conv_out_smem<1>(), st>>>(a);
   else if (dtype == D3_DTYPE_BF16) conv_out_kernel<3, kBF16><<<grid, kCoThreads, conv_out_smem<3>(), st>>>(a);
   else conv_out_kernel<3, kF16><<<grid, kCoThreads, conv_out_smem<3>(), st>>>(a);
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
+extern "C" int d3_conv_in_direct(const float* planes, int C, const float* wT, const float* base, const float* bias,
+                                 int B, int H, int W, float* out32, void* out16, int dtype, double* stats,
+                                 void* stream) {
+  using namespace d3;
+  D3_REQUIRE(planes && wT, "conv_in_direct: null pointer");
+  D3_REQUIRE(C >= 1 && C <= 12, "conv_in_direct: C must be in [1, 12] (got %d)", C);
+  D3_REQUIRE((out32 != nullptr) != (out16 != nullptr), "conv_in_direct: exactly one of out32 / out16 must be given");
+  D3_REQUIRE(out32 || dtype == D3_DTYPE_BF16 || dtype == D3_DTYPE_F16, "conv_in_direct: bad dtype %d", dtype);
+  D3_REQUIRE(base || bias, "conv_in_direct: base or bias required");
+  ConvInArgs a{planes, C, wT, base, bias, out32, static_cast<uint16_t*>(out16), stats, B, H, W};
+  const int items = H * ((W + kCiSeg - 1) / kCiSeg);
+  int gx = (num_sms() * 4 + B - 1) / B;
+  if (gx > items) gx = items;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, B);
+  const size_t smem = (size_t)C * 9 * 128 * sizeof(float);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    const int mx = 12 * 9 * 128 * 4;
+    D3_CHECK_CUDA(cudaFuncSetAttribute(conv_in_direct_kernel<kBF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    D3_CHECK_CUDA(cudaFuncSetAttribute(conv_in_direct_kernel<kBF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    D3_CHECK_CUDA(cudaFuncSetAttribute(conv_in_direct_kernel<kF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    attr_set = true;
+  }
+  if (out32) conv_in_direct_kernel<kBF16, true><<<grid, 256, smem, st>>>(a);
+  else if (dtype == D3_DTYPE_BF16) conv_in_direct_kernel<kBF16, false><<<grid, 256, smem, st>>>(a);
+  else conv_in_direct_kernel<kF16, false><<<grid, 256, smem, st>>>(a);
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

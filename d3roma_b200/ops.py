@@ -166,6 +166,39 @@ def im2col_input(sample: torch.Tensor, cond: Optional[torch.Tensor], out: Option
     return out
 
 
+def pack_conv_in_direct(w_oihw: torch.Tensor, c0: int, c1: int) -> torch.Tensor:
+    """fp32 OIHW conv_in weight [128, Cin, 3, 3] -> [(c1-c0)*9][128] fp32, k = (c-c0)*9 + kh*3 + kw, for
+    ``conv_in_direct`` over the input channels c0..c1-1."""
+    w = w_oihw[:, c0:c1].float()
+    return w.permute(1, 2, 3, 0).reshape((c1 - c0) * 9, w.shape[0]).contiguous()
+
+
+def conv_in_direct(planes: torch.Tensor, wT: torch.Tensor, *, base: Optional[torch.Tensor] = None,
+                   bias: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+                   out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Direct 3x3 conv of fp32 NCHW ``planes`` [B,C,H,W] with 128 output channels (``d3_conv_in_direct``).
+    ``out_dtype=None``: fp32 NHWC result (the per-loop conditioning term, ``bias`` added).  ``out_dtype`` bf16/fp16:
+    ``base`` (fp32 NHWC) + conv, rounded, plus GroupNorm quad statistics into ``stats``."""
+    if not (planes.is_cuda and planes.dtype == torch.float32 and planes.is_contiguous()):
+        raise ValueError("conv_in_direct expects a contiguous fp32 CUDA NCHW tensor")
+    B, C, H, W = planes.shape
+    if wT.shape != (C * 9, 128) or wT.dtype != torch.float32:
+        raise ValueError(f"conv_in_direct: weight must be fp32 [{C * 9}, 128]")
+    if base is not None and (base.shape != (B, H, W, 128) or base.dtype != torch.float32 or not base.is_contiguous()):
+        raise ValueError("conv_in_direct: base must be contiguous fp32 [B,H,W,128]")
+    if out_dtype is None:
+        if out is None:
+            out = torch.empty((B, H, W, 128), dtype=torch.float32, device=planes.device)
+        _lib.check(_lib.lib().d3_conv_in_direct(planes.data_ptr(), C, wT.data_ptr(), _ptr(base), _ptr(bias), B, H, W,
+                                                out.data_ptr(), None, 0, None, _stream()))
+        return out
+    if out is None:
+        out = torch.empty((B, H, W, 128), dtype=out_dtype, device=planes.device)
+    _lib.check(_lib.lib().d3_conv_in_direct(planes.data_ptr(), C, wT.data_ptr(), _ptr(base), _ptr(bias), B, H, W,
+                                            None, out.data_ptr(), _dt(out), _ptr(stats), _stream()))
+    return out
+
+
 def conv_out_fused(x: torch.Tensor, stats: torch.Tensor, gamma, beta, w, bias, dc: int, eps: float = 1e-5,
                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _check_nhwc(x, "x")

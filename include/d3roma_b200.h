@@ -105,6 +105,15 @@ int d3_upsample_nearest2x(const void* in, int B, int H, int W, int C, int in_pit
 int d3_im2col_input(const float* sample, int Cs, const float* cond, int Cc, int B, int H, int W, void* out,
                     int dtype, void* stream);
 
+/* ---- conv_in in split form: conv_in(cat[x, cond]) = conv3x3(x; W[:, :Cs]) + {conv3x3(cond; W[:, Cs:]) + bias}.
+ * The braces are constant over one sampling loop (custom_pipelines.py:158-171 re-concatenates the same conditioning
+ * every step), so the caller computes them once (out32 mode: planes = cond, base = NULL, bias given -> fp32 NHWC
+ * [B,H,W,128]) and every step adds the taps of the noisy sample (out16 mode: planes = sample, base = that tensor ->
+ * 16-bit NHWC [B,H,W,128] + GroupNorm quad statistics [B][32][2]).  planes fp32 NCHW [B,C,H,W]; wT fp32
+ * [C*9][128] with k = c*9 + (kh*3+kw).  Exactly one of out32 / out16 is non-NULL.  fp32 arithmetic throughout. */
+int d3_conv_in_direct(const float* planes, int C, const float* wT, const float* base, const float* bias, int B, int H,
+                      int W, float* out32, void* out16, int dtype, double* stats, void* stream);
+
 /* ---- conv_norm_out + SiLU + conv_out fused: bf16 NHWC [B,H,W,128] -> fp32 NCHW [B,dc,H,W] (dc = 1 or 3).
  * w fp32 [dc][9][128] (tap-major), stats = quad statistics of x ([B][32][2]). */
 int d3_conv_out_fused(const void* x, int pitch, const double* stats, const float* gamma, const float* beta,

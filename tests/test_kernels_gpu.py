@@ -108,3 +108,30 @@ def test_time_embedding():
         torch.testing.assert_close(semb.cpu(), ref_semb.detach(), rtol=1e-4, atol=1e-5)
         pr = ops.temb_project_all(semb, proj.weight.detach().cuda().contiguous(), proj.bias.detach().cuda())
         torch.testing.assert_close(pr.cpu(), ref_proj.detach(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,Cs,Cc,H,W", [(2, 1, 7, 32, 64), (1, 3, 9, 17, 70), (2, 1, 4, 40, 130)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_conv_in_direct_split_matches_torch(B, Cs, Cc, H, W, dt):
+    """conv_in(cat[x, cond]) = conv(x) + {conv(cond) + bias}: the per-loop fp32 conditioning term and the per-step
+    sample taps against torch's fp32 conv2d over the concatenated input; statistics are those of the stored values."""
+    import torch.nn.functional as F
+    from d3roma_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(B, Cs, H, W, device="cuda", generator=g)
+    c = torch.randn(B, Cc, H, W, device="cuda", generator=g)
+    w = torch.randn(128, Cs + Cc, 3, 3, device="cuda", generator=g) / (9 * (Cs + Cc)) ** 0.5
+    bias = torch.randn(128, device="cuda", generator=g)
+    base = ops.conv_in_direct(c, ops.pack_conv_in_direct(w, Cs, Cs + Cc), bias=bias)
+    ref_base = F.conv2d(c, w[:, Cs:], bias, padding=1).permute(0, 2, 3, 1)
+    torch.testing.assert_close(base, ref_base, rtol=1e-5, atol=2e-5)
+    stats = torch.zeros(B, 32, 2, dtype=torch.float64, device="cuda")
+    out = ops.conv_in_direct(x, ops.pack_conv_in_direct(w, 0, Cs), base=base, out_dtype=dt, stats=stats)
+    ref = F.conv2d(torch.cat([x, c], 1), w, bias, padding=1).permute(0, 2, 3, 1)
+    assert out.dtype == dt and out.shape == (B, H, W, 128)
+    ulp = 2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11
+    assert bool(((out.float() - ref).abs() <= ulp * ref.abs() + 1e-4).all())
+    o = out.double().reshape(B, H * W, 32, 4)
+    s_ref = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
+    torch.testing.assert_close(stats, s_ref, rtol=1e-5, atol=1e-3)

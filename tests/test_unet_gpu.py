@@ -44,12 +44,26 @@ def test_unet_matches_oracle(cin, dc, hw, ts, dtype):
             assert err <= TOL_NORTH_STAR, err
         else:
             assert err <= TOL_BF16_MAX and rms <= TOL_BF16_RMS, (err, rms)
-    # split entry (sample + cond) is the same computation as the concatenated call
-    y2 = net.forward_split(x[:, :dc].contiguous().cuda(), x[:, dc:].contiguous().cuda(), ts[-1]).cpu()
-    if dtype == "fp32":   # fp32 statistics use float atomics: run-to-run differences of a few ulp
+    # split entry (sample + cond): conv_in runs in its direct fp32 form (per-loop conditioning term + sample taps)
+    # instead of the 16-bit im2col GEMM of the concatenated call - same tolerance against the oracle
+    xs, xc = x[:, :dc].contiguous().cuda(), x[:, dc:].contiguous().cuda()
+    y2 = net.forward_split(xs, xc, ts[-1]).cpu()
+    e2 = (y2 - y_ref).abs()
+    print(f"{dtype} split entry: max-abs {e2.max().item():.3e} rms {e2.pow(2).mean().sqrt().item():.3e}")
+    if dtype == "fp32":   # same kernels as the concatenated call; fp32 statistics use float atomics
         torch.testing.assert_close(y2, y, rtol=0, atol=2e-5)
+    elif dtype == "fp16":
+        assert e2.max().item() <= TOL_NORTH_STAR
     else:
-        assert torch.equal(y2, y)
+        assert e2.max().item() <= TOL_BF16_MAX and e2.pow(2).mean().sqrt().item() <= TOL_BF16_RMS
+    if dtype != "fp32":
+        # a second call with the same conditioning tensor reuses the cached term and is bit-identical; changing the
+        # conditioning IN PLACE must invalidate the cache
+        assert torch.equal(net.forward_split(xs, xc, ts[-1]).cpu(), y2)
+        xc.mul_(0.5)
+        y4 = net.forward_split(xs, xc, ts[-1]).cpu()
+        assert not torch.equal(y4, y2)
+        assert torch.equal(net.forward_split(xs, xc.clone(), ts[-1]).cpu(), y4)
 
 
 @pytest.mark.parametrize("dtype,tol", [("fp32", TOL_FP32), ("fp16", TOL_NORTH_STAR)])
