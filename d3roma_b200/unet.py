@@ -157,6 +157,7 @@ class UNet2DModel:
 
         proj_w, proj_b, off = [], [], 0
         self._temb_off: Dict[str, int] = {}
+        self._identity_slab = set()
         for kind, i, j, cin_h, cin_s, cout, attn in self._specs:
             p = self._rprefix(kind, i, j)
             W[p + ".n1.g"], W[p + ".n1.b"] = get(p + ".norm1.weight").contiguous(), get(p + ".norm1.bias").contiguous()
@@ -166,6 +167,13 @@ class UNet2DModel:
             if cin_h + cin_s != cout:
                 W[p + ".w2"] = ops.pack_conv_weight(get(p + ".conv2.weight"), get(p + ".conv_shortcut.weight"), dtype=self._adt)
                 b2 = b2 + get(p + ".conv_shortcut.bias")
+            elif cout == 128 and self._adt != torch.float32:
+                # identity residual of the 128-channel layers as two extra K-blocks with an identity "shortcut" weight:
+                # exact (x * 1.0 accumulated in fp32) and 11 % more MMA work, where the residual read-back in the
+                # pixels-as-N epilogue measured +34 % (profiles/r01_conv_experiments.txt)
+                W[p + ".w2"] = ops.pack_conv_weight(get(p + ".conv2.weight"), torch.eye(128, device=dev),
+                                                    dtype=self._adt)
+                self._identity_slab.add(p)
             else:
                 W[p + ".w2"] = ops.pack_conv_weight(get(p + ".conv2.weight"), dtype=self._adt)
             W[p + ".b2"] = b2.contiguous()
@@ -286,6 +294,8 @@ class UNet2DModel:
         cin = h.t.shape[3] + (0 if skip is None else skip.t.shape[3])
         if cin != cout:
             return self._conv(a2, W[p + ".w2"], W[p + ".b2"], 3, B, sc1=h.t, sc2=None if skip is None else skip.t)
+        if p in self._identity_slab:
+            return self._conv(a2, W[p + ".w2"], W[p + ".b2"], 3, B, sc1=h.t)
         return self._conv(a2, W[p + ".w2"], W[p + ".b2"], 3, B, residual=h.t)
 
     def _attention(self, a: str, h: _Act, B: int) -> _Act:

@@ -49,3 +49,10 @@ total = sum(v[0] for v in tot.values())
 print(f"kernel time per forward: {total:.2f} ms")
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1][0])[:14]:
     print(f"  {v[0]:7.3f} ms {100 * v[0] / total:5.1f}%  x{v[1] // 3:4d}  {k}")
+if len(sys.argv) > 4:  # per-launch list of the last recorded forward (kernel order)
+    evs = [ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA]
+    evs.sort(key=lambda e: e.time_range.start)
+    per = len(evs) // 3
+    for ev in evs[2 * per:]:
+        nm = ev.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:48]
+        print(f"    {ev.device_time_total:9.1f} us  {nm}")
