@@ -64,7 +64,8 @@ struct TileCoord {
 // developer profiling (D3_CONV_DEBUG_SKIP bit 256): clock cycles summed over CTAs
 //   [0] MMA thread total, [1] waiting for a free accumulator, [2] waiting for pixel blocks, [3] waiting for weights,
 //   [4] epilogue thread total, [5] waiting for a full accumulator, [6] inside passes, [7] tiles
-__device__ unsigned long long g_conv_prof[8];
+//   [8] pass: store-buffer wait + barrier 1, [9] TMEM load, [10] math + staging stores, [11] fence + barrier 2 + store issue
+__device__ unsigned long long g_conv_prof[16];
 
 D3_DEVINL TileCoord decode_tile(const ConvKArgs& a, int tile, int BN) {
   TileCoord t;
@@ -781,6 +782,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t pass_ctr = 0;
     const bool prof = (a.debug_skip & 256) != 0 && et == 0;
     long long p_t0 = prof ? clock64() : 0, p_wait = 0, p_pass = 0, p_c = 0, p_tiles = 0;
+    long long p_q[4] = {0, 0, 0, 0};
     for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(a, tile, 128);
       const float bias = a.bias[(size_t)t.b * a.bias_bstride + t.n0 + ch];
@@ -855,6 +857,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int h = t.h0 + r;
         const int wpass = t.w0 + sg * PW;
         uint8_t* sbuf = staging + (pass_ctr & 1) * kStagingBytes;  // two 64-channel halves of 64 rows each
+        long long q0 = prof ? clock64() : 0, q1 = 0, q2 = 0, q3 = 0;
         if (et == 0) {
           tma_store_wait_read<1>();  // the store that used this buffer two passes ago has finished reading it
           if (has_res) {
@@ -869,6 +872,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           res_phase ^= 1;
         }
         const int c0 = (int)grp * 32;
+        if (prof) q1 = clock64();
         if (c0 < PN) {
           uint32_t v[32];
           if (!(a.debug_skip & 64))
@@ -884,6 +888,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // byte address of this lane's own channel at pixel row 0 of the chunk (residual read-back)
           const uint32_t sa_own = smem_u32(sbuf) + half * (kStagingBytes / 2) + (uint32_t)c0 * 128u + chb;
           tmem_ld_wait();
+          if (prof) q2 = clock64();
           if (a.debug_skip & 32) {  // developer experiment: no epilogue math
           } else if (a.debug_skip & 8) {
             epi_t_chunk2<DT, false, 0, 0, true>(v, sa, myswz, bias, vmask, odd, s_sum, s_sq);
@@ -906,6 +911,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             s_sq = q2.x + q2.y;
           }
         }
+        if (prof) q3 = clock64();
         if (ps == passes - 1) {
           tc_fence_before();
           __syncwarp();
@@ -917,6 +923,10 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tma_store_4d(&tmO, sbuf, t.n0, wpass, h, t.b);
           tma_store_4d(&tmO, sbuf + kStagingBytes / 2, t.n0 + 64, wpass, h, t.b);
           tma_store_commit();
+        }
+        if (prof) {
+          const long long q4 = clock64();
+          p_q[0] += q1 - q0; p_q[1] += q2 - q1; p_q[2] += q3 - q2; p_q[3] += q4 - q3;
         }
       }
       if (prof) p_pass += clock64() - p_c;
@@ -941,6 +951,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       atomicAdd(&g_conv_prof[5], (unsigned long long)p_wait);
       atomicAdd(&g_conv_prof[6], (unsigned long long)p_pass);
       atomicAdd(&g_conv_prof[7], (unsigned long long)p_tiles);
+      for (int i = 0; i < 4; ++i) atomicAdd(&g_conv_prof[8 + i], (unsigned long long)p_q[i]);
     }
   }
 
@@ -1337,10 +1348,10 @@ void choose_tile(int Ho, int Wo, int* TH, int* TW) {
 
 // Developer hook (not part of include/d3roma_b200.h): read (and optionally clear) the cycle counters collected while
 // D3_CONV_DEBUG_SKIP has bit 256 set.
-extern "C" int d3_debug_conv_profile(unsigned long long* out8, int reset) {
-  if (out8 && cudaMemcpyFromSymbol(out8, d3::g_conv_prof, sizeof(d3::g_conv_prof)) != cudaSuccess) return 1;
+extern "C" int d3_debug_conv_profile(unsigned long long* out16, int reset) {
+  if (out16 && cudaMemcpyFromSymbol(out16, d3::g_conv_prof, sizeof(d3::g_conv_prof)) != cudaSuccess) return 1;
   if (reset) {
-    unsigned long long z[8] = {};
+    unsigned long long z[16] = {};
     if (cudaMemcpyToSymbol(d3::g_conv_prof, z, sizeof(z)) != cudaSuccess) return 1;
   }
   return 0;

@@ -17,7 +17,7 @@ bias = torch.zeros(Cout, device="cuda")
 out = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
 stats = torch.zeros(B, Cout // 4, 2, dtype=torch.float64, device="cuda")
 L = _lib.lib()
-buf = (ctypes.c_ulonglong * 8)()
+buf = (ctypes.c_ulonglong * 16)()
 for _ in range(3):
     ops.conv2d_igemm(x, wp, bias, ksize=3, out=out, stats=stats)
 torch.cuda.synchronize()
@@ -31,4 +31,5 @@ v = [int(b) for b in buf]
 tiles = v[7]
 print(f"tiles {tiles}; per tile (cycles): MMA-thread total {v[0] / tiles:.0f}, wait acc {v[1] / tiles:.0f}, "
       f"wait blocks {v[2] / tiles:.0f}, wait weights {v[3] / tiles:.0f} | epilogue total {v[4] / tiles:.0f}, "
-      f"wait tfull {v[5] / tiles:.0f}, passes {v[6] / tiles:.0f}")
+      f"wait tfull {v[5] / tiles:.0f}, passes {v[6] / tiles:.0f} = buffer wait + bar1 {v[8] / tiles:.0f}, "
+      f"TMEM load {v[9] / tiles:.0f}, math + stores {v[10] / tiles:.0f}, fence + bar2 + issue {v[11] / tiles:.0f}")

@@ -9,12 +9,13 @@ path = sys.argv[1]
 n_last = int(sys.argv[2]) if len(sys.argv) > 2 else 172
 with open(path) as f:
     lines = [l for l in f if not l.startswith("==")]
-rows = [r for r in csv.DictReader(lines) if "d3::" in r["Kernel Name"]]
+MINE = re.compile(r"igemm|gn_apply|attention_hd8|conv_out|conv_in_direct|im2col|time_embed|temb_project|upsample2x|d3::")
+rows = [r for r in csv.DictReader(lines) if MINE.search(r["Kernel Name"])]
 rows = rows[-n_last:]
 agg = collections.defaultdict(lambda: [0, 0.0])
 detail = collections.defaultdict(float)
 for r in rows:
-    name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void d3::<unnamed>::", "").replace("d3::<unnamed>::", "")
+    name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "").replace("d3::<unnamed>::", "").replace("unnamed>::", "")
     v = float(r["Metric Value"].replace(",", ""))
     v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0}[r["Metric Unit"]]
     agg[name][0] += 1
