@@ -9,6 +9,8 @@
 //           input region is read once, normalised + SiLU'd into shared memory, then every thread produces one output
 //           pixel (9 taps x 128 ch) and writes the fp32 NCHW model output the schedulers consume.
 //           Algorithmic bytes: (128 + dc*2) * P * 2 B per sample.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -230,11 +232,21 @@ __global__ void __launch_bounds__(256, 2) conv_in_direct_kernel(const ConvInArgs
 }
 
 // ------------------------------------------------------------------------------------------------
-// fused GroupNorm + SiLU + conv3x3 (128 -> DC) -> fp32 NCHW
+// fused GroupNorm + SiLU + conv3x3 (128 -> DC) -> fp32 NCHW, in two kernels without any halo:
+//   A  taps:   y[b][d*9+tap][p] = sum_c w[d][tap][c] * silu(gn(x[b][p][c]))   for every pixel p and all 9*DC taps
+//              = a streaming GEMM [P x 128] x [128 x 9*DC]: each activation is read ONCE from HBM straight into MMA
+//              A-fragment registers (no shared memory), normalised + SiLU'd + rounded there (what the separate
+//              GroupNorm pass would have stored), multiplied by register-resident weight fragments (mma.m16n8k16).
+//   B  gather: out[b][d][h][w] = bias[d] + sum_tap y[b][d*9+tap][h+dh][w+dw]   (zero outside the image = the conv's
+//              zero padding of the normalised activation).
+// The earlier one-kernel version re-read every activation 9 times from shared memory (ldmatrix per tap: 0.38 ms of
+// shared-memory time) and normalised a 33 % halo.  Algorithmic bytes: (128 * 2 + 2 * 9*DC * 4 + DC * 4) * P per sample.
+//
+// K permutation: lane (g, t) owns the 16-byte chunks 4q + t (q = 0..3; 8 channels each) of pixels g and g+8, so one
+// load instruction of a warp covers 8 pixels x 64 contiguous bytes (whole sectors).  Chunk q feeds the m16n8k16 slabs
+// 2q (channels +0..3 as k = 2t, 2t+1, 2t+8, 2t+9) and 2q+1 (channels +4..7); the weight fragments are permuted the
+// same way.
 // ------------------------------------------------------------------------------------------------
-constexpr int kCoTY = 8, kCoTX = 32;                 // output tile: 256 pixels, one per thread
-constexpr int kCoRY = kCoTY + 2, kCoRX = kCoTX + 2;  // input region with halo
-constexpr int kCoPitch = 128 * 2 + 16;               // bytes per pixel row in smem (+16 B pad: conflict-free 16 B reads)
 constexpr int kCoThreads = 256;
 
 struct ConvOutArgs {
@@ -246,14 +258,10 @@ struct ConvOutArgs {
   const float* w;          // [DC][9][128] fp32 (tap-major, channel fastest)
   const float* bias;       // [DC]
   float* out;              // [B,DC,H,W]
+  float* taps;             // workspace [B][9*DC][H*W] fp32
   int B, H, W;
   float eps;
 };
-
-template <int DC>
-constexpr size_t conv_out_smem() {
-  return (size_t)kCoRY * kCoRX * kCoPitch + (size_t)9 * 8 * 8 * 16 * 2 + 2 * 128 * 4;
-}
 
 template <int DT>
 D3_DEVINL void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -269,126 +277,137 @@ D3_DEVINL void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
   }
 }
-D3_DEVINL void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(saddr));
+
+template <int DT>
+D3_DEVINL uint32_t norm_silu_pair(uint32_t raw, float s0, float h0, float s1, float h1) {
+  const float2 f = unpack2<DT>(raw);
+  return pack2<DT>(silu_fast(fmaf(f.x, s0, h0)), silu_fast(fmaf(f.y, s1, h1)));
 }
 
 template <int DC, int DT>
-__global__ void __launch_bounds__(kCoThreads) conv_out_kernel(const ConvOutArgs a) {
-  // Stage 1: the (8+2) x (32+2) x 128 input region is read ONCE from global (coalesced 16 B vectors), normalised,
-  // SiLU'd, rounded to the 16-bit activation type (exactly what the separate GroupNorm pass would have stored) and
-  // parked in shared memory; out-of-image pixels become the conv's zero padding.
-  // Stage 2: warp w owns output row w of the tile (32 pixels = two 16-pixel MMA tiles); for every tap and 16-channel
-  // slab: ldmatrix the activation fragment, mma.m16n8k16 against the weight fragment (n = dc padded to 8).
-  extern __shared__ __align__(16) uint8_t co_smem[];
-  uint8_t* s_in = co_smem;
-  uint16_t* s_w = reinterpret_cast<uint16_t*>(co_smem + (size_t)kCoRY * kCoRX * kCoPitch);  // [tap][ks][n=8][16]
-  float* s_sc = reinterpret_cast<float*>(s_w + 9 * 8 * 8 * 16);
-  float* s_sh = s_sc + 128;
-  const int b = blockIdx.z;
-  const int y0 = blockIdx.y * kCoTY, x0 = blockIdx.x * kCoTX;
-  for (int i = threadIdx.x; i < 9 * 8 * 8 * 16; i += kCoThreads) {
-    const int c16 = i & 15, n = (i >> 4) & 7, ks = (i >> 7) & 7, tap = i >> 10;
-    const float wv = (n < DC) ? a.w[((size_t)n * 9 + tap) * 128 + ks * 16 + c16] : 0.f;
-    s_w[i] = (uint16_t)pack2<DT>(wv, 0.f);
-  }
-  if (threadIdx.x < 128) {
-    const int c = threadIdx.x, g = c >> 2;
-    const double s = a.stats[((size_t)b * 32 + g) * 2], ss = a.stats[((size_t)b * 32 + g) * 2 + 1];
-    const double n = (double)a.H * a.W * 4.0;
+__global__ void __launch_bounds__(kCoThreads, (DC == 1) ? 2 : 1) conv_out_taps_kernel(const ConvOutArgs a) {
+  constexpr int NTAPS = 9 * DC;
+  constexpr int NT = (NTAPS + 7) / 8;  // n-tiles of 8 taps
+  __shared__ float s_sc[128], s_sh[128];
+  const int b = blockIdx.y;
+  const int HW = a.H * a.W;
+  if (threadIdx.x < 32) {
+    const int grp = threadIdx.x;  // 4 channels per group at C = 128
+    const double s = a.stats[((size_t)b * 32 + grp) * 2], ss = a.stats[((size_t)b * 32 + grp) * 2 + 1];
+    const double n = (double)HW * 4.0;
     const double mean = s / n;
     double var = ss / n - mean * mean;
     if (var < 0.0) var = 0.0;
     const float rstd = (float)(1.0 / sqrt(var + (double)a.eps));
-    const float sc = a.gamma[c] * rstd;
-    s_sc[c] = sc;
-    s_sh[c] = a.beta[c] - (float)mean * sc;
-  }
-  __syncthreads();
-  {
-    const int vec = threadIdx.x & 15;  // 16 vectors of 8 channels per pixel
-    float sc[8], sh[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      sc[k] = s_sc[vec * 8 + k];
-      sh[k] = s_sh[vec * 8 + k];
-    }
-    constexpr int kPixPerIter = kCoThreads / 16;  // 16
-    constexpr int U = 4;
-    for (int p0 = threadIdx.x >> 4; p0 < kCoRY * kCoRX; p0 += kPixPerIter * U) {
-      uint4 raw[U];
-      bool ok[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int pi = p0 + u * kPixPerIter;
-        const int ry = pi / kCoRX, rx = pi - ry * kCoRX;
-        const int y = y0 - 1 + ry, x = x0 - 1 + rx;
-        ok[u] = (pi < kCoRY * kCoRX) && y >= 0 && y < a.H && x >= 0 && x < a.W;
-        if (ok[u])
-          raw[u] = __ldg(reinterpret_cast<const uint4*>(a.x + (((size_t)b * a.H + y) * a.W + x) * a.pitch + vec * 8));
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int pi = p0 + u * kPixPerIter;
-        if (pi < kCoRY * kCoRX) {
-          uint4 o = make_uint4(0u, 0u, 0u, 0u);
-          if (ok[u]) {
-            const float2 f0 = unpack2<DT>(raw[u].x), f1 = unpack2<DT>(raw[u].y);
-            const float2 f2 = unpack2<DT>(raw[u].z), f3 = unpack2<DT>(raw[u].w);
-            o.x = pack2<DT>(silu_fast(fmaf(f0.x, sc[0], sh[0])), silu_fast(fmaf(f0.y, sc[1], sh[1])));
-            o.y = pack2<DT>(silu_fast(fmaf(f1.x, sc[2], sh[2])), silu_fast(fmaf(f1.y, sc[3], sh[3])));
-            o.z = pack2<DT>(silu_fast(fmaf(f2.x, sc[4], sh[4])), silu_fast(fmaf(f2.y, sc[5], sh[5])));
-            o.w = pack2<DT>(silu_fast(fmaf(f3.x, sc[6], sh[6])), silu_fast(fmaf(f3.y, sc[7], sh[7])));
-          }
-          *reinterpret_cast<uint4*>(s_in + (size_t)pi * kCoPitch + vec * 16) = o;
-        }
-      }
+    for (int k = 0; k < 4; ++k) {
+      const int c = grp * 4 + k;
+      const float scv = a.gamma[c] * rstd;
+      s_sc[c] = scv;
+      s_sh[c] = a.beta[c] - (float)mean * scv;
     }
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  float acc[2][4];
+  // weight fragments: slab s, n-tile j: b0 = {w[n][32t+4s], w[n][32t+4s+1]}, b1 = {.. +2, .. +3}, n = 8j + g
+  uint32_t wf[8][NT][2];
 #pragma unroll
-  for (int m = 0; m < 2; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
-  // ldmatrix row address of this lane inside a 16x16 fragment: row = lane % 16, k-half = lane / 16
-  const uint32_t s_in_u32 = smem_u32(s_in);
-  const uint32_t lrow = (uint32_t)(lane & 15), lk = (uint32_t)(lane >> 4) * 16u;
-  const uint32_t* s_w32 = reinterpret_cast<const uint32_t*>(s_w);
-#pragma unroll 1
-  for (int tap = 0; tap < 9; ++tap) {
-    const int kh = tap / 3, kw = tap - kh * 3;
-    const uint32_t rowbase = s_in_u32 + (uint32_t)((warp + kh) * kCoRX + kw) * kCoPitch + lrow * kCoPitch + lk;
+  for (int j = 0; j < NT; ++j) {
+    const int n = 8 * j + g;
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      const uint32_t b0 = s_w32[((tap * 8 + ks) * 8 + g) * 8 + t];
-      const uint32_t b1 = s_w32[((tap * 8 + ks) * 8 + g) * 8 + 4 + t];
-      uint32_t af[4];
-      ldmatrix_x4(af, rowbase + ks * 32);
-      mma16816<DT>(acc[0], af, b0, b1);
-      ldmatrix_x4(af, rowbase + 16 * kCoPitch + ks * 32);
-      mma16816<DT>(acc[1], af, b0, b1);
+    for (int sl = 0; sl < 8; ++sl) {
+      float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+      if (n < NTAPS) {
+        const float* wp = a.w + (size_t)n * 128 + 8 * (4 * (sl >> 1) + t) + 4 * (sl & 1);  // [n][c]
+        w0 = wp[0]; w1 = wp[1]; w2 = wp[2]; w3 = wp[3];
+      }
+      wf[sl][j][0] = pack2<DT>(w0, w1);
+      wf[sl][j][1] = pack2<DT>(w2, w3);
     }
   }
-  // C fragment: rows g / g+8 (pixels), columns 2t, 2t+1 (output channels)
-  const int y = y0 + warp;
-  if (y < a.H) {
+  const int n_groups = (HW + 15) / 16;
+  const uint16_t* xb = a.x + (size_t)b * HW * a.pitch;
+  float* yb = a.taps + (size_t)b * NTAPS * HW;
+  // software pipeline: the 8 x 16-byte loads of the warp's NEXT 16-pixel group are issued before the current group's
+  // arithmetic; scale/shift are re-read from shared memory per 8-channel vector to leave registers for that.
+  const float4* sc4 = reinterpret_cast<const float4*>(s_sc + 8 * t);  // + 32 floats per q
+  const float4* sh4 = reinterpret_cast<const float4*>(s_sh + 8 * t);
+  const int stride16 = gridDim.x * (kCoThreads / 32);
+  int grp16 = blockIdx.x * (kCoThreads / 32) + warp;
+  uint4 r0[4], r1[4];
+  auto load_group = [&](int gi) {
+    const int q0 = gi * 16 + g, q1 = q0 + 8;
 #pragma unroll
-    for (int m = 0; m < 2; ++m) {
+    for (int q = 0; q < 4; ++q) {
+      r0[q] = (q0 < HW) ? __ldcs(reinterpret_cast<const uint4*>(xb + (size_t)q0 * a.pitch + 8 * t) + 4 * q)
+                        : make_uint4(0u, 0u, 0u, 0u);
+      r1[q] = (q1 < HW) ? __ldcs(reinterpret_cast<const uint4*>(xb + (size_t)q1 * a.pitch + 8 * t) + 4 * q)
+                        : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  if (grp16 < n_groups) load_group(grp16);
+  for (; grp16 < n_groups; grp16 += stride16) {
+    const int p0 = grp16 * 16 + g, p1 = p0 + 8;
+    uint4 c0[4], c1[4];
 #pragma unroll
-      for (int hrow = 0; hrow < 2; ++hrow) {
-        const int x = x0 + 16 * m + g + 8 * hrow;
-        if (x < a.W) {
+    for (int q = 0; q < 4; ++q) { c0[q] = r0[q]; c1[q] = r1[q]; }
+    if (grp16 + stride16 < n_groups) load_group(grp16 + stride16);
+    float acc[NT][4];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int d = 2 * t + e;
-            if (d < DC) a.out[(((size_t)b * DC + d) * a.H + y) * a.W + x] = acc[m][2 * hrow + e] + a.bias[d];
-          }
+    for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      // uint4 q holds channels 8(4q+t) .. +7: slab 2q = words x, y; slab 2q+1 = words z, w
+      const float4 sa = sc4[8 * q], sb = sc4[8 * q + 1], ha = sh4[8 * q], hb = sh4[8 * q + 1];
+      uint32_t af[4];
+      af[0] = norm_silu_pair<DT>(c0[q].x, sa.x, ha.x, sa.y, ha.y);
+      af[1] = norm_silu_pair<DT>(c1[q].x, sa.x, ha.x, sa.y, ha.y);
+      af[2] = norm_silu_pair<DT>(c0[q].y, sa.z, ha.z, sa.w, ha.w);
+      af[3] = norm_silu_pair<DT>(c1[q].y, sa.z, ha.z, sa.w, ha.w);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) mma16816<DT>(acc[j], af, wf[2 * q][j][0], wf[2 * q][j][1]);
+      af[0] = norm_silu_pair<DT>(c0[q].z, sb.x, hb.x, sb.y, hb.y);
+      af[1] = norm_silu_pair<DT>(c1[q].z, sb.x, hb.x, sb.y, hb.y);
+      af[2] = norm_silu_pair<DT>(c0[q].w, sb.z, hb.z, sb.w, hb.w);
+      af[3] = norm_silu_pair<DT>(c1[q].w, sb.z, hb.z, sb.w, hb.w);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) mma16816<DT>(acc[j], af, wf[2 * q + 1][j][0], wf[2 * q + 1][j][1]);
+    }
+    // C fragment: rows g / g+8 (pixels), columns 2t, 2t+1 (taps of n-tile j) -> planar tap maps
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int n = 8 * j + 2 * t + e;
+        if (n < NTAPS) {
+          if (p0 < HW) yb[(size_t)n * HW + p0] = acc[j][e];
+          if (p1 < HW) yb[(size_t)n * HW + p1] = acc[j][2 + e];
         }
       }
     }
+  }
+}
+
+template <int DC>
+__global__ void __launch_bounds__(256) conv_out_gather_kernel(const float* __restrict__ taps,
+                                                              const float* __restrict__ bias, float* __restrict__ out,
+                                                              int B, int H, int W) {
+  const int HW = H * W;
+  const size_t total = (size_t)B * DC * HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    const int d = (int)((i / HW) % DC);
+    const size_t b = i / ((size_t)HW * DC);
+    const int h = p / W, w = p - h * W;
+    const float* yb = taps + (b * 9 * DC + (size_t)d * 9) * HW;
+    float acc = bias[d];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) acc += __ldg(yb + (size_t)tap * HW + (size_t)hh * W + ww);
+    }
+    out[i] = acc;
   }
 }
 
@@ -413,34 +432,39 @@ extern "C" int d3_im2col_input(const float* sample, int Cs, const float* cond, i
   return D3_OK;
 }
 
+extern "C" size_t d3_conv_out_workspace_bytes(int B, int H, int W, int dc) {
+  return (size_t)B * 9 * dc * H * W * sizeof(float);
+}
+
 extern "C" int d3_conv_out_fused(const void* x, int pitch, const double* stats, const float* gamma,
                                  const float* beta, const float* w, const float* bias, int B, int H, int W, int dc,
-                                 float eps, float* out, int dtype, void* stream) {
+                                 float eps, float* out, void* workspace, int dtype, void* stream) {
   using namespace d3;
   D3_REQUIRE(x && stats && gamma && beta && w && bias && out, "conv_out: null pointer");
   D3_REQUIRE(dc == 1 || dc == 3, "conv_out: depth_channels must be 1 or 3 (got %d)", dc);
   if (dtype == D3_DTYPE_F32)
     return conv_out_f32(x, pitch, stats, gamma, beta, w, bias, B, H, W, dc, eps, out, static_cast<cudaStream_t>(stream));
-  ConvOutArgs a{static_cast<const uint16_t*>(x), pitch, stats, gamma, beta, w, bias, out, B, H, W, eps};
+  D3_REQUIRE(workspace != nullptr, "conv_out: workspace of d3_conv_out_workspace_bytes() bytes required");
   D3_REQUIRE(pitch % 8 == 0, "conv_out: pitch must be a multiple of 8");
-  dim3 grid(ceil_div(W, kCoTX), ceil_div(H, kCoTY), B);
+  ConvOutArgs a{static_cast<const uint16_t*>(x), pitch, stats, gamma, beta, w, bias, out,
+                static_cast<float*>(workspace), B, H, W, eps};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    D3_CHECK_CUDA(cudaFuncSetAttribute(conv_out_kernel<1, kBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)conv_out_smem<1>()));
-    D3_CHECK_CUDA(cudaFuncSetAttribute(conv_out_kernel<1, kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)conv_out_smem<1>()));
-    D3_CHECK_CUDA(cudaFuncSetAttribute(conv_out_kernel<3, kBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)conv_out_smem<3>()));
-    D3_CHECK_CUDA(cudaFuncSetAttribute(conv_out_kernel<3, kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)conv_out_smem<3>()));
-    attr_set = true;
-  }
-  if (dc == 1 && dtype == D3_DTYPE_BF16) conv_out_kernel<1, kBF16><<<grid, kCoThreads, conv_out_smem<1>(), st>>>(a);
-  else if (dc == 1) conv_out_kernel<1, kF16><<<grid, kCoThreads, conv_out_smem<1>(), st>>>(a);
-  else if (dtype == D3_DTYPE_BF16) conv_out_kernel<3, kBF16><<<grid, kCoThreads, conv_out_smem<3>(), st>>>(a);
-  else conv_out_kernel<3, kF16><<<grid, kCoThreads, conv_out_smem<3>(), st>>>(a);
+  const int n_groups = (H * W + 15) / 16;
+  const int per_block = kCoThreads / 32;
+  int gx = (num_sms() * (dc == 1 ? 2 : 1) * 2 + B - 1) / B;   // ~2 waves of resident blocks over the whole batch
+  if (gx > (n_groups + per_block - 1) / per_block) gx = (n_groups + per_block - 1) / per_block;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, B);
+  if (dc == 1 && dtype == D3_DTYPE_BF16) conv_out_taps_kernel<1, kBF16><<<grid, kCoThreads, 0, st>>>(a);
+  else if (dc == 1) conv_out_taps_kernel<1, kF16><<<grid, kCoThreads, 0, st>>>(a);
+  else if (dtype == D3_DTYPE_BF16) conv_out_taps_kernel<3, kBF16><<<grid, kCoThreads, 0, st>>>(a);
+  else conv_out_taps_kernel<3, kF16><<<grid, kCoThreads, 0, st>>>(a);
+  D3_LAUNCH_CHECK();
+  const size_t total = (size_t)B * dc * H * W;
+  int gb = (int)((total + 255) / 256);
+  if (gb > num_sms() * 16) gb = num_sms() * 16;
+  if (dc == 1) conv_out_gather_kernel<1><<<gb, 256, 0, st>>>(a.taps, bias, out, B, H, W);
+  else conv_out_gather_kernel<3><<<gb, 256, 0, st>>>(a.taps, bias, out, B, H, W);
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

@@ -207,9 +207,12 @@ def conv_out_fused(x: torch.Tensor, stats: torch.Tensor, gamma, beta, w, bias, d
         raise ValueError("conv_out_fused expects 128 input channels")
     if out is None:
         out = torch.empty((B, dc, H, W), dtype=torch.float32, device=x.device)
+    ws = None
+    if x.dtype != torch.float32:  # scratch for the 9*dc fp32 tap maps (torch's caching allocator; graph-capturable)
+        ws = torch.empty((_lib.lib().d3_conv_out_workspace_bytes(B, H, W, dc),), dtype=torch.uint8, device=x.device)
     _lib.check(_lib.lib().d3_conv_out_fused(x.data_ptr(), x.stride(2), stats.data_ptr(), gamma.data_ptr(),
                                             beta.data_ptr(), w.data_ptr(), bias.data_ptr(), B, H, W, dc, eps,
-                                            out.data_ptr(), _dt(x), _stream()))
+                                            out.data_ptr(), _ptr(ws), _dt(x), _stream()))
     return out
 
 

@@ -115,10 +115,13 @@ int d3_conv_in_direct(const float* planes, int C, const float* wT, const float* 
                       int W, float* out32, void* out16, int dtype, double* stats, void* stream);
 
 /* ---- conv_norm_out + SiLU + conv_out fused: bf16 NHWC [B,H,W,128] -> fp32 NCHW [B,dc,H,W] (dc = 1 or 3).
- * w fp32 [dc][9][128] (tap-major), stats = quad statistics of x ([B][32][2]). */
+ * w fp32 [dc][9][128] (tap-major), stats = quad statistics of x ([B][32][2]).  16-bit dtypes run as a streaming
+ * per-pixel GEMM into `workspace` (9*dc fp32 tap maps, d3_conv_out_workspace_bytes(B,H,W,dc) bytes, caller-owned
+ * scratch) followed by a 9-neighbour gather; D3_DTYPE_F32 ignores the workspace. */
+size_t d3_conv_out_workspace_bytes(int B, int H, int W, int dc);
 int d3_conv_out_fused(const void* x, int pitch, const double* stats, const float* gamma, const float* beta,
                       const float* w, const float* bias, int B, int H, int W, int dc, float eps, float* out,
-                      int dtype, void* stream);
+                      void* workspace, int dtype, void* stream);
 
 /* ---- timestep embedding (Timesteps(128) -> Linear -> SiLU -> Linear -> SiLU) and all ResNet projections.
  * t fp32 [nt] (nt = 1 for the sampling loop, = B for per-sample timesteps). Weights are passed transposed:
