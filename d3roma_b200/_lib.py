@@ -6,6 +6,7 @@ is raised.  The product path never routes through ``oracle/`` or a PyTorch re-im
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "libd3roma_b200.so"
@@ -121,7 +122,13 @@ def lib() -> C.CDLL:
     return _lib
 
 
+_SYNC_CHECK = bool(int(os.environ.get("D3_SYNC_CHECK", "0")))   # debugging aid: synchronise after every library call
+
+
 def check(rc: int) -> None:
     if rc != 0:
         msg = lib().d3_last_error()
         raise D3Error(f"d3roma_b200 error {rc}: {msg.decode() if msg else '?'}")
+    if _SYNC_CHECK:
+        import torch
+        torch.cuda.synchronize()

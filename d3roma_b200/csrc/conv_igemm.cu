@@ -1008,13 +1008,23 @@ int pass_width(int tw) {
   return 1;
 }
 
+// The epilogue reads the accumulator in 32-column windows starting at r*TW + sg*PW + {0, 32}: every window must end
+// inside the 256-column accumulator stage (a window running past column 512 of the second stage is a TMEM fault).
+bool t_tile_windows_ok(int th, int tw) {
+  const int pw = pass_width(tw);
+  const int segs = tw / pw;
+  const int c0max = (pw > 32) ? 32 : 0;
+  return (th - 1) * tw + (segs - 1) * pw + c0max + 32 <= 256;
+}
+
 void choose_tile_t(int Ho, int Wo, int* TH, int* TW) {
   double best = -1.0;
   int bh = 1, bw = 1;
   for (int tw = 1; tw <= 256 && tw <= Wo; ++tw) {
     int th = 256 / tw;
     if (th > Ho) th = Ho;
-    if (th < 1) continue;
+    while (th > 1 && !t_tile_windows_ok(th, tw)) --th;
+    if (th < 1 || !t_tile_windows_ok(th, tw)) continue;
     const int pw = pass_width(tw);
     if (pw < 16 && tw > 16) continue;  // avoid degenerate pass widths (e.g. prime tile widths)
     const double tiles = double(ceil_div(Ho, th)) * ceil_div(Wo, tw);
@@ -1478,6 +1488,8 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   int rc = 0;
   a.pass_w = use_t ? pass_width(a.TW) : 0;
   a.pass_h = (use_strips && a.TW < 64) ? 64 / a.TW : 1;
+  if (use_t && !use_strips)
+    D3_REQUIRE(t_tile_windows_ok(a.TH, a.TW), "conv: internal error: tile %dx%d overruns the accumulator", a.TH, a.TW);
   {
     static int td = -1;
     if (td < 0) { const char* e = getenv("D3_CONV_T_DIRECT"); td = e ? atoi(e) : 0; }

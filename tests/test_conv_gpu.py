@@ -25,6 +25,8 @@ CASES = [
     (1, 8, 320, 256, 128, 3, 1, 128, 128, False),  # halo-block variant with folded 1x1 shortcut slabs
     (2, 5, 200, 64, 128, 3, 1, 0, 0, True),        # ragged width
     (1, 6, 960, 128, 128, 3, 1, 0, 0, False),      # 544x960 family
+    (2, 272, 480, 128, 128, 3, 2, 0, 0, False),    # regression: >1 tile per CTA with a tile whose last accumulator
+    (40, 24, 40, 128, 128, 3, 1, 0, 0, True),      #   window used to run past TMEM column 512 (2nd stage)
 ]
 
 
