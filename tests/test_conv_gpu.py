@@ -112,3 +112,47 @@ def test_kernel_variants_match():
         e = dict(os.environ, **env)
         r = subprocess.run([sys.executable, script], cwd=root, env=e, capture_output=True, text=True, timeout=300)
         assert "VARIANT_OK" in r.stdout, (env, r.stdout[-800:], r.stderr[-800:])
+
+
+def test_conv_fuzz_random_shapes():
+    """Seeded random shapes (ragged tiles, every kernel family, several tiles per persistent CTA so that both
+    accumulator stages and every ring wrap are exercised) against torch fp32 on the same rounded operands."""
+    import random
+    from d3roma_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    rnd = random.Random(1234)
+    g = torch.Generator(device="cuda").manual_seed(99)
+    n_multi = 0
+    for it in range(48):
+        cout = rnd.choice([128, 128, 128, 256, 512])
+        cin = rnd.choice([64, 128, 256])
+        k, stride = rnd.choice([(3, 1), (3, 1), (3, 1), (3, 2), (1, 1)])
+        H, W = rnd.randint(3, 60) * stride, rnd.randint(3, 90) * stride
+        target = rnd.choice([3_000, 30_000, 60_000, 120_000])   # output pixels: 148 x 256 = 37 888 fill one wave
+        B = max(1, min(64, -(-target // ((H // stride) * (W // stride)))))
+        use_sc = (k == 3 and stride == 1 and rnd.random() < 0.3)
+        use_res = (not use_sc) and rnd.random() < 0.4
+        dt = rnd.choice([torch.bfloat16, torch.float16])
+        Ho, Wo = H // stride, W // stride
+        n_multi += int(B * Ho * Wo > 148 * 256)
+        x = torch.randn(B, H, W, cin, device="cuda", generator=g).to(dt)
+        w = (torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5).to(dt)
+        bias = torch.randn(B, cout, device="cuda", generator=g)
+        sc1 = wsc = None
+        if use_sc:
+            sc1 = torch.randn(B, Ho, Wo, 64, device="cuda", generator=g).to(dt)
+            wsc = (torch.randn(cout, 64, device="cuda", generator=g) / 8.0).to(dt)
+        res = torch.randn(B, Ho, Wo, cout, device="cuda", generator=g).to(dt) if use_res else None
+        stats = torch.zeros(B, cout // 4, 2, dtype=torch.float64, device="cuda")
+        out = ops.conv2d_igemm(x, ops.pack_conv_weight(w, wsc, dtype=dt), bias, ksize=k, stride=stride, sc1=sc1,
+                               residual=res, stats=stats)
+        torch.cuda.synchronize()
+        ref = _ref(x, w, None, stride, sc1, wsc, res) + bias[:, None, None, :]
+        err = (out.float() - ref).abs()
+        tol = 2.0 ** -7 * ref.abs() + 2e-2 if dt == torch.bfloat16 else 2.0 ** -10 * ref.abs() + 3e-3
+        case = (it, B, H, W, cin, cout, k, stride, use_sc, use_res, str(dt))
+        assert bool((err <= tol).all()), (case, err.max().item())
+        o = out.double().reshape(B, Ho * Wo, cout // 4, 4)
+        s_ref = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
+        assert torch.allclose(stats, s_ref, rtol=1e-5, atol=1e-3), case
+    assert n_multi >= 12

@@ -83,3 +83,22 @@ def test_unet_sceneflow_shape_544x960(dtype, tol):
     err = (y - y_ref).abs().max().item()
     print(f"{dtype} 544x960 Cin=12 dc=3: max-abs {err:.3e} (ref absmax {y_ref.abs().max():.3f})")
     assert err <= tol, err
+
+
+@pytest.mark.parametrize("hw,B", [((544, 960), 3), ((96, 160), 5)])
+def test_unet_batch_invariance(hw, B):
+    """A batched forward equals the per-sample forwards (no cross-sample arithmetic anywhere).  At
+    544x960 with B = 3 every persistent conv CTA walks several tiles of every tile shape the 544x960 family produces
+    (this caught a TMEM window overrun that a B = 1 run cannot reach)."""
+    from d3roma_b200.unet import UNet2DModel
+    from d3roma_b200.weights import random_init_state_dict
+    net = UNet2DModel(sample_size=hw, in_channels=8, out_channels=1, compute_dtype="fp16").to("cuda")
+    net.load_state_dict(random_init_state_dict(8, 1, seed=0))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(B, 1, *hw, device="cuda", generator=g)
+    c = torch.randn(B, 7, *hw, device="cuda", generator=g)
+    y = net.forward_split(x, c, 60).clone()
+    assert torch.isfinite(y).all()
+    for i in range(B):
+        yi = net.forward_split(x[i:i + 1].contiguous(), c[i:i + 1].contiguous(), 60)
+        torch.testing.assert_close(yi, y[i:i + 1], rtol=0, atol=2e-3)
