@@ -78,6 +78,8 @@ def _declare(lib: C.CDLL) -> None:
         "d3_conv2d_igemm": (i32, [C.POINTER(ConvParams), vp]),
         "d3_groupnorm_silu": (i32, [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, f32, i32, vp, i32, i32,
                                     vp]),
+        "d3_groupnorm_silu_dual": (i32, [vp, i32, i32, vp, i32, i32, f32, vp, vp, i32, i32, vp, i32, vp, vp, i32, i32,
+                                         vp, i32, i32, vp]),
         "d3_upsample_nearest2x": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
         "d3_im2col_input": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, i32, vp]),
         "d3_conv_in_direct": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, vp, vp, i32, vp, vp]),

@@ -34,14 +34,22 @@ struct GnArgs {
   float eps;
   int silu;
   int pix_per_block;
+  // dual mode (single source only): a second normalisation of the SAME input with its own affine parameters and
+  // grouping, written to a second tensor - the up-path copy of a skip tensor (see d3_groupnorm_silu_dual)
+  const float* gamma2;
+  const float* beta2;
+  uint16_t* out2;
+  int pout2, groups2, silu2;
 };
 
-template <int DT>
+template <int DT, bool DUAL = false>
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
   // blockDim.x = nvec * k (nvec = C/8 16-byte vectors per pixel): every thread owns ONE channel vector for the whole
   // block, so its 8 scale/shift pairs live in registers and the inner loop is load - 8 FMA - 8 SiLU - store.
   __shared__ float s_mean[32];
   __shared__ float s_rstd[32];
+  __shared__ float s_mean2[32];
+  __shared__ float s_rstd2[32];
   const int b = blockIdx.y;
   const int C = a.C1 + a.C2;
   const int cpg = C / a.groups;
@@ -63,6 +71,22 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
     s_mean[g] = (float)mean;
     s_rstd[g] = (float)(1.0 / sqrt(var + (double)a.eps));
   }
+  if (DUAL && threadIdx.x >= 32 && threadIdx.x < 32 + a.groups2) {
+    const int g = threadIdx.x - 32;
+    const int cpg2 = C / a.groups2, qpg2 = cpg2 >> 2;
+    double s = 0.0, ss = 0.0;
+    for (int i = 0; i < qpg2; ++i) {
+      const double* p = a.st1 + ((size_t)b * Q1 + g * qpg2 + i) * 2;
+      s += p[0];
+      ss += p[1];
+    }
+    const double n = (double)a.HW * cpg2;
+    const double mean = s / n;
+    double var = ss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean2[g] = (float)mean;
+    s_rstd2[g] = (float)(1.0 / sqrt(var + (double)a.eps));
+  }
   __syncthreads();
   const int nvec = C >> 3;
   const int nvec1 = a.C1 >> 3;
@@ -77,6 +101,17 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
     sc[k] = a.gamma[c] * s_rstd[g];
     sh[k] = a.beta[c] - s_mean[g] * sc[k];
   }
+  float sc2[DUAL ? 8 : 1], sh2[DUAL ? 8 : 1];
+  if constexpr (DUAL) {
+    const int cpg2 = C / a.groups2;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = vec * 8 + k;
+      const int g = c / cpg2;
+      sc2[k] = a.gamma2[c] * s_rstd2[g];
+      sh2[k] = a.beta2[c] - s_mean2[g] * sc2[k];
+    }
+  }
   const int pix0 = blockIdx.x * a.pix_per_block;
   int npix = a.HW - pix0;
   if (npix > a.pix_per_block) npix = a.pix_per_block;
@@ -84,6 +119,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
   const uint16_t* src = (vec < nvec1) ? a.x1 + base_pix * a.p1 + vec * 8 : a.x2 + base_pix * a.p2 + (vec - nvec1) * 8;
   const int sp = (vec < nvec1) ? a.p1 : a.p2;
   uint16_t* dst = a.out + base_pix * a.pout + vec * 8;
+  uint16_t* dst2 = DUAL ? a.out2 + base_pix * a.pout2 + vec * 8 : nullptr;
 
   constexpr int U = 4;
   for (int p0 = prow; p0 < npix; p0 += pstride * U) {
@@ -118,6 +154,27 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
         o.z = pack2<DT>(y[4], y[5]);
         o.w = pack2<DT>(y[6], y[7]);
         *reinterpret_cast<uint4*>(dst + (size_t)p * a.pout) = o;
+        if constexpr (DUAL) {
+          float z[8];
+          z[0] = fmaf(f0.x, sc2[0], sh2[0]);
+          z[1] = fmaf(f0.y, sc2[1], sh2[1]);
+          z[2] = fmaf(f1.x, sc2[2], sh2[2]);
+          z[3] = fmaf(f1.y, sc2[3], sh2[3]);
+          z[4] = fmaf(f2.x, sc2[4], sh2[4]);
+          z[5] = fmaf(f2.y, sc2[5], sh2[5]);
+          z[6] = fmaf(f3.x, sc2[6], sh2[6]);
+          z[7] = fmaf(f3.y, sc2[7], sh2[7]);
+          if (a.silu2) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) z[k] = silu_fast(z[k]);
+          }
+          uint4 o2;
+          o2.x = pack2<DT>(z[0], z[1]);
+          o2.y = pack2<DT>(z[2], z[3]);
+          o2.z = pack2<DT>(z[4], z[5]);
+          o2.w = pack2<DT>(z[6], z[7]);
+          *reinterpret_cast<uint4*>(dst2 + (size_t)p * a.pout2) = o2;
+        }
       }
     }
   }
@@ -145,6 +202,32 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint16_t* __restr
   }
 }
 
+}  // namespace
+}  // namespace d3
+
+namespace d3 {
+namespace {
+int launch_gn(GnArgs& a, int B, int dtype, bool dual, cudaStream_t stream) {
+  const int C = a.C1 + a.C2;
+  // aim for ~8 blocks per SM over the whole batch, but at least 32 KB of work per block
+  int blocks_per_sample = ceil_div(num_sms() * 8, B);
+  int ppb = ceil_div(a.HW, blocks_per_sample);
+  const int min_ppb = ceil_div(16384, C);
+  if (ppb < min_ppb) ppb = min_ppb;
+  a.pix_per_block = ppb;
+  dim3 grid(ceil_div(a.HW, ppb), B);
+  const int nvec = C / 8;
+  const int threads = nvec * (kGnThreads / nvec > 0 ? kGnThreads / nvec : 1);  // multiple of nvec, <= 256 (nvec <= 128)
+  if (dual) {
+    if (dtype == D3_DTYPE_F16) gn_apply_kernel<kF16, true><<<grid, threads, 0, stream>>>(a);
+    else gn_apply_kernel<kBF16, true><<<grid, threads, 0, stream>>>(a);
+  } else {
+    if (dtype == D3_DTYPE_F16) gn_apply_kernel<kF16><<<grid, threads, 0, stream>>>(a);
+    else gn_apply_kernel<kBF16><<<grid, threads, 0, stream>>>(a);
+  }
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
 }  // namespace
 }  // namespace d3
 
@@ -179,21 +262,41 @@ extern "C" int d3_groupnorm_silu(const void* x1, int C1, int p1, const double* s
   a.groups = groups;
   a.eps = eps;
   a.silu = apply_silu;
-  // aim for ~8 blocks per SM over the whole batch, but at least 32 KB of work per block
-  int blocks_per_sample = ceil_div(num_sms() * 8, B);
-  int ppb = ceil_div(HW, blocks_per_sample);
-  const int min_ppb = ceil_div(16384, C);
-  if (ppb < min_ppb) ppb = min_ppb;
-  a.pix_per_block = ppb;
-  dim3 grid(ceil_div(HW, ppb), B);
-  const int nvec = C / 8;
-  const int threads = nvec * (kGnThreads / nvec > 0 ? kGnThreads / nvec : 1);  // multiple of nvec, <= 256 (nvec <= 128)
-  if (dtype == D3_DTYPE_F16)
-    gn_apply_kernel<kF16><<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  else
-    gn_apply_kernel<kBF16><<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(a);
-  D3_LAUNCH_CHECK();
-  return D3_OK;
+  return launch_gn(a, B, dtype, false, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int d3_groupnorm_silu_dual(const void* x, int C, int pitch, const double* stats, int B, int HW, float eps,
+                                      const float* gamma_a, const float* beta_a, int groups_a, int silu_a, void* out_a,
+                                      int pitch_a, const float* gamma_b, const float* beta_b, int groups_b, int silu_b,
+                                      void* out_b, int pitch_b, int dtype, void* stream) {
+  using namespace d3;
+  D3_REQUIRE(x && stats && gamma_a && beta_a && out_a && gamma_b && beta_b && out_b, "groupnorm_dual: null pointer");
+  D3_REQUIRE(dtype == D3_DTYPE_BF16 || dtype == D3_DTYPE_F16, "groupnorm_dual: 16-bit dtypes only (got %d)", dtype);
+  D3_REQUIRE(C <= kMaxC && C % 8 == 0 && pitch % 8 == 0 && pitch_a % 8 == 0 && pitch_b % 8 == 0,
+             "groupnorm_dual: channel count / pitches must be multiples of 8");
+  D3_REQUIRE(groups_a >= 1 && groups_a <= 32 && C % groups_a == 0 && (C / groups_a) % 4 == 0 && groups_b >= 1 &&
+                 groups_b <= 32 && C % groups_b == 0 && (C / groups_b) % 4 == 0,
+             "groupnorm_dual: unsupported grouping C=%d groups=%d/%d", C, groups_a, groups_b);
+  GnArgs a{};
+  a.x1 = static_cast<const uint16_t*>(x);
+  a.st1 = stats;
+  a.gamma = gamma_a;
+  a.beta = beta_a;
+  a.out = static_cast<uint16_t*>(out_a);
+  a.C1 = C;
+  a.p1 = pitch;
+  a.pout = pitch_a;
+  a.HW = HW;
+  a.groups = groups_a;
+  a.eps = eps;
+  a.silu = silu_a;
+  a.gamma2 = gamma_b;
+  a.beta2 = beta_b;
+  a.out2 = static_cast<uint16_t*>(out_b);
+  a.pout2 = pitch_b;
+  a.groups2 = groups_b;
+  a.silu2 = silu_b;
+  return launch_gn(a, B, dtype, true, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int d3_upsample_nearest2x(const void* in, int B, int H, int W, int C, int pin, void* out, int pout,

@@ -142,6 +142,27 @@ def groupnorm_silu(x1: torch.Tensor, stats1: torch.Tensor, gamma: torch.Tensor, 
     return out
 
 
+def groupnorm_silu_dual(x: torch.Tensor, stats: torch.Tensor, gamma_a: torch.Tensor, beta_a: torch.Tensor,
+                        gamma_b: torch.Tensor, beta_b: torch.Tensor, out_b: torch.Tensor, *, groups_a: int = 32,
+                        groups_b: int = 32, silu_a: bool = True, silu_b: bool = True, eps: float = 1e-5,
+                        out_a: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One read of ``x``, two normalised outputs (``d3_groupnorm_silu_dual``): returns ``out_a``; ``out_b`` may be a
+    channel-range view of a wider NHWC buffer (the up-block's concatenated GroupNorm output)."""
+    _check_nhwc(x, "x")
+    B, H, W, C = x.shape
+    if out_a is None:
+        out_a = torch.empty((B, H, W, C), dtype=x.dtype, device=x.device)
+    if out_b.shape != (B, H, W, C) or out_b.dtype != x.dtype or out_b.stride(3) != 1:
+        raise ValueError("groupnorm_silu_dual: out_b must be a [B,H,W,C] (view of an) NHWC tensor of x's dtype")
+    if gamma_b.numel() != C or beta_b.numel() != C or not (gamma_b.is_contiguous() and beta_b.is_contiguous()):
+        raise ValueError("groupnorm_silu_dual: gamma_b / beta_b must be contiguous [C] slices")
+    _lib.check(_lib.lib().d3_groupnorm_silu_dual(
+        x.data_ptr(), C, x.stride(2), stats.data_ptr(), B, H * W, eps, gamma_a.data_ptr(), beta_a.data_ptr(), groups_a,
+        int(silu_a), out_a.data_ptr(), out_a.stride(2), gamma_b.data_ptr(), beta_b.data_ptr(), groups_b, int(silu_b),
+        out_b.data_ptr(), out_b.stride(2), _dt(x), _stream()))
+    return out_a
+
+
 def upsample_nearest2x(x: torch.Tensor) -> torch.Tensor:
     _check_nhwc(x, "x")
     B, H, W, Cc = x.shape

@@ -284,10 +284,30 @@ class UNet2DModel:
         out = ops.conv2d_igemm(x, w, b, ksize=ksize, stride=stride, sc1=sc1, sc2=sc2, residual=residual, stats=stats)
         return _Act(out, stats)
 
-    def _resnet(self, p: str, h: _Act, skip: Optional[_Act], cout: int, bias1: torch.Tensor, B: int) -> _Act:
+    def _resnet(self, p: str, h: _Act, skip: Optional[_Act], cout: int, bias1: torch.Tensor, B: int,
+                up_copy=None, pre: Optional[torch.Tensor] = None) -> _Act:
+        """One ResnetBlock2D.  ``up_copy = (p_up, Cx, Cs)``: ``h`` is a skip tensor that the up-path resnet ``p_up``
+        will consume as the second half of its concatenated norm1 input - norm1 here also writes that normalised copy
+        (returned through ``self._pre_out``).  ``pre``: the concat buffer whose skip half was filled that way; only
+        the hidden-state half is normalised now."""
         W = self._w
-        a1 = ops.groupnorm_silu(h.t, h.stats, W[p + ".n1.g"], W[p + ".n1.b"],
-                                x2=None if skip is None else skip.t, stats2=None if skip is None else skip.stats)
+        if pre is not None:
+            Cx = h.t.shape[3]
+            cpg = pre.shape[3] // 32
+            ops.groupnorm_silu(h.t, h.stats, W[p + ".n1.g"][:Cx], W[p + ".n1.b"][:Cx], groups=Cx // cpg,
+                               out=pre[..., :Cx])
+            a1 = pre
+        elif up_copy is not None:
+            p_up, Cx, Cs = up_copy
+            Bn, Hh, Ww, _ = h.t.shape
+            buf = torch.empty((Bn, Hh, Ww, Cx + Cs), dtype=h.t.dtype, device=h.t.device)
+            cpg = (Cx + Cs) // 32
+            a1 = ops.groupnorm_silu_dual(h.t, h.stats, W[p + ".n1.g"], W[p + ".n1.b"], W[p_up + ".n1.g"][Cx:],
+                                         W[p_up + ".n1.b"][Cx:], buf[..., Cx:], groups_b=Cs // cpg)
+            self._pre_out = buf
+        else:
+            a1 = ops.groupnorm_silu(h.t, h.stats, W[p + ".n1.g"], W[p + ".n1.b"],
+                                    x2=None if skip is None else skip.t, stats2=None if skip is None else skip.stats)
         h1 = self._conv(a1, W[p + ".w1"], bias1, 3, B)
         del a1
         a2 = ops.groupnorm_silu(h1.t, h1.stats, W[p + ".n2.g"], W[p + ".n2.b"])
@@ -297,6 +317,18 @@ class UNet2DModel:
         if p in self._identity_slab:
             return self._conv(a2, W[p + ".w2"], W[p + ".b2"], 3, B, sc1=h.t)
         return self._conv(a2, W[p + ".w2"], W[p + ".b2"], 3, B, residual=h.t)
+
+    def _up_consumer(self, k: int):
+        """(prefix, Cx, Cs) of the up-path resnet that pops skip ``k`` (of 18), or None when its norm1 groups would
+        straddle the hidden/skip boundary (C = 384, 768) or the fp32 path is active."""
+        if self._adt == torch.float32:
+            return None
+        kind, bi, bj, cin_h, cin_s, cout, attn = self._specs[14 + (17 - k)]   # 12 down + 2 mid resnets precede
+        assert kind == "up"
+        cpg = (cin_h + cin_s) // 32
+        if cin_h % cpg or cin_s % cpg or (cin_h + cin_s) % 32:
+            return None
+        return (self._rprefix(kind, bi, bj), cin_h, cin_s)
 
     def _attention(self, a: str, h: _Act, B: int) -> _Act:
         W = self._w
@@ -377,12 +409,25 @@ class UNet2DModel:
             h = self._conv(col, W["conv_in.w"], W["conv_in.b"], 1, B)
             del col
         skips: List[_Act] = [h]
+        pre: Dict[int, torch.Tensor] = {}   # skip index -> concat buffer whose skip half is already normalised
+
+        def resnet_on_skip(p, h, cout):
+            """A resnet whose input is the most recent skip tensor: its norm1 pass also writes the up path's copy."""
+            k = len(skips) - 1
+            upc = self._up_consumer(k)
+            self._pre_out = None
+            out = self._resnet(p, h, None, cout, bias1(p, cout), B, up_copy=upc)
+            if self._pre_out is not None:
+                pre[k] = self._pre_out
+                self._pre_out = None
+            return out
+
         it = iter(self._specs)
         for i in range(6):
             for j in range(2):
                 kind, bi, bj, cin_h, cin_s, cout, attn = next(it)
                 p = self._rprefix(kind, bi, bj)
-                h = self._resnet(p, h, None, cout, bias1(p, cout), B)
+                h = resnet_on_skip(p, h, cout)     # h is skips[-1] here (conv_in / previous resnet / downsample)
                 if attn:
                     h = self._attention(self._aprefix(kind, bi, bj), h, B)
                 skips.append(h)
@@ -393,14 +438,15 @@ class UNet2DModel:
         for j in range(2):
             kind, bi, bj, cin_h, cin_s, cout, attn = next(it)
             p = self._rprefix(kind, bi, bj)
-            h = self._resnet(p, h, None, cout, bias1(p, cout), B)
+            h = resnet_on_skip(p, h, cout) if j == 0 else self._resnet(p, h, None, cout, bias1(p, cout), B)
             if attn:
                 h = self._attention(self._aprefix(kind, bi, bj), h, B)
         for i in range(6):
             for j in range(3):
                 kind, bi, bj, cin_h, cin_s, cout, attn = next(it)
                 p = self._rprefix(kind, bi, bj)
-                h = self._resnet(p, h, skips.pop(), cout, bias1(p, cout), B)
+                k = len(skips) - 1
+                h = self._resnet(p, h, skips.pop(), cout, bias1(p, cout), B, pre=pre.pop(k, None))
                 if attn:
                     h = self._attention(self._aprefix(kind, bi, bj), h, B)
             if i < 5:

@@ -95,6 +95,17 @@ int d3_groupnorm_silu(const void* x1, int C1, int pitch1, const double* stats1, 
                       const double* stats2, const float* gamma, const float* beta, int B, int HW, int groups,
                       float eps, int apply_silu, void* out, int out_pitch, int dtype, void* stream);
 
+/* ---- the same pass with TWO outputs from one read of a single-source tensor: out_a = act_a(GN_a(x)) and
+ * out_b = act_b(GN_b(x)) with separate affine parameters and groupings (groups_* groups over the C channels of x).
+ * Used for skip tensors: the down path normalises x for its next conv (a) and, in the same pass, writes the up path's
+ * normalised copy (b) straight into the channel range of the up-block's concatenated input (out_b pre-offset,
+ * pitch_b = C_x + C_skip), so the up-block GroupNorm no longer re-reads the skip (ResnetBlock2D.norm1 over
+ * torch.cat([hidden, skip]) in diffusers' UpBlock2D).  16-bit dtypes only. */
+int d3_groupnorm_silu_dual(const void* x, int C, int pitch, const double* stats, int B, int HW, float eps,
+                           const float* gamma_a, const float* beta_a, int groups_a, int silu_a, void* out_a,
+                           int pitch_a, const float* gamma_b, const float* beta_b, int groups_b, int silu_b,
+                           void* out_b, int pitch_b, int dtype, void* stream);
+
 /* ---- nearest-neighbour 2x upsample (F.interpolate(scale_factor=2, mode="nearest") of Upsample2D) */
 int d3_upsample_nearest2x(const void* in, int B, int H, int W, int C, int in_pitch, void* out, int out_pitch,
                           void* stream);
