@@ -176,9 +176,7 @@ class GuidedDiffusionPipeline:
             shape = (batch_size, depth_channels, image_shape[-2], image_shape[-1])
         else:
             raise ValueError("sample_size must be int or tuple of ints")
-        image = randn_tensor(shape, generator=generator)  # CPU draw (custom_pipelines.py:117-119)
         dev = self.device
-        image = image.to(dev, torch.float32).contiguous()
         srcs = {"rgb": rgb_images, "left": left_images, "right": right_images, "raw": sim_disp}
         srcs = {k: (None if v is None else v.to(dev, torch.float32)) for k, v in srcs.items()}
         if cond_channels not in COND_ORDER:
@@ -192,6 +190,12 @@ class GuidedDiffusionPipeline:
             return torch.cat(parts, dim=1).contiguous() if len(parts) > 1 else parts[0].contiguous()
 
         cond = None if add_noise_rgb else build_cond()
+        if cond is not None and hasattr(self.unet, "prime_conditioning"):
+            self.unet.prime_conditioning(shape, cond, self.use_cuda_graph)   # GPU works while the host draws x_T
+        # CPU draw, then moved (custom_pipelines.py:117-123); with CPU generator(s) the values do not depend on the target
+        # device, so the per-sample draws go straight into a pinned buffer and across asynchronously
+        image = randn_tensor(shape, generator=generator, device=dev if generator is not None else None)
+        image = image.to(dev, torch.float32).contiguous()
         image, stack = self._loop(image, cond, srcs, build_cond, num_inference_steps, plot_every, add_noise_rgb,
                                   raw_depth)
         return GuidedPipelineOutput(images=image, images_pred_orig=stack, images_perturbed_orig=stack,

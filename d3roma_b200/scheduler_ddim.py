@@ -7,6 +7,7 @@ as the reference, so ``prev_sample`` / ``pred_original_sample`` are bit-identica
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Tuple, Union
 
@@ -94,9 +95,22 @@ def clip_mode_of(config) -> int:
     return 1 if config.clip_sample else 0
 
 
+_RANDN_POOL = None
+
+
+def _randn_pool():
+    global _RANDN_POOL
+    if _RANDN_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _RANDN_POOL = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1), thread_name_prefix="d3-randn")
+    return _RANDN_POOL
+
+
 def randn_tensor(shape, generator=None, device=None, dtype=None):
     """diffusers' ``randn_tensor`` semantics: a CPU generator draws on the CPU and the result is moved; a list of
-    generators draws one sample each (batch-shard-invariant noise)."""
+    generators draws one sample each (batch-shard-invariant noise).  A list of CPU generators is drawn by
+    a small thread pool (the generators are independent, so the values are those of the serial loop) straight into one
+    pinned buffer that is then copied to the device asynchronously."""
     device = torch.device(device) if device is not None else torch.device("cpu")
     rand_device = device
     if generator is not None:
@@ -105,6 +119,12 @@ def randn_tensor(shape, generator=None, device=None, dtype=None):
             rand_device = torch.device("cpu")
     if isinstance(generator, (list, tuple)):
         one = (1,) + tuple(shape[1:])
+        if rand_device.type == "cpu" and len(generator) > 1:
+            buf = torch.empty((len(generator),) + tuple(shape[1:]), dtype=dtype or torch.float32,
+                              pin_memory=(device.type == "cuda"))
+            list(_randn_pool().map(lambda ig: torch.randn(one, generator=ig[1], dtype=buf.dtype, out=buf[ig[0]:ig[0] + 1]),
+                                   enumerate(generator)))
+            return buf.to(device, non_blocking=True) if device.type == "cuda" else buf
         return torch.cat([torch.randn(one, generator=g, device=rand_device, dtype=dtype) for g in generator]).to(device)
     return torch.randn(tuple(shape), generator=generator, device=rand_device, dtype=dtype).to(device)
 

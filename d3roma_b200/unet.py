@@ -505,6 +505,25 @@ class UNet2DModel:
         self.graph_kernel_launches += g["n_kernels"]
         return g["y"]
 
+    @torch.no_grad()
+    def prime_conditioning(self, sample_shape, cond: Optional[torch.Tensor], graphed: bool = True) -> None:
+        """Launch the per-loop conditioning work (static-buffer copy + conv_in conditioning term) NOW, so that it runs
+        on the GPU while the host is still busy (the pipeline calls this before drawing x_T on the CPU generators).
+        The first forward of the loop then finds everything cached.  No-op when there is nothing to prepare."""
+        if cond is None or self._adt == torch.float32 or sample_shape[1] > 3 or not self._loaded:
+            return
+        Cs = int(sample_shape[1])
+        if graphed:
+            g = self._graphs.get((tuple(sample_shape), tuple(cond.shape), cond.device.index))
+            if g is None or g["cond_src"] is cond:
+                return
+            g["c"].copy_(cond)
+            g["cond_src"] = cond
+            if g["base"] is not None:
+                self.cond_base(g["c"], Cs, out=g["base"])
+        else:
+            self.cond_base(cond, Cs)
+
     def reset_graphs(self):
         self._graphs.clear()
 

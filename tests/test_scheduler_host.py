@@ -109,3 +109,17 @@ def test_pipeline_argument_contract():
     out = GuidedPipelineOutput(images=torch.zeros(1))
     out.images = torch.ones(1)  # callers reassign fields (evaluate.py:103-111)
     assert out.images.item() == 1 and out["images"].item() == 1
+
+
+def test_randn_tensor_threaded_list_matches_serial_draws():
+    """A list of CPU generators is drawn by a thread pool into one buffer: same values as diffusers' serial loop
+    (one ``torch.randn((1, ...), generator=g)`` per sample, concatenated)."""
+    import torch
+    from d3roma_b200.scheduler_ddim import randn_tensor
+    shape = (5, 1, 24, 40)
+    a = randn_tensor(shape, generator=[torch.Generator().manual_seed(100 + i) for i in range(5)])
+    b = torch.cat([torch.randn((1,) + shape[1:], generator=torch.Generator().manual_seed(100 + i)) for i in range(5)])
+    assert torch.equal(a, b)
+    g = torch.Generator().manual_seed(3)
+    c = randn_tensor(shape, generator=g)
+    assert torch.equal(c, torch.randn(shape, generator=torch.Generator().manual_seed(3)))
