@@ -2,7 +2,7 @@
 
 Public surface mirrors the reference's classes for this path (jie0530/d3roma ``core/``):
 ``GuidedDiffusionPipeline``, ``MyDDIMScheduler``, ``MyDDPMScheduler``, ``FlowGuidance``, ``UNet2DModel``,
-``Normalizer``, ``InputPadder``.  All arithmetic runs in ``libd3roma_b200.so`` (build: ``python -m d3roma_b200.build``).
+``Normalizer``, ``InputPadder``, ``D3RoMa`` (single-frame inference front end).  All arithmetic runs in ``libd3roma_b200.so`` (build: ``python -m d3roma_b200.build``).
 """
 from .guidance import FlowGuidance  # noqa: F401
 from .pipelines import GuidedDiffusionPipeline, GuidedPipelineOutput  # noqa: F401
@@ -11,5 +11,6 @@ from .scheduler_ddim import DDIMSchedulerOutput, MyDDIMScheduler  # noqa: F401
 from .scheduler_ddpm import DDPMSchedulerOutput, MyDDPMScheduler  # noqa: F401
 from .unet import UNet2DModel  # noqa: F401
 from .metrics import compute_errors, compute_scale_and_shift, metrics_to_dict  # noqa: F401
+from .inference import D3RoMa  # noqa: F401
 
 __version__ = "0.1.0"

@@ -233,6 +233,20 @@ int d3_normalize_ssi(const float* x, const float* mask, const float* low_up, int
                      float* out, void* stream);
 int d3_affine_rows(const float* y, const float* scale_shift, int rows, int64_t HW, float* out, void* stream);
 
+/* ---- camera-frame front end (inference.py:99-213: cv2.resize + .float() + (x/255-0.5)*2 + batchify, padded as
+ * InputPadder would).  frames: uint8 [B,Hs,Ws,Cimg] (Cimg 1 = gray tiled to 3, 3 = RGB, 4 = RGBA without alpha);
+ * out: fp32 NCHW [B,3,Hp,Wp] where the H x W resized image sits at (pad_top, pad_left) and the border is replicated.
+ * The bilinear resize is OpenCV's 8-bit fixed-point INTER_LINEAR, bit for bit. */
+int d3_frame_to_input(const uint8_t* frames, int B, int Hs, int Ws, int Cimg, int H, int W, int pad_top, int pad_left,
+                      int Hp, int Wp, float* out, void* stream);
+
+/* ---- raw sensor depth (metres, fp32 [B,Hs,Ws]) -> cv2.resize(INTER_NEAREST) to H x W -> raw disparity
+ * fxb / depth where depth > 0 else 0 (inference.py:184-186) [B,1,H,W], validity mask (raw_disp > 0) [B,1,H,W], and
+ * the Normalizer("average")-normalised, replicate-padded conditioning map [B,1,Hp,Wp] (utils.py:171-196, 297-325). */
+int d3_depth_to_input(const float* depth, int B, int Hs, int Ws, int H, int W, int pad_top, int pad_left, int Hp,
+                      int Wp, float fxb, float bound, float gamma, float t, float s, float* raw_disp, float* mask,
+                      float* norm_padded, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

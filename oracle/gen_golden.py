@@ -316,11 +316,42 @@ def gen_postproc(store):
     store["ssi/den_out"] = _np(n.denormalize(yb, raw, mk.float()))
 
 
+def gen_frontend(store):
+    """Frame preprocessing of inference.py:108-213 pinned to cv2 itself: small uint8 frames / depth maps and what
+    ``cv2.resize`` + the reference's torch arithmetic produce for them (restated in oracle/frontend_ref.py because the
+    reference class needs hydra + a checkpoint to construct)."""
+    import cv2
+    rng = np.random.default_rng(2024)
+    store["cv2_version"] = np.array([int(v) for v in cv2.__version__.split(".")[:3]])
+    cases = [("down", (45, 80), (36, 64), 3), ("up", (20, 30), (36, 64), 3), ("same", (36, 64), (36, 64), 3),
+             ("odd", (53, 97), (36, 64), 4), ("gray", (48, 72), (36, 64), 1)]
+    for name, (hs, ws), (h, w), c in cases:
+        img = rng.integers(0, 256, (hs, ws) if c == 1 else (hs, ws, c), dtype=np.uint8)
+        depth = (rng.random((hs, ws)) * 1.7 + 0.3).astype(np.float32)
+        depth[rng.random((hs, ws)) < 0.2] = 0.0
+        src = img if c == 1 else img[..., :3]
+        if c == 1:
+            src = np.tile(src[..., None], (1, 1, 3))
+        res = cv2.resize(np.ascontiguousarray(src), (w, h), interpolation=cv2.INTER_LINEAR)
+        t = torch.from_numpy(res).permute(2, 0, 1).float()
+        d = cv2.resize(depth, dsize=(w, h), interpolation=cv2.INTER_NEAREST)
+        dt = torch.from_numpy(d[..., None]).permute(2, 0, 1).float()
+        raw_disp = torch.zeros_like(dt)
+        valid = dt > 0
+        raw_disp[valid] = 24.547 / dt[valid]
+        store[f"{name}/img"], store[f"{name}/depth"] = img, depth
+        store[f"{name}/size"] = np.array([h, w])
+        store[f"{name}/resized_u8"] = res
+        store[f"{name}/normalized"] = _np((t / 255. - 0.5) * 2)
+        store[f"{name}/raw_disp"] = _np(raw_disp)
+        store[f"{name}/norm_disp"] = _np(((torch.clamp(raw_disp, max=128.0) / 128.0) - 0.5) * 2.0)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
     for name, fn in (("ddim", gen_ddim), ("ddpm", gen_ddpm), ("prepost", gen_prepost), ("guidance", gen_guidance),
-                     ("pipeline", gen_pipeline), ("postproc", gen_postproc)):
+                     ("pipeline", gen_pipeline), ("postproc", gen_postproc), ("frontend", gen_frontend)):
         store = {}
         with torch.no_grad():
             fn(store)

@@ -1,0 +1,95 @@
+"""Camera-frame front end on the GPU (d3_frame_to_input / d3_depth_to_input, d3roma_b200.inference.D3RoMa) against the
+cv2-generated golden vectors and the oracle's restatement of inference.py:97-250.  Integer / byte work: bit-exact."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden" / "frontend.npz"
+CASES = ["down", "up", "same", "odd", "gray"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_frame_and_depth_kernels_bit_exact_vs_cv2_golden(name):
+    import d3roma_b200 as d
+    from d3roma_b200 import inference as I
+    from oracle import frontend_ref as F
+    g = np.load(GOLD)
+    h, w = (int(v) for v in g[f"{name}/size"])
+    padder = d.InputPadder((1, 1, h, w), divis_by=32)
+    normer = d.Normalizer(ssi=False, mode="average", num_chs=1, ch_bounds=[128.], ch_gammas=[1.], t=0.5, s=2.0)
+    img = torch.from_numpy(g[f"{name}/img"])
+    x = I.frames_to_input(torch.stack([img, img.flip(0)]), (h, w), padder, "cuda")      # batch of two frames
+    want = F.pad_replicate(torch.from_numpy(g[f"{name}/normalized"]), 32)
+    assert x.shape == (2, 3) + tuple(want.shape[-2:])
+    assert torch.equal(x[0].cpu(), want)
+    want1 = F.pad_replicate(F.preprocess_image(g[f"{name}/img"][::-1].copy(), (h, w)), 32) if True else None
+    assert torch.equal(x[1].cpu(), want1)
+    raw, mask, norm = I.depth_to_input(g[f"{name}/depth"], (h, w), padder, 24.547, normer, "cuda")
+    assert torch.equal(raw[0].cpu(), torch.from_numpy(g[f"{name}/raw_disp"]))
+    assert torch.equal(mask[0].cpu(), torch.from_numpy((g[f"{name}/raw_disp"] > 0).astype(np.float32)))
+    assert torch.equal(norm[0].cpu(), F.pad_replicate(torch.from_numpy(g[f"{name}/norm_disp"]), 32))
+
+
+def test_full_size_frames_match_cv2_directly():
+    """848x480 RealSense-sized frames -> 640x360: bit-exact against cv2 run here (skipped without OpenCV)."""
+    cv2 = pytest.importorskip("cv2")
+    import d3roma_b200 as d
+    from d3roma_b200 import inference as I
+    from oracle import frontend_ref as F
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, (480, 848, 3), dtype=np.uint8)
+    depth = (rng.random((480, 848)) * 2).astype(np.float32)
+    padder = d.InputPadder((1, 1, 360, 640), divis_by=32)
+    normer = d.Normalizer(ssi=False, mode="average", num_chs=1, ch_bounds=[128.], ch_gammas=[1.], t=0.5, s=2.0)
+    x = I.frames_to_input(img, (360, 640), padder, "cuda")
+    assert torch.equal(x[0].cpu(), F.pad_replicate(F.preprocess_image(img, (360, 640)), 32))
+    raw, mask, norm = I.depth_to_input(depth, (360, 640), padder, 24.547, normer, "cuda")
+    r_raw, r_mask, r_norm = F.preprocess_depth(depth, (360, 640), 24.547)
+    assert torch.equal(raw[0].cpu(), r_raw) and torch.equal(mask[0].cpu(), r_mask)
+    assert torch.equal(norm[0].cpu(), F.pad_replicate(r_norm, 32))
+
+
+def test_d3roma_infer_matches_reference_flow():
+    """D3RoMa.infer (inference.py:137-250): numpy frames in, depth in metres out; equals the reference flow assembled
+    from the oracle's preprocessing + the same pipeline + torch post-processing."""
+    pytest.importorskip("cv2")
+    import d3roma_b200 as d
+    from d3roma_b200 import evaluate
+    from d3roma_b200.inference import D3RoMa
+    from d3roma_b200.weights import random_init_state_dict
+    from oracle import frontend_ref as F
+    h, w = 60, 90
+    net = d.UNet2DModel(sample_size=(64, 96), in_channels=8, out_channels=1, compute_dtype="fp16").to("cuda")
+    net.load_state_dict(random_init_state_dict(8, 1, seed=0))
+    sched = d.MyDDIMScheduler.from_config(dict(beta_schedule="squaredcos_cap_v2", num_train_timesteps=128,
+                                               prediction_type="sample", clip_sample=True, set_alpha_to_one=False,
+                                               steps_offset=1))
+    pipe = d.GuidedDiffusionPipeline(net, sched, d.FlowGuidance(flow_guidance_weight=0.0))
+    cfg = evaluate.default_config(num_inference_timesteps=2, num_inference_rounds=2, camera_resolution=f"{w}x{h}")
+    cam = d.SIM_CAMERA
+    rng = np.random.default_rng(3)
+    left = rng.integers(0, 256, (120, 180), dtype=np.uint8)            # gray IR frames, 2x the working resolution
+    right = rng.integers(0, 256, (120, 180), dtype=np.uint8)
+    rgb = rng.integers(0, 256, (120, 180, 3), dtype=np.uint8)
+    depth = (rng.random((120, 180)) * 1.5 + 0.3).astype(np.float32)
+    depth[rng.random((120, 180)) < 0.2] = 0
+    eng = D3RoMa(pipe, cam, cfg)
+    torch.manual_seed(11)
+    got = eng.infer(left, right, depth, rgb)
+    assert got.shape == (h, w) and got.dtype == np.float32 and np.isfinite(got).all()
+    assert set(eng.last_metrics) == {"disp", "depth"}
+    # reference flow
+    R = 2
+    pad = lambda t: F.pad_replicate(t, 32)[None].repeat(R, 1, 1, 1).cuda()   # noqa: E731
+    n_l, n_r, n_rgb = (pad(F.preprocess_image(a, (h, w))) for a in (left, right, rgb))
+    raw, mask, norm = F.preprocess_depth(depth, (h, w), cam.fxb)
+    torch.manual_seed(11)
+    out = pipe(n_rgb, n_l, n_r, pad(norm), None, None, num_inference_steps=2, num_intermediate_images=1,
+               depth_channels=1, cond_channels="left+right+raw")
+    pred = out.images[:, :, 2:62, 3:93].cpu()
+    disp = ((pred / 2.0 + 0.5) * 128.0).mean(dim=0)[0]
+    want = torch.where(disp > 0, cam.fxb / disp, torch.zeros_like(disp)).numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
