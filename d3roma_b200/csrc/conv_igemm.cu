@@ -1404,13 +1404,12 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   // Cout == 128 layers run the pixels-as-N kernel (weights on the M side); see conv_igemm_t_kernel.
   static int no_t = -1;
   if (no_t < 0) { const char* e = getenv("D3_CONV_NO_T"); no_t = e ? atoi(e) : 0; }
-  const bool use_t = (p->Cout == 128) && !no_t;
   // halo-block variant: plain 3x3 stride-1 convs whose output is covered well by TH x TW = 256-pixel tiles with TW a
   // multiple of 8 (D3_CONV_VB: 0 = off, 1 = pick TW automatically, 8/16/32/64 = force that tile width)
   static int want_vb = -1;
   if (want_vb < 0) { const char* e = getenv("D3_CONV_VB"); want_vb = e ? atoi(e) : 1; }
   bool use_strips = false;
-  if (use_t && want_vb && p->ksize == 3 && p->stride == 1 && phase == 0) {
+  if (!no_t && p->Cout % 128 == 0 && want_vb && p->ksize == 3 && p->stride == 1 && phase == 0) {
     double best = 0.0;
     for (int tw = (want_vb == 8 ? 8 : 16); tw <= 64; tw *= 2) {
       if (want_vb > 1 && tw != want_vb) continue;
@@ -1421,6 +1420,17 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
       if ((eff >= 0.85 || want_vb > 1) && score > best) { best = score; a.TH = th; a.TW = tw; use_strips = true; }
     }
   }
+  // Wider layers run the pixels-as-N kernel too, as Cout / 128 channel tiles over the same pixel tile - but only in
+  // its halo-block form and with enough 256-pixel tiles to fill the SMs: measured +5..17 % over the pixels-as-M kernel
+  // on the 256-channel 3x3 layers (76 vs 96 KB of shared-memory traffic per K-block), while per-tap pixels-as-N tiles
+  // are up to 2x SLOWER on the 1x1 / small / stride-2 layers (profiles/r01_conv_experiments.txt).
+  // D3_CONV_T_MAXC caps the channel count (128 restores the old routing).
+  static int t_maxc = -1;
+  if (t_maxc < 0) { const char* e = getenv("D3_CONV_T_MAXC"); t_maxc = e ? atoi(e) : 4096; }
+  const long long t_tiles = ((long long)p->B * Ho * Wo + 255) / 256 * (p->Cout / 128);
+  const bool use_t = (p->Cout % 128 == 0) && !no_t &&
+                     (p->Cout == 128 || (use_strips && p->Cout <= t_maxc && t_tiles >= num_sms()));
+  if (!use_t) use_strips = false;
   if (use_strips) {
     a.blk_slot = (a.TH + 2) * a.TW * 128;
     // ring depths: 32 KB staging + barriers leave ~193 KB
@@ -1444,6 +1454,7 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   const int pixTiles = p->B * a.tilesH * a.tilesW;
   int BN = (p->Cout % 256 == 0) ? 256 : 128;
   if (BN == 256 && pixTiles * (p->Cout / 256) < num_sms()) BN = 128;  // more CTAs for tiny layers
+  if (use_t) BN = 128;  // pixels-as-N: the weight (M) tile is always 128 output channels
   a.nTilesN = p->Cout / BN;
   a.numTiles = pixTiles * a.nTilesN;
   a.ksize = p->ksize;
