@@ -151,7 +151,7 @@ def run_reference_arm(args):
         "note": "reference = jie0530/d3roma core/custom_pipelines.py loop restated in oracle/ (diffusers.UNet2DModel "
                 "is an un-vendored third-party dependency, so the CPU path is the oracle port, torch CPU fp32)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus: int):
@@ -336,12 +336,27 @@ def run_gpu_arm(args):
             line["cpu_baseline"] = {"value": maps_cpu, "unit": "maps/s", "cores": threads, "kind": "port",
                                     "sample": "oracle port of the reference loop: 1 pair 384x640, 3 timed single "
                                               "DDIM steps (UNet forward + scheduler), fp32, scaled x10 to maps/s"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's original stdout; see main()."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 def main():
+    # Libraries write banners to file descriptor 1 (e.g. "NCCL version ..." at communicator creation).  Keep a private
+    # handle on the real stdout for the JSON line and point fd 1 at stderr for everything else.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
