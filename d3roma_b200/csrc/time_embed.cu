@@ -36,10 +36,22 @@ __global__ void __launch_bounds__(512) time_embed_kernel(const float* __restrict
   }
   __syncthreads();
   {
-    float acc = b2[threadIdx.x];
+    // second layer: this block produces outputs [32*blockIdx.y, +32); 16 K-slices of 32 per output, combined in smem
+    // (one block per timestep reading the whole 1 MB of w2 through a single SM took 51 us)
+    __shared__ float s_part[16][33];
+    const int ol = threadIdx.x & 31, ks = threadIdx.x >> 5;
+    const int o = blockIdx.y * 32 + ol;
+    float acc = 0.f;
 #pragma unroll 8
-    for (int k = 0; k < 512; ++k) acc = fmaf(w2[(size_t)k * 512 + threadIdx.x], s_h[k], acc);
-    out[(size_t)n * 512 + threadIdx.x] = acc / (1.0f + expf(-acc));  // SiLU(emb): what every consumer applies first
+    for (int k = ks * 32; k < ks * 32 + 32; ++k) acc = fmaf(w2[(size_t)k * 512 + o], s_h[k], acc);
+    s_part[ks][ol] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = b2[o];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v += s_part[i][ol];
+      out[(size_t)n * 512 + o] = v / (1.0f + expf(-v));  // SiLU(emb): what every consumer applies first
+    }
   }
 }
 
@@ -78,7 +90,7 @@ extern "C" int d3_time_embed(const float* t, int nt, const float* w1, const floa
                              const float* b2, float* silu_emb_out, void* stream) {
   using namespace d3;
   D3_REQUIRE(t && w1 && b1 && w2 && b2 && silu_emb_out && nt > 0, "time_embed: bad arguments");
-  time_embed_kernel<<<nt, 512, 0, static_cast<cudaStream_t>(stream)>>>(t, w1, b1, w2, b2, silu_emb_out);
+  time_embed_kernel<<<dim3(nt, 16), 512, 0, static_cast<cudaStream_t>(stream)>>>(t, w1, b1, w2, b2, silu_emb_out);
   D3_LAUNCH_CHECK();
   return D3_OK;
 }
