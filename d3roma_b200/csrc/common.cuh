@@ -235,6 +235,22 @@ D3_DEVINL void umma_commit_2cta_mc(uint64_t* bar, uint16_t mask) {
                "h"(mask)
                : "memory");
 }
+// Multicast variants for plain (cta_group::1) kernels running as 2-CTA clusters: the TMA box lands at the same
+// shared-memory offset in every CTA of `mask` and completes bytes on the mbarrier at the same offset there; the commit
+// arrives on the mbarrier at the same offset in every CTA of `mask`.
+D3_DEVINL void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+D3_DEVINL void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                   "r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
 // TMA loads whose completion is signalled on the LEADER CTA's mbarrier (peer bit of the address cleared)
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
 D3_DEVINL void tma_load_2d_2cta(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {

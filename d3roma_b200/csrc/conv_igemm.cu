@@ -35,6 +35,7 @@ struct ConvKArgs {
   int B, Ho, Wo, Cout;
   int TH, TW, tilesH, tilesW, nTilesN, numTiles;
   int numPairs;  // cta_group::2 kernel: pairs of pixel tiles x nTilesN
+  int numUnits, pixTiles;  // weight-multicast clusters: work units = pairs of pixel tiles x nTilesN
   int ksize, stride, pad;
   int ntaps;
   signed char tap_dh[9], tap_dw[9];  // input offset of each filter tap (stride-1 path)
@@ -79,6 +80,35 @@ D3_DEVINL TileCoord decode_tile(const ConvKArgs& a, int tile, int BN) {
   t.w0 = tw * a.TW;
   t.n0 = nt * BN;
   return t;
+}
+
+// Work decode of the pixels-as-N kernel.  MC (2-CTA weight-multicast clusters): unit = (pair of pixel tiles, channel
+// tile); CTA `rank` of the cluster takes pixel tile 2*pair + rank; an odd tile count leaves one CTA with a dummy tile
+// (valid = false: it still consumes the multicast weights, loads zeros and stores nothing).
+template <bool MC>
+D3_DEVINL TileCoord decode_work(const ConvKArgs& a, int idx, uint32_t rank, bool& valid) {
+  if constexpr (!MC) {
+    valid = true;
+    return decode_tile(a, idx, 128);
+  } else {
+    TileCoord t;
+    const int nt = idx % a.nTilesN;
+    int p = 2 * (idx / a.nTilesN) + (int)rank;
+    valid = p < a.pixTiles;
+    t.n0 = nt * 128;
+    if (!valid) {
+      t.b = a.B;  // out of range in the batch dimension: TMA loads return zeros, TMA stores are dropped
+      t.h0 = 0;
+      t.w0 = 0;
+      return t;
+    }
+    const int tw = p % a.tilesW;
+    p /= a.tilesW;
+    t.h0 = (p % a.tilesH) * a.TH;
+    t.b = p / a.tilesH;
+    t.w0 = tw * a.TW;
+    return t;
+  }
 }
 
 // Butterfly transpose-reduce: on entry every lane holds 32 partial values v[0..31]; on exit lane l holds
@@ -509,7 +539,7 @@ constexpr int kMaxWts = 8;    // weight-tile ring slots (halo-block variant)
 // in the MMA itself (profiles/r01_conv_experiments.txt).  Activation TMA traffic drops by 3*TH/(TH+2).  Weights stream
 // through their own ring, fed by a second producer lane (warp 3).
 // K-loop order: for cb: for kw: block(kw, cb) -> for kh: weight tile (kh, kw, cb) -> 4 MMAs.
-template <int STAGES, int DT, bool STRIPS>
+template <int STAGES, int DT, bool STRIPS, bool MC = false>
 __global__ void __launch_bounds__(kTThreads, 1)
 conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS1,
                     const __grid_constant__ CUtensorMap tmS2, const __grid_constant__ CUtensorMap tmB,
@@ -547,7 +577,9 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NBAR; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      // MC: a weight slot is free again only when BOTH CTAs of the cluster have consumed it (each producer multicasts
+      // its half of the tile into both CTAs)
+      mbar_init(&empty_bar[i], (MC && STRIPS && i >= kMaxBlk) ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -562,8 +594,13 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
+  const int w_first = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // work index of this CTA / cluster
+  const int w_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int w_count = MC ? a.numUnits : a.numTiles;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -573,8 +610,9 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t blk_bytes = (uint32_t)(a.TH + 2) * a.TW * 128u;
       const uint32_t plain_bytes = (uint32_t)a.TH * a.TW * 128u;
       const int n_items = 3 * a.cbMain + a.kbSc1 + a.kbSc2;  // block loads per tile
-      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(a, tile, 128);
+      for (int tile = w_first; tile < w_count; tile += w_step) {
+        bool valid;
+        const TileCoord t = decode_work<MC>(a, tile, crank, valid);
         for (int it = 0; it < n_items; ++it) {
           mbar_wait(&sempty[ss], sphase ^ 1);
           uint8_t* sS = smem + ss * a.blk_slot;
@@ -649,7 +687,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n_items = 3 * a.cbMain + a.kbSc1 + a.kbSc2;
       const bool prof = (a.debug_skip & 256) != 0;
       long long p_t0 = prof ? clock64() : 0, p_acc = 0, p_blk = 0, p_wts = 0, p_c = 0;
-      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+      for (int tile = w_first; tile < w_count; tile += w_step) {
         if (prof) p_c = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         if (prof) p_acc += clock64() - p_c;
@@ -676,7 +714,8 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
             }
             first = 0;
-            umma_commit(&wempty[ws]);
+            if constexpr (MC) umma_commit_mc(&wempty[ws], 3);   // frees the slot in both CTAs' weight producers
+            else umma_commit(&wempty[ws]);
             if (++ws == a.n_wts) { ws = 0; wphase ^= 1; }
           }
           umma_commit(&sempty[ss]);
@@ -729,8 +768,9 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int ws = 0;
       uint32_t wphase = 0;
       const int n_items = 3 * a.cbMain + a.kbSc1 + a.kbSc2;
-      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(a, tile, 128);
+      for (int tile = w_first; tile < w_count; tile += w_step) {
+        bool valid;
+        const TileCoord t = decode_work<MC>(a, tile, crank, valid);
         for (int it = 0; it < n_items; ++it) {
           int nkb = 1, kb0 = a.kbMain + (it - 3 * a.cbMain);
           if (it < 3 * a.cbMain) {
@@ -743,8 +783,12 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (a.debug_skip & 2) {
               mbar_arrive(&wfull[ws]);
             } else {
-              mbar_arrive_expect_tx(&wfull[ws], kWTileBytes);
-              tma_load_2d(wring + ws * kWTileBytes, &tmB, &wfull[ws], (kb0 + i * 3 * a.cbMain) * 64, t.n0);
+              mbar_arrive_expect_tx(&wfull[ws], kWTileBytes);   // own half + the peer's half
+              if constexpr (MC)
+                tma_load_2d_mc(wring + ws * kWTileBytes + crank * (kWTileBytes / 2), &tmB, &wfull[ws],
+                               (kb0 + i * 3 * a.cbMain) * 64, t.n0 + (int)crank * 64, 3);   // tmB box = 64 rows
+              else
+                tma_load_2d(wring + ws * kWTileBytes, &tmB, &wfull[ws], (kb0 + i * 3 * a.cbMain) * 64, t.n0);
             }
             if (++ws == a.n_wts) { ws = 0; wphase ^= 1; }
           }
@@ -783,9 +827,10 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool prof = (a.debug_skip & 256) != 0 && et == 0;
     long long p_t0 = prof ? clock64() : 0, p_wait = 0, p_pass = 0, p_c = 0, p_tiles = 0;
     long long p_q[4] = {0, 0, 0, 0};
-    for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(a, tile, 128);
-      const float bias = a.bias[(size_t)t.b * a.bias_bstride + t.n0 + ch];
+    for (int tile = w_first; tile < w_count; tile += w_step) {
+      bool valid;
+      const TileCoord t = decode_work<MC>(a, tile, crank, valid);
+      const float bias = valid ? a.bias[(size_t)t.b * a.bias_bstride + t.n0 + ch] : 0.f;
       float s_sum = 0.f, s_sq = 0.f;
       if (prof) p_c = clock64();
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -881,7 +926,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int prow = (PH > 1) ? pc / PW : 0;
           const int pcol = pc - prow * PW;
           const uint32_t vmask = __ballot_sync(
-              0xffffffffu, (pc < PN) && (h + prow < a.Ho) && (wpass + pcol < a.Wo));
+              0xffffffffu, valid && (pc < PN) && (h + prow < a.Ho) && (wpass + pcol < a.Wo));
           // word address of this lane's channel pair; odd lanes write 4 pixel rows further down (see epi_t_chunk2)
           const uint32_t sa = smem_u32(sbuf) + half * (kStagingBytes / 2) + (uint32_t)c0 * 128u + (chb & ~3u) +
                               (odd ? 512u : 0u);
@@ -930,7 +975,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       if (prof) p_pass += clock64() - p_c;
-      if (a.stats != nullptr) {
+      if (a.stats != nullptr && valid) {
         // quad = 4 consecutive channels = 4 consecutive lanes
         s_sum += __shfl_xor_sync(0xffffffffu, s_sum, 1);
         s_sq += __shfl_xor_sync(0xffffffffu, s_sq, 1);
@@ -957,6 +1002,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();   // no CTA leaves while its peer can still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -975,7 +1021,31 @@ inline size_t conv_ts_smem_bytes(const ConvKArgs& a) {
 template <int STAGES, int DT>
 cudaError_t launch_conv_t(int grid, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmS1,
                           const CUtensorMap& tmS2, const CUtensorMap& tmB, const CUtensorMap& tmO,
-                          const CUtensorMap& tmR, const ConvKArgs& a, bool strips) {
+                          const CUtensorMap& tmR, const ConvKArgs& a, bool strips, bool mc) {
+  if (strips && mc) {
+    // 2-CTA clusters sharing every weight tile through TMA multicast; grid = 2 x clusters
+    const size_t smem = conv_ts_smem_bytes(a);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+      cudaError_t e = cudaFuncSetAttribute(conv_igemm_t_kernel<STAGES, DT, true, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr_smem = smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kTThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, conv_igemm_t_kernel<STAGES, DT, true, true>, tmA, tmS1, tmS2, tmB, tmO, tmR, a);
+  }
   if (strips) {
     const size_t smem = conv_ts_smem_bytes(a);
     static size_t attr_smem = 0;
@@ -1575,8 +1645,24 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
     }
   }
 
-  const int grid = a.numTiles < num_sms() ? a.numTiles : num_sms();
+  int grid = a.numTiles < num_sms() ? a.numTiles : num_sms();
   cudaError_t le = cudaSuccess;
+  // weight multicast: 2-CTA clusters of the halo-block kernel share every weight tile (each CTA fetches half of it and
+  // multicasts) - halves the L2 -> SM weight traffic.  D3_CONV_MC=1 to enable.
+  static int want_mc = -1;
+  if (want_mc < 0) { const char* e = getenv("D3_CONV_MC"); want_mc = e ? atoi(e) : 0; }
+  const bool use_mc = use_strips && want_mc && !a.t_direct && pixTiles >= 4;
+  if (use_mc) {
+    a.pixTiles = pixTiles;
+    a.numUnits = ((pixTiles + 1) / 2) * a.nTilesN;
+    const int max_clusters = num_sms() / 2;
+    grid = 2 * (a.numUnits < max_clusters ? a.numUnits : max_clusters);
+    uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)p->Cout};
+    uint64_t str[1] = {(uint64_t)Ktot * 2};
+    uint32_t box[2] = {64, 64};
+    if ((rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmB, p->w, 2, dims, str, box)))
+      return set_error(D3_ERR_CUDA, "conv: tensor map B(multicast half) encode failed (%d)", rc);
+  }
   static int use_2cta = -1;
   if (use_2cta < 0) { const char* e = getenv("D3_CONV_2CTA"); use_2cta = e ? atoi(e) : 0; }
   a.numPairs = ((pixTiles + 1) / 2) * a.nTilesN;
@@ -1598,9 +1684,9 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
     else
       le = launch_conv2<256, 5, kF16>(npg, stream, tmA, tmS1, tmS2, tmB, tmO, a);
   } else if (use_t && p->dtype == D3_DTYPE_BF16)
-    le = launch_conv_t<4, kBF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, tmR, a, use_strips);
+    le = launch_conv_t<4, kBF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, tmR, a, use_strips, use_mc);
   else if (use_t)
-    le = launch_conv_t<4, kF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, tmR, a, use_strips);
+    le = launch_conv_t<4, kF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, tmR, a, use_strips, use_mc);
   else if (BN == 128 && p->dtype == D3_DTYPE_BF16)
     le = launch_conv<128, 5, kBF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, a);
   else if (BN == 128)

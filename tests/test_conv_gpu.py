@@ -108,7 +108,7 @@ def test_kernel_variants_match():
     script = os.path.join(root, "tests", "_conv_variant_check.py")
     for env in ({"D3_CONV_VB": "0"}, {"D3_CONV_VB": "8"}, {"D3_CONV_VB": "16"}, {"D3_CONV_VB": "32"},
                 {"D3_CONV_VB": "64"}, {"D3_CONV_VB": "64", "D3_CONV_VB_NBLK": "3"}, {"D3_CONV_2CTA": "1"},
-                {"D3_CONV_T_DIRECT": "1"}, {"D3_CONV_NO_T": "1"}, {"D3_CONV_T_MAXC": "128"}):
+                {"D3_CONV_T_DIRECT": "1"}, {"D3_CONV_NO_T": "1"}, {"D3_CONV_T_MAXC": "128"}, {"D3_CONV_MC": "1"}):
         e = dict(os.environ, **env)
         r = subprocess.run([sys.executable, script], cwd=root, env=e, capture_output=True, text=True, timeout=300)
         assert "VARIANT_OK" in r.stdout, (env, r.stdout[-800:], r.stderr[-800:])
