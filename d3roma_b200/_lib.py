@@ -104,6 +104,8 @@ def _declare(lib: C.CDLL) -> None:
         "d3_masked_minmax": (i32, [vp, vp, i32, i64, vp, vp]),
         "d3_normalize_ssi": (i32, [vp, vp, vp, i32, i64, f32, f32, vp, vp]),
         "d3_affine_rows": (i32, [vp, vp, i32, i64, vp, vp]),
+        "d3_ransac_workspace_bytes": (C.c_size_t, [i32, i64]),
+        "d3_ransac_iteration": (i32, [vp, vp, vp, vp, i32, i32, i64, f32, f32, vp, vp, vp, vp, vp]),
         "d3_frame_to_input": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
         "d3_depth_to_input": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32, f32, f32, f32, f32, vp, vp,
                                     vp, vp]),

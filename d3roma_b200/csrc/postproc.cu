@@ -116,6 +116,96 @@ __global__ void __launch_bounds__(kRedThreads) scale_shift_kernel(const float* _
   }
 }
 
+// ---- RANSAC scale/shift (utils_d3roma/ransac.py:51-96; Normalizer.denormalize with safe_ssi, utils.py:240-243) ----
+// one iteration = {fit on the N sampled pixels, inlier set of that model, refit on the inliers, global accuracy score,
+// per-row keep-if-better}; the random permutation comes from the caller (torch.randperm, as the reference draws it).
+__global__ void __launch_bounds__(kRedThreads) scale_shift_gather_kernel(const float* __restrict__ pred,
+                                                                         const float* __restrict__ target,
+                                                                         const float* __restrict__ mask,
+                                                                         const int* __restrict__ idx, int N, int64_t HW,
+                                                                         float* __restrict__ out) {
+  __shared__ double sd[32];
+  const int b = blockIdx.x;
+  const float* p = pred + (size_t)b * HW;
+  const float* t = target + (size_t)b * HW;
+  const float* m = mask + (size_t)b * HW;
+  double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0;
+  for (int i = threadIdx.x; i < N; i += kRedThreads) {
+    const int j = idx[i];
+    if (m[j] != 0.f) {
+      const double pv = p[j], tv = t[j];
+      a00 += pv * pv; a01 += pv; a11 += 1.0; b0 += pv * tv; b1 += tv;
+    }
+  }
+  a00 = block_reduce(a00, SumD(), sd); a01 = block_reduce(a01, SumD(), sd); a11 = block_reduce(a11, SumD(), sd);
+  b0 = block_reduce(b0, SumD(), sd); b1 = block_reduce(b1, SumD(), sd);
+  if (threadIdx.x == 0) {
+    double det = a00 * a11 - a01 * a01;
+    if (!(det > 0.0)) det += 1e-4;
+    out[2 * b] = (float)((a11 * b0 - a01 * b1) / det);
+    out[2 * b + 1] = (float)((-a01 * b0 + a00 * b1) / det);
+  }
+}
+
+// thr[b][i] = ((target - (pred * s + t))^2 < T) & mask ; n_inlier[b] = sum(thr)      (ransac.py:80-81, 86)
+__global__ void __launch_bounds__(kRedThreads) ransac_inliers_kernel(const float* __restrict__ pred,
+                                                                     const float* __restrict__ target,
+                                                                     const float* __restrict__ mask,
+                                                                     const float* __restrict__ model, float T, int64_t HW,
+                                                                     float* __restrict__ thr, float* __restrict__ n_inlier) {
+  __shared__ double sd[32];
+  const int b = blockIdx.x;
+  const float s = model[2 * b], t = model[2 * b + 1];
+  double cnt = 0.0;
+  for (int64_t i = threadIdx.x; i < HW; i += kRedThreads) {
+    const size_t o = (size_t)b * HW + i;
+    const float x_ = __fadd_rn(__fmul_rn(pred[o], s), t);
+    const float e = __fsub_rn(target[o], x_);
+    const bool in = (__fmul_rn(e, e) < T) && (mask[o] != 0.f);
+    thr[o] = in ? 1.0f : 0.f;
+    cnt += in ? 1.0 : 0.0;
+  }
+  cnt = block_reduce(cnt, SumD(), sd);
+  if (threadIdx.x == 0) n_inlier[b] = (float)cnt;
+}
+
+// count of elements (ALL rows, all pixels - the reference's mean has no dim) with max(Y/X'', X''/Y) < 1.25  (ransac.py:19-21)
+__global__ void __launch_bounds__(256) ransac_score_kernel(const float* __restrict__ pred,
+                                                           const float* __restrict__ target,
+                                                           const float* __restrict__ model, int rows, int64_t HW,
+                                                           unsigned long long* __restrict__ count) {
+  unsigned int local = 0;
+  const int64_t total = (int64_t)rows * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const float x = __fadd_rn(__fmul_rn(pred[i], model[2 * b]), model[2 * b + 1]);
+    const float y = target[i];
+    const float r0 = __fdiv_rn(y, x), r1 = __fdiv_rn(x, y);
+    // torch.maximum propagates NaN, and NaN < 1.25 is false
+    if (!(r0 != r0) && !(r1 != r1) && fmaxf(r0, r1) < 1.25f) ++local;
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, (unsigned long long)local);
+}
+
+// keep the refit where it has more than D inliers and a better (global) score   (ransac.py:87-92)
+__global__ void ransac_select_kernel(int rows, const float* __restrict__ n_inlier, float D,
+                                     const unsigned long long* __restrict__ count, double total,
+                                     const float* __restrict__ better, float* __restrict__ best_num,
+                                     float* __restrict__ best_err, float* __restrict__ best_fit) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= rows) return;
+  const float mean_acc = (float)((double)*count / total);
+  const float this_err = 1.0f / mean_acc;   // inf when nothing is within 1.25x
+  if (n_inlier[b] > D && this_err < best_err[b]) {
+    best_num[b] = n_inlier[b];
+    best_err[b] = this_err;
+    best_fit[2 * b] = better[2 * b];
+    best_fit[2 * b + 1] = better[2 * b + 1];
+  }
+}
+
 __global__ void __launch_bounds__(kRedThreads) masked_minmax_kernel(const float* __restrict__ x,
                                                                     const float* __restrict__ mask, int64_t HW,
                                                                     float* __restrict__ out) {
@@ -215,6 +305,37 @@ extern "C" int d3_affine_rows(const float* y, const float* scale_shift, int rows
   D3_REQUIRE(y && scale_shift && out && rows >= 0 && HW > 0, "affine_rows: bad arguments");
   if (rows == 0) return D3_OK;
   affine_rows_kernel<<<ew_blocks(rows * HW), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, scale_shift, rows, HW, out);
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
+extern "C" size_t d3_ransac_workspace_bytes(int rows, int64_t HW) {
+  // inlier mask [rows][HW] + maybe-model, refit, inlier counts [rows] x 5 floats + one 64-bit counter
+  return ((size_t)rows * HW + (size_t)rows * 5) * sizeof(float) + 16;
+}
+
+extern "C" int d3_ransac_iteration(const float* pred, const float* target, const float* mask, const int* perm, int n_sample,
+                                   int rows, int64_t HW, float T, float min_inliers, void* workspace, float* best_fit,
+                                   float* best_err, float* best_num, void* stream) {
+  D3_REQUIRE(pred && target && mask && perm && workspace && best_fit && best_err && best_num, "ransac: null pointer");
+  D3_REQUIRE(rows > 0 && HW > 0 && n_sample > 0 && n_sample <= HW, "ransac: bad sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long* count = static_cast<unsigned long long*>(workspace);
+  float* thr = reinterpret_cast<float*>(static_cast<char*>(workspace) + 16);
+  float* maybe = thr + (size_t)rows * HW;
+  float* better = maybe + 2 * rows;
+  float* n_in = better + 2 * rows;
+  D3_CHECK_CUDA(cudaMemsetAsync(count, 0, 16, st));
+  scale_shift_gather_kernel<<<rows, kRedThreads, 0, st>>>(pred, target, mask, perm, n_sample, HW, maybe);
+  D3_LAUNCH_CHECK();
+  ransac_inliers_kernel<<<rows, kRedThreads, 0, st>>>(pred, target, mask, maybe, T, HW, thr, n_in);
+  D3_LAUNCH_CHECK();
+  scale_shift_kernel<<<rows, kRedThreads, 0, st>>>(pred, target, thr, HW, better);
+  D3_LAUNCH_CHECK();
+  ransac_score_kernel<<<ew_blocks((int64_t)rows * HW), 256, 0, st>>>(pred, target, better, rows, HW, count);
+  D3_LAUNCH_CHECK();
+  ransac_select_kernel<<<(rows + 127) / 128, 128, 0, st>>>(rows, n_in, min_inliers, count, (double)rows * (double)HW,
+                                                          better, best_num, best_err, best_fit);
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

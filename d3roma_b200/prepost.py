@@ -6,8 +6,8 @@
   inference.py:128-131, 246-249
 
 Every tensor op runs in ``libd3roma_b200.so`` (one fused pass each).  ``ssi=True`` (DREDS / ClearPose configs) is
-supported with the direct least-squares alignment (``safe_ssi=False``); the RANSAC variant and the piecewise
-multi-channel mode are not implemented.
+supported with the direct least-squares alignment (``safe_ssi=False``) and the RANSAC variant (``safe_ssi=True``,
+``metrics.RANSAC``); the piecewise multi-channel mode is not implemented.
 """
 from __future__ import annotations
 
@@ -82,6 +82,7 @@ class Normalizer:
         self.t, self.s = t, s
         self.safe_ssi, self.ransac_error_threshold = safe_ssi, ransac_error_threshold
         self.low_p, self.high_p = 0.0, 1.0
+        self.perm_fn = None   # test hook: source of RANSAC permutations (default torch.randperm on the device)
 
     @staticmethod
     def from_config(config):
@@ -121,14 +122,16 @@ class Normalizer:
         if self.ssi:
             # utils.py:232-251: per (sample, round) least-squares scale/shift against the raw disparity
             assert raw_disp is not None and mask is not None
-            if self.safe_ssi:
-                raise NotImplementedError("safe_ssi (RANSAC, utils_d3roma/ransac.py) is not implemented; "
-                                          "use safe_ssi=False for the direct least-squares alignment")
             B, R, H, W = y.shape
             pred = y.reshape(B * R, H * W)
             gt = raw_disp.to(torch.float32).repeat(1, R, 1, 1).reshape(B * R, H * W)
             mk = mask.to(torch.float32).repeat(1, R, 1, 1).reshape(B * R, H * W)
-            st = ops.scale_shift_lsq(pred, gt, mk)
+            if self.safe_ssi:
+                from .metrics import RANSAC                       # utils.py:240-243
+                st = RANSAC(n=0.1, k=10, d=0.2, t=self.ransac_error_threshold, perm_fn=self.perm_fn).fit(
+                    pred, gt, mk).best_fit
+            else:
+                st = ops.scale_shift_lsq(pred, gt, mk)
             return ops.affine_rows(pred, st).view(B, R, H, W)
         return ops.denormalize_disp(y, self.num_chs, float(self.ch_bounds[0]), float(self.ch_gammas[0]),
                                     float(self.t), float(self.s))

@@ -233,6 +233,17 @@ int d3_normalize_ssi(const float* x, const float* mask, const float* low_up, int
                      float* out, void* stream);
 int d3_affine_rows(const float* y, const float* scale_shift, int rows, int64_t HW, float* out, void* stream);
 
+/* ---- one RANSAC iteration of the robust scale/shift fit (utils_d3roma/ransac.py:51-96, used by
+ * Normalizer.denormalize with ssi + safe_ssi, utils.py:240-243): fit on the n_sample pixels perm[0..n_sample) (the
+ * caller's random permutation of 0..HW-1, int32), inliers = ((target - (pred*s+t))^2 < T) & mask, refit on them, score
+ * 1 / mean(max(Y/X'', X''/Y) < 1.25) over ALL rows and pixels, and per row keep the refit when it has more than
+ * min_inliers inliers and a better score.  best_fit [rows][2] (initialise to {1, 0}), best_err [rows] (initialise to
+ * +inf), best_num [rows] (0) are updated in place; workspace: d3_ransac_workspace_bytes(rows, HW) bytes of scratch. */
+size_t d3_ransac_workspace_bytes(int rows, int64_t HW);
+int d3_ransac_iteration(const float* pred, const float* target, const float* mask, const int* perm, int n_sample, int rows,
+                        int64_t HW, float T, float min_inliers, void* workspace, float* best_fit, float* best_err,
+                        float* best_num, void* stream);
+
 /* ---- camera-frame front end (inference.py:99-213: cv2.resize + .float() + (x/255-0.5)*2 + batchify, padded as
  * InputPadder would).  frames: uint8 [B,Hs,Ws,Cimg] (Cimg 1 = gray tiled to 3, 3 = RGB, 4 = RGBA without alpha);
  * out: fp32 NCHW [B,3,Hp,Wp] where the H x W resized image sits at (pad_top, pad_left) and the border is replicated.

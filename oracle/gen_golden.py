@@ -347,11 +347,56 @@ def gen_frontend(store):
         store[f"{name}/norm_disp"] = _np(((torch.clamp(raw_disp, max=128.0) / 128.0) - 0.5) * 2.0)
 
 
+def gen_ransac(store):
+    """utils_d3roma/ransac.py RANSAC.fit run unmodified on the CPU with the permutations it drew recorded, plus the
+    safe_ssi branch of Normalizer.denormalize (utils.py:240-251)."""
+    import io
+    import contextlib
+    from utils_d3roma.ransac import RANSAC
+    g = torch.Generator().manual_seed(77)
+    B, H, W = 3, 24, 40
+    HW = H * W
+    gt = torch.rand(B, HW, generator=g) * 60 + 5
+    a = torch.tensor([[50.], [64.], [33.]])                 # true scale / shift per row: gt = a * pred + b
+    b = torch.tensor([[3.], [-2.], [1.]])
+    pred = (gt - b) / a + torch.randn(B, HW, generator=g) * 0.004
+    outl = torch.rand(B, HW, generator=g) < 0.02           # 2 % outliers
+    pred = torch.where(outl, pred + (torch.rand(B, HW, generator=g) - 0.5) * 0.2, pred)
+    mask = (torch.rand(B, HW, generator=g) > 0.2).float()
+    perms = []
+    real_randperm = torch.randperm
+
+    def rec(n, **kw):
+        p = real_randperm(n, **kw)
+        perms.append(p.clone())
+        return p
+    torch.manual_seed(5)
+    torch.randperm = rec
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            reg = RANSAC(n=0.1, k=10, d=0.2, t=0.6).fit(pred, gt, mask)
+            perms_fit = [p.clone() for p in perms]
+            perms.clear()
+            n = Normalizer(ssi=True, mode="average", num_chs=1, ch_bounds=[128.], ch_gammas=[1.], t=0.5, s=2.0,
+                           safe_ssi=True, ransac_error_threshold=0.6)
+            y = pred.view(B, 1, H, W)
+            den = n.denormalize(y, gt.view(B, 1, H, W), mask.view(B, 1, H, W))
+            perms_den = [p.clone() for p in perms]
+    finally:
+        torch.randperm = real_randperm
+    store["pred"], store["gt"], store["mask"] = _np(pred), _np(gt), _np(mask)
+    store["perms_fit"] = np.stack([_np(p) for p in perms_fit]).astype(np.int32)
+    store["best_fit"], store["best_error"] = _np(reg.best_fit), _np(reg.best_error)
+    store["best_num_inlier"] = _np(reg.best_num_inlier)
+    store["perms_den"] = np.stack([_np(p) for p in perms_den]).astype(np.int32)
+    store["den_out"] = _np(den)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
     for name, fn in (("ddim", gen_ddim), ("ddpm", gen_ddpm), ("prepost", gen_prepost), ("guidance", gen_guidance),
-                     ("pipeline", gen_pipeline), ("postproc", gen_postproc), ("frontend", gen_frontend)):
+                     ("pipeline", gen_pipeline), ("postproc", gen_postproc), ("frontend", gen_frontend), ("ransac", gen_ransac)):
         store = {}
         with torch.no_grad():
             fn(store)

@@ -32,3 +32,19 @@ def test_scale_shift_and_ssi_normalizer_match_reference():
     d = P.denormalize_ssi(torch.from_numpy(z["ssi/den_in"]), torch.from_numpy(z["ssi/den_raw"]),
                           torch.from_numpy(z["ssi/den_mask"]).float())
     np.testing.assert_array_equal(d.numpy(), z["ssi/den_out"])
+
+
+def test_ransac_oracle_matches_reference_run():
+    """oracle/ransac_ref.py fed with the permutations the reference drew reproduces the reference's RANSAC.fit
+    (utils_d3roma/ransac.py:51-96) on the golden problem."""
+    import numpy as np
+    import torch
+    from pathlib import Path
+    from oracle.ransac_ref import ransac_fit
+    g = np.load(Path(__file__).parent / "golden" / "ransac.npz")
+    fit, err, num = ransac_fit(torch.from_numpy(g["pred"]), torch.from_numpy(g["gt"]), torch.from_numpy(g["mask"]),
+                               g["perms_fit"], n=0.1, t=0.6, d=0.2)
+    np.testing.assert_allclose(fit.numpy(), g["best_fit"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(err.numpy(), g["best_error"], rtol=1e-6)
+    np.testing.assert_array_equal(num.numpy(), g["best_num_inlier"])
+    assert (g["best_num_inlier"] > 0).all()          # the problem is one where RANSAC does select models

@@ -53,6 +53,28 @@ def test_scale_shift_and_ssi_normalizer_vs_reference_golden():
     out = n.denormalize(torch.from_numpy(z["ssi/den_in"]).cuda(), torch.from_numpy(z["ssi/den_raw"]).cuda(),
                         torch.from_numpy(z["ssi/den_mask"]).float().cuda())
     np.testing.assert_allclose(out.cpu().numpy(), z["ssi/den_out"], rtol=3e-5, atol=3e-4)
-    with pytest.raises(NotImplementedError):
-        d.Normalizer(ssi=True, mode="average", num_chs=1, ch_bounds=[128.], ch_gammas=[1.]).denormalize(
-            torch.zeros(1, 1, 4, 4, device="cuda"), torch.ones(1, 1, 4, 4, device="cuda"), torch.ones(1, 1, 4, 4, device="cuda"))
+
+
+def test_ransac_and_safe_ssi_denormalize_match_reference_golden():
+    """metrics.RANSAC (d3_ransac_iteration) and Normalizer(ssi=True, safe_ssi=True).denormalize fed with the
+    permutations of the recorded reference run (tests/golden/ransac.npz, utils_d3roma/ransac.py + utils.py:240-251)."""
+    from pathlib import Path
+    import d3roma_b200 as d
+    from d3roma_b200.metrics import RANSAC
+    g = np.load(Path(__file__).parent / "golden" / "ransac.npz")
+    X, Y, Mk = (torch.from_numpy(g[k]).cuda() for k in ("pred", "gt", "mask"))
+    perms = iter(g["perms_fit"])
+    reg = RANSAC(n=0.1, k=10, d=0.2, t=0.6, perm_fn=lambda hw, dev: torch.from_numpy(next(perms))).fit(X, Y, Mk)
+    np.testing.assert_allclose(reg.best_fit.cpu().numpy(), g["best_fit"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(reg.best_error.cpu().numpy(), g["best_error"], rtol=1e-6)
+    np.testing.assert_array_equal(reg.best_num_inlier.cpu().numpy(), g["best_num_inlier"])
+    n = d.Normalizer(ssi=True, mode="average", num_chs=1, ch_bounds=[128.], ch_gammas=[1.], t=0.5, s=2.0, safe_ssi=True,
+                     ransac_error_threshold=0.6)
+    perms2 = iter(g["perms_den"])
+    n.perm_fn = lambda hw, dev: torch.from_numpy(next(perms2))
+    B, _, H, W = g["den_out"].shape
+    out = n.denormalize(X.view(B, 1, H, W), Y.view(B, 1, H, W), Mk.view(B, 1, H, W))
+    np.testing.assert_allclose(out.cpu().numpy(), g["den_out"], rtol=1e-4, atol=1e-3)
+    # default permutation source: runs and returns a sane fit
+    reg2 = RANSAC(n=0.1, k=10, d=0.2, t=0.6).fit(X, Y, Mk)
+    assert torch.isfinite(reg2.best_fit).all() and (reg2.best_num_inlier > 0).all()
