@@ -208,3 +208,30 @@ def test_eval_batch_contract_and_metrics():
     mdict, rows = distributed.run_distributed_eval(evaluate.default_config(num_inference_timesteps=2), pipe, 3, 2,
                                                    make_batch_fn=lambda idx: synthetic.make_batch(idx, h=60, w=90))
     assert rows.shape == (3, 11) and set(mdict) == {"disp", "depth"} and np.isfinite(rows).all()
+
+
+def test_eval_batch_sceneflow_variant_three_depth_channels():
+    """conf/task/train_sceneflow.yaml: depth_channels = 3 with the 3-channel "average" normaliser (Cin = 12: sample 3 +
+    left 3 + right 3 + raw 3), DDPM sampler, SceneFlow min/max mask + clip branch of eval_batch (evaluate.py:126-130)."""
+    import d3roma_b200 as d
+    from d3roma_b200 import evaluate, synthetic
+    from d3roma_b200.weights import random_init_state_dict
+    net = d.UNet2DModel(sample_size=(64, 96), in_channels=12, out_channels=3, compute_dtype="fp16").to("cuda")
+    net.load_state_dict(random_init_state_dict(12, 3, seed=0))
+    pipe = d.GuidedDiffusionPipeline(net, d.MyDDPMScheduler.from_config(DDPM_CFG), d.FlowGuidance(flow_guidance_weight=0.0))
+    cfg = evaluate.default_config(num_inference_timesteps=2, depth_channels=3, num_chs=3, eval_dataset=["SceneFlow"],
+                                  camera_resolution="960x540")
+    batch = synthetic.make_batch([0, 1], h=60, w=90)
+    normer = d.Normalizer.from_config(cfg)
+    sim = torch.stack([normer.normalize(batch["sim_disp_unnorm"][i].cuda())[0] for i in range(2)])   # [B, 3, h, w]
+    assert sim.shape == (2, 3, 60, 90)
+    pred, (md, mz), unc, err, out = evaluate.eval_batch(
+        cfg, pipe, True, fxb=batch["fxb"], normalized_rgb=batch["normalized_rgb"], raw_disp=batch["raw_disp"],
+        mask=batch["mask"], left_image=batch["left_image"], right_image=batch["right_image"], sim_disp=sim,
+        raw_depth=batch["raw_depth"], generator=[torch.Generator().manual_seed(i) for i in range(2)])
+    assert out.images.shape == (2, 3, 60, 90) and pred.shape == (2, 60, 90) and unc is None
+    # denormalise (mean of the three replicas) + SceneFlow clip, restated in torch
+    want = ((out.images.cpu() / 2.0 + 0.5) * (128.0 / 3)).sum(dim=1)
+    want = want.clamp(0.5, 192.0)                       # scale = 960 / 960
+    np.testing.assert_allclose(pred, want.numpy(), rtol=1e-5, atol=1e-4)
+    assert np.isfinite(md).all() and np.isfinite(mz).all()
