@@ -235,3 +235,44 @@ def test_eval_batch_sceneflow_variant_three_depth_channels():
     want = want.clamp(0.5, 192.0)                       # scale = 960 / 960
     np.testing.assert_allclose(pred, want.numpy(), rtol=1e-5, atol=1e-4)
     assert np.isfinite(md).all() and np.isfinite(mz).all()
+
+
+def test_full_size_c1_ddim10_epe_delta_vs_oracle():
+    """BASELINE configs[0] at its real shape: 1 pair 360x640 (UNet at 384x640), left+right+raw, DDIM 10 steps, random-init
+    weights - the whole loop on the GPU (fp16 and bf16 operands) against the oracle loop on the host cores with the same
+    start noise.  North-star criteria: final-disparity EPE delta <= 0.05 px (both modes), and the final normalised
+    image within the per-step tolerance of the mode."""
+    import d3roma_b200 as d
+    from d3roma_b200 import synthetic
+    from oracle import pipeline_ref as P
+    from oracle.unet_ref import make_unet
+    torch.set_num_threads(16)
+    h, w = 360, 640
+    batch = synthetic.make_batch([0], h=h, w=w)
+    ref = make_unet(8, 1, seed=0, sample_size=(384, 640))
+    padder_pads = (12, 12)   # 360 -> 384 rows, centred
+    pad = lambda t: torch.nn.functional.pad(t, (0, 0, 12, 12), mode="replicate")   # noqa: E731
+    conds = {"left": pad(batch["left_image"]), "right": pad(batch["right_image"]), "raw": pad(batch["sim_disp"])}
+    x_T = torch.randn((1, 1, 384, 640), generator=torch.Generator().manual_seed(2024))
+    img_ref = P.run_pipeline(ref, x_T, conds, "left+right+raw", sampler="ddim", num_inference_steps=10)
+    disp_ref = ((img_ref[:, :, 12:-12] / 2.0 + 0.5) * 128.0)[0, 0]
+    gt = batch["raw_disp"][0, 0]
+    epe_ref = (disp_ref - gt).abs().mean().item()
+    for dtype, tol_img in (("fp16", 1e-2), ("bf16", 3e-2)):
+        net = d.UNet2DModel(sample_size=(384, 640), in_channels=8, out_channels=1, compute_dtype=dtype).to("cuda")
+        net.load_state_dict(ref.state_dict())
+        pipe = d.GuidedDiffusionPipeline(net, d.MyDDIMScheduler.from_config(DDIM_CFG),
+                                         d.FlowGuidance(flow_guidance_weight=0.0))
+        out = pipe(None, conds["left"], conds["right"], conds["raw"], None, None, num_inference_steps=10,
+                   num_intermediate_images=1, depth_channels=1, cond_channels="left+right+raw",
+                   generator=torch.Generator().manual_seed(2024))
+        img = out.images.cpu()
+        disp = ((img[:, :, 12:-12] / 2.0 + 0.5) * 128.0)[0, 0]
+        epe = (disp - gt).abs().mean().item()
+        err_img = (img - img_ref).abs().max().item()
+        mean_px = (disp - disp_ref).abs().mean().item()
+        print(f"{dtype}: final image max-abs {err_img:.3e}, mean |disp - disp_oracle| {mean_px:.4f} px, "
+              f"EPE {epe:.4f} vs oracle {epe_ref:.4f} (delta {abs(epe - epe_ref):.5f} px)")
+        assert abs(epe - epe_ref) <= 0.05
+        assert err_img <= tol_img
+        del net, pipe
