@@ -11,6 +11,8 @@
 // to two sources and writes ONE dense normalised tensor, i.e. the torch.cat of the up-blocks costs nothing extra.
 //
 // Algorithmic bytes: 2 * N * sizeof(bf16) per layer (one read, one write).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -18,6 +20,7 @@ namespace d3 {
 namespace {
 
 constexpr int kGnThreads = 256;
+
 constexpr int kMaxC = 1024;  // nvec = C/8 <= 128 threads per pixel
 
 struct GnArgs {
@@ -42,7 +45,7 @@ struct GnArgs {
   int pout2, groups2, silu2;
 };
 
-template <int DT, bool DUAL = false>
+template <int DT, bool DUAL = false, int U = 8>
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
   // blockDim.x = nvec * k (nvec = C/8 16-byte vectors per pixel): every thread owns ONE channel vector for the whole
   // block, so its 8 scale/shift pairs live in registers and the inner loop is load - 8 FMA - 8 SiLU - store.
@@ -121,7 +124,6 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
   uint16_t* dst = a.out + base_pix * a.pout + vec * 8;
   uint16_t* dst2 = DUAL ? a.out2 + base_pix * a.pout2 + vec * 8 : nullptr;
 
-  constexpr int U = 4;
   for (int p0 = prow; p0 < npix; p0 += pstride * U) {
     uint4 v[U];
 #pragma unroll
@@ -209,8 +211,13 @@ namespace d3 {
 namespace {
 int launch_gn(GnArgs& a, int B, int dtype, bool dual, cudaStream_t stream) {
   const int C = a.C1 + a.C2;
-  // aim for ~8 blocks per SM over the whole batch, but at least 32 KB of work per block
-  int blocks_per_sample = ceil_div(num_sms() * 8, B);
+  // at least 32 KB of work per block
+  // ~8 blocks per SM over the whole batch, 8 independent 16-byte loads per thread in flight.  (Alone, the pass is
+  // faster with 64 blocks per SM - 6.4 vs 5.8 TB/s - but inside the power-capped UNet forward, between two convs, 8 is
+  // the better setting: 6.19 vs 6.48 ms of GroupNorm per forward.  D3_GN_BPS overrides.)
+  static int bps = -1;
+  if (bps < 0) { const char* e = getenv("D3_GN_BPS"); bps = e ? atoi(e) : 8; }
+  int blocks_per_sample = ceil_div(num_sms() * bps, B);
   int ppb = ceil_div(a.HW, blocks_per_sample);
   const int min_ppb = ceil_div(16384, C);
   if (ppb < min_ppb) ppb = min_ppb;
