@@ -39,6 +39,7 @@ class ConvParams(C.Structure):
         ("stats", C.c_void_p),
         ("dtype", C.c_int32),
         ("up2x_phase", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -76,6 +77,7 @@ def _declare(lib: C.CDLL) -> None:
         "d3_launch_count": (i64, []),
         "d3_reset_launch_count": (None, []),
         "d3_conv2d_igemm": (i32, [C.POINTER(ConvParams), vp]),
+        "d3_conv2d_workspace_bytes": (C.c_size_t, [C.POINTER(ConvParams)]),
         "d3_groupnorm_silu": (i32, [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, f32, i32, vp, i32, i32,
                                     vp]),
         "d3_groupnorm_silu_dual": (i32, [vp, i32, i32, vp, i32, i32, f32, vp, vp, i32, i32, vp, i32, vp, vp, i32, i32,

@@ -36,6 +36,8 @@ struct ConvKArgs {
   int TH, TW, tilesH, tilesW, nTilesN, numTiles;
   int numPairs;  // cta_group::2 kernel: pairs of pixel tiles x nTilesN
   int numUnits, pixTiles;  // weight-multicast clusters: work units = pairs of pixel tiles x nTilesN
+  int splitK, kbPer;       // pixels-as-M kernel: K-blocks split over splitK CTAs per tile (fp32 partials in ws)
+  float* ws;               // [splitK][B*Ho*Wo][Cout] fp32
   int ksize, stride, pad;
   int ntaps;
   signed char tap_dh[9], tap_dw[9];  // input offset of each filter tap (stride-1 path)
@@ -229,9 +231,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < a.numTiles * a.splitK; work += gridDim.x) {
+        const int tile = work / a.splitK;
+        const int kb0 = (work - tile * a.splitK) * a.kbPer;
+        const int kb1 = min(a.kbTotal, kb0 + a.kbPer);
         const TileCoord t = decode_tile(a, tile, BN);
-        for (int kb = 0; kb < a.kbTotal; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * kStageBytes;
           uint8_t* sB = sA + kATileBytes;
@@ -279,11 +284,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < a.numTiles * a.splitK; work += gridDim.x) {
+        const int kb0 = (work % a.splitK) * a.kbPer;
+        const int kb1 = min(a.kbTotal, kb0 + a.kbPer);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < a.kbTotal; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sA = smem_u32(smem + stage * kStageBytes);
@@ -292,7 +299,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
@@ -315,12 +322,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t chunk_ctr = 0;
-    for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < a.numTiles * a.splitK; work += gridDim.x) {
+      const int tile = work / a.splitK;
       const TileCoord t = decode_tile(a, tile, BN);
       const int h = t.h0 + th, w = t.w0 + tw;
       const bool valid = (th < a.TH) && (h < a.Ho) && (w < a.Wo);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (a.splitK > 1) {
+        // split-K: this CTA holds a partial sum over its K range - park it as fp32 [split][pixel][Cout]; the finalize
+        // kernel adds the splits, bias and residual, rounds, stores and takes the statistics
+        const int split = work - tile * a.splitK;
+        float* dst = a.ws + ((size_t)split * a.B * a.Ho * a.Wo + ((size_t)(t.b * a.Ho + h) * a.Wo + w)) * a.Cout + t.n0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * BN + c * 32, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(dst + c * 32 + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       if (a.debug_skip & 4) {  // developer experiment: no epilogue work at all
         tc_fence_before();
         __syncwarp();
@@ -1386,6 +1417,81 @@ cudaError_t launch_conv2(int npairs_grid, cudaStream_t stream, const CUtensorMap
   return cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<BN, STAGES, DT>, tmA, tmS1, tmS2, tmB, tmO, a);
 }
 
+// Split-K finalize: out = round(sum_s ws[s] + bias (+ residual)), GroupNorm quad statistics of the rounded values.
+// Thread = one pixel slot x 8 channels; blockDim.x = (Cout / 8) * k.
+struct SplitKFinArgs {
+  const float* ws;
+  int splitK;
+  const float* bias;
+  int bias_bstride;
+  const uint16_t* residual;
+  int res_pitch;
+  uint16_t* out;
+  int out_pitch;
+  double* stats;
+  int B, HW, Cout;
+};
+
+template <int DT>
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(const SplitKFinArgs a) {
+  const int nvec = a.Cout >> 3;
+  const int vec = threadIdx.x % nvec, prow = threadIdx.x / nvec, pstride = blockDim.x / nvec;
+  const int b = blockIdx.y;
+  const size_t M = (size_t)a.B * a.HW;
+  float bias8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bias8[j] = a.bias[(size_t)b * a.bias_bstride + vec * 8 + j];
+  float st[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int p = blockIdx.x * pstride + prow; p < a.HW; p += gridDim.x * pstride) {
+    const size_t pix = (size_t)b * a.HW + p;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias8[j];
+    for (int s = 0; s < a.splitK; ++s) {
+      const float4* src = reinterpret_cast<const float4*>(a.ws + ((size_t)s * M + pix) * a.Cout + vec * 8);
+      const float4 u = __ldcs(src), v = __ldcs(src + 1);
+      acc[0] += u.x; acc[1] += u.y; acc[2] += u.z; acc[3] += u.w;
+      acc[4] += v.x; acc[5] += v.y; acc[6] += v.z; acc[7] += v.w;
+    }
+    if (a.residual != nullptr) {
+      const uint4 rv = *reinterpret_cast<const uint4*>(a.residual + pix * a.res_pitch + vec * 8);
+      float2 f;
+      f = unpack2<DT>(rv.x); acc[0] += f.x; acc[1] += f.y;
+      f = unpack2<DT>(rv.y); acc[2] += f.x; acc[3] += f.y;
+      f = unpack2<DT>(rv.z); acc[4] += f.x; acc[5] += f.y;
+      f = unpack2<DT>(rv.w); acc[6] += f.x; acc[7] += f.y;
+    }
+    uint4 pk;
+    pk.x = pack2<DT>(acc[0], acc[1]);
+    pk.y = pack2<DT>(acc[2], acc[3]);
+    pk.z = pack2<DT>(acc[4], acc[5]);
+    pk.w = pack2<DT>(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(a.out + pix * a.out_pitch + vec * 8) = pk;
+    const float2 f0 = unpack2<DT>(pk.x), f1 = unpack2<DT>(pk.y), f2 = unpack2<DT>(pk.z), f3 = unpack2<DT>(pk.w);
+    st[0] += (f0.x + f0.y) + (f1.x + f1.y);
+    st[1] += (f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y);
+    st[2] += (f2.x + f2.y) + (f3.x + f3.y);
+    st[3] += (f2.x * f2.x + f2.y * f2.y) + (f3.x * f3.x + f3.y * f3.y);
+  }
+  if (a.stats != nullptr) {
+    // combine the pixel slots of the block in shared memory (fixed order), then ONE fp64 atomic per value and block -
+    // per-thread atomics on the few hundred statistics addresses serialise in L2 (measured 40 us per launch)
+    __shared__ float s_red[256 * 4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s_red[threadIdx.x * 4 + i] = st[i];
+    __syncthreads();
+    if (prow == 0) {
+      double t[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int r = 0; r < pstride; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] += (double)s_red[(r * nvec + vec) * 4 + i];
+      double* dst = a.stats + ((size_t)b * (a.Cout >> 2) + 2 * vec) * 2;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(dst + i, t[i]);
+    }
+  }
+}
+
 template <int BN, int STAGES, int DT>
 cudaError_t launch_conv(int grid, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmS1,
                         const CUtensorMap& tmS2, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvKArgs& a) {
@@ -1425,6 +1531,45 @@ void choose_tile(int Ho, int Wo, int* TH, int* TW) {
 }  // namespace
 
 }  // namespace d3
+
+namespace d3 {
+namespace {
+// Split-K plan of the pixels-as-M kernel: when a layer has too few tiles to occupy half the SMs (small feature maps,
+// small batches) its K loop is cut into S ranges handled by S CTAs; 1 = no split.  Shared by d3_conv2d_igemm and
+// d3_conv2d_workspace_bytes.  D3_CONV_SPLITK=0 disables.
+int plan_split_k(const d3_conv_params* p, int* BN_out) {
+  const int Ho = p->H / p->stride, Wo = p->W / p->stride;
+  int TH, TW;
+  choose_tile(Ho, Wo, &TH, &TW);
+  const int pixTiles = p->B * ceil_div(Ho, TH) * ceil_div(Wo, TW);
+  int BN = (p->Cout % 256 == 0) ? 256 : 128;
+  if (BN == 256 && pixTiles * (p->Cout / 256) < num_sms()) BN = 128;
+  if (BN_out) *BN_out = BN;
+  static int want = -1;
+  if (want < 0) { const char* e = getenv("D3_CONV_SPLITK"); want = e ? atoi(e) : 4; }
+  if (!want || p->up2x_phase != 0 || p->Cout == 128) return 1;
+  const int numTiles = pixTiles * (p->Cout / BN);
+  const int kbTotal = (p->ksize * p->ksize * p->Cin + (p->sc1 ? p->C1 : 0) + (p->sc2 ? p->C2 : 0)) / 64;
+  if (numTiles * 2 > num_sms() || kbTotal < 8) return 1;
+  int S = num_sms() / numTiles;
+  if (S > kbTotal / 8) S = kbTotal / 8;   // at least 8 K-blocks per CTA
+  if (S > want) S = want;                 // D3_CONV_SPLITK = largest split factor (the fp32 partials cost S x the output)
+  if (S < 2) return 1;
+  const int per = ceil_div(kbTotal, S);
+  return ceil_div(kbTotal, per);
+}
+}  // namespace
+}  // namespace d3
+
+extern "C" size_t d3_conv2d_workspace_bytes(const d3_conv_params* p) {
+  using namespace d3;
+  if (p == nullptr || p->dtype == D3_DTYPE_F32 || p->Cin <= 0 || p->Cin % 64 || p->Cout <= 0 || p->Cout % 128 ||
+      (p->stride != 1 && p->stride != 2) || (p->ksize != 1 && p->ksize != 3))
+    return 0;
+  const int S = plan_split_k(p, nullptr);
+  if (S <= 1) return 0;
+  return (size_t)S * p->B * (p->H / p->stride) * (p->W / p->stride) * p->Cout * sizeof(float);
+}
 
 // Developer hook (not part of include/d3roma_b200.h): read (and optionally clear) the cycle counters collected while
 // D3_CONV_DEBUG_SKIP has bit 256 set.
@@ -1527,6 +1672,9 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   if (use_t) BN = 128;  // pixels-as-N: the weight (M) tile is always 128 output channels
   a.nTilesN = p->Cout / BN;
   a.numTiles = pixTiles * a.nTilesN;
+  a.splitK = 1;
+  a.kbPer = 0;   // set below once kbTotal is known
+  a.ws = nullptr;
   a.ksize = p->ksize;
   a.stride = p->stride;
   a.pad = p->ksize / 2;
@@ -1551,6 +1699,15 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   a.kbSc1 = p->sc1 ? p->C1 / 64 : 0;
   a.kbSc2 = p->sc2 ? p->C2 / 64 : 0;
   a.kbTotal = a.kbMain + a.kbSc1 + a.kbSc2;
+  a.kbPer = a.kbTotal;
+  if (!use_t && p->workspace != nullptr) {
+    const int S = plan_split_k(p, nullptr);
+    if (S > 1 && (size_t)p->workspace_bytes >= (size_t)S * p->B * Ho * Wo * p->Cout * sizeof(float)) {
+      a.splitK = S;
+      a.kbPer = ceil_div(a.kbTotal, S);
+      a.ws = static_cast<float*>(p->workspace);
+    }
+  }
   a.sc_off2 = p->x_pitch;
   a.bias = p->bias;
   a.bias_bstride = p->bias_bstride;
@@ -1645,7 +1802,7 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
     }
   }
 
-  int grid = a.numTiles < num_sms() ? a.numTiles : num_sms();
+  int grid = a.numTiles * a.splitK < num_sms() ? a.numTiles * a.splitK : num_sms();
   cudaError_t le = cudaSuccess;
   // weight multicast: 2-CTA clusters of the halo-block kernel share every weight tile (each CTA fetches half of it and
   // multicasts) - halves the L2 -> SM weight traffic.  D3_CONV_MC=1 to enable.
@@ -1666,7 +1823,7 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   static int use_2cta = -1;
   if (use_2cta < 0) { const char* e = getenv("D3_CONV_2CTA"); use_2cta = e ? atoi(e) : 0; }
   a.numPairs = ((pixTiles + 1) / 2) * a.nTilesN;
-  if (!use_t && use_2cta && a.numPairs >= 8) {
+  if (!use_t && use_2cta && a.numPairs >= 8 && a.splitK == 1) {
     // B-operand box covers this CTA's half of the weight tile
     uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)p->Cout};
     uint64_t str[1] = {(uint64_t)Ktot * 2};
@@ -1696,6 +1853,22 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   else
     le = launch_conv<256, 4, kF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, a);
   D3_CHECK_CUDA(le);
+  if (a.splitK > 1) {
+    D3_LAUNCH_CHECK();
+    SplitKFinArgs f{a.ws, a.splitK, p->bias, p->bias_bstride, static_cast<const uint16_t*>(p->residual), p->res_pitch,
+                    static_cast<uint16_t*>(p->out), p->out_pitch, p->stats, p->B, Ho * Wo, p->Cout};
+    const int nvec = p->Cout / 8;
+    const int threads = nvec <= 256 ? nvec * (256 / nvec) : 0;
+    D3_REQUIRE(threads > 0, "conv: split-K finalize supports Cout <= 2048 (got %d)", p->Cout);
+    const int pstride = threads / nvec;
+    int gx = ceil_div(Ho * Wo, pstride * 4);   // ~4 pixels per thread
+    const int cap = ceil_div(num_sms() * 2, p->B);
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    dim3 fgrid(gx, p->B);
+    if (p->dtype == D3_DTYPE_BF16) splitk_finalize_kernel<kBF16><<<fgrid, threads, 0, stream>>>(f);
+    else splitk_finalize_kernel<kF16><<<fgrid, threads, 0, stream>>>(f);
+  }
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

@@ -119,6 +119,10 @@ def conv2d_igemm(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, *,
     for t_ in (sc1, sc2, residual, out):
         if t_ is not None and t_.dtype != x.dtype:
             raise ValueError("all 16-bit operands of a conv must share one dtype")
+    ws_bytes = _lib.lib().d3_conv2d_workspace_bytes(C.byref(p))
+    if ws_bytes:   # split-K scratch for layers with too few tiles to fill the SMs (torch's allocator: graph-capturable)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws_bytes
     _lib.check(_lib.lib().d3_conv2d_igemm(C.byref(p), _stream()))
     return out
 

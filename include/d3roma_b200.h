@@ -83,8 +83,14 @@ typedef struct d3_conv_params {
                           writes output pixels (2i+py, 2j+px), (py,px) = ((phase-1)/2, (phase-1)%2), from the 2x2
                           input neighbourhood with pre-summed weights w[Cout][4*Cin]. 4 launches = the whole layer
                           at 4/9 of the FLOPs and without materialising the upsampled tensor.                   */
+  void* workspace;     /* optional fp32 scratch for split-K (small layers / small batches: too few tiles to fill the
+                          SMs, so the K loop is split across CTAs and a second kernel sums the partials); size from
+                          d3_conv2d_workspace_bytes(); NULL = never split                                           */
+  int64_t workspace_bytes;
 } d3_conv_params;
 
+/* bytes of split-K scratch this call would like (0 when it runs unsplit) */
+size_t d3_conv2d_workspace_bytes(const d3_conv_params* p);
 int d3_conv2d_igemm(const d3_conv_params* p, void* stream);
 
 /* ---- GroupNorm(32 groups) + optional SiLU over up to two concatenated sources ------------------
