@@ -47,7 +47,7 @@ def test_struct_layouts_match_header():
             decl = decl.strip()
             if not decl:
                 continue
-            decl = re.sub(r"^(const\s+)?(void|float|double|int32_t)\s*\*?", "", decl).strip()
+            decl = re.sub(r"^(const\s+)?(void|float|double|int32_t|int64_t)\s*\*?", "", decl).strip()
             fields += [f.strip().lstrip("*").strip() for f in decl.split(",")]
         assert fields == [f[0] for f in cls._fields_], (cname, fields)
 
