@@ -1,20 +1,30 @@
 #!/usr/bin/env python
 """Benchmark of the D3RoMa denoising hot path (BASELINE.json metric: disparity maps/sec at 360x640, 10 DDIM steps).
 
-    python bench.py --gpus N --steps K --warmup W          # this implementation (sm_100a kernels)
-    python bench.py --impl reference --steps K --warmup W  # the reference path on the host CPU cores (oracle port)
+    python bench.py --gpus N --steps K --warmup W [--config c2|c1|c3|c4|c5] [--dtype fp16|bf16]
+    python bench.py --impl reference --steps K --warmup W     # the reference path on the host CPU cores (oracle port)
 
-One "step" = one pass of the hot path over one batch: the left+right+raw variant, 16 stereo pairs per GPU at
-360x640 (computed at the padded 384x640 like the reference's eval path), 10 DDIM steps (BASELINE configs[1]).
-For N > 1 the driver launches this under torchrun; independent stereo pairs are sharded by rank (weak scaling,
-16 pairs per GPU) and the final disparity maps are all-gathered over NCCL inside the timed step.
+One "step" = one pass of the hot path over one batch.  The default workload is BASELINE configs[1] ("c2"): the
+left+right+raw variant, 16 stereo pairs per GPU at 360x640 (computed at the padded 384x640 like the reference's eval
+path), 10 DDIM steps, in the fp16-operand mode (the mode that meets the north-star per-step tolerance; `--dtype bf16`
+times the secondary bf16 mode).  For N > 1 the driver launches this under torchrun; independent stereo pairs are
+sharded by rank (weak scaling) and the final disparity maps are all-gathered over NCCL inside the timed step.
+
+Other BASELINE configs (parity-test cases made measurable; `config.workload` names what ran):
+  c1  1 pair, DDIM 10 (configs[0] on the GPU: the B = 1 latency case)
+  c3  rgb+raw variant with stereo-geometry guidance, 8 pairs per GPU (configs[2]: 64 pairs on 8 GPUs)
+  c4  540x960 (UNet at 544x960), DDPM 100 steps, fp32 reference-precision path, 1 pair per GPU (configs[3])
+  c5  32 pairs per GPU, DDIM 10, disparity maps AND the [n,11] metric rows all-gathered (configs[4]: 256 pairs on 8 GPUs)
 
 JSON keys beyond the base contract:
-  roofline      dominant kernel (tcgen05 implicit-GEMM conv, shape 3x3 128->128 @384x640, 31 % of the FLOPs) timed
-                alone with CUDA events: achieved TFLOP/s vs the measured cuBLAS bf16 burst peak.
-  roofline_hbm  the bandwidth kernel (GroupNorm+SiLU, 128 ch @384x640) vs the measured copy bandwidth.
-  unet          whole-UNet algorithmic TFLOP/s inside the timed region vs the sustained peak.
-  cpu_baseline  the oracle port of the reference pipeline timed on the host cores on a bounded sample.
+  roofline            dominant kernel (tcgen05 implicit-GEMM conv, 3x3 128->128 @384x640, 31 % of the FLOPs) timed alone
+                      with CUDA events in this run: achieved TFLOP/s vs the measured cuBLAS bf16 burst peak; `traffic` is
+                      read from profiles/ncu_traffic.json (written from an `ncu --set full` capture, with its commit).
+  roofline_hbm        the bandwidth kernel (GroupNorm+SiLU, 128 ch @384x640) vs the measured copy bandwidth.
+  unet                whole-UNet algorithmic TFLOP/s inside the timed region vs the sustained peak.
+  gpu_eager_baseline  the oracle's torch.nn UNet run by eager PyTorch (cuDNN / cuBLAS, same dtype, channels_last) on the
+                      SAME GPU in this run, outside the timed region: the "same-box library" bar.
+  cpu_baseline        the oracle port of the reference pipeline timed on the host cores on a bounded sample.
 """
 from __future__ import annotations
 
@@ -33,14 +43,27 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-H0, W0 = 360, 640           # image size the metric is quoted on
-HP, WP = 384, 640           # padded size the UNet runs at (InputPadder(divis_by=32))
-B_PER_GPU = 16
-DDIM_STEPS = 10
-UNET_GFLOP = 1872.53        # per sample per UNet forward at 384x640, Cin=8, dc=1
 DDIM_CFG = dict(num_train_timesteps=128, beta_schedule="squaredcos_cap_v2", prediction_type="sample",
                 clip_sample=True, set_alpha_to_one=False, steps_offset=1)
+DDPM_CFG = dict(num_train_timesteps=128, beta_schedule="squaredcos_cap_v2", prediction_type="sample",
+                thresholding=True, clip_sample=True)
 METRIC = "disparity maps/sec at 360x640, 10 DDIM steps"
+
+# per-sample UNet forward GFLOP: (Cin, dc, padded H, padded W) -> GFLOP
+UNET_GFLOP = {(8, 1, 384, 640): 1872.53, (5, 1, 384, 640): 1870.83, (8, 1, 544, 960): 4001.95}
+
+CONFIGS = {
+    # name: pairs/GPU, (h, w), cond_channels, Cin, sampler, steps, guidance weight, dtype override, BASELINE.json index
+    "c1": dict(pairs=1, hw=(360, 640), cond="left+right+raw", cin=8, sampler="ddim", n_steps=10, guid=0.0, dtype=None, idx=0),
+    "c2": dict(pairs=16, hw=(360, 640), cond="left+right+raw", cin=8, sampler="ddim", n_steps=10, guid=0.0, dtype=None, idx=1),
+    "c3": dict(pairs=8, hw=(360, 640), cond="rgb+raw", cin=5, sampler="ddim", n_steps=10, guid=2e-4, dtype=None, idx=2),
+    "c4": dict(pairs=1, hw=(540, 960), cond="left+right+raw", cin=8, sampler="ddpm", n_steps=100, guid=0.0, dtype="fp32", idx=3),
+    "c5": dict(pairs=32, hw=(360, 640), cond="left+right+raw", cin=8, sampler="ddim", n_steps=10, guid=0.0, dtype=None, idx=4),
+}
+
+
+def pad32(v: int) -> int:
+    return (v + 31) // 32 * 32
 
 
 def load_peaks():
@@ -49,6 +72,18 @@ def load_peaks():
         d = json.loads(p.read_text())
         return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+def load_ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the two roofline kernels, transcribed from a committed
+    `ncu --set full` capture (the file names the capture and the commit it was taken at).  None when absent."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if not p.exists():
+        return {}
+    try:
+        return json.loads(p.read_text())
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -95,32 +130,62 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- synthetic inputs
-def synth_inputs(n: int, first_index: int = 0, h: int = H0, w: int = W0):
-    """SURVEY.md §8d: seeded per global sample index; images uint8-like in [-1,1], raw depth uniform [0.3,2] m with
-    20 % holes -> disparity -> Normalizer(average, bound 128) -> [-1,1].  Host tensors (CPU)."""
+def synth_inputs(n: int, first_index: int = 0, h: int = 360, w: int = 640, stereo_consistent: bool = False):
+    """SURVEY.md 8d: seeded per global sample index; images uint8-like in [-1,1], raw depth uniform [0.3,2] m with
+    20 % holes.  Host tensors (CPU).  ``stereo_consistent``: the right image is the left one displaced by the true
+    disparity (so that the stereo-geometry guidance of config c3 sees a real correspondence), rgb = left."""
+    import torch.nn.functional as F
     lefts, rights, depths = [], [], []
     for i in range(n):
         g = torch.Generator().manual_seed(1234 + first_index + i)
-        lefts.append((torch.randint(0, 256, (3, h, w), generator=g).float() / 255.0 - 0.5) * 2)
-        rights.append((torch.randint(0, 256, (3, h, w), generator=g).float() / 255.0 - 0.5) * 2)
+        left = (torch.randint(0, 256, (3, h, w), generator=g).float() / 255.0 - 0.5) * 2
+        right = (torch.randint(0, 256, (3, h, w), generator=g).float() / 255.0 - 0.5) * 2
         d = torch.rand((1, h, w), generator=g) * 1.7 + 0.3
-        d[torch.rand((1, h, w), generator=g) < 0.2] = 0.0
+        holes = torch.rand((1, h, w), generator=g) < 0.2
+        if stereo_consistent:
+            d = F.interpolate(d[None, :, ::24, ::24], size=(h, w), mode="bilinear", align_corners=True)[0]
+            left = F.avg_pool2d(F.pad(left[None], (1, 1, 1, 1), mode="replicate"), 3, 1)[0]
+            disp = 24.5471958 / d
+            xx, yy = torch.meshgrid(torch.arange(w), torch.arange(h), indexing="xy")
+            grid = torch.stack([(xx + disp[0]) / ((w - 1) / 2.0) - 1, yy / ((h - 1) / 2.0) - 1], -1)[None]
+            right = F.grid_sample(left[None], grid, align_corners=True, mode="bilinear", padding_mode="border")[0]
+        d = d.clone()
+        d[holes] = 0.0
+        lefts.append(left)
+        rights.append(right)
         depths.append(d)
     return torch.stack(lefts), torch.stack(rights), torch.stack(depths)
+
+
+def workload_config(name: str, n_gpus: int, dtype: str):
+    c = CONFIGS[name]
+    hp, wp = pad32(c["hw"][0]), pad32(c["hw"][1])
+    sampler = f"{'DDIM' if c['sampler'] == 'ddim' else 'DDPM'} {c['n_steps']} steps"
+    guid = f", stereo-geometry guidance (weight {c['guid']:g})" if c["guid"] > 0 else ""
+    return {"workload": f"BASELINE configs[{c['idx']}] ({name}): {c['cond']} variant, batch {c['pairs']} per GPU at "
+                        f"{c['hw'][0]}x{c['hw'][1]} (UNet at padded {hp}x{wp}), {sampler}{guid}, random-init "
+                        f"UNet2DModel({c['cin']}->1, 113.68 M params), {dtype} operands",
+            "config": name, "pairs_per_gpu": c["pairs"], "global_pairs": c["pairs"] * n_gpus,
+            "sampler_steps": c["n_steps"],
+            "parallelism": f"batch-shard x{n_gpus} (replicated weights, output all-gather)",
+            "l2": "per-step working set (>1 GB of activations per layer at batch 16) exceeds the 126 MB L2; no explicit "
+                  "flush" if c["pairs"] >= 8 else "small batch: layers of the deep levels fit in the 126 MB L2 (as they "
+                  "do in the real single-pair loop); inputs of every step are rewritten by the previous kernel"}
 
 
 # --------------------------------------------------------------------------------------------- CPU reference arm
 def cpu_reference_steps(n_steps: int, n_warm: int, threads: int):
     """Time the oracle port of the reference pipeline (core/custom_pipelines.py loop + restated UNet) on the host:
-    each timed unit = 1 stereo pair, ONE DDIM step (UNet forward + scheduler update) at 384x640, fp32."""
+    each timed unit = 1 stereo pair, ONE DDIM step (UNet forward + scheduler update) at 384x640, fp32.
+    Returns (seconds per timed unit, maps/s equivalent = 1 / (10 units))."""
     from oracle import pipeline_ref, prepost_ref as P
     from oracle.unet_ref import make_unet
     torch.set_num_threads(threads)
-    unet = make_unet(8, 1, seed=0, sample_size=(HP, WP))
+    unet = make_unet(8, 1, seed=0, sample_size=(384, 640))
     left, right, depth = synth_inputs(1)
     raw = P.normalize_average(P.depth_to_disp(depth[0], 24.5471958), 128.0)[None]
     conds = {"left": P.pad_replicate(left), "right": P.pad_replicate(right), "raw": P.pad_replicate(raw)}
-    x_T = torch.randn((1, 1, HP, WP), generator=torch.Generator().manual_seed(42))
+    x_T = torch.randn((1, 1, 384, 640), generator=torch.Generator().manual_seed(42))
     times = []
     for i in range(n_warm + n_steps):
         t0 = time.perf_counter()
@@ -128,8 +193,13 @@ def cpu_reference_steps(n_steps: int, n_warm: int, threads: int):
         dt = time.perf_counter() - t0
         if i >= n_warm:
             times.append(dt)
-    sec_per_unet_step = sum(times) / len(times)
-    return sec_per_unet_step, 1.0 / (DDIM_STEPS * sec_per_unet_step)
+    sec = sum(times) / len(times)
+    return sec, 1.0 / (10 * sec)
+
+
+CPU_SAMPLE = ("bounded sample of BASELINE configs[1]: each timed step = 1 stereo pair x 1 DDIM step (UNet forward + "
+              "scheduler update, fp32, 384x640) out of the workload's 16 pairs x 10 steps; maps/s = 1 / (10 x seconds "
+              "per timed step)")
 
 
 def run_reference_arm(args):
@@ -138,46 +208,31 @@ def run_reference_arm(args):
         return
     threads = os.cpu_count() or 1
     sec, maps = cpu_reference_steps(max(1, args.steps), max(1, min(args.warmup, 2)), threads)
-    sample = ("1 synthetic stereo pair 384x640 (padded 360x640), ONE DDIM step (UNet forward + scheduler update) per "
-              "timed step, fp32, scaled x10 steps to maps/s")
+    cfg = workload_config("c2", args.gpus, "f32")
+    cfg["workload"] = ("CPU reference arm, " + CPU_SAMPLE + " | config it samples: " + cfg["workload"])
+    cfg["timed_unit"] = {"pairs": 1, "ddim_steps": 1, "units_per_map": 10}
     line = {
         "impl": "reference", "metric": METRIC, "value": maps, "unit": "maps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * DDIM_STEPS,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": maps, "unit": "maps/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": maps, "unit": "maps/s", "cores": threads, "kind": "port", "sample": CPU_SAMPLE},
         "e2e": {"value": maps, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "reference = jie0530/d3roma core/custom_pipelines.py loop restated in oracle/ (diffusers.UNet2DModel "
-                "is an un-vendored third-party dependency, so the CPU path is the oracle port, torch CPU fp32)",
+                "is an un-vendored third-party dependency, so the CPU path is the oracle port, torch CPU fp32); "
+                "ms_per_step is the wall time of ONE timed unit (1 pair x 1 DDIM step), value is scaled to maps/s",
     }
     emit(line)
 
 
-def workload_config(n_gpus: int):
-    return {"workload": "left+right+raw variant, batch 16 per GPU at 360x640 (UNet at padded 384x640), DDIM 10 steps, "
-                        "random-init UNet2DModel(8->1, 113.68 M params), BASELINE configs[1]",
-            "pairs_per_gpu": B_PER_GPU, "global_pairs": B_PER_GPU * n_gpus, "ddim_steps": DDIM_STEPS,
-            "parallelism": f"batch-shard x{n_gpus} (replicated weights, output all-gather)",
-            "l2": "per-step working set (>1 GB activations per layer) exceeds the 126 MB L2; no explicit flush"}
-
-
 # --------------------------------------------------------------------------------------------- GPU arm
-def build_pipeline(dtype: str, device):
-    import d3roma_b200 as d
-    from d3roma_b200.weights import random_init_state_dict
-    net = d.UNet2DModel(sample_size=(HP, WP), in_channels=8, out_channels=1, compute_dtype=dtype).to(device)
-    net.load_state_dict(random_init_state_dict(8, 1, seed=0))
-    pipe = d.GuidedDiffusionPipeline(net, d.MyDDIMScheduler.from_config(DDIM_CFG),
-                                     d.FlowGuidance(flow_guidance_weight=0.0))
-    return d, pipe
-
-
-def time_dominant_kernels(dtype, peaks):
-    """Roofline legs: the dominant conv shape and the GroupNorm+SiLU pass, each timed alone with CUDA events."""
+def time_dominant_kernels(dtype, peaks, B=16):
+    """Roofline legs: the dominant conv shape and the GroupNorm+SiLU pass, each timed alone with CUDA events on the
+    stream the kernels are launched on (torch's current stream)."""
     from d3roma_b200 import ops
     adt = torch.bfloat16 if dtype == "bf16" else torch.float16
-    B = B_PER_GPU
+    HP, WP = 384, 640
     x = torch.randn(B, HP, WP, 128, device="cuda").to(adt)
     w = (torch.randn(128, 1152, device="cuda") / 34.0).to(adt)
     bias = torch.zeros(128, device="cuda")
@@ -201,19 +256,49 @@ def time_dominant_kernels(dtype, peaks):
     flops = 2.0 * B * HP * WP * 128 * 1152
     t_gn = timeit(lambda: ops.groupnorm_silu(x, stats, gamma, beta, out=out))
     gn_bytes = 2.0 * x.numel() * 2
-    roof = {"bound": "tensor", "kernel": "conv_igemm_t_kernel (pixels-as-N, 16x16 halo blocks) 3x3 128->128 @16x384x640",
+    tr = load_ncu_traffic()
+    roof = {"bound": "tensor",
+            "kernel": "conv_igemm_t_kernel (pixels-as-N, 16x16 halo blocks, stmatrix epilogue) 3x3 128->128 @16x384x640",
             "achieved": flops / t_conv / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
             "frac": flops / t_conv / 1e12 / peaks["tf_burst"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r01b_ncu_full_summary.csv)
-            "traffic": 1.014290e9 + 0.964388e9, "algorithmic_bytes": 2.0 * x.numel() * 2,
-            "ncu_tensor_pipe_active_pct": 69.5,
-            "flops_per_launch": flops, "ms_per_launch": t_conv * 1e3, "peak_source": peaks["src"] + " burst"}
+            "traffic": tr.get("conv", {}).get("dram_bytes"), "traffic_source": tr.get("conv", {}).get("source"),
+            "algorithmic_bytes": 2.0 * x.numel() * 2, "flops_per_launch": flops, "ms_per_launch": t_conv * 1e3,
+            "peak_source": peaks["src"] + " burst (kernel timed alone)"}
     roof_hbm = {"bound": "hbm", "kernel": "gn_apply_kernel 128ch @16x384x640 (GroupNorm+SiLU)",
                 "achieved": gn_bytes / t_gn / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                "frac": gn_bytes / t_gn / 1e9 / peaks["hbm"], "traffic": 1.006704e9 + 0.950754e9,
-                "bytes_per_launch": gn_bytes,
-                "ms_per_launch": t_gn * 1e3, "peak_source": peaks["src"]}
+                "frac": gn_bytes / t_gn / 1e9 / peaks["hbm"],
+                "traffic": tr.get("groupnorm", {}).get("dram_bytes"),
+                "traffic_source": tr.get("groupnorm", {}).get("source"),
+                "bytes_per_launch": gn_bytes, "ms_per_launch": t_gn * 1e3, "peak_source": peaks["src"]}
     return roof, roof_hbm
+
+
+def gpu_eager_baseline(dtype: str, B: int, hw, cin: int, n_steps: int):
+    """The oracle's torch.nn UNet through eager PyTorch (cuDNN convs, SDPA-free attention as restated) on this GPU in
+    the same 16-bit dtype, channels_last: 1 warm-up + 3 timed forwards, outside the timed region of the bench."""
+    from oracle.unet_ref import make_unet
+    adt = torch.bfloat16 if dtype == "bf16" else torch.float16
+    try:
+        net = make_unet(cin, 1, seed=0, sample_size=hw).to("cuda", adt).to(memory_format=torch.channels_last)
+        x = torch.randn(B, cin, *hw, device="cuda", dtype=adt).to(memory_format=torch.channels_last)
+        t = torch.tensor(61, device="cuda")
+        with torch.no_grad():
+            net(x, t)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                net(x, t)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        del net, x
+        torch.cuda.empty_cache()
+        return {"ms_per_unet_step": ms, "value": B / (ms * 1e-3 * n_steps), "unit": "maps/s",
+                "what": f"eager PyTorch {torch.__version__} (cuDNN/cuBLAS) on the oracle's torch.nn UNet, {dtype}, "
+                        f"channels_last, batch {B}, UNet forwards only (scheduler excluded), same GPU, this run"}
+    except Exception as e:  # noqa: BLE001  (an out-of-memory or cuDNN failure must not kill the bench line)
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:120]}"}
 
 
 def run_gpu_arm(args):
@@ -229,33 +314,61 @@ def run_gpu_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
+    import d3roma_b200 as d
     from d3roma_b200 import _lib
-    d, pipe = build_pipeline(args.dtype, dev)
     from d3roma_b200.evaluate import denoise_batch
+    from d3roma_b200.weights import random_init_state_dict
+    from d3roma_b200 import metrics as M
+
+    C = CONFIGS[args.config]
+    dtype = C["dtype"] or args.dtype
+    Bp, (H0, W0), n_steps = C["pairs"], C["hw"], C["n_steps"]
+    HP, WP = pad32(H0), pad32(W0)
+    guided = C["guid"] > 0
+    net = d.UNet2DModel(sample_size=(HP, WP), in_channels=C["cin"], out_channels=1, compute_dtype=dtype).to(dev)
+    net.load_state_dict(random_init_state_dict(C["cin"], 1, seed=0))
+    sched = (d.MyDDIMScheduler.from_config(DDIM_CFG) if C["sampler"] == "ddim"
+             else d.MyDDPMScheduler.from_config(DDPM_CFG))
+    guidance = d.FlowGuidance(flow_guidance_weight=C["guid"], flow_guidance_mode="stereo" if guided else "imputation")
+    pipe = d.GuidedDiffusionPipeline(net, sched, guidance)
     normalizer = d.Normalizer(ssi=False, mode="average", num_chs=1, ch_bounds=[128.], ch_gammas=[1.], t=0.5, s=2.0)
     cam = d.SIM_CAMERA
 
     # ---- synthetic inputs: host (pinned) copies for the e2e leg, device-resident padded copies for `value`
-    left_h, right_h, depth_h = synth_inputs(B_PER_GPU, first_index=rank * B_PER_GPU)
+    left_h, right_h, depth_h = synth_inputs(Bp, first_index=rank * Bp, h=H0, w=W0, stereo_consistent=guided)
     left_h, right_h, depth_h = left_h.pin_memory(), right_h.pin_memory(), depth_h.pin_memory()
     padder = d.InputPadder(left_h.shape, divis_by=32)
+    names = ("rgb", "raw") if C["cond"] == "rgb+raw" else ("left", "right", "raw")
 
     def prep_device():
         dd = depth_h.to(dev)
-        raw = normalizer.normalize(d.prepost.depth_to_disp(dd, cam.fxb).view(B_PER_GPU, H0, W0))[0]
-        l, r, rw = padder.pad(left_h.to(dev), right_h.to(dev), raw.view(B_PER_GPU, 1, H0, W0))
-        return torch.cat([l, r, rw], 1).contiguous()
+        raw = normalizer.normalize(d.prepost.depth_to_disp(dd, cam.fxb).view(Bp, H0, W0))[0]
+        l, r, rw = padder.pad(left_h.to(dev), right_h.to(dev), raw.view(Bp, 1, H0, W0))
+        srcs = {"rgb": l, "left": l, "right": r, "raw": rw}
+        return torch.cat([srcs[n] for n in names], 1).contiguous(), l, r
 
-    cond = prep_device()
-    gens = [torch.Generator().manual_seed(10_000 + rank * B_PER_GPU + i) for i in range(B_PER_GPU)]
+    cond, left_d, right_d = prep_device()
+    gens = [torch.Generator().manual_seed(10_000 + rank * Bp + i) for i in range(Bp)]
     x_T = torch.cat([torch.randn((1, 1, HP, WP), generator=g) for g in gens]).to(dev)
-    gather_buf = torch.empty((world * B_PER_GPU, 1, H0, W0), device=dev) if world > 1 else None
+    gather_buf = torch.empty((world * Bp, 1, H0, W0), device=dev) if world > 1 else None
+    rows_buf = torch.empty((world * Bp, 11), dtype=torch.float64, device=dev) if world > 1 else None
+    want_rows = args.config == "c5"
+    gt_disp = d.prepost.depth_to_disp(depth_h.to(dev), cam.fxb).view(Bp, H0, W0) if want_rows else None
+    fxb_t = torch.full((Bp,), float(cam.fxb), device=dev) if want_rows else None
 
     def one_step():
-        img = pipe.sample_from(x_T, cond, DDIM_STEPS)
+        cond.mul_(1.0)   # a new batch every step: the per-loop conditioning term of conv_in is recomputed, not cached
+        img = pipe.sample_from(x_T, cond, n_steps, left_images=left_d if guided else None,
+                               right_images=right_d if guided else None,
+                               denorm=normalizer.denormalize if guided else None)
         disp = normalizer.denormalize(padder.unpad(img))
+        rows = None
+        if want_rows:   # distributed_evaluate.py:153-163: per-sample metric rows gathered with the maps
+            rows = M.compute_errors_device(gt_disp, disp[:, 0], gt_disp > 0, fxb_t)
         if world > 1:
             dist.all_gather_into_tensor(gather_buf, disp)
+            if rows is not None:
+                dist.all_gather_into_tensor(rows_buf, rows)
         return disp
 
     def sync():
@@ -263,7 +376,8 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
+    warm = max(3, args.warmup)
+    for _ in range(warm):
         one_step()
     sync()
     lib = _lib.lib()
@@ -285,15 +399,18 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     sec = float(t.item())
-    value = world * B_PER_GPU * args.steps / sec
+    value = world * Bp * args.steps / sec
 
     # ---- e2e: the public call chain with HOST buffers (pad -> pipeline.__call__ -> unpad -> denormalise -> D2H)
     def e2e_step():
         dd = depth_h.to(dev, non_blocking=True)
-        raw = normalizer.normalize(d.prepost.depth_to_disp(dd, cam.fxb).view(B_PER_GPU, H0, W0))[0]
-        return denoise_batch(pipe, normalizer, left=left_h, right=right_h, sim_disp=raw.view(B_PER_GPU, 1, H0, W0),
-                             cond_channels="left+right+raw", num_inference_steps=DDIM_STEPS,
-                             num_intermediate_images=1, generator=gens, to_host=True)
+        raw = normalizer.normalize(d.prepost.depth_to_disp(dd, cam.fxb).view(Bp, H0, W0))[0]
+        kw = dict(rgb=left_h, sim_disp=raw.view(Bp, 1, H0, W0)) if C["cond"] == "rgb+raw" else \
+            dict(left=left_h, right=right_h, sim_disp=raw.view(Bp, 1, H0, W0))
+        if guided:
+            kw.update(left=left_h, right=right_h)
+        return denoise_batch(pipe, normalizer, cond_channels=C["cond"], num_inference_steps=n_steps,
+                             num_intermediate_images=1, generator=gens, to_host=True, **kw)
 
     for _ in range(2):
         e2e_step()
@@ -309,33 +426,40 @@ def run_gpu_arm(args):
     te = torch.tensor([max(e0.elapsed_time(e1) * 1e-3, wall)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B_PER_GPU * n_e2e / float(te.item())
-    h2d = left_h.numel() * 4 + right_h.numel() * 4 + depth_h.numel() * 4 + x_T.numel() * 4
+    e2e_value = world * Bp * n_e2e / float(te.item())
+    n_img = 2 if (C["cond"] != "rgb+raw" or guided) else 1
+    h2d = (left_h.numel() * n_img + depth_h.numel() + x_T.numel()) * 4
     d2h = out_h.numel() * 4
 
     if rank == 0:
-        roof, roof_hbm = time_dominant_kernels(args.dtype, peaks)
-        unet_tf = world * B_PER_GPU * DDIM_STEPS * UNET_GFLOP * 1e9 * args.steps / sec / 1e12
+        gflop = UNET_GFLOP.get((C["cin"], 1, HP, WP))
+        unet_tf = (Bp * n_steps * gflop * 1e9 * args.steps / sec / 1e12) if gflop else None
         line = {
-            "metric": METRIC, "value": value, "unit": "maps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": workload_config(world),
-            "ms_per_unet_step": sec / args.steps / DDIM_STEPS * 1e3,
+            "metric": METRIC if args.config != "c4" else "disparity maps/sec at 540x960, 100 DDPM steps (fp32 path)",
+            "value": value, "unit": "maps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": workload_config(args.config, world, dtype),
+            "ms_per_unet_step": sec / args.steps / n_steps * 1e3,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": n_e2e, "api": "d3roma_b200.evaluate.denoise_batch -> GuidedDiffusionPipeline.__call__"},
             "gpu_launches": launches,
-            "roofline": roof, "roofline_hbm": roof_hbm,
-            "unet": {"algorithmic_tflops": unet_tf / world, "peak": peaks["tf_sust"],
-                     "frac_of_sustained_peak": unet_tf / world / peaks["tf_sust"], "gflop_per_sample_step": UNET_GFLOP},
         }
+        if unet_tf is not None and dtype != "fp32":
+            line["unet"] = {"algorithmic_tflops": unet_tf, "peak": peaks["tf_sust"],
+                            "frac_of_sustained_peak": unet_tf / peaks["tf_sust"], "gflop_per_sample_step": gflop,
+                            "peak_source": peaks["src"] + " sustained (kernels timed inside a long step)"}
+        if dtype != "fp32":
+            roof, roof_hbm = time_dominant_kernels(dtype, peaks)
+            line["roofline"], line["roofline_hbm"] = roof, roof_hbm
+            if not args.no_gpu_baseline:
+                line["gpu_eager_baseline"] = gpu_eager_baseline(dtype, Bp, (HP, WP), C["cin"], n_steps)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sec_cpu, maps_cpu = cpu_reference_steps(3, 1, threads)
             line["cpu_baseline"] = {"value": maps_cpu, "unit": "maps/s", "cores": threads, "kind": "port",
-                                    "sample": "oracle port of the reference loop: 1 pair 384x640, 3 timed single "
-                                              "DDIM steps (UNet forward + scheduler), fp32, scaled x10 to maps/s"}
+                                    "sample": CPU_SAMPLE + f" (3 timed steps of {sec_cpu:.2f} s)"}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -362,8 +486,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="d3roma_b200", choices=["d3roma_b200", "reference"])
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -66,6 +66,20 @@ class DDPMCoeffs(C.Structure):
     ]
 
 
+class GuidanceParams(C.Structure):
+    """Mirror of ``d3_guidance_params``."""
+
+    _fields_ = [
+        ("x0", C.c_void_p), ("left", C.c_void_p), ("right", C.c_void_p),
+        ("grad", C.c_void_p), ("x0_out", C.c_void_p), ("out2", C.c_void_p),
+        ("aux1", C.c_void_p), ("aux2", C.c_void_p),
+        ("B", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("margin", C.c_int32),
+        ("disp_scale", C.c_float), ("disp_offset", C.c_float), ("min_disp", C.c_float), ("max_disp", C.c_float),
+        ("w_ssim", C.c_float),
+        ("step", C.c_float), ("ca", C.c_float), ("cb", C.c_float), ("cc", C.c_float),
+    ]
+
+
 _lib = None
 
 
@@ -84,7 +98,7 @@ def _declare(lib: C.CDLL) -> None:
                                          vp, i32, i32, vp]),
         "d3_upsample_nearest2x": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
         "d3_im2col_input": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, i32, vp]),
-        "d3_conv_in_direct": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, vp, vp, i32, vp, vp]),
+        "d3_conv_in_direct": (i32, [vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp, i32, vp, vp]),
         "d3_conv_out_fused": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, i32, vp]),
         "d3_conv_out_workspace_bytes": (C.c_size_t, [i32, i32, i32, i32]),
         "d3_time_embed": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),
@@ -94,6 +108,7 @@ def _declare(lib: C.CDLL) -> None:
         "d3_sched_ddpm_step": (i32, [vp, vp, vp, C.POINTER(DDPMCoeffs), i64, vp, vp, vp, vp]),
         "d3_lincomb": (i32, [f32, vp, f32, vp, f32, vp, i64, vp, vp]),
         "d3_guidance_grad": (i32, [vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, f32, vp, vp]),
+        "d3_guidance_step": (i32, [C.POINTER(GuidanceParams), vp]),
         "d3_depth_to_disp": (i32, [vp, f32, i64, vp, vp]),
         "d3_disp_to_depth": (i32, [vp, f32, i64, vp, vp]),
         "d3_normalize_disp": (i32, [vp, i64, i64, i32, f32, f32, f32, f32, vp, vp]),

@@ -28,6 +28,8 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
     "-Xcudafe", "--diag_suppress=177",
 ]
+if os.environ.get("D3_DEV"):   # developer build: kernel experiments (skip loads / epilogue, cycle counters); see conv_igemm.cu
+    NVCC_FLAGS.append("-DD3_DEV")
 
 
 def _nvcc() -> str:

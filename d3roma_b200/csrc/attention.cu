@@ -179,14 +179,8 @@ extern "C" int d3_attention_hd8(const void* qkv, int pitch, int B, int N, int C,
   const int Npad = (N + kKeyBlock - 1) / kKeyBlock * kKeyBlock;
   const size_t smem = (size_t)Npad * 16 + (size_t)8 * (Npad + kVPad) * 2;
   D3_REQUIRE(smem <= 220 * 1024, "attention: N=%d tokens exceed the shared-memory K/V budget", N);
-  static size_t configured = 0;
-  if (smem > configured) {
-    D3_CHECK_CUDA(cudaFuncSetAttribute(attention_hd8_kernel<kBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-    D3_CHECK_CUDA(cudaFuncSetAttribute(attention_hd8_kernel<kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-    configured = smem;
-  }
+  D3_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(attention_hd8_kernel<kBF16>), smem));
+  D3_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(attention_hd8_kernel<kF16>), smem));
   dim3 grid(ceil_div(N, kQPerBlock), C / kHeadDim, B);
   if (dtype == D3_DTYPE_F16)
     attention_hd8_kernel<kF16><<<grid, kAttnThreads, smem, static_cast<cudaStream_t>(stream)>>>(

@@ -22,6 +22,14 @@
 #include "internal.h"
 #include "tensormap.h"
 
+// Developer experiments (skip loads / skip the epilogue / per-role cycle counters) exist only in -DD3_DEV builds
+// (D3_DEV=1 python -m d3roma_b200.build); the product library has no knob that can produce wrong results.
+#ifdef D3_DEV
+#define D3_DBG(a, mask) ((a).debug_skip & (mask))
+#else
+#define D3_DBG(a, mask) 0
+#endif
+
 namespace d3 {
 
 namespace {
@@ -34,8 +42,6 @@ constexpr uint32_t kStagingBytes = kTileM * 128;   // one 64-channel chunk of th
 struct ConvKArgs {
   int B, Ho, Wo, Cout;
   int TH, TW, tilesH, tilesW, nTilesN, numTiles;
-  int numPairs;  // cta_group::2 kernel: pairs of pixel tiles x nTilesN
-  int numUnits, pixTiles;  // weight-multicast clusters: work units = pairs of pixel tiles x nTilesN
   int splitK, kbPer;       // pixels-as-M kernel: K-blocks split over splitK CTAs per tile (fp32 partials in ws)
   float* ws;               // [splitK][B*Ho*Wo][Cout] fp32
   int ksize, stride, pad;
@@ -53,22 +59,21 @@ struct ConvKArgs {
   int blk_slot;    // halo-block variant: bytes per block ring slot ((TH+2)*TW*128)
   int n_blk, n_wts;  // halo-block variant: ring depths (<= kMaxBlk, kMaxWts)
   int pass_h;      // pixels-as-N kernel: tile rows per epilogue pass (1 unless TW < 64)
-  int t_direct;    // pixels-as-N kernel: epilogue stores straight to global (no staging / TMA store)
-  uint16_t* out;   // output base pointer + pitch for the direct epilogue
-  int out_pitch;
   int pass_w;      // pixels-as-N kernel: pixels per epilogue pass (divides TW, <= 64)
-  int debug_skip;  // developer experiment: bit0 = skip A loads, bit1 = skip B loads (results are garbage)
+  int debug_skip;  // D3_DEV builds only: bit0 = skip A loads, bit1 = skip B loads, ... (results are garbage)
 };
 
 struct TileCoord {
   int b, h0, w0, n0;
 };
 
+#ifdef D3_DEV
 // developer profiling (D3_CONV_DEBUG_SKIP bit 256): clock cycles summed over CTAs
 //   [0] MMA thread total, [1] waiting for a free accumulator, [2] waiting for pixel blocks, [3] waiting for weights,
 //   [4] epilogue thread total, [5] waiting for a full accumulator, [6] inside passes, [7] tiles
 //   [8] pass: store-buffer wait + barrier 1, [9] TMEM load, [10] math + staging stores, [11] fence + barrier 2 + store issue
 __device__ unsigned long long g_conv_prof[16];
+#endif
 
 D3_DEVINL TileCoord decode_tile(const ConvKArgs& a, int tile, int BN) {
   TileCoord t;
@@ -82,35 +87,6 @@ D3_DEVINL TileCoord decode_tile(const ConvKArgs& a, int tile, int BN) {
   t.w0 = tw * a.TW;
   t.n0 = nt * BN;
   return t;
-}
-
-// Work decode of the pixels-as-N kernel.  MC (2-CTA weight-multicast clusters): unit = (pair of pixel tiles, channel
-// tile); CTA `rank` of the cluster takes pixel tile 2*pair + rank; an odd tile count leaves one CTA with a dummy tile
-// (valid = false: it still consumes the multicast weights, loads zeros and stores nothing).
-template <bool MC>
-D3_DEVINL TileCoord decode_work(const ConvKArgs& a, int idx, uint32_t rank, bool& valid) {
-  if constexpr (!MC) {
-    valid = true;
-    return decode_tile(a, idx, 128);
-  } else {
-    TileCoord t;
-    const int nt = idx % a.nTilesN;
-    int p = 2 * (idx / a.nTilesN) + (int)rank;
-    valid = p < a.pixTiles;
-    t.n0 = nt * 128;
-    if (!valid) {
-      t.b = a.B;  // out of range in the batch dimension: TMA loads return zeros, TMA stores are dropped
-      t.h0 = 0;
-      t.w0 = 0;
-      return t;
-    }
-    const int tw = p % a.tilesW;
-    p /= a.tilesW;
-    t.h0 = (p % a.tilesH) * a.TH;
-    t.b = p / a.tilesH;
-    t.w0 = tw * a.TW;
-    return t;
-  }
 }
 
 // Butterfly transpose-reduce: on entry every lane holds 32 partial values v[0..31]; on exit lane l holds
@@ -240,11 +216,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * kStageBytes;
           uint8_t* sB = sA + kATileBytes;
-          if (a.debug_skip) {
-            const uint32_t bytes = ((a.debug_skip & 1) ? 0u : a.a_bytes) + ((a.debug_skip & 2) ? 0u : kBBytes);
+          if (D3_DBG(a, 3)) {
+            const uint32_t bytes = (D3_DBG(a, 1) ? 0u : a.a_bytes) + (D3_DBG(a, 2) ? 0u : kBBytes);
             if (bytes) mbar_arrive_expect_tx(&full_bar[stage], bytes); else mbar_arrive(&full_bar[stage]);
-            if (!(a.debug_skip & 1)) tma_load_4d(sA, &tmA, &full_bar[stage], 0, t.w0, t.h0, t.b);
-            if (!(a.debug_skip & 2)) tma_load_2d(sB, &tmB, &full_bar[stage], kb * 64, t.n0);
+            if (!D3_DBG(a, 1)) tma_load_4d(sA, &tmA, &full_bar[stage], 0, t.w0, t.h0, t.b);
+            if (!D3_DBG(a, 2)) tma_load_2d(sB, &tmB, &full_bar[stage], kb * 64, t.n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
@@ -352,7 +328,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (acc == 0) acc_phase ^= 1;
         continue;
       }
-      if (a.debug_skip & 4) {  // developer experiment: no epilogue work at all
+      if (D3_DBG(a, 4)) {  // developer experiment: no epilogue work at all
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -442,60 +418,6 @@ constexpr uint32_t kTStageBytes = kWTileBytes + kPTileBytes;
 constexpr uint32_t kTStagingBytes = 2 * kStagingBytes;  // 128 pixels x 128 channels (two 64-channel halves)
 
 
-// One 32-pixel chunk of the pixels-as-N epilogue for one channel (thread): + bias (+ residual read back from the
-// staging tile), round to 16 bit, store at [pixel row][channel] of the SWIZZLE_128B staging tile, accumulate the
-// channel's sum / sum-of-squares over in-image pixels.
-template <int DT, bool HAS_RES, int J = 0>
-D3_DEVINL void epi_t_chunk(const uint32_t (&v)[32], uint32_t sa, const uint32_t (&swz)[8], float bias, uint32_t vmask,
-                           float& s_sum, float& s_sq) {
-  if constexpr (J < 32) {
-    const uint32_t addr = sa + swz[J & 7];
-    float x = __uint_as_float(v[J]) + bias;
-    if constexpr (HAS_RES) x += unpack2<DT>(lds_u16<J * 128>(addr)).x;
-    const uint32_t pk = pack2<DT>(x, 0.f);
-    sts_u16<J * 128>(addr, pk);
-    const float xr = ((vmask >> J) & 1u) ? unpack2<DT>(pk & 0xFFFFu).x : 0.f;
-    s_sum += xr;
-    s_sq = fmaf(xr, xr, s_sq);
-    epi_t_chunk<DT, HAS_RES, J + 1>(v, sa, swz, bias, vmask, s_sum, s_sq);
-  }
-}
-
-// Paired variant of the chunk epilogue: lanes 2k / 2k+1 (adjacent channels) exchange values so that the even lane
-// stores the 32-bit word {ch, ch+1} of pixel row j and the odd lane the word {ch-1, ch} of pixel row j+4.  Rows j and
-// j+4 sit in opposite halves of the swizzle pattern, so a warp's 32 word stores hit 32 distinct banks (the 16-bit
-// version measured 50 % bank conflicts).  Statistics: each lane sums both halves of the words it stores; the quad
-// total is the sum over the 4 lanes of a quad, which is all the caller needs.
-template <int DT, bool HAS_RES, int BASE = 0, int JJ = 0, bool NO_STORE = false>
-D3_DEVINL void epi_t_chunk2(const uint32_t (&v)[32], uint32_t sa_lane, const uint32_t (&myswz)[4], float bias,
-                            uint32_t vmask, bool odd, float& s_sum, float& s_sq) {
-  if constexpr (BASE < 32) {
-    constexpr int J0 = BASE + JJ, J1 = J0 + 4;
-    const float x0 = __uint_as_float(v[J0]) + bias;   // own channel, pixel J0
-    const float x1 = __uint_as_float(v[J1]) + bias;   // own channel, pixel J1
-    const float recv = __shfl_xor_sync(0xffffffffu, odd ? x0 : x1, 1);
-    float lo = odd ? recv : x0;                       // even: {ch @J0, ch+1 @J0}; odd: {ch-1 @J1, ch @J1}
-    float hi = odd ? x1 : recv;
-    const uint32_t addr = sa_lane + myswz[JJ];
-    if constexpr (HAS_RES) {
-      const float2 r = unpack2<DT>(lds_u32<J0 * 128>(addr));
-      lo += r.x;
-      hi += r.y;
-    }
-    const uint32_t pk = pack2<DT>(lo, hi);
-    if (!NO_STORE) sts_u32<J0 * 128>(addr, pk);
-    const bool ok = ((vmask >> (odd ? J1 : J0)) & 1u) != 0;
-    const float2 xr = unpack2<DT>(pk);
-    const float a0 = ok ? xr.x : 0.f, a1 = ok ? xr.y : 0.f;
-    s_sum += a0 + a1;
-    s_sq = fmaf(a0, a0, fmaf(a1, a1, s_sq));
-    if constexpr (JJ < 3)
-      epi_t_chunk2<DT, HAS_RES, BASE, JJ + 1, NO_STORE>(v, sa_lane, myswz, bias, vmask, odd, s_sum, s_sq);
-    else
-      epi_t_chunk2<DT, HAS_RES, BASE + 8, 0, NO_STORE>(v, sa_lane, myswz, bias, vmask, odd, s_sum, s_sq);
-  }
-}
-
 // Packed fp32x2 accumulate (Blackwell FADD2 / FFMA2): acc += x, sq += x * x on two lanes of a register pair.
 D3_DEVINL void stats_acc2(float2& s, float2& q, float2 x) {
   asm("{\n\t.reg .b64 s, q, x;\n\t"
@@ -506,7 +428,18 @@ D3_DEVINL void stats_acc2(float2& s, float2& q, float2 x) {
       : "f"(x.x), "f"(x.y));
 }
 
-// Lean chunk epilogue (default): each lane rounds ITS OWN channel at pixels J0 and J0+4 into one packed word, swaps it
+D3_DEVINL float2 f2_add(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 a, b, r;\n\t"
+      "mov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\t"
+      "add.rn.f32x2 r, a, b;\n\t"
+      "mov.b64 {%0, %1}, r;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+
+// Lean chunk epilogue (per-tap kernel): each lane rounds ITS OWN channel at pixels J0 and J0+4 into one packed word, swaps it
 // with the neighbouring channel's lane and assembles the 32-bit staging word with one PRMT (even lane: {ch, ch+1} at
 // pixel J0; odd lane: {ch-1, ch} at pixel J0+4 - the same conflict-free store pattern as epi_t_chunk2, without its
 // selects).  Statistics are per own channel on the rounded values, accumulated with packed fp32x2 ops; the MASKED
@@ -539,29 +472,71 @@ D3_DEVINL void epi_t_chunk3(const uint32_t (&v)[32], uint32_t sa_lane, const uin
   }
 }
 
-// Variant that writes straight to global memory (no staging tile, no TMA store): the warp's 32 lanes hold 32
-// consecutive channels of one pixel, i.e. each store instruction covers one contiguous 64-byte segment.
-template <int DT, bool HAS_RES, int J = 0>
-D3_DEVINL void epi_t_chunk_global(const uint32_t (&v)[32], uint16_t* gp, const uint16_t* rp, size_t pitch, float bias,
-                                  uint32_t vmask, float& s_sum, float& s_sq) {
-  if constexpr (J < 32) {
-    if ((vmask >> J) & 1u) {
-      float x = __uint_as_float(v[J]) + bias;
-      if constexpr (HAS_RES) x += unpack2<DT>((uint32_t)__ldg(rp + (size_t)J * pitch)).x;
-      const uint32_t pk = pack2<DT>(x, 0.f);
-      gp[(size_t)J * pitch] = (uint16_t)pk;
-      const float xr = unpack2<DT>(pk & 0xFFFFu).x;
-      s_sum += xr;
-      s_sq = fmaf(xr, xr, s_sq);
-    }
-    epi_t_chunk_global<DT, HAS_RES, J + 1>(v, gp, rp, pitch, bias, vmask, s_sum, s_sq);
-  }
-}
-
-constexpr int kTThreads = 384;  // warps 0-3: producer / MMA / TMEM alloc / idle; warps 4-11: two epilogue groups
+constexpr int kTThreads = 384;  // warps 0-3: producer / MMA / TMEM alloc / weight producer; warps 4-11: two epilogue groups
 
 constexpr int kMaxBlk = 3;    // halo-block ring slots (halo-block variant)
 constexpr int kMaxWts = 8;    // weight-tile ring slots (halo-block variant)
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Transposing epilogue through stmatrix (halo-block kernel).  The accumulator is D[channel lane][pixel column]; the
+// output tile in shared memory is [pixel row][channel] (what the NHWC TMA store needs).  tcgen05.ld.16x256b hands every
+// warp 16 channels x 8 pixels per repetition in the mma C-fragment layout (thread T: channel T/4 (+8), pixels 2(T%4),
+// 2(T%4)+1 - verified on B200 by tools/probes/probe_tmem_layout.cu), which is exactly the source fragment of
+// stmatrix.m8n8.trans: after bias + rounding, ONE stmatrix.x4.trans writes four 8x8 blocks transposed as 16-byte
+// (8-channel) row segments, conflict-free in the SWIZZLE_128B staging tile.  Per 32 x 32 chunk and warp: 2 TMEM loads,
+// 4 stmatrix - against 16 shuffles + 16 PRMT + 16 STS.32 of the lane-exchange epilogue.  The residual (when given) is
+// read back from the TMA-loaded staging tile with the mirror ldmatrix.x4.trans.  GroupNorm statistics are taken from
+// the fp32 values before rounding (four channels per thread, packed f32x2 adds).
+// ---------------------------------------------------------------------------------------------------------------------
+D3_DEVINL void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+D3_DEVINL void stmatrix_x4_trans(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b),
+               "r"(c), "r"(d)
+               : "memory");
+}
+D3_DEVINL void ldmatrix_x4_trans(uint32_t saddr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr)
+               : "memory");
+}
+
+// 16 channels (one TMEM half-quarter) x 32 pixels: v = the 16 registers of one tcgen05.ld.16x256b.x4.
+//   v[4i + 2hl + e] = D[channel base + T/4 + 8 hl][pixel 8i + 2(T%4) + e]
+// sa = this thread's stmatrix row address for pixel block i = 0 (blocks 2, 3 are 2048 B further down).
+template <int DT, bool HAS_RES, bool MASKED>
+D3_DEVINL void epi_t_stsm16(const uint32_t (&v)[16], uint32_t sa, float bias_lo, float bias_hi, uint32_t vmask,
+                            uint32_t t4, float2& s_lo, float2& q_lo, float2& s_hi, float2& q_hi) {
+#pragma unroll
+  for (int ii = 0; ii < 4; ii += 2) {
+    uint32_t pk[4];
+    uint32_t res[4];
+    if constexpr (HAS_RES) ldmatrix_x4_trans(sa + ii * 1024, res);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int i = ii + (m >> 1), hl = m & 1;
+      const float bsel = hl ? bias_hi : bias_lo;
+      float2 x = f2_add(make_float2(__uint_as_float(v[4 * i + 2 * hl]), __uint_as_float(v[4 * i + 2 * hl + 1])),
+                        make_float2(bsel, bsel));
+      if constexpr (HAS_RES) x = f2_add(x, unpack2<DT>(res[m]));
+      pk[m] = pack2<DT>(x.x, x.y);
+      if constexpr (MASKED) {
+        const uint32_t bit = 8u * i + 2u * t4;
+        x.x = ((vmask >> bit) & 1u) ? x.x : 0.f;
+        x.y = ((vmask >> (bit + 1)) & 1u) ? x.y : 0.f;
+      }
+      if (hl) stats_acc2(s_hi, q_hi, x); else stats_acc2(s_lo, q_lo, x);
+    }
+    stmatrix_x4_trans(sa + ii * 1024, pk[0], pk[1], pk[2], pk[3]);
+  }
+}
 
 // STRIPS = true ("halo blocks"): 3x3 stride-1 convs.  The pixel operand of a TH x TW tile (TW a multiple of 8, so one
 // tile row = TW*128 B is a whole number of 1024 B swizzle atoms) is loaded ONCE per (kw, 64-channel block) as a block of
@@ -570,7 +545,9 @@ constexpr int kMaxWts = 8;    // weight-tile ring slots (halo-block variant)
 // in the MMA itself (profiles/r01_conv_experiments.txt).  Activation TMA traffic drops by 3*TH/(TH+2).  Weights stream
 // through their own ring, fed by a second producer lane (warp 3).
 // K-loop order: for cb: for kw: block(kw, cb) -> for kh: weight tile (kh, kw, cb) -> 4 MMAs.
-template <int STAGES, int DT, bool STRIPS, bool MC = false>
+// EPI: 0 = lane-exchange epilogue (epi_t_chunk3), 1 = stmatrix epilogue (epi_t_stsm16; needs pass windows that start on
+// multiples of 8 accumulator columns, which the halo-block tiles guarantee).
+template <int STAGES, int DT, bool STRIPS, int EPI>
 __global__ void __launch_bounds__(kTThreads, 1)
 conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS1,
                     const __grid_constant__ CUtensorMap tmS2, const __grid_constant__ CUtensorMap tmB,
@@ -608,9 +585,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NBAR; ++i) {
       mbar_init(&full_bar[i], 1);
-      // MC: a weight slot is free again only when BOTH CTAs of the cluster have consumed it (each producer multicasts
-      // its half of the tile into both CTAs)
-      mbar_init(&empty_bar[i], (MC && STRIPS && i >= kMaxBlk) ? 2 : 1);
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -625,13 +600,8 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t crank = MC ? cluster_ctarank() : 0u;
-  const int w_first = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // work index of this CTA / cluster
-  const int w_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int w_count = MC ? a.numUnits : a.numTiles;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -641,13 +611,12 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t blk_bytes = (uint32_t)(a.TH + 2) * a.TW * 128u;
       const uint32_t plain_bytes = (uint32_t)a.TH * a.TW * 128u;
       const int n_items = 3 * a.cbMain + a.kbSc1 + a.kbSc2;  // block loads per tile
-      for (int tile = w_first; tile < w_count; tile += w_step) {
-        bool valid;
-        const TileCoord t = decode_work<MC>(a, tile, crank, valid);
+      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(a, tile, 128);
         for (int it = 0; it < n_items; ++it) {
           mbar_wait(&sempty[ss], sphase ^ 1);
           uint8_t* sS = smem + ss * a.blk_slot;
-          if (a.debug_skip & 1) {  // developer experiment: no activation loads
+          if (D3_DBG(a, 1)) {  // developer experiment: no activation loads
             mbar_arrive(&sfull[ss]);
           } else if (it < 3 * a.cbMain) {
             const int cb = it / 3, kw = it - cb * 3;
@@ -671,11 +640,11 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sW = smem + stage * kTStageBytes;
           uint8_t* sP = sW + kWTileBytes;
-          if (a.debug_skip & 3) {
-            const uint32_t bytes = ((a.debug_skip & 1) ? 0u : a.a_bytes) + ((a.debug_skip & 2) ? 0u : kWTileBytes);
+          if (D3_DBG(a, 3)) {
+            const uint32_t bytes = (D3_DBG(a, 1) ? 0u : a.a_bytes) + (D3_DBG(a, 2) ? 0u : kWTileBytes);
             if (bytes) mbar_arrive_expect_tx(&full_bar[stage], bytes); else mbar_arrive(&full_bar[stage]);
-            if (!(a.debug_skip & 1)) tma_load_4d(sP, &tmA, &full_bar[stage], 0, t.w0, t.h0, t.b);
-            if (!(a.debug_skip & 2)) tma_load_2d(sW, &tmB, &full_bar[stage], kb * 64, t.n0);
+            if (!D3_DBG(a, 1)) tma_load_4d(sP, &tmA, &full_bar[stage], 0, t.w0, t.h0, t.b);
+            if (!D3_DBG(a, 2)) tma_load_2d(sW, &tmB, &full_bar[stage], kb * 64, t.n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
@@ -716,26 +685,31 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t acc_phase = 0;
       const uint32_t row_bytes = (uint32_t)a.TW * 128u;
       const int n_items = 3 * a.cbMain + a.kbSc1 + a.kbSc2;
-      const bool prof = (a.debug_skip & 256) != 0;
+#ifdef D3_DEV
+      const bool prof = D3_DBG(a, 256) != 0;
       long long p_t0 = prof ? clock64() : 0, p_acc = 0, p_blk = 0, p_wts = 0, p_c = 0;
-      for (int tile = w_first; tile < w_count; tile += w_step) {
-        if (prof) p_c = clock64();
+#define D3_PROF(stmt) do { if (prof) { stmt; } } while (0)
+#else
+#define D3_PROF(stmt) do { } while (0)
+#endif
+      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+        D3_PROF(p_c = clock64());
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        if (prof) p_acc += clock64() - p_c;
+        D3_PROF(p_acc += clock64() - p_c);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         uint32_t first = 1;
         for (int it = 0; it < n_items; ++it) {
-          if (prof) p_c = clock64();
+          D3_PROF(p_c = clock64());
           mbar_wait(&sfull[ss], sphase);
-          if (prof) p_blk += clock64() - p_c;
+          D3_PROF(p_blk += clock64() - p_c);
           tc_fence_after();
           const uint32_t sS = smem_u32(smem + ss * a.blk_slot);
           const int nkb = (it < 3 * a.cbMain) ? 3 : 1;
           for (int i = 0; i < nkb; ++i) {
-            if (prof) p_c = clock64();
+            D3_PROF(p_c = clock64());
             mbar_wait(&wfull[ws], wphase);
-            if (prof) p_wts += clock64() - p_c;
+            D3_PROF(p_wts += clock64() - p_c);
             tc_fence_after();
             const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(wring + ws * kWTileBytes));
             // pixel window of tap kh = i: tile rows i .. i+TH-1 of the block (whole swizzle atoms further down)
@@ -745,8 +719,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
             }
             first = 0;
-            if constexpr (MC) umma_commit_mc(&wempty[ws], 3);   // frees the slot in both CTAs' weight producers
-            else umma_commit(&wempty[ws]);
+            umma_commit(&wempty[ws]);
             if (++ws == a.n_wts) { ws = 0; wphase ^= 1; }
           }
           umma_commit(&sempty[ss]);
@@ -756,12 +729,15 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+#ifdef D3_DEV
       if (prof) {
         atomicAdd(&g_conv_prof[0], (unsigned long long)(clock64() - p_t0));
         atomicAdd(&g_conv_prof[1], (unsigned long long)p_acc);
         atomicAdd(&g_conv_prof[2], (unsigned long long)p_blk);
         atomicAdd(&g_conv_prof[3], (unsigned long long)p_wts);
       }
+#endif
+#undef D3_PROF
     } else if (lane == 0) {
       const uint32_t idesc = make_idesc_16bit(kTileM, n_mma, DT == kBF16);
       int stage = 0;
@@ -799,9 +775,8 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int ws = 0;
       uint32_t wphase = 0;
       const int n_items = 3 * a.cbMain + a.kbSc1 + a.kbSc2;
-      for (int tile = w_first; tile < w_count; tile += w_step) {
-        bool valid;
-        const TileCoord t = decode_work<MC>(a, tile, crank, valid);
+      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(a, tile, 128);
         for (int it = 0; it < n_items; ++it) {
           int nkb = 1, kb0 = a.kbMain + (it - 3 * a.cbMain);
           if (it < 3 * a.cbMain) {
@@ -811,15 +786,11 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           for (int i = 0; i < nkb; ++i) {
             mbar_wait(&wempty[ws], wphase ^ 1);
-            if (a.debug_skip & 2) {
+            if (D3_DBG(a, 2)) {
               mbar_arrive(&wfull[ws]);
             } else {
-              mbar_arrive_expect_tx(&wfull[ws], kWTileBytes);   // own half + the peer's half
-              if constexpr (MC)
-                tma_load_2d_mc(wring + ws * kWTileBytes + crank * (kWTileBytes / 2), &tmB, &wfull[ws],
-                               (kb0 + i * 3 * a.cbMain) * 64, t.n0 + (int)crank * 64, 3);   // tmB box = 64 rows
-              else
-                tma_load_2d(wring + ws * kWTileBytes, &tmB, &wfull[ws], (kb0 + i * 3 * a.cbMain) * 64, t.n0);
+              mbar_arrive_expect_tx(&wfull[ws], kWTileBytes);
+              tma_load_2d(wring + ws * kWTileBytes, &tmB, &wfull[ws], (kb0 + i * 3 * a.cbMain) * 64, t.n0);
             }
             if (++ws == a.n_wts) { ws = 0; wphase ^= 1; }
           }
@@ -831,6 +802,15 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t q = (warp - 4) & 3;          // TMEM lane quarter this warp may access
     const uint32_t grp = (warp - 4) >> 2;       // the two groups take the two 32-pixel chunks of a pass
     const uint32_t et = threadIdx.x - 128;
+    const bool has_res = a.residual != nullptr;
+    // A pass = PW (<= 64) consecutive pixels of one tile row = a contiguous range of accumulator columns.  Staging is
+    // double-buffered by pass so the TMA store of pass p overlaps the math of pass p+1.
+    const int PW = a.pass_w;
+    const int PH = a.pass_h;                    // > 1 only for narrow tiles (TW < 64): a pass = PH whole tile rows
+    const int PN = PW * PH;                     // pixels (accumulator columns) per pass
+    const int segs = a.TW / PW;
+    const int passes = (a.TH / PH) * segs;
+    // ---- lane-exchange epilogue (EPI == 0): one channel per thread
     const uint32_t ch = q * 32 + lane;          // channel inside the 128-channel tile == TMEM lane
     const uint32_t half = ch >> 6;              // which 64-channel staging half
     const uint32_t ch16 = (ch & 63) >> 3;       // 16-byte chunk of this channel inside the 128-byte row
@@ -843,31 +823,48 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
     for (int i = 0; i < 4; ++i) myswz[i] = swz[i + (odd ? 4 : 0)];
     const uint32_t prmt_sel = odd ? 0x3276u : 0x5410u;  // see epi_t_chunk3
-    const bool has_res = a.residual != nullptr;
-    // A pass = PW (<= 64) consecutive pixels of one tile row = a contiguous range of accumulator columns.  Staging is
-    // double-buffered by pass so the TMA store of pass p overlaps the math of pass p+1.
-    const int PW = a.pass_w;
-    const int PH = a.pass_h;                    // > 1 only for narrow tiles (TW < 64): a pass = PH whole tile rows
-    const int PN = PW * PH;                     // pixels (accumulator columns) per pass
-    const int segs = a.TW / PW;
-    const int passes = (a.TH / PH) * segs;
+    // ---- stmatrix epilogue (EPI == 1): four channels per thread: 32q + 16 ab + 8 hl + lane/4
+    const uint32_t t4 = lane & 3, l4 = lane >> 2;
+    const uint32_t sm_m = lane >> 3, sm_j = lane & 7;       // stmatrix: this lane addresses row j of matrix m
+    uint32_t sm_off[2];                                     // per ab: row offset of this lane inside the staging buffer
+#pragma unroll
+    for (int ab = 0; ab < 2; ++ab) {
+      const uint32_t cb16 = (q & 1u) * 4u + 2u * ab + (sm_m & 1u);   // 16-byte channel chunk inside the 64-channel half
+      sm_off[ab] = (q >> 1) * (kStagingBytes / 2) + (8u * (sm_m >> 1) + sm_j) * 128u + ((cb16 ^ sm_j) << 4);
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t res_phase = 0;
     uint32_t pass_ctr = 0;
-    const bool prof = (a.debug_skip & 256) != 0 && et == 0;
+#ifdef D3_DEV
+    const bool prof = D3_DBG(a, 256) != 0 && et == 0;
     long long p_t0 = prof ? clock64() : 0, p_wait = 0, p_pass = 0, p_c = 0, p_tiles = 0;
     long long p_q[4] = {0, 0, 0, 0};
-    for (int tile = w_first; tile < w_count; tile += w_step) {
-      bool valid;
-      const TileCoord t = decode_work<MC>(a, tile, crank, valid);
-      const float bias = valid ? a.bias[(size_t)t.b * a.bias_bstride + t.n0 + ch] : 0.f;
-      float s_sum = 0.f, s_sq = 0.f;
-      if (prof) p_c = clock64();
+    long long q0 = 0, q1 = 0, q2c = 0, q3 = 0;
+#define D3_PROF(stmt) do { if (prof) { stmt; } } while (0)
+#else
+#define D3_PROF(stmt) do { } while (0)
+#endif
+    for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(a, tile, 128);
+      const float* bias_p = a.bias + (size_t)t.b * a.bias_bstride + t.n0;
+      const float bias = bias_p[ch];
+      float s_sum = 0.f, s_sq = 0.f;                                  // EPI 0
+      float b4[4];                                                    // EPI 1: bias of the thread's four channels
+      float2 s4[4], q4[4];                                            //        and their packed partial statistics
+      if constexpr (EPI == 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          b4[k] = bias_p[q * 32 + 8 * k + l4];
+          s4[k] = make_float2(0.f, 0.f);
+          q4[k] = make_float2(0.f, 0.f);
+        }
+      }
+      D3_PROF(p_c = clock64());
       mbar_wait(&tfull_bar[acc], acc_phase);
-      if (prof) { const long long n = clock64(); p_wait += n - p_c; p_c = n; ++p_tiles; }
+      D3_PROF(const long long n = clock64(); p_wait += n - p_c; p_c = n; ++p_tiles);
       tc_fence_after();
-      if (a.debug_skip & 4) {  // developer experiment: no epilogue work at all
+      if (D3_DBG(a, 4)) {  // developer experiment: no epilogue work at all
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -875,65 +872,13 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (acc == 0) acc_phase ^= 1;
         continue;
       }
-      if (a.t_direct) {
-        // direct-to-global epilogue: 32-pixel chunks of the tile's accumulator columns, alternating between groups
-        const int NPx = a.TH * a.TW;
-        for (int c0 = (int)grp * 32; c0 < NPx; c0 += 64) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * 256 + c0, v);
-          const int px = c0 + (int)lane;
-          const int pr = px / a.TW;
-          const int pw = px - pr * a.TW;
-          const bool ok = (px < NPx) && (t.h0 + pr < a.Ho) && (t.w0 + pw < a.Wo);
-          const uint32_t vmask = __ballot_sync(0xffffffffu, ok);
-          // pixel offset (in pixels) of chunk element j relative to element 0: contiguous inside a tile row
-          const int r0 = c0 / a.TW, w0c = c0 - r0 * a.TW;
-          const size_t pix0 = ((size_t)(t.b * a.Ho + t.h0 + r0) * a.Wo + t.w0 + w0c);
-          tmem_ld_wait();
-          if (w0c + 32 <= a.TW) {  // the 32 pixels of this chunk lie in one tile row: constant pixel stride
-            uint16_t* gp = a.out + pix0 * a.out_pitch + t.n0 + ch;
-            if (has_res) {
-              const uint16_t* rp = a.residual + pix0 * a.res_pitch + t.n0 + ch;
-              if (a.res_pitch == a.out_pitch)
-                epi_t_chunk_global<DT, true>(v, gp, rp, (size_t)a.out_pitch, bias, vmask, s_sum, s_sq);
-              else
-                for (int j = 0; j < 32; ++j)
-                  if ((vmask >> j) & 1u) {
-                    const float x = __uint_as_float(v[j]) + bias + unpack2<DT>((uint32_t)rp[(size_t)j * a.res_pitch]).x;
-                    const uint32_t pk = pack2<DT>(x, 0.f);
-                    gp[(size_t)j * a.out_pitch] = (uint16_t)pk;
-                    const float xr = unpack2<DT>(pk & 0xFFFFu).x;
-                    s_sum += xr; s_sq = fmaf(xr, xr, s_sq);
-                  }
-            } else {
-              epi_t_chunk_global<DT, false>(v, gp, nullptr, (size_t)a.out_pitch, bias, vmask, s_sum, s_sq);
-            }
-          } else {  // chunk straddles tile rows (narrow tiles): generic addressing
-            for (int j = 0; j < 32; ++j) {
-              if ((vmask >> j) & 1u) {
-                const int pxj = c0 + j, prj = pxj / a.TW, pwj = pxj - prj * a.TW;
-                const size_t pix = ((size_t)(t.b * a.Ho + t.h0 + prj) * a.Wo + t.w0 + pwj);
-                float x = __uint_as_float(v[j]) + bias;
-                if (has_res) x += unpack2<DT>((uint32_t)a.residual[pix * a.res_pitch + t.n0 + ch]).x;
-                const uint32_t pk = pack2<DT>(x, 0.f);
-                a.out[pix * a.out_pitch + t.n0 + ch] = (uint16_t)pk;
-                const float xr = unpack2<DT>(pk & 0xFFFFu).x;
-                s_sum += xr; s_sq = fmaf(xr, xr, s_sq);
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      } else
       for (int ps = 0; ps < passes; ++ps, ++pass_ctr) {
         const int r = (ps / segs) * PH;
         const int sg = ps - (ps / segs) * segs;
         const int h = t.h0 + r;
         const int wpass = t.w0 + sg * PW;
         uint8_t* sbuf = staging + (pass_ctr & 1) * kStagingBytes;  // two 64-channel halves of 64 rows each
-        long long q0 = prof ? clock64() : 0, q1 = 0, q2 = 0, q3 = 0;
+        D3_PROF(q0 = clock64());
         if (et == 0) {
           tma_store_wait_read<1>();  // the store that used this buffer two passes ago has finished reading it
           if (has_res) {
@@ -948,34 +893,51 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           res_phase ^= 1;
         }
         const int c0 = (int)grp * 32;
-        if (prof) q1 = clock64();
+        D3_PROF(q1 = clock64());
         if (c0 < PN) {
-          uint32_t v[32];
-          if (!(a.debug_skip & 64))
-            tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * 256 + r * a.TW + sg * PW + c0, v);
           const int pc = c0 + (int)lane;          // pixel of the pass; row pc / PW, column pc % PW (PH == 1: row 0)
           const int prow = (PH > 1) ? pc / PW : 0;
           const int pcol = pc - prow * PW;
-          const uint32_t vmask = __ballot_sync(
-              0xffffffffu, valid && (pc < PN) && (h + prow < a.Ho) && (wpass + pcol < a.Wo));
-          // word address of this lane's channel pair; odd lanes write 4 pixel rows further down (see epi_t_chunk2)
-          const uint32_t sa = smem_u32(sbuf) + half * (kStagingBytes / 2) + (uint32_t)c0 * 128u + (chb & ~3u) +
-                              (odd ? 512u : 0u);
-          // byte address of this lane's own channel at pixel row 0 of the chunk (residual read-back)
-          const uint32_t sa_own = smem_u32(sbuf) + half * (kStagingBytes / 2) + (uint32_t)c0 * 128u + chb;
-          tmem_ld_wait();
-          if (prof) q2 = clock64();
-          if (a.debug_skip & 32) {  // developer experiment: no epilogue math
-          } else if (a.debug_skip & 8) {
-            epi_t_chunk2<DT, false, 0, 0, true>(v, sa, myswz, bias, vmask, odd, s_sum, s_sq);
-          } else if (a.debug_skip & 16) {  // previous (select-based) epilogue, kept for A/B timing
-            if (has_res) epi_t_chunk2<DT, true>(v, sa, myswz, bias, vmask, odd, s_sum, s_sq);
-            else epi_t_chunk2<DT, false>(v, sa, myswz, bias, vmask, odd, s_sum, s_sq);
+          const uint32_t vmask = __ballot_sync(0xffffffffu, (pc < PN) && (h + prow < a.Ho) && (wpass + pcol < a.Wo));
+          const bool full = (vmask == 0xffffffffu);
+          const uint32_t tcol = tmem_base + ((q * 32) << 16) + acc * 256 + r * a.TW + sg * PW + c0;
+          if constexpr (EPI == 1) {
+            uint32_t va[16], vb[16];
+            tmem_ld_16x256b_x4(tcol, va);
+            tmem_ld_16x256b_x4(tcol + (16u << 16), vb);
+            const uint32_t sa = smem_u32(sbuf) + (uint32_t)c0 * 128u;
+            tmem_ld_wait();
+            D3_PROF(q2c = clock64());
+            if (D3_DBG(a, 32)) {  // developer experiment: no epilogue math
+            } else if (has_res) {
+              if (full) {
+                epi_t_stsm16<DT, true, false>(va, sa + sm_off[0], b4[0], b4[1], vmask, t4, s4[0], q4[0], s4[1], q4[1]);
+                epi_t_stsm16<DT, true, false>(vb, sa + sm_off[1], b4[2], b4[3], vmask, t4, s4[2], q4[2], s4[3], q4[3]);
+              } else {
+                epi_t_stsm16<DT, true, true>(va, sa + sm_off[0], b4[0], b4[1], vmask, t4, s4[0], q4[0], s4[1], q4[1]);
+                epi_t_stsm16<DT, true, true>(vb, sa + sm_off[1], b4[2], b4[3], vmask, t4, s4[2], q4[2], s4[3], q4[3]);
+              }
+            } else {
+              if (full) {
+                epi_t_stsm16<DT, false, false>(va, sa + sm_off[0], b4[0], b4[1], vmask, t4, s4[0], q4[0], s4[1], q4[1]);
+                epi_t_stsm16<DT, false, false>(vb, sa + sm_off[1], b4[2], b4[3], vmask, t4, s4[2], q4[2], s4[3], q4[3]);
+              } else {
+                epi_t_stsm16<DT, false, true>(va, sa + sm_off[0], b4[0], b4[1], vmask, t4, s4[0], q4[0], s4[1], q4[1]);
+                epi_t_stsm16<DT, false, true>(vb, sa + sm_off[1], b4[2], b4[3], vmask, t4, s4[2], q4[2], s4[3], q4[3]);
+              }
+            }
           } else {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tcol, v);
+            // word address of this lane's channel pair; odd lanes write 4 pixel rows further down (see epi_t_chunk3)
+            const uint32_t sa = smem_u32(sbuf) + half * (kStagingBytes / 2) + (uint32_t)c0 * 128u + (chb & ~3u) +
+                                (odd ? 512u : 0u);
+            // byte address of this lane's own channel at pixel row 0 of the chunk (residual read-back)
+            const uint32_t sa_own = smem_u32(sbuf) + half * (kStagingBytes / 2) + (uint32_t)c0 * 128u + chb;
+            tmem_ld_wait();
+            D3_PROF(q2c = clock64());
             float2 s2 = make_float2(s_sum, 0.f), q2 = make_float2(s_sq, 0.f);
-            const bool full = (vmask == 0xffffffffu);
-            if (a.debug_skip & 128) {  // developer experiment: no lane exchange (wrong results)
-              epi_t_chunk3<DT, false, false, 0, 0, true>(v, sa, myswz, sa_own, swz, bias, vmask, prmt_sel, s2, q2);
+            if (D3_DBG(a, 32)) {  // developer experiment: no epilogue math
             } else if (has_res) {
               if (full) epi_t_chunk3<DT, true, false>(v, sa, myswz, sa_own, swz, bias, vmask, prmt_sel, s2, q2);
               else epi_t_chunk3<DT, true, true>(v, sa, myswz, sa_own, swz, bias, vmask, prmt_sel, s2, q2);
@@ -987,7 +949,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             s_sq = q2.x + q2.y;
           }
         }
-        if (prof) q3 = clock64();
+        D3_PROF(q3 = clock64());
         if (ps == passes - 1) {
           tc_fence_before();
           __syncwarp();
@@ -995,33 +957,51 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 256);
-        if (et == 0 && !(a.debug_skip & 8)) {
+        if (et == 0 && !D3_DBG(a, 8)) {
           tma_store_4d(&tmO, sbuf, t.n0, wpass, h, t.b);
           tma_store_4d(&tmO, sbuf + kStagingBytes / 2, t.n0 + 64, wpass, h, t.b);
           tma_store_commit();
         }
-        if (prof) {
-          const long long q4 = clock64();
-          p_q[0] += q1 - q0; p_q[1] += q2 - q1; p_q[2] += q3 - q2; p_q[3] += q4 - q3;
-        }
+        D3_PROF(const long long q4c = clock64(); p_q[0] += q1 - q0; p_q[1] += q2c - q1; p_q[2] += q3 - q2c;
+                p_q[3] += q4c - q3);
       }
-      if (prof) p_pass += clock64() - p_c;
-      if (a.stats != nullptr && valid) {
-        // quad = 4 consecutive channels = 4 consecutive lanes
-        s_sum += __shfl_xor_sync(0xffffffffu, s_sum, 1);
-        s_sq += __shfl_xor_sync(0xffffffffu, s_sq, 1);
-        s_sum += __shfl_xor_sync(0xffffffffu, s_sum, 2);
-        s_sq += __shfl_xor_sync(0xffffffffu, s_sq, 2);
-        if ((lane & 3) == 0) {
-          double* dst = a.stats + ((size_t)t.b * (a.Cout >> 2) + ((t.n0 + ch) >> 2)) * 2;
-          atomicAdd(dst, (double)s_sum);
-          atomicAdd(dst + 1, (double)s_sq);
+      D3_PROF(p_pass += clock64() - p_c);
+      if (a.stats != nullptr) {
+        if constexpr (EPI == 1) {
+          // thread holds, for channels 32q + 8k + lane/4 (k = 0..3), partial sums over its pixel columns: reduce over
+          // the 4 lanes of a channel (xor 1, 2), then over the 4 channels of a quad (lane/4 = 4m..4m+3: xor 4, 8)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float s = s4[k].x + s4[k].y, qq = q4[k].x + q4[k].y;
+#pragma unroll
+            for (int off = 1; off <= 8; off <<= 1) {
+              s += __shfl_xor_sync(0xffffffffu, s, off);
+              qq += __shfl_xor_sync(0xffffffffu, qq, off);
+            }
+            if ((lane & 15u) == 0) {   // lane 0: channels 8k .. 8k+3 of the quarter; lane 16: channels 8k+4 .. 8k+7
+              double* dst = a.stats + ((size_t)t.b * (a.Cout >> 2) + ((t.n0 + q * 32 + 8 * k) >> 2) + (lane >> 4)) * 2;
+              atomicAdd(dst, (double)s);
+              atomicAdd(dst + 1, (double)qq);
+            }
+          }
+        } else {
+          // quad = 4 consecutive channels = 4 consecutive lanes
+          s_sum += __shfl_xor_sync(0xffffffffu, s_sum, 1);
+          s_sq += __shfl_xor_sync(0xffffffffu, s_sq, 1);
+          s_sum += __shfl_xor_sync(0xffffffffu, s_sum, 2);
+          s_sq += __shfl_xor_sync(0xffffffffu, s_sq, 2);
+          if ((lane & 3) == 0) {
+            double* dst = a.stats + ((size_t)t.b * (a.Cout >> 2) + ((t.n0 + ch) >> 2)) * 2;
+            atomicAdd(dst, (double)s_sum);
+            atomicAdd(dst + 1, (double)s_sq);
+          }
         }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
     if (et == 0) tma_store_wait_all<0>();
+#ifdef D3_DEV
     if (prof) {
       atomicAdd(&g_conv_prof[4], (unsigned long long)(clock64() - p_t0));
       atomicAdd(&g_conv_prof[5], (unsigned long long)p_wait);
@@ -1029,11 +1009,12 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       atomicAdd(&g_conv_prof[7], (unsigned long long)p_tiles);
       for (int i = 0; i < 4; ++i) atomicAdd(&g_conv_prof[8 + i], (unsigned long long)p_q[i]);
     }
+#endif
+#undef D3_PROF
   }
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC) cluster_sync_all();   // no CTA leaves while its peer can still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -1052,52 +1033,24 @@ inline size_t conv_ts_smem_bytes(const ConvKArgs& a) {
 template <int STAGES, int DT>
 cudaError_t launch_conv_t(int grid, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmS1,
                           const CUtensorMap& tmS2, const CUtensorMap& tmB, const CUtensorMap& tmO,
-                          const CUtensorMap& tmR, const ConvKArgs& a, bool strips, bool mc) {
-  if (strips && mc) {
-    // 2-CTA clusters sharing every weight tile through TMA multicast; grid = 2 x clusters
-    const size_t smem = conv_ts_smem_bytes(a);
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-      cudaError_t e = cudaFuncSetAttribute(conv_igemm_t_kernel<STAGES, DT, true, true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      attr_smem = smem;
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kTThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, conv_igemm_t_kernel<STAGES, DT, true, true>, tmA, tmS1, tmS2, tmB, tmO, tmR, a);
-  }
+                          const CUtensorMap& tmR, const ConvKArgs& a, bool strips, int epi) {
   if (strips) {
     const size_t smem = conv_ts_smem_bytes(a);
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-      cudaError_t e = cudaFuncSetAttribute(conv_igemm_t_kernel<STAGES, DT, true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (epi == 1) {
+      cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(conv_igemm_t_kernel<STAGES, DT, true, 1>), smem);
       if (e != cudaSuccess) return e;
-      attr_smem = smem;
+      conv_igemm_t_kernel<STAGES, DT, true, 1><<<grid, kTThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, tmR, a);
+    } else {
+      cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(conv_igemm_t_kernel<STAGES, DT, true, 0>), smem);
+      if (e != cudaSuccess) return e;
+      conv_igemm_t_kernel<STAGES, DT, true, 0><<<grid, kTThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, tmR, a);
     }
-    conv_igemm_t_kernel<STAGES, DT, true><<<grid, kTThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, tmR, a);
     return cudaSuccess;
   }
   constexpr size_t smem = conv_t_smem_bytes<STAGES>();
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_t_kernel<STAGES, DT, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  conv_igemm_t_kernel<STAGES, DT, false><<<grid, kTThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, tmR, a);
+  cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(conv_igemm_t_kernel<STAGES, DT, false, 0>), smem);
+  if (e != cudaSuccess) return e;
+  conv_igemm_t_kernel<STAGES, DT, false, 0><<<grid, kTThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, tmR, a);
   return cudaSuccess;
 }
 
@@ -1141,281 +1094,6 @@ void choose_tile_t(int Ho, int Wo, int* TH, int* TW) {
   *TW = bw;
 }
 
-
-// =====================================================================================================================
-// CTA-pair variant (cta_group::2) of the pixels-as-M kernel: two CTAs of a cluster own two adjacent pixel tiles
-// (M = 256 = 2 x 128 rows) and each keeps only HALF of the weight tile (BN/2 output channels) in shared memory; one
-// tcgen05.mma.cta_group::2 issued by the leader drives both SMs.  Per CTA the weight operand costs half the TMA
-// writes and half the operand reads of the single-CTA kernel, which is what the shared-memory port is short of
-// (profiles/r01_conv_experiments.txt).
-// =====================================================================================================================
-template <int BN, int STAGES, int DT>
-__global__ void __launch_bounds__(kThreads, 1)
-conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmS1,
-                   const __grid_constant__ CUtensorMap tmS2, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmO, const ConvKArgs a) {
-  constexpr uint32_t kBHalfBytes = (BN / 2) * 128;
-  constexpr uint32_t kStageBytes = kATileBytes + kBHalfBytes;
-  constexpr uint32_t kTmemCols = 2 * BN;
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* staging = smem + STAGES * kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* spart = reinterpret_cast<float*>(tmem_ptr + 4);  // [4][32]
-
-  const uint32_t warp = threadIdx.x >> 5;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();       // 0 = leader (issues the MMAs), 1 = peer
-  const int pair = blockIdx.x >> 1;
-  const int npairs_grid = gridDim.x >> 1;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmO);
-    if (a.kbSc1) tma_prefetch_desc(&tmS1);
-    if (a.kbSc2) tma_prefetch_desc(&tmS2);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);   // leader's producer arrival (+ the bytes of both CTAs)
-      mbar_init(&empty_bar[i], 1);  // multicast commit from the leader's MMA lane
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull_bar[i], 1);   // multicast commit
-      mbar_init(&tempty_bar[i], 8);  // 4 epilogue warps of each CTA (only the leader's copy is waited on)
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) {
-    tmem_alloc2(tmem_ptr, kTmemCols);
-    tmem_relinquish2();
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  // pair-tile decode: pixel tiles 2*pp + rank share the weight tile nt
-  auto decode = [&](int tp, TileCoord& t) -> bool {
-    const int nt = tp % a.nTilesN;
-    const int pp = tp / a.nTilesN;
-    int p = 2 * pp + (int)rank;
-    const int pixTiles = a.B * a.tilesH * a.tilesW;
-    const bool real = p < pixTiles;
-    if (!real) p = pixTiles;  // decodes to b == B: every TMA coordinate out of range (zero fill / clipped store)
-    const int tw = p % a.tilesW;
-    const int q = p / a.tilesW;
-    const int th = q % a.tilesH;
-    t.b = q / a.tilesH;
-    t.h0 = th * a.TH;
-    t.w0 = tw * a.TW;
-    t.n0 = nt * BN;
-    return real;
-  };
-
-  if (warp == 0) {
-    // ================================ TMA producer (both CTAs) ================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tp = pair; tp < a.numPairs; tp += npairs_grid) {
-        TileCoord t;
-        decode(tp, t);
-        for (int kb = 0; kb < a.kbTotal; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sA = smem + stage * kStageBytes;
-          uint8_t* sB = sA + kATileBytes;
-          if (a.debug_skip & 3) {
-            const uint32_t bytes = ((a.debug_skip & 1) ? 0u : a.a_bytes) + ((a.debug_skip & 2) ? 0u : kBHalfBytes);
-            if (rank == 0) { if (bytes) mbar_arrive_expect_tx(&full_bar[stage], 2u * bytes); else mbar_arrive(&full_bar[stage]); }
-            if (!(a.debug_skip & 1)) tma_load_4d_2cta(sA, &tmA, &full_bar[stage], 0, t.w0, t.h0, t.b);
-            if (!(a.debug_skip & 2)) tma_load_2d_2cta(sB, &tmB, &full_bar[stage], kb * 64, t.n0 + (int)rank * (BN / 2));
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            continue;
-          }
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (a.a_bytes + kBHalfBytes));
-          if (kb < a.kbMain) {
-            const int tap = kb / a.cbMain;
-            const int cb = kb - tap * a.cbMain;
-            if (a.stride == 1) {
-              tma_load_4d_2cta(sA, &tmA, &full_bar[stage], cb * 64, t.w0 + a.tap_dw[tap], t.h0 + a.tap_dh[tap], t.b);
-            } else {
-              const int kh = tap / a.ksize;
-              const int kw = tap - kh * a.ksize;
-              const int dh = kh - 1, dw = kw - 1;
-              const int hh = t.h0 + (dh < 0 ? -1 : 0), ph = (dh == 0) ? 0 : 1;
-              const int ww = t.w0 + (dw < 0 ? -1 : 0), pw = (dw == 0) ? 0 : 1;
-              tma_load_5d_2cta(sA, &tmA, &full_bar[stage], pw * a.sc_off2 + cb * 64, ww, ph, hh, t.b);
-            }
-          } else if (kb < a.kbMain + a.kbSc1) {
-            tma_load_4d_2cta(sA, &tmS1, &full_bar[stage], (kb - a.kbMain) * 64, t.w0, t.h0, t.b);
-          } else {
-            tma_load_4d_2cta(sA, &tmS2, &full_bar[stage], (kb - a.kbMain - a.kbSc1) * 64, t.w0, t.h0, t.b);
-          }
-          // this CTA's half of the weight tile: output channels n0 + rank*BN/2 ...
-          tma_load_2d_2cta(sB, &tmB, &full_bar[stage], kb * 64, t.n0 + (int)rank * (BN / 2));
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================================ MMA issuer (leader CTA only) ================================
-    if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_16bit(256, BN, DT == kBF16);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tp = pair; tp < a.numPairs; tp += npairs_grid) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < a.kbTotal; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sA = smem_u32(smem + stage * kStageBytes);
-          const uint64_t adesc = make_sw128_kmajor_desc(sA);
-          const uint64_t bdesc = make_sw128_kmajor_desc(sA + kATileBytes);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_bf16_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit_2cta_mc(&empty_bar[stage], 0x3);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        umma_commit_2cta_mc(&tfull_bar[acc], 0x3);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    }
-  } else if (warp >= 4) {
-    // ================================ epilogue (both CTAs, own 128 rows) ================================
-    const uint32_t q = warp - 4;
-    const uint32_t et = threadIdx.x - 128;
-    const uint32_t r = q * 32 + lane;
-    const int th = r / a.TW;
-    const int tw = r - th * a.TW;
-    const uint32_t tempty_leader0 = mapa_u32(smem_u32(&tempty_bar[0]), 0);
-    const uint32_t tempty_leader1 = mapa_u32(smem_u32(&tempty_bar[1]), 0);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    uint32_t chunk_ctr = 0;
-    for (int tp = pair; tp < a.numPairs; tp += npairs_grid) {
-      TileCoord t;
-      const bool real = decode(tp, t);
-      const int h = t.h0 + th, w = t.w0 + tw;
-      const bool valid = real && (th < a.TH) && (h < a.Ho) && (w < a.Wo);
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      if (a.debug_skip & 4) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-        continue;
-      }
-#pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
-        uint32_t v0[32], v1[32];
-        {
-          const uint32_t taddr = tmem_base + ((q * 32) << 16) + acc * BN + c * 64;
-          tmem_ld_32x32b_x32(taddr, v0);
-          tmem_ld_32x32b_x32(taddr + 32, v1);
-          tmem_ld_wait();
-        }
-        if (c == BN / 64 - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
-        }
-        uint8_t* sbuf = staging + (chunk_ctr & 1) * kStagingBytes;
-        if (et == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
-        const int n_base = t.n0 + c * 64;
-        const int bb = real ? t.b : 0;
-        const float4* bp = reinterpret_cast<const float4*>(a.bias + (size_t)bb * a.bias_bstride + n_base);
-        const uint4* rp = nullptr;
-        if (a.residual != nullptr && valid) {
-          rp = reinterpret_cast<const uint4*>(a.residual + ((size_t)(t.b * a.Ho + h) * a.Wo + w) * a.res_pitch +
-                                              n_base);
-        }
-        float sums[32];
-        epi_process32<0, DT>(v0, sums, bp, rp, valid, sbuf, r);
-        epi_process32<1, DT>(v1, sums, bp, rp, valid, sbuf, r);
-        if (a.stats != nullptr) {
-          const float tot = warp_transpose_reduce32(sums, lane);
-          spart[q * 32 + lane] = tot;
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(2, 128);
-        if (et == 0) {
-          tma_store_4d(&tmO, sbuf, n_base, t.w0, t.h0, t.b);
-          tma_store_commit();
-        }
-        if (a.stats != nullptr && et < 32 && real) {
-          const float tot = spart[et] + spart[32 + et] + spart[64 + et] + spart[96 + et];
-          const int quad = (n_base >> 2) + (et & 15);
-          atomicAdd(a.stats + ((size_t)t.b * (a.Cout >> 2) + quad) * 2 + (et >> 4), static_cast<double>(tot));
-        }
-        ++chunk_ctr;
-      }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-    if (et == 0) tma_store_wait_all<0>();
-  }
-
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc2(tmem_base, kTmemCols);
-  }
-}
-
-template <int BN, int STAGES>
-constexpr size_t conv2_smem_bytes() {
-  return 1024 + STAGES * (kATileBytes + (BN / 2) * 128) + 2 * kStagingBytes + (2 * STAGES + 4) * 8 + 16 + 4 * 32 * 4;
-}
-
-template <int BN, int STAGES, int DT>
-cudaError_t launch_conv2(int npairs_grid, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmS1,
-                         const CUtensorMap& tmS2, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvKArgs& a) {
-  constexpr size_t smem = conv2_smem_bytes<BN, STAGES>();
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm2_kernel<BN, STAGES, DT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * npairs_grid);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<BN, STAGES, DT>, tmA, tmS1, tmS2, tmB, tmO, a);
-}
 
 // Split-K finalize: out = round(sum_s ws[s] + bias (+ residual)), GroupNorm quad statistics of the rounded values.
 // Thread = one pixel slot x 8 channels; blockDim.x = (Cout / 8) * k.
@@ -1496,13 +1174,8 @@ template <int BN, int STAGES, int DT>
 cudaError_t launch_conv(int grid, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmS1,
                         const CUtensorMap& tmS2, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvKArgs& a) {
   constexpr size_t smem = conv_smem_bytes<BN, STAGES>();
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, DT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(conv_igemm_kernel<BN, STAGES, DT>), smem);
+  if (e != cudaSuccess) return e;
   conv_igemm_kernel<BN, STAGES, DT><<<grid, kThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, a);
   return cudaSuccess;
 }
@@ -1571,8 +1244,9 @@ extern "C" size_t d3_conv2d_workspace_bytes(const d3_conv_params* p) {
   return (size_t)S * p->B * (p->H / p->stride) * (p->W / p->stride) * p->Cout * sizeof(float);
 }
 
-// Developer hook (not part of include/d3roma_b200.h): read (and optionally clear) the cycle counters collected while
-// D3_CONV_DEBUG_SKIP has bit 256 set.
+#ifdef D3_DEV
+// Developer hook (D3_DEV builds only; not part of include/d3roma_b200.h): read (and optionally clear) the cycle
+// counters collected while D3_CONV_DEBUG_SKIP has bit 256 set.
 extern "C" int d3_debug_conv_profile(unsigned long long* out16, int reset) {
   if (out16 && cudaMemcpyFromSymbol(out16, d3::g_conv_prof, sizeof(d3::g_conv_prof)) != cudaSuccess) return 1;
   if (reset) {
@@ -1581,6 +1255,7 @@ extern "C" int d3_debug_conv_profile(unsigned long long* out16, int reset) {
   }
   return 0;
 }
+#endif
 
 extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   using namespace d3;
@@ -1715,11 +1390,14 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   a.res_pitch = p->res_pitch;
   a.stats = p->stats;
   a.a_bytes = static_cast<uint32_t>(a.TH * a.TW * 128);
+  a.debug_skip = 0;
+#ifdef D3_DEV
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("D3_CONV_DEBUG_SKIP"); dbg = e ? atoi(e) : 0; }
     a.debug_skip = dbg;
   }
+#endif
   D3_REQUIRE((p->sc1 ? p->C1 : 0) + (p->sc2 ? p->C2 : 0) == p->C1 + p->C2, "conv: C1/C2 set without pointers");
 
   CUtensorMap tmA, tmS1, tmS2, tmB, tmO, tmR;
@@ -1728,13 +1406,6 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   a.pass_h = (use_strips && a.TW < 64) ? 64 / a.TW : 1;
   if (use_t && !use_strips)
     D3_REQUIRE(t_tile_windows_ok(a.TH, a.TW), "conv: internal error: tile %dx%d overruns the accumulator", a.TH, a.TW);
-  {
-    static int td = -1;
-    if (td < 0) { const char* e = getenv("D3_CONV_T_DIRECT"); td = e ? atoi(e) : 0; }
-    a.t_direct = (use_t && phase == 0) ? td : 0;
-  }
-  a.out = static_cast<uint16_t*>(p->out);
-  a.out_pitch = p->out_pitch;
   const int store_rows = use_t ? a.pass_h : a.TH;        // rows per TMA store box
   const int store_cols = use_t ? a.pass_w : a.TW;        // pixels per row of the TMA store box
   if (p->stride == 1) {
@@ -1804,46 +1475,15 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
 
   int grid = a.numTiles * a.splitK < num_sms() ? a.numTiles * a.splitK : num_sms();
   cudaError_t le = cudaSuccess;
-  // weight multicast: 2-CTA clusters of the halo-block kernel share every weight tile (each CTA fetches half of it and
-  // multicasts) - halves the L2 -> SM weight traffic.  D3_CONV_MC=1 to enable.
-  static int want_mc = -1;
-  if (want_mc < 0) { const char* e = getenv("D3_CONV_MC"); want_mc = e ? atoi(e) : 0; }
-  const bool use_mc = use_strips && want_mc && !a.t_direct && pixTiles >= 4;
-  if (use_mc) {
-    a.pixTiles = pixTiles;
-    a.numUnits = ((pixTiles + 1) / 2) * a.nTilesN;
-    const int max_clusters = num_sms() / 2;
-    grid = 2 * (a.numUnits < max_clusters ? a.numUnits : max_clusters);
-    uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)p->Cout};
-    uint64_t str[1] = {(uint64_t)Ktot * 2};
-    uint32_t box[2] = {64, 64};
-    if ((rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmB, p->w, 2, dims, str, box)))
-      return set_error(D3_ERR_CUDA, "conv: tensor map B(multicast half) encode failed (%d)", rc);
-  }
-  static int use_2cta = -1;
-  if (use_2cta < 0) { const char* e = getenv("D3_CONV_2CTA"); use_2cta = e ? atoi(e) : 0; }
-  a.numPairs = ((pixTiles + 1) / 2) * a.nTilesN;
-  if (!use_t && use_2cta && a.numPairs >= 8 && a.splitK == 1) {
-    // B-operand box covers this CTA's half of the weight tile
-    uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)p->Cout};
-    uint64_t str[1] = {(uint64_t)Ktot * 2};
-    uint32_t box[2] = {64, (uint32_t)(BN / 2)};
-    if ((rc = make_tmap_16bit(p->dtype == D3_DTYPE_F16, &tmB, p->w, 2, dims, str, box)))
-      return set_error(D3_ERR_CUDA, "conv: tensor map B(half) encode failed (%d)", rc);
-    const int max_pairs = num_sms() / 2;
-    const int npg = a.numPairs < max_pairs ? a.numPairs : max_pairs;
-    if (BN == 128 && p->dtype == D3_DTYPE_BF16)
-      le = launch_conv2<128, 6, kBF16>(npg, stream, tmA, tmS1, tmS2, tmB, tmO, a);
-    else if (BN == 128)
-      le = launch_conv2<128, 6, kF16>(npg, stream, tmA, tmS1, tmS2, tmB, tmO, a);
-    else if (p->dtype == D3_DTYPE_BF16)
-      le = launch_conv2<256, 5, kBF16>(npg, stream, tmA, tmS1, tmS2, tmB, tmO, a);
-    else
-      le = launch_conv2<256, 5, kF16>(npg, stream, tmA, tmS1, tmS2, tmB, tmO, a);
-  } else if (use_t && p->dtype == D3_DTYPE_BF16)
-    le = launch_conv_t<4, kBF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, tmR, a, use_strips, use_mc);
+  // epilogue of the halo-block kernel: 1 = stmatrix transposing epilogue (default), 0 = lane-exchange epilogue
+  // (D3_CONV_EPI, a routing override for A/B measurements; both are parity-tested)
+  static int want_epi = -1;
+  if (want_epi < 0) { const char* e = getenv("D3_CONV_EPI"); want_epi = e ? atoi(e) : 1; }
+  const int epi = (use_strips && want_epi) ? 1 : 0;
+  if (use_t && p->dtype == D3_DTYPE_BF16)
+    le = launch_conv_t<4, kBF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, tmR, a, use_strips, epi);
   else if (use_t)
-    le = launch_conv_t<4, kF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, tmR, a, use_strips, use_mc);
+    le = launch_conv_t<4, kF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, tmR, a, use_strips, epi);
   else if (BN == 128 && p->dtype == D3_DTYPE_BF16)
     le = launch_conv<128, 5, kBF16>(grid, stream, tmA, tmS1, tmS2, tmB, tmO, a);
   else if (BN == 128)

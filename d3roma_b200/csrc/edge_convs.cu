@@ -107,7 +107,8 @@ struct ConvInArgs {
   const float* planes;  // [B, C, H, W] fp32
   int C;
   const float* wT;      // [C*9][128] fp32, k = c*9 + tap
-  const float* base;    // [B,H,W,128] fp32 or nullptr
+  const void* base;     // [B,H,W,128] fp32 (base_f16 == 0) or fp16 (base_f16 == 1), or nullptr
+  int base_f16;
   const float* bias;    // [128] or nullptr (added when base == nullptr)
   float* out32;         // OUT32 mode
   uint16_t* out16;      // OUT16 mode
@@ -142,8 +143,23 @@ __global__ void __launch_bounds__(256, 2) conv_in_direct_kernel(const ConvInArgs
       for (int j = 0; j < 8; ++j) acc[p][j] = bias8[j];
     // issue the loads of the per-loop term first so that they are in flight during the tap arithmetic
     float4 bv[kCiPx][2];
-    if (a.base != nullptr) {
-      const float* bp = a.base + (((size_t)b * a.H + h) * a.W + w0) * 128 + oct * 8;
+    if (a.base != nullptr && a.base_f16) {
+      // 16-bit per-loop term (fp16 in both operand modes: |values| = O(1), 11 significant bits - below the rounding of
+      // the 16-bit activation this kernel stores): (2 + 2) * 128 * P bytes per step instead of (4 + 2) * 128 * P
+      const __half* bp = static_cast<const __half*>(a.base) + (((size_t)b * a.H + h) * a.W + w0) * 128 + oct * 8;
+#pragma unroll
+      for (int p = 0; p < kCiPx; ++p) {
+        if (w0 + p < a.W) {
+          const uint4 u = __ldcs(reinterpret_cast<const uint4*>(bp + (size_t)p * 128));
+          const float2 f0 = unpack2<kF16>(u.x), f1 = unpack2<kF16>(u.y), f2 = unpack2<kF16>(u.z), f3 = unpack2<kF16>(u.w);
+          bv[p][0] = make_float4(f0.x, f0.y, f1.x, f1.y);
+          bv[p][1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+        } else {
+          bv[p][0] = bv[p][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    } else if (a.base != nullptr) {
+      const float* bp = static_cast<const float*>(a.base) + (((size_t)b * a.H + h) * a.W + w0) * 128 + oct * 8;
 #pragma unroll
       for (int p = 0; p < kCiPx; ++p) {
         if (w0 + p < a.W) {
@@ -469,16 +485,19 @@ extern "C" int d3_conv_out_fused(const void* x, int pitch, const double* stats, 
   return D3_OK;
 }
 
-extern "C" int d3_conv_in_direct(const float* planes, int C, const float* wT, const float* base, const float* bias,
-                                 int B, int H, int W, float* out32, void* out16, int dtype, double* stats,
-                                 void* stream) {
+extern "C" int d3_conv_in_direct(const float* planes, int C, const float* wT, const void* base, int base_dtype,
+                                 const float* bias, int B, int H, int W, float* out32, void* out16, int dtype,
+                                 double* stats, void* stream) {
   using namespace d3;
   D3_REQUIRE(planes && wT, "conv_in_direct: null pointer");
   D3_REQUIRE(C >= 1 && C <= 12, "conv_in_direct: C must be in [1, 12] (got %d)", C);
   D3_REQUIRE((out32 != nullptr) != (out16 != nullptr), "conv_in_direct: exactly one of out32 / out16 must be given");
   D3_REQUIRE(out32 || dtype == D3_DTYPE_BF16 || dtype == D3_DTYPE_F16, "conv_in_direct: bad dtype %d", dtype);
   D3_REQUIRE(base || bias, "conv_in_direct: base or bias required");
-  ConvInArgs a{planes, C, wT, base, bias, out32, static_cast<uint16_t*>(out16), stats, B, H, W};
+  D3_REQUIRE(!base || base_dtype == D3_DTYPE_F32 || base_dtype == D3_DTYPE_F16,
+             "conv_in_direct: base must be fp32 or fp16 (got dtype %d)", base_dtype);
+  ConvInArgs a{planes, C, wT, base, base_dtype == D3_DTYPE_F16 ? 1 : 0, bias, out32, static_cast<uint16_t*>(out16),
+               stats, B, H, W};
   const int items = H * ((W + kCiSeg - 1) / kCiSeg);
   int gx = (num_sms() * 4 + B - 1) / B;
   if (gx > items) gx = items;
@@ -486,14 +505,10 @@ extern "C" int d3_conv_in_direct(const float* planes, int C, const float* wT, co
   dim3 grid(gx, B);
   const size_t smem = (size_t)C * 9 * 128 * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    const int mx = 12 * 9 * 128 * 4;
-    D3_CHECK_CUDA(cudaFuncSetAttribute(conv_in_direct_kernel<kBF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    D3_CHECK_CUDA(cudaFuncSetAttribute(conv_in_direct_kernel<kBF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    D3_CHECK_CUDA(cudaFuncSetAttribute(conv_in_direct_kernel<kF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    attr_set = true;
-  }
+  const size_t mx = 12 * 9 * 128 * 4;
+  D3_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_in_direct_kernel<kBF16, true>), mx));
+  D3_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_in_direct_kernel<kBF16, false>), mx));
+  D3_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_in_direct_kernel<kF16, false>), mx));
   if (out32) conv_in_direct_kernel<kBF16, true><<<grid, 256, smem, st>>>(a);
   else if (dtype == D3_DTYPE_BF16) conv_in_direct_kernel<kBF16, false><<<grid, 256, smem, st>>>(a);
   else conv_in_direct_kernel<kF16, false><<<grid, 256, smem, st>>>(a);

@@ -439,11 +439,7 @@ int groupnorm_f32(const void* x1, int C1, int p1, const double* stats1, const vo
 int attention_f32(const void* qkv, int pitch, int B, int N, int C, void* out, int opitch, cudaStream_t stream) {
   const size_t smem = (size_t)N * 64;
   D3_REQUIRE(smem <= 220 * 1024, "attention(f32): N=%d exceeds the shared-memory K/V budget", N);
-  static size_t configured = 0;
-  if (smem > configured) {
-    D3_CHECK_CUDA(cudaFuncSetAttribute(attention_hd8_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  D3_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(attention_hd8_f32_kernel), smem));
   dim3 grid(ceil_div(N, 256), C / 8, B);
   attention_hd8_f32_kernel<<<grid, 256, smem, stream>>>(static_cast<const float*>(qkv), pitch, C, N,
                                                         static_cast<float*>(out), opitch);

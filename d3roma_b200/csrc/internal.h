@@ -10,7 +10,10 @@ namespace d3 {
 
 int set_error(int code, const char* fmt, ...);
 void count_launch(int n = 1);
-int num_sms();
+int num_sms();  // SM count of the CURRENT device
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel, size): the attribute is per device, so
+// the cache is too (one process may drive several GPUs).
+cudaError_t ensure_dyn_smem(const void* func, size_t bytes);
 
 #define D3_CHECK_CUDA(expr)                                                                   \
   do {                                                                                        \

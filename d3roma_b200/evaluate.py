@@ -5,6 +5,7 @@ the pipeline (:90-104) -> unpad (:103) -> denormalise (:122) -> mean over rounds
 """
 from __future__ import annotations
 
+import functools
 from typing import Optional
 
 import torch
@@ -53,13 +54,24 @@ def eval_batch(config, pipeline, disable_bar=True, fxb=None, normalized_rgb=None
     if getattr(config, "ensemble", False):
         raise NotImplementedError("ensemble_depths (scipy optimisation, utils.py:346-460) is not implemented")
     preds, out = [], None
+    denorm = functools.partial(denormalize, config)                            # evaluate.py:76
     for r in range(config.num_inference_rounds):
         pipeline.set_progress_bar_config(desc=f"Denoising, round={r}", disable=disable_bar)
         out = pipeline(p_rgb, p_left, p_right, p_sim, p_raw, mask, num_inference_steps=config.num_inference_timesteps,
                        num_intermediate_images=config.num_intermediate_images, add_noise_rgb=config.noise_rgb,
-                       depth_channels=config.depth_channels, cond_channels=config.cond_channels, generator=generator)
+                       depth_channels=config.depth_channels, cond_channels=config.cond_channels, denorm=denorm,
+                       generator=generator)
         out.images = padder.unpad(out.images)
         preds.append(out.images)
+    # only the last round's intermediates are kept, unpadded and denormalised like the reference's (evaluate.py:105-110);
+    # the pipeline aliases one stack five times, so it is converted once and every field gets its own handle on the result
+    if out.images_pred_orig is not None:
+        inter = denorm(padder.unpad(out.images_pred_orig), raw_disp, mask)
+        out.images_pred_orig = inter
+        out.images_perturbed_orig = inter.clone()
+        out.images_pred_prev = inter.clone()
+        out.images_sampled_prev = inter.clone()
+        out.images_purturbed_pred_prev = inter.clone()
     pred_disps = torch.cat(preds, dim=1)                                       # [B, R*dc, H, W]
     pred_un = denormalize(config, pred_disps, raw_disp, mask).mean(dim=1)      # [B, H, W]
     gt = raw_disp.squeeze(1)
@@ -101,7 +113,7 @@ def denoise_batch(pipeline, normalizer: Normalizer, *, rgb=None, left=None, righ
     for _ in range(num_inference_rounds):
         out = pipeline(rgb, left, right, sim_disp, raw_depth, mask, num_inference_steps=num_inference_steps,
                        num_intermediate_images=num_intermediate_images, depth_channels=depth_channels,
-                       cond_channels=cond_channels, generator=generator)
+                       cond_channels=cond_channels, denorm=normalizer.denormalize, generator=generator)
         preds.append(padder.unpad(out.images))
     pred = torch.cat(preds, dim=1)                       # [B, R*dc, h, w]  (evaluate.py:113)
     disp = normalizer.denormalize(pred)                  # [B, R, h, w]

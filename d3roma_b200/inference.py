@@ -120,7 +120,8 @@ class D3RoMa:
         out = self.pipeline(rep(n_rgb), rep(n_left), rep(n_right), rep(n_raw), rep(raw_disp), rep(mask),
                             num_inference_steps=cfg.num_inference_timesteps,
                             num_intermediate_images=cfg.num_intermediate_images, add_noise_rgb=cfg.noise_rgb,
-                            depth_channels=cfg.depth_channels, cond_channels=cfg.cond_channels)
+                            depth_channels=cfg.depth_channels, cond_channels=cfg.cond_channels,
+                            denorm=self.normer.denormalize)                      # inference.py:214-223
         pred = padder.unpad(out.images)                                          # [R, dc, H, W]
         disp = self.normer.denormalize(pred, rep(raw_disp), rep(mask))           # inference.py:232
         disp = disp.mean(dim=0, keepdim=True).mean(dim=1)                        # rounds (and dc replicas) -> [1, H, W]

@@ -202,25 +202,31 @@ def conv_in_direct(planes: torch.Tensor, wT: torch.Tensor, *, base: Optional[tor
                    bias: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
                    out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Direct 3x3 conv of fp32 NCHW ``planes`` [B,C,H,W] with 128 output channels (``d3_conv_in_direct``).
-    ``out_dtype=None``: fp32 NHWC result (the per-loop conditioning term, ``bias`` added).  ``out_dtype`` bf16/fp16:
-    ``base`` (fp32 NHWC) + conv, rounded, plus GroupNorm quad statistics into ``stats``."""
+    ``out_dtype=None``: fp32 NHWC result (``bias`` added).  ``out_dtype`` bf16/fp16: (``base`` or ``bias``) + conv,
+    rounded, plus GroupNorm quad statistics into ``stats`` when given.  ``base`` is the per-loop conditioning term, NHWC
+    [B,H,W,128] in fp32 or fp16 (the UNet keeps it in fp16: 4 instead of 6 bytes per element and step)."""
     if not (planes.is_cuda and planes.dtype == torch.float32 and planes.is_contiguous()):
         raise ValueError("conv_in_direct expects a contiguous fp32 CUDA NCHW tensor")
     B, C, H, W = planes.shape
     if wT.shape != (C * 9, 128) or wT.dtype != torch.float32:
         raise ValueError(f"conv_in_direct: weight must be fp32 [{C * 9}, 128]")
-    if base is not None and (base.shape != (B, H, W, 128) or base.dtype != torch.float32 or not base.is_contiguous()):
-        raise ValueError("conv_in_direct: base must be contiguous fp32 [B,H,W,128]")
+    base_dt = _lib.DTYPE_F32
+    if base is not None:
+        if base.shape != (B, H, W, 128) or base.dtype not in (torch.float32, torch.float16) or not base.is_contiguous():
+            raise ValueError("conv_in_direct: base must be contiguous fp32 or fp16 [B,H,W,128]")
+        base_dt = _dt(base)
+    if out is not None:
+        out_dtype = None if out.dtype == torch.float32 else out.dtype
     if out_dtype is None:
         if out is None:
             out = torch.empty((B, H, W, 128), dtype=torch.float32, device=planes.device)
-        _lib.check(_lib.lib().d3_conv_in_direct(planes.data_ptr(), C, wT.data_ptr(), _ptr(base), _ptr(bias), B, H, W,
-                                                out.data_ptr(), None, 0, None, _stream()))
+        _lib.check(_lib.lib().d3_conv_in_direct(planes.data_ptr(), C, wT.data_ptr(), _ptr(base), base_dt, _ptr(bias), B,
+                                                H, W, out.data_ptr(), None, 0, None, _stream()))
         return out
     if out is None:
         out = torch.empty((B, H, W, 128), dtype=out_dtype, device=planes.device)
-    _lib.check(_lib.lib().d3_conv_in_direct(planes.data_ptr(), C, wT.data_ptr(), _ptr(base), _ptr(bias), B, H, W,
-                                            None, out.data_ptr(), _dt(out), _ptr(stats), _stream()))
+    _lib.check(_lib.lib().d3_conv_in_direct(planes.data_ptr(), C, wT.data_ptr(), _ptr(base), base_dt, _ptr(bias), B, H,
+                                            W, None, out.data_ptr(), _dt(out), _ptr(stats), _stream()))
     return out
 
 
@@ -310,6 +316,7 @@ def lincomb(a: float, x, b: float = 1.0, y=None, c: float = 0.0, z=None):
 
 def guidance_grad(disp_norm, left, right, min_disp: float, max_disp: float, shift: float = 0.0,
                   w_ssim: float = 0.95):
+    """Reference ``FlowGuidance.grad`` semantic: d(loss)/d(camera-normalised disparity) (``d3_guidance_grad``)."""
     d, l, r = _f32c(disp_norm, "disp_norm"), _f32c(left, "left"), _f32c(right, "right")
     B, _, H, W = d.shape
     margin = r.shape[-1] - W
@@ -319,6 +326,39 @@ def guidance_grad(disp_norm, left, right, min_disp: float, max_disp: float, shif
     _lib.check(_lib.lib().d3_guidance_grad(d.data_ptr(), l.data_ptr(), r.data_ptr(), B, H, W, margin, min_disp,
                                            max_disp, shift, w_ssim, out.data_ptr(), _stream()))
     return out
+
+
+def guidance_step(x0, left, right, disp_scale: float, disp_offset: float, min_disp: float, max_disp: float,
+                  w_ssim: float = 0.95, *, step: float = 0.0, want_x0: bool = False, want_grad: bool = False,
+                  ca: float = 0.0, aux1=None, cb: float = 0.0, aux2=None, cc: float = 0.0):
+    """``d3_guidance_step``: photometric gradient w.r.t. x0 through ``disp = offset + scale * sum_c x0_c`` and,
+    optionally, ``x0' = x0 - step * g`` and ``out2 = ca * x0' + cb * aux1 (+ cc * aux2)`` in the same launch.
+    Returns ``(x0' or None, out2 or None, g or None)``."""
+    x, l, r = _f32c(x0, "x0"), _f32c(left, "left"), _f32c(right, "right")
+    B, Cc, H, W = x.shape
+    margin = r.shape[-1] - W
+    if l.shape != r.shape or l.shape[1] != 3 or l.shape[0] != B or l.shape[2] != H or margin < 0:
+        raise ValueError("guidance_step: left/right must be [B,3,H,W+margin]")
+    p = _lib.GuidanceParams()
+    p.x0, p.left, p.right = x.data_ptr(), l.data_ptr(), r.data_ptr()
+    g = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device) if want_grad else None
+    xo = torch.empty_like(x) if want_x0 else None
+    o2 = None
+    if aux1 is not None:
+        a1 = _f32c(aux1, "aux1")
+        if a1.shape != x.shape:
+            raise ValueError("guidance_step: aux1 must have the shape of x0")
+        o2 = torch.empty_like(x)
+        p.out2, p.aux1 = o2.data_ptr(), a1.data_ptr()
+        if aux2 is not None:
+            a2 = _f32c(aux2, "aux2")
+            p.aux2 = a2.data_ptr()
+    p.grad, p.x0_out = _ptr(g), _ptr(xo)
+    p.B, p.C, p.H, p.W, p.margin = B, Cc, H, W, margin
+    p.disp_scale, p.disp_offset, p.min_disp, p.max_disp, p.w_ssim = disp_scale, disp_offset, min_disp, max_disp, w_ssim
+    p.step, p.ca, p.cb, p.cc = step, ca, cb, cc
+    _lib.check(_lib.lib().d3_guidance_step(C.byref(p), _stream()))
+    return xo, o2, g
 
 
 def depth_to_disp(depth, fxb: float):

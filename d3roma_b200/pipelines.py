@@ -96,8 +96,12 @@ class GuidedDiffusionPipeline:
         scheduler = sched_cls.from_config(scfg)
         gpath = os.path.join(path, "guidance", "config.json")
         gcfg = load_config(os.path.join(path, "guidance"), "config.json") if os.path.exists(gpath) else {}
-        gcfg.pop("_class_name", None)
-        return cls(unet, scheduler, FlowGuidance(**gcfg))
+        # the reference's FlowGuidance registers no config (guidance.py:94 `@register_to_config` is commented out), so the
+        # config.json it saves holds only bookkeeping keys (_class_name, _diffusers_version, _name_or_path): keep what
+        # the constructor knows, like ConfigMixin.from_config does
+        import inspect
+        known = set(inspect.signature(FlowGuidance.__init__).parameters) - {"self", "camera"}
+        return cls(unet, scheduler, FlowGuidance(**{k: v for k, v in gcfg.items() if k in known}))
 
     def set_progress_bar_config(self, **kwargs):
         self._progress_bar_config = kwargs
@@ -113,7 +117,8 @@ class GuidedDiffusionPipeline:
 
     # ---- the loop body, on device-resident tensors
     @torch.no_grad()
-    def _loop(self, image, cond, srcs, build_cond, num_inference_steps, plot_every, add_noise_rgb, raw_depth):
+    def _loop(self, image, cond, srcs, build_cond, num_inference_steps, plot_every, add_noise_rgb, raw_depth,
+              denorm=None):
         """custom_pipelines.py:134-196 for tensors already on the device. Returns (clamped image, intermediates)."""
         dev = image.device
         batch_size, depth_channels = image.shape[:2]
@@ -124,6 +129,10 @@ class GuidedDiffusionPipeline:
                   and srcs.get("right") is not None)
         if guided:
             guidance.num_train_timesteps = self.scheduler.config.num_train_timesteps
+            if denorm is not None:
+                guidance.denormer = denorm   # the DDPM hook passes no denormer (scheduler_ddpm.py:507-511)
+            import inspect
+            step_kw = {"denormer": denorm} if "denormer" in inspect.signature(self.scheduler.step).parameters else {}
         n_plots = num_inference_steps // plot_every
         stack = torch.empty((batch_size, depth_channels * n_plots, image.shape[2], image.shape[3]),
                             dtype=torch.float32, device=dev)
@@ -139,7 +148,7 @@ class GuidedDiffusionPipeline:
             model_output = fwd(image, cond, t)
             if guided:
                 g = self.scheduler.step(model_output, t, image, guidance=guidance, left_image=srcs["left"],
-                                        right_image=srcs["right"], raw_depth=raw_depth)
+                                        right_image=srcs["right"], raw_depth=raw_depth, **step_kw)
             else:
                 g = self.scheduler.step(model_output, t, image)
             image = g.prev_sample
@@ -151,11 +160,12 @@ class GuidedDiffusionPipeline:
 
     @torch.no_grad()
     def sample_from(self, x_T: torch.Tensor, cond: torch.Tensor, num_inference_steps: int = 10,
-                    left_images=None, right_images=None) -> torch.Tensor:
+                    left_images=None, right_images=None, denorm=None) -> torch.Tensor:
         """Device-resident entry: start noise ``x_T`` [B,dc,H,W] and pre-concatenated conditioning ``cond``
-        [B,Cc,H,W] already in HBM (fp32, contiguous). Returns the clamped final sample."""
+        [B,Cc,H,W] already in HBM (fp32, contiguous). Returns the clamped final sample.  ``left_images`` /
+        ``right_images`` (+ ``denorm``, the x0 -> pixels map) enable stereo guidance when the guidance object asks."""
         srcs = {"left": left_images, "right": right_images}
-        image, _ = self._loop(x_T, cond, srcs, None, num_inference_steps, num_inference_steps, False, None)
+        image, _ = self._loop(x_T, cond, srcs, None, num_inference_steps, num_inference_steps, False, None, denorm)
         return image
 
     @torch.no_grad()
@@ -197,7 +207,7 @@ class GuidedDiffusionPipeline:
         image = randn_tensor(shape, generator=generator, device=dev if generator is not None else None)
         image = image.to(dev, torch.float32).contiguous()
         image, stack = self._loop(image, cond, srcs, build_cond, num_inference_steps, plot_every, add_noise_rgb,
-                                  raw_depth)
+                                  raw_depth, denorm)
         return GuidedPipelineOutput(images=image, images_pred_orig=stack, images_perturbed_orig=stack,
                                     images_pred_prev=stack, images_purturbed_pred_prev=stack,
                                     images_sampled_prev=stack)

@@ -224,11 +224,16 @@ class MyDDIMScheduler(ConfigMixin):
                                                           want_mean=(n32 is not None and not guided),
                                                           want_dir=guided)
         if guided:
-            perturbed = guidance.perturb(x0, timestep, decoder, denormer, raw_mask=raw_mask, left_image=left_image,
-                                         right_image=right_image, raw_depth=raw_depth)
             prev = prev_noised  # no noise was added above
+            if hasattr(guidance, "perturb_fused"):   # x0' and sqrt(a_prev) * x0' + dir in the guidance kernel itself
+                perturbed, prev_perturbed = guidance.perturb_fused(
+                    x0, timestep, decoder, denormer, c.sqrt_alpha_prev, dirv, 1.0, raw_mask=raw_mask,
+                    left_image=left_image, right_image=right_image, raw_depth=raw_depth)
+            else:
+                perturbed = guidance.perturb(x0, timestep, decoder, denormer, raw_mask=raw_mask,
+                                             left_image=left_image, right_image=right_image, raw_depth=raw_depth)
+                prev_perturbed = ops.lincomb(c.sqrt_alpha_prev, perturbed, 1.0, dirv)  # scheduler_ddim.py:468
             x0 = perturbed
-            prev_perturbed = ops.lincomb(c.sqrt_alpha_prev, perturbed, 1.0, dirv)  # scheduler_ddim.py:468
             prev_noised = prev_perturbed if n32 is None else ops.lincomb(1.0, prev_perturbed, c.std_dev, n32)
         else:
             perturbed = x0

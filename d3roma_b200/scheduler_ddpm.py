@@ -163,11 +163,17 @@ class MyDDPMScheduler(ConfigMixin):
                                                     want_mean=(n32 is not None and not guided))
         if guided:
             # the reference's call omits the positional `denormer` (scheduler_ddpm.py:507-511, a TypeError there);
-            # the hook is invoked with denormer=None here.
-            perturbed = guidance.perturb(x0, t, decoder, None, raw_depth=raw_depth, raw_mask=raw_mask,
-                                         left_image=left_image, right_image=right_image)
+            # the hook is invoked with denormer=None here and the guidance object falls back to its own `.denormer`
+            # (set by the pipeline from its `denorm=` argument).
             mean = prev_noised
-            mean_perturbed = ops.lincomb(c.x0_coeff, perturbed, c.xt_coeff, s32)  # scheduler_ddpm.py:512
+            if hasattr(guidance, "perturb_fused"):
+                perturbed, mean_perturbed = guidance.perturb_fused(
+                    x0, t, decoder, None, c.x0_coeff, s32, c.xt_coeff, raw_depth=raw_depth, raw_mask=raw_mask,
+                    left_image=left_image, right_image=right_image)
+            else:
+                perturbed = guidance.perturb(x0, t, decoder, None, raw_depth=raw_depth, raw_mask=raw_mask,
+                                             left_image=left_image, right_image=right_image)
+                mean_perturbed = ops.lincomb(c.x0_coeff, perturbed, c.xt_coeff, s32)  # scheduler_ddpm.py:512
             prev_noised = mean_perturbed if n32 is None else ops.lincomb(1.0, mean_perturbed, c.sigma, n32)
         else:
             perturbed = x0

@@ -17,7 +17,10 @@ return_dict=True)``, ``.sample_size``, ``.config``, ``load_state_dict`` with dif
     head         d3_conv_out_fused (GroupNorm + SiLU + conv 128 -> dc, fp32 NCHW out)
     time         d3_time_embed + d3_temb_project_all (all 32 ResNet projections in one launch)
 
-Activations are bf16 NHWC; accumulation, GroupNorm statistics and the model output are fp32/fp64.
+Activations are 16-bit NHWC - fp16 by default (``compute_dtype="fp16"``: per-step max-abs error 1.2-1.6e-3 against
+the fp32 oracle, inside the north-star bound of 1e-2), bf16 on request (same tensor-core rate, 1.0-1.25e-2) - or fp32
+(``compute_dtype="fp32"``, CUDA-core reference-precision path); accumulation, GroupNorm statistics and the model
+output are fp32/fp64.
 There is no PyTorch fallback: without the CUDA library every call raises.
 """
 from __future__ import annotations
@@ -95,7 +98,7 @@ class UNet2DModel:
     def __init__(self, sample_size: Sequence[int] = (384, 640), in_channels: int = 8, out_channels: int = 1,
                  layers_per_block: int = 2, block_out_channels: Sequence[int] = BLOCK_OUT,
                  down_block_types: Sequence[str] = DOWN_TYPES, up_block_types: Sequence[str] = UP_TYPES,
-                 compute_dtype: str = "bf16", **unused):
+                 compute_dtype: str = "fp16", **unused):
         if (tuple(block_out_channels) != BLOCK_OUT or tuple(down_block_types) != DOWN_TYPES
                 or tuple(up_block_types) != UP_TYPES or layers_per_block != 2):
             raise NotImplementedError("d3roma_b200.UNet2DModel implements the architecture of train.py:788-810 only")
@@ -113,11 +116,15 @@ class UNet2DModel:
                              "(CUDA-core reference-precision path)")
         self.compute_dtype = compute_dtype
         self._adt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[compute_dtype]
+        # per-loop conv_in conditioning term: fp16 in both 16-bit modes (O(1) values, 11 significant bits - finer than
+        # the 16-bit activation conv_in stores; 4 instead of 6 bytes per element and step, SURVEY 8d conv_in bytes)
+        self._base_dtype = torch.float16
         self.device = torch.device("cpu")
         self.dtype = torch.float32  # dtype of the pipeline-facing tensors
         self._w: Dict[str, torch.Tensor] = {}
         self._specs = _resnet_specs()
-        self._arena: Optional[_StatsArena] = None
+        self._arena: Optional[_StatsArena] = None         # arena of the forward in flight
+        self._eager_arena: Optional[_StatsArena] = None   # arena of the non-graph path (grown on demand)
         self._loaded = False
         self.keep_state_dict = True   # keep a host copy of the loaded fp32 state_dict (for save_pretrained)
         self._sd_cpu = None
@@ -131,7 +138,7 @@ class UNet2DModel:
             raise RuntimeError("d3roma_b200.UNet2DModel needs a CUDA device (no CPU fallback)")
         dev = self.device if self.device.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
         self.device = dev
-        sd = {k: v.detach() for k, v in sd.items()}
+        sd = {self._modern_key(k): v.detach() for k, v in sd.items()}
         used = set()
 
         def get(k):
@@ -210,7 +217,19 @@ class UNet2DModel:
                 raise KeyError(f"unexpected keys in state_dict: {sorted(missing)[:5]} ...")
         self._loaded = True
         self._sd_cpu = {k: v.to("cpu") for k, v in sd.items()} if self.keep_state_dict else None
+        self.reset_graphs()   # captured graphs hold raw pointers into the previous weight tensors
         return self
+
+    @staticmethod
+    def _modern_key(k: str) -> str:
+        """Checkpoints saved by diffusers < 0.14 name the attention linears query / key / value / proj_attn
+        (SURVEY Appendix A.6); map them onto to_q / to_k / to_v / to_out.0."""
+        if ".attentions." in k:
+            for old, new in ((".query.", ".to_q."), (".key.", ".to_k."), (".value.", ".to_v."),
+                             (".proj_attn.", ".to_out.0.")):
+                if old in k:
+                    return k.replace(old, new)
+        return k
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         """The diffusers-keyed fp32 state_dict this model was loaded from (kept on the host)."""
@@ -236,7 +255,7 @@ class UNet2DModel:
         import os
         with open(os.path.join(path, "config.json")) as f:
             cfg = json.load(f)
-        cfg.pop("_class_name", None)
+        cfg = {k: v for k, v in cfg.items() if not k.startswith("_")}   # _class_name, _diffusers_version, _name_or_path
         if compute_dtype is not None:
             cfg["compute_dtype"] = compute_dtype
         net = cls(**cfg).to(device)
@@ -267,7 +286,9 @@ class UNet2DModel:
                 device = torch.device("cuda", torch.cuda.current_device())
             if self._loaded and device != self.device:
                 self._w = {k: v.to(device) for k, v in self._w.items()}
-                self._arena = None
+                self._arena = self._eager_arena = None
+                self._cin_packs, self._cond_base_cache = {}, None
+                self.reset_graphs()
             self.device = device
         return self
 
@@ -357,17 +378,20 @@ class UNet2DModel:
         key = (cond.data_ptr(), cond._version, tuple(cond.shape), Cs)
         if out is None and self._cond_base_cache is not None and self._cond_base_cache[0] == key:
             return self._cond_base_cache[1]
-        base = ops.conv_in_direct(cond, self._cin_pack(Cs)[1], bias=self._w["conv_in.b"], out=out)
+        base = ops.conv_in_direct(cond, self._cin_pack(Cs)[1], bias=self._w["conv_in.b"], out=out,
+                                  out_dtype=self._base_dtype)
         if out is None:
             self._cond_base_cache = (key, base, cond)  # keeps `cond` alive so the storage address cannot be reused
         return base
 
     @torch.no_grad()
     def forward_split(self, sample: torch.Tensor, cond: Optional[torch.Tensor], timestep,
-                      cond_base: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      cond_base: Optional[torch.Tensor] = None, arena: Optional[_StatsArena] = None) -> torch.Tensor:
         """UNet forward on ``cat([sample, cond], 1)`` without materialising the concat.
         sample fp32 [B,dc,H,W], cond fp32 [B,Cc,H,W] (contiguous, CUDA); returns fp32 [B,out_channels,H,W].
-        ``cond_base``: precomputed ``self.cond_base(cond, Cs)`` (the CUDA-graph path passes its static buffer)."""
+        ``cond_base``: precomputed ``self.cond_base(cond, Cs)`` (the CUDA-graph path passes its static buffer).
+        ``arena``: the GroupNorm statistics arena to use (a captured graph owns its own, so that a later call with a
+        larger batch can never free memory a live graph still writes to)."""
         if not self._loaded:
             raise RuntimeError("UNet2DModel: load_state_dict() has not been called")
         B, Cs, H, Wd = sample.shape
@@ -379,8 +403,15 @@ class UNet2DModel:
         dev = sample.device
         W = self._w
         need = B * 2 * 40000
-        if self._arena is None or self._arena.buf.numel() < need or self._arena.buf.device != dev:
-            self._arena = _StatsArena(dev, need)
+        if arena is not None:
+            if arena.buf.numel() < need or arena.buf.device != dev:
+                raise RuntimeError("forward_split: the supplied statistics arena is too small for this batch")
+            self._arena = arena
+        elif (self._eager_arena is None or self._eager_arena.buf.numel() < need
+              or self._eager_arena.buf.device != dev):
+            self._arena = self._eager_arena = _StatsArena(dev, need)
+        else:
+            self._arena = self._eager_arena
         self._arena.reset()
 
         # timestep -> fused per-ResNet bias vectors
@@ -461,45 +492,70 @@ class UNet2DModel:
                 h = _Act(up, st)
         return ops.conv_out_fused(h.t, h.stats, W["out.g"], W["out.b"], W["out.w"], W["out.bias"], self.out_channels)
 
-    @torch.no_grad()
-    def forward_graphed(self, sample: torch.Tensor, cond: Optional[torch.Tensor], timestep) -> torch.Tensor:
-        """Same as ``forward_split`` but replayed from a CUDA graph captured per (B, H, W, Cs, Cc): the ~430 kernel
-        launches of one UNet forward become a single graph launch.  ``timestep`` must be one scalar for the batch.
-        Returns a STATIC output buffer that the next call overwrites (the sampling loop consumes it immediately)."""
+    @staticmethod
+    def _cond_key(cond: Optional[torch.Tensor]):
+        """Identity of a conditioning tensor's CONTENTS: storage address, in-place version counter and shape (the same
+        key ``cond_base`` uses) - a caller that refills one preallocated buffer per frame bumps the version."""
+        return None if cond is None else (cond.data_ptr(), cond._version, tuple(cond.shape))
+
+    def _graph_for(self, sample: torch.Tensor, cond: Optional[torch.Tensor], tval: float) -> dict:
+        """Capture (once per (B, H, W, Cs, Cc, device)) the UNet forward into a CUDA graph over static buffers.  The
+        graph owns everything it touches: input / conditioning / timestep buffers, the conv_in conditioning term and
+        its own GroupNorm statistics arena."""
         key = (tuple(sample.shape), None if cond is None else tuple(cond.shape), sample.device.index)
         g = self._graphs.get(key)
-        tval = float(timestep)
-        if g is None:
-            g = {"x": torch.empty_like(sample), "c": None if cond is None else torch.empty_like(cond),
-                 "t": torch.zeros(1, dtype=torch.float32, device=sample.device)}
-            g["x"].copy_(sample)
-            if cond is not None:
-                g["c"].copy_(cond)
-            g["t"].fill_(tval)
-            split = cond is not None and sample.shape[1] <= 3 and self._adt != torch.float32
-            g["base"] = self.cond_base(g["c"], sample.shape[1], out=torch.empty(
-                (sample.shape[0], sample.shape[2], sample.shape[3], 128), dtype=torch.float32,
-                device=sample.device)) if split else None
-            side = torch.cuda.Stream(device=sample.device)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                self.forward_split(g["x"], g["c"], g["t"], cond_base=g["base"])  # warm-up: attributes, arena, allocator
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            from . import _lib
-            n0 = _lib.lib().d3_launch_count()
-            with torch.cuda.graph(graph):
-                g["y"] = self.forward_split(g["x"], g["c"], g["t"], cond_base=g["base"])
-            g["n_kernels"] = int(_lib.lib().d3_launch_count() - n0)
-            g["graph"] = graph
-            g["cond_src"] = None
-            self._graphs[key] = g
+        if g is not None:
+            return g
+        B = sample.shape[0]
+        g = {"x": torch.empty_like(sample), "c": None if cond is None else torch.empty_like(cond),
+             "t": torch.zeros(1, dtype=torch.float32, device=sample.device),
+             "arena": _StatsArena(sample.device, B * 2 * 40000)}
         g["x"].copy_(sample)
-        if cond is not None and g["cond_src"] is not cond:
-            g["c"].copy_(cond)  # conditioning is constant across the steps of one sampling loop: copy once
-            g["cond_src"] = cond
-            if g["base"] is not None:
-                self.cond_base(g["c"], sample.shape[1], out=g["base"])  # ... and so is its conv_in term
+        if cond is not None:
+            g["c"].copy_(cond)
+        g["t"].fill_(tval)
+        split = cond is not None and sample.shape[1] <= 3 and self._adt != torch.float32
+        g["base"] = self.cond_base(g["c"], sample.shape[1], out=torch.empty(
+            (B, sample.shape[2], sample.shape[3], 128), dtype=self._base_dtype, device=sample.device)) if split else None
+        side = torch.cuda.Stream(device=sample.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            # warm-up: function attributes, allocator pools
+            self.forward_split(g["x"], g["c"], g["t"], cond_base=g["base"], arena=g["arena"])
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        from . import _lib
+        n0 = _lib.lib().d3_launch_count()
+        with torch.cuda.graph(graph):
+            g["y"] = self.forward_split(g["x"], g["c"], g["t"], cond_base=g["base"], arena=g["arena"])
+        g["n_kernels"] = int(_lib.lib().d3_launch_count() - n0)
+        g["graph"] = graph
+        g["cond_key"] = self._cond_key(cond)
+        self._graphs[key] = g
+        return g
+
+    def _refresh_graph_cond(self, g: dict, cond: Optional[torch.Tensor], Cs: int) -> None:
+        """Conditioning is constant across the steps of one sampling loop: copy it into the graph's static buffer (and
+        recompute its conv_in term) only when its contents changed."""
+        if cond is None:
+            return
+        key = self._cond_key(cond)
+        if g["cond_key"] == key:
+            return
+        g["c"].copy_(cond)
+        g["cond_key"] = key
+        if g["base"] is not None:
+            self.cond_base(g["c"], Cs, out=g["base"])
+
+    @torch.no_grad()
+    def forward_graphed(self, sample: torch.Tensor, cond: Optional[torch.Tensor], timestep) -> torch.Tensor:
+        """Same as ``forward_split`` but replayed from a CUDA graph captured per (B, H, W, Cs, Cc): the ~180 kernel
+        launches of one UNet forward become a single graph launch.  ``timestep`` must be one scalar for the batch.
+        Returns a STATIC output buffer that the next call overwrites (the sampling loop consumes it immediately)."""
+        tval = float(timestep)
+        g = self._graph_for(sample, cond, tval)
+        g["x"].copy_(sample)
+        self._refresh_graph_cond(g, cond, sample.shape[1])
         g["t"].fill_(tval)
         g["graph"].replay()
         self.graph_kernel_launches += g["n_kernels"]
@@ -515,12 +571,8 @@ class UNet2DModel:
         Cs = int(sample_shape[1])
         if graphed:
             g = self._graphs.get((tuple(sample_shape), tuple(cond.shape), cond.device.index))
-            if g is None or g["cond_src"] is cond:
-                return
-            g["c"].copy_(cond)
-            g["cond_src"] = cond
-            if g["base"] is not None:
-                self.cond_base(g["c"], Cs, out=g["base"])
+            if g is not None:
+                self._refresh_graph_cond(g, cond, Cs)
         else:
             self.cond_base(cond, Cs)
 

@@ -127,9 +127,12 @@ int d3_im2col_input(const float* sample, int Cs, const float* cond, int Cc, int 
  * every step), so the caller computes them once (out32 mode: planes = cond, base = NULL, bias given -> fp32 NHWC
  * [B,H,W,128]) and every step adds the taps of the noisy sample (out16 mode: planes = sample, base = that tensor ->
  * 16-bit NHWC [B,H,W,128] + GroupNorm quad statistics [B][32][2]).  planes fp32 NCHW [B,C,H,W]; wT fp32
- * [C*9][128] with k = c*9 + (kh*3+kw).  Exactly one of out32 / out16 is non-NULL.  fp32 arithmetic throughout. */
-int d3_conv_in_direct(const float* planes, int C, const float* wT, const float* base, const float* bias, int B, int H,
-                      int W, float* out32, void* out16, int dtype, double* stats, void* stream);
+ * [C*9][128] with k = c*9 + (kh*3+kw).  Exactly one of out32 / out16 is non-NULL.  fp32 arithmetic throughout.
+ * The per-loop term may also be kept in fp16 (computed with out16 + dtype = D3_DTYPE_F16, no stats; passed back as
+ * base with base_dtype = D3_DTYPE_F16): per-step traffic (2 + 2) * 128 * P bytes instead of (4 + 2) * 128 * P. */
+int d3_conv_in_direct(const float* planes, int C, const float* wT, const void* base, int base_dtype,
+                      const float* bias, int B, int H, int W, float* out32, void* out16, int dtype, double* stats,
+                      void* stream);
 
 /* ---- conv_norm_out + SiLU + conv_out fused: bf16 NHWC [B,H,W,128] -> fp32 NCHW [B,dc,H,W] (dc = 1 or 3).
  * w fp32 [dc][9][128] (tap-major), stats = quad statistics of x ([B][32][2]).  16-bit dtypes run as a streaming
@@ -194,10 +197,36 @@ int d3_sched_ddpm_step(const float* model_output, const float* sample, const flo
 int d3_lincomb(float a, const float* x, float b, const float* y, float c, const float* z, int64_t n, float* out,
                void* stream);
 
-/* ---- stereo photometric guidance gradient (FlowGuidance.grad stereo branch, core/guidance.py:298-323 + SSIM :28-42)
- * grad[b,0,y,x] = d/d(disp_norm) [ w_ssim * sum SSIM_loss(left, warp) + (1 - w_ssim) * sum |left - warp| ],
- * warp = right sampled at x - clip(min_disp + (disp_norm - shift) * (max_disp - min_disp)) (bilinear, border).
- * disp_norm fp32 [B,1,H,W]; left, right fp32 [B,3,H,W+margin]. Replaces ~50 autograd launches by one kernel. */
+/* ---- stereo photometric guidance (FlowGuidance.grad stereo branch, core/guidance.py:298-323 + SSIM :28-42) and the
+ * guided update of the scheduler hook (core/scheduler_ddim.py:461-468, core/scheduler_ddpm.py:506-516), one kernel.
+ *   disparity [px] = clip(disp_offset + disp_scale * sum_c x0[b,c,y,x], min_disp, max_disp)
+ *   warp           = right sampled at x - disparity (+ margin), bilinear, border padding, align_corners
+ *   loss           = w_ssim * sum SSIM_loss(left, warp) + (1 - w_ssim) * sum |left - warp|
+ *   g[b,0,y,x]     = d(loss)/d(x0[b,c,y,x]) = disp_scale * d(loss)/d(disparity)        (the same for every c)
+ *   x0_out         = x0 - step * g                                   (FlowGuidance.perturb, core/guidance.py:214)
+ *   out2           = ca * x0_out + cb * aux1 (+ cc * aux2)           (each product / sum rounded separately)
+ * The affine map x0 -> pixels is what the reference's `denormer` hook argument stands for (Normalizer.denormalize,
+ * utils_d3roma/utils.py:260-273, "average" mode, gamma 1: disp_scale = bound / (s * C), disp_offset = t * bound); the
+ * reference's own grad() takes camera-normalised disparity (utils_d3roma/camera.py:599-602, 771-780:
+ * disp_scale = max - min, disp_offset = min - shift * (max - min)) - d3_guidance_grad below.
+ * x0, x0_out, out2, aux1, aux2 fp32 [B,C,H,W] (C = 1 or 3); grad fp32 [B,1,H,W]; left, right fp32 [B,3,H,W+margin].
+ * Any of grad / x0_out / out2 may be NULL (at least one is required). */
+typedef struct d3_guidance_params {
+  const float* x0;
+  const float* left;
+  const float* right;
+  float* grad;
+  float* x0_out;
+  float* out2;
+  const float* aux1;
+  const float* aux2;
+  int32_t B, C, H, W, margin;
+  float disp_scale, disp_offset, min_disp, max_disp, w_ssim;
+  float step, ca, cb, cc;
+} d3_guidance_params;
+int d3_guidance_step(const d3_guidance_params* p, void* stream);
+/* grad[b,0,y,x] = d(loss)/d(disp_norm) with disparity = clip(min_disp + (disp_norm - shift) * (max_disp - min_disp)):
+ * the output of the reference's FlowGuidance.grad.  disp_norm fp32 [B,1,H,W]. */
 int d3_guidance_grad(const float* disp_norm, const float* left, const float* right, int B, int H, int W, int margin,
                      float min_disp, float max_disp, float shift, float w_ssim, float* grad, void* stream);
 

@@ -284,6 +284,116 @@ def gen_pipeline(store):
         store[f"{tag}/model_outputs"] = np.stack([_np(o) for o in rec.outs])
 
 
+def make_stereo_pair(B, H, W, gen, max_shift=9.0):
+    """Synthetic rectified pair with a known disparity: smooth random left image, smooth ground-truth disparity in
+    [min_d, min_d + max_shift] px, right = left sampled at x + disp (so that warping right by the true disparity
+    reproduces left up to interpolation)."""
+    cam = ref_camera.Realsense.default_sim()
+    left = torch.rand(B, 3, H + 8, W + 8, generator=gen)
+    for _ in range(3):
+        left = F.avg_pool2d(left, 3, 1)
+    left = (left[..., 1:H + 1, 1:W + 1] - left.mean()) / left.std() * 0.35
+    left = left.clamp(-1, 1)
+    d = torch.rand(B, 1, H // 8 + 2, W // 8 + 2, generator=gen)
+    d = F.interpolate(d, size=(H, W), mode="bilinear", align_corners=True)
+    disp = float(cam.min_disp) + 0.5 + d[:, 0] * max_shift                     # [B,H,W] pixels
+    # right(x') with x' = x - disp(x): build it by sampling left at x' + disp (first-order inverse warp)
+    xx, yy = torch.meshgrid(torch.arange(W), torch.arange(H), indexing="xy")
+    gx = (xx[None] + disp) / ((W - 1) / 2.0) - 1
+    gy = (yy[None] / ((H - 1) / 2.0) - 1).expand_as(gx)
+    right = F.grid_sample(left, torch.stack([gx, gy], dim=-1), align_corners=True, mode="bilinear",
+                          padding_mode="border")
+    return left, right, disp
+
+
+def gen_guided(store):
+    """The guided DDIM loop: the reference's MyDDIMScheduler.step with its guidance hook (scheduler_ddim.py:461-472)
+    driven by a FlowGuidance whose perturb() is the chain rule over the reference's own pieces - Normalizer.denormalize
+    (the `denormer` hook argument), camera.normalize_disp / unnormalize_disp, the SSIM module and the lines of
+    FlowGuidance.grad (guidance.py:298-323) - since the reference leaves that hook unconnected."""
+    from oracle.unet_ref import make_unet
+    cam = ref_camera.Realsense.default_sim()
+    ssim = SSIM()
+    H, W, B = 32, 64, 2
+    gen = torch.Generator().manual_seed(777)
+    left, right, disp_gt = make_stereo_pair(B, H, W, gen)
+    normer = Normalizer(ssi=False, mode="average", num_chs=1, ch_bounds=[128.], ch_gammas=[1.], t=0.5, s=2.0)
+    raw = torch.stack([normer.normalize((disp_gt[b:b + 1] + torch.randn(1, H, W, generator=gen) * 2.0).clamp(min=0))[0]
+                       for b in range(B)])
+    x_T = torch.randn(B, 1, H, W, generator=gen)
+    weight = 2e-3
+
+    class StereoGuidance(FlowGuidance):
+        def __init__(self, w):
+            super().__init__(flow_guidance_weight=w, flow_guidance_mode="stereo")
+            self.camera = cam
+            self.log = []
+
+        def loss_of(self, x0, denormer, left_image, right_image):
+            px = denormer(x0)                                   # [B,1,H,W] pixels (utils.py:260-273)
+            d_hat = cam.normalize_disp(px)                      # camera.py:771-776
+            g, _ = _guidance_grad_reference(self, ssim, cam, d_hat, left_image, right_image)
+            return g
+
+        def perturb(self, pred_original_sample, t, decoder, denormer, raw_mask=None, left_image=None,
+                    right_image=None, raw_depth=None):
+            x = pred_original_sample.detach().clone().requires_grad_(True)
+            with torch.enable_grad():
+                px = denormer(x)
+                d_hat = cam.normalize_disp(px).squeeze(1)
+                disp = cam.unnormalize_disp(d_hat)
+                Bn, Hh, Ww = disp.shape
+                margin_left = right_image.shape[-1] - Ww
+                xx, yy = torch.meshgrid(torch.arange(Ww), torch.arange(Hh), indexing='xy')
+                xx = xx[None, ...].repeat(Bn, 1, 1)
+                yy = yy[None, ...].repeat(Bn, 1, 1)
+                xx = (xx - disp + margin_left) / ((Ww + margin_left - 1) / 2.) - 1
+                yy = yy / ((Hh - 1) / 2.) - 1
+                grid = torch.stack([xx, yy], dim=-1)
+                warp = F.grid_sample(right_image, grid, align_corners=True, mode="bilinear", padding_mode="border")
+                loss = F.l1_loss(left_image[..., margin_left:], warp, reduction='sum')
+                loss = 0.95 * ssim(left_image[..., margin_left:], warp).sum() + 0.05 * loss
+                g = torch.autograd.grad(loss, x)[0]
+            out = (pred_original_sample - self.flow_guidance_weight * g).detach()
+            self.log.append(dict(x0=pred_original_sample.clone(), g=g.clone(), x0p=out.clone(), loss=float(loss)))
+            return out
+
+    unet = make_unet(8, 1, seed=0, sample_size=(H, W))
+    for tag, w in (("guided", weight), ("plain", 0.0)):
+        sch = MyDDIMScheduler.from_config(DDIM_CONFIGS["cos128_sample"])
+        sch.set_timesteps(10)
+        guid = StereoGuidance(w)
+        image = x_T.clone()
+        cond = torch.cat([left, right, raw], dim=1)
+        for i, t in enumerate(sch.timesteps):
+            with torch.no_grad():
+                m = unet(torch.cat([image, cond], dim=1), t).sample
+            out = sch.step(m, t, image, guidance=guid, denormer=normer.denormalize, left_image=left, right_image=right)
+            if tag == "guided":
+                store[f"guided/m{i}"], store[f"guided/x{i}"] = _np(m), _np(image)
+                store[f"guided/x0{i}"] = _np(guid.log[-1]["x0"])
+                store[f"guided/g{i}"] = _np(guid.log[-1]["g"])
+                store[f"guided/x0p{i}"] = _np(out.images_perturbed_orig)
+                store[f"guided/prev{i}"] = _np(out.prev_sample)
+                store[f"guided/loss{i}"] = np.float64(guid.log[-1]["loss"])
+            image = out.prev_sample
+        store[f"{tag}/images"] = _np(image.clamp(-1, 1))
+    store["left"], store["right"], store["raw"], store["x_T"] = _np(left), _np(right), _np(raw), _np(x_T)
+    store["disp_gt"] = _np(disp_gt)
+    store["weight"] = np.float64(weight)
+    store["cam"] = np.array([cam.min_disp, cam.max_disp, cam.config["shift"]], dtype=np.float64)
+    # photometric loss of the final disparities (reference pieces): guidance must not increase it
+    with torch.no_grad():
+        for tag in ("guided", "plain"):
+            px = normer.denormalize(torch.from_numpy(store[f"{tag}/images"]))
+            d_hat = cam.normalize_disp(px)
+    for tag in ("guided", "plain"):
+        x = torch.from_numpy(store[f"{tag}/images"])
+        g = StereoGuidance(1.0)
+        g.perturb(x, 0, None, normer.denormalize, left_image=left, right_image=right)
+        store[f"{tag}/final_loss"] = np.float64(g.log[-1]["loss"])
+
+
 def gen_postproc(store):
     """compute_errors / compute_scale_and_shift / Normalizer(ssi=True) of the reference (utils_d3roma/utils.py)."""
     g = torch.Generator().manual_seed(31)
@@ -396,7 +506,7 @@ def main():
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
     for name, fn in (("ddim", gen_ddim), ("ddpm", gen_ddpm), ("prepost", gen_prepost), ("guidance", gen_guidance),
-                     ("pipeline", gen_pipeline), ("postproc", gen_postproc), ("frontend", gen_frontend), ("ransac", gen_ransac)):
+                     ("pipeline", gen_pipeline), ("guided", gen_guided), ("postproc", gen_postproc), ("frontend", gen_frontend), ("ransac", gen_ransac)):
         store = {}
         with torch.no_grad():
             fn(store)

@@ -8,6 +8,7 @@ import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from d3roma_b200 import ops  # noqa: E402
+from tests._util import check_conv_stats  # noqa: E402
 
 torch.backends.cudnn.allow_tf32 = False
 g = torch.Generator(device="cuda").manual_seed(3)
@@ -35,9 +36,7 @@ for (B, H, W, Ci, Co, C1, C2, use_res) in SHAPES:
     if use_res:
         ref = ref + res.float()
     good = bool(((out.float() - ref).abs() <= 2 ** -7 * ref.abs() + 2e-2).all())
-    o = out.double().reshape(B, H * W, Co // 4, 4)
-    s_ref = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
-    good = good and torch.allclose(stats, s_ref, rtol=1e-5, atol=1e-3)
+    good = good and check_conv_stats(stats, out, ref)
     if not good:
         print("BAD shape", (B, H, W, Ci, Co, C1, C2, use_res), float((out.float() - ref).abs().max()))
     ok = ok and good

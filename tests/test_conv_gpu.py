@@ -4,6 +4,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from tests._util import check_conv_stats
+
 pytestmark = pytest.mark.gpu
 
 CASES = [
@@ -69,10 +71,7 @@ def test_conv_igemm_matches_torch(case, dt):
     err = (out.float() - ref).abs()
     tol = 2.0 ** -7 * ref.abs() + 2e-2 if dt == torch.bfloat16 else 2.0 ** -10 * ref.abs() + 3e-3
     assert bool((err <= tol).all()), f"max err {err.max().item():.4g} (ref max {ref.abs().max().item():.3g})"
-    # statistics are those of the stored (rounded) output
-    o = out.double().reshape(B, Ho * Wo, Cout // 4, 4)
-    s_ref = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
-    torch.testing.assert_close(stats, s_ref, rtol=1e-5, atol=1e-3)
+    assert check_conv_stats(stats, out, ref), "GroupNorm quad statistics mismatch"
 
 
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
@@ -94,21 +93,20 @@ def test_upsample_conv_subpixel_phases(B, H, W, C, dt):
     err = (out.float() - ref).abs()
     tol = (2.0 ** -7 if dt == torch.bfloat16 else 2.0 ** -10) * ref.abs() + (3e-2 if dt == torch.bfloat16 else 4e-3)
     assert bool((err <= tol).all()), f"max err {err.max().item():.4g}"
-    o = out.double().reshape(B, 4 * H * W, C // 4, 4)
-    s_ref = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
-    torch.testing.assert_close(stats, s_ref, rtol=1e-5, atol=1e-3)
+    assert check_conv_stats(stats, out, ref.contiguous()), "GroupNorm quad statistics mismatch"
 
 
 def test_kernel_variants_match():
-    """Kernel variants (halo blocks with each tile width, per-tap tiles, cta_group::2 pairs, direct-store epilogue,
-    pixels-as-M only) are selected through environment variables read once per process; run every variant in a
-    subprocess over shapes with ragged tiles, residuals, folded shortcuts and statistics (tests/_conv_variant_check.py)."""
+    """Routing overrides (halo blocks with each tile width, per-tap tiles, the lane-exchange epilogue, pixels-as-M only)
+    are selected through environment variables read once per process; every one of them must give correct results:
+    run each in a subprocess over shapes with ragged tiles, residuals, folded shortcuts and statistics
+    (tests/_conv_variant_check.py)."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = os.path.join(root, "tests", "_conv_variant_check.py")
     for env in ({"D3_CONV_VB": "0"}, {"D3_CONV_VB": "8"}, {"D3_CONV_VB": "16"}, {"D3_CONV_VB": "32"},
-                {"D3_CONV_VB": "64"}, {"D3_CONV_VB": "64", "D3_CONV_VB_NBLK": "3"}, {"D3_CONV_2CTA": "1"},
-                {"D3_CONV_T_DIRECT": "1"}, {"D3_CONV_NO_T": "1"}, {"D3_CONV_T_MAXC": "128"}, {"D3_CONV_MC": "1"}):
+                {"D3_CONV_VB": "64"}, {"D3_CONV_VB": "64", "D3_CONV_VB_NBLK": "3"}, {"D3_CONV_EPI": "0"},
+                {"D3_CONV_EPI": "0", "D3_CONV_VB": "32"}, {"D3_CONV_NO_T": "1"}, {"D3_CONV_T_MAXC": "128"}):
         e = dict(os.environ, **env)
         r = subprocess.run([sys.executable, script], cwd=root, env=e, capture_output=True, text=True, timeout=300)
         assert "VARIANT_OK" in r.stdout, (env, r.stdout[-800:], r.stderr[-800:])
@@ -152,7 +150,5 @@ def test_conv_fuzz_random_shapes():
         tol = 2.0 ** -7 * ref.abs() + 2e-2 if dt == torch.bfloat16 else 2.0 ** -10 * ref.abs() + 3e-3
         case = (it, B, H, W, cin, cout, k, stride, use_sc, use_res, str(dt))
         assert bool((err <= tol).all()), (case, err.max().item())
-        o = out.double().reshape(B, Ho * Wo, cout // 4, 4)
-        s_ref = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
-        assert torch.allclose(stats, s_ref, rtol=1e-5, atol=1e-3), case
+        assert check_conv_stats(stats, out, ref), case
     assert n_multi >= 12

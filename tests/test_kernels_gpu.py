@@ -135,3 +135,9 @@ def test_conv_in_direct_split_matches_torch(B, Cs, Cc, H, W, dt):
     o = out.double().reshape(B, H * W, 32, 4)
     s_ref = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1)
     torch.testing.assert_close(stats, s_ref, rtol=1e-5, atol=1e-3)
+    # the per-loop term kept in fp16 (what the UNet does: 4 instead of 6 bytes per element and step)
+    base16 = ops.conv_in_direct(c, ops.pack_conv_in_direct(w, Cs, Cs + Cc), bias=bias, out_dtype=torch.float16)
+    assert base16.dtype == torch.float16
+    assert bool(((base16.float() - ref_base).abs() <= 2.0 ** -11 * ref_base.abs() + 1e-6).all())
+    out16 = ops.conv_in_direct(x, ops.pack_conv_in_direct(w, 0, Cs), base=base16, out_dtype=dt)
+    assert bool(((out16.float() - ref).abs() <= ulp * ref.abs() + 2.0 ** -11 * ref_base.abs() + 1e-4).all())

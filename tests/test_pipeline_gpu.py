@@ -111,8 +111,10 @@ def test_guided_pipeline_runs_and_differs():
     for w in (0.0, 1e-3):
         fg = d.FlowGuidance(flow_guidance_weight=w, flow_guidance_mode="stereo")
         pipe = d.GuidedDiffusionPipeline(net, d.MyDDIMScheduler.from_config(DDIM_CFG), fg)
+        normer = d.Normalizer(ssi=False, mode="average", num_chs=1, ch_bounds=[128.], ch_gammas=[1.], t=0.5, s=2.0)
         outs.append(pipe(None, left, right, raw, None, None, num_inference_steps=4, num_intermediate_images=1,
-                         cond_channels="left+right+raw", generator=torch.Generator().manual_seed(9)).images)
+                         cond_channels="left+right+raw", denorm=normer.denormalize,
+                         generator=torch.Generator().manual_seed(9)).images)
     assert torch.isfinite(outs[1]).all() and not torch.equal(outs[0], outs[1])
 
 
@@ -276,3 +278,76 @@ def test_full_size_c1_ddim10_epe_delta_vs_oracle():
         assert abs(epe - epe_ref) <= 0.05
         assert err_img <= tol_img
         del net, pipe
+
+
+def test_real_shape_teacher_forced_steps_384x640_b2():
+    """BASELINE configs[1] shape (384x640, left+right+raw), B = 2, in the TIMED dtype (fp16 operands): per-step model
+    output against the oracle UNet on the oracle's own DDIM trajectory (teacher forcing), north-star bound 1e-2."""
+    import d3roma_b200 as d
+    from d3roma_b200 import synthetic
+    from oracle import schedulers_ref as S
+    from oracle.unet_ref import make_unet
+    torch.set_num_threads(16)
+    hw = (384, 640)
+    batch = synthetic.make_batch([0, 1], h=360, w=640)
+    pad = lambda t: torch.nn.functional.pad(t, (0, 0, 12, 12), mode="replicate")   # noqa: E731
+    cond = torch.cat([pad(batch["left_image"]), pad(batch["right_image"]), pad(batch["sim_disp"])], 1)
+    ref = make_unet(8, 1, seed=0, sample_size=hw)
+    net = d.UNet2DModel(sample_size=hw, in_channels=8, out_channels=1, compute_dtype="fp16").to("cuda")
+    net.load_state_dict(ref.state_dict())
+    ac = torch.cumprod(1 - S.make_betas("squaredcos_cap_v2", 128), 0)
+    ts = S.make_timesteps(128, 10, "leading", 1)
+    x = torch.randn((2, 1, *hw), generator=torch.Generator().manual_seed(7))
+    cond_d = cond.cuda()
+    worst = 0.0
+    for i, t in enumerate(ts.tolist()):
+        with torch.no_grad():
+            m_ref = ref(torch.cat([x, cond], 1), torch.tensor(t)).sample
+        if i in (0, 1, 4, 8, 9):   # the oracle forward dominates the run time; the trajectory itself is always advanced
+            m = net.forward_graphed(x.cuda(), cond_d, t).cpu()
+            worst = max(worst, float((m - m_ref).abs().max()))
+        x, _ = S.ddim_step(m_ref, t, x, ac, ac[0], 128, 10, prediction_type="sample", clip_sample=True)
+    print(f"384x640 B=2 fp16 teacher-forced: worst per-step model-output max-abs err {worst:.3e}")
+    assert worst <= 1e-2
+
+
+def test_real_shape_ddpm_slice_544x960_fp32():
+    """BASELINE configs[3] at its real shape (540x960 padded to 544x960, DDPM of 100 steps, fp32 path): the first 6 and the
+    last 4 steps of the oracle trajectory, per-step model output and posterior sample within 1e-4."""
+    import d3roma_b200 as d
+    from oracle import schedulers_ref as S
+    from oracle.unet_ref import make_unet
+    torch.set_num_threads(16)
+    hw = (544, 960)
+    g = torch.Generator().manual_seed(12)
+    left, right = (torch.rand(1, 3, *hw, generator=g) * 2 - 1 for _ in range(2))
+    raw = torch.rand(1, 1, *hw, generator=g) * 2 - 1
+    cond = torch.cat([left, right, raw], 1)
+    ref = make_unet(8, 1, seed=0, sample_size=hw)
+    net = d.UNet2DModel(sample_size=hw, in_channels=8, out_channels=1, compute_dtype="fp32").to("cuda")
+    net.load_state_dict(ref.state_dict())
+    sch = d.MyDDPMScheduler.from_config(DDPM_CFG)
+    sch.set_timesteps(100)
+    ac = torch.cumprod(1 - S.make_betas("squaredcos_cap_v2", 128), 0)
+    steps = sch.timesteps.tolist()
+    x = torch.randn((1, 1, *hw), generator=g)
+    worst_m = worst_x = 0.0
+    for t in steps[:6] + steps[-4:]:
+        with torch.no_grad():
+            m_ref = ref(torch.cat([x, cond], 1), torch.tensor(t)).sample
+        m = net.forward_split(x.cuda(), cond.cuda(), t)
+        worst_m = max(worst_m, float((m.cpu() - m_ref).abs().max()))
+        noise = torch.randn(m_ref.shape, generator=g) if t > 0 else None
+        x_ref, _, _ = S.ddpm_step(m_ref, t, x, ac, 128, 100, noise, prediction_type="sample", thresholding=True)
+        # our scheduler on our model output, with the same noise
+        import d3roma_b200.scheduler_ddpm as sd
+        orig = sd.randn_tensor
+        sd.randn_tensor = lambda shape, generator=None, device=None, dtype=None: noise.to(device)
+        try:
+            got = sch.step(m, t, x.cuda()).prev_sample.cpu()
+        finally:
+            sd.randn_tensor = orig
+        worst_x = max(worst_x, float((got - x_ref).abs().max()))
+        x = x_ref
+    print(f"544x960 DDPM fp32 slice: worst model-output err {worst_m:.3e}, worst x_(t-1) err {worst_x:.3e}")
+    assert worst_m <= 1e-4 and worst_x <= 1e-4

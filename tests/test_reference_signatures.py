@@ -1,0 +1,63 @@
+"""The drop-in classes must keep the reference's call surface: compare ``inspect.signature`` against the reference's own
+classes, imported from /root/reference behind the diffusers stub.  Skipped where the reference tree is absent (the GPU
+box); the hard-coded copies in tests/test_scheduler_host.py cover that case."""
+import inspect
+import sys
+from pathlib import Path
+
+import pytest
+
+REF = Path("/root/reference")
+pytestmark = pytest.mark.skipif(not (REF / "core" / "custom_pipelines.py").exists(), reason="reference tree absent")
+
+
+@pytest.fixture(scope="module")
+def ref_modules():
+    from oracle import diffusers_stub
+    diffusers_stub.install()
+    sys.path.insert(0, str(REF))
+    try:
+        from core import custom_pipelines, guidance, scheduler_ddim, scheduler_ddpm
+        from utils_d3roma import utils as ref_utils
+        yield dict(pipelines=custom_pipelines, guidance=guidance, ddim=scheduler_ddim, ddpm=scheduler_ddpm, utils=ref_utils)
+    finally:
+        sys.path.remove(str(REF))
+
+
+def _params(fn):
+    """(name, kind, default) triples; annotations are ignored (the reference annotates with diffusers types)."""
+    return [(p.name, p.kind, p.default) for p in inspect.signature(fn).parameters.values()]
+
+
+def test_scheduler_signatures(ref_modules):
+    import d3roma_b200 as d
+    for ours, theirs in ((d.MyDDIMScheduler, ref_modules["ddim"].MyDDIMScheduler),
+                         (d.MyDDPMScheduler, ref_modules["ddpm"].MyDDPMScheduler)):
+        for name in ("__init__", "set_timesteps", "step", "add_noise", "get_velocity", "scale_model_input"):
+            assert _params(getattr(ours, name)) == _params(getattr(theirs, name)), (ours.__name__, name)
+
+
+def test_pipeline_and_output_signatures(ref_modules):
+    import dataclasses
+    import d3roma_b200 as d
+    rp = ref_modules["pipelines"]
+    assert _params(d.GuidedDiffusionPipeline.__init__) == _params(rp.GuidedDiffusionPipeline.__init__)
+    assert _params(d.GuidedDiffusionPipeline.__call__) == _params(rp.GuidedDiffusionPipeline.__call__)
+    ours = [f.name for f in dataclasses.fields(d.GuidedPipelineOutput)]
+    theirs = [f.name for f in dataclasses.fields(rp.GuidedPipelineOutput)]
+    assert ours == theirs
+    for o, t in ((d.scheduler_ddim.DDIMSchedulerOutput, ref_modules["ddim"].DDIMSchedulerOutput),
+                 (d.scheduler_ddpm.DDPMSchedulerOutput, ref_modules["ddpm"].DDPMSchedulerOutput)):
+        assert [f.name for f in dataclasses.fields(o)] == [f.name for f in dataclasses.fields(t)]
+
+
+def test_guidance_and_prepost_signatures(ref_modules):
+    import d3roma_b200 as d
+    rg, ru = ref_modules["guidance"].FlowGuidance, ref_modules["utils"]
+    assert _params(d.FlowGuidance.perturb) == _params(rg.perturb)
+    ours, theirs = _params(d.FlowGuidance.__init__), _params(rg.__init__)
+    assert ours[:len(theirs)] == theirs and [p[0] for p in ours[len(theirs):]] == ["camera"]   # one trailing extra
+    for name in ("__init__", "normalize", "denormalize"):
+        assert _params(getattr(d.Normalizer, name)) == _params(getattr(ru.Normalizer, name)), name
+    for name in ("__init__", "pad", "unpad"):
+        assert _params(getattr(d.InputPadder, name)) == _params(getattr(ru.InputPadder, name)), name

@@ -155,10 +155,12 @@ def test_guidance_gradient_vs_reference_and_oracle():
         scale = ref.abs().max()
         bad = ((g - ref).abs() > 2e-3 * ref.abs() + 2e-4 * scale).float().mean().item()
         assert bad < 1e-3, bad  # isolated pixels may sit on a clamp / floor discontinuity
-    # perturb hook: x0' = x0 - w * grad
+    # perturb hook: x0' = x0 - w * d(loss)/d(x0) through the denormer; with the camera's own unnormalize_disp as the
+    # x0 -> pixels map this is x0 - w * grad(x0) (tests/test_guided_gpu.py covers the Normalizer chain)
     x0 = torch.from_numpy(z["a/disp"]).cuda()
     l, r = torch.from_numpy(z["a/left"]).cuda(), torch.from_numpy(z["a/right"]).cuda()
     fg.flow_guidance_weight = 0.01
-    torch.testing.assert_close(fg.perturb(x0, 5, None, None, left_image=l, right_image=r), x0 - 0.01 * fg.grad(x0, l, r))
+    torch.testing.assert_close(fg.perturb(x0, 5, None, fg.camera.unnormalize_disp, left_image=l, right_image=r),
+                               x0 - 0.01 * fg.grad(x0, l, r), rtol=1e-5, atol=1e-5)
     with pytest.raises(NotImplementedError):
         FlowGuidance().perturb(x0, 5, None, None)

@@ -38,9 +38,11 @@ def run(name, B, hw, cond_channels, cin, dc, steps, sched_cls, dtype, guidance_w
                                             batch["sim_disp"], batch["raw_depth"])
     gens = [torch.Generator().manual_seed(100 + i) for i in range(B)]
 
+    normer = d.Normalizer(ssi=False, mode="average", num_chs=dc, ch_bounds=[128.], ch_gammas=[1.], t=0.5, s=2.0)
+
     def once():
         return pipe(rgb, left, right, sim, raw, None, num_inference_steps=steps, num_intermediate_images=1,
-                    depth_channels=dc, cond_channels=cond_channels, generator=gens)
+                    depth_channels=dc, cond_channels=cond_channels, denorm=normer.denormalize, generator=gens)
     once()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

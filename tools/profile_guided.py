@@ -20,8 +20,9 @@ pipe = d.GuidedDiffusionPipeline(net, d.MyDDIMScheduler.from_config(cfg),
 rgb, left, right = (torch.rand(B, 3, 384, 640, device="cuda") * 2 - 1 for _ in range(3))
 raw = torch.rand(B, 1, 384, 640, device="cuda") * 2 - 1
 gens = [torch.Generator().manual_seed(i) for i in range(B)]
+normer = d.Normalizer(ssi=False, mode="average", num_chs=1, ch_bounds=[128.], ch_gammas=[1.], t=0.5, s=2.0)
 once = lambda: pipe(rgb, left, right, raw, None, None, num_inference_steps=10, num_intermediate_images=1,  # noqa: E731
-                    depth_channels=1, cond_channels="rgb+raw", generator=gens)
+                    depth_channels=1, cond_channels="rgb+raw", denorm=normer.denormalize, generator=gens)
 for _ in range(2):
     once()
 torch.cuda.synchronize()
