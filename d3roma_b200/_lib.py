@@ -109,10 +109,15 @@ def _declare(lib: C.CDLL) -> None:
         "d3_lincomb": (i32, [f32, vp, f32, vp, f32, vp, i64, vp, vp]),
         "d3_guidance_grad": (i32, [vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, f32, vp, vp]),
         "d3_guidance_step": (i32, [C.POINTER(GuidanceParams), vp]),
+        "d3_depth_to_rgb_frame_workspace_bytes": (C.c_size_t, [i32, i32]),
+        "d3_depth_to_rgb_frame": (i32, [vp, i32, i32, C.POINTER(f64), C.POINTER(f64), C.POINTER(f64), i32, i32, i32, i32,
+                                        i32, i32, i32, vp, vp, vp]),
         "d3_depth_to_disp": (i32, [vp, f32, i64, vp, vp]),
         "d3_disp_to_depth": (i32, [vp, f32, i64, vp, vp]),
         "d3_normalize_disp": (i32, [vp, i64, i64, i32, f32, f32, f32, f32, vp, vp]),
         "d3_denormalize_disp": (i32, [vp, i64, i64, i32, f32, f32, f32, f32, vp, vp]),
+        "d3_normalize_piecewise": (i32, [vp, i64, i64, i32, C.POINTER(f32), C.POINTER(f32), f32, f32, vp, vp]),
+        "d3_denormalize_piecewise": (i32, [vp, i64, i64, i32, C.POINTER(f32), C.POINTER(f32), f32, f32, vp, vp]),
         "d3_pad_replicate": (i32, [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]),
         "d3_crop": (i32, [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]),
         "d3_clamp_into": (i32, [vp, i64, i64, i64, i64, f32, f32, vp, vp]),

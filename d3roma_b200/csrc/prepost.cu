@@ -60,6 +60,46 @@ __global__ void denormalize_disp_kernel(const float* __restrict__ y, int64_t NR,
   }
 }
 
+// Normalizer "piecewise" mode (utils_d3roma/utils.py:198-229): the disparity is split over up to 3 channels, channel c
+// covering the range [sum_{j<c} bound_j, sum_{j<=c} bound_j):
+//   ch0 = min(x, b0) / b0, res0 = (ch0 < 1) ? 0 : x - b0;  ch1 = min(res0, b1) / b1, res1 = (ch1 < 1) ? 0 : res0 - b1; ...
+//   out_c = (ch_c ** gamma_c - t) * s        and back (utils.py:275-293):  sum_c (y_c / s + t) ** (1 / gamma_c) * b_c
+struct PiecewiseArgs {
+  float b[3], g[3];
+  int n;
+};
+
+__global__ void normalize_piecewise_kernel(const float* __restrict__ disp, int64_t N, int64_t HW, const PiecewiseArgs a,
+                                           float t, float s, float* __restrict__ out) {
+  float total = 0.f;
+  for (int c = 0; c < a.n; ++c) total = __fadd_rn(total, a.b[c]);
+  D3_GRID_STRIDE(i, N * HW) {
+    const int64_t n = i / HW, p = i - n * HW;
+    float x = fminf(disp[i], total);
+    for (int c = 0; c < a.n; ++c) {
+      const float ch = __fdiv_rn(fminf(x, a.b[c]), a.b[c]);
+      x = (ch < 1.0f) ? 0.f : __fsub_rn(x, a.b[c]);
+      const float y = (a.g[c] != 1.0f) ? powf(ch, a.g[c]) : ch;
+      out[(n * a.n + c) * HW + p] = __fmul_rn(__fsub_rn(y, t), s);
+    }
+  }
+}
+
+__global__ void denormalize_piecewise_kernel(const float* __restrict__ y, int64_t NR, int64_t HW, const PiecewiseArgs a,
+                                             float t, float s, float* __restrict__ out) {
+  D3_GRID_STRIDE(i, NR * HW) {
+    const int64_t n = i / HW, p = i - n * HW;
+    float z = 0.f;
+    for (int c = 0; c < a.n; ++c) {
+      float v = __fadd_rn(__fdiv_rn(y[(n * a.n + c) * HW + p], s), t);
+      if (a.g[c] != 1.0f) v = powf(v, 1.0f / a.g[c]);
+      const float term = __fmul_rn(v, a.b[c]);
+      z = (c == 0) ? term : __fadd_rn(z, term);
+    }
+    out[i] = z;
+  }
+}
+
 __global__ void disp_to_depth_kernel(const float* __restrict__ disp, float fxb, int64_t n, float* __restrict__ depth) {
   D3_GRID_STRIDE(i, n) {
     const float d = disp[i];
@@ -170,6 +210,133 @@ extern "C" int d3_clamp_into(const float* in, int64_t B, int64_t chw, int64_t ou
   if (B * chw == 0) return D3_OK;
   clamp_into_kernel<<<ew_blocks(B * chw), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, B, chw, out_bstride,
                                                                                       out_off, lo, hi, out);
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
+extern "C" int d3_normalize_piecewise(const float* disp, int64_t N, int64_t HW, int num_chs, const float* bounds,
+                                      const float* gammas, float t, float s, float* out, void* stream) {
+  using namespace d3;
+  D3_REQUIRE(disp && out && bounds && gammas, "normalize_piecewise: null pointer");
+  D3_REQUIRE(num_chs >= 1 && num_chs <= 3, "normalize_piecewise: num_chs must be 1..3 (got %d)", num_chs);
+  PiecewiseArgs a{};
+  a.n = num_chs;
+  for (int c = 0; c < num_chs; ++c) { a.b[c] = bounds[c]; a.g[c] = gammas[c]; }
+  if (N * HW == 0) return D3_OK;
+  normalize_piecewise_kernel<<<ew_blocks(N * HW), 256, 0, static_cast<cudaStream_t>(stream)>>>(disp, N, HW, a, t, s, out);
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
+extern "C" int d3_denormalize_piecewise(const float* y, int64_t NR, int64_t HW, int num_chs, const float* bounds,
+                                        const float* gammas, float t, float s, float* out, void* stream) {
+  using namespace d3;
+  D3_REQUIRE(y && out && bounds && gammas, "denormalize_piecewise: null pointer");
+  D3_REQUIRE(num_chs >= 1 && num_chs <= 3, "denormalize_piecewise: num_chs must be 1..3 (got %d)", num_chs);
+  PiecewiseArgs a{};
+  a.n = num_chs;
+  for (int c = 0; c < num_chs; ++c) { a.b[c] = bounds[c]; a.g[c] = gammas[c]; }
+  if (NR * HW == 0) return D3_OK;
+  denormalize_piecewise_kernel<<<ew_blocks(NR * HW), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, NR, HW, a, t, s, out);
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
+namespace d3 {
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------------
+// Depth map -> colour (RGB) camera frame: back-project every valid depth pixel with the depth intrinsics, move it into
+// the colour frame, project with the colour intrinsics and splat the ORIGINAL depth value at the rounded pixel
+// (DepthCamera.transform_depth_to_rgb_frame / transform_cropped_depth_to_rgb_frame,
+// /root/reference/utils_d3roma/camera.py:610-701).  The reference is numpy: float64 matrix products, then
+// `depth_map[v, u] = values` - a fancy-index assignment in which, for colliding targets, the LAST source pixel in
+// row-major order wins; with "aggressive_fill" four such assignments run one after the other on the
+// (floor, floor), (floor, ceil), (ceil, floor), (ceil, ceil) corners, later ones overwriting earlier ones.
+// Both orders are reproduced exactly with one 32-bit atomicMax per splat on the key (fill index, source index), followed
+// by a gather of the winning source's depth (fused with the output crop).  Arithmetic is fp64 like numpy's.
+// ------------------------------------------------------------------------------------------------------------------
+struct ReprojArgs {
+  double Kinv[9];   // inverse depth intrinsics, row-major
+  double T[12];     // colour <- depth rigid transform, row-major 3x4
+  double Kc[9];     // colour intrinsics, row-major
+  int H, W;         // source size
+  int CH, CW;       // canvas (colour image) size
+  int aggressive;
+};
+
+__global__ void reproject_scatter_kernel(const float* __restrict__ depth, const ReprojArgs a,
+                                         unsigned int* __restrict__ keys) {
+  const int64_t n = (int64_t)a.H * a.W;
+  D3_GRID_STRIDE(i, n) {
+    const float dz = depth[i];
+    const int y = (int)(i / a.W), x = (int)(i - (int64_t)y * a.W);
+    const double fx = (double)(float)x, fy = (double)(float)y;   // numpy builds the pixel grid in float32
+    // (Kinv @ [x, y, 1]) * depth
+    const double px = (a.Kinv[0] * fx + a.Kinv[1] * fy + a.Kinv[2]) * (double)dz;
+    const double py = (a.Kinv[3] * fx + a.Kinv[4] * fy + a.Kinv[5]) * (double)dz;
+    const double pz = (a.Kinv[6] * fx + a.Kinv[7] * fy + a.Kinv[8]) * (double)dz;
+    if (!(pz > 0.0)) continue;
+    const double cx = a.T[0] * px + a.T[1] * py + a.T[2] * pz + a.T[3];
+    const double cy = a.T[4] * px + a.T[5] * py + a.T[6] * pz + a.T[7];
+    const double cz = a.T[8] * px + a.T[9] * py + a.T[10] * pz + a.T[11];
+    const double qx = a.Kc[0] * cx + a.Kc[1] * cy + a.Kc[2] * cz;
+    const double qy = a.Kc[3] * cx + a.Kc[4] * cy + a.Kc[5] * cz;
+    const double qz = a.Kc[6] * cx + a.Kc[7] * cy + a.Kc[8] * cz;
+    const double u = qx / qz, v = qy / qz;
+    const int nfill = a.aggressive ? 4 : 1;
+    for (int f = 0; f < nfill; ++f) {
+      double uu, vv;
+      if (a.aggressive) {
+        uu = (f & 2) ? ceil(u) : floor(u);     // fills: (left, up), (left, bottom), (right, up), (right, bottom)
+        vv = (f & 1) ? ceil(v) : floor(v);
+      } else {
+        uu = rint(u);                           // np.round: half to even
+        vv = rint(v);
+      }
+      // astype(np.uint32) wraps negative values to huge ones (rejected by the `< W` test); -0.0 becomes 0
+      if (!(uu >= 0.0 && uu < (double)a.CW && vv >= 0.0 && vv < (double)a.CH)) continue;
+      const unsigned int key = ((unsigned int)(f + 1) << 28) | (unsigned int)i;
+      atomicMax(keys + (size_t)(int)vv * a.CW + (int)uu, key);
+    }
+  }
+}
+
+__global__ void reproject_gather_kernel(const float* __restrict__ depth, const unsigned int* __restrict__ keys, int CW,
+                                        int oy, int ox, int OH, int OW, float* __restrict__ out) {
+  D3_GRID_STRIDE(i, (int64_t)OH * OW) {
+    const int y = (int)(i / OW), x = (int)(i - (int64_t)y * OW);
+    const unsigned int k = keys[(size_t)(y + oy) * CW + (x + ox)];
+    out[i] = k ? depth[k & 0x0FFFFFFFu] : 0.f;
+  }
+}
+
+}  // namespace
+}  // namespace d3
+
+extern "C" size_t d3_depth_to_rgb_frame_workspace_bytes(int canvas_h, int canvas_w) {
+  return (size_t)canvas_h * canvas_w * sizeof(unsigned int);
+}
+
+extern "C" int d3_depth_to_rgb_frame(const float* depth, int H, int W, const double* Kinv_depth, const double* T_cl,
+                                     const double* K_color, int canvas_h, int canvas_w, int aggressive_fill, int crop_y,
+                                     int crop_x, int out_h, int out_w, void* workspace, float* out, void* stream) {
+  using namespace d3;
+  D3_REQUIRE(depth && Kinv_depth && T_cl && K_color && workspace && out, "depth_to_rgb_frame: null pointer");
+  D3_REQUIRE(H > 0 && W > 0 && (int64_t)H * W < (1 << 28), "depth_to_rgb_frame: bad source size %dx%d", H, W);
+  D3_REQUIRE(canvas_h > 0 && canvas_w > 0 && crop_y >= 0 && crop_x >= 0 && crop_y + out_h <= canvas_h &&
+                 crop_x + out_w <= canvas_w && out_h > 0 && out_w > 0,
+             "depth_to_rgb_frame: crop window outside the %dx%d canvas", canvas_h, canvas_w);
+  ReprojArgs a;
+  for (int i = 0; i < 9; ++i) { a.Kinv[i] = Kinv_depth[i]; a.Kc[i] = K_color[i]; }
+  for (int i = 0; i < 12; ++i) a.T[i] = T_cl[i];
+  a.H = H; a.W = W; a.CH = canvas_h; a.CW = canvas_w; a.aggressive = aggressive_fill ? 1 : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  D3_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)canvas_h * canvas_w * sizeof(unsigned int), st));
+  reproject_scatter_kernel<<<ew_blocks((int64_t)H * W), 256, 0, st>>>(depth, a, static_cast<unsigned int*>(workspace));
+  D3_LAUNCH_CHECK();
+  reproject_gather_kernel<<<ew_blocks((int64_t)out_h * out_w), 256, 0, st>>>(
+      depth, static_cast<const unsigned int*>(workspace), canvas_w, crop_y, crop_x, out_h, out_w, out);
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

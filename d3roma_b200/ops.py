@@ -397,6 +397,35 @@ def denormalize_disp(y, num_chs: int, bound: float, gamma: float, t: float, s: f
     return out
 
 
+def _f32_array(vals):
+    arr = (C.c_float * len(vals))(*[float(v) for v in vals])
+    return arr
+
+
+def normalize_piecewise(disp, bounds, gammas, t: float, s: float):
+    """disp [..., H, W] -> [N * len(bounds), H, W] (``d3_normalize_piecewise``)."""
+    d = _f32c(disp, "disp")
+    H, W = d.shape[-2:]
+    N = d.numel() // (H * W)
+    n = len(bounds)
+    out = torch.empty((N * n, H, W), dtype=torch.float32, device=d.device)
+    _lib.check(_lib.lib().d3_normalize_piecewise(d.data_ptr(), N, H * W, n, _f32_array(bounds), _f32_array(gammas), t, s,
+                                                 out.data_ptr(), _stream()))
+    return out
+
+
+def denormalize_piecewise(y, bounds, gammas, t: float, s: float):
+    """y [B, R*n, H, W] -> [B, R, H, W] (``d3_denormalize_piecewise``)."""
+    y = _f32c(y, "y")
+    B, Cc, H, W = y.shape
+    n = len(bounds)
+    R = Cc // n
+    out = torch.empty((B, R, H, W), dtype=torch.float32, device=y.device)
+    _lib.check(_lib.lib().d3_denormalize_piecewise(y.data_ptr(), B * R, H * W, n, _f32_array(bounds), _f32_array(gammas),
+                                                   t, s, out.data_ptr(), _stream()))
+    return out
+
+
 def pad_replicate(x, pads):
     """x [B,C,H,W] fp32, pads = [left, right, top, bottom] (InputPadder._pad order)."""
     x = _f32c(x, "x")

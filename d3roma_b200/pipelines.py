@@ -49,6 +49,8 @@ class GuidedDiffusionPipeline:
         self.register_modules(unet=unet, scheduler=scheduler, guidance=guidance)
         self._progress_bar_config = {}
         self.use_cuda_graph = True
+        self.graph_whole_loop = True    # deterministic DDIM loops: ONE graph for all steps (UNet forwards + scheduler steps)
+        self._loop_graphs = {}
 
     # ---- DiffusionPipeline-ish plumbing used by the callers (inference.py:71-91,215; evaluate.py:314-317)
     def register_modules(self, **kwargs):
@@ -134,6 +136,8 @@ class GuidedDiffusionPipeline:
             import inspect
             step_kw = {"denormer": denorm} if "denormer" in inspect.signature(self.scheduler.step).parameters else {}
         n_plots = num_inference_steps // plot_every
+        if self._whole_loop_ok(image, cond, add_noise_rgb, guided):
+            return self._loop_graphed(image, cond, num_inference_steps, plot_every)
         stack = torch.empty((batch_size, depth_channels * n_plots, image.shape[2], image.shape[3]),
                             dtype=torch.float32, device=dev)
         fwd = self.unet.forward_graphed if self.use_cuda_graph else self.unet.forward_split
@@ -157,6 +161,81 @@ class GuidedDiffusionPipeline:
             step += 1
         image = ops.clamp_into(image, torch.empty_like(image), 0)
         return image, stack
+
+    # ---- whole-loop CUDA graph ------------------------------------------------------------------------------------
+    def _whole_loop_ok(self, image, cond, add_noise_rgb, guided) -> bool:
+        """The unguided DDIM loop is a fixed sequence of kernels (no host-side randomness, every scalar known up front:
+        the timestep embeddings and the scheduler coefficients of all steps are baked into the graph), so all N x (UNet
+        forward + scheduler step) replay as ONE graph launch - no per-step host work at all (the B = 1 latency case)."""
+        from .scheduler_ddim import MyDDIMScheduler
+        u = self.unet
+        return (self.use_cuda_graph and self.graph_whole_loop and not add_noise_rgb and not guided and cond is not None
+                and type(self.scheduler) is MyDDIMScheduler and hasattr(u, "forward_split")
+                and getattr(u, "compute_dtype", "fp32") != "fp32" and image.shape[1] <= 3 and image.is_cuda
+                and self._progress_bar_config.get("disable", True) and "desc" not in self._progress_bar_config)
+
+    def _loop_graphed(self, image, cond, num_inference_steps, plot_every):
+        from . import _lib
+        from .unet import _StatsArena
+        u, sch = self.unet, self.scheduler
+        B, dc, H, W = image.shape
+        key = self._loop_key(image.shape, cond, num_inference_steps, plot_every)
+        g = self._loop_graphs.get(key)
+        if g is None:
+            for k in [k for k in self._loop_graphs if k[:3] == key[:3]]:   # same shapes, stale weights / scheduler
+                del self._loop_graphs[k]
+            n_plots = num_inference_steps // plot_every
+            g = {"x": image.clone(), "c": cond.clone(), "arena": _StatsArena(image.device, B * 2 * 40000),
+                 "ts": [torch.full((1,), float(t), dtype=torch.float32, device=image.device) for t in sch.timesteps],
+                 "stack": torch.empty((B, dc * n_plots, H, W), dtype=torch.float32, device=image.device),
+                 "img": torch.empty_like(image)}
+            g["tb"] = [u.time_bias(t) for t in g["ts"]]    # all steps' time-embedding rows, once per graph (SURVEY 2.3)
+            g["base"] = u.cond_base(g["c"], dc, out=torch.empty((B, H, W, 128), dtype=u._base_dtype, device=image.device))
+            g["cond_key"], g["cond_ref"] = u._cond_key(cond), cond   # the tensor is held: see UNet2DModel._cond_key
+
+            def run():
+                x = g["x"]
+                for i, t in enumerate(sch.timesteps):
+                    m = u.forward_split(x, g["c"], g["ts"][i], cond_base=g["base"], arena=g["arena"], tb=g["tb"][i])
+                    x = sch.step(m, t, x).prev_sample
+                    if (i + 1) % plot_every == 0:
+                        ops.clamp_into(x, g["stack"], (i + 1) // plot_every - 1)
+                ops.clamp_into(x, g["img"], 0)
+
+            side = torch.cuda.Stream(device=image.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                u.forward_split(g["x"], g["c"], g["ts"][0], cond_base=g["base"], arena=g["arena"])   # warm-up
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.lib().d3_launch_count()
+            with torch.cuda.graph(graph):
+                run()
+            g["n_kernels"] = int(_lib.lib().d3_launch_count() - n0)
+            g["graph"] = graph
+            self._loop_graphs[key] = g
+        g["x"].copy_(image)
+        self._refresh_loop_cond(g, cond, dc)
+        g["graph"].replay()
+        u.graph_kernel_launches += g["n_kernels"]
+        return g["img"].clone(), g["stack"].clone()
+
+    def _loop_key(self, image_shape, cond, num_inference_steps, plot_every):
+        u, sch = self.unet, self.scheduler
+        return (tuple(image_shape), tuple(cond.shape), cond.device.index, num_inference_steps, plot_every, id(u),
+                getattr(u, "_weights_epoch", 0), id(sch), tuple(sorted((k, str(v)) for k, v in dict(sch.config).items())))
+
+    def _refresh_loop_cond(self, g, cond, dc):
+        ck = self.unet._cond_key(cond)
+        if g["cond_key"] != ck:
+            g["c"].copy_(cond)
+            g["cond_key"], g["cond_ref"] = ck, cond
+            self.unet.cond_base(g["c"], dc, out=g["base"])
+
+    def reset_graphs(self):
+        self._loop_graphs.clear()
+        if hasattr(self.unet, "reset_graphs"):
+            self.unet.reset_graphs()
 
     @torch.no_grad()
     def sample_from(self, x_T: torch.Tensor, cond: torch.Tensor, num_inference_steps: int = 10,
@@ -201,7 +280,13 @@ class GuidedDiffusionPipeline:
 
         cond = None if add_noise_rgb else build_cond()
         if cond is not None and hasattr(self.unet, "prime_conditioning"):
-            self.unet.prime_conditioning(shape, cond, self.use_cuda_graph)   # GPU works while the host draws x_T
+            # the GPU starts on the per-loop conditioning work while the host still draws x_T
+            g = self._loop_graphs.get(self._loop_key(shape, cond, num_inference_steps, plot_every)) \
+                if self.use_cuda_graph and self.graph_whole_loop else None
+            if g is not None:
+                self._refresh_loop_cond(g, cond, shape[1])
+            else:
+                self.unet.prime_conditioning(shape, cond, self.use_cuda_graph)
         # CPU draw, then moved (custom_pipelines.py:117-123); with CPU generator(s) the values do not depend on the target
         # device, so the per-sample draws go straight into a pinned buffer and across asynchronously
         image = randn_tensor(shape, generator=generator, device=dev if generator is not None else None)

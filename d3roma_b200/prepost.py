@@ -7,7 +7,8 @@
 
 Every tensor op runs in ``libd3roma_b200.so`` (one fused pass each).  ``ssi=True`` (DREDS / ClearPose configs) is
 supported with the direct least-squares alignment (``safe_ssi=False``) and the RANSAC variant (``safe_ssi=True``,
-``metrics.RANSAC``); the piecewise multi-channel mode is not implemented.
+``metrics.RANSAC``); both channel layouts are implemented: "average" (the pixel-space configs) and "piecewise" (up
+to three range-splitting channels, the LDM-family configs; utils.py:198-229, 275-293).
 """
 from __future__ import annotations
 
@@ -92,9 +93,12 @@ class Normalizer:
     def _check(self):
         if self.ssi:
             return
-        if self.mode != "average":
-            raise NotImplementedError("only normalize_mode='average' (the pixel-space configs) is implemented")
-        assert len(self.ch_bounds) == len(self.ch_gammas) == 1, "inconsistent params"
+        if self.mode == "average":
+            assert len(self.ch_bounds) == len(self.ch_gammas) == 1, "inconsistent params"
+        else:   # "piecewise" (utils.py:198-229): one bound / gamma per channel
+            assert len(self.ch_bounds) == len(self.ch_gammas) == self.num_chs, "inconsistent params"
+            if not 1 <= self.num_chs <= 3:
+                raise RuntimeError("not implemented")
 
     def normalize(self, x: torch.Tensor, mask=None, low=None, up=None):
         """[1,H,W] raw disparity -> ([num_chs,H,W] in [-1,1], None, None)   (utils.py:171-196)."""
@@ -111,8 +115,11 @@ class Normalizer:
             y = ops.normalize_ssi(x.reshape(1, -1), None if m is None else m.reshape(1, -1), lu, float(self.t),
                                   float(self.s)).view_as(x)
             return y, lu[0, 0], lu[0, 1]
-        y = ops.normalize_disp(x, self.num_chs, float(self.ch_bounds[0]), float(self.ch_gammas[0]), float(self.t),
-                               float(self.s))
+        if self.mode != "average":
+            y = ops.normalize_piecewise(x, self.ch_bounds, self.ch_gammas, float(self.t), float(self.s))
+        else:
+            y = ops.normalize_disp(x, self.num_chs, float(self.ch_bounds[0]), float(self.ch_gammas[0]), float(self.t),
+                                   float(self.s))
         return y.view(x.shape[0] * self.num_chs, *x.shape[1:]), None, None
 
     def denormalize(self, y: torch.Tensor, raw_disp=None, mask=None):
@@ -133,6 +140,8 @@ class Normalizer:
             else:
                 st = ops.scale_shift_lsq(pred, gt, mk)
             return ops.affine_rows(pred, st).view(B, R, H, W)
+        if self.mode != "average":
+            return ops.denormalize_piecewise(y, self.ch_bounds, self.ch_gammas, float(self.t), float(self.s))
         return ops.denormalize_disp(y, self.num_chs, float(self.ch_bounds[0]), float(self.ch_gammas[0]),
                                     float(self.t), float(self.s))
 

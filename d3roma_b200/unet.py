@@ -25,6 +25,7 @@ There is no PyTorch fallback: without the CUDA library every call raises.
 """
 from __future__ import annotations
 
+import os
 from types import SimpleNamespace
 from typing import Dict, List, Optional, Sequence
 
@@ -126,6 +127,7 @@ class UNet2DModel:
         self._arena: Optional[_StatsArena] = None         # arena of the forward in flight
         self._eager_arena: Optional[_StatsArena] = None   # arena of the non-graph path (grown on demand)
         self._loaded = False
+        self.identity_slab = os.environ.get("D3_UNET_IDENTITY_SLAB", "1") != "0"   # A/B switch, see load_state_dict
         self.keep_state_dict = True   # keep a host copy of the loaded fp32 state_dict (for save_pretrained)
         self._sd_cpu = None
         self._graphs: Dict[tuple, dict] = {}
@@ -174,7 +176,7 @@ class UNet2DModel:
             if cin_h + cin_s != cout:
                 W[p + ".w2"] = ops.pack_conv_weight(get(p + ".conv2.weight"), get(p + ".conv_shortcut.weight"), dtype=self._adt)
                 b2 = b2 + get(p + ".conv_shortcut.bias")
-            elif cout == 128 and self._adt != torch.float32:
+            elif cout == 128 and self._adt != torch.float32 and self.identity_slab:
                 # identity residual of the 128-channel layers as two extra K-blocks with an identity "shortcut" weight:
                 # exact (x * 1.0 accumulated in fp32) and 11 % more MMA work, where the residual read-back in the
                 # pixels-as-N epilogue measured +34 % (profiles/r01_conv_experiments.txt)
@@ -385,8 +387,25 @@ class UNet2DModel:
         return base
 
     @torch.no_grad()
+    def time_bias(self, timestep, device=None, batch: int = 1) -> torch.Tensor:
+        """Timestep -> the fused per-ResNet bias rows ``[nt, rows]`` (sinusoidal embedding, 2-layer MLP, all 32
+        ``time_emb_proj`` + conv1 biases).  Depends on the scalar ``t`` only: a sampling loop can compute the rows of all
+        its steps before the loop and hand them to ``forward_split(tb=...)``."""
+        dev = self.device if device is None else device
+        W = self._w
+        if torch.is_tensor(timestep):
+            t = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
+        else:
+            t = torch.tensor([float(timestep)], dtype=torch.float32, device=dev)
+        if t.numel() not in (1, batch):
+            raise ValueError("timestep must be a scalar or have one entry per sample")
+        semb = ops.time_embed(t, W["time.w1t"], W["time.b1"], W["time.w2t"], W["time.b2"])
+        return ops.temb_project_all(semb, W["temb.w"], W["temb.b"])  # [nt, rows]
+
+    @torch.no_grad()
     def forward_split(self, sample: torch.Tensor, cond: Optional[torch.Tensor], timestep,
-                      cond_base: Optional[torch.Tensor] = None, arena: Optional[_StatsArena] = None) -> torch.Tensor:
+                      cond_base: Optional[torch.Tensor] = None, arena: Optional[_StatsArena] = None,
+                      tb: Optional[torch.Tensor] = None) -> torch.Tensor:
         """UNet forward on ``cat([sample, cond], 1)`` without materialising the concat.
         sample fp32 [B,dc,H,W], cond fp32 [B,Cc,H,W] (contiguous, CUDA); returns fp32 [B,out_channels,H,W].
         ``cond_base``: precomputed ``self.cond_base(cond, Cs)`` (the CUDA-graph path passes its static buffer).
@@ -414,15 +433,9 @@ class UNet2DModel:
             self._arena = self._eager_arena
         self._arena.reset()
 
-        # timestep -> fused per-ResNet bias vectors
-        if torch.is_tensor(timestep):
-            t = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
-        else:
-            t = torch.tensor([float(timestep)], dtype=torch.float32, device=dev)
-        if t.numel() not in (1, B):
-            raise ValueError("timestep must be a scalar or have one entry per sample")
-        semb = ops.time_embed(t, W["time.w1t"], W["time.b1"], W["time.w2t"], W["time.b2"])
-        tb = ops.temb_project_all(semb, W["temb.w"], W["temb.b"])  # [nt, rows]
+        # timestep -> fused per-ResNet bias vectors (``tb``: precomputed by the caller with time_bias())
+        if tb is None:
+            tb = self.time_bias(timestep, dev, B)
 
         def bias1(p, cout):
             o = self._temb_off[p]
@@ -495,7 +508,8 @@ class UNet2DModel:
     @staticmethod
     def _cond_key(cond: Optional[torch.Tensor]):
         """Identity of a conditioning tensor's CONTENTS: storage address, in-place version counter and shape (the same
-        key ``cond_base`` uses) - a caller that refills one preallocated buffer per frame bumps the version."""
+        key ``cond_base`` uses) - a caller that refills one preallocated buffer per frame bumps the version.  Whoever
+        stores the key must also hold the tensor (an address is only unique among LIVE tensors)."""
         return None if cond is None else (cond.data_ptr(), cond._version, tuple(cond.shape))
 
     def _graph_for(self, sample: torch.Tensor, cond: Optional[torch.Tensor], tval: float) -> dict:
@@ -530,7 +544,7 @@ class UNet2DModel:
             g["y"] = self.forward_split(g["x"], g["c"], g["t"], cond_base=g["base"], arena=g["arena"])
         g["n_kernels"] = int(_lib.lib().d3_launch_count() - n0)
         g["graph"] = graph
-        g["cond_key"] = self._cond_key(cond)
+        g["cond_key"], g["cond_ref"] = self._cond_key(cond), cond
         self._graphs[key] = g
         return g
 
@@ -543,7 +557,9 @@ class UNet2DModel:
         if g["cond_key"] == key:
             return
         g["c"].copy_(cond)
-        g["cond_key"] = key
+        # the key names a storage address: hold the tensor so that the allocator cannot hand the same address (with a
+        # fresh version counter) to a DIFFERENT conditioning tensor while the key is still trusted
+        g["cond_key"], g["cond_ref"] = key, cond
         if g["base"] is not None:
             self.cond_base(g["c"], Cs, out=g["base"])
 
@@ -578,6 +594,7 @@ class UNet2DModel:
 
     def reset_graphs(self):
         self._graphs.clear()
+        self._weights_epoch = getattr(self, "_weights_epoch", 0) + 1   # invalidates pipeline-level whole-loop graphs
 
     @torch.no_grad()
     def __call__(self, sample: torch.Tensor, timestep, return_dict: bool = True):

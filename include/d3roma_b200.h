@@ -197,6 +197,19 @@ int d3_sched_ddpm_step(const float* model_output, const float* sample, const flo
 int d3_lincomb(float a, const float* x, float b, const float* y, float c, const float* z, int64_t n, float* out,
                void* stream);
 
+/* ---- depth map -> colour-camera frame (DepthCamera.transform_depth_to_rgb_frame and
+ * transform_cropped_depth_to_rgb_frame, utils_d3roma/camera.py:610-701): back-project with the inverse depth intrinsics
+ * (row-major 3x3, float64), apply T_cl (row-major 3x4), project with the colour intrinsics, write the source depth at the
+ * rounded target pixel of a canvas_h x canvas_w map and return the window [crop_y, crop_y+out_h) x [crop_x, crop_x+out_w).
+ * numpy's collision order is reproduced exactly: within one fill the last source pixel in row-major order wins;
+ * aggressive_fill runs the four (floor|ceil) corner fills in the reference's order, later fills overwriting earlier
+ * ones.  depth fp32 [H,W] (device); the three matrices are HOST pointers; workspace = device scratch of
+ * d3_depth_to_rgb_frame_workspace_bytes(canvas_h, canvas_w) bytes. */
+size_t d3_depth_to_rgb_frame_workspace_bytes(int canvas_h, int canvas_w);
+int d3_depth_to_rgb_frame(const float* depth, int H, int W, const double* Kinv_depth, const double* T_cl,
+                          const double* K_color, int canvas_h, int canvas_w, int aggressive_fill, int crop_y,
+                          int crop_x, int out_h, int out_w, void* workspace, float* out, void* stream);
+
 /* ---- stereo photometric guidance (FlowGuidance.grad stereo branch, core/guidance.py:298-323 + SSIM :28-42) and the
  * guided update of the scheduler hook (core/scheduler_ddim.py:461-468, core/scheduler_ddpm.py:506-516), one kernel.
  *   disparity [px] = clip(disp_offset + disp_scale * sum_c x0[b,c,y,x], min_disp, max_disp)
@@ -242,6 +255,13 @@ int d3_normalize_disp(const float* disp, int64_t N, int64_t HW, int num_chs, flo
  * sum_c (y_c / s + t) ** (1/gamma) * (bound / num_chs). */
 int d3_denormalize_disp(const float* y, int64_t NR, int64_t HW, int num_chs, float bound, float gamma, float t,
                         float s, float* out, void* stream);
+/* Normalizer mode="piecewise" (utils_d3roma/utils.py:198-229, 275-293; the LDM-family configs): the disparity is split
+ * over num_chs <= 3 channels, channel c covering bounds[c] pixels with its own gamma.  bounds / gammas are HOST arrays of
+ * num_chs floats.  disp [N][HW] -> out [N][num_chs][HW];  y [NR][num_chs][HW] -> out [NR][HW]. */
+int d3_normalize_piecewise(const float* disp, int64_t N, int64_t HW, int num_chs, const float* bounds,
+                           const float* gammas, float t, float s, float* out, void* stream);
+int d3_denormalize_piecewise(const float* y, int64_t NR, int64_t HW, int num_chs, const float* bounds,
+                             const float* gammas, float t, float s, float* out, void* stream);
 /* InputPadder.pad (replicate) / unpad (utils.py:313-325) over `planes` = B*C planes of H x W. */
 int d3_pad_replicate(const float* in, int64_t planes, int H, int W, int left, int right, int top, int bottom,
                      float* out, void* stream);

@@ -394,6 +394,59 @@ def gen_guided(store):
         store[f"{tag}/final_loss"] = np.float64(g.log[-1]["loss"])
 
 
+def gen_piecewise(store):
+    """Normalizer(mode="piecewise") of the reference (utils_d3roma/utils.py:198-229, 275-293): 3 channels with bounds
+    [64, 32, 32] (the class defaults), 2 channels with a gamma, and the 1-channel degenerate case."""
+    g = torch.Generator().manual_seed(17)
+    disp = torch.rand(1, 20, 36, generator=g) * 150.0     # beyond the 128 total bound -> clamp path
+    disp[0, :3, :5] = 0.0
+    disp[0, 5, :4] = torch.tensor([64.0, 96.0, 128.0, 63.999])   # exactly on the channel boundaries
+    for tag, kw in (("pw3", dict(num_chs=3, ch_bounds=[64., 32., 32.], ch_gammas=[1., 1., 1.])),
+                    ("pw2g", dict(num_chs=2, ch_bounds=[64., 64.], ch_gammas=[0.5, 1.])),
+                    ("pw1", dict(num_chs=1, ch_bounds=[128.], ch_gammas=[1.]))):
+        n = Normalizer(ssi=False, mode="piecewise", t=0.5, s=2.0, **kw)
+        store[f"{tag}/in"] = _np(disp)
+        store[f"{tag}/out"] = _np(n.normalize(disp.clone())[0])
+        pred = torch.rand(2, 2 * kw["num_chs"], 20, 36, generator=g) * 2 - 1
+        store[f"{tag}/den_in"] = _np(pred)
+        store[f"{tag}/den_out"] = _np(n.denormalize(pred.clone()))
+        # round trip of a normalised map
+        store[f"{tag}/roundtrip"] = _np(n.denormalize(n.normalize(disp.clone())[0][None]))
+
+
+def gen_reproject(store):
+    """Depth -> colour-frame reprojection (camera.py:610-701) run by the reference's own real-camera object
+    (Realsense.default_real("wsl"): non-identity colour<-depth extrinsics) on small synthetic depth maps with holes:
+    the aggressive (4-corner) fill, the single rounded fill, and the cropped variant."""
+    cam = ref_camera.Realsense.default_real("wsl")
+    rng = np.random.default_rng(5)
+    H, W = cam.H, cam.W
+    store["hw"] = np.array([H, W])
+    store["K_depth"], store["K_color"] = cam.K_depth.vec, cam.K_color.vec
+    store["color_to_depth"], store["T_fc"], store["T_cl"] = cam.extrinsics["color_to_depth"], cam._T_fc, cam.T_cl
+    ys, xs = np.mgrid[0:H, 0:W]
+    # sensor-like depth: millimetre-quantised uint16 (stored as such: the fixture stays small), metres = mm / 1000
+    mm = np.round((0.45 + 0.35 * np.sin(xs / 37.0) * np.cos(ys / 23.0)) * 1000.0 + rng.integers(0, 3, (H, W)))
+    mm[(xs * 7 + ys * 13) % 11 == 0] = 0                 # holes
+    mm[100:140, 200:260] = 310                           # a near box: occlusion / collisions at its border
+    mm = mm.astype(np.uint16)
+    depth = mm.astype(np.float32) / np.float32(1000.0)
+    store["depth_mm"] = mm
+    to_mm = lambda o: np.round(o.astype(np.float64) * 1000.0).astype(np.uint16)   # noqa: E731  (outputs are copies of inputs)
+    cam.config["aggressive_fill"] = True
+    store["out_aggressive_mm"] = to_mm(cam.transform_depth_to_rgb_frame(depth.copy()))
+    cam.config["aggressive_fill"] = False
+    store["out_round_mm"] = to_mm(cam.transform_depth_to_rgb_frame(depth.copy()))
+    # cropped variant: a 200 x 320 window of the sensor image with shifted principal point
+    oy, ox, ch, cw = 60, 110, 200, 320
+    cropped_K = cam.K_depth.arr.copy()
+    cropped_K[0, 2] -= ox
+    cropped_K[1, 2] -= oy
+    store["cropped_K"], store["crop"] = cropped_K, np.array([oy, ox, ch, cw])
+    store["out_cropped_mm"] = to_mm(cam.transform_cropped_depth_to_rgb_frame(depth[oy:oy + ch, ox:ox + cw].copy(),
+                                                                             cropped_K))
+
+
 def gen_postproc(store):
     """compute_errors / compute_scale_and_shift / Normalizer(ssi=True) of the reference (utils_d3roma/utils.py)."""
     g = torch.Generator().manual_seed(31)
@@ -506,7 +559,7 @@ def main():
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
     for name, fn in (("ddim", gen_ddim), ("ddpm", gen_ddpm), ("prepost", gen_prepost), ("guidance", gen_guidance),
-                     ("pipeline", gen_pipeline), ("guided", gen_guided), ("postproc", gen_postproc), ("frontend", gen_frontend), ("ransac", gen_ransac)):
+                     ("pipeline", gen_pipeline), ("guided", gen_guided), ("reproject", gen_reproject), ("piecewise", gen_piecewise), ("postproc", gen_postproc), ("frontend", gen_frontend), ("ransac", gen_ransac)):
         store = {}
         with torch.no_grad():
             fn(store)

@@ -33,6 +33,30 @@ def denormalize_average(y: torch.Tensor, bound: float, gamma: float = 1.0, num_c
     return z.view(B, R, H, W)
 
 
+def normalize_piecewise(x: torch.Tensor, bounds, gammas, t: float = 0.5, s: float = 2.0) -> torch.Tensor:
+    """utils.py:186-189, 198-229: [1,H,W] -> [len(bounds),H,W]; channel c carries the part of the disparity inside
+    [sum(bounds[:c]), sum(bounds[:c+1])), divided by its bound, ** gamma_c; then (y - t) * s."""
+    x = torch.clamp(x, max=torch.sum(torch.tensor(bounds, dtype=torch.float32)))
+    chans, res = [], x
+    for b, g in zip(bounds, gammas):
+        ch = torch.minimum(res, torch.ones_like(res) * b) / b
+        res = torch.where(ch < 1.0, torch.zeros_like(res), res - b)
+        chans.append(ch ** g)
+    return (torch.cat(chans, dim=0) - t) * s
+
+
+def denormalize_piecewise(y: torch.Tensor, bounds, gammas, t: float = 0.5, s: float = 2.0) -> torch.Tensor:
+    """utils.py:252-258, 275-293: [B,R*n,H,W] -> [B,R,H,W]; sum_c (y_c/s+t)^(1/gamma_c) * bound_c."""
+    B, C, H, W = y.shape
+    n = len(bounds)
+    R = C // n
+    v = y.view(B * R, n, H, W) / s + t
+    z = v[:, 0:1] ** (1 / gammas[0]) * bounds[0]
+    for c in range(1, n):
+        z = z + v[:, c:c + 1] ** (1 / gammas[c]) * bounds[c]
+    return z.view(B, R, H, W)
+
+
 def pad_amounts(h: int, w: int, divis_by: int = 32):
     """utils.py:299-304 ('sintel' mode): [left, right, top, bottom]."""
     ph = (((h // divis_by) + 1) * divis_by - h) % divis_by

@@ -93,3 +93,41 @@ def test_d3roma_infer_matches_reference_flow():
     disp = ((pred / 2.0 + 0.5) * 128.0).mean(dim=0)[0]
     want = torch.where(disp > 0, cam.fxb / disp, torch.zeros_like(disp)).numpy()
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+def test_depth_to_rgb_frame_reprojection_bit_exact_vs_reference_and_oracle():
+    """DepthCamera.transform_depth_to_rgb_frame / transform_cropped_depth_to_rgb_frame (utils_d3roma/camera.py:610-701)
+    on the device: bit-identical to the reference camera object's outputs (tests/golden/reproject.npz, including numpy's
+    last-writer-wins collision order and the 4-corner aggressive fill) and to the oracle on a larger random map."""
+    from pathlib import Path
+    import numpy as np
+    from d3roma_b200.camera import DepthCamera
+    from oracle import reproject_ref as R
+    z = np.load(Path(__file__).resolve().parent / "golden" / "reproject.npz")
+    H, W = (int(v) for v in z["hw"])
+    cam = DepthCamera(f"{W}x{H}", 1.0, intrinsics={"color": z["K_color"], "depth": z["K_depth"]},
+                      extrinsics={"color_to_depth": z["color_to_depth"]}, T_fc=z["T_fc"],
+                      config={"auto_scale": True, "aggressive_fill": True})
+    assert np.allclose(cam.T_cl, z["T_cl"])
+    depth = z["depth_mm"].astype(np.float32) / np.float32(1000.0)
+    mm = lambda o: np.round(o.astype(np.float64) * 1000.0).astype(np.uint16)   # noqa: E731
+    out = cam.transform_depth_to_rgb_frame(depth)
+    assert isinstance(out, np.ndarray) and np.array_equal(mm(out), z["out_aggressive_mm"])
+    cam.config["aggressive_fill"] = False
+    out_t = cam.transform_depth_to_rgb_frame(torch.from_numpy(depth).cuda())        # device in, device out
+    assert out_t.is_cuda and np.array_equal(mm(out_t.cpu().numpy()), z["out_round_mm"])
+    oy, ox, ch, cw = (int(v) for v in z["crop"])
+    out_c = cam.transform_cropped_depth_to_rgb_frame(depth[oy:oy + ch, ox:ox + cw], z["cropped_K"])
+    assert np.array_equal(mm(out_c), z["out_cropped_mm"])
+    # random depth (every value distinct: exposes any difference in collision order) against the oracle, both fills
+    rng = np.random.default_rng(3)
+    d2 = (rng.random((H, W)) * 1.5 + 0.25).astype(np.float32)
+    d2[rng.random((H, W)) < 0.2] = 0.0
+    for aggressive in (True, False):
+        cam.config["aggressive_fill"] = aggressive
+        want = R.reproject(d2, cam.K_depth.inv, cam.T_cl, cam.K_color.arr, (H, W), aggressive)
+        assert np.array_equal(cam.transform_depth_to_rgb_frame(d2), want)
+    # identity extrinsics: returned unchanged, like the reference (:655-657)
+    cam_id = DepthCamera(f"{W}x{H}", 1.0, intrinsics={"color": z["K_color"], "depth": z["K_depth"]},
+                         extrinsics={"color_to_depth": np.eye(4)})
+    assert cam_id.transform_depth_to_rgb_frame(depth) is depth

@@ -34,6 +34,18 @@ def test_normalizer_bit_exact():
         np.testing.assert_array_equal(d.numpy(), z[f"norm/{tag}/den_out"])
 
 
+PIECEWISE = {"pw3": ([64., 32., 32.], [1., 1., 1.]), "pw2g": ([64., 64.], [0.5, 1.]), "pw1": ([128.], [1.])}
+
+
+def test_normalizer_piecewise_bit_exact():
+    z = np.load(G / "piecewise.npz")
+    for tag, (bounds, gammas) in PIECEWISE.items():
+        y = P.normalize_piecewise(torch.from_numpy(z[f"{tag}/in"]), bounds, gammas)
+        assert np.array_equal(y.numpy(), z[f"{tag}/out"]), tag
+        d = P.denormalize_piecewise(torch.from_numpy(z[f"{tag}/den_in"]), bounds, gammas)
+        np.testing.assert_array_equal(d.numpy(), z[f"{tag}/den_out"])
+
+
 def test_input_padder():
     z = np.load(G / "prepost.npz")
     for hw in ((360, 640), (540, 960), (37, 50), (64, 96)):

@@ -351,3 +351,39 @@ def test_real_shape_ddpm_slice_544x960_fp32():
         x = x_ref
     print(f"544x960 DDPM fp32 slice: worst model-output err {worst_m:.3e}, worst x_(t-1) err {worst_x:.3e}")
     assert worst_m <= 1e-4 and worst_x <= 1e-4
+
+
+def test_whole_loop_graph_matches_per_step_path():
+    """The unguided DDIM loop replayed as ONE CUDA graph (all UNet forwards + scheduler steps) gives the tensors of the
+    per-step path bit for bit, follows new inputs / in-place conditioning updates, and is re-captured when the
+    scheduler object or the weights change."""
+    d, ref, net = _make("fp16")
+    from d3roma_b200.weights import random_init_state_dict
+    pipe = d.GuidedDiffusionPipeline(net, d.MyDDIMScheduler.from_config(DDIM_CFG), d.FlowGuidance(flow_guidance_weight=0.0))
+    g = torch.Generator().manual_seed(5)
+    mk = lambda: (torch.rand(2, 3, 32, 64, generator=g) * 2 - 1, torch.rand(2, 3, 32, 64, generator=g) * 2 - 1,  # noqa: E731
+                  torch.rand(2, 1, 32, 64, generator=g) * 2 - 1)
+
+    def run(inputs, whole, seed=3, steps=10, plots=2):
+        pipe.graph_whole_loop = whole
+        l, r, raw = inputs
+        return pipe(None, l, r, raw, None, None, num_inference_steps=steps, num_intermediate_images=plots,
+                    cond_channels="left+right+raw", generator=torch.Generator().manual_seed(seed))
+
+    a, b = mk(), mk()
+    for inputs in (a, b, a):
+        o1, o0 = run(inputs, True), run(inputs, False)
+        assert torch.equal(o1.images, o0.images) and torch.equal(o1.images_pred_orig, o0.images_pred_orig)
+    assert len(pipe._loop_graphs) == 1
+    o_first = run(a, True)
+    # outputs are fresh tensors, not the graph's static buffers
+    o_second = run(b, True)
+    assert not torch.equal(o_first.images, o_second.images)
+    # a different step count -> another graph; a new scheduler object with other constants -> re-capture
+    assert torch.equal(run(a, True, steps=4, plots=1).images, run(a, False, steps=4, plots=1).images)
+    pipe.scheduler = d.MyDDIMScheduler.from_config(dict(DDIM_CFG, prediction_type="epsilon"))
+    assert torch.equal(run(a, True).images, run(a, False).images)
+    assert not torch.equal(run(a, True).images, o_first.images)
+    # new weights on the same UNet object
+    net.load_state_dict(random_init_state_dict(8, 1, seed=9))
+    assert torch.equal(run(a, True).images, run(a, False).images)

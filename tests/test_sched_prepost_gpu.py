@@ -126,8 +126,21 @@ def test_prepost_bit_exact_vs_reference():
     depth = torch.rand(4, 1, 360, 640, device="cuda") * 1.7 + 0.3
     back = prepost.disp_to_depth(prepost.depth_to_disp(depth, fxb), fxb)
     torch.testing.assert_close(back, depth, rtol=3e-7, atol=0)
-    with pytest.raises(NotImplementedError):   # piecewise multi-channel mode is not implemented
-        Normalizer(ssi=False, mode="piecewise").normalize(torch.zeros(1, 4, 4, device="cuda"))
+    # piecewise multi-channel mode (utils.py:198-229, 275-293) against the reference's outputs
+    zp = np.load(G / "piecewise.npz")
+    for tag, (bounds, gammas) in {"pw3": ([64., 32., 32.], [1., 1., 1.]), "pw2g": ([64., 64.], [0.5, 1.]),
+                                  "pw1": ([128.], [1.])}.items():
+        n = Normalizer(ssi=False, mode="piecewise", num_chs=len(bounds), ch_bounds=bounds, ch_gammas=gammas, t=0.5, s=2.0)
+        y = n.normalize(torch.from_numpy(zp[f"{tag}/in"]).cuda())[0]
+        d = n.denormalize(torch.from_numpy(zp[f"{tag}/den_in"]).cuda()).cpu().numpy()
+        rt = n.denormalize(y[None]).cpu().numpy()
+        if all(g == 1.0 for g in gammas):
+            assert np.array_equal(y.cpu().numpy(), zp[f"{tag}/out"]) and np.array_equal(d, zp[f"{tag}/den_out"])
+            assert np.array_equal(rt, zp[f"{tag}/roundtrip"])
+        else:
+            np.testing.assert_allclose(y.cpu().numpy(), zp[f"{tag}/out"], rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(d, zp[f"{tag}/den_out"], rtol=1e-5, atol=1e-5, equal_nan=True)
+            np.testing.assert_allclose(rt, zp[f"{tag}/roundtrip"], rtol=1e-5, atol=1e-4)
 
 
 def test_guidance_gradient_vs_reference_and_oracle():

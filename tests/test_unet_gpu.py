@@ -153,6 +153,14 @@ def test_graphed_forward_sees_in_place_conditioning_updates():
     assert torch.equal(yb, net.forward_graphed(x, frame2.clone(), 30))
     net.prime_conditioning(x.shape, buf)                            # no-op when nothing changed
     assert torch.equal(net.forward_graphed(x, buf, 30), yb)
+    # a NEW tensor that the caching allocator places at the address of a freed one (same pointer, version 0 again)
+    # must not be mistaken for the old contents
+    outs = []
+    for i in range(3):
+        c_new = torch.full((2, 7, *hw), 0.1 * (i + 1), device="cuda")
+        outs.append(net.forward_graphed(x, c_new, 30).clone())
+        del c_new
+    assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
 
 
 def test_from_pretrained_accepts_reference_style_checkpoints(tmp_path):
