@@ -90,6 +90,7 @@ def _declare(lib: C.CDLL) -> None:
         "d3_version": (i32, []),
         "d3_launch_count": (i64, []),
         "d3_reset_launch_count": (None, []),
+        "d3_set_pdl": (i32, [i32]),
         "d3_conv2d_igemm": (i32, [C.POINTER(ConvParams), vp]),
         "d3_conv2d_workspace_bytes": (C.c_size_t, [C.POINTER(ConvParams)]),
         "d3_groupnorm_silu": (i32, [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, f32, i32, vp, i32, i32,

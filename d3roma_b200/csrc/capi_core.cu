@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -36,6 +37,18 @@ int num_sms() {
   return n;
 }
 
+static std::atomic<int> g_pdl{-1};   // -1: not decided yet (D3_PDL, default off); 0 / 1: set by d3_set_pdl or the env
+
+bool pdl_enabled() {
+  int on = g_pdl.load(std::memory_order_relaxed);
+  if (on < 0) {
+    const char* e = getenv("D3_PDL");
+    on = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+    g_pdl.store(on, std::memory_order_relaxed);
+  }
+  return on != 0;
+}
+
 cudaError_t ensure_dyn_smem(const void* func, size_t bytes) {
   static std::mutex mu;
   static std::map<std::pair<int, const void*>, size_t> done;
@@ -60,5 +73,10 @@ const char* d3_last_error(void) { return d3::g_err; }
 int d3_version(void) { return 100; }
 int64_t d3_launch_count(void) { return d3::g_launches.load(std::memory_order_relaxed); }
 void d3_reset_launch_count(void) { d3::g_launches.store(0, std::memory_order_relaxed); }
+int d3_set_pdl(int on) {
+  const int prev = d3::pdl_enabled() ? 1 : 0;
+  d3::g_pdl.store(on ? 1 : 0, std::memory_order_relaxed);
+  return prev;
+}
 
 }  // extern "C"

@@ -39,6 +39,13 @@ D3_DEVINL bool elect_one_sync() {
   return pred != 0;
 }
 
+// Programmatic dependent launch: let the next kernel in the stream start launching, then wait until the previous grid
+// has completed and flushed its writes.  Must precede the kernel's first global-memory access (internal.h: launch_pdl).
+D3_DEVINL void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 D3_DEVINL void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

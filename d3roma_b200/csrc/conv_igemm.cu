@@ -201,6 +201,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_prologue();   // barriers / TMEM are set up; from here on the kernel reads what its predecessor wrote
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -602,6 +603,7 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_prologue();   // barriers / TMEM are set up; from here on the kernel reads what its predecessor wrote
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -1039,19 +1041,21 @@ cudaError_t launch_conv_t(int grid, cudaStream_t stream, const CUtensorMap& tmA,
     if (epi == 1) {
       cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(conv_igemm_t_kernel<STAGES, DT, true, 1>), smem);
       if (e != cudaSuccess) return e;
-      conv_igemm_t_kernel<STAGES, DT, true, 1><<<grid, kTThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, tmR, a);
+      return launch_pdl(conv_igemm_t_kernel<STAGES, DT, true, 1>, dim3(grid), dim3(kTThreads), smem, stream, tmA, tmS1,
+                        tmS2, tmB, tmO, tmR, a);
     } else {
       cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(conv_igemm_t_kernel<STAGES, DT, true, 0>), smem);
       if (e != cudaSuccess) return e;
-      conv_igemm_t_kernel<STAGES, DT, true, 0><<<grid, kTThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, tmR, a);
+      return launch_pdl(conv_igemm_t_kernel<STAGES, DT, true, 0>, dim3(grid), dim3(kTThreads), smem, stream, tmA, tmS1,
+                        tmS2, tmB, tmO, tmR, a);
     }
     return cudaSuccess;
   }
   constexpr size_t smem = conv_t_smem_bytes<STAGES>();
   cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(conv_igemm_t_kernel<STAGES, DT, false, 0>), smem);
   if (e != cudaSuccess) return e;
-  conv_igemm_t_kernel<STAGES, DT, false, 0><<<grid, kTThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, tmR, a);
-  return cudaSuccess;
+  return launch_pdl(conv_igemm_t_kernel<STAGES, DT, false, 0>, dim3(grid), dim3(kTThreads), smem, stream, tmA, tmS1,
+                    tmS2, tmB, tmO, tmR, a);
 }
 
 // Pixel tile for the pixels-as-N kernel: TH*TW <= 256; the epilogue walks it in passes of PW pixels of one row,
@@ -1112,6 +1116,7 @@ struct SplitKFinArgs {
 
 template <int DT>
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(const SplitKFinArgs a) {
+  pdl_prologue();
   const int nvec = a.Cout >> 3;
   const int vec = threadIdx.x % nvec, prow = threadIdx.x / nvec, pstride = blockDim.x / nvec;
   const int b = blockIdx.y;
@@ -1176,8 +1181,8 @@ cudaError_t launch_conv(int grid, cudaStream_t stream, const CUtensorMap& tmA, c
   constexpr size_t smem = conv_smem_bytes<BN, STAGES>();
   cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(conv_igemm_kernel<BN, STAGES, DT>), smem);
   if (e != cudaSuccess) return e;
-  conv_igemm_kernel<BN, STAGES, DT><<<grid, kThreads, smem, stream>>>(tmA, tmS1, tmS2, tmB, tmO, a);
-  return cudaSuccess;
+  return launch_pdl(conv_igemm_kernel<BN, STAGES, DT>, dim3(grid), dim3(kThreads), smem, stream, tmA, tmS1, tmS2, tmB,
+                    tmO, a);
 }
 
 // Pick the pixel tile TH x TW (TH*TW <= 128) that wastes the fewest MMA rows.
@@ -1506,8 +1511,10 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     dim3 fgrid(gx, p->B);
-    if (p->dtype == D3_DTYPE_BF16) splitk_finalize_kernel<kBF16><<<fgrid, threads, 0, stream>>>(f);
-    else splitk_finalize_kernel<kF16><<<fgrid, threads, 0, stream>>>(f);
+    if (p->dtype == D3_DTYPE_BF16)
+      D3_CHECK_CUDA(launch_pdl(splitk_finalize_kernel<kBF16>, fgrid, dim3(threads), 0, stream, f));
+    else
+      D3_CHECK_CUDA(launch_pdl(splitk_finalize_kernel<kF16>, fgrid, dim3(threads), 0, stream, f));
   }
   D3_LAUNCH_CHECK();
   return D3_OK;

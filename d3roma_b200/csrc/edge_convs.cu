@@ -27,6 +27,7 @@ template <int DT>
 __global__ void __launch_bounds__(256) im2col_input_kernel(const float* __restrict__ xs, int Cs,
                                                            const float* __restrict__ cond, int Cc, int B, int H,
                                                            int W, uint32_t* __restrict__ out) {
+  pdl_prologue();
   // Work item = 64 consecutive pixels of one image row.  Phase 1: for every pair of k = (tap, channel) the 64 pixel
   // values are read with COALESCED loads along W (lanes = consecutive pixels) and dropped, packed, into a
   // [pixel][k-pair] smem tile.  Phase 2: the tile is streamed out as full 256-byte rows (coalesced 4-byte words).
@@ -121,8 +122,9 @@ __global__ void __launch_bounds__(256, 2) conv_in_direct_kernel(const ConvInArgs
   extern __shared__ __align__(16) float ci_w[];  // [C*9][128]
   __shared__ float s_part[8][64];
   const int K = a.C * 9;
-  for (int i = threadIdx.x; i < K * 128; i += 256) ci_w[i] = a.wT[i];
+  for (int i = threadIdx.x; i < K * 128; i += 256) ci_w[i] = a.wT[i];   // static weights: staged BEFORE the PDL wait
   __syncthreads();
+  pdl_prologue();
   const int oct = threadIdx.x & 15, pg = threadIdx.x >> 4;
   const int b = blockIdx.y;
   const int segs = (a.W + kCiSeg - 1) / kCiSeg;
@@ -302,6 +304,7 @@ D3_DEVINL uint32_t norm_silu_pair(uint32_t raw, float s0, float h0, float s1, fl
 
 template <int DC, int DT>
 __global__ void __launch_bounds__(kCoThreads, (DC == 1) ? 2 : 1) conv_out_taps_kernel(const ConvOutArgs a) {
+  pdl_prologue();
   constexpr int NTAPS = 9 * DC;
   constexpr int NT = (NTAPS + 7) / 8;  // n-tiles of 8 taps
   __shared__ float s_sc[128], s_sh[128];
@@ -409,6 +412,7 @@ template <int DC>
 __global__ void __launch_bounds__(256) conv_out_gather_kernel(const float* __restrict__ taps,
                                                               const float* __restrict__ bias, float* __restrict__ out,
                                                               int B, int H, int W) {
+  pdl_prologue();
   const int HW = H * W;
   const size_t total = (size_t)B * DC * HW;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -439,11 +443,9 @@ extern "C" int d3_im2col_input(const float* sample, int Cs, const float* cond, i
   int blocks = B * H * ((W + kI2cPix - 1) / kI2cPix);
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   if (dtype == D3_DTYPE_F16)
-    im2col_input_kernel<kF16><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        sample, Cs, cond, Cc, B, H, W, static_cast<uint32_t*>(out));
+    D3_CHECK_CUDA(launch_pdl(im2col_input_kernel<kF16>, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), sample, Cs, cond, Cc, B, H, W, static_cast<uint32_t*>(out)));
   else
-    im2col_input_kernel<kBF16><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        sample, Cs, cond, Cc, B, H, W, static_cast<uint32_t*>(out));
+    D3_CHECK_CUDA(launch_pdl(im2col_input_kernel<kBF16>, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), sample, Cs, cond, Cc, B, H, W, static_cast<uint32_t*>(out)));
   D3_LAUNCH_CHECK();
   return D3_OK;
 }
@@ -471,16 +473,16 @@ extern "C" int d3_conv_out_fused(const void* x, int pitch, const double* stats, 
   if (gx > (n_groups + per_block - 1) / per_block) gx = (n_groups + per_block - 1) / per_block;
   if (gx < 1) gx = 1;
   dim3 grid(gx, B);
-  if (dc == 1 && dtype == D3_DTYPE_BF16) conv_out_taps_kernel<1, kBF16><<<grid, kCoThreads, 0, st>>>(a);
-  else if (dc == 1) conv_out_taps_kernel<1, kF16><<<grid, kCoThreads, 0, st>>>(a);
-  else if (dtype == D3_DTYPE_BF16) conv_out_taps_kernel<3, kBF16><<<grid, kCoThreads, 0, st>>>(a);
-  else conv_out_taps_kernel<3, kF16><<<grid, kCoThreads, 0, st>>>(a);
+  if (dc == 1 && dtype == D3_DTYPE_BF16) D3_CHECK_CUDA(launch_pdl(conv_out_taps_kernel<1, kBF16>, dim3(grid), dim3(kCoThreads), 0, st, a));
+  else if (dc == 1) D3_CHECK_CUDA(launch_pdl(conv_out_taps_kernel<1, kF16>, dim3(grid), dim3(kCoThreads), 0, st, a));
+  else if (dtype == D3_DTYPE_BF16) D3_CHECK_CUDA(launch_pdl(conv_out_taps_kernel<3, kBF16>, dim3(grid), dim3(kCoThreads), 0, st, a));
+  else D3_CHECK_CUDA(launch_pdl(conv_out_taps_kernel<3, kF16>, dim3(grid), dim3(kCoThreads), 0, st, a));
   D3_LAUNCH_CHECK();
   const size_t total = (size_t)B * dc * H * W;
   int gb = (int)((total + 255) / 256);
   if (gb > num_sms() * 16) gb = num_sms() * 16;
-  if (dc == 1) conv_out_gather_kernel<1><<<gb, 256, 0, st>>>(a.taps, bias, out, B, H, W);
-  else conv_out_gather_kernel<3><<<gb, 256, 0, st>>>(a.taps, bias, out, B, H, W);
+  if (dc == 1) D3_CHECK_CUDA(launch_pdl(conv_out_gather_kernel<1>, dim3(gb), dim3(256), 0, st, a.taps, bias, out, B, H, W));
+  else D3_CHECK_CUDA(launch_pdl(conv_out_gather_kernel<3>, dim3(gb), dim3(256), 0, st, a.taps, bias, out, B, H, W));
   D3_LAUNCH_CHECK();
   return D3_OK;
 }
@@ -509,9 +511,9 @@ extern "C" int d3_conv_in_direct(const float* planes, int C, const float* wT, co
   D3_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_in_direct_kernel<kBF16, true>), mx));
   D3_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_in_direct_kernel<kBF16, false>), mx));
   D3_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_in_direct_kernel<kF16, false>), mx));
-  if (out32) conv_in_direct_kernel<kBF16, true><<<grid, 256, smem, st>>>(a);
-  else if (dtype == D3_DTYPE_BF16) conv_in_direct_kernel<kBF16, false><<<grid, 256, smem, st>>>(a);
-  else conv_in_direct_kernel<kF16, false><<<grid, 256, smem, st>>>(a);
+  if (out32) D3_CHECK_CUDA(launch_pdl(conv_in_direct_kernel<kBF16, true>, dim3(grid), dim3(256), smem, st, a));
+  else if (dtype == D3_DTYPE_BF16) D3_CHECK_CUDA(launch_pdl(conv_in_direct_kernel<kBF16, false>, dim3(grid), dim3(256), smem, st, a));
+  else D3_CHECK_CUDA(launch_pdl(conv_in_direct_kernel<kF16, false>, dim3(grid), dim3(256), smem, st, a));
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

@@ -47,6 +47,7 @@ struct GnArgs {
 
 template <int DT, bool DUAL = false, int U = 8>
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
+  pdl_prologue();
   // blockDim.x = nvec * k (nvec = C/8 16-byte vectors per pixel): every thread owns ONE channel vector for the whole
   // block, so its 8 scale/shift pairs live in registers and the inner loop is load - 8 FMA - 8 SiLU - store.
   __shared__ float s_mean[32];
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnArgs a) {
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint16_t* __restrict__ in,
                                                          uint16_t* __restrict__ out, int B, int H, int W, int C,
                                                          int pin, int pout) {
+  pdl_prologue();
   const int nvec = C >> 3;
   const size_t total = (size_t)B * H * W * nvec;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -226,11 +228,11 @@ int launch_gn(GnArgs& a, int B, int dtype, bool dual, cudaStream_t stream) {
   const int nvec = C / 8;
   const int threads = nvec * (kGnThreads / nvec > 0 ? kGnThreads / nvec : 1);  // multiple of nvec, <= 256 (nvec <= 128)
   if (dual) {
-    if (dtype == D3_DTYPE_F16) gn_apply_kernel<kF16, true><<<grid, threads, 0, stream>>>(a);
-    else gn_apply_kernel<kBF16, true><<<grid, threads, 0, stream>>>(a);
+    if (dtype == D3_DTYPE_F16) D3_CHECK_CUDA(launch_pdl(gn_apply_kernel<kF16, true>, dim3(grid), dim3(threads), 0, stream, a));
+    else D3_CHECK_CUDA(launch_pdl(gn_apply_kernel<kBF16, true>, dim3(grid), dim3(threads), 0, stream, a));
   } else {
-    if (dtype == D3_DTYPE_F16) gn_apply_kernel<kF16><<<grid, threads, 0, stream>>>(a);
-    else gn_apply_kernel<kBF16><<<grid, threads, 0, stream>>>(a);
+    if (dtype == D3_DTYPE_F16) D3_CHECK_CUDA(launch_pdl(gn_apply_kernel<kF16>, dim3(grid), dim3(threads), 0, stream, a));
+    else D3_CHECK_CUDA(launch_pdl(gn_apply_kernel<kBF16>, dim3(grid), dim3(threads), 0, stream, a));
   }
   D3_LAUNCH_CHECK();
   return D3_OK;
@@ -314,8 +316,7 @@ extern "C" int d3_upsample_nearest2x(const void* in, int B, int H, int W, int C,
   int blocks = (int)((total + 255) / 256);
   const int cap = num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  upsample2x_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), B, H, W, C, pin, pout);
+  D3_CHECK_CUDA(launch_pdl(upsample2x_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), B, H, W, C, pin, pout));
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

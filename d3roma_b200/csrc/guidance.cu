@@ -57,6 +57,7 @@ struct Row5 {  // horizontal 3-sums of one image row for one channel
 };
 
 __global__ void __launch_bounds__(kGuidWarps * 32) guidance_stream_kernel(const GuidArgs a) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int wid = blockIdx.x * kGuidWarps + (threadIdx.x >> 5);
   const int total = a.B * a.bands * a.stripsX;
@@ -235,8 +236,7 @@ extern "C" int d3_guidance_step(const d3_guidance_params* p, void* stream) {
   a.bands = ceil_div(p->H, kRows);
   const long long warps = (long long)p->B * a.bands * a.stripsX;
   D3_REQUIRE(warps < (1ll << 30), "guidance: problem too large");
-  guidance_stream_kernel<<<(unsigned)ceil_div((int)warps, kGuidWarps), kGuidWarps * 32, 0,
-                           static_cast<cudaStream_t>(stream)>>>(a);
+  D3_CHECK_CUDA(launch_pdl(guidance_stream_kernel, dim3((unsigned)ceil_div((int)warps, kGuidWarps)), dim3(kGuidWarps * 32), 0, static_cast<cudaStream_t>(stream), a));
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

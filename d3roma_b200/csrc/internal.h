@@ -50,4 +50,28 @@ int im2col_f32(const float* sample, int Cs, const float* cond, int Cc, int B, in
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch (PDL): the kernels of the denoising loop are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so that the next kernel's blocks become resident and run their
+// prologue (barrier init, TMEM allocation, tensor-map prefetch, index arithmetic) while the previous kernel drains;
+// every such kernel calls pdl_prologue() before its first global-memory access (griddepcontrol.wait returns only when
+// the prerequisite grid has completed and its writes are visible).  D3_PDL=0 launches them the plain way.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const bool on = pdl_enabled();
+  cfg.attrs = on ? attr : nullptr;
+  cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace d3

@@ -135,6 +135,7 @@ __global__ void crop_kernel(const float* __restrict__ in, int64_t N, int Hi, int
 // clamp to [-1, 1] (custom_pipelines.py:196) into a slot of a wider channel stack: out[b][c_off + c]
 __global__ void clamp_into_kernel(const float* __restrict__ in, int64_t B, int64_t CHW, int64_t out_bstride,
                                   int64_t out_off, float lo, float hi, float* __restrict__ out) {
+  pdl_prologue();
   D3_GRID_STRIDE(i, B * CHW) {
     const int64_t b = i / CHW, r = i - b * CHW;
     out[b * out_bstride + out_off + r] = fminf(fmaxf(in[i], lo), hi);
@@ -208,8 +209,8 @@ extern "C" int d3_clamp_into(const float* in, int64_t B, int64_t chw, int64_t ou
                              float hi, float* out, void* stream) {
   D3_REQUIRE(in && out && B >= 0 && chw >= 0, "clamp_into: bad arguments");
   if (B * chw == 0) return D3_OK;
-  clamp_into_kernel<<<ew_blocks(B * chw), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, B, chw, out_bstride,
-                                                                                      out_off, lo, hi, out);
+  D3_CHECK_CUDA(launch_pdl(clamp_into_kernel, dim3(ew_blocks(B * chw)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                           in, B, chw, out_bstride, out_off, lo, hi, out));
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(const float* __restrict_
                                                         const float* __restrict__ noise, d3_ddim_coeffs c, int64_t n,
                                                         float* __restrict__ prev, float* __restrict__ orig,
                                                         float* __restrict__ prev_mean, float* __restrict__ dir_out) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float m = mo[i], s = xs[i];
     float x0, eps;
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(const float* __restrict_
                                                         const float* __restrict__ noise, d3_ddpm_coeffs c, int64_t n,
                                                         float* __restrict__ prev, float* __restrict__ orig,
                                                         float* __restrict__ prev_mean) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float m = mo[i], s = xs[i];
     float x0, eps;
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(256) lincomb_kernel(float a, const float* __re
                                                       const float* __restrict__ y, float c,
                                                       const float* __restrict__ z, int64_t n,
                                                       float* __restrict__ out) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float r = __fmul_rn(a, x[i]);
     if (y) r = __fadd_rn(r, (b == 1.0f) ? y[i] : __fmul_rn(b, y[i]));
@@ -99,8 +102,7 @@ extern "C" int d3_sched_ddim_step(const float* model_output, const float* sample
   D3_REQUIRE(c->prediction_type >= 0 && c->prediction_type <= 2, "ddim_step: bad prediction_type %d",
              c->prediction_type);
   if (n == 0) return D3_OK;
-  ddim_step_kernel<<<ew_blocks(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      model_output, sample, variance_noise, *c, n, prev_sample, pred_original, prev_mean, dir_out);
+  D3_CHECK_CUDA(launch_pdl(ddim_step_kernel, dim3(ew_blocks(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), model_output, sample, variance_noise, *c, n, prev_sample, pred_original, prev_mean, dir_out));
   D3_LAUNCH_CHECK();
   return D3_OK;
 }
@@ -113,8 +115,7 @@ extern "C" int d3_sched_ddpm_step(const float* model_output, const float* sample
   D3_REQUIRE(c->prediction_type >= 0 && c->prediction_type <= 2, "ddpm_step: bad prediction_type %d",
              c->prediction_type);
   if (n == 0) return D3_OK;
-  ddpm_step_kernel<<<ew_blocks(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      model_output, sample, variance_noise, *c, n, prev_sample, pred_original, prev_mean);
+  D3_CHECK_CUDA(launch_pdl(ddpm_step_kernel, dim3(ew_blocks(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), model_output, sample, variance_noise, *c, n, prev_sample, pred_original, prev_mean));
   D3_LAUNCH_CHECK();
   return D3_OK;
 }
@@ -124,7 +125,7 @@ extern "C" int d3_lincomb(float a, const float* x, float b, const float* y, floa
   using namespace d3;
   D3_REQUIRE(x && out && n >= 0, "lincomb: bad arguments");
   if (n == 0) return D3_OK;
-  lincomb_kernel<<<ew_blocks(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, x, b, y, c, z, n, out);
+  D3_CHECK_CUDA(launch_pdl(lincomb_kernel, dim3(ew_blocks(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), a, x, b, y, c, z, n, out));
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

@@ -16,6 +16,7 @@ namespace {
 __global__ void __launch_bounds__(512) time_embed_kernel(const float* __restrict__ t, const float* __restrict__ w1,
                                                          const float* __restrict__ b1, const float* __restrict__ w2,
                                                          const float* __restrict__ b2, float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float s_sin[128];
   __shared__ float s_h[512];
   const int n = blockIdx.x;
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(512) time_embed_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) temb_project_kernel(const float* __restrict__ semb, const float* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ out,
                                                            int rows, int nt) {
+  pdl_prologue();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -90,7 +92,7 @@ extern "C" int d3_time_embed(const float* t, int nt, const float* w1, const floa
                              const float* b2, float* silu_emb_out, void* stream) {
   using namespace d3;
   D3_REQUIRE(t && w1 && b1 && w2 && b2 && silu_emb_out && nt > 0, "time_embed: bad arguments");
-  time_embed_kernel<<<dim3(nt, 16), 512, 0, static_cast<cudaStream_t>(stream)>>>(t, w1, b1, w2, b2, silu_emb_out);
+  D3_CHECK_CUDA(launch_pdl(time_embed_kernel, dim3(dim3(nt, 16)), dim3(512), 0, static_cast<cudaStream_t>(stream), t, w1, b1, w2, b2, silu_emb_out));
   D3_LAUNCH_CHECK();
   return D3_OK;
 }
@@ -100,8 +102,7 @@ extern "C" int d3_temb_project_all(const float* silu_emb, int nt, const float* w
   using namespace d3;
   D3_REQUIRE(silu_emb && w_all && bias_all && out && rows > 0 && nt > 0, "temb_project: bad arguments");
   const int blocks = ceil_div(rows * 32, 256);
-  temb_project_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(silu_emb, w_all, bias_all, out, rows,
-                                                                             nt);
+  D3_CHECK_CUDA(launch_pdl(temb_project_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), silu_emb, w_all, bias_all, out, rows, nt));
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

@@ -128,6 +128,9 @@ class UNet2DModel:
         self._eager_arena: Optional[_StatsArena] = None   # arena of the non-graph path (grown on demand)
         self._loaded = False
         self.identity_slab = os.environ.get("D3_UNET_IDENTITY_SLAB", "1") != "0"   # A/B switch, see load_state_dict
+        # batch * H * W up to which the loop's kernels are launched with programmatic dependent launch (None: leave the
+        # library setting alone, e.g. when D3_PDL is being A/B-tested)
+        self.pdl_max_pixels = None if "D3_PDL" in os.environ else 2 * 384 * 640
         self.keep_state_dict = True   # keep a host copy of the loaded fp32 state_dict (for save_pretrained)
         self._sd_cpu = None
         self._graphs: Dict[tuple, dict] = {}
@@ -421,6 +424,10 @@ class UNet2DModel:
             raise ValueError(f"H and W must be multiples of 32 (got {H}x{Wd}); pad with InputPadder(divis_by=32)")
         dev = sample.device
         W = self._w
+        # programmatic dependent launch pays in the latency regime only (c1: +2 %; batch 16: -2 %, profiles/r02_*)
+        if self.pdl_max_pixels is not None:
+            from . import _lib
+            _lib.lib().d3_set_pdl(1 if B * H * Wd <= self.pdl_max_pixels else 0)
         need = B * 2 * 40000
         if arena is not None:
             if arena.buf.numel() < need or arena.buf.device != dev:

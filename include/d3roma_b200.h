@@ -48,6 +48,10 @@ int d3_version(void);
 /* Number of kernels launched by this library since the last d3_reset_launch_count() (host counter). */
 int64_t d3_launch_count(void);
 void d3_reset_launch_count(void);
+/* Programmatic dependent launch for the kernels of the denoising loop (the next kernel's blocks start their prologue
+ * while the previous kernel drains): measured +2 % at batch 1 (latency case), -2 % at batch 16 on B200, so the UNet turns
+ * it on for small batches only.  Returns the previous setting; D3_PDL=1 in the environment sets the initial value. */
+int d3_set_pdl(int on);
 
 /* ---- implicit-GEMM convolution (tcgen05 / TMEM / TMA) ---------------------------------------
  * Replaces aten::conv2d as invoked by ResnetBlock2D.conv1/conv2/conv_shortcut, Downsample2D.conv,
