@@ -394,6 +394,21 @@ def gen_guided(store):
         store[f"{tag}/final_loss"] = np.float64(g.log[-1]["loss"])
 
 
+def gen_unet_oracle(store):
+    """Regression fixture of the UNet restatement itself (oracle/unet_ref.py).  diffusers is absent, so this does NOT pin
+    the restatement to the reference's arithmetic - it freezes the restatement's own outputs (seeded weights, seeded
+    inputs) so that it cannot drift unnoticed while kernels are compared against it."""
+    from oracle.unet_ref import make_unet
+    torch.set_num_threads(8)
+    for tag, (cin, dc, hw, t) in {"c8": (8, 1, (32, 64), 49), "c5": (5, 1, (32, 32), 109), "c12": (12, 3, (32, 32), 1)}.items():
+        net = make_unet(cin, dc, seed=0, sample_size=hw)
+        x = torch.randn(1, cin, *hw, generator=torch.Generator().manual_seed(123))
+        store[f"{tag}/x"] = _np(x)
+        store[f"{tag}/y"] = _np(net(x, torch.tensor(t)).sample)
+        store[f"{tag}/meta"] = np.array([cin, dc, hw[0], hw[1], t])
+        store[f"{tag}/n_params"] = np.array(sum(p.numel() for p in net.parameters()))
+
+
 def gen_piecewise(store):
     """Normalizer(mode="piecewise") of the reference (utils_d3roma/utils.py:198-229, 275-293): 3 channels with bounds
     [64, 32, 32] (the class defaults), 2 channels with a gamma, and the 1-channel degenerate case."""
@@ -559,7 +574,7 @@ def main():
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
     for name, fn in (("ddim", gen_ddim), ("ddpm", gen_ddpm), ("prepost", gen_prepost), ("guidance", gen_guidance),
-                     ("pipeline", gen_pipeline), ("guided", gen_guided), ("reproject", gen_reproject), ("piecewise", gen_piecewise), ("postproc", gen_postproc), ("frontend", gen_frontend), ("ransac", gen_ransac)):
+                     ("pipeline", gen_pipeline), ("guided", gen_guided), ("reproject", gen_reproject), ("piecewise", gen_piecewise), ("unet_oracle", gen_unet_oracle), ("postproc", gen_postproc), ("frontend", gen_frontend), ("ransac", gen_ransac)):
         store = {}
         with torch.no_grad():
             fn(store)

@@ -64,3 +64,20 @@ def test_pipeline_restatement_matches_reference_pipeline():
     img = pipeline_ref.run_pipeline(unet, x_T, conds, "left+right+raw", sampler="ddpm", num_inference_steps=8,
                                     ddpm_noise=lambda i, shape: torch.randn(shape))
     np.testing.assert_allclose(img.numpy(), z["ddpm8/images"], atol=1e-5)
+
+
+def test_oracle_forward_regression_fixture():
+    """The restatement's own outputs are frozen in tests/golden/unet_oracle.npz (oracle/gen_golden.py:gen_unet_oracle):
+    not a pin to diffusers (absent), but a guard against the oracle drifting while kernels are compared against it."""
+    from pathlib import Path
+    import numpy as np
+    from oracle.unet_ref import make_unet
+    z = np.load(Path(__file__).resolve().parent / "golden" / "unet_oracle.npz")
+    torch.set_num_threads(8)
+    for tag in ("c8", "c5", "c12"):
+        cin, dc, h, w, t = (int(v) for v in z[f"{tag}/meta"])
+        net = make_unet(cin, dc, seed=0, sample_size=(h, w))
+        assert sum(p.numel() for p in net.parameters()) == int(z[f"{tag}/n_params"])
+        with torch.no_grad():
+            y = net(torch.from_numpy(z[f"{tag}/x"]), torch.tensor(t)).sample
+        np.testing.assert_allclose(y.numpy(), z[f"{tag}/y"], rtol=0, atol=5e-5)
