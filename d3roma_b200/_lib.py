@@ -101,6 +101,8 @@ def _declare(lib: C.CDLL) -> None:
         "d3_im2col_input": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, i32, vp]),
         "d3_conv_in_direct": (i32, [vp, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp, i32, vp, vp]),
         "d3_conv_out_fused": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, i32, vp]),
+        "d3_conv_out_fused_ddim": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, vp, i32, vp,
+                                         C.POINTER(DDIMCoeffs), vp, vp, vp]),
         "d3_conv_out_workspace_bytes": (C.c_size_t, [i32, i32, i32, i32]),
         "d3_time_embed": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),
         "d3_temb_project_all": (i32, [vp, i32, vp, vp, i32, vp, vp]),

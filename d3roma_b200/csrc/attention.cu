@@ -12,6 +12,7 @@
 // each).  Online softmax in the exp2 domain over 64-key blocks.  The op is exp-bound (one MUFU.EX2 per score), not
 // MMA-bound: a tcgen05/TMEM variant would have to pad K 8->16 and could not go faster than the MUFU pipe either; see
 // DESIGN.md.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -20,9 +21,8 @@
 namespace d3 {
 namespace {
 
-constexpr int kAttnWarps = 4;
-constexpr int kAttnThreads = kAttnWarps * 32;
-constexpr int kQPerBlock = kAttnWarps * 16;
+// Warps (x 16 queries) per block: every block stages the whole K / V of its (sample, head) in shared memory, so more
+// warps per block means fewer redundant K/V loads (N = 960: 8 blocks of 128 queries instead of 15 of 64).
 constexpr int kHeadDim = 8;
 constexpr int kKeyBlock = 64;
 constexpr int kVPad = 8;  // V^T row pitch = N + 8 elements -> conflict-free fragment loads
@@ -61,8 +61,8 @@ D3_DEVINL void mma_m16n8k16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2
   }
 }
 
-template <int DT>
-__global__ void __launch_bounds__(kAttnThreads) attention_hd8_kernel(const uint16_t* __restrict__ qkv, int pitch,
+template <int DT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) attention_hd8_kernel(const uint16_t* __restrict__ qkv, int pitch,
                                                                      int C, int N, uint16_t* __restrict__ out,
                                                                      int opitch) {
   pdl_prologue();
@@ -73,6 +73,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_hd8_kernel(const uint1
   uint16_t* s_vt = reinterpret_cast<uint16_t*>(s_raw + (size_t)Npad * 16);  // [8][vpitch]
   const int head = blockIdx.y, b = blockIdx.z;
   const uint16_t* base = qkv + (size_t)b * N * pitch + head * kHeadDim;
+  constexpr int kAttnThreads = WARPS * 32;
+  constexpr int kQPerBlock = WARPS * 16;
   for (int j = threadIdx.x; j < Npad; j += kAttnThreads) {
     uint4 kr = make_uint4(0u, 0u, 0u, 0u), vr = make_uint4(0u, 0u, 0u, 0u);
     if (j < N) {
@@ -189,13 +191,23 @@ extern "C" int d3_attention_hd8(const void* qkv, int pitch, int B, int N, int C,
   const int Npad = (N + kKeyBlock - 1) / kKeyBlock * kKeyBlock;
   const size_t smem = (size_t)Npad * 16 + (size_t)8 * (Npad + kVPad) * 2;
   D3_REQUIRE(smem <= 220 * 1024, "attention: N=%d tokens exceed the shared-memory K/V budget", N);
-  D3_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(attention_hd8_kernel<kBF16>), smem));
-  D3_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(attention_hd8_kernel<kF16>), smem));
-  dim3 grid(ceil_div(N, kQPerBlock), C / kHeadDim, B);
-  if (dtype == D3_DTYPE_F16)
-    D3_CHECK_CUDA(launch_pdl(attention_hd8_kernel<kF16>, dim3(grid), dim3(kAttnThreads), smem, static_cast<cudaStream_t>(stream), static_cast<const uint16_t*>(qkv), pitch, C, N, static_cast<uint16_t*>(out), opitch));
-  else
-    D3_CHECK_CUDA(launch_pdl(attention_hd8_kernel<kBF16>, dim3(grid), dim3(kAttnThreads), smem, static_cast<cudaStream_t>(stream), static_cast<const uint16_t*>(qkv), pitch, C, N, static_cast<uint16_t*>(out), opitch));
+  static int warps = -1;
+  if (warps < 0) { const char* e = getenv("D3_ATTN_WARPS"); warps = (e && atoi(e) == 4) ? 4 : 8; }
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint16_t* q = static_cast<const uint16_t*>(qkv);
+  uint16_t* o = static_cast<uint16_t*>(out);
+#define D3_ATTN_LAUNCH(DTV, WV)                                                                                 \
+  do {                                                                                                           \
+    D3_CHECK_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(attention_hd8_kernel<DTV, WV>), smem));          \
+    dim3 grid(ceil_div(N, WV * 16), C / kHeadDim, B);                                                            \
+    D3_CHECK_CUDA(launch_pdl(attention_hd8_kernel<DTV, WV>, grid, dim3(WV * 32), smem, st, q, pitch, C, N, o, opitch)); \
+  } while (0)
+  if (dtype == D3_DTYPE_F16) {
+    if (warps == 8) D3_ATTN_LAUNCH(kF16, 8); else D3_ATTN_LAUNCH(kF16, 4);
+  } else {
+    if (warps == 8) D3_ATTN_LAUNCH(kBF16, 8); else D3_ATTN_LAUNCH(kBF16, 4);
+  }
+#undef D3_ATTN_LAUNCH
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "sched_math.cuh"
 
 namespace d3 {
 namespace {
@@ -408,10 +409,19 @@ __global__ void __launch_bounds__(kCoThreads, (DC == 1) ? 2 : 1) conv_out_taps_k
   }
 }
 
-template <int DC>
+// FUSE: the gathered value IS the model output of the step; apply the DDIM update to it right here (sample in, x_{t-1}
+// and x0 out: scheduler_ddim.py:423-459 with eta = 0) instead of writing it for a separate step kernel to read back.
+struct GatherDdim {
+  const float* sample;   // x_t, same [B,DC,H,W] layout as the model output
+  d3_ddim_coeffs c;
+  float* prev;           // x_{t-1}
+  float* orig;           // predicted x0
+};
+
+template <int DC, bool FUSE>
 __global__ void __launch_bounds__(256) conv_out_gather_kernel(const float* __restrict__ taps,
                                                               const float* __restrict__ bias, float* __restrict__ out,
-                                                              int B, int H, int W) {
+                                                              int B, int H, int W, const GatherDdim f) {
   pdl_prologue();
   const int HW = H * W;
   const size_t total = (size_t)B * DC * HW;
@@ -427,7 +437,18 @@ __global__ void __launch_bounds__(256) conv_out_gather_kernel(const float* __res
       const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
       if (hh >= 0 && hh < H && ww >= 0 && ww < W) acc += __ldg(yb + (size_t)tap * HW + (size_t)hh * W + ww);
     }
-    out[i] = acc;
+    if constexpr (FUSE) {
+      const float s = f.sample[i];
+      float x0, eps;
+      split_x0_eps(f.c.prediction_type, acc, s, f.c.sqrt_alpha_t, f.c.sqrt_beta_t, x0, eps);
+      x0 = clip_x0(x0, f.c.clip_mode, f.c.clip_range);
+      if (f.c.use_clipped_model_output) eps = __fdiv_rn(__fsub_rn(s, __fmul_rn(f.c.sqrt_alpha_t, x0)), f.c.sqrt_beta_t);
+      f.orig[i] = x0;
+      f.prev[i] = __fadd_rn(__fmul_rn(f.c.sqrt_alpha_prev, x0), __fmul_rn(f.c.dir_coeff, eps));
+      if (out != nullptr) out[i] = acc;
+    } else {
+      out[i] = acc;
+    }
   }
 }
 
@@ -454,14 +475,17 @@ extern "C" size_t d3_conv_out_workspace_bytes(int B, int H, int W, int dc) {
   return (size_t)B * 9 * dc * H * W * sizeof(float);
 }
 
-extern "C" int d3_conv_out_fused(const void* x, int pitch, const double* stats, const float* gamma,
-                                 const float* beta, const float* w, const float* bias, int B, int H, int W, int dc,
-                                 float eps, float* out, void* workspace, int dtype, void* stream) {
-  using namespace d3;
-  D3_REQUIRE(x && stats && gamma && beta && w && bias && out, "conv_out: null pointer");
+namespace d3 {
+namespace {
+int conv_out_impl(const void* x, int pitch, const double* stats, const float* gamma, const float* beta, const float* w,
+                  const float* bias, int B, int H, int W, int dc, float eps, float* out, void* workspace, int dtype,
+                  const GatherDdim* fuse, void* stream) {
+  D3_REQUIRE(x && stats && gamma && beta && w && bias && (out || fuse), "conv_out: null pointer");
   D3_REQUIRE(dc == 1 || dc == 3, "conv_out: depth_channels must be 1 or 3 (got %d)", dc);
-  if (dtype == D3_DTYPE_F32)
+  if (dtype == D3_DTYPE_F32) {
+    D3_REQUIRE(fuse == nullptr, "conv_out: the fused DDIM update exists for the 16-bit paths only");
     return conv_out_f32(x, pitch, stats, gamma, beta, w, bias, B, H, W, dc, eps, out, static_cast<cudaStream_t>(stream));
+  }
   D3_REQUIRE(workspace != nullptr, "conv_out: workspace of d3_conv_out_workspace_bytes() bytes required");
   D3_REQUIRE(pitch % 8 == 0, "conv_out: pitch must be a multiple of 8");
   ConvOutArgs a{static_cast<const uint16_t*>(x), pitch, stats, gamma, beta, w, bias, out,
@@ -481,10 +505,35 @@ extern "C" int d3_conv_out_fused(const void* x, int pitch, const double* stats, 
   const size_t total = (size_t)B * dc * H * W;
   int gb = (int)((total + 255) / 256);
   if (gb > num_sms() * 16) gb = num_sms() * 16;
-  if (dc == 1) D3_CHECK_CUDA(launch_pdl(conv_out_gather_kernel<1>, dim3(gb), dim3(256), 0, st, a.taps, bias, out, B, H, W));
-  else D3_CHECK_CUDA(launch_pdl(conv_out_gather_kernel<3>, dim3(gb), dim3(256), 0, st, a.taps, bias, out, B, H, W));
+  GatherDdim f{};
+  if (fuse) f = *fuse;
+  if (fuse && dc == 1) D3_CHECK_CUDA(launch_pdl(conv_out_gather_kernel<1, true>, dim3(gb), dim3(256), 0, st, a.taps, bias, out, B, H, W, f));
+  else if (fuse) D3_CHECK_CUDA(launch_pdl(conv_out_gather_kernel<3, true>, dim3(gb), dim3(256), 0, st, a.taps, bias, out, B, H, W, f));
+  else if (dc == 1) D3_CHECK_CUDA(launch_pdl(conv_out_gather_kernel<1, false>, dim3(gb), dim3(256), 0, st, a.taps, bias, out, B, H, W, f));
+  else D3_CHECK_CUDA(launch_pdl(conv_out_gather_kernel<3, false>, dim3(gb), dim3(256), 0, st, a.taps, bias, out, B, H, W, f));
   D3_LAUNCH_CHECK();
   return D3_OK;
+}
+}  // namespace
+}  // namespace d3
+
+extern "C" int d3_conv_out_fused(const void* x, int pitch, const double* stats, const float* gamma,
+                                 const float* beta, const float* w, const float* bias, int B, int H, int W, int dc,
+                                 float eps, float* out, void* workspace, int dtype, void* stream) {
+  D3_REQUIRE(out != nullptr, "conv_out: null output");
+  return d3::conv_out_impl(x, pitch, stats, gamma, beta, w, bias, B, H, W, dc, eps, out, workspace, dtype, nullptr, stream);
+}
+
+extern "C" int d3_conv_out_fused_ddim(const void* x, int pitch, const double* stats, const float* gamma,
+                                      const float* beta, const float* w, const float* bias, int B, int H, int W, int dc,
+                                      float eps, float* model_out, void* workspace, int dtype, const float* sample,
+                                      const d3_ddim_coeffs* c, float* prev_sample, float* pred_original,
+                                      void* stream) {
+  D3_REQUIRE(sample && c && prev_sample && pred_original, "conv_out_ddim: null pointer");
+  D3_REQUIRE(c->std_dev == 0.0f, "conv_out_ddim: the fused update is the eta = 0 step (no variance noise)");
+  d3::GatherDdim f{sample, *c, prev_sample, pred_original};
+  return d3::conv_out_impl(x, pitch, stats, gamma, beta, w, bias, B, H, W, dc, eps, model_out, workspace, dtype, &f,
+                           stream);
 }
 
 extern "C" int d3_conv_in_direct(const float* planes, int C, const float* wT, const void* base, int base_dtype,

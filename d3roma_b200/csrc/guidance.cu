@@ -96,14 +96,26 @@ __global__ void __launch_bounds__(kGuidWarps * 32) guidance_stream_kernel(const 
       pX[c][s] = pY[c][s] = pD[c][s] = 0.f;
     }
 
-  for (int yr = y_first - 2; yr < y_end + 2; ++yr) {
-    // ---------------- stage A: X, Y, dY of input row yr (reflected at the image border)
-    const int yl = reflect_idx(yr, H);
-    const bool row_ld = (yl >= 0) && (yl < H);
-    float Xc[3] = {0.f, 0.f, 0.f}, Yc[3] = {0.f, 0.f, 0.f}, Dc[3] = {0.f, 0.f, 0.f};
-    if (row_ld && x_ld) {
-      float ssum = 0.f;
+  // ---- software pipeline of the loads: the disparity of row yr+2 and the image gathers of row yr+1 (which depend on
+  // the disparity of that row) are in flight while rows yr-2 .. yr are being processed - with 12 resident warps per SM
+  // the two dependent load levels per row were fully exposed (ncu: issue 37 % busy, profiles/r02_ncu_full_summary.csv)
+  struct RowLoads {   // what stage A needs of one input row
+    float r0[3], r1[3], X[3], fa, dsel;
+  };
+  auto load_xsum = [&](int yrow) -> float {   // sum_c x0 of image row reflect(yrow) at this lane's column (0 if none)
+    const int yl = reflect_idx(yrow, H);
+    float ssum = 0.f;
+    if (yl >= 0 && yl < H && x_ld)
       for (int c = 0; c < a.C; ++c) ssum += __ldg(x0b + (size_t)c * plane + (size_t)yl * W + xl_);
+    return ssum;
+  };
+  auto issue_row = [&](int yrow, float ssum, RowLoads& L) {
+    const int yl = reflect_idx(yrow, H);
+    L.fa = 0.f;
+    L.dsel = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) L.r0[c] = L.r1[c] = L.X[c] = 0.f;
+    if (yl >= 0 && yl < H && x_ld) {
       const float raw = fmaf(a.sc, ssum, a.off);
       const float d = fminf(fmaxf(raw, a.min_d), a.max_d);
       const bool d_free = (raw >= a.min_d) && (raw <= a.max_d);
@@ -113,19 +125,34 @@ __global__ void __launch_bounds__(kGuidWarps * 32) guidance_stream_kernel(const 
       const bool x_free = (ix >= 0.0f) && (ix <= (float)(Wr - 1));
       ix = fminf(fmaxf(ix, 0.0f), (float)(Wr - 1));
       const int xi = (int)floorf(ix);
-      const float fa = ix - (float)xi;
+      L.fa = ix - (float)xi;
       const bool has1 = xi + 1 < Wr;
-      const float dsel = (d_free && x_free) ? -1.f : 0.f;
+      L.dsel = (d_free && x_free) ? -1.f : 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float* Rp = Rb + (size_t)c * planeR + (size_t)yl * Wr;
-        const float r0 = __ldg(Rp + xi);
-        const float r1 = has1 ? __ldg(Rp + xi + 1) : 0.f;
-        Xc[c] = __ldg(Lb + (size_t)c * planeR + (size_t)yl * Wr + xl_);
-        Yc[c] = (1.0f - fa) * r0 + fa * r1;
-        Dc[c] = dsel * (r1 - r0);
+        L.r0[c] = __ldg(Rp + xi);
+        L.r1[c] = has1 ? __ldg(Rp + xi + 1) : 0.f;
+        L.X[c] = __ldg(Lb + (size_t)c * planeR + (size_t)yl * Wr + xl_);
       }
     }
+  };
+  RowLoads cur, nxt;
+  issue_row(y_first - 2, load_xsum(y_first - 2), cur);
+  float xsum_next = load_xsum(y_first - 1);
+
+  for (int yr = y_first - 2; yr < y_end + 2; ++yr) {
+    // ---------------- stage A: X, Y, dY of input row yr (reflected at the image border) from the loads issued one
+    // iteration ago; then put the next row's gathers and the disparity of the row after it in flight
+    float Xc[3], Yc[3], Dc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      Xc[c] = cur.X[c];
+      Yc[c] = (1.0f - cur.fa) * cur.r0[c] + cur.fa * cur.r1[c];
+      Dc[c] = cur.dsel * (cur.r1[c] - cur.r0[c]);
+    }
+    if (yr + 1 < y_end + 2) issue_row(yr + 1, xsum_next, nxt);
+    if (yr + 2 < y_end + 2) xsum_next = load_xsum(yr + 2);
     // ---------------- stage B: horizontal sums of row yr, window coefficients of row qy = yr - 1
     const int qy = yr - 1;
     const bool q_in = (qy >= 0) && (qy < H) && x_in;
@@ -212,6 +239,7 @@ __global__ void __launch_bounds__(kGuidWarps * 32) guidance_stream_kernel(const 
         }
       }
     }
+    cur = nxt;
   }
 }
 

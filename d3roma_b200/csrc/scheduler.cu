@@ -11,28 +11,10 @@
 // (+ n * 4 B for the variance noise of DDPM / eta > 0).
 #include "common.cuh"
 #include "internal.h"
+#include "sched_math.cuh"
 
 namespace d3 {
 namespace {
-
-D3_DEVINL float clip_x0(float x0, int mode, float range) {
-  if (mode == 1) return fminf(fmaxf(x0, -range), range);
-  if (mode == 2) return __fdiv_rn(fminf(fmaxf(x0, -1.0f), 1.0f), 1.0f);
-  return x0;
-}
-
-D3_DEVINL void split_x0_eps(int ptype, float m, float s, float sa, float sb, float& x0, float& eps) {
-  if (ptype == 0) {  // epsilon
-    x0 = __fdiv_rn(__fsub_rn(s, __fmul_rn(sb, m)), sa);
-    eps = m;
-  } else if (ptype == 1) {  // sample
-    x0 = m;
-    eps = __fdiv_rn(__fsub_rn(s, __fmul_rn(sa, x0)), sb);
-  } else {  // v_prediction
-    x0 = __fsub_rn(__fmul_rn(sa, s), __fmul_rn(sb, m));
-    eps = __fadd_rn(__fmul_rn(sa, m), __fmul_rn(sb, s));
-  }
-}
 
 __global__ void __launch_bounds__(256) ddim_step_kernel(const float* __restrict__ mo, const float* __restrict__ xs,
                                                         const float* __restrict__ noise, d3_ddim_coeffs c, int64_t n,

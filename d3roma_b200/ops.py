@@ -231,16 +231,30 @@ def conv_in_direct(planes: torch.Tensor, wT: torch.Tensor, *, base: Optional[tor
 
 
 def conv_out_fused(x: torch.Tensor, stats: torch.Tensor, gamma, beta, w, bias, dc: int, eps: float = 1e-5,
-                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   out: Optional[torch.Tensor] = None, ddim=None):
+    """conv_norm_out + SiLU + conv_out.  ``ddim=(sample, coeffs)``: the DDIM update (eta = 0) is applied to the model
+    output in the same pass (``d3_conv_out_fused_ddim``) and ``(prev_sample, pred_original)`` is returned instead of the
+    model output."""
     _check_nhwc(x, "x")
     B, H, W, Cc = x.shape
     if Cc != 128:
         raise ValueError("conv_out_fused expects 128 input channels")
-    if out is None:
-        out = torch.empty((B, dc, H, W), dtype=torch.float32, device=x.device)
     ws = None
     if x.dtype != torch.float32:  # scratch for the 9*dc fp32 tap maps (torch's caching allocator; graph-capturable)
         ws = torch.empty((_lib.lib().d3_conv_out_workspace_bytes(B, H, W, dc),), dtype=torch.uint8, device=x.device)
+    if ddim is not None:
+        sample, coeffs = ddim
+        s = _f32c(sample, "sample")
+        if s.shape != (B, dc, H, W) or x.dtype == torch.float32:
+            raise ValueError("conv_out_fused(ddim=): sample must be fp32 [B,dc,H,W] and the activations 16-bit")
+        prev, orig = torch.empty_like(s), torch.empty_like(s)
+        _lib.check(_lib.lib().d3_conv_out_fused_ddim(
+            x.data_ptr(), x.stride(2), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w.data_ptr(),
+            bias.data_ptr(), B, H, W, dc, eps, _ptr(out), _ptr(ws), _dt(x), s.data_ptr(), C.byref(coeffs),
+            prev.data_ptr(), orig.data_ptr(), _stream()))
+        return prev, orig
+    if out is None:
+        out = torch.empty((B, dc, H, W), dtype=torch.float32, device=x.device)
     _lib.check(_lib.lib().d3_conv_out_fused(x.data_ptr(), x.stride(2), stats.data_ptr(), gamma.data_ptr(),
                                             beta.data_ptr(), w.data_ptr(), bias.data_ptr(), B, H, W, dc, eps,
                                             out.data_ptr(), _ptr(ws), _dt(x), _stream()))

@@ -196,8 +196,9 @@ class GuidedDiffusionPipeline:
             def run():
                 x = g["x"]
                 for i, t in enumerate(sch.timesteps):
-                    m = u.forward_split(x, g["c"], g["ts"][i], cond_base=g["base"], arena=g["arena"], tb=g["tb"][i])
-                    x = sch.step(m, t, x).prev_sample
+                    # the DDIM update rides in the UNet's last kernel (d3_conv_out_fused_ddim): same bits as sch.step(m, t, x)
+                    x, _ = u.forward_split(x, g["c"], g["ts"][i], cond_base=g["base"], arena=g["arena"], tb=g["tb"][i],
+                                           ddim=sch.step_coeffs(int(t)))
                     if (i + 1) % plot_every == 0:
                         ops.clamp_into(x, g["stack"], (i + 1) // plot_every - 1)
                 ops.clamp_into(x, g["img"], 0)

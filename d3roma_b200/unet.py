@@ -408,12 +408,15 @@ class UNet2DModel:
     @torch.no_grad()
     def forward_split(self, sample: torch.Tensor, cond: Optional[torch.Tensor], timestep,
                       cond_base: Optional[torch.Tensor] = None, arena: Optional[_StatsArena] = None,
-                      tb: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      tb: Optional[torch.Tensor] = None, ddim=None):
         """UNet forward on ``cat([sample, cond], 1)`` without materialising the concat.
         sample fp32 [B,dc,H,W], cond fp32 [B,Cc,H,W] (contiguous, CUDA); returns fp32 [B,out_channels,H,W].
         ``cond_base``: precomputed ``self.cond_base(cond, Cs)`` (the CUDA-graph path passes its static buffer).
         ``arena``: the GroupNorm statistics arena to use (a captured graph owns its own, so that a later call with a
-        larger batch can never free memory a live graph still writes to)."""
+        larger batch can never free memory a live graph still writes to).
+        ``ddim``: a ``d3_ddim_coeffs`` struct (``MyDDIMScheduler.step_coeffs``) - the DDIM update of ``sample`` (eta = 0)
+        is applied to the model output inside the last kernel and ``(prev_sample, pred_original_sample)`` is returned
+        instead of the model output (bit-identical to ``scheduler.step`` on it)."""
         if not self._loaded:
             raise RuntimeError("UNet2DModel: load_state_dict() has not been called")
         B, Cs, H, Wd = sample.shape
@@ -510,7 +513,8 @@ class UNet2DModel:
                     ops.conv2d_igemm(h.t, W[p + f".w{ph}"], W[p + ".b"], ksize=3, out=up, stats=st,
                                      up2x_phase=ph + 1)
                 h = _Act(up, st)
-        return ops.conv_out_fused(h.t, h.stats, W["out.g"], W["out.b"], W["out.w"], W["out.bias"], self.out_channels)
+        return ops.conv_out_fused(h.t, h.stats, W["out.g"], W["out.b"], W["out.w"], W["out.bias"], self.out_channels,
+                                  ddim=None if ddim is None else (sample, ddim))
 
     @staticmethod
     def _cond_key(cond: Optional[torch.Tensor]):

@@ -196,6 +196,14 @@ int d3_sched_ddim_step(const float* model_output, const float* sample, const flo
 int d3_sched_ddpm_step(const float* model_output, const float* sample, const float* variance_noise,
                        const d3_ddpm_coeffs* c, int64_t n, float* prev_sample, float* pred_original,
                        float* prev_mean, void* stream);
+/* conv_norm_out + SiLU + conv_out (d3_conv_out_fused) with the DDIM update (eta = 0) applied to the model output in
+ * the same gather pass: sample = x_t fp32 [B,dc,H,W]; writes prev_sample = x_{t-1} and pred_original = x0 exactly as
+ * d3_sched_ddim_step would (bit-identical), model_out optional (may be NULL).  16-bit dtypes only.  Replaces
+ * custom_pipelines.py:173-175 (unet(...).sample followed by scheduler.step) for the unguided loop. */
+int d3_conv_out_fused_ddim(const void* x, int pitch, const double* stats, const float* gamma, const float* beta,
+                           const float* w, const float* bias, int B, int H, int W, int dc, float eps, float* model_out,
+                           void* workspace, int dtype, const float* sample, const d3_ddim_coeffs* c, float* prev_sample,
+                           float* pred_original, void* stream);
 /* out = a*x (+ b*y) (+ c*z), each product and sum rounded separately (recombination after a guidance
  * perturbation of x0: scheduler_ddim.py:468, scheduler_ddpm.py:512). y, z may be NULL. */
 int d3_lincomb(float a, const float* x, float b, const float* y, float c, const float* z, int64_t n, float* out,

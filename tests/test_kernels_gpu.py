@@ -141,3 +141,32 @@ def test_conv_in_direct_split_matches_torch(B, Cs, Cc, H, W, dt):
     assert bool(((base16.float() - ref_base).abs() <= 2.0 ** -11 * ref_base.abs() + 1e-6).all())
     out16 = ops.conv_in_direct(x, ops.pack_conv_in_direct(w, 0, Cs), base=base16, out_dtype=dt)
     assert bool(((out16.float() - ref).abs() <= ulp * ref.abs() + 2.0 ** -11 * ref_base.abs() + 1e-4).all())
+
+
+@pytest.mark.parametrize("ptype", ["sample", "epsilon", "v_prediction"])
+@pytest.mark.parametrize("dc", [1, 3])
+def test_conv_out_with_fused_ddim_update_is_bit_identical(ptype, dc):
+    """d3_conv_out_fused_ddim (the DDIM update applied inside the conv_out gather) == d3_conv_out_fused followed by
+    d3_sched_ddim_step, bit for bit, for every prediction type."""
+    import d3roma_b200 as d
+    from d3roma_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(13)
+    B, H, W = 2, 24, 40
+    x = torch.randn(B, H, W, 128, device="cuda", generator=g).to(torch.float16)
+    gamma, beta = torch.rand(128, device="cuda", generator=g) + 0.5, torch.randn(128, device="cuda", generator=g) * 0.1
+    w = torch.randn(dc, 9, 128, device="cuda", generator=g) / 34.0
+    bias = torch.randn(dc, device="cuda", generator=g) * 0.1
+    sample = torch.randn(B, dc, H, W, device="cuda", generator=g)
+    sch = d.MyDDIMScheduler.from_config(dict(num_train_timesteps=128, beta_schedule="squaredcos_cap_v2",
+                                             prediction_type=ptype, clip_sample=True, set_alpha_to_one=False,
+                                             steps_offset=1))
+    sch.set_timesteps(10)
+    for t in (109, 61, 1):
+        m = ops.conv_out_fused(x, _quad_stats(x), gamma, beta, w, bias, dc)
+        want = sch.step(m, t, sample)
+        prev, x0 = ops.conv_out_fused(x, _quad_stats(x), gamma, beta, w, bias, dc, ddim=(sample, sch.step_coeffs(t)))
+        assert torch.equal(prev, want.prev_sample) and torch.equal(x0, want.pred_original_sample)
+        # the model output can be written too
+        mo = torch.empty_like(m)
+        ops.conv_out_fused(x, _quad_stats(x), gamma, beta, w, bias, dc, out=mo, ddim=(sample, sch.step_coeffs(t)))
+        assert torch.equal(mo, m)
