@@ -6,6 +6,7 @@ Public surface mirrors the reference's classes for this path (jie0530/d3roma ``c
 """
 from .guidance import FlowGuidance  # noqa: F401
 from .pipelines import GuidedDiffusionPipeline, GuidedPipelineOutput  # noqa: F401
+from .latent_pipeline import GuidedLatentDiffusionPipeline  # noqa: F401
 from .prepost import SIM_CAMERA, Camera, InputPadder, Normalizer  # noqa: F401
 from .scheduler_ddim import DDIMSchedulerOutput, MyDDIMScheduler  # noqa: F401
 from .scheduler_ddpm import DDPMSchedulerOutput, MyDDPMScheduler  # noqa: F401

@@ -1,0 +1,188 @@
+"""``GuidedLatentDiffusionPipeline`` — the sampling LOOP of the reference's latent family
+(``/root/reference/core/custom_pipelines.py:208-460``) with the same constructor, ``__call__`` signature, conditioning
+keys, RNG consumption and output semantics, over this package's scheduler kernels.
+
+Scope (honest labelling): the three NETWORKS of the latent family — the SD-2.1
+``UNet2DConditionModel``, the ``AutoencoderKL`` VAE and the CLIP text encoder — are third-party models that this
+package does NOT implement; ``unet`` / ``vae`` / ``tokenizer`` / ``text_encoder`` are whatever torch modules the caller
+loads (exactly the objects the reference passes, ``train.py:743-772, 821-833``).  What is built here is the part of the
+path that is the reference's own code: the loop, its latent encode / decode conventions (``encode_rgb`` :47-59,
+``encode_disp`` :35-45, ``__decode_depth`` :255-272), and the scheduler steps (``d3_sched_ddim_step`` /
+``d3_sched_ddpm_step``) with the guidance hook wiring of :389-399.
+
+Differences from the reference, none of which change a returned value:
+  * ``encode_disp(sim_disp)`` is evaluated once instead of at every step of the ``"rgb+raw"`` variant (:356 re-encodes
+    a constant with a deterministic encoder);
+  * the final ``__decode_depth(image)`` of :428 is skipped (its result is discarded: the pipeline returns
+    ``image_final``, the decoded x0 of the last step, :414-415, 454);
+  * the five intermediate lists (:403-411) hold one decoded tensor per plotted step, aliased five times.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Union
+
+import torch
+
+from .pipelines import GuidedPipelineOutput
+from .scheduler_ddim import randn_tensor
+
+LATENT_SCALE = 0.18215
+
+
+def encode_rgb(vae, x: torch.Tensor, rgb_latent_scale_factor: float = LATENT_SCALE) -> torch.Tensor:
+    """custom_pipelines.py:47-59: mean of the VAE posterior, scaled."""
+    moments = vae.quant_conv(vae.encoder(x))
+    mean, _ = torch.chunk(moments, 2, dim=1)
+    return mean * rgb_latent_scale_factor
+
+
+def encode_disp(vae, x: torch.Tensor, depth_latent_scale_factor: float = LATENT_SCALE) -> torch.Tensor:
+    """custom_pipelines.py:35-45: the one-channel map replicated to three channels, then ``encode_rgb``."""
+    return encode_rgb(vae, x.repeat(1, 3, 1, 1), depth_latent_scale_factor)
+
+
+class LatentGradientGuidance:
+    """The latent-space form of ``FlowGuidance.perturb`` in "gradient" mode (core/guidance.py:225-241): ten Adam steps
+    (lr 1e-3) on the predicted latent, minimising the masked L1 distance between the decoded + denormalised map and the
+    raw depth.  It differentiates THROUGH the decoder, so it needs a decoder torch.autograd can see (the caller's torch
+    ``AutoencoderKL``); with the forward-only CUDA decoder of this package it raises.  Every LDM config the reference
+    ships evaluates with ``flow_guidance_weights: [0]`` (conf/task/eval_ldm*.yaml), i.e. never reaches this."""
+
+    def __init__(self, guidance):
+        self.flow_guidance_weight = guidance.flow_guidance_weight
+        self.flow_guidance_mode = guidance.flow_guidance_mode
+
+    def perturb(self, pred_original_sample, t, decoder, denormer, raw_mask=None, left_image=None, right_image=None,
+                raw_depth=None):
+        if self.flow_guidance_mode != "gradient":
+            raise NotImplementedError
+        lat = pred_original_sample.clone().requires_grad_(True)
+        raw_depth = raw_depth.to(lat.device)
+        mask = raw_depth > 0.0
+        opt = torch.optim.Adam([lat], lr=0.001)
+        with torch.enable_grad():
+            for _ in range(10):
+                opt.zero_grad()
+                pred = denormer(decoder(lat))
+                if not pred.requires_grad:
+                    raise NotImplementedError("latent gradient guidance needs a differentiable (torch) VAE decoder")
+                torch.nn.functional.l1_loss(pred * mask, raw_depth * mask).backward()
+                opt.step()
+        return lat.detach()
+
+
+class GuidedLatentDiffusionPipeline:
+    def __init__(self, unet, vae, tokenizer, text_encoder, scheduler, guidance):
+        self.register_modules(unet=unet, vae=vae, tokenizer=tokenizer, text_encoder=text_encoder, scheduler=scheduler,
+                              guidance=guidance)
+        self._progress_bar_config = {}
+
+    def register_modules(self, **kwargs):
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    @property
+    def device(self) -> torch.device:
+        for m in (self.unet, self.vae):
+            if isinstance(m, torch.nn.Module):
+                for p in m.parameters():
+                    return p.device
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def to(self, device):
+        for m in (self.unet, self.vae, self.text_encoder):
+            if isinstance(m, torch.nn.Module):
+                m.to(device)
+        return self
+
+    def set_progress_bar_config(self, **kwargs):
+        self._progress_bar_config = kwargs
+
+    def progress_bar(self, iterable):
+        if self._progress_bar_config.get("disable", True) and "desc" not in self._progress_bar_config:
+            return iterable
+        try:
+            from tqdm.auto import tqdm
+            return tqdm(iterable, **self._progress_bar_config)
+        except Exception:  # pragma: no cover
+            return iterable
+
+    def _encode_empty_text(self) -> torch.Tensor:
+        """custom_pipelines.py:241-253: embedding of the empty prompt ([1, 2, 1024] for the SD-2.1 text encoder)."""
+        tok = self.tokenizer("", padding="do_not_pad", max_length=self.tokenizer.model_max_length, truncation=True,
+                             return_tensors="pt")
+        return self.text_encoder(tok.input_ids.to(self.text_encoder.device))[0]
+
+    def _decode_depth(self, depth_latent: torch.Tensor, depth_latent_scale_factor: float = LATENT_SCALE) -> torch.Tensor:
+        """custom_pipelines.py:255-272: undo the latent scale, decode, mean over the output channels."""
+        z = self.vae.post_quant_conv(depth_latent / depth_latent_scale_factor)
+        return self.vae.decoder(z).mean(dim=1, keepdim=True)
+
+    @torch.no_grad()
+    def __call__(self, rgb_images, left_images=None, right_images=None, sim_disp=None, raw_depth=None, raw_mask=None,
+                 empty_text_embed=None, num_inference_steps: int = 128, num_intermediate_images: int = 128,
+                 add_noise_rgb: bool = False, depth_channels: int = 1, cond_channels: str = "rgb",
+                 denorm: Callable = None,
+                 generator: Optional[Union[torch.Generator, List[torch.Generator]]] = None):
+        """ in & out images are preferably on the same device """
+        assert num_intermediate_images > 0 and num_inference_steps % num_intermediate_images == 0
+        plot_every = num_inference_steps // num_intermediate_images
+        shapes = [t.shape for t in (rgb_images, left_images, right_images, sim_disp) if t is not None]
+        assert shapes, "no input image"
+        input_shape = shapes[0]
+        dev = self.device
+        if empty_text_embed is None:
+            empty_text_embed = self._encode_empty_text()
+        empty_text_embed = empty_text_embed.to(dev).repeat((input_shape[0], 1, 1))
+
+        image = randn_tensor((input_shape[0], 4, input_shape[2] // 8, input_shape[3] // 8), generator=generator)
+        image = image.to(dev)
+        up = lambda t: None if t is None else t.to(dev)  # noqa: E731
+        rgb_images, left_images, right_images, sim_disp = up(rgb_images), up(left_images), up(right_images), up(sim_disp)
+        cond_images = None if rgb_images is None else encode_rgb(self.vae, rgb_images)
+        left_lat = None if left_images is None else encode_rgb(self.vae, left_images)
+        right_lat = None if right_images is None else encode_rgb(self.vae, right_images)
+        sim_lat = None if sim_disp is None else encode_disp(self.vae, sim_disp)
+
+        orders = {"rgb": ("rgb",), "rgb+raw": ("rgb", "raw"), "left+right": ("left", "right"),
+                  "left+right+raw": ("left", "right", "raw"), "rgb+left+right": ("rgb", "left", "right"),
+                  "rgb+left+right+raw": ("rgb", "left", "right", "raw")}
+        if cond_channels not in orders:
+            raise ValueError(f"Unknown cond_channels: {cond_channels}")
+        lat = {"left": left_lat, "right": right_lat, "raw": sim_lat}
+
+        self.scheduler.set_timesteps(num_inference_steps)
+        is_ddim = self.scheduler.__class__.__name__ == "MyDDIMScheduler"
+        guided = self.guidance is not None and self.guidance.flow_guidance_weight > 0.0
+        guidance = LatentGradientGuidance(self.guidance) if guided else None
+        decoded: List[torch.Tensor] = []
+        image_final = None
+        for step, t in enumerate(self.progress_bar(self.scheduler.timesteps)):
+            final_rgb = cond_images
+            if "rgb" in cond_channels and add_noise_rgb:
+                noise_rgb = torch.randn(cond_images.shape).to(cond_images.device)
+                timesteps = (t * torch.ones(cond_images.shape[0]).to(cond_images.device)).long()
+                noisy_rgb = self.scheduler.add_noise(cond_images, noise_rgb, timesteps)
+                final_rgb = cond_images * 0.5 + noisy_rgb * 0.5
+            parts = [image] + [final_rgb if k == "rgb" else lat[k] for k in orders[cond_channels]]
+            model_output = self.unet(torch.cat(parts, dim=1), t, empty_text_embed).sample
+            if is_ddim:
+                assert self.guidance.flow_guidance_mode != "imputation", \
+                    "latent diffusion does not support imputation mode"
+                g = self.scheduler.step(model_output, t, image, guidance=guidance, decoder=self._decode_depth,
+                                        denormer=denorm, raw_mask=raw_mask, left_image=left_images,
+                                        right_image=right_images, raw_depth=raw_depth)
+            else:
+                g = self.scheduler.step(model_output, t, image)
+            image = g.prev_sample
+            last = step == num_inference_steps - 1
+            d_hat = None
+            if (step + 1) % plot_every == 0:
+                d_hat = self._decode_depth(g.pred_original_sample).clamp(-1, 1)
+                decoded.append(d_hat)
+            if last:
+                image_final = d_hat if d_hat is not None else self._decode_depth(g.pred_original_sample).clamp(-1, 1)
+        stack = torch.concat(decoded, dim=1)
+        return GuidedPipelineOutput(images=image_final, images_pred_orig=stack, images_perturbed_orig=stack,
+                                    images_pred_prev=stack, images_purturbed_pred_prev=stack,
+                                    images_sampled_prev=stack)

@@ -409,6 +409,43 @@ def gen_unet_oracle(store):
         store[f"{tag}/n_params"] = np.array(sum(p.numel() for p in net.parameters()))
 
 
+def gen_latent(store):
+    """The reference's GuidedLatentDiffusionPipeline (core/custom_pipelines.py:208-460) driven with tiny stand-in
+    networks (oracle/ldm_standins.py): pins the LOOP logic of the latent family - latent encode / decode conventions,
+    conditioning order per cond_channels key, scheduler steps, returned image_final and intermediates."""
+    import contextlib
+    import io
+    from core.custom_pipelines import GuidedLatentDiffusionPipeline
+    from oracle.ldm_standins import TinyCondUNet, TinyVAE, empty_text_embed
+    g = torch.Generator().manual_seed(2025)
+    B, H, W = 2, 32, 64
+    rgb, left, right = (torch.rand(B, 3, H, W, generator=g) * 2 - 1 for _ in range(3))
+    sim = torch.rand(B, 1, H, W, generator=g) * 2 - 1
+    raw_depth = torch.rand(B, 1, H, W, generator=g) * 2.0
+    raw_depth[raw_depth < 0.4] = 0.0
+    store["rgb"], store["left"], store["right"], store["sim"], store["raw_depth"] = (_np(v) for v in
+                                                                                       (rgb, left, right, sim, raw_depth))
+    vae, ete = TinyVAE(), empty_text_embed()
+    cases = {
+        # clipped-x0 scheduler configs keep the random stand-in UNet's trajectories inside the decoder's linear range
+        "ddim_lrr": ("left+right+raw", 16, MyDDIMScheduler.from_config(DDIM_CONFIGS["cos128_v"]), 10, 5, 0.0),
+        "ddim_rgbraw": ("rgb+raw", 12, MyDDIMScheduler.from_config(DDIM_CONFIGS["lin1000_v_trailing"]), 8, 2, 0.0),
+        "ddpm_rgb": ("rgb", 8, MyDDPMScheduler.from_config(DDPM_CONFIGS["cos128_sample_thresh"]), 8, 4, 0.0),
+        "ddim_grad": ("rgb+left+right+raw", 20, MyDDIMScheduler.from_config(DDIM_CONFIGS["cos128_epsilon"]), 4, 2, 1.0),
+    }
+    for tag, (cc, cin, sch, n, plots, w) in cases.items():
+        unet = TinyCondUNet(cin)
+        guid = FlowGuidance(flow_guidance_weight=w, flow_guidance_mode="gradient")
+        pipe = GuidedLatentDiffusionPipeline(unet, vae, None, None, sch, guid)
+        torch.manual_seed(321)     # DDPM variance noise: default generator
+        with contextlib.redirect_stdout(io.StringIO()):
+            out = pipe(rgb, left, right, sim, raw_depth, None, empty_text_embed=ete, num_inference_steps=n,
+                       num_intermediate_images=plots, cond_channels=cc, denorm=lambda d: (d / 2.0 + 0.5) * 2.0,
+                       generator=torch.Generator().manual_seed(7))
+        store[f"{tag}/images"] = _np(out.images)
+        store[f"{tag}/intermediate"] = _np(out.images_pred_orig)
+
+
 def gen_piecewise(store):
     """Normalizer(mode="piecewise") of the reference (utils_d3roma/utils.py:198-229, 275-293): 3 channels with bounds
     [64, 32, 32] (the class defaults), 2 channels with a gamma, and the 1-channel degenerate case."""
@@ -574,7 +611,7 @@ def main():
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
     for name, fn in (("ddim", gen_ddim), ("ddpm", gen_ddpm), ("prepost", gen_prepost), ("guidance", gen_guidance),
-                     ("pipeline", gen_pipeline), ("guided", gen_guided), ("reproject", gen_reproject), ("piecewise", gen_piecewise), ("unet_oracle", gen_unet_oracle), ("postproc", gen_postproc), ("frontend", gen_frontend), ("ransac", gen_ransac)):
+                     ("pipeline", gen_pipeline), ("guided", gen_guided), ("reproject", gen_reproject), ("piecewise", gen_piecewise), ("latent", gen_latent), ("unet_oracle", gen_unet_oracle), ("postproc", gen_postproc), ("frontend", gen_frontend), ("ransac", gen_ransac)):
         store = {}
         with torch.no_grad():
             fn(store)
