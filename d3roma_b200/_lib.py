@@ -40,6 +40,7 @@ class ConvParams(C.Structure):
         ("dtype", C.c_int32),
         ("up2x_phase", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("Cout_valid", C.c_int32), ("asym_pad", C.c_int32),
     ]
 
 
@@ -134,6 +135,17 @@ def _declare(lib: C.CDLL) -> None:
         "d3_frame_to_input": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
         "d3_depth_to_input": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, f32, f32, f32, f32, f32, vp, vp,
                                     vp, vp]),
+        "d3_gn_stats": (i32, [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, vp]),
+        "d3_gn_apply": (i32, [vp, i32, i32, vp, i32, i32, vp, vp, vp, i32, i32, i32, f32, i32, vp, i32, i32, vp]),
+        "d3_layernorm": (i32, [vp, i32, vp, vp, i64, i32, f32, vp, i32, i32, vp]),
+        "d3_geglu": (i32, [vp, i32, i64, i32, vp, i32, i32, vp]),
+        "d3_attention_hd64": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp]),
+        "d3_cross_attention_small": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp]),
+        "d3_linear_small": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, vp, i32, vp]),
+        "d3_timestep_sincos": (i32, [vp, i32, i32, i32, f32, vp, vp]),
+        "d3_nchw_to_nhwc16": (i32, [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
+        "d3_nhwc16_to_nchw": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+        "d3_resize_nearest_nhwc16": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, i32, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here == header and library out of sync

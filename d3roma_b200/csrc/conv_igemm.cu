@@ -41,6 +41,7 @@ constexpr uint32_t kStagingBytes = kTileM * 128;   // one 64-channel chunk of th
 
 struct ConvKArgs {
   int B, Ho, Wo, Cout;
+  int CoutV;               // channels that exist in the output tensor (<= Cout; the rest are weight padding)
   int TH, TW, tilesH, tilesW, nTilesN, numTiles;
   int splitK, kbPer;       // pixels-as-M kernel: K-blocks split over splitK CTAs per tile (fp32 partials in ws)
   float* ws;               // [splitK][B*Ho*Wo][Cout] fp32
@@ -234,10 +235,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (a.stride == 1) {
               tma_load_4d(sA, &tmA, &full_bar[stage], cb * 64, t.w0 + a.tap_dw[tap], t.h0 + a.tap_dh[tap], t.b);
             } else {
-              // input pixel (2*ho + kh - 1, 2*wo + kw - 1) in the parity-split 5-D view
-              const int dh = kh - 1, dw = kw - 1;
-              const int hh = t.h0 + (dh < 0 ? -1 : 0), ph = (dh == 0) ? 0 : 1;
-              const int ww = t.w0 + (dw < 0 ? -1 : 0), pw = (dw == 0) ? 0 : 1;
+              // input pixel (2*ho + kh - pad, 2*wo + kw - pad) in the parity-split 5-D view (pad = 1, or 0 for the
+              // VAE encoder's F.pad(0,1,0,1) + unpadded stride-2 conv): row 2*hh + ph with hh = ho + floor(dh / 2)
+              const int dh = kh - a.pad, dw = kw - a.pad;
+              const int hh = t.h0 + (dh >> 1), ph = dh & 1;
+              const int ww = t.w0 + (dw >> 1), pw = dw & 1;
               tma_load_5d(sA, &tmA, &full_bar[stage], pw * a.sc_off2 + cb * 64, ww, ph, hh, t.b);
             }
           } else if (kb < a.kbMain + a.kbSc1) {
@@ -359,7 +361,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int n_base = t.n0 + c * 64;
         const float4* bp = reinterpret_cast<const float4*>(a.bias + (size_t)t.b * a.bias_bstride + n_base);
         const uint4* rp = nullptr;
-        if (a.residual != nullptr && valid) {
+        if (a.residual != nullptr && valid && n_base < a.CoutV) {   // padded channel chunks have no residual
           rp = reinterpret_cast<const uint4*>(a.residual + ((size_t)(t.b * a.Ho + h) * a.Wo + w) * a.res_pitch +
                                               n_base);
         }
@@ -373,7 +375,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
         if (et == 0) {
-          tma_store_4d(&tmO, sbuf, n_base, t.w0, t.h0, t.b);
+          if (n_base < a.CoutV) tma_store_4d(&tmO, sbuf, n_base, t.w0, t.h0, t.b);
           tma_store_commit();
         }
         if (a.stats != nullptr && et < 32) {
@@ -659,9 +661,9 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (a.stride == 1) {
               tma_load_4d(sP, &tmA, &full_bar[stage], cb * 64, t.w0 + a.tap_dw[tap], t.h0 + a.tap_dh[tap], t.b);
             } else {
-              const int dh = kh - 1, dw = kw - 1;
-              const int hh = t.h0 + (dh < 0 ? -1 : 0), ph = (dh == 0) ? 0 : 1;
-              const int ww = t.w0 + (dw < 0 ? -1 : 0), pw = (dw == 0) ? 0 : 1;
+              const int dh = kh - a.pad, dw = kw - a.pad;
+              const int hh = t.h0 + (dh >> 1), ph = dh & 1;
+              const int ww = t.w0 + (dw >> 1), pw = dw & 1;
               tma_load_5d(sP, &tmA, &full_bar[stage], pw * a.sc_off2 + cb * 64, ww, ph, hh, t.b);
             }
           } else if (kb < a.kbMain + a.kbSc1) {
@@ -960,8 +962,8 @@ conv_igemm_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         fence_proxy_async_smem();
         named_bar_sync(2, 256);
         if (et == 0 && !D3_DBG(a, 8)) {
-          tma_store_4d(&tmO, sbuf, t.n0, wpass, h, t.b);
-          tma_store_4d(&tmO, sbuf + kStagingBytes / 2, t.n0 + 64, wpass, h, t.b);
+          if (t.n0 < a.CoutV) tma_store_4d(&tmO, sbuf, t.n0, wpass, h, t.b);
+          if (t.n0 + 64 < a.CoutV) tma_store_4d(&tmO, sbuf + kStagingBytes / 2, t.n0 + 64, wpass, h, t.b);
           tma_store_commit();
         }
         D3_PROF(const long long q4c = clock64(); p_q[0] += q1 - q0; p_q[1] += q2c - q1; p_q[2] += q3 - q2c;
@@ -1226,6 +1228,8 @@ int plan_split_k(const d3_conv_params* p, int* BN_out) {
   static int want = -1;
   if (want < 0) { const char* e = getenv("D3_CONV_SPLITK"); want = e ? atoi(e) : 4; }
   if (!want || p->up2x_phase != 0 || p->Cout == 128) return 1;
+  if (p->Cout_valid > 0 && p->Cout_valid != p->Cout) return 1;   // the finalize kernel writes all Cout channels
+  if (p->Cout > 2048) return 1;                                   // ... with one thread per 8 channels of a pixel
   const int numTiles = pixTiles * (p->Cout / BN);
   const int kbTotal = (p->ksize * p->ksize * p->Cin + (p->sc1 ? p->C1 : 0) + (p->sc2 ? p->C2 : 0)) / 64;
   if (numTiles * 2 > num_sms() || kbTotal < 8) return 1;
@@ -1271,6 +1275,8 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   if (p->dtype == D3_DTYPE_F32) {
     D3_REQUIRE(p->x && p->w && p->out && p->bias, "conv: null pointer");
     D3_REQUIRE(p->up2x_phase >= 0 && p->up2x_phase <= 4, "conv: bad up2x_phase");
+    D3_REQUIRE((p->Cout_valid == 0 || p->Cout_valid == p->Cout) && !p->asym_pad,
+               "conv: Cout_valid / asym_pad are 16-bit tensor-core path options");
     return conv2d_f32(p, stream);
   }
   D3_REQUIRE(p->Cin > 0 && p->Cin % 64 == 0, "conv: Cin must be a multiple of 64 (got %d)", p->Cin);
@@ -1296,6 +1302,12 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   a.Ho = Ho;
   a.Wo = Wo;
   a.Cout = p->Cout;
+  const int CoutV = p->Cout_valid > 0 ? p->Cout_valid : p->Cout;
+  a.CoutV = CoutV;
+  D3_REQUIRE(CoutV <= p->Cout && CoutV % 64 == 0, "conv: Cout_valid must be a multiple of 64, <= Cout (got %d)", CoutV);
+  D3_REQUIRE(CoutV == p->Cout || (p->stats == nullptr && p->up2x_phase >= 0),
+             "conv: GroupNorm statistics are not available with a clipped output (Cout_valid < Cout)");
+  D3_REQUIRE(!p->asym_pad || (p->stride == 2 && p->ksize == 3), "conv: asym_pad needs a 3x3 stride-2 conv");
   // Cout == 128 layers run the pixels-as-N kernel (weights on the M side); see conv_igemm_t_kernel.
   static int no_t = -1;
   if (no_t < 0) { const char* e = getenv("D3_CONV_NO_T"); no_t = e ? atoi(e) : 0; }
@@ -1357,7 +1369,7 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
   a.ws = nullptr;
   a.ksize = p->ksize;
   a.stride = p->stride;
-  a.pad = p->ksize / 2;
+  a.pad = p->asym_pad ? 0 : p->ksize / 2;
   a.ntaps = taps;
   if (phase) {
     // nearest-2x upsample folded into the conv: output pixel (2i+py, 2j+px) reads input rows {i+py-1, i+py} and
@@ -1454,7 +1466,8 @@ extern "C" int d3_conv2d_igemm(const d3_conv_params* p, void* stream_) {
       return set_error(D3_ERR_CUDA, "conv: tensor map B encode failed (%d)", rc);
   }
   {
-    uint64_t dims[4] = {(uint64_t)p->Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)p->B};
+    // channels >= Cout_valid are weight padding: the TMA store (and the residual load) clips them
+    uint64_t dims[4] = {(uint64_t)CoutV, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)p->B};
     uint64_t str[3] = {(uint64_t)p->out_pitch * 2, (uint64_t)Wo * p->out_pitch * 2,
                        (uint64_t)Ho * Wo * p->out_pitch * 2};
     const void* obase = p->out;

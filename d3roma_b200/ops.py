@@ -74,18 +74,21 @@ def pack_upsample_weights(w_oihw: torch.Tensor, dtype: torch.dtype = torch.bfloa
 def conv2d_igemm(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, *, ksize: int, stride: int = 1,
                  sc1: Optional[torch.Tensor] = None, sc2: Optional[torch.Tensor] = None,
                  residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                 stats: Optional[torch.Tensor] = None, up2x_phase: int = 0) -> torch.Tensor:
-    """tcgen05 implicit-GEMM conv (see ``d3_conv2d_igemm`` in include/d3roma_b200.h)."""
+                 stats: Optional[torch.Tensor] = None, up2x_phase: int = 0, cout_valid: int = 0,
+                 asym_pad: bool = False) -> torch.Tensor:
+    """tcgen05 implicit-GEMM conv (see ``d3_conv2d_igemm`` in include/d3roma_b200.h).  ``cout_valid``: the output has
+    only that many channels; the remaining rows of ``w_packed`` / ``bias`` are zero padding up to a multiple of 128."""
     _check_nhwc(x, "x")
     B, H, W, Cin = x.shape
     Cout = w_packed.shape[0]
+    Cv = cout_valid or Cout
     Ho, Wo = H // stride, W // stride
     if up2x_phase:
         Ho, Wo = 2 * H, 2 * W
     if out is None:
-        out = torch.empty((B, Ho, Wo, Cout), dtype=x.dtype, device=x.device)
-    if tuple(out.shape) != (B, Ho, Wo, Cout):
-        raise ValueError(f"out has shape {tuple(out.shape)}, expected {(B, Ho, Wo, Cout)}")
+        out = torch.empty((B, Ho, Wo, Cv), dtype=x.dtype, device=x.device)
+    if tuple(out.shape) != (B, Ho, Wo, Cv):
+        raise ValueError(f"out has shape {tuple(out.shape)}, expected {(B, Ho, Wo, Cv)}")
     _check_nhwc(out, "out")
     p = _lib.ConvParams()
     p.x, p.B, p.H, p.W, p.Cin, p.x_pitch = x.data_ptr(), B, H, W, Cin, x.stride(2)
@@ -116,6 +119,8 @@ def conv2d_igemm(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, *,
         p.stats = stats.data_ptr()
     p.dtype = _dt(x)
     p.up2x_phase = int(up2x_phase)
+    p.Cout_valid = int(cout_valid)
+    p.asym_pad = int(bool(asym_pad))
     for t_ in (sc1, sc2, residual, out):
         if t_ is not None and t_.dtype != x.dtype:
             raise ValueError("all 16-bit operands of a conv must share one dtype")
@@ -283,6 +288,137 @@ def attention_hd8(qkv: torch.Tensor, C_: int) -> torch.Tensor:
     out = torch.empty((B, H, W, C_), dtype=qkv.dtype, device=qkv.device)
     _lib.check(_lib.lib().d3_attention_hd8(qkv.data_ptr(), qkv.stride(2), B, H * W, C_, out.data_ptr(),
                                            out.stride(2), _dt(qkv), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# latent family (UNet2DConditionModel / AutoencoderKL): ops of csrc/ldm_ops.cu
+# ------------------------------------------------------------------------------------------------
+def pad_rows(w: torch.Tensor, multiple: int = 128) -> torch.Tensor:
+    """Zero-pad dim 0 (output channels of a packed weight or bias) up to a multiple of the 128-channel MMA tile."""
+    r = (-w.shape[0]) % multiple
+    if r == 0:
+        return w.contiguous()
+    return torch.cat([w, w.new_zeros((r,) + tuple(w.shape[1:]))], 0).contiguous()
+
+
+def gn_stats(x1: torch.Tensor, chan: torch.Tensor, x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-channel fp64 sum / sum of squares of cat(x1, x2) accumulated into ``chan`` [B, C, 2] (zero on entry)."""
+    _check_nhwc(x1, "x1")
+    B, H, W, C1 = x1.shape
+    C2 = 0 if x2 is None else x2.shape[3]
+    if x2 is not None:
+        _check_nhwc(x2, "x2")
+    if chan.dtype != torch.float64 or chan.numel() != B * (C1 + C2) * 2:
+        raise ValueError("gn_stats: chan must be fp64 [B, C, 2]")
+    _lib.check(_lib.lib().d3_gn_stats(x1.data_ptr(), C1, x1.stride(2), _ptr(x2), C2, x2.stride(2) if x2 is not None else 0,
+                                      B, H * W, chan.data_ptr(), _dt(x1), _stream()))
+    return chan
+
+
+def gn_apply(x1: torch.Tensor, chan: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *,
+             x2: Optional[torch.Tensor] = None, groups: int = 32, eps: float = 1e-5, silu: bool = True,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm (+SiLU) of cat(x1, x2) from the per-channel moments of ``gn_stats`` (any group width)."""
+    B, H, W, C1 = x1.shape
+    C2 = 0 if x2 is None else x2.shape[3]
+    if out is None:
+        out = torch.empty((B, H, W, C1 + C2), dtype=x1.dtype, device=x1.device)
+    _lib.check(_lib.lib().d3_gn_apply(x1.data_ptr(), C1, x1.stride(2), _ptr(x2), C2, x2.stride(2) if x2 is not None else 0,
+                                      chan.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, H * W, groups, eps, int(silu),
+                                      out.data_ptr(), out.stride(2), _dt(x1), _stream()))
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """LayerNorm over the last dim of a 16-bit [..., C] tensor whose rows are ``x.stride(-2)`` apart."""
+    C_ = x.shape[-1]
+    M = x.numel() // C_
+    out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().d3_layernorm(x.data_ptr(), x.stride(-2), gamma.data_ptr(), beta.data_ptr(), M, C_, eps,
+                                       out.data_ptr(), C_, _dt(x), _stream()))
+    return out
+
+
+def geglu(x: torch.Tensor) -> torch.Tensor:
+    """[..., 2D] -> [..., D]: x[..., :D] * gelu(x[..., D:])."""
+    D = x.shape[-1] // 2
+    M = x.numel() // (2 * D)
+    out = torch.empty(tuple(x.shape[:-1]) + (D,), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().d3_geglu(x.data_ptr(), x.stride(-2), M, D, out.data_ptr(), D, _dt(x), _stream()))
+    return out
+
+
+def attention_hd64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
+    """q, k, v: [B, H, W, 64*heads] (channel-slice views of a fused QKV tensor are fine) -> [B, H, W, 64*heads]."""
+    B, H, W, C_ = q.shape
+    if C_ != 64 * heads:
+        raise ValueError("attention_hd64: head_dim must be 64")
+    out = torch.empty((B, H, W, C_), dtype=q.dtype, device=q.device)
+    _lib.check(_lib.lib().d3_attention_hd64(q.data_ptr(), q.stride(2), k.data_ptr(), k.stride(2), v.data_ptr(),
+                                            v.stride(2), B, H * W, heads, out.data_ptr(), C_, _dt(q), _stream()))
+    return out
+
+
+def cross_attention_small(q: torch.Tensor, kc: torch.Tensor, vc: torch.Tensor) -> torch.Tensor:
+    """q 16-bit [B, H, W, C]; kc, vc fp32 [B, L, C] (L <= 8) -> [B, H, W, C]."""
+    B, H, W, C_ = q.shape
+    L = kc.shape[1]
+    if kc.shape != (B, L, C_) or vc.shape != (B, L, C_) or kc.dtype != torch.float32 or not (kc.is_contiguous() and vc.is_contiguous()):
+        raise ValueError("cross_attention_small: kc / vc must be contiguous fp32 [B, L, C]")
+    out = torch.empty((B, H, W, C_), dtype=q.dtype, device=q.device)
+    _lib.check(_lib.lib().d3_cross_attention_small(q.data_ptr(), q.stride(2), kc.data_ptr(), vc.data_ptr(), B, H * W, L,
+                                                   C_, out.data_ptr(), C_, _dt(q), _stream()))
+    return out
+
+
+def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act_in: int = 0,
+                 act_out: int = 0) -> torch.Tensor:
+    """fp32 [n, K] x fp32 [rows, K]^T (+ bias) -> [n, rows]; act 0 = identity, 1 = SiLU."""
+    n, K = x.shape
+    rows = w.shape[0]
+    if w.shape[1] != K or x.dtype != torch.float32 or w.dtype != torch.float32 or not (x.is_contiguous() and w.is_contiguous()):
+        raise ValueError("linear_small: contiguous fp32 [n, K] and [rows, K] expected")
+    out = torch.empty((n, rows), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().d3_linear_small(x.data_ptr(), n, K, w.data_ptr(), _ptr(bias), rows, act_in, act_out,
+                                          out.data_ptr(), rows, _stream()))
+    return out
+
+
+def timestep_sincos(t: torch.Tensor, dim: int, flip_sin_to_cos: bool = True, freq_shift: float = 0.0) -> torch.Tensor:
+    out = torch.empty((t.numel(), dim), dtype=torch.float32, device=t.device)
+    _lib.check(_lib.lib().d3_timestep_sincos(t.data_ptr(), t.numel(), dim, int(flip_sin_to_cos), freq_shift,
+                                             out.data_ptr(), _stream()))
+    return out
+
+
+def nchw_to_nhwc16(x: torch.Tensor, out: torch.Tensor, c_off: int = 0) -> torch.Tensor:
+    """fp32 NCHW [B, C, H, W] -> channels [c_off, c_off + C) of the 16-bit NHWC tensor ``out``."""
+    x = _f32c(x, "x")
+    B, C_, H, W = x.shape
+    _check_nhwc(out, "out")
+    _lib.check(_lib.lib().d3_nchw_to_nhwc16(x.data_ptr(), B, C_, H, W, out.data_ptr(), out.stride(2), c_off, _dt(out),
+                                            _stream()))
+    return out
+
+
+def nhwc16_to_nchw(x: torch.Tensor, C_: int, c_off: int = 0) -> torch.Tensor:
+    _check_nhwc(x, "x")
+    B, H, W, _ = x.shape
+    out = torch.empty((B, C_, H, W), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().d3_nhwc16_to_nchw(x.data_ptr(), x.stride(2), c_off, B, C_, H, W, out.data_ptr(), _dt(x),
+                                            _stream()))
+    return out
+
+
+def resize_nearest(x: torch.Tensor, Ho: int, Wo: int, Hbuf: Optional[int] = None, Wbuf: Optional[int] = None):
+    """F.interpolate(size=(Ho, Wo), mode="nearest") into the top-left window of a zero-filled [B, Hbuf, Wbuf, C] buffer."""
+    _check_nhwc(x, "x")
+    B, H, W, C_ = x.shape
+    Hbuf, Wbuf = Hbuf or Ho, Wbuf or Wo
+    out = torch.empty((B, Hbuf, Wbuf, C_), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().d3_resize_nearest_nhwc16(x.data_ptr(), B, H, W, C_, x.stride(2), out.data_ptr(), Ho, Wo, Hbuf,
+                                                   Wbuf, C_, _stream()))
     return out
 
 

@@ -91,6 +91,11 @@ typedef struct d3_conv_params {
                           SMs, so the K loop is split across CTAs and a second kernel sums the partials); size from
                           d3_conv2d_workspace_bytes(); NULL = never split                                           */
   int64_t workspace_bytes;
+  int32_t Cout_valid;  /* 0 = Cout.  Otherwise the number of channels that exist in `out` / `residual` (a multiple of 64): the weight / bias rows [Cout_valid, Cout) are zero padding up to the
+                          128-channel MMA tile (the 320-channel layers of the latent UNet run with Cout = 384) and are
+                          clipped by the TMA store.  No statistics, no split-K in this mode.                          */
+  int32_t asym_pad;    /* stride-2 3x3 only: 1 = input padded by (0,1,0,1) instead of 1 on every side - Downsample2D
+                          with padding=0 of the VAE encoder (F.pad(x, (0,1,0,1)) + conv stride 2)                     */
 } d3_conv_params;
 
 /* bytes of split-K scratch this call would like (0 when it runs unsplit) */
@@ -324,6 +329,50 @@ int d3_frame_to_input(const uint8_t* frames, int B, int Hs, int Ws, int Cimg, in
 int d3_depth_to_input(const float* depth, int B, int Hs, int Ws, int H, int W, int pad_top, int pad_left, int Hp,
                       int Wp, float fxb, float bound, float gamma, float t, float s, float* raw_disp, float* mask,
                       float* norm_padded, void* stream);
+
+/* ==== latent family: diffusers UNet2DConditionModel in the SD-2.1 configuration
+ * (/root/reference/train.py:743-772, called at core/custom_pipelines.py:386) and AutoencoderKL (train.py:830-833, used at
+ * custom_pipelines.py:35-59, 255-272).  Convolutions and every Linear layer run on d3_conv2d_igemm; the entry points below
+ * are the remaining ops.  16-bit NHWC activations / [tokens][C] rows with explicit pitches, as above. ================== */
+
+/* GroupNorm for any group width (aten::native_group_norm of ResnetBlock2D.norm1/2, Transformer2DModel.norm,
+ * conv_norm_out): pass 1 accumulates per-channel sum / sum of squares of cat(x1, x2) into chan_stats fp64 [B][C1+C2][2]
+ * (zero on entry); pass 2 normalises (+ SiLU) into one dense tensor. */
+int d3_gn_stats(const void* x1, int C1, int pitch1, const void* x2, int C2, int pitch2, int B, int HW,
+                double* chan_stats, int dtype, void* stream);
+int d3_gn_apply(const void* x1, int C1, int pitch1, const void* x2, int C2, int pitch2, const double* chan_stats,
+                const float* gamma, const float* beta, int B, int HW, int groups, float eps, int apply_silu, void* out,
+                int out_pitch, int dtype, void* stream);
+/* aten::native_layer_norm over the last dimension of M rows of C (<= 1280) channels (BasicTransformerBlock.norm1-3). */
+int d3_layernorm(const void* x, int x_pitch, const float* gamma, const float* beta, int64_t M, int C, float eps,
+                 void* out, int out_pitch, int dtype, void* stream);
+/* diffusers GEGLU after its projection: out[m][d] = x[m][d] * gelu(x[m][D + d]), exact (erf) GELU. */
+int d3_geglu(const void* x, int x_pitch, int64_t M, int D, void* out, int out_pitch, int dtype, void* stream);
+/* softmax(q k^T / sqrt(64)) v, head_dim 64 (diffusers Attention of attn1): q / k / v rows of B*N tokens with their own
+ * pitches (channel slices of a fused QKV tensor), head h at channels [64h, 64h + 64); out [B*N][out_pitch]. */
+int d3_attention_hd64(const void* q, int q_pitch, const void* k, int k_pitch, const void* v, int v_pitch, int B, int N,
+                      int heads, void* out, int out_pitch, int dtype, void* stream);
+/* attention of N query tokens per sample against L <= 8 context tokens whose keys / values kc, vc fp32 [B][L][C] were
+ * projected beforehand (attn2 against the [B, 2, 1024] empty-prompt embedding, custom_pipelines.py:299-304, 386);
+ * C = 64 * heads. */
+int d3_cross_attention_small(const void* q, int q_pitch, const float* kc, const float* vc, int B, int N, int L, int C,
+                             void* out, int out_pitch, int dtype, void* stream);
+/* out[n][r] = act_out(bias[r] + sum_k w[r][k] * act_in(x[n][k])), fp32, act 0 = identity / 1 = SiLU: the time-embedding
+ * MLP, all time_emb_proj layers stacked, the context key / value projections.  bias may be NULL; K % 4 == 0. */
+int d3_linear_small(const float* x, int n_rows, int K, const float* w, const float* bias, int rows, int act_in,
+                    int act_out, float* out, int out_stride, void* stream);
+/* diffusers Timesteps(dim, flip_sin_to_cos, downscale_freq_shift): t fp32 [nt] -> out fp32 [nt][dim]. */
+int d3_timestep_sincos(const float* t, int nt, int dim, int flip_sin_to_cos, float freq_shift, float* out, void* stream);
+/* layout glue: fp32 NCHW [B,C,H,W] <-> channels [c_off, c_off + C) of a 16-bit NHWC tensor with pixel pitch `pitch`. */
+int d3_nchw_to_nhwc16(const float* x, int B, int C, int H, int W, void* out, int out_pitch, int c_off, int dtype,
+                      void* stream);
+int d3_nhwc16_to_nchw(const void* x, int pitch, int c_off, int B, int C, int H, int W, float* out, int dtype,
+                      void* stream);
+/* F.interpolate(size=(Ho, Wo), mode="nearest") of a 16-bit NHWC tensor into the top-left Ho x Wo window of a
+ * [B, Hbuf, Wbuf, C] buffer; the rest of the buffer is zero-filled (Upsample2D with an explicit output size, and the
+ * even-sized zero-extended copy an odd feature map needs before a stride-2 conv). */
+int d3_resize_nearest_nhwc16(const void* in, int B, int H, int W, int C, int in_pitch, void* out, int Ho, int Wo,
+                             int Hbuf, int Wbuf, int out_pitch, void* stream);
 
 #ifdef __cplusplus
 }
