@@ -146,6 +146,9 @@ def _declare(lib: C.CDLL) -> None:
         "d3_nchw_to_nhwc16": (i32, [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
         "d3_nhwc16_to_nchw": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
         "d3_resize_nearest_nhwc16": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, i32, i32, vp]),
+        "d3_softmax_rows": (i32, [vp, i32, i32, i32, f32, i32, vp]),
+        "d3_transpose_pad16": (i32, [vp, i32, i32, i32, vp, i32, vp]),
+        "d3_conv1x1_nchw_small": (i32, [vp, i32, i32, i32, i64, vp, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here == header and library out of sync

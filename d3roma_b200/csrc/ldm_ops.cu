@@ -694,6 +694,127 @@ __global__ void __launch_bounds__(256) resize_nearest_kernel(const uint16_t* __r
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// VAE mid-block attention (one head of 512 channels) runs as two tcgen05 GEMMs per sample (S = Q K^T, O = P V on the
+// igemm kernel) with these two helpers in between.
+// softmax_rows: in place, P[r][c] = softmax_c(scale * S[r][c]) over the first n_cols columns of a [rows][pitch] 16-bit
+// matrix; the padding columns [n_cols, pitch) are written as zero (they are K columns of the second GEMM).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(uint16_t* __restrict__ s, int rows, int n_cols, int pitch,
+                                                           float scale_log2) {
+  pdl_prologue();
+  const int row = blockIdx.x;
+  if (row >= rows) return;
+  uint16_t* r = s + (size_t)row * pitch;
+  const int nvec = pitch >> 3;
+  __shared__ float s_red[8];
+  __shared__ float s_bcast;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float mx = -INFINITY;
+  for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(r + vi * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack2<DT>(w[k]);
+      if (vi * 8 + 2 * k < n_cols) mx = fmaxf(mx, f.x);
+      if (vi * 8 + 2 * k + 1 < n_cols) mx = fmaxf(mx, f.y);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = s_red[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, s_red[i]);
+    s_bcast = m;
+  }
+  __syncthreads();
+  mx = s_bcast;
+  const float nm = -mx * scale_log2;
+  float sum = 0.f;
+  for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(r + vi * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack2<DT>(w[k]);
+      if (vi * 8 + 2 * k < n_cols) sum += exp2f(fmaf(f.x, scale_log2, nm));
+      if (vi * 8 + 2 * k + 1 < n_cols) sum += exp2f(fmaf(f.y, scale_log2, nm));
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  __syncthreads();   // s_red is reused
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
+    s_bcast = 1.0f / t;
+  }
+  __syncthreads();
+  const float inv = s_bcast;
+  for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(r + vi * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack2<DT>(w[k]);
+      const float p0 = (vi * 8 + 2 * k < n_cols) ? exp2f(fmaf(f.x, scale_log2, nm)) * inv : 0.f;
+      const float p1 = (vi * 8 + 2 * k + 1 < n_cols) ? exp2f(fmaf(f.y, scale_log2, nm)) * inv : 0.f;
+      o[k] = pack2<DT>(p0, p1);
+    }
+    *reinterpret_cast<uint4*>(r + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// out[c][n] = in[n][c] for n < N, 0 for N <= n < Np   (V -> V^T as the K-major weight operand of O = P V)
+__global__ void __launch_bounds__(256) transpose_pad_kernel(const uint16_t* __restrict__ in, int N, int C, int pin,
+                                                            uint16_t* __restrict__ out, int Np) {
+  pdl_prologue();
+  __shared__ uint16_t tile[32][34];
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + i, c = c0 + tx;
+    tile[i][tx] = (n < N && c < C) ? in[(size_t)n * pin + c] : (uint16_t)0;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, n = n0 + tx;
+    if (c < C && n < Np) out[(size_t)c * Np + n] = tile[tx][i];
+  }
+}
+
+// 1x1 conv over fp32 NCHW with <= 8 channels on both sides (quant_conv 8 -> 8, post_quant_conv 4 -> 4 of AutoencoderKL)
+__global__ void __launch_bounds__(256) conv1x1_nchw_small_kernel(const float* __restrict__ x, int Cin, int Cout,
+                                                                 long long HW, long long total,
+                                                                 const float* __restrict__ w, const float* __restrict__ b,
+                                                                 float* __restrict__ out) {
+  pdl_prologue();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, hw = i - n * HW;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = c < Cin ? x[(n * Cin + c) * HW + hw] : 0.f;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      if (o < Cout) {
+        float acc = b ? b[o] : 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < Cin) acc = fmaf(w[o * Cin + c], v[c], acc);
+        out[(n * Cout + o) * HW + hw] = acc;
+      }
+    }
+  }
+}
+
 int grid_for(long long total, int threads) {
   long long blocks = (total + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 16;
@@ -885,6 +1006,41 @@ extern "C" int d3_resize_nearest_nhwc16(const void* in, int B, int H, int W, int
   D3_CHECK_CUDA(launch_pdl(resize_nearest_kernel, dim3(grid_for(total, 256)), dim3(256), 0,
                            static_cast<cudaStream_t>(stream), static_cast<const uint16_t*>(in), B, H, W, C, in_pitch,
                            static_cast<uint16_t*>(out), Ho, Wo, Hbuf, Wbuf, out_pitch));
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
+extern "C" int d3_softmax_rows(void* s, int rows, int n_cols, int pitch, float scale, int dtype, void* stream) {
+  D3_16BIT(dtype);
+  D3_REQUIRE(s && rows > 0 && n_cols > 0 && n_cols <= pitch && pitch % 8 == 0, "softmax_rows: bad arguments");
+  const float sl2 = scale * 1.4426950408889634f;
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == D3_DTYPE_F16)
+    D3_CHECK_CUDA(launch_pdl(softmax_rows_kernel<kF16>, dim3(rows), dim3(256), 0, st, static_cast<uint16_t*>(s), rows,
+                             n_cols, pitch, sl2));
+  else
+    D3_CHECK_CUDA(launch_pdl(softmax_rows_kernel<kBF16>, dim3(rows), dim3(256), 0, st, static_cast<uint16_t*>(s), rows,
+                             n_cols, pitch, sl2));
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
+extern "C" int d3_transpose_pad16(const void* in, int N, int C, int in_pitch, void* out, int Np, void* stream) {
+  D3_REQUIRE(in && out && N > 0 && C > 0 && Np >= N, "transpose_pad16: bad arguments");
+  dim3 grid(ceil_div(Np, 32), ceil_div(C, 32));
+  D3_CHECK_CUDA(launch_pdl(transpose_pad_kernel, grid, dim3(256), 0, static_cast<cudaStream_t>(stream),
+                           static_cast<const uint16_t*>(in), N, C, in_pitch, static_cast<uint16_t*>(out), Np));
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
+extern "C" int d3_conv1x1_nchw_small(const float* x, int B, int Cin, int Cout, int64_t HW, const float* w,
+                                     const float* bias, float* out, void* stream) {
+  D3_REQUIRE(x && w && out && Cin >= 1 && Cin <= 8 && Cout >= 1 && Cout <= 8 && B > 0 && HW > 0,
+             "conv1x1_nchw_small: channel counts must be in [1, 8]");
+  const long long total = (long long)B * HW;
+  D3_CHECK_CUDA(launch_pdl(conv1x1_nchw_small_kernel, dim3(grid_for(total, 256)), dim3(256), 0,
+                           static_cast<cudaStream_t>(stream), x, Cin, Cout, (long long)HW, total, w, bias, out));
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

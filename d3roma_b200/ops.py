@@ -422,6 +422,34 @@ def resize_nearest(x: torch.Tensor, Ho: int, Wo: int, Hbuf: Optional[int] = None
     return out
 
 
+def softmax_rows_(s: torch.Tensor, n_cols: int, scale: float) -> torch.Tensor:
+    """In-place softmax(scale * s) over the first ``n_cols`` columns of a 16-bit [rows, pitch] matrix (rest zeroed)."""
+    rows, pitch = s.shape
+    if not s.is_contiguous():
+        raise ValueError("softmax_rows_: contiguous [rows, pitch] expected")
+    _lib.check(_lib.lib().d3_softmax_rows(s.data_ptr(), rows, n_cols, pitch, scale, _dt(s), _stream()))
+    return s
+
+
+def transpose_pad(x: torch.Tensor, Np: int) -> torch.Tensor:
+    """16-bit [N, C] (row pitch ``x.stride(0)``) -> [C, Np] with zero columns N..Np-1."""
+    N, C_ = x.shape
+    out = torch.empty((C_, Np), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().d3_transpose_pad16(x.data_ptr(), N, C_, x.stride(0), out.data_ptr(), Np, _stream()))
+    return out
+
+
+def conv1x1_nchw_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """fp32 NCHW 1x1 conv with <= 8 channels on both sides; ``w`` fp32 [Cout, Cin]."""
+    x = _f32c(x, "x")
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().d3_conv1x1_nchw_small(x.data_ptr(), B, Cin, Cout, H * W, w.data_ptr(), _ptr(bias),
+                                                out.data_ptr(), _stream()))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # scheduler / guidance / pre-post wrappers (fp32 NCHW tensors)
 # ------------------------------------------------------------------------------------------------

@@ -373,6 +373,16 @@ int d3_nhwc16_to_nchw(const void* x, int pitch, int c_off, int B, int C, int H, 
  * even-sized zero-extended copy an odd feature map needs before a stride-2 conv). */
 int d3_resize_nearest_nhwc16(const void* in, int B, int H, int W, int C, int in_pitch, void* out, int Ho, int Wo,
                              int Hbuf, int Wbuf, int out_pitch, void* stream);
+/* VAE mid-block attention (diffusers Attention with one 512-wide head, AutoencoderKL mid_block.attentions.0) runs as two
+ * d3_conv2d_igemm GEMMs per sample - S = Q K^T with K as the "weight" operand, O = P V with V^T - around these helpers:
+ * in-place row softmax of scale * S over the first n_cols columns of a 16-bit [rows][pitch] matrix (padding columns
+ * are zeroed), and V [N][C] -> V^T [C][Np] zero-padded to the K-block multiple. */
+int d3_softmax_rows(void* s, int rows, int n_cols, int pitch, float scale, int dtype, void* stream);
+int d3_transpose_pad16(const void* in, int N, int C, int in_pitch, void* out, int Np, void* stream);
+/* quant_conv (8 -> 8) / post_quant_conv (4 -> 4) of AutoencoderKL (custom_pipelines.py:54, 268): 1x1 conv over fp32 NCHW
+ * with at most 8 channels on either side; w fp32 [Cout][Cin]. */
+int d3_conv1x1_nchw_small(const float* x, int B, int Cin, int Cout, int64_t HW, const float* w, const float* bias,
+                          float* out, void* stream);
 
 #ifdef __cplusplus
 }
