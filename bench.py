@@ -15,6 +15,7 @@ Other BASELINE configs (parity-test cases made measurable; `config.workload` nam
   c3  rgb+raw variant with stereo-geometry guidance, 8 pairs per GPU (configs[2]: 64 pairs on 8 GPUs)
   c4  540x960 (UNet at 544x960), DDPM 100 steps, fp32 reference-precision path, 1 pair per GPU (configs[3])
   c5  32 pairs per GPU, DDIM 10, disparity maps AND the [n,11] metric rows all-gathered (configs[4]: 256 pairs on 8 GPUs)
+  ldm the latent family: rgb+raw, SD-2.1 UNet2DConditionModel + SD VAE, DDPM 10 of 1000 steps, 16 pairs per GPU
 
 JSON keys beyond the base contract:
   roofline            dominant kernel (tcgen05 implicit-GEMM conv, 3x3 128->128 @384x640, 31 % of the FLOPs) timed alone
@@ -465,6 +466,193 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------- latent family (f1)
+LDM_SCHED = dict(num_train_timesteps=1000, beta_schedule="scaled_linear", beta_start=0.00085, beta_end=0.012,
+                 prediction_type="v_prediction", clip_sample=False, thresholding=False)
+LDM_PAIRS, LDM_STEPS, LDM_PLOTS = 16, 10, 5
+
+
+def ldm_eager_baseline(dtype: str, Bp: int, hw, n_steps: int, plots: int):
+    """The oracle's torch.nn restatements of the SD-2.1 UNet and the SD VAE run by eager PyTorch (cuDNN / cuBLAS / SDPA
+    math, same 16-bit dtype, channels_last) on the SAME GPU, outside the timed region: one UNet forward, one encoder
+    pass, one decoder pass at the workload's batch, combined with the loop's call counts."""
+    from oracle.ldm_ref import AutoencoderKL, UNet2DConditionModel
+    tdt = torch.float16 if dtype == "fp16" else torch.bfloat16
+    h, w = hw[0] // 8, hw[1] // 8
+    with torch.device("cuda"):
+        unet = UNet2DConditionModel(in_channels=12).to(tdt).to(memory_format=torch.channels_last).eval()
+        vae = AutoencoderKL().to(tdt).to(memory_format=torch.channels_last).eval()
+
+    def t_of(fn, reps=2):
+        with torch.no_grad():
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    x = torch.randn(Bp, 12, h, w, device="cuda", dtype=tdt).contiguous(memory_format=torch.channels_last)
+    ctx = torch.randn(Bp, 2, 1024, device="cuda", dtype=tdt)
+    img = torch.randn(2 * Bp, 3, hw[0], hw[1], device="cuda", dtype=tdt).contiguous(memory_format=torch.channels_last)
+    z = torch.randn(Bp, 4, h, w, device="cuda", dtype=tdt)
+    ms_u = t_of(lambda: unet(x, 500, ctx))
+    ms_e = t_of(lambda: vae.quant_conv(vae.encoder(img)))
+    ms_d = t_of(lambda: vae.decoder(vae.post_quant_conv(z)))
+    ms = n_steps * ms_u + ms_e + plots * ms_d
+    del unet, vae
+    torch.cuda.empty_cache()
+    return {"value": Bp / (ms * 1e-3), "unit": "maps/s", "ms_unet_forward": ms_u, "ms_vae_encode_2B": ms_e,
+            "ms_vae_decode_B": ms_d, "kind": "eager PyTorch (cuDNN/cuBLAS) on the same GPU, oracle torch.nn modules, "
+            f"{dtype}, channels_last; loop time composed as {n_steps} UNet + 1 encode (rgb+raw = 2B images) + "
+            f"{plots} decode passes", "data": "synthetic"}
+
+
+def run_ldm_arm(args):
+    """--config ldm: the reference's latent family (GuidedLatentDiffusionPipeline, custom_pipelines.py:208-460) in the
+    shape of conf/task/eval_ldm_mixed_rgb+raw.yaml - rgb+raw conditioning, SD-2.1 UNet2DConditionModel (12-channel
+    conv_in), SD AutoencoderKL, DDPM sampler with 10 inference steps of 1000 (v-prediction, scaled-linear betas), 5
+    decoded intermediate images - at the BASELINE metric's 360x640 with 16 pairs per GPU."""
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import d3roma_b200 as d
+    from d3roma_b200 import _lib
+    from d3roma_b200.autoencoder_kl import AutoencoderKL
+    from d3roma_b200.unet_condition import UNet2DConditionModel
+    from d3roma_b200.weights import random_init_cond_unet_state_dict, random_init_vae_state_dict
+    dtype = args.dtype
+    Bp, (H0, W0), n_steps, plots = LDM_PAIRS, (360, 640), LDM_STEPS, LDM_PLOTS
+    unet = UNet2DConditionModel(in_channels=12, compute_dtype=dtype).to(dev)
+    unet.load_state_dict(random_init_cond_unet_state_dict(12, seed=0, device=dev))
+    vae = AutoencoderKL(compute_dtype=dtype).to(dev)
+    vae.load_state_dict(random_init_vae_state_dict(seed=1, device=dev))
+    pipe = d.GuidedLatentDiffusionPipeline(unet, vae, None, None, d.MyDDPMScheduler.from_config(LDM_SCHED),
+                                           d.FlowGuidance(flow_guidance_weight=0.0, flow_guidance_mode="gradient"))
+    normalizer = d.Normalizer(ssi=False, mode="average", num_chs=1, ch_bounds=[128.], ch_gammas=[1.], t=0.5, s=2.0)
+    cam = d.SIM_CAMERA
+    ete = torch.randn(1, 2, 1024, generator=torch.Generator().manual_seed(3)).to(dev)   # empty-prompt embedding stand-in
+    left_h, _, depth_h = synth_inputs(Bp, first_index=rank * Bp, h=H0, w=W0)
+    left_h, depth_h = left_h.pin_memory(), depth_h.pin_memory()
+    gens = [torch.Generator().manual_seed(10_000 + rank * Bp + i) for i in range(Bp)]
+    gather_buf = torch.empty((world * Bp, 1, H0, W0), device=dev) if world > 1 else None
+
+    def raw_of(depth_dev):
+        return normalizer.normalize(d.prepost.depth_to_disp(depth_dev, cam.fxb).view(Bp, H0, W0))[0].view(Bp, 1, H0, W0)
+
+    rgb_d, raw_d = left_h.to(dev), raw_of(depth_h.to(dev))
+
+    def loop(rgb, raw):
+        out = pipe(rgb, None, None, raw, None, None, empty_text_embed=ete, num_inference_steps=n_steps,
+                   num_intermediate_images=plots, cond_channels="rgb+raw", denorm=normalizer.denormalize, generator=gens)
+        disp = normalizer.denormalize(out.images)
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, disp)
+        return disp
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warm = max(3, args.warmup)
+    for _ in range(warm):
+        loop(rgb_d, raw_d)
+    sync()
+    lib = _lib.lib()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    lib.d3_reset_launch_count()
+    g0 = unet.graph_kernel_launches
+    e0.record()
+    for _ in range(args.steps):
+        loop(rgb_d, raw_d)
+    e1.record()
+    sync()
+    clocks = sampler.stop() if rank == 0 else None
+    eager_launches = int(lib.d3_launch_count()) + (unet.graph_kernel_launches - g0)
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item())
+    value = world * Bp * args.steps / sec
+
+    def e2e_step():
+        rgb = left_h.to(dev, non_blocking=True)
+        return loop(rgb, raw_of(depth_h.to(dev, non_blocking=True))).to("cpu")
+
+    for _ in range(2):
+        e2e_step()
+    sync()
+    n_e2e = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        out_h = e2e_step()
+    sync()
+    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * Bp * n_e2e / float(te.item())
+
+    if rank == 0:
+        # component times (CUDA events, after the timed region): one UNet forward (graph replay), encode, decode
+        def t_of(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        x = torch.randn(Bp, 12, H0 // 8, W0 // 8, device=dev)
+        ctx = ete.repeat(Bp, 1, 1)
+        img2 = torch.cat([rgb_d, raw_d.repeat(1, 3, 1, 1)])
+        z = torch.randn(Bp, 4, H0 // 8, W0 // 8, device=dev) * 0.18215
+        ms_u = t_of(lambda: unet(x, 500, ctx))
+        ms_e = t_of(lambda: vae.encode_latent(img2, 0.18215))
+        ms_d = t_of(lambda: vae.decode_mean(z, 0.18215))
+        g = next(iter(unet._graphs.values()), None)
+        line = {
+            "metric": "disparity maps/sec at 360x640, 10 DDPM steps (latent family: SD-2.1 UNet + VAE)",
+            "value": value, "unit": "maps/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": dtype, "data": "synthetic",
+            "config": {"workload": "latent family (SURVEY 8 f1; reference conf/task/eval_ldm_mixed_rgb+raw.yaml loop shape): "
+                                   f"rgb+raw variant, batch {Bp} per GPU at {H0}x{W0} (latents {H0 // 8}x{W0 // 8}), DDPM "
+                                   f"{n_steps} of 1000 steps, v-prediction, {plots} decoded intermediate images, random-init "
+                                   "UNet2DConditionModel (SD-2.1 layout, 12-channel conv_in, 865.9 M params) + AutoencoderKL "
+                                   f"(SD VAE, 83.7 M params), {dtype} operands",
+                       "config": "ldm", "pairs_per_gpu": Bp, "global_pairs": Bp * world, "sampler_steps": n_steps,
+                       "parallelism": f"batch-shard x{world} (replicated weights, output all-gather)",
+                       "l2": "weights alone (1.9 GB in fp16) exceed the 126 MB L2; no explicit flush"},
+            "ms_per_unet_step": ms_u, "ms_vae_encode_2B_images": ms_e, "ms_vae_decode_B_images": ms_d,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "maps/s", "h2d_bytes_per_step": (left_h.numel() + depth_h.numel()) * 4
+                    + Bp * 4 * (H0 // 8) * (W0 // 8) * 4, "d2h_bytes_per_step": out_h.numel() * 4, "steps": n_e2e,
+                    "api": "d3roma_b200.GuidedLatentDiffusionPipeline.__call__ (host buffers in, host maps out)"},
+            "gpu_launches": eager_launches,
+        }
+        if not args.no_gpu_baseline:
+            line["gpu_eager_baseline"] = ldm_eager_baseline(dtype, Bp, (H0, W0), n_steps, plots)
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 _JSON_OUT = None
 
 
@@ -486,13 +674,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="d3roma_b200", choices=["d3roma_b200", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS) + ["ldm"])
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.config == "ldm":
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the d3roma_b200 path has no CPU fallback)")
+        run_ldm_arm(args)
     else:
         run_gpu_arm(args)
 

@@ -2,13 +2,16 @@
 (``/root/reference/core/custom_pipelines.py:208-460``) with the same constructor, ``__call__`` signature, conditioning
 keys, RNG consumption and output semantics, over this package's scheduler kernels.
 
-Scope (honest labelling): the three NETWORKS of the latent family — the SD-2.1
-``UNet2DConditionModel``, the ``AutoencoderKL`` VAE and the CLIP text encoder — are third-party models that this
-package does NOT implement; ``unet`` / ``vae`` / ``tokenizer`` / ``text_encoder`` are whatever torch modules the caller
-loads (exactly the objects the reference passes, ``train.py:743-772, 821-833``).  What is built here is the part of the
-path that is the reference's own code: the loop, its latent encode / decode conventions (``encode_rgb`` :47-59,
-``encode_disp`` :35-45, ``__decode_depth`` :255-272), and the scheduler steps (``d3_sched_ddim_step`` /
-``d3_sched_ddpm_step``) with the guidance hook wiring of :389-399.
+Networks: ``unet`` is ``d3roma_b200.UNet2DConditionModel`` and ``vae`` ``d3roma_b200.AutoencoderKL``
+(the SD-2.1 UNet / SD VAE architectures on the sm_100a kernels, ``unet_condition.py`` / ``autoencoder_kl.py``); any object
+with the same call surface works too (the loop only uses ``unet(x, t, ctx).sample`` and ``vae.encoder / quant_conv /
+post_quant_conv / decoder``, exactly what the reference touches, ``train.py:743-772, 821-833``).  The CLIP text encoder is
+NOT implemented: its only use on this path is the embedding of the empty prompt, a constant ``[1, 2, 1024]`` tensor that
+callers pass as ``empty_text_embed`` (the argument the reference provides for exactly that, custom_pipelines.py:229,
+299-301); when it is omitted, ``tokenizer`` / ``text_encoder`` must be the caller's own transformers objects.  This file is the reference's own part of
+the path: the loop, its latent encode / decode conventions (``encode_rgb`` :47-59, ``encode_disp`` :35-45,
+``__decode_depth`` :255-272), and the scheduler steps (``d3_sched_ddim_step`` / ``d3_sched_ddpm_step``) with the guidance
+hook wiring of :389-399.
 
 Differences from the reference, none of which change a returned value:
   * ``encode_disp(sim_disp)`` is evaluated once instead of at every step of the ``"rgb+raw"`` variant (:356 re-encodes
@@ -114,9 +117,26 @@ class GuidedLatentDiffusionPipeline:
         return self.text_encoder(tok.input_ids.to(self.text_encoder.device))[0]
 
     def _decode_depth(self, depth_latent: torch.Tensor, depth_latent_scale_factor: float = LATENT_SCALE) -> torch.Tensor:
-        """custom_pipelines.py:255-272: undo the latent scale, decode, mean over the output channels."""
+        """custom_pipelines.py:255-272: undo the latent scale, decode, mean over the output channels.  With this
+        package's ``AutoencoderKL`` the three steps are one pass (``decode_mean``: scale and channel mean folded into
+        the 1x1 / output convs)."""
+        if hasattr(self.vae, "decode_mean"):
+            return self.vae.decode_mean(depth_latent, depth_latent_scale_factor)
         z = self.vae.post_quant_conv(depth_latent / depth_latent_scale_factor)
         return self.vae.decoder(z).mean(dim=1, keepdim=True)
+
+    def _encode_all(self, rgb, left, right, sim):
+        """Latents of every conditioning image the call was given (custom_pipelines.py:312-325).  With this package's
+        ``AutoencoderKL`` the images go through the encoder as ONE batch (the reference runs up to four encoder passes)
+        and the mean / scale selection is folded into the quant conv (``encode_latent``)."""
+        if not hasattr(self.vae, "encode_latent"):
+            return (None if rgb is None else encode_rgb(self.vae, rgb), None if left is None else encode_rgb(self.vae, left),
+                    None if right is None else encode_rgb(self.vae, right), None if sim is None else encode_disp(self.vae, sim))
+        imgs = [rgb, left, right, None if sim is None else sim.repeat(1, 3, 1, 1)]
+        present = [t for t in imgs if t is not None]
+        lat = self.vae.encode_latent(torch.cat(present, dim=0).float().contiguous(), LATENT_SCALE)
+        parts = iter(torch.split(lat, [t.shape[0] for t in present], dim=0))
+        return tuple(None if t is None else next(parts).contiguous() for t in imgs)
 
     @torch.no_grad()
     def __call__(self, rgb_images, left_images=None, right_images=None, sim_disp=None, raw_depth=None, raw_mask=None,
@@ -139,10 +159,7 @@ class GuidedLatentDiffusionPipeline:
         image = image.to(dev)
         up = lambda t: None if t is None else t.to(dev)  # noqa: E731
         rgb_images, left_images, right_images, sim_disp = up(rgb_images), up(left_images), up(right_images), up(sim_disp)
-        cond_images = None if rgb_images is None else encode_rgb(self.vae, rgb_images)
-        left_lat = None if left_images is None else encode_rgb(self.vae, left_images)
-        right_lat = None if right_images is None else encode_rgb(self.vae, right_images)
-        sim_lat = None if sim_disp is None else encode_disp(self.vae, sim_disp)
+        cond_images, left_lat, right_lat, sim_lat = self._encode_all(rgb_images, left_images, right_images, sim_disp)
 
         orders = {"rgb": ("rgb",), "rgb+raw": ("rgb", "raw"), "left+right": ("left", "right"),
                   "left+right+raw": ("left", "right", "raw"), "rgb+left+right": ("rgb", "left", "right"),

@@ -99,7 +99,11 @@ class UNet2DConditionModel:
         self.dtype = torch.float32
         self._w: Dict[str, torch.Tensor] = {}
         self._loaded = False
-        self._arena: Optional[_ChanArena] = None
+        self._arena: Optional[_ChanArena] = None          # arena of the forward in flight
+        self._eager_arena: Optional[_ChanArena] = None
+        self._graphs: Dict[tuple, dict] = {}
+        self.use_cuda_graph = True
+        self.graph_kernel_launches = 0   # kernels executed through CUDA-graph replays (launch accounting)
         self._ctx_cache = None
         self._cin_pad = (in_channels + 63) // 64 * 64
         if out_channels > 64:
@@ -223,6 +227,7 @@ class UNet2DConditionModel:
                 raise KeyError(f"unexpected keys in state_dict: {sorted(extra)[:5]} ...")
         self._loaded = True
         self._ctx_cache = None
+        self.reset_graphs()    # captured graphs hold raw pointers into the previous weight tensors
         return self
 
     def to(self, device=None, dtype=None):
@@ -234,7 +239,8 @@ class UNet2DConditionModel:
                 device = torch.device("cuda", torch.cuda.current_device())
             if self._loaded and device != self.device:
                 self._w = {k: v.to(device) for k, v in self._w.items()}
-                self._arena, self._ctx_cache = None, None
+                self._arena = self._eager_arena = self._ctx_cache = None
+                self.reset_graphs()
             self.device = device
         return self
 
@@ -325,38 +331,95 @@ class UNet2DConditionModel:
         return out
 
     # ------------------------------------------------------------------ forward
-    @torch.no_grad()
-    def forward(self, sample: torch.Tensor, timestep, encoder_hidden_states: torch.Tensor, return_dict: bool = True):
+    def _arena_need(self, B: int) -> int:
+        boc = self.config.block_out_channels
+        return B * 2 * (sum(ch + cs + co for _, ch, cs, co in self._resnets())
+                        + sum(C for _, C, _ in self._transformers()) + boc[0])
+
+    def _check_inputs(self, sample, timestep, ctx):
         if not self._loaded:
             raise RuntimeError("load_state_dict() first")
         if not ((sample.is_cuda or _TEST_DEVICE is not None) and sample.dtype == torch.float32 and sample.dim() == 4):
             raise ValueError("sample must be an fp32 CUDA NCHW tensor (no CPU fallback)")
-        B, Cin, H, Wd = sample.shape
+        B, Cin, _, _ = sample.shape
         if Cin != self.in_channels:
             raise ValueError(f"expected {self.in_channels} input channels, got {Cin}")
+        t = torch.as_tensor(timestep).to(device=sample.device, dtype=torch.float32).reshape(-1)
+        if t.numel() not in (1, B):
+            raise ValueError("timestep must be a scalar or have one entry per sample")
+        if not ((ctx.is_cuda or _TEST_DEVICE is not None) and ctx.dim() == 3 and ctx.shape[0] == B
+                and ctx.shape[2] == self.config.cross_attention_dim):
+            raise ValueError(f"encoder_hidden_states must be a CUDA [B, L, {self.config.cross_attention_dim}] tensor")
+        return t, (ctx if ctx.dtype == torch.float32 else ctx.float())
+
+    @torch.no_grad()
+    def forward(self, sample: torch.Tensor, timestep, encoder_hidden_states: torch.Tensor, return_dict: bool = True):
+        t, ctx = self._check_inputs(sample, timestep, encoder_hidden_states)
+        if self.use_cuda_graph and _TEST_DEVICE is None:
+            out = self._forward_graphed(sample, t, ctx)
+        else:
+            B, dev = sample.shape[0], sample.device
+            need = self._arena_need(B)
+            if self._eager_arena is None or self._eager_arena.buf.numel() < need or self._eager_arena.buf.device != dev:
+                self._eager_arena = _ChanArena(dev, need)
+            out = self._run(sample, t, self._context_kv(ctx), self._eager_arena)
+        return UNet2DConditionOutput(sample=out) if return_dict else (out,)
+
+    __call__ = forward
+
+    def reset_graphs(self):
+        self._graphs = {}
+
+    def _forward_graphed(self, sample, t, ctx):
+        """One CUDA-graph replay per forward (the ~410 launches of the SD-2.1 layout are launch-bound at latent sizes).
+        A graph is captured once per (input shape, timestep count, context shape, device) over static buffers it owns -
+        input, timestep, context keys / values, GroupNorm arena, output; the context projections are refreshed outside
+        the graph only when the context's content changes."""
+        key = (tuple(sample.shape), t.numel(), tuple(ctx.shape), sample.device.index)
+        g = self._graphs.get(key)
+        if g is None:
+            g = {"x": sample.clone(), "t": t.clone(), "arena": _ChanArena(sample.device, self._arena_need(sample.shape[0])),
+                 "kv": {k: (a.clone(), b.clone()) for k, (a, b) in self._context_kv(ctx).items()},
+                 "ctx_key": self._ctx_cache[0]}
+            side = torch.cuda.Stream(device=sample.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):   # warm-up: kernel attributes, allocator pools
+                self._run(g["x"], g["t"], g["kv"], g["arena"])
+            torch.cuda.current_stream().wait_stream(side)
+            from . import _lib
+            n0 = int(_lib.lib().d3_launch_count())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g["out"] = self._run(g["x"], g["t"], g["kv"], g["arena"])
+            g["graph"], g["n_kernels"] = graph, int(_lib.lib().d3_launch_count()) - n0
+            self._graphs[key] = g
+        else:
+            g["x"].copy_(sample)
+            g["t"].copy_(t)
+            kv = self._context_kv(ctx)
+            if self._ctx_cache[0] != g["ctx_key"]:
+                for k, (a, b) in kv.items():
+                    g["kv"][k][0].copy_(a)
+                    g["kv"][k][1].copy_(b)
+                g["ctx_key"] = self._ctx_cache[0]
+        g["graph"].replay()
+        self.graph_kernel_launches += g["n_kernels"]
+        return g["out"].clone()
+
+    def _run(self, sample, t, kv, arena):
+        """The kernel sequence of one forward (capturable: no host synchronisation, no data-dependent control flow)."""
+        B, Cin, H, Wd = sample.shape
         cfg = self.config
         boc, L, heads = cfg.block_out_channels, cfg.layers_per_block, cfg.attention_head_dim
         n = len(boc)
         dev, W = sample.device, self._w
-        # GroupNorm statistics arena of this forward
-        need = B * 2 * (sum(ch + cs + co for _, ch, cs, co in self._resnets()) + sum(C for _, C, _ in self._transformers()) + boc[0])
-        if self._arena is None or self._arena.buf.numel() < need or self._arena.buf.device != dev:
-            self._arena = _ChanArena(dev, need)
-        self._arena.reset()
+        self._arena = arena
+        arena.reset()
         # time embedding -> SiLU(emb) -> every time_emb_proj (+ conv1.bias) in one launch
-        t = torch.as_tensor(timestep)
-        t = t.to(device=dev, dtype=torch.float32).reshape(-1)
-        if t.numel() not in (1, B):
-            raise ValueError("timestep must be a scalar or have one entry per sample")
         emb = ops.timestep_sincos(t, boc[0])
         emb = ops.linear_small(emb, W["time.w1"], W["time.b1"], act_out=1)
         emb = ops.linear_small(emb, W["time.w2"], W["time.b2"], act_out=1)     # SiLU(emb): what every resnet consumes
         temb_all = ops.linear_small(emb, W["temb.w"], W["temb.b"])
-        ctx = encoder_hidden_states
-        if not ((ctx.is_cuda or _TEST_DEVICE is not None) and ctx.dim() == 3 and ctx.shape[0] == B
-                and ctx.shape[2] == cfg.cross_attention_dim):
-            raise ValueError(f"encoder_hidden_states must be a CUDA [B, L, {cfg.cross_attention_dim}] tensor")
-        kv = self._context_kv(ctx if ctx.dtype == torch.float32 else ctx.float())
         # input
         x = torch.zeros((B, H, Wd, self._cin_pad), dtype=self._adt, device=dev)
         ops.nchw_to_nhwc16(sample, x)
@@ -389,7 +452,4 @@ class UNet2DConditionModel:
                 h = self._upsample(f"up_blocks.{i}.upsamplers.0.conv", h, rev[i], size)
         a = self._gn(h, W["out.g"], W["out.b"])
         o = ops.conv2d_igemm(a, W["out.w"], W["out.bias"], ksize=3, cout_valid=64)
-        out = ops.nhwc16_to_nchw(o, self.out_channels)
-        return UNet2DConditionOutput(sample=out) if return_dict else (out,)
-
-    __call__ = forward
+        return ops.nhwc16_to_nchw(o, self.out_channels)

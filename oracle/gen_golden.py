@@ -446,6 +446,38 @@ def gen_latent(store):
         store[f"{tag}/intermediate"] = _np(out.images_pred_orig)
 
 
+def gen_latent_nets(store):
+    """The reference's GuidedLatentDiffusionPipeline driven with the ORACLE restatements of its two networks
+    (oracle/ldm_ref.py, reduced widths, seeded default init): the end-to-end target of the CUDA UNet2DConditionModel +
+    AutoencoderKL inside d3roma_b200.GuidedLatentDiffusionPipeline (tests/test_latent_nets_gpu.py)."""
+    import contextlib
+    import io
+    from core.custom_pipelines import GuidedLatentDiffusionPipeline
+    from oracle.ldm_ref import make_cond_unet, make_vae
+    g = torch.Generator().manual_seed(77)
+    B, H, W = 2, 64, 96
+    rgb, left, right = (torch.rand(B, 3, H, W, generator=g) * 2 - 1 for _ in range(3))
+    sim = torch.rand(B, 1, H, W, generator=g) * 2 - 1
+    store["rgb"], store["left"], store["right"], store["sim"] = (_np(v) for v in (rgb, left, right, sim))
+    ete = torch.randn(1, 2, 64, generator=g)
+    store["empty_text_embed"] = _np(ete)
+    vae = make_vae(seed=11, block_out_channels=(128, 128, 128, 128))
+    cases = {
+        "ddim_rgbraw": ("rgb+raw", 12, MyDDIMScheduler.from_config(DDIM_CONFIGS["sl1000_epsilon"]), 6, 3),
+        "ddim_lrr": ("left+right+raw", 16, MyDDIMScheduler.from_config(DDIM_CONFIGS["lin1000_v_trailing"]), 4, 2),
+    }
+    for tag, (cc, cin, sch, n, plots) in cases.items():
+        unet = make_cond_unet(in_channels=cin, seed=5, block_out_channels=(64, 128, 128), attention_head_dim=(1, 2, 2),
+                              cross_attention_dim=64)
+        pipe = GuidedLatentDiffusionPipeline(unet, vae, None, None, sch,
+                                             FlowGuidance(flow_guidance_weight=0.0, flow_guidance_mode="gradient"))
+        with contextlib.redirect_stdout(io.StringIO()):
+            out = pipe(rgb, left, right, sim, None, None, empty_text_embed=ete, num_inference_steps=n,
+                       num_intermediate_images=plots, cond_channels=cc, generator=torch.Generator().manual_seed(9))
+        store[f"{tag}/images"] = _np(out.images)
+        store[f"{tag}/intermediate"] = _np(out.images_pred_orig)
+
+
 def gen_piecewise(store):
     """Normalizer(mode="piecewise") of the reference (utils_d3roma/utils.py:198-229, 275-293): 3 channels with bounds
     [64, 32, 32] (the class defaults), 2 channels with a gamma, and the 1-channel degenerate case."""
@@ -611,7 +643,7 @@ def main():
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
     for name, fn in (("ddim", gen_ddim), ("ddpm", gen_ddpm), ("prepost", gen_prepost), ("guidance", gen_guidance),
-                     ("pipeline", gen_pipeline), ("guided", gen_guided), ("reproject", gen_reproject), ("piecewise", gen_piecewise), ("latent", gen_latent), ("unet_oracle", gen_unet_oracle), ("postproc", gen_postproc), ("frontend", gen_frontend), ("ransac", gen_ransac)):
+                     ("pipeline", gen_pipeline), ("guided", gen_guided), ("reproject", gen_reproject), ("piecewise", gen_piecewise), ("latent", gen_latent), ("latent_nets", gen_latent_nets), ("unet_oracle", gen_unet_oracle), ("postproc", gen_postproc), ("frontend", gen_frontend), ("ransac", gen_ransac)):
         store = {}
         with torch.no_grad():
             fn(store)

@@ -244,7 +244,7 @@ class UNet2DConditionModel(nn.Module):
         if t.dim() == 0:
             t = t[None]
         t = t.expand(sample.shape[0])
-        temb = timestep_embedding(t, self.config.block_out_channels[0])
+        temb = timestep_embedding(t, self.config.block_out_channels[0]).to(sample.dtype)   # diffusers: t_emb.to(sample.dtype)
         temb = self.time_embedding.linear_2(F.silu(self.time_embedding.linear_1(temb)))
         ctx = encoder_hidden_states
         n_up = len(self.up_blocks) - 1

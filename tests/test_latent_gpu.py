@@ -76,7 +76,12 @@ def test_latent_pipeline_contract():
     ddim_cfgs, _ = _configs()
     pipe = d.GuidedLatentDiffusionPipeline(TinyCondUNet(8).cuda(), TinyVAE().cuda(), None, None,
                                            d.MyDDIMScheduler.from_config(ddim_cfgs["cos128_v"]),
-                                           d.FlowGuidance(flow_guidance_weight=0.0))
+                                           d.FlowGuidance(flow_guidance_weight=0.0, flow_guidance_mode="gradient"))
+    imp = d.GuidedLatentDiffusionPipeline(pipe.unet, pipe.vae, None, None, pipe.scheduler,
+                                          d.FlowGuidance(flow_guidance_weight=0.0))   # default mode: "imputation"
+    with pytest.raises(AssertionError):      # custom_pipelines.py:392
+        imp(torch.rand(1, 3, 32, 64), empty_text_embed=empty_text_embed(), num_inference_steps=4,
+            num_intermediate_images=1, cond_channels="rgb")
     rgb = torch.rand(1, 3, 32, 64) * 2 - 1
     with pytest.raises(AssertionError):
         pipe(rgb, empty_text_embed=empty_text_embed(), num_inference_steps=10, num_intermediate_images=4)

@@ -1,0 +1,69 @@
+"""End to end: ``d3roma_b200.GuidedLatentDiffusionPipeline`` over the CUDA ``UNet2DConditionModel`` + ``AutoencoderKL``
+against golden outputs of the REFERENCE's pipeline class (core/custom_pipelines.py:208-460) run with the oracle
+restatements of the two networks (tests/golden/latent_nets.npz, oracle/gen_golden.py:gen_latent_nets; reduced widths,
+same seeded weights).  fp16 activations against an fp32 CPU run over encoder + 4-6 UNet steps + decoder."""
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = Path(__file__).parent / "golden"
+
+DDIM = {  # oracle/gen_golden.py DDIM_CONFIGS
+    "sl1000_epsilon": dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                           prediction_type="epsilon", clip_sample=False, set_alpha_to_one=False, steps_offset=1),
+    "lin1000_v_trailing": dict(num_train_timesteps=1000, beta_schedule="linear", prediction_type="v_prediction",
+                               clip_sample=True, set_alpha_to_one=True, timestep_spacing="trailing"),
+}
+CASES = {"ddim_rgbraw": ("rgb+raw", 12, "sl1000_epsilon", 6, 3), "ddim_lrr": ("left+right+raw", 16, "lin1000_v_trailing", 4, 2)}
+UCFG = dict(block_out_channels=(64, 128, 128), attention_head_dim=(1, 2, 2), cross_attention_dim=64)
+VCFG = dict(block_out_channels=(128, 128, 128, 128))
+
+
+def _nets(cin):
+    import d3roma_b200.autoencoder_kl as ak
+    import d3roma_b200.unet_condition as uc
+    from oracle.ldm_ref import make_cond_unet, make_vae
+    unet = uc.UNet2DConditionModel(in_channels=cin, **UCFG).to("cuda")
+    unet.load_state_dict(make_cond_unet(in_channels=cin, seed=5, **UCFG).state_dict())
+    vae = ak.AutoencoderKL(**VCFG).to("cuda")
+    vae.load_state_dict(make_vae(seed=11, **VCFG).state_dict())
+    return unet, vae
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_latent_pipeline_with_cuda_networks_vs_reference_golden(tag):
+    import d3roma_b200 as d
+    z = np.load(G / "latent_nets.npz")
+    cc, cin, cfg, n, plots = CASES[tag]
+    unet, vae = _nets(cin)
+    pipe = d.GuidedLatentDiffusionPipeline(unet, vae, None, None, d.MyDDIMScheduler.from_config(DDIM[cfg]),
+                                           d.FlowGuidance(flow_guidance_weight=0.0, flow_guidance_mode="gradient"))
+    rgb, left, right, sim = (torch.from_numpy(z[k]) for k in ("rgb", "left", "right", "sim"))
+    ete = torch.from_numpy(z["empty_text_embed"])
+    out = pipe(rgb, left, right, sim, None, None, empty_text_embed=ete, num_inference_steps=n,
+               num_intermediate_images=plots, cond_channels=cc, generator=torch.Generator().manual_seed(9))
+    img, want = out.images.cpu().numpy(), z[f"{tag}/images"]
+    err = np.abs(img - want).max()
+    mean_err = np.abs(img - want).mean()
+    erri = np.abs(out.images_pred_orig.cpu().numpy() - z[f"{tag}/intermediate"]).max()
+    print(f"{tag}: final max-abs {err:.2e} mean-abs {mean_err:.2e}; intermediates max-abs {erri:.2e}")
+    assert out.images.shape == want.shape and out.images.is_cuda
+    # fp16 end to end (VAE encoder -> n UNet steps -> VAE decoder) against fp32: the per-network bound is 1e-2
+    # (tests/test_ldm_unet_gpu.py, test_ldm_vae_gpu.py); the chain is held to the same 1e-2 max (and 1e-3 mean) on maps in [-1, 1]
+    assert err <= 1e-2 and erri <= 1e-2 and mean_err <= 1e-3
+
+    # the fused entry points (one batched encoder pass, decode_mean) give the same result as the reference's own call
+    # sequence over the four VAE attributes
+    plain = SimpleNamespace(encoder=vae.encoder, quant_conv=vae.quant_conv, post_quant_conv=vae.post_quant_conv,
+                            decoder=vae.decoder)
+    pipe2 = d.GuidedLatentDiffusionPipeline(unet, plain, None, None, d.MyDDIMScheduler.from_config(DDIM[cfg]),
+                                            d.FlowGuidance(flow_guidance_weight=0.0, flow_guidance_mode="gradient"))
+    out2 = pipe2(rgb, left, right, sim, None, None, empty_text_embed=ete, num_inference_steps=n,
+                 num_intermediate_images=plots, cond_channels=cc, generator=torch.Generator().manual_seed(9))
+    d2 = (out2.images - out.images).abs().max().item()
+    print(f"{tag}: fused vs four-attribute call form {d2:.2e}")
+    assert d2 <= 1e-2

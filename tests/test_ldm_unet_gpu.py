@@ -98,3 +98,24 @@ def test_full_sd21_configuration():
     _check(ref, net, 1, (24, 40), 16, 1024, 321)
     del ref, net
     torch.cuda.empty_cache()
+
+
+def test_cuda_graph_path_matches_eager_and_survives_shape_changes():
+    ref, net = _pair(SMALL, 8)
+    g = torch.Generator().manual_seed(4)
+    ctx = torch.randn(2, 2, 64, generator=g).cuda()
+    xs = [torch.randn(2, 8, 16, 24, generator=g).cuda(), torch.randn(2, 8, 8, 8, generator=g).cuda(),
+          torch.randn(2, 8, 16, 24, generator=g).cuda()]
+    assert net.use_cuda_graph
+    got = [net(x, t, ctx).sample for x, t in zip(xs, (10, 20, torch.tensor([30, 40])))]
+    assert len(net._graphs) == 3 and net.graph_kernel_launches > 0
+    net.use_cuda_graph = False
+    want = [net(x, t, ctx).sample for x, t in zip(xs, (10, 20, torch.tensor([30, 40])))]
+    for a, b in zip(got, want):
+        assert (a - b).abs().max().item() <= 2e-3     # fp64 atomics of the GroupNorm moments may reorder
+    net.use_cuda_graph = True
+    again = net(xs[0], 10, ctx).sample            # replay of the first graph after other shapes ran
+    assert (again - want[0]).abs().max().item() <= 2e-3
+    # reloading weights drops the graphs (they hold raw pointers into the old tensors)
+    net.load_state_dict(ref.state_dict())
+    assert not net._graphs
