@@ -140,6 +140,8 @@ def _declare(lib: C.CDLL) -> None:
         "d3_layernorm": (i32, [vp, i32, vp, vp, i64, i32, f32, vp, i32, i32, vp]),
         "d3_geglu": (i32, [vp, i32, i64, i32, vp, i32, i32, vp]),
         "d3_attention_hd64": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp]),
+        "d3_attention_hd64_tc": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp, i32, vp]),
+        "d3_attention_hd64_tc_workspace_bytes": (C.c_size_t, [i32, i32, i32]),
         "d3_cross_attention_small": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp]),
         "d3_linear_small": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, vp, i32, vp]),
         "d3_timestep_sincos": (i32, [vp, i32, i32, i32, f32, vp, vp]),

@@ -360,6 +360,19 @@ def attention_hd64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int
     return out
 
 
+def attention_hd64_tc(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
+    """``attention_hd64`` on the tcgen05 / TMEM / TMA path (``d3_attention_hd64_tc``)."""
+    B, H, W, C_ = q.shape
+    if C_ != 64 * heads:
+        raise ValueError("attention_hd64_tc: head_dim must be 64")
+    out = torch.empty((B, H, W, C_), dtype=q.dtype, device=q.device)
+    ws = torch.empty((_lib.lib().d3_attention_hd64_tc_workspace_bytes(B, H * W, heads),), dtype=torch.uint8, device=q.device)
+    _lib.check(_lib.lib().d3_attention_hd64_tc(q.data_ptr(), q.stride(2), k.data_ptr(), k.stride(2), v.data_ptr(),
+                                               v.stride(2), B, H * W, heads, out.data_ptr(), C_, ws.data_ptr(), _dt(q),
+                                               _stream()))
+    return out
+
+
 def cross_attention_small(q: torch.Tensor, kc: torch.Tensor, vc: torch.Tensor) -> torch.Tensor:
     """q 16-bit [B, H, W, C]; kc, vc fp32 [B, L, C] (L <= 8) -> [B, H, W, C]."""
     B, H, W, C_ = q.shape

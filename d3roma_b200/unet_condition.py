@@ -13,7 +13,8 @@ block, head_dim 64, 32 GroupNorm groups — and runs it entirely through ``libd3
                           epilogue, QKV fused into one GEMM; 320-channel layers run with Cout padded to 384)
     GroupNorm (+SiLU)     d3_gn_stats + d3_gn_apply (group widths 10 / 20 / 30 / 40 / 60 / 80, virtual concat of the skip)
     LayerNorm, GEGLU      d3_layernorm, d3_geglu
-    self-attention        d3_attention_hd64
+    self-attention        d3_attention_hd64_tc (tcgen05 MMAs with S / P / O in TMEM, TMA-fed) for >= 1024 tokens,
+                          d3_attention_hd64 (mma.sync) below
     cross-attention       d3_cross_attention_small against keys / values of the context projected once per context
                           (d3_linear_small; the context is the constant [B, 2, 1024] empty-prompt embedding)
     time embedding        d3_timestep_sincos + d3_linear_small (all time_emb_proj layers in one launch)
@@ -103,6 +104,7 @@ class UNet2DConditionModel:
         self._eager_arena: Optional[_ChanArena] = None
         self._graphs: Dict[tuple, dict] = {}
         self.use_cuda_graph = True
+        self.tc_attention_min_tokens = 1024
         self.graph_kernel_launches = 0   # kernels executed through CUDA-graph replays (launch accounting)
         self._ctx_cache = None
         self._cin_pad = (in_channels + 63) // 64 * 64
@@ -303,7 +305,10 @@ class UNet2DConditionModel:
         n = self._gn(x, W[p + ".norm.g"], W[p + ".norm.b"], eps=1e-6, silu=False)
         h = self._linear(n, p + ".pi", C)
         qkv = self._linear(ops.layernorm(h, W[t + ".norm1.g"], W[t + ".norm1.b"]), t + ".qkv", 3 * C)
-        a = ops.attention_hd64(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads)
+        # tcgen05 / TMEM / TMA attention for the long token sequences (levels 0 / 1); the register-fragment mma.sync kernel
+        # for the short ones, where a 128-query CTA tile would mostly be padding (tools/bench_attn64.py)
+        attn = ops.attention_hd64_tc if qkv.shape[1] * qkv.shape[2] >= self.tc_attention_min_tokens else ops.attention_hd64
+        a = attn(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads)
         h = self._linear(a, t + ".o1", C, residual=h)
         q2 = self._linear(ops.layernorm(h, W[t + ".norm2.g"], W[t + ".norm2.b"]), t + ".q2", C)
         a = ops.cross_attention_small(q2, kv[0], kv[1])

@@ -352,6 +352,12 @@ int d3_geglu(const void* x, int x_pitch, int64_t M, int D, void* out, int out_pi
  * pitches (channel slices of a fused QKV tensor), head h at channels [64h, 64h + 64); out [B*N][out_pitch]. */
 int d3_attention_hd64(const void* q, int q_pitch, const void* k, int k_pitch, const void* v, int v_pitch, int B, int N,
                       int heads, void* out, int out_pitch, int dtype, void* stream);
+/* The same attention (head_dim 64) on the Blackwell tensor path: S = Q K^T and O = P V as tcgen05.mma with TMEM
+ * accumulators, Q / K / V^T tiles by TMA, softmax rows read straight from TMEM.  `workspace` (device scratch of
+ * d3_attention_hd64_tc_workspace_bytes(B, N, heads) bytes) receives V^T with the keys contiguous. */
+size_t d3_attention_hd64_tc_workspace_bytes(int B, int N, int heads);
+int d3_attention_hd64_tc(const void* q, int q_pitch, const void* k, int k_pitch, const void* v, int v_pitch, int B, int N,
+                         int heads, void* out, int out_pitch, void* workspace, int dtype, void* stream);
 /* attention of N query tokens per sample against L <= 8 context tokens whose keys / values kc, vc fp32 [B][L][C] were
  * projected beforehand (attn2 against the [B, 2, 1024] empty-prompt embedding, custom_pipelines.py:299-304, 386);
  * C = 64 * heads. */

@@ -93,6 +93,9 @@ def attention_hd64(q, k, v, heads):
     return o.transpose(1, 2).reshape(B, H, W, C).to(q.dtype)
 
 
+attention_hd64_tc = attention_hd64
+
+
 def cross_attention_small(q, kc, vc):
     B, H, W, C = q.shape
     L, heads = kc.shape[1], C // 64

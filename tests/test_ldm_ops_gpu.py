@@ -85,6 +85,25 @@ def test_attention_hd64(dt, B, hw, heads):
 
 
 @pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("B,hw,heads", [(2, (12, 20), 10), (1, (24, 40), 5), (2, (6, 10), 20), (1, (7, 10), 3),
+                                        (1, (1, 128), 1), (1, (5, 13), 2), (2, (45, 80), 5), (1, (16, 16), 1)])
+def test_attention_hd64_tcgen05(dt, B, hw, heads):
+    """The tcgen05 / TMEM / TMA formulation against the same fp32 reference (and against the mma.sync kernel)."""
+    from d3roma_b200 import ops
+    H, W = hw
+    C = 64 * heads
+    qkv = _rnd((B, H, W, 3 * C), dt, 5, 1.5)
+    out = ops.attention_hd64_tc(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads)
+    q, k, v = (t.float().reshape(B, H * W, heads, 64).transpose(1, 2) for t in qkv.split(C, -1))
+    ref = torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1) @ v
+    ref = ref.transpose(1, 2).reshape(B, H, W, C)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= (3e-3 if dt == torch.float16 else 2e-2) * max(1.0, ref.abs().max().item()), err
+    old = ops.attention_hd64(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads)
+    assert (out.float() - old.float()).abs().max().item() <= (4e-3 if dt == torch.float16 else 3e-2)
+
+
+@pytest.mark.parametrize("dt", DT)
 @pytest.mark.parametrize("L", [2, 1, 8, 5])
 def test_cross_attention_small(dt, L):
     from d3roma_b200 import ops

@@ -37,17 +37,17 @@ def wrap(name):
             flops = 2.0 * Bn * (Hh // s) * (Ww // s) * w.shape[0] * w.shape[1]
             kind = "lin" if k["ksize"] == 1 else ("up" if ph else f"c3s{s}")
             tag = f"conv {kind} {Cin}->{k.get('cout_valid') or w.shape[0]}"
-        elif name == "attention_hd64":
+        elif name in ("attention_hd64", "attention_hd64_tc"):
             q = a[0]
             Bn, Hh, Ww, C = q.shape
             flops = 4.0 * Bn * (Hh * Ww) ** 2 * C
-            tag = f"attention_hd64 N={Hh * Ww} heads={a[3]}"
+            tag = f"{name} N={Hh * Ww} heads={a[3]}"
         records.append((tag, flops, e0, e1))
         return out
     setattr(ops, name, f)
 
 
-for nm in ("conv2d_igemm", "gn_stats", "gn_apply", "layernorm", "geglu", "attention_hd64", "cross_attention_small",
+for nm in ("conv2d_igemm", "gn_stats", "gn_apply", "layernorm", "geglu", "attention_hd64", "attention_hd64_tc", "cross_attention_small",
            "linear_small", "timestep_sincos", "nchw_to_nhwc16", "nhwc16_to_nchw", "resize_nearest", "groupnorm_silu",
            "conv_in_direct", "conv_out_fused", "softmax_rows_", "transpose_pad", "conv1x1_nchw_small"):
     wrap(nm)
