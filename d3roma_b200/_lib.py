@@ -137,6 +137,7 @@ def _declare(lib: C.CDLL) -> None:
                                     vp, vp]),
         "d3_gn_stats": (i32, [vp, i32, i32, vp, i32, i32, i32, i32, vp, i32, vp]),
         "d3_gn_apply": (i32, [vp, i32, i32, vp, i32, i32, vp, vp, vp, i32, i32, i32, f32, i32, vp, i32, i32, vp]),
+        "d3_groupnorm_one_pass": (i32, [vp, i32, i32, vp, i32, i32, vp, vp, i32, i32, i32, f32, i32, vp, i32, i32, vp]),
         "d3_layernorm": (i32, [vp, i32, vp, vp, i64, i32, f32, vp, i32, i32, vp]),
         "d3_geglu": (i32, [vp, i32, i64, i32, vp, i32, i32, vp]),
         "d3_attention_hd64": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp]),

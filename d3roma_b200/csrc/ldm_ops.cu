@@ -176,6 +176,116 @@ __global__ void __launch_bounds__(256) gn_apply_gen_kernel(const GnGenArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GroupNorm in ONE kernel for the small tensors of the latent UNet (<= 40 MB: they sit in the 126 MB L2 between the two
+// passes): a block owns one sample and a set of whole groups whose channels form 16-byte vectors, reduces their moments
+// itself (no atomics, no statistics arena, no second launch) and normalises from the L2-resident data.
+// ---------------------------------------------------------------------------------------------------------------------
+struct GnOneArgs {
+  const uint16_t* x1;
+  const uint16_t* x2;
+  int C1, C2, p1, p2, HW;
+  int cpg;           // channels per group
+  int gpb;           // groups per block: gpb * cpg is a multiple of 8 (whole 16-byte vectors)
+  const float* gamma;
+  const float* beta;
+  uint16_t* out;
+  int pout, silu;
+  float eps;
+};
+
+template <int DT>
+__global__ void __launch_bounds__(512) gn_one_kernel(const GnOneArgs a) {
+  pdl_prologue();
+  constexpr int kMaxG = 8;                      // groups per block
+  __shared__ double s_sum[16][kMaxG][2];        // [warp][group][sum, sum of squares]
+  __shared__ float s_mean[kMaxG], s_rstd[kMaxG];
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * a.gpb * a.cpg;    // first channel of this block
+  const int nv = a.gpb * a.cpg / 8;             // 16-byte vectors per pixel in this block's slice
+  const int total = a.HW * nv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  auto src_of = [&](int pix, int vi) -> const uint16_t* {
+    const int c = c0 + vi * 8;
+    return c < a.C1 ? a.x1 + ((size_t)b * a.HW + pix) * a.p1 + c : a.x2 + ((size_t)b * a.HW + pix) * a.p2 + (c - a.C1);
+  };
+  // ---- pass 1: per-thread moments of the channels of one vector position (vi is fixed per thread when nv | blockDim)
+  float s[kMaxG], q[kMaxG];
+#pragma unroll
+  for (int g = 0; g < kMaxG; ++g) s[g] = q[g] = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int pix = i / nv, vi = i - pix * nv;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src_of(pix, vi)));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack2<DT>(w[k]);
+      const int ch = vi * 8 + 2 * k;            // channel inside the slice (cpg is even: both halves in one group)
+      const int g = ch / a.cpg;
+#pragma unroll
+      for (int gg = 0; gg < kMaxG; ++gg)
+        if (gg == g) {
+          s[gg] += f.x + f.y;
+          q[gg] = fmaf(f.x, f.x, fmaf(f.y, f.y, q[gg]));
+        }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < kMaxG; ++g) {
+    if (g < a.gpb) {
+      double ds = (double)s[g], dq = (double)q[g];
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        ds += __shfl_xor_sync(0xffffffffu, ds, off);
+        dq += __shfl_xor_sync(0xffffffffu, dq, off);
+      }
+      if (lane == 0) {
+        s_sum[warp][g][0] = ds;
+        s_sum[warp][g][1] = dq;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < a.gpb) {
+    double ds = 0.0, dq = 0.0;
+    for (int w = 0; w < nw; ++w) {
+      ds += s_sum[w][threadIdx.x][0];
+      dq += s_sum[w][threadIdx.x][1];
+    }
+    const double n = (double)a.HW * a.cpg;
+    const double mean = ds / n;
+    double var = dq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)a.eps));
+  }
+  __syncthreads();
+  // ---- pass 2: normalise (+ SiLU) from the L2-resident slice
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int pix = i / nv, vi = i - pix * nv;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src_of(pix, vi)));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack2<DT>(w[k]);
+      const int ch = vi * 8 + 2 * k;
+      const int g = ch / a.cpg;
+      const int c = c0 + ch;
+      const float r = s_rstd[g], m = s_mean[g];
+      const float g0 = __ldg(a.gamma + c) * r, g1 = __ldg(a.gamma + c + 1) * r;
+      float y0 = fmaf(f.x - m, g0, __ldg(a.beta + c)), y1 = fmaf(f.y - m, g1, __ldg(a.beta + c + 1));
+      if (a.silu) {
+        y0 = silu_fast(y0);
+        y1 = silu_fast(y1);
+      }
+      o[k] = pack2<DT>(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(a.out + ((size_t)b * a.HW + pix) * a.pout + c0 + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // smallest number of channel chunks such that a chunk has <= 128 channel vectors and the chunks are equal
 int gn_chunks(int nvec) {
   for (int n = 1; n <= nvec; ++n)
@@ -1041,6 +1151,32 @@ extern "C" int d3_conv1x1_nchw_small(const float* x, int B, int Cin, int Cout, i
   const long long total = (long long)B * HW;
   D3_CHECK_CUDA(launch_pdl(conv1x1_nchw_small_kernel, dim3(grid_for(total, 256)), dim3(256), 0,
                            static_cast<cudaStream_t>(stream), x, Cin, Cout, (long long)HW, total, w, bias, out));
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
+extern "C" int d3_groupnorm_one_pass(const void* x1, int C1, int pitch1, const void* x2, int C2, int pitch2,
+                                     const float* gamma, const float* beta, int B, int HW, int groups, float eps,
+                                     int apply_silu, void* out, int out_pitch, int dtype, void* stream) {
+  D3_16BIT(dtype);
+  const int C = C1 + C2;
+  D3_REQUIRE(x1 && gamma && beta && out && C1 > 0 && C1 % 8 == 0 && C2 % 8 == 0 && pitch1 % 8 == 0 && out_pitch % 8 == 0 &&
+                 (C2 == 0 || (x2 && pitch2 % 8 == 0)) && groups >= 1 && C % groups == 0,
+             "groupnorm_one_pass: bad arguments (C=%d groups=%d)", C, groups);
+  const int cpg = C / groups;
+  D3_REQUIRE(cpg % 2 == 0, "groupnorm_one_pass: channels per group must be even (got %d)", cpg);
+  int gpb = 0;
+  for (int g = 1; g <= 8; ++g)
+    if ((g * cpg) % 8 == 0 && groups % g == 0) { gpb = g; break; }
+  D3_REQUIRE(gpb > 0, "groupnorm_one_pass: no block shape for %d channels per group", cpg);
+  GnOneArgs a{static_cast<const uint16_t*>(x1), static_cast<const uint16_t*>(x2), C1, C2, pitch1, pitch2, HW, cpg, gpb,
+              gamma, beta, static_cast<uint16_t*>(out), out_pitch, apply_silu, eps};
+  dim3 grid(groups / gpb, B);
+  const long long work = (long long)HW * gpb * cpg / 8;
+  const int threads = work >= 4096 ? 512 : (work >= 1024 ? 256 : 128);
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == D3_DTYPE_F16) D3_CHECK_CUDA(launch_pdl(gn_one_kernel<kF16>, grid, dim3(threads), 0, st, a));
+  else D3_CHECK_CUDA(launch_pdl(gn_one_kernel<kBF16>, grid, dim3(threads), 0, st, a));
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

@@ -330,6 +330,20 @@ def gn_apply(x1: torch.Tensor, chan: torch.Tensor, gamma: torch.Tensor, beta: to
     return out
 
 
+def groupnorm_one_pass(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, x2: Optional[torch.Tensor] = None,
+                       groups: int = 32, eps: float = 1e-5, silu: bool = True) -> torch.Tensor:
+    """GroupNorm (+SiLU) of cat(x1, x2) in one launch (``d3_groupnorm_one_pass``; L2-resident tensors)."""
+    _check_nhwc(x1, "x1")
+    B, H, W, C1 = x1.shape
+    C2 = 0 if x2 is None else x2.shape[3]
+    out = torch.empty((B, H, W, C1 + C2), dtype=x1.dtype, device=x1.device)
+    _lib.check(_lib.lib().d3_groupnorm_one_pass(x1.data_ptr(), C1, x1.stride(2), _ptr(x2), C2,
+                                                x2.stride(2) if x2 is not None else 0, gamma.data_ptr(), beta.data_ptr(),
+                                                B, H * W, groups, eps, int(silu), out.data_ptr(), out.stride(2), _dt(x1),
+                                                _stream()))
+    return out
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     """LayerNorm over the last dim of a 16-bit [..., C] tensor whose rows are ``x.stride(-2)`` apart."""
     C_ = x.shape[-1]

@@ -105,6 +105,7 @@ class UNet2DConditionModel:
         self._graphs: Dict[tuple, dict] = {}
         self.use_cuda_graph = True
         self.tc_attention_min_tokens = 1024
+        self.gn_one_pass_max_bytes = 48 << 20    # larger tensors take the two-launch form (d3_gn_stats + d3_gn_apply)
         self.graph_kernel_launches = 0   # kernels executed through CUDA-graph replays (launch accounting)
         self._ctx_cache = None
         self._cin_pad = (in_channels + 63) // 64 * 64
@@ -256,6 +257,8 @@ class UNet2DConditionModel:
     def _gn(self, x, gamma, beta, *, x2=None, eps=1e-5, silu=True):
         B = x.shape[0]
         C = x.shape[3] + (0 if x2 is None else x2.shape[3])
+        if x.numel() // x.shape[3] * C * 2 <= self.gn_one_pass_max_bytes:   # stays in L2 between the two passes
+            return ops.groupnorm_one_pass(x, gamma, beta, x2=x2, groups=32, eps=eps, silu=silu)
         chan = self._arena.take(B, C)
         ops.gn_stats(x, chan, x2=x2)
         return ops.gn_apply(x, chan, gamma, beta, x2=x2, groups=32, eps=eps, silu=silu)

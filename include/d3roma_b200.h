@@ -343,6 +343,12 @@ int d3_gn_stats(const void* x1, int C1, int pitch1, const void* x2, int C2, int 
 int d3_gn_apply(const void* x1, int C1, int pitch1, const void* x2, int C2, int pitch2, const double* chan_stats,
                 const float* gamma, const float* beta, int B, int HW, int groups, float eps, int apply_silu, void* out,
                 int out_pitch, int dtype, void* stream);
+/* The same GroupNorm (+ SiLU) as ONE kernel, for tensors small enough to stay in the 126 MB L2 between its two passes (the
+ * latent UNet's): a block owns one sample and a set of whole groups, reduces their moments itself and normalises - no
+ * statistics buffer, no atomics.  Channels per group must be even. */
+int d3_groupnorm_one_pass(const void* x1, int C1, int pitch1, const void* x2, int C2, int pitch2, const float* gamma,
+                          const float* beta, int B, int HW, int groups, float eps, int apply_silu, void* out,
+                          int out_pitch, int dtype, void* stream);
 /* aten::native_layer_norm over the last dimension of M rows of C (<= 1280) channels (BasicTransformerBlock.norm1-3). */
 int d3_layernorm(const void* x, int x_pitch, const float* gamma, const float* beta, int64_t M, int C, float eps,
                  void* out, int out_pitch, int dtype, void* stream);

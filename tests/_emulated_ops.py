@@ -77,6 +77,12 @@ def gn_apply(x1, chan, gamma, beta, *, x2=None, groups=32, eps=1e-5, silu=True, 
     return (F.silu(y) if silu else y).to(x1.dtype)
 
 
+def groupnorm_one_pass(x1, gamma, beta, *, x2=None, groups=32, eps=1e-5, silu=True):
+    cat = x1 if x2 is None else torch.cat([x1, x2], -1)
+    y = F.group_norm(cat.float().permute(0, 3, 1, 2), groups, gamma, beta, eps).permute(0, 2, 3, 1)
+    return (F.silu(y) if silu else y).to(x1.dtype)
+
+
 def layernorm(x, gamma, beta, eps=1e-5):
     return F.layer_norm(x.float(), (x.shape[-1],), gamma, beta, eps).to(x.dtype)
 

@@ -44,6 +44,9 @@ def test_groupnorm_generic(dt, C1, C2, hw, silu, eps):
         ref = F.silu(ref)
     err = (out.float() - ref.permute(0, 2, 3, 1)).abs().max().item()
     assert err <= _tol(dt) * max(1.0, ref.abs().max().item()), err
+    one = ops.groupnorm_one_pass(x1, g, b, x2=x2, eps=eps, silu=silu)      # the single-launch form
+    err1 = (one.float() - ref.permute(0, 2, 3, 1)).abs().max().item()
+    assert err1 <= _tol(dt) * max(1.0, ref.abs().max().item()), err1
 
 
 @pytest.mark.parametrize("dt", DT)

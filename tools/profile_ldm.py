@@ -88,6 +88,7 @@ def timed(fn, reps=3):
 
 
 unet = UNet2DConditionModel(in_channels=12, compute_dtype=dtype).to("cuda")
+unet.use_cuda_graph = False   # per-op events need the eager launch sequence
 unet.load_state_dict(random_init_cond_unet_state_dict(12, device="cuda"))
 vae = AutoencoderKL(compute_dtype=dtype).to("cuda")
 vae.load_state_dict(random_init_vae_state_dict(device="cuda"))
