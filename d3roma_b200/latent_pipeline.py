@@ -79,6 +79,7 @@ class GuidedLatentDiffusionPipeline:
         self.register_modules(unet=unet, vae=vae, tokenizer=tokenizer, text_encoder=text_encoder, scheduler=scheduler,
                               guidance=guidance)
         self._progress_bar_config = {}
+        self.empty_text_embed = None   # optional cached [1, 2, D] embedding of the empty prompt (skips the text encoder)
 
     def register_modules(self, **kwargs):
         for k, v in kwargs.items():
@@ -151,6 +152,8 @@ class GuidedLatentDiffusionPipeline:
         assert shapes, "no input image"
         input_shape = shapes[0]
         dev = self.device
+        if empty_text_embed is None:        # callers that cannot pass it (evaluate.py:95 eval_batch) may set the attribute
+            empty_text_embed = getattr(self, "empty_text_embed", None)
         if empty_text_embed is None:
             empty_text_embed = self._encode_empty_text()
         empty_text_embed = empty_text_embed.to(dev).repeat((input_shape[0], 1, 1))

@@ -67,3 +67,26 @@ def test_latent_pipeline_with_cuda_networks_vs_reference_golden(tag):
     d2 = (out2.images - out.images).abs().max().item()
     print(f"{tag}: fused vs four-attribute call form {d2:.2e}")
     assert d2 <= 1e-2
+
+
+def test_eval_batch_runs_the_latent_pipeline():
+    """evaluate.py:66-148 calls both pipeline classes the same way (six positional tensors); divis_by 8 for LDM configs
+    (conf/task/train_ldm_mixed_rgb+raw.yaml), 2 rounds -> uncertainties."""
+    import d3roma_b200 as d
+    from d3roma_b200.evaluate import default_config, eval_batch
+    unet, vae = _nets(12)
+    pipe = d.GuidedLatentDiffusionPipeline(unet, vae, None, None, d.MyDDIMScheduler.from_config(DDIM["sl1000_epsilon"]),
+                                           d.FlowGuidance(flow_guidance_weight=0.0, flow_guidance_mode="gradient"))
+    pipe.empty_text_embed = torch.randn(1, 2, 64, generator=torch.Generator().manual_seed(0))
+    cfg = default_config(divis_by=8, cond_channels="rgb+raw", num_inference_timesteps=4, num_intermediate_images=2,
+                         num_inference_rounds=2, depth_channels=1)
+    g = torch.Generator().manual_seed(2)
+    B, H, W = 2, 60, 92                       # padded to 64 x 96 -> 8 x 12 latents
+    rgb = torch.rand(B, 3, H, W, generator=g) * 2 - 1
+    gt = torch.rand(B, 1, H, W, generator=g) * 60 + 5
+    sim = (gt / 128.0 - 0.5) * 2.0            # Normalizer("average", bound 128, t 0.5, s 2): utils.py:183-196
+    mask = torch.ones(B, 1, H, W)
+    pred, (m5, m6), unc, err, out = eval_batch(cfg, pipe, True, torch.full((B,), 24.5), rgb, gt, mask, None, None,
+                                               sim, None)
+    assert pred.shape == (B, H, W) and m5.shape == (B, 5) and m6.shape == (B, 6) and unc.shape == (B, H, W)
+    assert np.isfinite(pred).all() and out.images_pred_orig.shape == (B, 2, H, W)
