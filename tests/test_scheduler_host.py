@@ -12,6 +12,7 @@ from oracle import schedulers_ref as S
 
 G = Path(__file__).parent / "golden"
 from tests.test_oracle_schedulers import DDIM, DDPM  # noqa: E402
+from tests._golden import SOURCES, load, same  # noqa: E402
 
 
 def _ddim(c):
@@ -42,9 +43,10 @@ def test_ddim_tables_and_timesteps(name):
             assert c.sqrt_alpha_t == float(ac[t] ** 0.5) and c.sqrt_alpha_prev == float(a_prev ** 0.5)
 
 
+@pytest.mark.parametrize("source", SOURCES)
 @pytest.mark.parametrize("name", list(DDPM))
-def test_ddpm_tables_and_timesteps(name):
-    z = np.load(G / "ddpm.npz")
+def test_ddpm_tables_and_timesteps(name, source):
+    z = load("ddpm", source)
     c = DDPM[name]
     s = MyDDPMScheduler.from_config(dict(num_train_timesteps=c["T"], beta_schedule=c["sched"],
                                          prediction_type=c["pt"], clip_sample=c["clip"], thresholding=c["thr"],
@@ -56,9 +58,9 @@ def test_ddpm_tables_and_timesteps(name):
         s.set_timesteps(n)
         assert np.array_equal(s.timesteps.numpy(), z[f"{name}/n{n}/timesteps"])
     a, b, t = (torch.from_numpy(z[f"{name}/an_{k}"]) for k in "abt")
-    assert np.array_equal(s.add_noise(a, b, t).numpy(), z[f"{name}/add_noise"])
-    assert np.array_equal(s.get_velocity(a, b, t).numpy(), z[f"{name}/velocity"])
-    assert np.array_equal(s.posterior_mean_variance(a, b, t)[0].numpy(), z[f"{name}/posterior_mean"])
+    assert same(s.add_noise(a, b, t).numpy(), z[f"{name}/add_noise"], source)
+    assert same(s.get_velocity(a, b, t).numpy(), z[f"{name}/velocity"], source)
+    assert same(s.posterior_mean_variance(a, b, t)[0].numpy(), z[f"{name}/posterior_mean"], source)
 
 
 def test_survey_appendix_c4_variances():
