@@ -44,6 +44,22 @@ class ConvParams(C.Structure):
     ]
 
 
+class WgradParams(C.Structure):
+    """Mirror of ``d3_wgrad_params``."""
+
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("Cin", C.c_int32), ("x_pitch", C.c_int32),
+        ("dy", C.c_void_p),
+        ("Cout", C.c_int32), ("dy_pitch", C.c_int32),
+        ("ksize", C.c_int32), ("stride", C.c_int32),
+        ("dw", C.c_void_p),
+        ("dw_pitch", C.c_int64),
+        ("dw_col0", C.c_int32), ("dtype", C.c_int32),
+    ]
+
+
 class DDIMCoeffs(C.Structure):
     """Mirror of ``d3_ddim_coeffs``."""
 
@@ -152,6 +168,24 @@ def _declare(lib: C.CDLL) -> None:
         "d3_softmax_rows": (i32, [vp, i32, i32, i32, f32, i32, vp]),
         "d3_transpose_pad16": (i32, [vp, i32, i32, i32, vp, i32, vp]),
         "d3_conv1x1_nchw_small": (i32, [vp, i32, i32, i32, i64, vp, vp, vp, vp]),
+        # training step
+        "d3_conv2d_wgrad": (i32, [C.POINTER(WgradParams), vp]),
+        "d3_groupnorm_bwd_workspace_bytes": (C.c_size_t, [i32, i32]),
+        "d3_groupnorm_silu_bwd": (i32, [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, f32, i32, vp, i32, vp,
+                                        i32, vp, i32, vp, vp, vp, i64, vp, i32, vp]),
+        "d3_colsum_nhwc16": (i32, [vp, i32, i32, i32, i32, vp, i64, i32, vp]),
+        "d3_add_nhwc16": (i32, [vp, i32, vp, i32, vp, i32, i64, i32, i32, vp]),
+        "d3_sumpool2x_nhwc16": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
+        "d3_conv_out_bwd": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, i32, vp, i32, vp]),
+        "d3_attention_hd8_bwd_workspace_bytes": (C.c_size_t, [i32, i32, i32]),
+        "d3_attention_hd8_bwd": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp, i32, vp]),
+        "d3_masked_loss_grad": (i32, [vp, vp, vp, vp, i32, i32, i64, i32, f32, vp, vp, vp, vp]),
+        "d3_linear_small_bwd": (i32, [vp, i32, i32, i32, vp, i32, vp, vp, vp, vp, i32, vp]),
+        "d3_sumsq": (i32, [vp, i64, vp, vp]),
+        "d3_adamw_step": (i32, [vp, vp, vp, vp, i64, vp, i64, i32, f32, f32, f32, f32, f32, i32, vp, f32, f32, vp, vp]),
+        "d3_cast_f32_to_16": (i32, [vp, vp, i64, i32, vp]),
+        "d3_gather_add": (i32, [vp, vp, vp, vp, i32, vp]),
+        "d3_pack_taps16": (i32, [vp, i64, i32, i32, i32, C.POINTER(C.c_int32), i32, vp, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here == header and library out of sync

@@ -715,3 +715,177 @@ def affine_rows(y, scale_shift) -> torch.Tensor:
     out = torch.empty_like(y)
     _lib.check(_lib.lib().d3_affine_rows(y.data_ptr(), st.data_ptr(), R, y.numel() // max(R, 1), out.data_ptr(), _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# training step: backward / optimizer ops of csrc/conv_wgrad.cu, train_ops.cu, attention_bwd.cu
+# ------------------------------------------------------------------------------------------------
+def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, *, ksize: int, stride: int = 1,
+                 col0: int = 0) -> torch.Tensor:
+    """dw[co, col0 + tap*Cin + ci] += sum dy[b,y,x,co] * x[b, s*y+kh-1, s*x+kw-1, ci] (``d3_conv2d_wgrad``); dw fp32
+    [Cout, Ktot] in the forward pack layout (a row-pitched view is allowed)."""
+    _check_nhwc(x, "x")
+    _check_nhwc(dy, "dy")
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[3]
+    if dy.shape[:3] != (B, H // stride, W // stride) or dy.dtype != x.dtype:
+        raise ValueError(f"conv2d_wgrad: dy {tuple(dy.shape)} does not match x {tuple(x.shape)} at stride {stride}")
+    if dw.dtype != torch.float32 or dw.dim() != 2 or dw.shape[0] != Cout or dw.stride(1) != 1:
+        raise ValueError("conv2d_wgrad: dw must be fp32 [Cout, Ktot] with contiguous rows")
+    p = _lib.WgradParams()
+    p.x, p.B, p.H, p.W, p.Cin, p.x_pitch = x.data_ptr(), B, H, W, Cin, x.stride(2)
+    p.dy, p.Cout, p.dy_pitch = dy.data_ptr(), Cout, dy.stride(2)
+    p.ksize, p.stride = ksize, stride
+    p.dw, p.dw_pitch, p.dw_col0 = dw.data_ptr(), dw.stride(0), col0
+    p.dtype = _dt(x)
+    _lib.check(_lib.lib().d3_conv2d_wgrad(C.byref(p), _stream()))
+    return dw
+
+
+def groupnorm_silu_bwd(x1: torch.Tensor, stats1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, dy: torch.Tensor, *,
+                       x2: Optional[torch.Tensor] = None, stats2: Optional[torch.Tensor] = None, silu: bool = True,
+                       groups: int = 32, eps: float = 1e-5, addend: Optional[torch.Tensor] = None,
+                       dgamma: Optional[torch.Tensor] = None, dbeta: Optional[torch.Tensor] = None,
+                       colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Backward of ``groupnorm_silu``: returns dx over the concatenated channels (+ ``addend``); ``dgamma`` / ``dbeta``
+    (fp32 [C]) are accumulated; ``colsum`` (fp32 [B, C] view with contiguous channels, or [C] = summed over the batch)
+    receives the per-channel sums of dx."""
+    _check_nhwc(x1, "x1")
+    _check_nhwc(dy, "dy")
+    B, H, W, C1 = x1.shape
+    C2 = 0 if x2 is None else x2.shape[3]
+    Ct = C1 + C2
+    if dy.shape != (B, H, W, Ct):
+        raise ValueError("groupnorm_silu_bwd: dy must cover the concatenated channels")
+    dx = torch.empty((B, H, W, Ct), dtype=x1.dtype, device=x1.device)
+    ws = torch.empty((B * Ct * 2,), dtype=torch.float32, device=x1.device)
+    cs_ptr, cs_stride = None, 0
+    if colsum is not None:
+        if colsum.dtype != torch.float32 or colsum.stride(-1) != 1 or colsum.shape[-1] != Ct:
+            raise ValueError("groupnorm_silu_bwd: colsum must be fp32 [..., C] with contiguous channels")
+        cs_ptr, cs_stride = colsum.data_ptr(), (colsum.stride(0) if colsum.dim() == 2 else 0)
+    _lib.check(_lib.lib().d3_groupnorm_silu_bwd(
+        x1.data_ptr(), C1, x1.stride(2), stats1.data_ptr(), _ptr(x2), C2, x2.stride(2) if x2 is not None else 0,
+        _ptr(stats2), gamma.data_ptr(), beta.data_ptr(), B, H * W, groups, eps, int(silu), dy.data_ptr(), dy.stride(2),
+        _ptr(addend), addend.stride(2) if addend is not None else 0, dx.data_ptr(), dx.stride(2), _ptr(dgamma),
+        _ptr(dbeta), cs_ptr, cs_stride, ws.data_ptr(), _dt(x1), _stream()))
+    return dx
+
+
+def colsum_nhwc16(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out (fp32 [B, C] view or [C]) += per-channel sums of x over the pixels (and over the batch for a 1-D out)."""
+    _check_nhwc(x, "x")
+    B, H, W, Cc = x.shape
+    if out.dtype != torch.float32 or out.shape[-1] != Cc or out.stride(-1) != 1:
+        raise ValueError("colsum_nhwc16: out must be fp32 [..., C] with contiguous channels")
+    _lib.check(_lib.lib().d3_colsum_nhwc16(x.data_ptr(), x.stride(2), B, H * W, Cc, out.data_ptr(),
+                                           out.stride(0) if out.dim() == 2 else 0, _dt(x), _stream()))
+    return out
+
+
+def add_nhwc16(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _check_nhwc(a, "a")
+    _check_nhwc(b, "b")
+    if a.shape != b.shape or a.dtype != b.dtype:
+        raise ValueError("add_nhwc16: shape / dtype mismatch")
+    B, H, W, Cc = a.shape
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=a.dtype, device=a.device)
+    _lib.check(_lib.lib().d3_add_nhwc16(a.data_ptr(), a.stride(2), b.data_ptr(), b.stride(2), out.data_ptr(),
+                                        out.stride(2), B * H * W, Cc, _dt(a), _stream()))
+    return out
+
+
+def sumpool2x_nhwc16(x: torch.Tensor, addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[B, 2H, 2W, C] -> [B, H, W, C] block sums (+ addend): backward of ``upsample_nearest2x``."""
+    _check_nhwc(x, "x")
+    B, H2, W2, Cc = x.shape
+    out = torch.empty((B, H2 // 2, W2 // 2, Cc), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().d3_sumpool2x_nhwc16(x.data_ptr(), x.stride(2), _ptr(addend),
+                                              addend.stride(2) if addend is not None else 0, out.data_ptr(),
+                                              out.stride(2), B, H2 // 2, W2 // 2, Cc, _dt(x), _stream()))
+    return out
+
+
+def conv_out_bwd(h: torch.Tensor, stats: torch.Tensor, gamma, beta, w, dy: torch.Tensor, dw: torch.Tensor,
+                 eps: float = 1e-5) -> torch.Tensor:
+    """Backward of ``conv_out_fused`` up to SiLU(GroupNorm(h)): returns da (16-bit NHWC [B,H,W,128]); dw fp32 [dc,9,128]
+    is accumulated."""
+    _check_nhwc(h, "h")
+    B, H, W, Cc = h.shape
+    dc = dy.shape[1]
+    dy = _f32c(dy, "dy")
+    da = torch.empty((B, H, W, 128), dtype=h.dtype, device=h.device)
+    _lib.check(_lib.lib().d3_conv_out_bwd(h.data_ptr(), h.stride(2), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                          w.data_ptr(), dy.data_ptr(), B, H, W, dc, eps, da.data_ptr(), da.stride(2),
+                                          dw.data_ptr(), _dt(h), _stream()))
+    return da
+
+
+def attention_hd8_bwd(qkv: torch.Tensor, o: torch.Tensor, d_o: torch.Tensor) -> torch.Tensor:
+    _check_nhwc(qkv, "qkv")
+    B, H, W, C3 = qkv.shape
+    C_ = C3 // 3
+    dqkv = torch.empty((B, H, W, C3), dtype=qkv.dtype, device=qkv.device)
+    ws = torch.empty((_lib.lib().d3_attention_hd8_bwd_workspace_bytes(B, H * W, C_),), dtype=torch.uint8, device=qkv.device)
+    _lib.check(_lib.lib().d3_attention_hd8_bwd(qkv.data_ptr(), qkv.stride(2), o.data_ptr(), o.stride(2), d_o.data_ptr(),
+                                               d_o.stride(2), B, H * W, C_, dqkv.data_ptr(), dqkv.stride(2),
+                                               ws.data_ptr(), _dt(qkv), _stream()))
+    return dqkv
+
+
+def masked_loss_grad(pred: torch.Tensor, target: torch.Tensor, mask: Optional[torch.Tensor],
+                     weights: Optional[torch.Tensor], *, l1: bool = False, grad_scale: float = 1.0,
+                     dbias: Optional[torch.Tensor] = None):
+    """Returns (dy fp32 like pred, loss_sum fp64 [B]): see ``d3_masked_loss_grad``."""
+    pred, target = _f32c(pred, "pred"), _f32c(target, "target")
+    B, dc, H, W = pred.shape
+    dy = torch.empty_like(pred)
+    loss_sum = torch.zeros((B,), dtype=torch.float64, device=pred.device)
+    _lib.check(_lib.lib().d3_masked_loss_grad(pred.data_ptr(), target.data_ptr(), _ptr(mask), _ptr(weights), B, dc, H * W,
+                                              int(l1), grad_scale, dy.data_ptr(), loss_sum.data_ptr(), _ptr(dbias),
+                                              _stream()))
+    return dy, loss_sum
+
+
+def linear_small_bwd(x: torch.Tensor, w: Optional[torch.Tensor], dy: torch.Tensor, *, act_in: int = 0,
+                     dw: Optional[torch.Tensor] = None, db: Optional[torch.Tensor] = None, want_dx: bool = True):
+    """Backward of ``linear_small`` (y = act_in(x) W^T + b): accumulates dw / db, returns dx (or None)."""
+    n, K = x.shape
+    rows = dy.shape[1]
+    dx = torch.empty_like(x) if want_dx else None
+    _lib.check(_lib.lib().d3_linear_small_bwd(x.data_ptr(), n, K, act_in, _ptr(w), rows, dy.data_ptr(), _ptr(dw), _ptr(db),
+                                              _ptr(dx), 0, _stream()))
+    return dx
+
+
+def sumsq(g: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _lib.check(_lib.lib().d3_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream()))
+    return out
+
+
+def adamw_step(p, g, m, v, *, p16=None, n16: int = 0, lr: float, beta1: float = 0.9, beta2: float = 0.999,
+               eps: float = 1e-8, weight_decay: float = 0.01, step: int, sumsq_buf=None, inv_loss_scale: float = 1.0,
+               max_norm: float = 0.0, norm_out=None) -> None:
+    _lib.check(_lib.lib().d3_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), _ptr(p16), n16,
+                                        _dt(p16) if p16 is not None else 0, lr, beta1, beta2, eps, weight_decay, step,
+                                        _ptr(sumsq_buf), inv_loss_scale, max_norm, _ptr(norm_out), _stream()))
+
+
+def cast_f32_to_16(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _lib.check(_lib.lib().d3_cast_f32_to_16(x.data_ptr(), out.data_ptr(), x.numel(), _dt(out), _stream()))
+    return out
+
+
+def gather_add(src: torch.Tensor, ia: torch.Tensor, ib: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _lib.check(_lib.lib().d3_gather_add(src.data_ptr(), ia.data_ptr(), ib.data_ptr(), out.data_ptr(), out.numel(), _stream()))
+    return out
+
+
+def pack_taps16(w: torch.Tensor, col0: int, Cin: int, tap_map, out: torch.Tensor) -> torch.Tensor:
+    """out[ci, j, co] (16-bit) = w[co, col0 + tap_map[j]*Cin + ci] (0 where tap_map[j] < 0); w fp32 [Cout, Ktot]."""
+    Cout = w.shape[0]
+    tm = (C.c_int32 * len(tap_map))(*tap_map)
+    _lib.check(_lib.lib().d3_pack_taps16(w.data_ptr(), w.stride(0), col0, Cin, Cout, tm, len(tap_map), out.data_ptr(),
+                                         _dt(out), _stream()))
+    return out

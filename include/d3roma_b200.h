@@ -396,6 +396,88 @@ int d3_transpose_pad16(const void* in, int N, int C, int in_pitch, void* out, in
 int d3_conv1x1_nchw_small(const float* x, int B, int Cin, int Cout, int64_t HW, const float* w, const float* bias,
                           float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training step: backward pass, loss and optimizer of /root/reference/train.py:157-538
+ * (`accelerator.backward(loss)` :455, `clip_grad_norm_` :518, `optimizer.step()` :524 over torch.optim.AdamW :862).
+ * The data gradient of a convolution is a convolution with transposed weights and runs on d3_conv2d_igemm (weights
+ * re-packed by d3_pack_taps16); the entry points below are what autograd / the optimizer add to the forward kernels.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* Weight gradient of a 3x3 (padding 1, stride 1 or 2) or 1x1 convolution - replaces the weight half of
+ * aten::convolution_backward:   dw[co][col0 + tap*Cin + ci] += sum_{b,y,x} dy[b,y,x,co] * x[b, s*y+kh-1, s*x+kw-1, ci]
+ * (the [Cout][taps*Cin] layout of the forward weight packs, in fp32, ACCUMULATED: zero it first). */
+typedef struct d3_wgrad_params {
+  const void* x;       /* 16-bit NHWC [B,H,W,Cin]: the conv's input, pixel pitch x_pitch                  */
+  int32_t B, H, W;     /* INPUT spatial size                                                               */
+  int32_t Cin;         /* multiple of 64                                                                   */
+  int32_t x_pitch;
+  const void* dy;      /* 16-bit NHWC [B,H/stride,W/stride,Cout]: gradient w.r.t. the conv's output        */
+  int32_t Cout;        /* multiple of 128                                                                  */
+  int32_t dy_pitch;
+  int32_t ksize;       /* 3 or 1                                                                           */
+  int32_t stride;      /* 1, or 2 (ksize 3 only)                                                           */
+  float* dw;           /* fp32 [Cout][dw_pitch]                                                            */
+  int64_t dw_pitch;    /* row pitch of dw in elements (multiple of 4)                                      */
+  int32_t dw_col0;     /* first column of this conv's block inside the row (multiple of 4)                 */
+  int32_t dtype;       /* D3_DTYPE_BF16 / D3_DTYPE_F16                                                     */
+} d3_wgrad_params;
+int d3_conv2d_wgrad(const d3_wgrad_params* p, void* stream);
+
+/* Backward of d3_groupnorm_silu (native_group_norm_backward + silu_backward) over the virtual concat of two sources:
+ * dy = gradient w.r.t. the dense output; dx (dense, C1 + C2 channels) = gradient w.r.t. the concatenated input
+ * (+ `addend`, e.g. the residual branch's gradient); dgamma / dbeta fp32 [C] are ACCUMULATED; `colsum` (optional, fp32
+ * rows `colsum_bstride` elements apart, accumulated; stride 0 = all samples into one row) receives the per-(sample,
+ * channel) sums of dx - the bias / time-embedding gradient of the conv that produced the input.  workspace: d3_groupnorm_bwd_workspace_bytes(B, C1 + C2) bytes. */
+size_t d3_groupnorm_bwd_workspace_bytes(int B, int C);
+int d3_groupnorm_silu_bwd(const void* x1, int C1, int p1, const double* stats1, const void* x2, int C2, int p2,
+                          const double* stats2, const float* gamma, const float* beta, int B, int HW, int groups,
+                          float eps, int apply_silu, const void* dy, int pdy, const void* addend, int padd, void* dx,
+                          int pdx, float* dgamma, float* dbeta, float* colsum, int64_t colsum_bstride, float* workspace,
+                          int dtype, void* stream);
+/* out[b * out_bstride + c] += sum over pixels of x[b,p,c] (bias gradients; out_bstride 0 sums over the batch too); out = a + b; backward of the nearest-2x upsample
+ * (2x2 block sums of a [B,2H,2W,C] tensor, + optional addend). */
+int d3_colsum_nhwc16(const void* x, int pitch, int B, int HW, int C, float* out, int64_t out_bstride, int dtype,
+                     void* stream);
+int d3_add_nhwc16(const void* a, int pa, const void* b, int pb, void* out, int po, int64_t npix, int C, int dtype,
+                  void* stream);
+int d3_sumpool2x_nhwc16(const void* in, int pin, const void* addend, int padd, void* out, int pout, int B, int H, int W,
+                        int C, int dtype, void* stream);
+/* Backward of d3_conv_out_fused (conv_norm_out + SiLU + conv_out): dy fp32 NCHW [B,dc,H,W] -> da = gradient w.r.t.
+ * SiLU(GroupNorm(h)) as 16-bit NHWC [B,H,W,128] (feed it to d3_groupnorm_silu_bwd), dw fp32 [dc][9][128] accumulated. */
+int d3_conv_out_bwd(const void* h, int pitch, const double* stats, const float* gamma, const float* beta, const float* w,
+                    const float* dy, int B, int H, int W, int dc, float eps, void* da, int pda, float* dw, int dtype,
+                    void* stream);
+/* Backward of d3_attention_hd8: dq | dk | dv in the layout of the QKV tensor.  workspace:
+ * d3_attention_hd8_bwd_workspace_bytes(B, N, C) bytes. */
+size_t d3_attention_hd8_bwd_workspace_bytes(int B, int N, int C);
+int d3_attention_hd8_bwd(const void* qkv, int pitch, const void* o, int opitch, const void* d_o, int dopitch, int B, int N,
+                         int C, void* dqkv, int dpitch, float* workspace, int dtype, void* stream);
+/* The loss of train.py:322-417: network_loss = loss_fn(pred * mask, target * mask) (MSE, or L1 when l1 != 0; mask fp32
+ * [B,1,H,W] or NULL), loss = mean(network_loss * weights[b]).  loss_sum[b] (fp64, accumulated) = sum of network_loss over
+ * sample b; dy = grad_scale * weights[b] * d network_loss / d pred (grad_scale = loss_scale / (B*dc*plane));
+ * dbias[d] (optional, accumulated) = sum of dy over channel d (conv_out's bias gradient). */
+int d3_masked_loss_grad(const float* pred, const float* target, const float* mask, const float* weights, int B, int dc,
+                        int64_t plane, int l1, float grad_scale, float* dy, double* loss_sum, float* dbias, void* stream);
+/* Backward of d3_linear_small, y = act_in(x) W^T: dw [rows][K] and db [rows] accumulated (dw NULL: skip),
+ * dx [n_rows][K] = (dy W) * act_in'(x) (dx NULL: skip; accumulate_dx: add to dx). */
+int d3_linear_small_bwd(const float* x, int n_rows, int K, int act_in, const float* w, int rows, const float* dy,
+                        float* dw, float* db, float* dx, int accumulate_dx, void* stream);
+/* Optimizer (torch.optim.AdamW semantics, train.py:862; clip_grad_norm_ :518): out += sum g^2 (fp64);  one fused AdamW
+ * step over a flat parameter buffer - gradients are multiplied by inv_loss_scale and by min(1, max_norm / (norm + 1e-6))
+ * with norm = sqrt(*sumsq) * inv_loss_scale (sumsq NULL or max_norm <= 0: no clipping); the first n16 parameters are
+ * also written as 16-bit (the tensor-core weight packs); norm_out (optional) receives the gradient norm. */
+int d3_sumsq(const float* g, int64_t n, double* out, void* stream);
+int d3_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, void* p16, int64_t n16, int dtype16, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, const double* sumsq,
+                  float inv_loss_scale, float max_norm, float* norm_out, void* stream);
+int d3_cast_f32_to_16(const float* x, void* out, int64_t n, int dtype16, void* stream);
+/* out[i] = src[ia[i]] + (ib[i] >= 0 ? src[ib[i]] : 0): the merged per-channel biases the forward kernels read. */
+int d3_gather_add(const float* src, const int32_t* ia, const int32_t* ib, float* out, int n, void* stream);
+/* Data-gradient weight packs: out[ci][j][co] (16-bit) = tap_map[j] >= 0 ? w[co][col0 + tap_map[j]*Cin + ci] : 0
+ * (flipped taps for a stride-1 conv, the phase sub-sets of a stride-2 conv, the plain transpose for 1x1). */
+int d3_pack_taps16(const float* w, int64_t w_pitch, int col0, int Cin, int Cout, const int32_t* tap_map, int n_out_taps,
+                   void* out, int dtype16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

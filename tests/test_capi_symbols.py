@@ -38,7 +38,8 @@ def test_struct_layouts_match_header():
     """Field order of the ctypes mirrors == field order in the header structs."""
     from d3roma_b200 import _lib
     text = (ROOT / "include" / "d3roma_b200.h").read_text()
-    for cname, cls in (("d3_conv_params", _lib.ConvParams), ("d3_ddim_coeffs", _lib.DDIMCoeffs),
+    for cname, cls in (("d3_conv_params", _lib.ConvParams), ("d3_wgrad_params", _lib.WgradParams),
+                       ("d3_ddim_coeffs", _lib.DDIMCoeffs),
                        ("d3_ddpm_coeffs", _lib.DDPMCoeffs), ("d3_guidance_params", _lib.GuidanceParams)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), text, flags=re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
