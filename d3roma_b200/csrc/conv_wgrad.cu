@@ -51,7 +51,6 @@ struct WgArgs {
   float* dw;
   long long dw_pitch;
   int sc_off2;      // stride 2: x pitch (element offset of the odd-column parity plane)
-  int variant;      // D3_DEV builds: descriptor experiments
 };
 
 // MN-major SWIZZLE_128B shared-memory matrix descriptor: 64 MN elements (128 B) contiguous, 8 K rows 128 B apart,
@@ -193,6 +192,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // 16 pixels = two 8-row K groups = 2048 B further into every box
+            // (validated on B200: leading byte offset = distance between the 64-channel boxes, stride byte offset =
+            // distance between 8-pixel row groups; the swapped assignment gives wrong sums)
             const uint64_t adesc = make_sw128_mnmajor_desc(sA + k * 2048, kBoxBytes, 1024);
             const uint64_t bdesc = make_sw128_mnmajor_desc(sB + k * 2048, kBoxBytes, 1024);
             umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (t != w.t0 || k != 0) ? 1u : 0u);

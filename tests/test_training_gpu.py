@@ -1,0 +1,281 @@
+"""GPU parity of the training-step kernels: every backward / optimizer kernel against the torch restatement
+of the same op (tests/_emulated_train_ops.py, autograd where a derivative is involved), then the whole backward pass and
+whole optimisation steps of ``UNetTrainer`` against autograd / AdamW on the oracle UNet (oracle/train_ref.py)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.bfloat16, torch.float16]
+
+
+def _ops():
+    from d3roma_b200 import ops
+    return ops
+
+
+def _rel(got, want):
+    return float((got.float() - want.float()).abs().max()) / (float(want.float().abs().max()) + 1e-20)
+
+
+def _rand(shape, dtype, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen, device="cuda") * scale).to(dtype)
+
+
+def _quad_stats(x):
+    """fp64 [B, C/4, 2] sum / sum of squares per 4-channel quad, as the conv epilogues produce them."""
+    B, H, W, C = x.shape
+    v = x.double().view(B, H * W, C // 4, 4)
+    return torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1).contiguous()
+
+
+WGRAD_CASES = [
+    # B, H, W, Cin, Cout, ksize, stride
+    (2, 16, 24, 128, 128, 3, 1),
+    (1, 8, 8, 64, 128, 1, 1),
+    (2, 16, 16, 256, 128, 3, 1),
+    (2, 16, 16, 128, 256, 3, 2),
+    (1, 24, 40, 384, 256, 1, 1),
+    (2, 12, 20, 512, 512, 3, 1),
+    (3, 32, 32, 128, 128, 3, 1),
+    (2, 6, 10, 256, 256, 3, 1),
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_conv_wgrad(case, dtype):
+    from tests import _emulated_train_ops as E
+    ops = _ops()
+    B, H, W, Cin, Cout, k, s = case
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = _rand((B, H, W, Cin), dtype, g)
+    dy = _rand((B, H // s, W // s, Cout), dtype, g)
+    K = k * k * Cin
+    dw = torch.zeros((Cout, K + 64), dtype=torch.float32, device="cuda")
+    ops.conv2d_wgrad(x, dy, dw, ksize=k, stride=s, col0=64)
+    want = torch.zeros_like(dw)
+    E.conv2d_wgrad(x, dy, want, ksize=k, stride=s, col0=64)
+    assert float(dw[:, :64].abs().max()) == 0.0
+    err = _rel(dw, want)
+    assert err < 2e-3, (case, err)
+    # accumulation: a second call adds
+    ops.conv2d_wgrad(x, dy, dw, ksize=k, stride=s, col0=64)
+    assert _rel(dw, 2 * want) < 2e-3
+
+
+def test_conv_wgrad_pitched_operands():
+    """x and dy as channel slices of wider buffers (the concat halves of the up blocks)."""
+    from tests import _emulated_train_ops as E
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    xb = _rand((2, 16, 16, 384), torch.bfloat16, g)
+    dyb = _rand((2, 16, 16, 256), torch.bfloat16, g)
+    x, dy = xb[..., 128:384], dyb[..., :128]
+    dw = torch.zeros((128, 256), dtype=torch.float32, device="cuda")
+    ops.conv2d_wgrad(x, dy, dw, ksize=1)
+    want = torch.zeros_like(dw)
+    E.conv2d_wgrad(x.contiguous(), dy.contiguous(), want, ksize=1)
+    assert _rel(dw, want) < 2e-3
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C1,C2,silu", [(128, 0, True), (256, 128, True), (512, 0, False), (512, 512, True), (256, 0, True)])
+def test_groupnorm_silu_bwd(C1, C2, silu, dtype):
+    from tests import _emulated_train_ops as E
+    ops = _ops()
+    B, H, W = 2, 12, 20
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x1 = _rand((B, H, W, C1), dtype, g) + 0.3
+    x2 = (_rand((B, H, W, C2), dtype, g, 2.0) - 0.5) if C2 else None
+    C = C1 + C2
+    gamma = torch.rand(C, generator=g, device="cuda") + 0.5
+    beta = torch.randn(C, generator=g, device="cuda") * 0.3
+    dy = _rand((B, H, W, C), dtype, g)
+    addend = _rand((B, H, W, C), dtype, g) if C2 == 0 else None
+    st1, st2 = _quad_stats(x1), (_quad_stats(x2) if C2 else None)
+    dga, dbe = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    cs = torch.zeros((B, C + 8), device="cuda")
+    dx = ops.groupnorm_silu_bwd(x1, st1, gamma, beta, dy, x2=x2, stats2=st2, silu=silu, addend=addend, dgamma=dga,
+                                dbeta=dbe, colsum=cs[:, 8:])
+    wga, wbe, wcs = torch.zeros_like(dga), torch.zeros_like(dbe), torch.zeros((B, C), device="cuda")
+    want = E.groupnorm_silu_bwd(x1.float(), None, gamma, beta, dy.float(), x2=None if x2 is None else x2.float(), silu=silu,
+                                addend=None if addend is None else addend.float(), dgamma=wga, dbeta=wbe, colsum=wcs)
+    tol = 2e-2 if dtype == torch.bfloat16 else 4e-3
+    assert _rel(dx, want) < tol, _rel(dx, want)
+    assert _rel(dga, wga) < 5e-3 and _rel(dbe, wbe) < 5e-3, (_rel(dga, wga), _rel(dbe, wbe))
+    assert _rel(cs[:, 8:], wcs) < 2e-2
+    assert float(cs[:, :8].abs().max()) == 0.0
+
+
+def test_colsum_add_sumpool():
+    from tests import _emulated_train_ops as E
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for dtype in DTYPES:
+        x = _rand((3, 10, 12, 1536), dtype, g)
+        out2, out1 = torch.zeros((3, 1536), device="cuda"), torch.zeros(1536, device="cuda")
+        ops.colsum_nhwc16(x, out2)
+        ops.colsum_nhwc16(x, out1)
+        assert _rel(out2, x.float().sum((1, 2))) < 1e-4 and _rel(out1, x.float().sum((0, 1, 2))) < 1e-4
+        a, b = _rand((2, 8, 8, 384), dtype, g), _rand((2, 8, 8, 384), dtype, g)
+        assert torch.equal(ops.add_nhwc16(a[..., 128:], b[..., :256]), E.add_nhwc16(a[..., 128:], b[..., :256]))
+        u = _rand((2, 16, 24, 128), dtype, g)
+        ad = _rand((2, 8, 12, 128), dtype, g)
+        assert _rel(ops.sumpool2x_nhwc16(u, addend=ad), E.sumpool2x_nhwc16(u, addend=ad)) < 1e-2
+        assert torch.equal(ops.sumpool2x_nhwc16(ops.upsample_nearest2x(ad)).float(), (4 * ad.float()).to(dtype).float())
+
+
+@pytest.mark.parametrize("dc", [1, 3])
+def test_conv_out_bwd(dc):
+    from tests import _emulated_train_ops as E
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, H, W = 2, 20, 28
+    h = _rand((B, H, W, 128), torch.bfloat16, g) + 0.2
+    gamma = torch.rand(128, generator=g, device="cuda") + 0.5
+    beta = torch.randn(128, generator=g, device="cuda") * 0.3
+    w = torch.randn((dc, 9, 128), generator=g, device="cuda") * 0.1
+    dy = torch.randn((B, dc, H, W), generator=g, device="cuda")
+    dw = torch.zeros_like(w)
+    da = ops.conv_out_bwd(h, _quad_stats(h), gamma, beta, w, dy, dw)
+    wdw = torch.zeros_like(w)
+    wda = E.conv_out_bwd(h.float(), None, gamma, beta, w, dy, wdw)
+    assert _rel(da, wda) < 1e-2, _rel(da, wda)
+    assert _rel(dw, wdw) < 2e-3, _rel(dw, wdw)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("hw", [(12, 20), (6, 10), (17, 30)])
+def test_attention_hd8_bwd(hw, dtype):
+    from tests import _emulated_train_ops as E
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(6)
+    B, C = 2, 512
+    qkv = _rand((B, *hw, 3 * C), dtype, g)
+    d_o = _rand((B, *hw, C), dtype, g)
+    o = ops.attention_hd8(qkv, C)
+    dqkv = ops.attention_hd8_bwd(qkv, o, d_o)
+    want = E.attention_hd8_bwd(qkv.float(), None, d_o.float())
+    tol = 2e-2 if dtype == torch.bfloat16 else 5e-3
+    assert _rel(dqkv, want) < tol, _rel(dqkv, want)
+
+
+def test_loss_linear_optimizer_kernels():
+    from tests import _emulated_train_ops as E
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, dc, H, W = 3, 3, 20, 24
+    pred, tgt = torch.randn((B, dc, H, W), generator=g, device="cuda"), torch.randn((B, dc, H, W), generator=g, device="cuda")
+    mask = (torch.rand((B, 1, H, W), generator=g, device="cuda") > 0.3).float()
+    wts = torch.rand(B, generator=g, device="cuda") + 0.5
+    for l1 in (False, True):
+        db, wdb = torch.zeros(dc, device="cuda"), torch.zeros(dc, device="cuda")
+        dy, ls = ops.masked_loss_grad(pred, tgt, mask, wts, l1=l1, grad_scale=0.37, dbias=db)
+        wdy, wls = E.masked_loss_grad(pred, tgt, mask, wts, l1=l1, grad_scale=0.37, dbias=wdb)
+        assert _rel(dy, wdy) < 1e-6 and _rel(ls, wls) < 1e-6 and _rel(db, wdb) < 1e-4
+    dy, ls = ops.masked_loss_grad(pred, tgt, None, None)
+    assert _rel(dy, 2 * (pred - tgt)) < 1e-6
+    # small Linear backward
+    x, w = torch.randn((5, 512), generator=g, device="cuda"), torch.randn((640, 512), generator=g, device="cuda") * 0.05
+    dyl = torch.randn((5, 640), generator=g, device="cuda")
+    for act in (0, 1):
+        dw, db = torch.zeros_like(w), torch.zeros(640, device="cuda")
+        wdw, wdb = torch.zeros_like(w), torch.zeros(640, device="cuda")
+        dx = ops.linear_small_bwd(x, w, dyl, act_in=act, dw=dw, db=db)
+        wdx = E.linear_small_bwd(x, w, dyl, act_in=act, dw=wdw, db=wdb)
+        assert _rel(dx, wdx) < 1e-4 and _rel(dw, wdw) < 1e-4 and _rel(db, wdb) < 1e-5
+    # AdamW + clipping + 16-bit mirror
+    n = 100_000
+    p, gr = torch.randn(n, generator=g, device="cuda"), torch.randn(n, generator=g, device="cuda") * 3
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    p2, m2, v2 = p.clone(), m.clone(), v.clone()
+    p16, p16b = torch.zeros(4096, dtype=torch.bfloat16, device="cuda"), torch.zeros(4096, dtype=torch.bfloat16, device="cuda")
+    for step in (1, 2, 3):
+        ss, norm = torch.zeros(1, dtype=torch.float64, device="cuda"), torch.zeros(1, device="cuda")
+        ops.sumsq(gr, ss)
+        kw = dict(lr=1e-2, step=step, sumsq_buf=ss, inv_loss_scale=0.5, max_norm=1.0, n16=4096)
+        ops.adamw_step(p, gr, m, v, p16=p16, norm_out=norm, **kw)
+        E.adamw_step(p2, gr, m2, v2, p16=p16b, **kw)
+        assert abs(float(norm) - float(gr.double().norm()) * 0.5) < 1e-3 * float(norm)
+    assert _rel(p, p2) < 1e-5 and _rel(v, v2) < 1e-4 and torch.equal(p16, p[:4096].to(torch.bfloat16))
+    # transposed weight packs
+    wm = torch.randn((256, 9 * 128 + 64), generator=g, device="cuda")
+    for tm in ([8 - j for j in range(9)], [-1, 4, 5, -1], [0]):
+        out = torch.zeros((128, len(tm) * 256), dtype=torch.float16, device="cuda")
+        want = torch.zeros_like(out)
+        ops.pack_taps16(wm, 64, 128, tm, out)
+        E.pack_taps16(wm, 64, 128, tm, want)
+        assert torch.equal(out, want)
+
+
+def _setup(dc, cin, B, H, W, dtype, seed=0, loss_scale=1.0, **kw):
+    import d3roma_b200.training as T
+    from oracle.unet_ref import make_unet
+    ref = make_unet(cin, dc, seed=seed, sample_size=(H, W)).cuda()
+    tr = T.UNetTrainer(in_channels=cin, out_channels=dc, compute_dtype=dtype, loss_scale=loss_scale, device="cuda", **kw)
+    tr.load_state_dict(ref.state_dict())
+    return ref, tr
+
+
+@pytest.mark.parametrize("dtype,loss_scale", [("bf16", 1.0), ("fp16", 4096.0)])
+def test_backward_matches_autograd(dtype, loss_scale):
+    from oracle import schedulers_ref as S, train_ref
+    from tests.test_training_host import _inputs
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    B, H, W, dc, cin = 2, 64, 96, 1, 8
+    ref, tr = _setup(dc, cin, B, H, W, dtype, loss_scale=loss_scale)
+    clean, cond, noise, t, mask, w = (x.cuda() for x in _inputs(B, H, W, dc, cin - dc))
+    ac = torch.cumprod(1 - S.make_betas("squaredcos_cap_v2", 128), 0).cuda()
+    noisy = S.add_noise(clean, noise, t, ac)
+    loss_ref, out_ref, grads_ref = train_ref.loss_and_grads(ref, noisy, cond, t, clean, mask, w, "mse")
+    ops = _ops()
+    tr.zero_grad()
+    pred = tr.forward(noisy, cond, t)
+    assert float((pred - out_ref).abs().max()) < (2e-2 if dtype == "bf16" else 1e-2)
+    dy, loss_sum = ops.masked_loss_grad(pred, clean, mask, w, grad_scale=loss_scale / pred.numel(), dbias=tr.G("out.bias"))
+    tr.backward(dy, bias_grad_done=True)
+    got = tr.grad_dict()
+    gmax = max(float(g.abs().max()) for g in grads_ref.values())
+    num = den = 0.0
+    worst = ("", 0.0)
+    for k, g in grads_ref.items():
+        a = got[k].cuda().double().flatten()
+        b = g.double().flatten()
+        num += float(((a - b) ** 2).sum())
+        den += float((b ** 2).sum())
+        if float(b.abs().max()) > 1e-4 * gmax:
+            cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
+            if 1 - cos > worst[1]:
+                worst = (k, 1 - cos)
+    rel_l2 = math.sqrt(num / den)
+    print(f"[{dtype}] whole-gradient relative L2 error {rel_l2:.3e}; worst per-tensor 1-cos {worst}")
+    assert rel_l2 < (6e-2 if dtype == "bf16" else 2e-2), rel_l2
+    assert worst[1] < (3e-2 if dtype == "bf16" else 1e-2), worst
+
+
+def test_train_steps_track_adamw_oracle():
+    """Five optimisation steps on a fixed batch: the loss falls and follows the fp32 AdamW oracle."""
+    from oracle import schedulers_ref as S, train_ref
+    from tests.test_training_host import _inputs
+    B, H, W, dc, cin = 2, 32, 64, 1, 8
+    ref, tr = _setup(dc, cin, B, H, W, "bf16", lr=2e-4, max_grad_norm=1.0)
+    opt = torch.optim.AdamW(ref.parameters(), lr=2e-4)
+    ac = torch.cumprod(1 - S.make_betas("squaredcos_cap_v2", 128), 0).cuda()
+
+    class Sched:
+        add_noise = staticmethod(lambda a, b, t: S.add_noise(a, b, t, ac))
+        get_velocity = staticmethod(lambda a, b, t: S.get_velocity(a, b, t, ac))
+
+    clean, cond, noise, t, mask, w = (x.cuda() for x in _inputs(B, H, W, dc, cin - dc, seed=3))
+    ours, theirs = [], []
+    for _ in range(5):
+        theirs.append(float(train_ref.train_step(ref, opt, clean, cond, noise, t, ac, mask, w, "sample", "mse", 1.0)[0]))
+        ours.append(float(tr.train_step(clean, cond, noise, t, Sched, mask=mask, weights=w, prediction_type="sample")))
+    print("loss ours", ours, "oracle", theirs)
+    assert ours[-1] < 0.7 * ours[0]
+    for a, b in zip(ours, theirs):
+        assert abs(a - b) < 0.1 * abs(b) + 1e-3, (ours, theirs)
