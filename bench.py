@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the D3RoMa denoising hot path (BASELINE.json metric: disparity maps/sec at 360x640, 10 DDIM steps).
 
-    python bench.py --gpus N --steps K --warmup W [--config c2|c1|c3|c4|c5] [--dtype fp16|bf16]
+    python bench.py --gpus N --steps K --warmup W [--config c2|c1|c3|c4|c5|ldm|train] [--dtype fp16|bf16]
     python bench.py --impl reference --steps K --warmup W     # the reference path on the host CPU cores (oracle port)
 
 One "step" = one pass of the hot path over one batch.  The default workload is BASELINE configs[1] ("c2"): the
@@ -653,6 +653,208 @@ def run_ldm_arm(args):
         dist.destroy_process_group()
 
 
+TRAIN_PAIRS = 16     # samples per GPU and optimisation step (reference default train_batch_size is 16 per device)
+
+
+def train_eager_baseline(dtype: str, B: int, hw, cin: int, n_steps: int):
+    """The same optimisation step under eager PyTorch (autograd + cuDNN / cuBLAS, autocast to ``dtype``, channels_last,
+    torch.optim.AdamW, clip_grad_norm_) on the oracle's torch.nn UNet, same GPU, this run."""
+    from oracle.unet_ref import make_unet
+    adt = torch.float16 if dtype == "fp16" else torch.bfloat16
+    dev = torch.device("cuda", torch.cuda.current_device())
+    try:
+        net = make_unet(cin, 1, seed=0, sample_size=hw).to(dev).to(memory_format=torch.channels_last)
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-4)
+        scaler = torch.amp.GradScaler("cuda", enabled=dtype == "fp16")
+        x = torch.randn(B, cin, *hw, device=dev).to(memory_format=torch.channels_last)
+        tgt = torch.randn(B, 1, *hw, device=dev)
+        t = torch.randint(0, 128, (B,), device=dev)
+
+        def step():
+            with torch.autocast("cuda", dtype=adt):
+                out = net(x, t)
+                out = out.sample if hasattr(out, "sample") else out
+            loss = torch.nn.functional.mse_loss(out.float(), tgt)
+            scaler.scale(loss).backward()
+            scaler.unscale_(opt)
+            torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+            scaler.step(opt)
+            scaler.update()
+            opt.zero_grad(set_to_none=True)
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n_steps
+        del net, opt, x
+        torch.cuda.empty_cache()
+        return {"ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "samples/s",
+                "what": f"eager PyTorch {torch.__version__} (autograd, cuDNN/cuBLAS, autocast {dtype}, channels_last, AdamW, "
+                        f"clip_grad_norm_) on the oracle's torch.nn UNet, batch {B}, same GPU, this run"}
+    except Exception as e:   # noqa: BLE001 - the baseline is informative; never let it take the bench line down
+        torch.cuda.empty_cache()
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+
+
+def run_train_arm(args):
+    """--config train: the reference's training step for the pixel-space model (train.py:157-538) -
+    add_noise, UNet forward with one timestep per sample, masked MSE loss, backward, gradient all-reduce across the GPUs
+    (DDP), clip_grad_norm_, AdamW - on 16 synthetic left+right+raw samples per GPU at 360x640 (padded 384x640)."""
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import d3roma_b200 as d
+    from d3roma_b200 import _lib, ops
+    from d3roma_b200.training import UNetTrainer
+    from d3roma_b200.weights import random_init_state_dict
+    dtype = args.dtype if args.dtype_given else "bf16"
+    B, (H, W) = TRAIN_PAIRS, (pad32(360), pad32(640))
+    tr = UNetTrainer(in_channels=8, out_channels=1, compute_dtype=dtype, lr=1e-4, max_grad_norm=1.0,
+                     loss_scale=65536.0 if dtype == "fp16" else 1.0, device=dev)
+    tr.load_state_dict(random_init_state_dict(8, 1, seed=0))
+    sched = d.MyDDPMScheduler.from_config(dict(num_train_timesteps=128, beta_schedule="squaredcos_cap_v2",
+                                               prediction_type="sample", clip_sample=True))
+    g = torch.Generator().manual_seed(100 + rank)
+    host = {"clean": torch.rand(B, 1, H, W, generator=g) * 2 - 1, "cond": torch.rand(B, 7, H, W, generator=g) * 2 - 1,
+            "noise": torch.randn(B, 1, H, W, generator=g), "mask": (torch.rand(B, 1, H, W, generator=g) > 0.1).float()}
+    host = {k: v.pin_memory() for k, v in host.items()}
+    t_host = torch.randint(0, 128, (B,), generator=g).pin_memory()
+    devt = {k: v.to(dev) for k, v in host.items()}
+    t_dev = t_host.to(dev)
+
+    def step(x, t):
+        return tr.train_step(x["clean"], x["cond"], x["noise"], t, sched, mask=x["mask"], prediction_type="sample",
+                             world_size=world)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warm = max(3, args.warmup)
+    losses = []
+    for _ in range(warm):
+        losses.append(step(devt, t_dev))
+    sync()
+    lib = _lib.lib()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    lib.d3_reset_launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        losses.append(step(devt, t_dev))
+    e1.record()
+    sync()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = int(lib.d3_launch_count())
+    tt = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    sec = float(tt.item())
+    value = world * B * args.steps / sec
+
+    def e2e_step():
+        x = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        return float(step(x, t_host.to(dev, non_blocking=True)).item())      # D2H read of the loss
+
+    e2e_step()
+    sync()
+    n_e2e = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        last_loss = e2e_step()
+    sync()
+    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * n_e2e / float(te.item())
+
+    if rank == 0:
+        def t_of(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        # phases of one step (CUDA events, after the timed region)
+        noisy = sched.add_noise(devt["clean"], devt["noise"], t_dev)
+        ms_fwd = t_of(lambda: tr.forward(noisy, devt["cond"], t_dev))
+        pred = tr.forward(noisy, devt["cond"], t_dev)
+        dy, _ = ops.masked_loss_grad(pred, devt["clean"], devt["mask"], None, grad_scale=tr.loss_scale / pred.numel())
+
+        def fb():
+            tr.zero_grad()
+            tr.forward(noisy, devt["cond"], t_dev)
+            tr.backward(dy)
+        ms_fb = t_of(fb)
+        ms_opt = t_of(lambda: tr.optimizer_step(1))
+        # dominant backward kernel timed alone: weight gradient of a 3x3 128->128 conv at the full resolution
+        adt = torch.float16 if dtype == "fp16" else torch.bfloat16
+        xa = torch.randn(B, H, W, 128, device=dev).to(adt)
+        ga = torch.randn(B, H, W, 128, device=dev).to(adt)
+        gw = torch.zeros(128, 9 * 128, device=dev)
+        ms_wg = t_of(lambda: ops.conv2d_wgrad(xa, ga, gw, ksize=3), reps=10)
+        flops = 2.0 * B * H * W * 9 * 128 * 128
+        peaks = load_peaks()
+        peak = float(peaks["tf_burst"])
+        unet_tflop = 3 * 1872.53e9 * B / 1e12    # forward + data gradients + weight gradients, per step and GPU
+        line = {
+            "metric": "training samples/sec at 360x640 (forward + backward + AdamW step)",
+            "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": dtype, "data": "synthetic",
+            "config": {"workload": "training step of the pixel-space denoiser (SURVEY 8 f4; reference train.py:157-538): "
+                                   f"left+right+raw variant, {B} samples per GPU at 360x640 (UNet at padded {H}x{W}), one "
+                                   "timestep per sample, masked MSE on x0 ('sample' prediction), clip_grad_norm_ 1.0, AdamW "
+                                   f"lr 1e-4, random-init UNet2DModel(8->1, 113.68 M params), {dtype} activations / "
+                                   "gradients with fp32 master weights and moments",
+                       "config": "train", "samples_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"data parallel x{world} (replicated weights, NCCL all-reduce of the flat fp32 "
+                                      "gradient buffer)",
+                       "l2": "per-step working set (>1 GB per activation at batch 16) exceeds the 126 MB L2; no explicit flush"},
+            "ms_forward": ms_fwd, "ms_forward_backward": ms_fb, "ms_optimizer": ms_opt,
+            "loss_first_last": [float(losses[0]), float(losses[-1])],
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "samples/s",
+                    "h2d_bytes_per_step": sum(v.numel() for v in host.values()) * 4 + t_host.numel() * 8,
+                    "d2h_bytes_per_step": 8, "steps": n_e2e, "last_loss": last_loss,
+                    "api": "d3roma_b200.training.UNetTrainer.train_step (pinned host batch in, loss out)"},
+            "gpu_launches": launches,
+            "unet": {"algorithmic_tflops": unet_tflop * args.steps / sec, "peak": float(peaks["tf_sust"]),
+                     "frac_of_sustained_peak": unet_tflop * args.steps / sec / float(peaks["tf_sust"]),
+                     "gflop_per_sample_step": 3 * 1872.53, "peak_source": "measured sustained (cuBLAS bf16 inside a long step)"},
+            "roofline": {"bound": "tensor", "kernel": f"conv_wgrad_kernel (split-K, MN-major TMA operands) 3x3 128->128 @{B}x{H}x{W}",
+                         "achieved": flops / (ms_wg * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": flops / (ms_wg * 1e-3) / 1e12 / peak, "traffic": None, "flops_per_launch": flops,
+                         "ms_per_launch": ms_wg,
+                         "peak_source": ("measured" if peaks["src"] == "measured" else "fallback") + " burst (kernel timed alone)"},
+        }
+        if not args.no_gpu_baseline:
+            del xa, ga
+            torch.cuda.empty_cache()
+            line["gpu_eager_baseline"] = train_eager_baseline(dtype, B, (H, W), 8, 2)
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 _JSON_OUT = None
 
 
@@ -674,17 +876,24 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="d3roma_b200", choices=["d3roma_b200", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS) + ["ldm"])
-    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS) + ["ldm", "train"])
+    ap.add_argument("--dtype", default=None, choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.dtype_given = args.dtype is not None      # --config train defaults to bf16, everything else to fp16
+    if args.dtype is None:
+        args.dtype = "fp16"
     if args.impl == "reference":
         run_reference_arm(args)
     elif args.config == "ldm":
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device (the d3roma_b200 path has no CPU fallback)")
         run_ldm_arm(args)
+    elif args.config == "train":
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the d3roma_b200 path has no CPU fallback)")
+        run_train_arm(args)
     else:
         run_gpu_arm(args)
 
