@@ -16,6 +16,16 @@
 // the fp32 gradient with vector reductions (red.global.add.v4.f32); the pixel range is split over the CTAs (split-K)
 // so that a layer always fills the 148 SMs.
 //
+// 3x3 stride-1 layers run the HALO form (the kernel is L2-bandwidth bound: per 64-pixel K block the generic form pulls
+// 48 KB through the L2 for 128 x 256 x 64 MACs, 14.7 GB for a 128 -> 128 layer at 16 x 384 x 640, which is what capped
+// it at 620 TFLOP/s): the pixel tile is 8 x 8, so one tile row is exactly one 1024-byte swizzle atom, and the x operand
+// of a (kw, channel block) pair is loaded ONCE as a 10-row halo block [64 ch, 8, 10] (10 KB); the three kh taps are the
+// same block seen through descriptors whose 64-channel atoms start 0, 1 and 2 rows in (leading byte offset = 1024 B =
+// one tile row: overlapping atoms of one N = 192 operand), i.e. ONE tcgen05.mma per K step covers three filter taps.
+// A work item owns two such groups (384 fp32 accumulator columns): 36 KB of L2 traffic per K block for
+// 128 x 384 x 64 MACs - half the bytes per MAC - and no half-empty N tile (128 -> 128: 3 items of 384 columns instead
+// of 4 x 256 + 1 x 128).
+//
 // One persistent CTA per SM: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue;
 // 4-stage smem ring of {dy 16 KB, x 32 KB}; two 256-column fp32 accumulators in TMEM (the epilogue of one work item runs
 // under the MMAs of the next).
@@ -37,6 +47,10 @@ constexpr uint32_t kBoxBytes = 64 * 128;          // one [64 ch x 64 px] box
 constexpr uint32_t kWgABytes = 2 * kBoxBytes;     // 128 output channels
 constexpr uint32_t kWgBBytes = 4 * kBoxBytes;     // up to 256 (tap, ci) columns
 constexpr uint32_t kWgStageBytes = kWgABytes + kWgBBytes;
+// halo form: 8 x 8 pixel tiles, x as (8 + 2) rows of 8 pixels per (kw, channel block) group, two groups per stage
+constexpr int kHaloStages = 5;
+constexpr uint32_t kHaloBytes = 10 * 8 * 128;
+constexpr uint32_t kHaloStageBytes = kWgABytes + 2 * kHaloBytes;
 
 struct WgArgs {
   int B, Ho, Wo;
@@ -51,6 +65,8 @@ struct WgArgs {
   float* dw;
   long long dw_pitch;
   int sc_off2;      // stride 2: x pitch (element offset of the odd-column parity plane)
+  int Cin;
+  int G;            // halo form: 3 * cbPerTap (kw, channel block) groups, two per work item
 };
 
 // MN-major SWIZZLE_128B shared-memory matrix descriptor: 64 MN elements (128 B) contiguous, 8 K rows 128 B apart,
@@ -89,14 +105,17 @@ D3_DEVINL WgWork wg_decode(const WgArgs& a, int work) {
   return w;
 }
 
-template <int DT>
+template <int DT, bool HALO>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgArgs a) {
+  constexpr int kStages = HALO ? kHaloStages : kWgStages;
+  constexpr uint32_t kStageBytes = HALO ? kHaloStageBytes : kWgStageBytes;
+  constexpr int kAccs = HALO ? 1 : 2;   // halo form: one 384-column accumulator set; generic: two of 256 columns
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
-  uint64_t* empty_bar = full_bar + kWgStages;
-  uint64_t* tfull_bar = empty_bar + kWgStages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -108,7 +127,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     tma_prefetch_desc(&tmX);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kWgStages; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -136,7 +155,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       for (int work = blockIdx.x; work < a.numWork; work += gridDim.x) {
         const WgWork w = wg_decode(a, work);
         const int u0 = w.n * 4;
-        const int cnt = min(4, a.U - u0);
+        const int cnt = HALO ? min(2, a.G - w.n * 2) : min(4, a.U - u0);
         for (int t = w.t0; t < w.t1; ++t) {
           int p = t;
           const int tw = p % a.tilesW;
@@ -145,11 +164,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           const int b = p / a.tilesH;
           const int h0 = th * a.TH, w0 = tw * a.TW;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sA = smem + stage * kWgStageBytes;
+          uint8_t* sA = smem + stage * kStageBytes;
           uint8_t* sB = sA + kWgABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], (2 + cnt) * kBoxBytes);
+          mbar_arrive_expect_tx(&full_bar[stage], 2 * kBoxBytes + cnt * (HALO ? kHaloBytes : kBoxBytes));
           tma_load_4d(sA, &tmDY, &full_bar[stage], w.m * 128, w0, h0, b);
           tma_load_4d(sA + kBoxBytes, &tmDY, &full_bar[stage], w.m * 128 + 64, w0, h0, b);
+          if constexpr (HALO) {
+            for (int g = 0; g < cnt; ++g) {
+              const int hg = w.n * 2 + g;              // group = (kw, channel block), kw-major
+              const int kw = hg / a.cbPerTap;
+              const int cb = hg - kw * a.cbPerTap;
+              tma_load_4d(sB + g * kHaloBytes, &tmX, &full_bar[stage], cb * 64, w0 + kw - 1, h0 - 1, b);
+            }
+          } else
           for (int j = 0; j < cnt; ++j) {
             const int u = u0 + j;
             const int tap = u / a.cbPerTap;
@@ -163,7 +190,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                           dh & 1, h0 + (dh >> 1), b);
             }
           }
-          if (++stage == kWgStages) {
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
@@ -179,16 +206,28 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       uint32_t acc_phase = 0;
       for (int work = blockIdx.x; work < a.numWork; work += gridDim.x) {
         const WgWork w = wg_decode(a, work);
-        const int cnt = min(4, a.U - w.n * 4);
-        const uint32_t idesc = make_idesc_16bit_mn(128, 64 * cnt, DT == kBF16);
+        const int cnt = HALO ? min(2, a.G - w.n * 2) : min(4, a.U - w.n * 4);
+        const uint32_t idesc = make_idesc_16bit_mn(128, HALO ? 192 : 64 * cnt, DT == kBF16);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int t = w.t0; t < w.t1; ++t) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sA = smem_u32(smem + stage * kWgStageBytes);
+          const uint32_t sA = smem_u32(smem + stage * kStageBytes);
           const uint32_t sB = sA + kWgABytes;
+          if constexpr (HALO) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // K step k = tile rows 2k, 2k + 1 (16 pixels); the three 64-channel atoms of the x operand (kh = 0, 1, 2)
+              // start one tile row = one 1024-byte swizzle atom apart inside the halo block
+              const uint64_t adesc = make_sw128_mnmajor_desc(sA + k * 2048, kBoxBytes, 1024);
+              for (int g = 0; g < cnt; ++g) {
+                const uint64_t bdesc = make_sw128_mnmajor_desc(sB + g * kHaloBytes + k * 2048, 1024, 1024);
+                umma_bf16_ss(d_tmem + g * 192, adesc, bdesc, idesc, (t != w.t0 || k != 0) ? 1u : 0u);
+              }
+            }
+          } else
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // 16 pixels = two 8-row K groups = 2048 B further into every box
@@ -199,13 +238,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
             umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (t != w.t0 || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == kWgStages) {
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
         umma_commit(&tfull_bar[acc]);
-        acc ^= 1;
+        if (++acc == kAccs) acc = 0;
         if (acc == 0) acc_phase ^= 1;
       }
     }
@@ -217,16 +256,31 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     uint32_t acc_phase = 0;
     for (int work = blockIdx.x; work < a.numWork; work += gridDim.x) {
       const WgWork w = wg_decode(a, work);
-      const int cnt = min(4, a.U - w.n * 4);
-      float* dst = a.dw + (size_t)(w.m * 128 + row) * a.dw_pitch + (size_t)w.n * 256;
+      const int cnt = HALO ? min(2, a.G - w.n * 2) : min(4, a.U - w.n * 4);
+      float* drow = a.dw + (size_t)(w.m * 128 + row) * a.dw_pitch;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if constexpr (HALO) {
 #pragma unroll 1
-      for (int c = 0; c < 2 * cnt; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * 256 + c * 32, v);
-        tmem_ld_wait();
-        if (w.t1 > w.t0) {
+        for (int c = 0; c < 6 * cnt; ++c) {   // 32-column chunks: group g = c / 6, kh = (c % 6) / 2, half = c & 1
+          const int g = c / 6, kh = (c % 6) >> 1, half = c & 1;
+          const int hg = w.n * 2 + g;
+          const int kw = hg / a.cbPerTap;
+          const int cb = hg - kw * a.cbPerTap;
+          float* dst = drow + (size_t)(kh * 3 + kw) * a.Cin + cb * 64 + half * 32;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + g * 192 + kh * 64 + half * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) red_add_v4(dst + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      } else {
+        float* dst = drow + (size_t)w.n * 256;
+#pragma unroll 1
+        for (int c = 0; c < 2 * cnt; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((q * 32) << 16) + acc * 256 + c * 32, v);
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j) red_add_v4(dst + c * 32 + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
@@ -234,7 +288,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1;
+      if (++acc == kAccs) acc = 0;
       if (acc == 0) acc_phase ^= 1;
     }
   }
@@ -289,9 +343,17 @@ extern "C" int d3_conv2d_wgrad(const d3_wgrad_params* p, void* stream_) {
   a.pad = p->ksize / 2;
   a.cbPerTap = p->Cin / 64;
   a.U = taps * a.cbPerTap;
-  a.nTilesN = ceil_div(a.U, 4);
+  a.Cin = p->Cin;
+  a.G = 3 * a.cbPerTap;
+  // halo form for every 3x3 stride-1 layer (D3_WGRAD_HALO=0 routes them to the generic per-tap form; both are
+  // parity-tested)
+  static int want_halo = -1;
+  if (want_halo < 0) { const char* e = getenv("D3_WGRAD_HALO"); want_halo = e ? atoi(e) : 1; }
+  const bool halo = want_halo && p->ksize == 3 && p->stride == 1;
+  a.nTilesN = halo ? ceil_div(a.G, 2) : ceil_div(a.U, 4);
   a.nTilesM = p->Cout / 128;
-  choose_tile64(Ho, Wo, &a.TH, &a.TW);
+  if (halo) a.TH = a.TW = 8;
+  else choose_tile64(Ho, Wo, &a.TH, &a.TW);
   a.tilesH = ceil_div(Ho, a.TH);
   a.tilesW = ceil_div(Wo, a.TW);
   a.pixTiles = p->B * a.tilesH * a.tilesW;
@@ -324,7 +386,7 @@ extern "C" int d3_conv2d_wgrad(const d3_wgrad_params* p, void* stream_) {
   if (p->stride == 1) {
     uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
     uint64_t str[3] = {(uint64_t)p->x_pitch * 2, (uint64_t)p->W * p->x_pitch * 2, (uint64_t)p->H * p->W * p->x_pitch * 2};
-    uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
+    uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)(halo ? a.TH + 2 : a.TH), 1};
     rc = make_tmap_16bit(f16, &tmX, p->x, 4, dims, str, box);
   } else {
     // parity-split view: (pw*pitch + c, w/2, h parity, h/2, b)
@@ -336,16 +398,19 @@ extern "C" int d3_conv2d_wgrad(const d3_wgrad_params* p, void* stream_) {
   }
   if (rc) return set_error(D3_ERR_CUDA, "wgrad: tensor map x encode failed (%d)", rc);
 
-  const size_t smem = kWgStages * kWgStageBytes + 1024 + 256;
+  const size_t smem = (halo ? kHaloStages * kHaloStageBytes : kWgStages * kWgStageBytes) + 1024 + 256;
   const int grid = a.numWork < num_sms() ? a.numWork : num_sms();
   cudaError_t le;
-  if (f16) {
-    if ((le = ensure_dyn_smem(reinterpret_cast<const void*>(conv_wgrad_kernel<kF16>), smem)) == cudaSuccess)
-      le = launch_pdl(conv_wgrad_kernel<kF16>, dim3(grid), dim3(kWgThreads), smem, stream, tmDY, tmX, a);
-  } else {
-    if ((le = ensure_dyn_smem(reinterpret_cast<const void*>(conv_wgrad_kernel<kBF16>), smem)) == cudaSuccess)
-      le = launch_pdl(conv_wgrad_kernel<kBF16>, dim3(grid), dim3(kWgThreads), smem, stream, tmDY, tmX, a);
-  }
+#define D3_WG_LAUNCH(DT, H)                                                                                     \
+  do {                                                                                                          \
+    if ((le = ensure_dyn_smem(reinterpret_cast<const void*>(conv_wgrad_kernel<DT, H>), smem)) == cudaSuccess)   \
+      le = launch_pdl(conv_wgrad_kernel<DT, H>, dim3(grid), dim3(kWgThreads), smem, stream, tmDY, tmX, a);      \
+  } while (0)
+  if (f16 && halo) D3_WG_LAUNCH(kF16, true);
+  else if (f16) D3_WG_LAUNCH(kF16, false);
+  else if (halo) D3_WG_LAUNCH(kBF16, true);
+  else D3_WG_LAUNCH(kBF16, false);
+#undef D3_WG_LAUNCH
   D3_CHECK_CUDA(le);
   D3_LAUNCH_CHECK();
   return D3_OK;
