@@ -171,8 +171,9 @@ def _declare(lib: C.CDLL) -> None:
         # training step
         "d3_conv2d_wgrad": (i32, [C.POINTER(WgradParams), vp]),
         "d3_groupnorm_bwd_workspace_bytes": (C.c_size_t, [i32, i32]),
-        "d3_groupnorm_silu_bwd": (i32, [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, f32, i32, vp, i32, vp,
-                                        i32, vp, i32, vp, vp, vp, i64, vp, i32, vp]),
+        "d3_groupnorm_silu_bwd": (i32, [vp, i32, i32, vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, f32, i32, vp, i32,
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_int), i32, vp, i32, vp, vp, vp, i64, i32, vp,
+                                        i32, vp]),
         "d3_colsum_nhwc16": (i32, [vp, i32, i32, i32, i32, vp, i64, i32, vp]),
         "d3_add_nhwc16": (i32, [vp, i32, vp, i32, vp, i32, i64, i32, i32, vp]),
         "d3_sumpool2x_nhwc16": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),

@@ -57,6 +57,7 @@ D3_DEVINL uint4 pack8(const float (&f)[8]) {
 }
 
 constexpr int kBwThreads = 256;
+constexpr int kMaxAddends = 3;
 
 // ----------------------------------------------------------------------------------------------------------------
 // GroupNorm (+SiLU) backward
@@ -69,14 +70,16 @@ struct GnBwdArgs {
   const float* gamma;
   const float* beta;
   const uint16_t* dy;
-  const uint16_t* addend;
+  const uint16_t* addend[kMaxAddends];   // optional tensors added to dx (gradients that reached the input on other paths)
+  int padd[kMaxAddends];
   uint16_t* dx;
   float* dgamma;
   float* dbeta;
   float* colsum;
   long long colsum_bstride;   // elements between the rows of consecutive samples (0: all samples add into one row)
   float* ws;   // [B][C][2]: sum over pixels of dz, of dz * xhat
-  int C1, C2, p1, p2, pdy, padd, pdx;
+  int C1, C2, p1, p2, pdy, pdx;
+  int colsum_C;   // leading channels whose sums are wanted
   int HW, groups;
   float eps;
   int silu;
@@ -106,9 +109,11 @@ D3_DEVINL void gn_group_moments(const GnBwdArgs& a, int b, float* s_mean, float*
   }
 }
 
-// pass 1: ws[b][c] += (sum_p dz, sum_p dz * xhat),  dz = dy * silu'(z),  z = xhat * gamma + beta
+// pass 1: ws[b][c] += (sum_p dz, sum_p dz * xhat),  dz = dy * silu'(z),  z = xhat * gamma + beta.
+// Per-thread constants are folded so that two blocks of 256 threads fit an SM without spills:
+//   z = zs * x + zb (zs = rstd * gamma, zb = beta - mean * zs);  sum dz * xhat = rstd * sum dz * x - mean * rstd * sum dz.
 template <int DT>
-__global__ void __launch_bounds__(kBwThreads) gn_bwd_reduce_kernel(const GnBwdArgs a) {
+__global__ void __launch_bounds__(kBwThreads, 2) gn_bwd_reduce_kernel(const GnBwdArgs a) {
   pdl_prologue();
   __shared__ float s_mean[32];
   __shared__ float s_rstd[32];
@@ -122,15 +127,13 @@ __global__ void __launch_bounds__(kBwThreads) gn_bwd_reduce_kernel(const GnBwdAr
   const int vec = threadIdx.x % nvec;
   const int prow = threadIdx.x / nvec;
   const int pstride = blockDim.x / nvec;
-  float r[8], mr[8], ga[8], be[8];
+  float zs[8], zb[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c = vec * 8 + k;
     const int g = c / cpg;
-    r[k] = s_rstd[g];
-    mr[k] = s_mean[g] * s_rstd[g];
-    ga[k] = a.gamma[c];
-    be[k] = a.beta[c];
+    zs[k] = a.gamma[c] * s_rstd[g];
+    zb[k] = a.beta[c] - s_mean[g] * zs[k];
   }
   const int pix0 = blockIdx.x * a.pix_per_block;
   int npix = a.HW - pix0;
@@ -139,18 +142,18 @@ __global__ void __launch_bounds__(kBwThreads) gn_bwd_reduce_kernel(const GnBwdAr
   const uint16_t* src = (vec < nvec1) ? a.x1 + base_pix * a.p1 + vec * 8 : a.x2 + base_pix * a.p2 + (vec - nvec1) * 8;
   const int sp = (vec < nvec1) ? a.p1 : a.p2;
   const uint16_t* gy = a.dy + base_pix * a.pdy + vec * 8;
-  float s1[8], s2[8];
+  float s1[8], s2[8];   // sum dz, sum dz * x
 #pragma unroll
   for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
-  constexpr int U = 8;
+  constexpr int U = 4;
   for (int p0 = prow; p0 < npix; p0 += pstride * U) {
     uint4 xv[U], gv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int p = p0 + u * pstride;
       if (p < npix) {
-        xv[u] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)p * sp));
-        gv[u] = __ldg(reinterpret_cast<const uint4*>(gy + (size_t)p * a.pdy));
+        xv[u] = __ldcs(reinterpret_cast<const uint4*>(src + (size_t)p * sp));
+        gv[u] = __ldcs(reinterpret_cast<const uint4*>(gy + (size_t)p * a.pdy));
       }
     }
 #pragma unroll
@@ -162,11 +165,10 @@ __global__ void __launch_bounds__(kBwThreads) gn_bwd_reduce_kernel(const GnBwdAr
         unpack8<DT>(gv[u], g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float xh = fmaf(x[k], r[k], -mr[k]);
           float dz = g[k];
-          if (a.silu) dz *= dsilu_fast(fmaf(xh, ga[k], be[k]));
+          if (a.silu) dz *= dsilu_fast(fmaf(x[k], zs[k], zb[k]));
           s1[k] += dz;
-          s2[k] = fmaf(dz, xh, s2[k]);
+          s2[k] = fmaf(dz, x[k], s2[k]);
         }
       }
     }
@@ -188,15 +190,18 @@ __global__ void __launch_bounds__(kBwThreads) gn_bwd_reduce_kernel(const GnBwdAr
     float* w = a.ws + ((size_t)b * C + vec * 8) * 2;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
+      const int g = (vec * 8 + k) / cpg;
+      const float r = s_rstd[g], mr = s_mean[g] * r;
       atomicAdd(w + 2 * k, s1[k]);
-      atomicAdd(w + 2 * k + 1, s2[k]);
+      atomicAdd(w + 2 * k + 1, fmaf(r, s2[k], -mr * s1[k]));   // sum dz * xhat
     }
   }
 }
 
-// pass 2: dx = rstd * (gamma * dz - mean_g(gamma * dz) - xhat * mean_g(gamma * dz * xhat)) (+ addend)
+// pass 2: dx = rstd * (gamma * dz - mean_g(gamma * dz) - xhat * mean_g(gamma * dz * xhat)) (+ addends)
+//            = zs * dz + e * x + f   with  e = kd * rstd,  f = kb - kd * mean * rstd  (kb, kd: the two group means, scaled)
 template <int DT>
-__global__ void __launch_bounds__(kBwThreads) gn_bwd_apply_kernel(const GnBwdArgs a) {
+__global__ void __launch_bounds__(kBwThreads, 2) gn_bwd_apply_kernel(const GnBwdArgs a) {
   pdl_prologue();
   __shared__ float s_mean[32];
   __shared__ float s_rstd[32];
@@ -234,17 +239,16 @@ __global__ void __launch_bounds__(kBwThreads) gn_bwd_apply_kernel(const GnBwdArg
       atomicAdd(a.dgamma + c, a.ws[((size_t)b * C + c) * 2 + 1]);
     }
   }
-  float r[8], mr[8], ga[8], be[8], kb[8], kd[8];
+  float zs[8], zb[8], ce[8], cf[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c = vec * 8 + k;
     const int g = c / cpg;
-    r[k] = s_rstd[g];
-    mr[k] = s_mean[g] * s_rstd[g];
-    ga[k] = a.gamma[c];
-    be[k] = a.beta[c];
-    kb[k] = s_b[g];
-    kd[k] = s_d[g];
+    const float r = s_rstd[g], mr = s_mean[g] * r;
+    zs[k] = a.gamma[c] * r;
+    zb[k] = a.beta[c] - s_mean[g] * zs[k];
+    ce[k] = s_d[g] * r;
+    cf[k] = s_b[g] - s_d[g] * mr;
   }
   const int pix0 = blockIdx.x * a.pix_per_block;
   int npix = a.HW - pix0;
@@ -253,21 +257,26 @@ __global__ void __launch_bounds__(kBwThreads) gn_bwd_apply_kernel(const GnBwdArg
   const uint16_t* src = (vec < nvec1) ? a.x1 + base_pix * a.p1 + vec * 8 : a.x2 + base_pix * a.p2 + (vec - nvec1) * 8;
   const int sp = (vec < nvec1) ? a.p1 : a.p2;
   const uint16_t* gy = a.dy + base_pix * a.pdy + vec * 8;
-  const uint16_t* ad = a.addend ? a.addend + base_pix * a.padd + vec * 8 : nullptr;
+  const uint16_t* ad[kMaxAddends];
+#pragma unroll
+  for (int i = 0; i < kMaxAddends; ++i) ad[i] = a.addend[i] ? a.addend[i] + base_pix * a.padd[i] + vec * 8 : nullptr;
   uint16_t* dst = a.dx + base_pix * a.pdx + vec * 8;
+  const bool want_cs = a.colsum != nullptr && vec * 8 < a.colsum_C;
   float cs[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) cs[k] = 0.f;
-  constexpr int U = 4;
+  constexpr int U = 2;
   for (int p0 = prow; p0 < npix; p0 += pstride * U) {
-    uint4 xv[U], gv[U], av[U];
+    uint4 xv[U], gv[U], av[U][kMaxAddends];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int p = p0 + u * pstride;
       if (p < npix) {
-        xv[u] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)p * sp));
-        gv[u] = __ldg(reinterpret_cast<const uint4*>(gy + (size_t)p * a.pdy));
-        if (ad) av[u] = __ldg(reinterpret_cast<const uint4*>(ad + (size_t)p * a.padd));
+        xv[u] = __ldcs(reinterpret_cast<const uint4*>(src + (size_t)p * sp));
+        gv[u] = __ldcs(reinterpret_cast<const uint4*>(gy + (size_t)p * a.pdy));
+#pragma unroll
+        for (int i = 0; i < kMaxAddends; ++i)
+          if (ad[i]) av[u][i] = __ldcs(reinterpret_cast<const uint4*>(ad[i] + (size_t)p * a.padd[i]));
       }
     }
 #pragma unroll
@@ -279,20 +288,22 @@ __global__ void __launch_bounds__(kBwThreads) gn_bwd_apply_kernel(const GnBwdArg
         unpack8<DT>(gv[u], g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float xh = fmaf(x[k], r[k], -mr[k]);
           float dz = g[k];
-          if (a.silu) dz *= dsilu_fast(fmaf(xh, ga[k], be[k]));
-          o[k] = fmaf(r[k] * ga[k], dz, fmaf(kd[k], xh, kb[k]));
+          if (a.silu) dz *= dsilu_fast(fmaf(x[k], zs[k], zb[k]));
+          o[k] = fmaf(zs[k], dz, fmaf(ce[k], x[k], cf[k]));
         }
-        if (ad) {
-          float e[8];
-          unpack8<DT>(av[u], e);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] += e[k];
+        for (int i = 0; i < kMaxAddends; ++i) {
+          if (ad[i]) {
+            float e[8];
+            unpack8<DT>(av[u][i], e);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] += e[k];
+          }
         }
         const uint4 pk = pack8<DT>(o);
         *reinterpret_cast<uint4*>(dst + (size_t)p * a.pdx) = pk;
-        if (a.colsum != nullptr) {
+        if (want_cs) {
           float rr[8];
           unpack8<DT>(pk, rr);   // sums of the values as stored
 #pragma unroll
@@ -305,7 +316,7 @@ __global__ void __launch_bounds__(kBwThreads) gn_bwd_apply_kernel(const GnBwdArg
 #pragma unroll
     for (int k = 0; k < 8; ++k) s_red[threadIdx.x * 8 + k] = cs[k];
     __syncthreads();
-    if (prow == 0) {
+    if (prow == 0 && want_cs) {
       for (int rr = 1; rr < pstride; ++rr) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) cs[k] += s_red[(rr * nvec + vec) * 8 + k];
@@ -735,9 +746,10 @@ extern "C" size_t d3_groupnorm_bwd_workspace_bytes(int B, int C) { return (size_
 
 extern "C" int d3_groupnorm_silu_bwd(const void* x1, int C1, int p1, const double* stats1, const void* x2, int C2, int p2,
                                      const double* stats2, const float* gamma, const float* beta, int B, int HW,
-                                     int groups, float eps, int apply_silu, const void* dy, int pdy, const void* addend,
-                                     int padd, void* dx, int pdx, float* dgamma, float* dbeta, float* colsum,
-                                     int64_t colsum_bstride, float* workspace, int dtype, void* stream_) {
+                                     int groups, float eps, int apply_silu, const void* dy, int pdy,
+                                     const void* const* addends, const int* addend_pitches, int n_addends, void* dx,
+                                     int pdx, float* dgamma, float* dbeta, float* colsum, int64_t colsum_bstride,
+                                     int colsum_channels, float* workspace, int dtype, void* stream_) {
   using namespace d3;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int C = C1 + C2;
@@ -747,9 +759,11 @@ extern "C" int d3_groupnorm_silu_bwd(const void* x1, int C1, int p1, const doubl
   D3_REQUIRE(dtype == D3_DTYPE_BF16 || dtype == D3_DTYPE_F16, "groupnorm_bwd: 16-bit dtypes only (got %d)", dtype);
   D3_REQUIRE(C <= 1024 && C % groups == 0 && (C / groups) % 4 == 0 && groups <= 32, "groupnorm_bwd: unsupported C=%d groups=%d",
              C, groups);
-  D3_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && p1 % 8 == 0 && (C2 == 0 || p2 % 8 == 0) && pdy % 8 == 0 && pdx % 8 == 0 &&
-                 (addend == nullptr || padd % 8 == 0),
+  D3_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && p1 % 8 == 0 && (C2 == 0 || p2 % 8 == 0) && pdy % 8 == 0 && pdx % 8 == 0,
              "groupnorm_bwd: channel counts / pitches must be multiples of 8");
+  D3_REQUIRE(n_addends >= 0 && n_addends <= kMaxAddends && (n_addends == 0 || (addends && addend_pitches)),
+             "groupnorm_bwd: at most %d addends", kMaxAddends);
+  D3_REQUIRE(colsum_channels >= 0 && colsum_channels <= C && colsum_channels % 8 == 0, "groupnorm_bwd: bad colsum_channels");
   GnBwdArgs a{};
   a.x1 = static_cast<const uint16_t*>(x1);
   a.x2 = static_cast<const uint16_t*>(x2);
@@ -758,14 +772,19 @@ extern "C" int d3_groupnorm_silu_bwd(const void* x1, int C1, int p1, const doubl
   a.gamma = gamma;
   a.beta = beta;
   a.dy = static_cast<const uint16_t*>(dy);
-  a.addend = static_cast<const uint16_t*>(addend);
+  for (int i = 0; i < n_addends; ++i) {
+    D3_REQUIRE(addends[i] != nullptr && addend_pitches[i] % 8 == 0, "groupnorm_bwd: bad addend %d", i);
+    a.addend[i] = static_cast<const uint16_t*>(addends[i]);
+    a.padd[i] = addend_pitches[i];
+  }
+  a.colsum_C = colsum_channels > 0 ? colsum_channels : C;
   a.dx = static_cast<uint16_t*>(dx);
   a.dgamma = dgamma;
   a.dbeta = dbeta;
   a.colsum = colsum;
   a.colsum_bstride = colsum_bstride;
   a.ws = workspace;
-  a.C1 = C1; a.C2 = C2; a.p1 = p1; a.p2 = p2; a.pdy = pdy; a.padd = padd; a.pdx = pdx;
+  a.C1 = C1; a.C2 = C2; a.p1 = p1; a.p2 = p2; a.pdy = pdy; a.pdx = pdx;
   a.HW = HW;
   a.groups = groups;
   a.eps = eps;

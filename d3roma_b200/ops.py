@@ -744,12 +744,11 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, *, ksize: 
 
 def groupnorm_silu_bwd(x1: torch.Tensor, stats1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, dy: torch.Tensor, *,
                        x2: Optional[torch.Tensor] = None, stats2: Optional[torch.Tensor] = None, silu: bool = True,
-                       groups: int = 32, eps: float = 1e-5, addend: Optional[torch.Tensor] = None,
-                       dgamma: Optional[torch.Tensor] = None, dbeta: Optional[torch.Tensor] = None,
-                       colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Backward of ``groupnorm_silu``: returns dx over the concatenated channels (+ ``addend``); ``dgamma`` / ``dbeta``
-    (fp32 [C]) are accumulated; ``colsum`` (fp32 [B, C] view with contiguous channels, or [C] = summed over the batch)
-    receives the per-channel sums of dx."""
+                       groups: int = 32, eps: float = 1e-5, addends=(), dgamma: Optional[torch.Tensor] = None,
+                       dbeta: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Backward of ``groupnorm_silu``: returns dx over the concatenated channels (+ up to 3 ``addends``, dense NHWC
+    tensors of dx's shape); ``dgamma`` / ``dbeta`` (fp32 [C]) are accumulated; ``colsum`` (fp32 [B, Cs] view with
+    contiguous channels, or [Cs] = summed over the batch) receives the per-channel sums of dx over its first Cs channels."""
     _check_nhwc(x1, "x1")
     _check_nhwc(dy, "dy")
     B, H, W, C1 = x1.shape
@@ -757,18 +756,28 @@ def groupnorm_silu_bwd(x1: torch.Tensor, stats1: torch.Tensor, gamma: torch.Tens
     Ct = C1 + C2
     if dy.shape != (B, H, W, Ct):
         raise ValueError("groupnorm_silu_bwd: dy must cover the concatenated channels")
+    addends = [t for t in addends if t is not None]
+    if len(addends) > 3:
+        raise ValueError("groupnorm_silu_bwd: at most 3 addends")
+    for t in addends:
+        _check_nhwc(t, "addend")
+        if t.shape != (B, H, W, Ct) or t.dtype != x1.dtype:
+            raise ValueError("groupnorm_silu_bwd: addends must have dx's shape and dtype")
     dx = torch.empty((B, H, W, Ct), dtype=x1.dtype, device=x1.device)
     ws = torch.empty((B * Ct * 2,), dtype=torch.float32, device=x1.device)
-    cs_ptr, cs_stride = None, 0
+    cs_ptr, cs_stride, cs_ch = None, 0, 0
     if colsum is not None:
-        if colsum.dtype != torch.float32 or colsum.stride(-1) != 1 or colsum.shape[-1] != Ct:
-            raise ValueError("groupnorm_silu_bwd: colsum must be fp32 [..., C] with contiguous channels")
-        cs_ptr, cs_stride = colsum.data_ptr(), (colsum.stride(0) if colsum.dim() == 2 else 0)
+        if colsum.dtype != torch.float32 or colsum.stride(-1) != 1 or colsum.shape[-1] > Ct or colsum.shape[-1] % 8:
+            raise ValueError("groupnorm_silu_bwd: colsum must be fp32 [..., Cs <= C] with contiguous channels")
+        cs_ptr, cs_stride, cs_ch = colsum.data_ptr(), (colsum.stride(0) if colsum.dim() == 2 else 0), colsum.shape[-1]
+    n = len(addends)
+    ptrs = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in addends])
+    pitches = (C.c_int * max(n, 1))(*[t.stride(2) for t in addends])
     _lib.check(_lib.lib().d3_groupnorm_silu_bwd(
         x1.data_ptr(), C1, x1.stride(2), stats1.data_ptr(), _ptr(x2), C2, x2.stride(2) if x2 is not None else 0,
         _ptr(stats2), gamma.data_ptr(), beta.data_ptr(), B, H * W, groups, eps, int(silu), dy.data_ptr(), dy.stride(2),
-        _ptr(addend), addend.stride(2) if addend is not None else 0, dx.data_ptr(), dx.stride(2), _ptr(dgamma),
-        _ptr(dbeta), cs_ptr, cs_stride, ws.data_ptr(), _dt(x1), _stream()))
+        ptrs, pitches, n, dx.data_ptr(), dx.stride(2), _ptr(dgamma), _ptr(dbeta), cs_ptr, cs_stride, cs_ch,
+        ws.data_ptr(), _dt(x1), _stream()))
     return dx
 
 

@@ -57,6 +57,7 @@ class UNetTrainer:
         self._loaded = False
         self._tape: List = []
         self._grads: Dict[int, tuple] = {}
+        self._consumed, self._bias_req = set(), {}
 
     # ------------------------------------------------------------------ parameter layout
     def _build_layout(self):
@@ -320,29 +321,54 @@ class UNetTrainer:
             ops.pack_taps16(self.P(name), col0, cin, tm, self._dg[key])
 
     # ------------------------------------------------------------------ gradient bookkeeping
+    # Every forward tensor collects the gradient contributions of its consumers as a list of pending 16-bit tensors
+    # (channel-slice views allowed).  They are summed as late as possible: a GroupNorm backward folds up to three of them
+    # into its own pass, a data-gradient conv one (its `residual` input); only what exceeds that costs an add kernel.
     def _put(self, t, g):
-        self._grads[id(t)] = (t, g)
-
-    def _take(self, t):
-        e = self._grads.pop(id(t), None)
-        return None if e is None else e[1]
+        self._grads[id(t)] = (t, [g])
 
     def _acc(self, t, g):
-        e = self._grads.get(id(t))
-        self._grads[id(t)] = (t, g if e is None else ops.add_nhwc16(e[1], g))
+        self._grads.setdefault(id(t), (t, []))[1].append(g)
+
+    def _pending(self, t, keep: int):
+        e = self._grads.pop(id(t), None)
+        lst = [] if e is None else e[1]
+        while len(lst) > keep:
+            b, a = lst.pop(), lst.pop()
+            lst.append(ops.add_nhwc16(a, b))
+        return lst
+
+    def _take(self, t):
+        lst = self._pending(t, 1)
+        return lst[0] if lst else None
+
+    def _consume(self, t) -> bool:
+        """Mark a forward tensor as consumed; True for its FIRST consumer (whose backward therefore runs last)."""
+        first = id(t) not in self._consumed
+        self._consumed.add(id(t))
+        return first
 
     # ------------------------------------------------------------------ forward pieces (each records its backward)
     def _gn(self, x1: _Act, gname: str, bname: str, x2: Optional[_Act] = None, silu: bool = True, colsum=None):
         g, b = self.P(gname), self.P(bname)
         a = ops.groupnorm_silu(x1.t, x1.stats, g, b, x2=None if x2 is None else x2.t,
                                stats2=None if x2 is None else x2.stats, silu=silu)
+        first = self._consume(x1.t)
+        if x2 is not None:
+            self._consume(x2.t)
+        # the first consumer's backward runs last: with a single source its dx (+ everything pending) IS the total
+        # gradient of x1, so the bias gradient of the conv that produced x1 (channel sums) is taken in the same pass
+        req = self._bias_req.get(id(x1.t)) if (first and x2 is None and colsum is None) else None
 
         def bwd():
             da = self._take(a)
-            addend = self._take(x1.t) if x2 is None else None
+            addends = self._pending(x1.t, 3) if x2 is None else ()
+            cs = colsum
+            if req is not None:
+                cs, req["done"] = req["bg"], True
             dx = ops.groupnorm_silu_bwd(x1.t, x1.stats, g, b, da, x2=None if x2 is None else x2.t,
-                                        stats2=None if x2 is None else x2.stats, silu=silu, addend=addend,
-                                        dgamma=self.G(gname), dbeta=self.G(bname), colsum=colsum)
+                                        stats2=None if x2 is None else x2.stats, silu=silu, addends=addends,
+                                        dgamma=self.G(gname), dbeta=self.G(bname), colsum=cs)
             if x2 is None:
                 self._put(x1.t, dx)
             else:
@@ -361,12 +387,18 @@ class UNetTrainer:
         sc = list(sc)
         out = ops.conv2d_igemm(x, w, bias, ksize=ksize, stride=stride, sc1=sc[0] if len(sc) > 0 else None,
                                sc2=sc[1] if len(sc) > 1 else None, residual=residual, stats=stats)
+        for t_ in (x, residual, *sc):
+            if t_ is not None:
+                self._consume(t_)
+        req = {"bg": bias_grad, "done": False}
+        if bias_grad is not None:
+            self._bias_req[id(out)] = req      # a GroupNorm that consumes `out` first may take the channel sums for us
 
         def bwd():
             dy = self._take(out)
             cin = x.shape[3]
             gw = self.G(wname)
-            if bias_grad is not None:
+            if bias_grad is not None and not req["done"]:
                 ops.colsum_nhwc16(dy, bias_grad)
             ops.conv2d_wgrad(x, dy, gw, ksize=ksize, stride=stride, col0=0)
             col = ksize * ksize * cin
@@ -416,6 +448,7 @@ class UNetTrainer:
         n = self._gn(h, a + ".gn.g", a + ".gn.b", silu=False)
         qkv = self._conv(n, a + ".wqkv", self.P(a + ".bqkv"), 1, B, want_stats=False, bias_grad=self.G(a + ".bqkv"))
         o = ops.attention_hd8(qkv.t, C)
+        self._consume(qkv.t)
 
         def bwd():
             d_o = self._take(o)
@@ -437,6 +470,7 @@ class UNetTrainer:
             raise ValueError(f"H and W must be multiples of 32 (got {H}x{Wd}); pad with InputPadder(divis_by=32)")
         dev = sample.device
         self._tape, self._grads = [], {}
+        self._consumed, self._bias_req = set(), {}
         need = B * 2 * 40000
         if self._arena is None or self._arena.buf.numel() < need or self._arena.buf.device != dev:
             self._arena = _StatsArena(dev, need)
@@ -483,6 +517,7 @@ class UNetTrainer:
                 p = f"up_blocks.{i}.upsamplers.0.conv"
                 src = h.t
                 u = ops.upsample_nearest2x(src)
+                self._consume(src)
 
                 def bwd(src=src, u=u):
                     du = self._take(u)
@@ -490,6 +525,7 @@ class UNetTrainer:
                 self._tape.append(bwd)
                 h = self._conv(u, p + ".w", self.P(p + ".b"), 3, B, bias_grad=self.G(p + ".b"))
         self._head = h
+        self._consume(h.t)
         return ops.conv_out_fused(h.t, h.stats, self.P("out.g"), self.P("out.b"), self.P("out.w"), self.P("out.bias"),
                                   self.out_channels)
 
@@ -510,6 +546,7 @@ class UNetTrainer:
         for fn in reversed(self._tape):
             fn()
         self._tape, self._grads, self._head = [], {}, None
+        self._consumed, self._bias_req = set(), {}
         # time path: rows = Linear(SiLU(emb)); emb = Linear(SiLU(a1)); a1 = Linear(e0)
         e0, a1, emb = self._time_saved
         d_emb = ops.linear_small_bwd(emb, self.P("temb.w"), self._d_rows, act_in=1, dw=self.G("temb.w"), db=self.G("temb.b"))

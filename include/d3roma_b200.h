@@ -425,15 +425,18 @@ int d3_conv2d_wgrad(const d3_wgrad_params* p, void* stream);
 
 /* Backward of d3_groupnorm_silu (native_group_norm_backward + silu_backward) over the virtual concat of two sources:
  * dy = gradient w.r.t. the dense output; dx (dense, C1 + C2 channels) = gradient w.r.t. the concatenated input
- * (+ `addend`, e.g. the residual branch's gradient); dgamma / dbeta fp32 [C] are ACCUMULATED; `colsum` (optional, fp32
+ * (+ up to 3 `addends`: dense 16-bit tensors of the same shape with their own pixel pitches - the gradients that reached
+ * the input over other paths, e.g. the residual branch); dgamma / dbeta fp32 [C] are ACCUMULATED; `colsum` (optional, fp32
  * rows `colsum_bstride` elements apart, accumulated; stride 0 = all samples into one row) receives the per-(sample,
- * channel) sums of dx - the bias / time-embedding gradient of the conv that produced the input.  workspace: d3_groupnorm_bwd_workspace_bytes(B, C1 + C2) bytes. */
+ * channel) sums of dx over the first `colsum_channels` channels (0 = all) - the bias / time-embedding gradient of the
+ * conv that produced the input.  workspace: d3_groupnorm_bwd_workspace_bytes(B, C1 + C2) bytes. */
 size_t d3_groupnorm_bwd_workspace_bytes(int B, int C);
 int d3_groupnorm_silu_bwd(const void* x1, int C1, int p1, const double* stats1, const void* x2, int C2, int p2,
                           const double* stats2, const float* gamma, const float* beta, int B, int HW, int groups,
-                          float eps, int apply_silu, const void* dy, int pdy, const void* addend, int padd, void* dx,
-                          int pdx, float* dgamma, float* dbeta, float* colsum, int64_t colsum_bstride, float* workspace,
-                          int dtype, void* stream);
+                          float eps, int apply_silu, const void* dy, int pdy, const void* const* addends,
+                          const int* addend_pitches, int n_addends, void* dx, int pdx, float* dgamma, float* dbeta,
+                          float* colsum, int64_t colsum_bstride, int colsum_channels, float* workspace, int dtype,
+                          void* stream);
 /* out[b * out_bstride + c] += sum over pixels of x[b,p,c] (bias gradients; out_bstride 0 sums over the batch too); out = a + b; backward of the nearest-2x upsample
  * (2x2 block sums of a [B,2H,2W,C] tensor, + optional addend). */
 int d3_colsum_nhwc16(const void* x, int pitch, int B, int HW, int C, float* out, int64_t out_bstride, int dtype,

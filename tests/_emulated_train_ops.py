@@ -26,21 +26,22 @@ def groupnorm_silu(x1, stats1, gamma, beta, *, x2=None, stats2=None, silu=True, 
     return _nhwc(y, x1.dtype)
 
 
-def groupnorm_silu_bwd(x1, stats1, gamma, beta, dy, *, x2=None, stats2=None, silu=True, groups=32, eps=1e-5, addend=None,
+def groupnorm_silu_bwd(x1, stats1, gamma, beta, dy, *, x2=None, stats2=None, silu=True, groups=32, eps=1e-5, addends=(),
                        dgamma=None, dbeta=None, colsum=None):
     cat = (x1 if x2 is None else torch.cat([x1, x2], -1)).float().detach().requires_grad_(True)
     g, b = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
     y = F.group_norm(cat.permute(0, 3, 1, 2), groups, g, b, eps)
     y = (F.silu(y) if silu else y).permute(0, 2, 3, 1)
     dx, dg, db = torch.autograd.grad(y, (cat, g, b), dy.float())
-    if addend is not None:
-        dx = dx + addend.float()
+    for t in addends:
+        if t is not None:
+            dx = dx + t.float()
     dx = dx.to(x1.dtype)
     if dgamma is not None:
         dgamma += dg
         dbeta += db
     if colsum is not None:
-        s = dx.float().sum(dim=(1, 2))
+        s = dx.float().sum(dim=(1, 2))[:, :colsum.shape[-1]]
         colsum += s if colsum.dim() == 2 else s.sum(0)
     return dx.contiguous()
 

@@ -94,15 +94,16 @@ def test_groupnorm_silu_bwd(C1, C2, silu, dtype):
     gamma = torch.rand(C, generator=g, device="cuda") + 0.5
     beta = torch.randn(C, generator=g, device="cuda") * 0.3
     dy = _rand((B, H, W, C), dtype, g)
-    addend = _rand((B, H, W, C), dtype, g) if C2 == 0 else None
+    addends = [_rand((B, H, W, C), dtype, g) for _ in range(3 if C1 == 128 else (1 if C2 == 0 else 0))]
     st1, st2 = _quad_stats(x1), (_quad_stats(x2) if C2 else None)
     dga, dbe = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
-    cs = torch.zeros((B, C + 8), device="cuda")
-    dx = ops.groupnorm_silu_bwd(x1, st1, gamma, beta, dy, x2=x2, stats2=st2, silu=silu, addend=addend, dgamma=dga,
+    Cs = C1                      # channel sums over the first source only (the concat case of the up blocks)
+    cs = torch.zeros((B, Cs + 8), device="cuda")
+    dx = ops.groupnorm_silu_bwd(x1, st1, gamma, beta, dy, x2=x2, stats2=st2, silu=silu, addends=addends, dgamma=dga,
                                 dbeta=dbe, colsum=cs[:, 8:])
-    wga, wbe, wcs = torch.zeros_like(dga), torch.zeros_like(dbe), torch.zeros((B, C), device="cuda")
+    wga, wbe, wcs = torch.zeros_like(dga), torch.zeros_like(dbe), torch.zeros((B, Cs), device="cuda")
     want = E.groupnorm_silu_bwd(x1.float(), None, gamma, beta, dy.float(), x2=None if x2 is None else x2.float(), silu=silu,
-                                addend=None if addend is None else addend.float(), dgamma=wga, dbeta=wbe, colsum=wcs)
+                                addends=[t.float() for t in addends], dgamma=wga, dbeta=wbe, colsum=wcs)
     tol = 2e-2 if dtype == torch.bfloat16 else 4e-3
     assert _rel(dx, want) < tol, _rel(dx, want)
     assert _rel(dga, wga) < 5e-3 and _rel(dbe, wbe) < 5e-3, (_rel(dga, wga), _rel(dbe, wbe))

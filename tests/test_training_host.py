@@ -102,3 +102,67 @@ def test_train_steps_match_adamw(trainer_mod):
         worst = max(worst, float((sd[k] - v).abs().max()))
     # three AdamW steps of size lr = 1e-3 each: parameters must agree far below one step
     assert worst < 2e-4, worst
+
+
+# ---------------------------------------------------------------------------------------------- data parallel (gloo)
+def _ddp_worker(rank, world, port, q):
+    import os
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from d3roma_b200 import training
+    for name in dir(E):
+        if not name.startswith("_") and callable(getattr(E, name)) and name != "math":
+            setattr(training.ops, name, getattr(E, name))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = _run_steps(training, lambda x: x[rank::world], world)
+    if rank == 0:
+        q.put({k: v.numpy() for k, v in out.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_steps(training, shard, world):
+    B, H, W, dc, cin = 2, 32, 32, 1, 8
+    ref = make_unet(cin, dc, seed=2, sample_size=(H, W))
+    tr = training.UNetTrainer(in_channels=cin, out_channels=dc, lr=1e-3, max_grad_norm=0.3, device="cpu")
+    tr._adt = torch.float32
+    tr.load_state_dict(ref.state_dict())
+    ac = torch.cumprod(1 - S.make_betas("squaredcos_cap_v2", 128), 0)
+
+    class Sched:
+        add_noise = staticmethod(lambda a, b, t: S.add_noise(a, b, t, ac))
+        get_velocity = staticmethod(lambda a, b, t: S.get_velocity(a, b, t, ac))
+
+    for step in range(2):
+        clean, cond, noise, t, mask, w = (shard(x) for x in _inputs(B, H, W, dc, cin - dc, seed=20 + step))
+        tr.train_step(clean, cond, noise, t, Sched, mask=mask, weights=w, prediction_type="epsilon", world_size=world)
+    sd = tr.state_dict()
+    keys = ["conv_in.weight", "mid_block.attentions.0.to_q.weight", "up_blocks.5.resnets.2.conv2.weight",
+            "down_blocks.2.resnets.0.conv_shortcut.weight", "time_embedding.linear_2.bias", "conv_out.bias"]
+    return {k: sd[k] for k in keys}
+
+
+def test_data_parallel_matches_global_batch(trainer_mod):
+    """world_size 2 over gloo: each rank takes every second sample, gradients are all-reduced and averaged before
+    clipping / AdamW - the parameters after two steps equal those of one process training on the whole batch."""
+    import socket
+    import torch.multiprocessing as mp
+    want = _run_steps(trainer_mod, lambda x: x, 1)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for k, v in want.items():
+        assert float(np.abs(got[k] - v.numpy()).max()) < 2e-5, k

@@ -1,27 +1,29 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel totals of the LAST `n` d3 launches
-(one eager UNet forward = 172 launches).  usage: python tools/summarize_launches.py file.csv [n_last]"""
+"""Developer tool: aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel.
+    python tools/summarize_launches.py launches.csv [runs_in_file] > profiles/xxx.txt"""
 import collections
 import csv
 import re
 import sys
 
 path = sys.argv[1]
-n_last = int(sys.argv[2]) if len(sys.argv) > 2 else 172
+runs = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 with open(path) as f:
     lines = [l for l in f if not l.startswith("==")]
-MINE = re.compile(r"igemm|gn_apply|attention_hd8|conv_out|conv_in_direct|im2col|time_embed|temb_project|upsample2x|d3::")
-rows = [r for r in csv.DictReader(lines) if MINE.search(r["Kernel Name"])]
-rows = rows[-n_last:]
-agg = collections.defaultdict(lambda: [0, 0.0])
-detail = collections.defaultdict(float)
-for r in rows:
-    name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "").replace("d3::<unnamed>::", "").replace("unnamed>::", "")
-    v = float(r["Metric Value"].replace(",", ""))
-    v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0}[r["Metric Unit"]]
-    agg[name][0] += 1
-    agg[name][1] += v
-    detail[(name, r["Grid Size"])] += v
-tot = sum(v[1] for v in agg.values())
-print(f"# {len(rows)} launches, total {tot:.3f} ms (cold-cache, serialised under ncu: compare SHARES)")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    print(f"{v[1]:8.3f} ms {100 * v[1] / tot:5.1f}%  x{v[0]:4d}  {k}")
+per = collections.defaultdict(lambda: [0, 0.0])
+for row in csv.DictReader(lines):
+    try:
+        t = float(row["Metric Value"].replace(",", ""))
+    except (ValueError, KeyError):
+        continue
+    unit = row["Metric Unit"]
+    t = t / 1e3 if unit == "ns" else (t * 1e3 if unit == "ms" else t)
+    name = row["Kernel Name"]
+    m = re.search(r"(?:d3::\(anonymous namespace\)::|d3::|at::native::|at::)?([A-Za-z_0-9]+)\s*(<[^>]*>)?\s*\(", name)
+    key = (m.group(1) + (m.group(2) or "")) if m else name[:60]
+    per[key][0] += 1
+    per[key][1] += t
+tot = sum(v[1] for v in per.values())
+print(f"{path}: per-kernel totals of the ncu launch list (gpu__time_duration.sum, --clock-control none), divided by {runs:g} runs")
+for k, v in sorted(per.items(), key=lambda kv: -kv[1][1])[:36]:
+    print(f"{v[1] / runs / 1e3:9.2f} ms {v[0] / runs:8.1f} launches {100 * v[1] / tot:5.1f}%  {k[:110]}")
+print(f"total {tot / runs / 1e3:.1f} ms")
