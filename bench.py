@@ -203,11 +203,52 @@ CPU_SAMPLE = ("bounded sample of BASELINE configs[1]: each timed step = 1 stereo
               "per timed step)")
 
 
+TRAIN_CPU_SAMPLE = ("bounded sample of the training workload: each timed step = ONE optimisation step (add_noise, UNet "
+                    "forward, masked MSE, autograd backward, clip_grad_norm_, AdamW) on 1 sample at 384x640, fp32, out of "
+                    "the workload's 16 samples per step")
+
+
+def cpu_train_steps(n_steps: int, n_warm: int, threads: int):
+    """The oracle port of the reference's train_step (oracle/train_ref.py) on the host cores: seconds per 1-sample step."""
+    from oracle import schedulers_ref as S, train_ref
+    from oracle.unet_ref import make_unet
+    torch.set_num_threads(threads)
+    unet = make_unet(8, 1, seed=0, sample_size=(384, 640))
+    opt = torch.optim.AdamW(unet.parameters(), lr=1e-4)
+    g = torch.Generator().manual_seed(7)
+    clean, cond = torch.rand(1, 1, 384, 640, generator=g) * 2 - 1, torch.rand(1, 7, 384, 640, generator=g) * 2 - 1
+    noise, t = torch.randn(1, 1, 384, 640, generator=g), torch.randint(0, 128, (1,), generator=g)
+    mask = (torch.rand(1, 1, 384, 640, generator=g) > 0.1).float()
+    ac = torch.cumprod(1 - S.make_betas("squaredcos_cap_v2", 128), 0)
+    times = []
+    for i in range(n_warm + n_steps):
+        t0 = time.perf_counter()
+        train_ref.train_step(unet, opt, clean, cond, noise, t, ac, mask, None, "sample", "mse", 1.0)
+        if i >= n_warm:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return sec, 1.0 / sec
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    if args.config == "train":
+        sec, sps = cpu_train_steps(max(1, min(args.steps, 3)), 1, threads)
+        emit({"impl": "reference", "metric": "training samples/sec at 360x640 (forward + backward + AdamW step)",
+              "value": sps, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+              "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+              "data": "synthetic",
+              "config": {"workload": "CPU reference arm, " + TRAIN_CPU_SAMPLE, "config": "train",
+                         "timed_unit": {"samples": 1, "optimisation_steps": 1}},
+              "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "sample": TRAIN_CPU_SAMPLE},
+              "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+              "gpu_launches": 0,
+              "note": "reference = train.py:157-538 restated in oracle/train_ref.py over the oracle UNet (accelerate and "
+                      "diffusers are un-vendored third-party dependencies); ms_per_step is the wall time of ONE timed unit"})
+        return
     sec, maps = cpu_reference_steps(max(1, args.steps), max(1, min(args.warmup, 2)), threads)
     cfg = workload_config("c2", args.gpus, "f32")
     cfg["workload"] = ("CPU reference arm, " + CPU_SAMPLE + " | config it samples: " + cfg["workload"])
@@ -850,6 +891,11 @@ def run_train_arm(args):
             del xa, ga
             torch.cuda.empty_cache()
             line["gpu_eager_baseline"] = train_eager_baseline(dtype, B, (H, W), 8, 2)
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sec_c, sps_c = cpu_train_steps(2, 1, threads)
+            line["cpu_baseline"] = {"value": sps_c, "unit": "samples/s", "cores": threads, "kind": "port",
+                                    "sample": TRAIN_CPU_SAMPLE + f" (2 timed steps of {sec_c:.2f} s)"}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -651,6 +651,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a) {
   if (a.sumsq != nullptr) {
     const float norm = (float)sqrt(*a.sumsq) * a.inv_scale;
     if (a.norm_out && blockIdx.x == 0 && threadIdx.x == 0) *a.norm_out = norm;
+    if (!isfinite(norm)) return;   // overflowed / NaN gradients (fp16 loss scale too high): skip the step, like GradScaler
     if (a.max_norm > 0.f) {
       const float coef = a.max_norm / (norm + 1e-6f);   // torch.nn.utils.clip_grad_norm_
       if (coef < 1.0f) gmul *= coef;

@@ -468,7 +468,8 @@ int d3_linear_small_bwd(const float* x, int n_rows, int K, int act_in, const flo
 /* Optimizer (torch.optim.AdamW semantics, train.py:862; clip_grad_norm_ :518): out += sum g^2 (fp64);  one fused AdamW
  * step over a flat parameter buffer - gradients are multiplied by inv_loss_scale and by min(1, max_norm / (norm + 1e-6))
  * with norm = sqrt(*sumsq) * inv_loss_scale (sumsq NULL or max_norm <= 0: no clipping); the first n16 parameters are
- * also written as 16-bit (the tensor-core weight packs); norm_out (optional) receives the gradient norm. */
+ * also written as 16-bit (the tensor-core weight packs); norm_out (optional) receives the gradient norm.  A non-finite norm
+ * (sumsq given) leaves parameters and moments untouched - the step is skipped, as torch's GradScaler does. */
 int d3_sumsq(const float* g, int64_t n, double* out, void* stream);
 int d3_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, void* p16, int64_t n16, int dtype16, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int step, const double* sumsq,

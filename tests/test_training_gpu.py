@@ -258,6 +258,31 @@ def test_backward_matches_autograd(dtype, loss_scale):
     assert worst[1] < (3e-2 if dtype == "bf16" else 1e-2), worst
 
 
+def test_backward_full_resolution():
+    """One sample at the bench resolution (384 x 640: 48 x 80 weight-gradient tiles per sample, every stride-2 level,
+    2400-token attention at level 4 is NOT part of this net - its attention runs at 24 x 40) against fp32 autograd."""
+    from oracle import schedulers_ref as S, train_ref
+    from tests.test_training_host import _inputs
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    B, H, W, dc, cin = 1, 384, 640, 1, 8
+    ref, tr = _setup(dc, cin, B, H, W, "bf16")
+    clean, cond, noise, t, mask, w = (x.cuda() for x in _inputs(B, H, W, dc, cin - dc, seed=9))
+    ac = torch.cumprod(1 - S.make_betas("squaredcos_cap_v2", 128), 0).cuda()
+    noisy = S.add_noise(clean, noise, t, ac)
+    _, out_ref, grads_ref = train_ref.loss_and_grads(ref, noisy, cond, t, clean, mask, w, "mse")
+    tr.zero_grad()
+    pred = tr.forward(noisy, cond, t)
+    dy, _ = _ops().masked_loss_grad(pred, clean, mask, w, grad_scale=1.0 / pred.numel(), dbias=tr.G("out.bias"))
+    tr.backward(dy, bias_grad_done=True)
+    got = tr.grad_dict()
+    num = sum(float(((got[k].cuda().double() - g.double()) ** 2).sum()) for k, g in grads_ref.items())
+    den = sum(float((g.double() ** 2).sum()) for g in grads_ref.values())
+    rel = math.sqrt(num / den)
+    print(f"[bf16, 1 x 384 x 640] whole-gradient relative L2 error {rel:.3e}")
+    assert rel < 6e-2, rel
+
+
 def test_train_steps_track_adamw_oracle():
     """Five optimisation steps on a fixed batch: the loss falls and follows the fp32 AdamW oracle."""
     from oracle import schedulers_ref as S, train_ref
@@ -280,3 +305,35 @@ def test_train_steps_track_adamw_oracle():
     assert ours[-1] < 0.7 * ours[0]
     for a, b in zip(ours, theirs):
         assert abs(a - b) < 0.1 * abs(b) + 1e-3, (ours, theirs)
+
+
+def test_nonfinite_gradients_skip_the_step_and_weights_hand_over_to_inference():
+    """(1) An overflowed gradient buffer must not touch parameters or moments (GradScaler semantics).  (2) After real
+    steps, ``trainer.state_dict()`` loads into the inference ``UNet2DModel`` and both forwards agree (train.py:640 runs
+    the validation pipeline on the weights being trained)."""
+    import d3roma_b200 as d
+    from oracle import schedulers_ref as S
+    from tests.test_training_host import _inputs
+    B, H, W, dc, cin = 2, 32, 64, 1, 8
+    ref, tr = _setup(dc, cin, B, H, W, "bf16", lr=1e-3)
+    ac = torch.cumprod(1 - S.make_betas("squaredcos_cap_v2", 128), 0).cuda()
+
+    class Sched:
+        add_noise = staticmethod(lambda a, b, t: S.add_noise(a, b, t, ac))
+        get_velocity = staticmethod(lambda a, b, t: S.get_velocity(a, b, t, ac))
+
+    clean, cond, noise, t, mask, w = (x.cuda() for x in _inputs(B, H, W, dc, cin - dc, seed=5))
+    tr.train_step(clean, cond, noise, t, Sched, mask=mask, weights=w)
+    p0, m0 = tr._p.clone(), tr._m.clone()
+    tr._g.fill_(float("inf"))
+    tr.optimizer_step()
+    assert torch.equal(tr._p, p0) and torch.equal(tr._m, m0) and not math.isfinite(tr.grad_norm)
+    tr.train_step(clean, cond, noise, t, Sched, mask=mask, weights=w)
+    assert math.isfinite(tr.grad_norm) and not torch.equal(tr._p, p0)
+    # hand-over: the trained weights through the inference model
+    net = d.UNet2DModel(sample_size=(H, W), in_channels=cin, out_channels=dc, compute_dtype="bf16").to("cuda")
+    net.load_state_dict(tr.state_dict())
+    x = torch.cat([clean, cond], 1)
+    want = tr.forward(clean, cond, torch.full((B,), 37, device="cuda"))
+    got = net(x, 37).sample
+    assert float((got - want).abs().max()) < 3e-2, float((got - want).abs().max())
