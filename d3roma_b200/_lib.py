@@ -176,6 +176,7 @@ def _declare(lib: C.CDLL) -> None:
                                         i32, vp]),
         "d3_colsum_nhwc16": (i32, [vp, i32, i32, i32, i32, vp, i64, i32, vp]),
         "d3_add_nhwc16": (i32, [vp, i32, vp, i32, vp, i32, i64, i32, i32, vp]),
+        "d3_add_colsum_nhwc16": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i64, i32, vp]),
         "d3_sumpool2x_nhwc16": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
         "d3_conv_out_bwd": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp, i32, vp, i32, vp]),
         "d3_attention_hd8_bwd_workspace_bytes": (C.c_size_t, [i32, i32, i32]),
@@ -202,8 +203,9 @@ def lib() -> C.CDLL:
             raise D3Error(
                 f"{LIB_PATH} is missing: build it with `python -m d3roma_b200.build` "
                 "(there is no CPU / PyTorch fallback for the CUDA path)")
-        _lib = C.CDLL(str(LIB_PATH))
-        _declare(_lib)
+        handle = C.CDLL(str(LIB_PATH))
+        _declare(handle)      # raises when header and library are out of sync: never hand out a half-declared library
+        _lib = handle         # (calls through undeclared ctypes prototypes would truncate 64-bit pointers)
     return _lib
 
 

@@ -383,6 +383,72 @@ __global__ void __launch_bounds__(256) add16_kernel(const uint16_t* __restrict__
   }
 }
 
+// out = a + b over [B, HW, C] with the per-(sample, channel) sums of the (rounded) result added to colsum: the last add of
+// a conv output's gradient and that conv's bias gradient in one pass
+template <int DT>
+__global__ void __launch_bounds__(kBwThreads) add_colsum_kernel(const uint16_t* __restrict__ a, int pa,
+                                                                const uint16_t* __restrict__ b2, int pb,
+                                                                uint16_t* __restrict__ out, int po, int HW, int C,
+                                                                int pix_per_block, float* __restrict__ colsum,
+                                                                long long cs_bstride) {
+  pdl_prologue();
+  __shared__ float s_red[kBwThreads * 8];
+  const int b = blockIdx.y;
+  const int nvec = C >> 3;
+  const int vec = threadIdx.x % nvec;
+  const int prow = threadIdx.x / nvec;
+  const int pstride = blockDim.x / nvec;
+  const int pix0 = blockIdx.x * pix_per_block;
+  int npix = HW - pix0;
+  if (npix > pix_per_block) npix = pix_per_block;
+  const size_t base = (size_t)b * HW + pix0;
+  const uint16_t* sa = a + base * pa + vec * 8;
+  const uint16_t* sb = b2 + base * pb + vec * 8;
+  uint16_t* so = out + base * po + vec * 8;
+  float cs[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) cs[k] = 0.f;
+  constexpr int U = 4;
+  for (int p0 = prow; p0 < npix; p0 += pstride * U) {
+    uint4 va[U], vb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * pstride;
+      if (p < npix) {
+        va[u] = __ldcs(reinterpret_cast<const uint4*>(sa + (size_t)p * pa));
+        vb[u] = __ldcs(reinterpret_cast<const uint4*>(sb + (size_t)p * pb));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * pstride;
+      if (p < npix) {
+        float x[8], y[8];
+        unpack8<DT>(va[u], x);
+        unpack8<DT>(vb[u], y);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] += y[k];
+        const uint4 pk = pack8<DT>(x);
+        *reinterpret_cast<uint4*>(so + (size_t)p * po) = pk;
+        unpack8<DT>(pk, y);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cs[k] += y[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s_red[threadIdx.x * 8 + k] = cs[k];
+  __syncthreads();
+  if (prow == 0) {
+    for (int rr = 1; rr < pstride; ++rr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cs[k] += s_red[(rr * nvec + vec) * 8 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(colsum + (size_t)b * cs_bstride + vec * 8 + k, cs[k]);
+  }
+}
+
 // out[b, i, j, :] = sum of the 2x2 block in[b, 2i + {0,1}, 2j + {0,1}, :] (+ addend): backward of nearest-2x upsampling
 template <int DT>
 __global__ void __launch_bounds__(256) sumpool2x_kernel(const uint16_t* __restrict__ in, int pin, const uint16_t* __restrict__ addend,
@@ -441,7 +507,7 @@ struct ConvOutBwdArgs {
 };
 
 template <int DT>
-__global__ void __launch_bounds__(256) conv_out_bwd_kernel(const ConvOutBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) conv_out_bwd_kernel(const ConvOutBwdArgs a) {
   pdl_prologue();
   __shared__ float s_mean[32];
   __shared__ float s_rstd[32];
@@ -600,17 +666,21 @@ __global__ void __launch_bounds__(256) linear_bwd_w_kernel(const float* __restri
   dw[i] += acc;
   if (db != nullptr && k == 0) db[n] += accb;
 }
+// dx[b][k] (+)= act'(x) * sum_n dy[b][n] W[n][k]; blockIdx.y splits the n range (dx must be zero / hold the value to
+// accumulate onto on entry: partial sums are added with atomics)
+constexpr int kLinChunk = 256;
 __global__ void __launch_bounds__(256) linear_bwd_x_kernel(const float* __restrict__ x, int act_in,
                                                            const float* __restrict__ dy, const float* __restrict__ w,
-                                                           int nb, int K, int N, float* __restrict__ dx, int accumulate) {
-  // one warp per (b, k-chunk of 32): lanes own consecutive k (coalesced reads of W rows)
+                                                           int nb, int K, int N, float* __restrict__ dx) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)nb * K) return;
   const int b = (int)(i / K), k = (int)(i % K);
+  const int n0 = blockIdx.y * kLinChunk, n1 = min(N, n0 + kLinChunk);
   float acc = 0.f;
-  for (int n = 0; n < N; ++n) acc = fmaf(dy[(size_t)b * N + n], w[(size_t)n * K + k], acc);
+#pragma unroll 4
+  for (int n = n0; n < n1; ++n) acc = fmaf(__ldg(dy + (size_t)b * N + n), __ldg(w + (size_t)n * K + k), acc);
   if (act_in) acc *= dsilu_f(x[i]);
-  dx[i] = accumulate ? dx[i] + acc : acc;
+  atomicAdd(dx + i, acc);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -833,6 +903,23 @@ extern "C" int d3_add_nhwc16(const void* a, int pa, const void* b, int pb, void*
   return D3_OK;
 }
 
+extern "C" int d3_add_colsum_nhwc16(const void* a, int pa, const void* b, int pb, void* out, int po, int B, int HW, int C,
+                                    float* colsum, int64_t colsum_bstride, int dtype, void* stream_) {
+  using namespace d3;
+  D3_REQUIRE(a && b && out && colsum && C % 8 == 0 && C <= 2048 && pa % 8 == 0 && pb % 8 == 0 && po % 8 == 0,
+             "add_colsum: bad arguments");
+  D3_REQUIRE(dtype == D3_DTYPE_BF16 || dtype == D3_DTYPE_F16, "add_colsum: 16-bit dtypes only");
+  int threads, ppb;
+  dim3 grid;
+  vec_geometry(B, HW, C, &threads, &grid, &ppb);
+  if (dtype == D3_DTYPE_F16)
+    D3_CHECK_CUDA(launch_pdl(add_colsum_kernel<kF16>, grid, dim3(threads), 0, static_cast<cudaStream_t>(stream_), static_cast<const uint16_t*>(a), pa, static_cast<const uint16_t*>(b), pb, static_cast<uint16_t*>(out), po, HW, C, ppb, colsum, (long long)colsum_bstride));
+  else
+    D3_CHECK_CUDA(launch_pdl(add_colsum_kernel<kBF16>, grid, dim3(threads), 0, static_cast<cudaStream_t>(stream_), static_cast<const uint16_t*>(a), pa, static_cast<const uint16_t*>(b), pb, static_cast<uint16_t*>(out), po, HW, C, ppb, colsum, (long long)colsum_bstride));
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
 extern "C" int d3_sumpool2x_nhwc16(const void* in, int pin, const void* addend, int padd, void* out, int pout, int B,
                                    int H, int W, int C, int dtype, void* stream_) {
   using namespace d3;
@@ -868,7 +955,7 @@ extern "C" int d3_conv_out_bwd(const void* h, int pitch, const double* stats, co
   a.dw = dw;
   a.B = B; a.H = H; a.W = W; a.dc = dc;
   a.eps = eps;
-  int blocks_per_sample = ceil_div(num_sms() * 4, B);
+  int blocks_per_sample = ceil_div(num_sms() * 8, B);
   a.rows_per_block = ceil_div(H, blocks_per_sample);
   if (a.rows_per_block < 1) a.rows_per_block = 1;
   dim3 grid(ceil_div(H, a.rows_per_block), B);
@@ -908,8 +995,9 @@ extern "C" int d3_linear_small_bwd(const float* x, int n_rows, int K, int act_in
   }
   if (dx != nullptr) {
     D3_REQUIRE(w != nullptr, "linear_small_bwd: dx needs the weight");
-    linear_bwd_x_kernel<<<(unsigned)(((size_t)n_rows * K + 255) / 256), 256, 0, stream>>>(x, act_in, dy, w, n_rows, K, rows, dx,
-                                                                                         accumulate_dx);
+    if (!accumulate_dx) D3_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)n_rows * K * sizeof(float), stream));
+    linear_bwd_x_kernel<<<dim3((unsigned)(((size_t)n_rows * K + 255) / 256), (unsigned)ceil_div(rows, kLinChunk)), 256, 0,
+                          stream>>>(x, act_in, dy, w, n_rows, K, rows, dx);
     D3_LAUNCH_CHECK();
   }
   return D3_OK;

@@ -792,7 +792,9 @@ def colsum_nhwc16(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def add_nhwc16(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def add_nhwc16(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None,
+               colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a + b; ``colsum`` (fp32 [B, C] view or [C]) additionally receives the per-channel sums of the result."""
     _check_nhwc(a, "a")
     _check_nhwc(b, "b")
     if a.shape != b.shape or a.dtype != b.dtype:
@@ -800,6 +802,13 @@ def add_nhwc16(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = N
     B, H, W, Cc = a.shape
     if out is None:
         out = torch.empty((B, H, W, Cc), dtype=a.dtype, device=a.device)
+    if colsum is not None:
+        if colsum.dtype != torch.float32 or colsum.shape[-1] != Cc or colsum.stride(-1) != 1:
+            raise ValueError("add_nhwc16: colsum must be fp32 [..., C] with contiguous channels")
+        _lib.check(_lib.lib().d3_add_colsum_nhwc16(a.data_ptr(), a.stride(2), b.data_ptr(), b.stride(2), out.data_ptr(),
+                                                   out.stride(2), B, H * W, Cc, colsum.data_ptr(),
+                                                   colsum.stride(0) if colsum.dim() == 2 else 0, _dt(a), _stream()))
+        return out
     _lib.check(_lib.lib().d3_add_nhwc16(a.data_ptr(), a.stride(2), b.data_ptr(), b.stride(2), out.data_ptr(),
                                         out.stride(2), B * H * W, Cc, _dt(a), _stream()))
     return out

@@ -330,16 +330,24 @@ class UNetTrainer:
     def _acc(self, t, g):
         self._grads.setdefault(id(t), (t, []))[1].append(g)
 
-    def _pending(self, t, keep: int):
+    def _pending(self, t, keep: int, colsum=None):
         e = self._grads.pop(id(t), None)
         lst = [] if e is None else e[1]
         while len(lst) > keep:
             b, a = lst.pop(), lst.pop()
-            lst.append(ops.add_nhwc16(a, b))
+            last = len(lst) + 1 == keep          # the add that leaves `keep` tensors
+            lst.append(ops.add_nhwc16(a, b, colsum=colsum if (last and keep == 1) else None))
         return lst
 
-    def _take(self, t):
-        lst = self._pending(t, 1)
+    def _take(self, t, colsum=None):
+        """The summed gradient of ``t``.  ``colsum``: a dict ``{"bg": fp32 view, "done": bool}`` - when a final add is
+        needed anyway, the channel sums of the result (a conv's bias gradient) are taken in that pass."""
+        n = len(self._grads.get(id(t), (None, []))[1])
+        if colsum is not None and n >= 2 and not colsum["done"] and colsum["bg"] is not None:
+            lst = self._pending(t, 1, colsum=colsum["bg"])
+            colsum["done"] = True
+        else:
+            lst = self._pending(t, 1)
         return lst[0] if lst else None
 
     def _consume(self, t) -> bool:
@@ -395,7 +403,7 @@ class UNetTrainer:
             self._bias_req[id(out)] = req      # a GroupNorm that consumes `out` first may take the channel sums for us
 
         def bwd():
-            dy = self._take(out)
+            dy = self._take(out, colsum=req)
             cin = x.shape[3]
             gw = self.G(wname)
             if bias_grad is not None and not req["done"]:

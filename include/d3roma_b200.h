@@ -443,6 +443,9 @@ int d3_colsum_nhwc16(const void* x, int pitch, int B, int HW, int C, float* out,
                      void* stream);
 int d3_add_nhwc16(const void* a, int pa, const void* b, int pb, void* out, int po, int64_t npix, int C, int dtype,
                   void* stream);
+/* out = a + b and colsum[b * colsum_bstride + c] += per-channel sums of the result, in one pass. */
+int d3_add_colsum_nhwc16(const void* a, int pa, const void* b, int pb, void* out, int po, int B, int HW, int C,
+                         float* colsum, int64_t colsum_bstride, int dtype, void* stream);
 int d3_sumpool2x_nhwc16(const void* in, int pin, const void* addend, int padd, void* out, int pout, int B, int H, int W,
                         int C, int dtype, void* stream);
 /* Backward of d3_conv_out_fused (conv_norm_out + SiLU + conv_out): dy fp32 NCHW [B,dc,H,W] -> da = gradient w.r.t.

@@ -60,8 +60,11 @@ def colsum_nhwc16(x, out):
     return out
 
 
-def add_nhwc16(a, b, out=None):
+def add_nhwc16(a, b, out=None, colsum=None):
     r = (a.float() + b.float()).to(a.dtype)
+    if colsum is not None:
+        cs = r.float().sum(dim=(1, 2))
+        colsum += cs if colsum.dim() == 2 else cs.sum(0)
     if out is not None:
         out.copy_(r)
         return out
