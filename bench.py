@@ -883,7 +883,10 @@ def run_train_arm(args):
                      "gflop_per_sample_step": 3 * 1872.53, "peak_source": "measured sustained (cuBLAS bf16 inside a long step)"},
             "roofline": {"bound": "tensor", "kernel": f"conv_wgrad_kernel (split-K, MN-major TMA operands) 3x3 128->128 @{B}x{H}x{W}",
                          "achieved": flops / (ms_wg * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                         "frac": flops / (ms_wg * 1e-3) / 1e12 / peak, "traffic": None, "flops_per_launch": flops,
+                         "frac": flops / (ms_wg * 1e-3) / 1e12 / peak,
+                         "traffic": load_ncu_traffic().get("wgrad", {}).get("dram_bytes"),
+                         "traffic_source": load_ncu_traffic().get("wgrad", {}).get("source"),
+                         "algorithmic_bytes": 2.0 * B * H * W * 128 * 2, "flops_per_launch": flops,
                          "ms_per_launch": ms_wg,
                          "peak_source": ("measured" if peaks["src"] == "measured" else "fallback") + " burst (kernel timed alone)"},
         }
