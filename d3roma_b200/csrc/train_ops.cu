@@ -200,7 +200,10 @@ __global__ void __launch_bounds__(kBwThreads, 2) gn_bwd_reduce_kernel(const GnBw
 
 // pass 2: dx = rstd * (gamma * dz - mean_g(gamma * dz) - xhat * mean_g(gamma * dz * xhat)) (+ addends)
 //            = zs * dz + e * x + f   with  e = kd * rstd,  f = kb - kd * mean * rstd  (kb, kd: the two group means, scaled)
-template <int DT>
+// NADD: how many addend pointers the instantiation reads (0, 1 or kMaxAddends); U: pixels in flight per thread - the
+// fewer streams, the deeper the pipeline the 128-register budget allows (ncu: the U = 2 form of the no-addend case sat at
+// 4.1 TB/s with every warp stalled on its loads)
+template <int DT, int NADD, int U>
 __global__ void __launch_bounds__(kBwThreads, 2) gn_bwd_apply_kernel(const GnBwdArgs a) {
   pdl_prologue();
   __shared__ float s_mean[32];
@@ -257,17 +260,16 @@ __global__ void __launch_bounds__(kBwThreads, 2) gn_bwd_apply_kernel(const GnBwd
   const uint16_t* src = (vec < nvec1) ? a.x1 + base_pix * a.p1 + vec * 8 : a.x2 + base_pix * a.p2 + (vec - nvec1) * 8;
   const int sp = (vec < nvec1) ? a.p1 : a.p2;
   const uint16_t* gy = a.dy + base_pix * a.pdy + vec * 8;
-  const uint16_t* ad[kMaxAddends];
+  const uint16_t* ad[NADD > 0 ? NADD : 1];
 #pragma unroll
-  for (int i = 0; i < kMaxAddends; ++i) ad[i] = a.addend[i] ? a.addend[i] + base_pix * a.padd[i] + vec * 8 : nullptr;
+  for (int i = 0; i < NADD; ++i) ad[i] = a.addend[i] ? a.addend[i] + base_pix * a.padd[i] + vec * 8 : nullptr;
   uint16_t* dst = a.dx + base_pix * a.pdx + vec * 8;
   const bool want_cs = a.colsum != nullptr && vec * 8 < a.colsum_C;
   float cs[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) cs[k] = 0.f;
-  constexpr int U = 2;
   for (int p0 = prow; p0 < npix; p0 += pstride * U) {
-    uint4 xv[U], gv[U], av[U][kMaxAddends];
+    uint4 xv[U], gv[U], av[U][NADD > 0 ? NADD : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int p = p0 + u * pstride;
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(kBwThreads, 2) gn_bwd_apply_kernel(const GnBwd
         xv[u] = __ldcs(reinterpret_cast<const uint4*>(src + (size_t)p * sp));
         gv[u] = __ldcs(reinterpret_cast<const uint4*>(gy + (size_t)p * a.pdy));
 #pragma unroll
-        for (int i = 0; i < kMaxAddends; ++i)
+        for (int i = 0; i < NADD; ++i)
           if (ad[i]) av[u][i] = __ldcs(reinterpret_cast<const uint4*>(ad[i] + (size_t)p * a.padd[i]));
       }
     }
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(kBwThreads, 2) gn_bwd_apply_kernel(const GnBwd
           o[k] = fmaf(zs[k], dz, fmaf(ce[k], x[k], cf[k]));
         }
 #pragma unroll
-        for (int i = 0; i < kMaxAddends; ++i) {
+        for (int i = 0; i < NADD; ++i) {
           if (ad[i]) {
             float e[8];
             unpack8<DT>(av[u][i], e);
@@ -867,8 +869,15 @@ extern "C" int d3_groupnorm_silu_bwd(const void* x1, int C1, int p1, const doubl
   if (dtype == D3_DTYPE_F16) D3_CHECK_CUDA(launch_pdl(gn_bwd_reduce_kernel<kF16>, grid, dim3(threads), 0, stream, a));
   else D3_CHECK_CUDA(launch_pdl(gn_bwd_reduce_kernel<kBF16>, grid, dim3(threads), 0, stream, a));
   D3_LAUNCH_CHECK();
-  if (dtype == D3_DTYPE_F16) D3_CHECK_CUDA(launch_pdl(gn_bwd_apply_kernel<kF16>, grid, dim3(threads), 0, stream, a));
-  else D3_CHECK_CUDA(launch_pdl(gn_bwd_apply_kernel<kBF16>, grid, dim3(threads), 0, stream, a));
+#define D3_GNB_APPLY(NA, UU)                                                                                          \
+  do {                                                                                                                \
+    if (dtype == D3_DTYPE_F16) D3_CHECK_CUDA(launch_pdl(gn_bwd_apply_kernel<kF16, NA, UU>, grid, dim3(threads), 0, stream, a)); \
+    else D3_CHECK_CUDA(launch_pdl(gn_bwd_apply_kernel<kBF16, NA, UU>, grid, dim3(threads), 0, stream, a));           \
+  } while (0)
+  if (n_addends == 0) D3_GNB_APPLY(0, 4);
+  else if (n_addends == 1) D3_GNB_APPLY(1, 3);
+  else D3_GNB_APPLY(kMaxAddends, 2);
+#undef D3_GNB_APPLY
   D3_LAUNCH_CHECK();
   return D3_OK;
 }
