@@ -140,6 +140,8 @@ def _declare(lib: C.CDLL) -> None:
         "d3_denormalize_piecewise": (i32, [vp, i64, i64, i32, C.POINTER(f32), C.POINTER(f32), f32, f32, vp, vp]),
         "d3_pad_replicate": (i32, [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]),
         "d3_crop": (i32, [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]),
+        "d3_pad_zero": (i32, [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]),
+        "d3_clamp_target": (i32, [vp, vp, i64, i32, i64, f32, vp]),
         "d3_clamp_into": (i32, [vp, i64, i64, i64, i64, f32, f32, vp, vp]),
         "d3_disp_metrics": (i32, [vp, vp, vp, vp, i32, i32, i64, vp, vp]),
         "d3_scale_shift_lsq": (i32, [vp, vp, vp, i32, i64, vp, vp]),

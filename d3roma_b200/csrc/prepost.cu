@@ -121,6 +121,34 @@ __global__ void pad_replicate_kernel(const float* __restrict__ in, int64_t N, in
   }
 }
 
+// planes [N][H][W] -> [N][H+pt+pb][W+pl+pr], zero border (InputPadder.pad_zero, utils.py:317-319: the training mask)
+__global__ void pad_zero_kernel(const float* __restrict__ in, int64_t N, int H, int W, int pl, int pr, int pt, int pb,
+                                float* __restrict__ out) {
+  const int Ho = H + pt + pb, Wo = W + pl + pr;
+  D3_GRID_STRIDE(i, N * Ho * Wo) {
+    const int x = (int)(i % Wo) - pl;
+    const int64_t r = i / Wo;
+    const int y = (int)(r % Ho) - pt;
+    const int64_t n = r / Ho;
+    out[i] = (x >= 0 && x < W && y >= 0 && y < H) ? in[(n * H + y) * W + x] : 0.f;
+  }
+}
+
+// train.py:175-178: x <- clamp(x, -r, r); mask <- mask * (|x| < r), mask [B][1][HW] broadcast over the C channels of x
+__global__ void clamp_target_kernel(float* __restrict__ x, float* __restrict__ mask, int64_t B, int C, int64_t HW, float r) {
+  D3_GRID_STRIDE(i, B * HW) {
+    const int64_t b = i / HW, p = i - b * HW;
+    float m = mask[i];
+    for (int c = 0; c < C; ++c) {
+      float* px = x + (b * C + c) * HW + p;
+      const float v = fminf(fmaxf(*px, -r), r);
+      *px = v;
+      m *= (fabsf(v) < r) ? 1.f : 0.f;
+    }
+    mask[i] = m;
+  }
+}
+
 __global__ void crop_kernel(const float* __restrict__ in, int64_t N, int Hi, int Wi, int top, int left, int H, int W,
                             float* __restrict__ out) {
   D3_GRID_STRIDE(i, N * H * W) {
@@ -191,6 +219,23 @@ extern "C" int d3_pad_replicate(const float* in, int64_t planes, int H, int W, i
   if (n == 0) return D3_OK;
   pad_replicate_kernel<<<ew_blocks(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, planes, H, W, left, right, top,
                                                                                    bottom, out);
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
+extern "C" int d3_pad_zero(const float* in, int64_t planes, int H, int W, int left, int right, int top, int bottom,
+                           float* out, void* stream) {
+  D3_REQUIRE(in && out && H > 0 && W > 0 && left >= 0 && right >= 0 && top >= 0 && bottom >= 0, "pad_zero: bad arguments");
+  const int64_t n = planes * (H + top + bottom) * (W + left + right);
+  if (n == 0) return D3_OK;
+  pad_zero_kernel<<<ew_blocks(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, planes, H, W, left, right, top, bottom, out);
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
+extern "C" int d3_clamp_target(float* x, float* mask, int64_t B, int C, int64_t HW, float range, void* stream) {
+  D3_REQUIRE(x && mask && B > 0 && C > 0 && HW > 0 && range > 0.f, "clamp_target: bad arguments");
+  clamp_target_kernel<<<ew_blocks(B * HW), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, mask, B, C, HW, range);
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

@@ -641,6 +641,25 @@ def pad_replicate(x, pads):
     return out
 
 
+def pad_zero(x, pads):
+    """x [B,C,H,W] fp32, zero border, pads = [left, right, top, bottom] (InputPadder.pad_zero)."""
+    x = _f32c(x, "x")
+    B, Cc, H, W = x.shape
+    l, r, t, b = pads
+    out = torch.empty((B, Cc, H + t + b, W + l + r), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().d3_pad_zero(x.data_ptr(), B * Cc, H, W, l, r, t, b, out.data_ptr(), _stream()))
+    return out
+
+
+def clamp_target_(x, mask, clip_range: float):
+    """In place: x <- clamp(x, -r, r), mask <- mask * (|x| < r)  (train.py:175-178); x [B,C,H,W], mask [B,1,H,W]."""
+    B, Cc, H, W = x.shape
+    if not (x.is_contiguous() and mask.is_contiguous() and x.dtype == mask.dtype == torch.float32 and x.is_cuda):
+        raise ValueError("clamp_target_: contiguous fp32 CUDA tensors expected")
+    _lib.check(_lib.lib().d3_clamp_target(x.data_ptr(), mask.data_ptr(), B, Cc, H * W, clip_range, _stream()))
+    return x, mask
+
+
 def crop(x, top: int, left: int, H: int, W: int):
     x = _f32c(x, "x")
     B, Cc, Hi, Wi = x.shape

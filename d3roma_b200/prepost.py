@@ -166,6 +166,11 @@ class InputPadder:
         assert all((x.ndim == 4) for x in inputs if x is not None)
         return [ops.pad_replicate(x, self._pad) if x is not None else x for x in inputs]
 
+    def pad_zero(self, *inputs):
+        """utils.py:317-319 (the training mask is padded with zeros, train.py:186)."""
+        assert all((x.ndim == 4) for x in inputs if x is not None)
+        return [ops.pad_zero(x, self._pad) if x is not None else x for x in inputs]
+
     def unpad(self, x: torch.Tensor):
         assert x.ndim == 4, "B,C,H,W"
         ht, wd = x.shape[-2:]

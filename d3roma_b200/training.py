@@ -612,5 +612,85 @@ class UNetTrainer:
                                             dbias=self.G("out.bias"))
         self.backward(dy, bias_grad_done=True)
         self.optimizer_step(world_size)
+        self.last_loss_sum = loss_sum          # fp64 [B]: sum of network_loss over each sample (train.py:422 `losses`)
         ls = loss_sum if w is None else loss_sum * w.double()
         return ls.sum() / n
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# train_step with the reference's signature (train.py:157-165)
+# ----------------------------------------------------------------------------------------------------------------------
+COND_ORDER = {   # train.py:283-297: channels concatenated after the noisy disparity
+    "rgb": ("rgb",), "rgb+raw": ("rgb", "raw"), "left+right": ("left", "right"), "left+right+raw": ("left", "right", "raw"),
+    "rgb+left+right": ("rgb", "left", "right"), "rgb+left+right+raw": ("rgb", "left", "right", "raw"),
+}
+
+
+def train_step(accelerator, config, model: UNetTrainer, optimizer, lr_scheduler, noise_scheduler, t_sampler, step_counter,
+               normalized_disp=None, normalized_rgb=None, mask=None, left_image=None, right_image=None, sim_disp=None,
+               tokenizer=None, text_encoder=None, vae=None, empty_text_embed=None, **kwargs):
+    """``train_step`` of the reference (train.py:157-538) for the pixel-space model, over a ``UNetTrainer``.
+
+    Same positional / keyword arguments and the same return value ``(loss, {"t", "losses", "gradn",
+    "abnormal_loss_detected"})``.  ``model`` is the ``UNetTrainer`` (it owns the parameters, the gradients and the AdamW
+    state, so ``optimizer`` is unused and may be ``None``); ``accelerator`` only has to provide ``num_processes`` (``None``:
+    taken from ``torch.distributed``); ``lr_scheduler`` (optional) is stepped after the update and its learning rate is
+    used for the NEXT step, as ``lr_scheduler.step()`` does at :528.  ``config.ldm`` raises ``NotImplementedError``."""
+    import torch.distributed as dist
+    from .prepost import InputPadder
+    if getattr(config, "ldm", False):
+        raise NotImplementedError("d3roma_b200.training.train_step covers the pixel-space model (config.ldm = False)")
+    if config.loss_type not in ("l1", "mse"):
+        raise ValueError(f"loss type {config.loss_type} not supported")                    # :255-260
+    if config.loss_type != model.loss_type:
+        raise ValueError("config.loss_type differs from the UNetTrainer's loss_type")
+    if config.noise_strategy != "randn":
+        raise NotImplementedError                                                           # :263-269 ('pyramid' not built)
+    if config.cond_channels not in COND_ORDER:
+        raise NotImplementedError                                                           # :283-297
+    if config.prediction_type not in ("epsilon", "v_prediction", "sample"):
+        raise NotImplementedError                                                           # :310-415 ('v_pred_depth' is LDM-only)
+    if "rgb" in config.cond_channels and getattr(config, "noise_rgb", False):
+        raise NotImplementedError("noise_rgb (train.py:271-276)")
+    assert normalized_disp.shape[1] == config.depth_channels, "depth channel inconsistency"   # :181
+    normalized_disp = normalized_disp.to(torch.float32).contiguous()
+    mask = mask.to(torch.float32).contiguous()
+    if config.clip_sample:                                                                   # :175-178
+        lo_hi = ops.masked_minmax(normalized_disp.reshape(1, -1)).tolist()[0]
+        if lo_hi[1] > config.clip_sample_range or lo_hi[0] < -config.clip_sample_range:
+            normalized_disp, mask = ops.clamp_target_(normalized_disp.clone(), mask.clone(), float(config.clip_sample_range))
+    padder = InputPadder(normalized_disp.shape, divis_by=config.divis_by)                    # :183-186
+    normalized_disp, normalized_rgb, left_image, right_image, sim_disp = padder.pad(
+        normalized_disp, normalized_rgb, left_image, right_image, sim_disp)
+    mask = padder.pad_zero(mask)[0]
+    noise = torch.randn(normalized_disp.shape).to(normalized_disp.device)                    # :266 (host generator, as there)
+    bs = noise.shape[0]
+    timesteps, weights = t_sampler.sample(bs, noise.device)                                  # :261
+    parts = {"rgb": normalized_rgb, "left": left_image, "right": right_image, "raw": sim_disp}
+    cond = torch.cat([parts[k] for k in COND_ORDER[config.cond_channels]], dim=1)
+    if accelerator is not None:
+        world = int(accelerator.num_processes)
+    else:
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    model.max_grad_norm = float(config.clip_grad_norm)                                       # :518
+    loss = model.train_step(normalized_disp, cond, noise, timesteps, noise_scheduler, mask=mask, weights=weights,
+                            prediction_type=config.prediction_type, world_size=world)
+    per_sample = model.last_loss_sum / float(normalized_disp[0].numel())                     # :422 network_loss.mean((1,2,3))
+    losses = {"loss": per_sample.to(torch.float32)}
+    losses["mse"] = losses["loss"] ** 2 if config.loss_type == "l1" else losses["loss"]      # :423 (sic)
+    gathered_t, gathered_losses = timesteps, losses
+    if world > 1:                                                                            # :427-428 gather_for_metrics
+        def gather(x):
+            out = [torch.empty_like(x) for _ in range(world)]
+            dist.all_gather(out, x.contiguous())
+            return torch.cat(out)
+        gathered_t = gather(timesteps)
+        gathered_losses = {k: gather(v) for k, v in losses.items()}
+    if lr_scheduler is not None:                                                             # :527-528
+        lr_scheduler.step()
+        model.lr = float(lr_scheduler.get_last_lr()[0])
+    loss_value = float(loss.item())
+    abnormal = bool(step_counter is not None and hasattr(step_counter, "avg_loss") and step_counter.avg_loss() > 0
+                    and loss_value / step_counter.avg_loss() > 100)                          # :431 (reported, not acted on)
+    return loss_value, {"t": gathered_t, "losses": gathered_losses, "gradn": model.grad_norm,
+                        "abnormal_loss_detected": abnormal}

@@ -284,6 +284,11 @@ int d3_pad_replicate(const float* in, int64_t planes, int H, int W, int left, in
                      float* out, void* stream);
 int d3_crop(const float* in, int64_t planes, int Hin, int Win, int top, int left, int H, int W, float* out,
             void* stream);
+/* InputPadder.pad_zero (utils.py:317-319; the training mask, train.py:186). */
+int d3_pad_zero(const float* in, int64_t planes, int H, int W, int left, int right, int top, int bottom, float* out,
+                void* stream);
+/* train.py:175-178, in place: x[B][C][HW] <- clamp(x, -range, range); mask[B][1][HW] <- mask * (|x| < range). */
+int d3_clamp_target(float* x, float* mask, int64_t B, int C, int64_t HW, float range, void* stream);
 /* out[b][out_off + i] = clamp(in[b][i], lo, hi), i < chw (custom_pipelines.py:176-182,196: image.clamp(-1,1) written
  * straight into its slot of the intermediate-image stack). */
 int d3_clamp_into(const float* in, int64_t B, int64_t chw, int64_t out_bstride, int64_t out_off, float lo, float hi,

@@ -59,3 +59,46 @@ def train_step(unet: torch.nn.Module, optimizer: torch.optim.Optimizer, clean: t
     optimizer.step()
     optimizer.zero_grad()
     return loss, gn
+
+
+def train_step_full(config, unet, optimizer, alphas_cumprod, t_sampler, normalized_disp, normalized_rgb=None, mask=None,
+                    left_image=None, right_image=None, sim_disp=None):
+    """The whole pixel-space ``train_step`` including its front end: out-of-range clamp + mask update (train.py:175-178),
+    ``InputPadder.pad`` / ``pad_zero`` (:183-186), ``torch.randn`` noise (:266), ``t_sampler.sample`` (:261), the
+    ``cond_channels`` concatenation (:283-297).  Returns (loss, per-sample losses, grad_norm, timesteps)."""
+    from . import prepost_ref as P
+    if config.clip_sample and (normalized_disp.max() > config.clip_sample_range
+                               or normalized_disp.min() < -config.clip_sample_range):
+        normalized_disp = torch.clamp(normalized_disp, -config.clip_sample_range, config.clip_sample_range)
+        mask = mask * (normalized_disp.abs() < config.clip_sample_range).to(torch.float32)
+    pads = P.pad_amounts(normalized_disp.shape[-2], normalized_disp.shape[-1], config.divis_by)
+    rep = lambda x: None if x is None else F.pad(x, pads, mode="replicate")   # noqa: E731
+    normalized_disp, normalized_rgb, left_image, right_image, sim_disp = map(
+        rep, (normalized_disp, normalized_rgb, left_image, right_image, sim_disp))
+    mask = F.pad(mask, pads, mode="constant", value=0)
+    noise = torch.randn(normalized_disp.shape)
+    timesteps, weights = t_sampler.sample(noise.shape[0], noise.device)
+    parts = {"rgb": normalized_rgb, "left": left_image, "right": right_image, "raw": sim_disp}
+    order = {"rgb": ("rgb",), "rgb+raw": ("rgb", "raw"), "left+right": ("left", "right"),
+             "left+right+raw": ("left", "right", "raw"), "rgb+left+right": ("rgb", "left", "right"),
+             "rgb+left+right+raw": ("rgb", "left", "right", "raw")}[config.cond_channels]
+    cond = torch.cat([parts[k] for k in order], dim=1)
+    noisy = S.add_noise(normalized_disp, noise, timesteps, alphas_cumprod)
+    if config.prediction_type == "sample":
+        target, m = normalized_disp, mask
+    elif config.prediction_type == "epsilon":
+        target, m = noise, mask
+    else:
+        target, m = S.get_velocity(normalized_disp, noise, timesteps, alphas_cumprod), None
+    unet.zero_grad(set_to_none=True)
+    out = unet(torch.cat([noisy, cond], 1), timesteps)
+    out = out.sample if hasattr(out, "sample") else out
+    fn = F.mse_loss if config.loss_type == "mse" else F.l1_loss
+    mm = 1.0 if m is None else m
+    network_loss = fn(out * mm, target * mm, reduction="none")
+    loss = (network_loss * weights.view(-1, 1, 1, 1)).mean()
+    loss.backward()
+    gn = torch.nn.utils.clip_grad_norm_(unet.parameters(), config.clip_grad_norm)
+    optimizer.step()
+    optimizer.zero_grad()
+    return loss.detach(), network_loss.mean(dim=(1, 2, 3)).detach(), gn, timesteps

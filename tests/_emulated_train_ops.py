@@ -207,3 +207,21 @@ def adamw_step(p, g, m, v, *, p16=None, n16=0, lr, beta1=0.9, beta2=0.999, eps=1
     p.addcdiv_(m, v.sqrt() / math.sqrt(bc2) + eps, value=-lr / bc1)
     if p16 is not None:
         p16.copy_(p[:n16].to(p16.dtype))
+
+
+def pad_replicate(x, pads):
+    return F.pad(x, tuple(pads), mode="replicate")
+
+
+def pad_zero(x, pads):
+    return F.pad(x, tuple(pads), mode="constant", value=0)
+
+
+def masked_minmax(x, mask=None):
+    return torch.stack([x.amin(dim=1), x.amax(dim=1)], dim=1)
+
+
+def clamp_target_(x, mask, clip_range):
+    x.clamp_(-clip_range, clip_range)
+    mask.mul_((x.abs() < clip_range).all(dim=1, keepdim=True).float())
+    return x, mask

@@ -59,5 +59,22 @@ def test_guidance_and_prepost_signatures(ref_modules):
     assert ours[:len(theirs)] == theirs and [p[0] for p in ours[len(theirs):]] == ["camera"]   # one trailing extra
     for name in ("__init__", "normalize", "denormalize"):
         assert _params(getattr(d.Normalizer, name)) == _params(getattr(ru.Normalizer, name)), name
-    for name in ("__init__", "pad", "unpad"):
+    for name in ("__init__", "pad", "pad_zero", "unpad"):
         assert _params(getattr(d.InputPadder, name)) == _params(getattr(ru.InputPadder, name)), name
+
+
+def test_train_step_signature():
+    """train.py imports accelerate / hydra at module level and cannot be imported here: its ``train_step`` signature is
+    read from the source with ``ast`` and compared with ``d3roma_b200.training.train_step``."""
+    import ast
+    from d3roma_b200 import training
+    tree = ast.parse((REF / "train.py").read_text())
+    fn = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "train_step")
+    theirs = [a.arg for a in fn.args.args]
+    n_def = len(fn.args.defaults)
+    assert all(isinstance(d, ast.Constant) and d.value is None for d in fn.args.defaults)
+    sig = inspect.signature(training.train_step)
+    ours = [p.name for p in sig.parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]
+    assert ours == theirs
+    assert [p.name for p in sig.parameters.values() if p.default is None] == theirs[-n_def:]
+    assert fn.args.kwarg is not None and any(p.kind == p.VAR_KEYWORD for p in sig.parameters.values())

@@ -352,3 +352,44 @@ def test_nonfinite_gradients_skip_the_step_and_weights_hand_over_to_inference():
     want = tr.forward(clean, cond, torch.full((B,), 37, device="cuda"))
     got = net(x, 37).sample
     assert float((got - want).abs().max()) < 3e-2, float((got - want).abs().max())
+
+
+def test_train_step_reference_signature_on_gpu():
+    """The drop-in ``training.train_step`` (reference signature) on the device: zero / replicate padding and the
+    out-of-range clamp kernels against torch, then a few steps on one batch (loss falls; returned fields)."""
+    import torch.nn.functional as F
+    from types import SimpleNamespace
+    import d3roma_b200 as d
+    from d3roma_b200 import training
+    from tests.test_training_host import _Sampler
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn((2, 3, 37, 50), generator=g, device="cuda")
+    assert torch.equal(ops.pad_zero(x, [7, 7, 13, 14]), F.pad(x, (7, 7, 13, 14)))
+    disp = torch.rand((2, 3, 20, 24), generator=g, device="cuda") * 2.4 - 1.2
+    m = (torch.rand((2, 1, 20, 24), generator=g, device="cuda") > 0.3).float()
+    want_x = disp.clamp(-1, 1)
+    want_m = m * (want_x.abs() < 1).all(dim=1, keepdim=True).float()
+    got_x, got_m = ops.clamp_target_(disp.clone(), m.clone(), 1.0)
+    assert torch.equal(got_x, want_x) and torch.equal(got_m, want_m)
+
+    B, H, W = 2, 40, 48
+    cfg = SimpleNamespace(ldm=False, loss_type="mse", noise_strategy="randn", cond_channels="left+right+raw",
+                          prediction_type="sample", noise_rgb=False, depth_channels=1, clip_sample=True,
+                          clip_sample_range=1.0, divis_by=32, clip_grad_norm=1.0)
+    ref, tr = _setup(1, 8, B, 64, 64, "bf16", lr=3e-4)
+    sched = d.MyDDPMScheduler.from_config(dict(num_train_timesteps=128, beta_schedule="squaredcos_cap_v2",
+                                               prediction_type="sample", clip_sample=True))
+    gc = torch.Generator().manual_seed(3)
+    disp = (torch.rand(B, 1, H, W, generator=gc) * 2.2 - 1.1).cuda()
+    left, right = ((torch.rand(B, 3, H, W, generator=gc) * 2 - 1).cuda() for _ in range(2))
+    raw = (torch.rand(B, 1, H, W, generator=gc) * 2 - 1).cuda()
+    mask = (torch.rand(B, 1, H, W, generator=gc) > 0.2).float().cuda()
+    losses = []
+    for _ in range(4):
+        torch.manual_seed(5)        # the same noise draw every step: the loss of THIS batch must fall
+        loss, info = training.train_step(None, cfg, tr, None, None, sched, _Sampler(), None, normalized_disp=disp,
+                                         mask=mask, left_image=left, right_image=right, sim_disp=raw)
+        losses.append(loss)
+        assert info["t"].shape == (B,) and info["losses"]["loss"].shape == (B,) and math.isfinite(info["gradn"])
+    assert losses[-1] < 0.8 * losses[0], losses

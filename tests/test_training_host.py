@@ -166,3 +166,60 @@ def test_data_parallel_matches_global_batch(trainer_mod):
         assert p.exitcode == 0
     for k, v in want.items():
         assert float(np.abs(got[k] - v.numpy()).max()) < 2e-5, k
+
+
+# ---------------------------------------------------------------------------------- train_step with the reference's signature
+class _Sampler:
+    """Stand-in for core/resample.py's samplers: a fixed draw with non-uniform importance weights."""
+
+    def sample(self, batch_size, device):
+        g = torch.Generator().manual_seed(77)
+        return torch.randint(0, 128, (batch_size,), generator=g).to(device), (torch.rand(batch_size, generator=g) + 0.5).to(device)
+
+
+def test_train_step_reference_signature(trainer_mod):
+    """``training.train_step(accelerator, config, model, optimizer, lr_scheduler, noise_scheduler, t_sampler, step_counter,
+    normalized_disp=..., ...)`` against the restated front end + step of train.py:157-538: out-of-range targets (clamp +
+    mask update), a 40 x 48 crop padded to 64 x 64 (replicate / zero), cond_channels order, weighted loss, the returned
+    per-sample losses."""
+    import inspect
+    from types import SimpleNamespace
+    sig = list(inspect.signature(trainer_mod.train_step).parameters)
+    assert sig[:8] == ["accelerator", "config", "model", "optimizer", "lr_scheduler", "noise_scheduler", "t_sampler",
+                       "step_counter"]                                                         # train.py:157
+    assert sig[8:14] == ["normalized_disp", "normalized_rgb", "mask", "left_image", "right_image", "sim_disp"]
+    B, H, W = 2, 40, 48
+    for cond_channels, cin, pt, lt in (("left+right+raw", 8, "sample", "mse"), ("rgb+raw", 5, "epsilon", "l1")):
+        cfg = SimpleNamespace(ldm=False, loss_type=lt, noise_strategy="randn", cond_channels=cond_channels,
+                              prediction_type=pt, noise_rgb=False, depth_channels=1, clip_sample=True,
+                              clip_sample_range=1.0, divis_by=32, clip_grad_norm=0.7)
+        ref = make_unet(cin, 1, seed=4, sample_size=(64, 64))
+        tr = trainer_mod.UNetTrainer(in_channels=cin, out_channels=1, lr=1e-3, loss_type=lt, device="cpu")
+        tr._adt = torch.float32
+        tr.load_state_dict(ref.state_dict())
+        opt = torch.optim.AdamW(ref.parameters(), lr=1e-3)
+        ac = torch.cumprod(1 - S.make_betas("squaredcos_cap_v2", 128), 0)
+
+        class Sched:
+            add_noise = staticmethod(lambda a, b, t: S.add_noise(a, b, t, ac))
+            get_velocity = staticmethod(lambda a, b, t: S.get_velocity(a, b, t, ac))
+
+        g = torch.Generator().manual_seed(31)
+        disp = torch.rand(B, 1, H, W, generator=g) * 2.4 - 1.2          # partly outside [-1, 1]
+        rgb, left, right = (torch.rand(B, 3, H, W, generator=g) * 2 - 1 for _ in range(3))
+        raw = torch.rand(B, 1, H, W, generator=g) * 2 - 1
+        mask = (torch.rand(B, 1, H, W, generator=g) > 0.2).float()
+        kw = dict(normalized_disp=disp, normalized_rgb=rgb, mask=mask, left_image=left, right_image=right, sim_disp=raw)
+        torch.manual_seed(123)
+        l_ref, per_ref, gn_ref, t_ref = train_ref.train_step_full(cfg, ref, opt, ac, _Sampler(), **{k: v.clone() for k, v in kw.items()})
+        torch.manual_seed(123)
+        loss, info = trainer_mod.train_step(None, cfg, tr, None, None, Sched, _Sampler(), None, **kw)
+        assert abs(loss - float(l_ref)) < 2e-4 * max(1.0, abs(float(l_ref))), (loss, float(l_ref))
+        assert torch.equal(info["t"], t_ref) and not info["abnormal_loss_detected"]
+        assert float((info["losses"]["loss"] - per_ref).abs().max()) < 1e-4
+        assert abs(info["gradn"] - float(gn_ref)) < 1e-2 * float(gn_ref)
+        sd = tr.state_dict()
+        # one AdamW step moves every parameter by ~lr = 1e-3 (first step: lr * sign(g)); agreement far below that
+        assert max(float((sd[k] - v).abs().max()) for k, v in ref.state_dict().items()) < 3e-4
+    with pytest.raises(NotImplementedError):
+        trainer_mod.train_step(None, SimpleNamespace(ldm=True), tr, None, None, Sched, _Sampler(), None, **kw)
