@@ -185,6 +185,8 @@ def _declare(lib: C.CDLL) -> None:
         "d3_attention_hd8_bwd": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp, i32, vp]),
         "d3_masked_loss_grad": (i32, [vp, vp, vp, vp, i32, i32, i64, i32, f32, vp, vp, vp, vp]),
         "d3_linear_small_bwd": (i32, [vp, i32, i32, i32, vp, i32, vp, vp, vp, vp, i32, vp]),
+        "d3_bilinear_upsample_acc": (i32, [vp, i64, i32, i32, vp, i32, i32, f32, vp]),
+        "d3_div_by_std": (i32, [vp, i64, vp, vp]),
         "d3_sumsq": (i32, [vp, i64, vp, vp]),
         "d3_adamw_step": (i32, [vp, vp, vp, vp, i64, vp, i64, i32, f32, f32, f32, f32, f32, i32, vp, f32, f32, vp, vp]),
         "d3_cast_f32_to_16": (i32, [vp, vp, i64, i32, vp]),

@@ -792,6 +792,59 @@ __global__ void __launch_bounds__(256) pack_taps_kernel(const PackTapsArgs a) {
   }
 }
 
+// dst[n][y][x] += mul * bilinear(src[n])(y, x)  - torch.nn.Upsample(size=(H, W), mode="bilinear") (align_corners=False):
+// source index max(0, (dst + 0.5) * in / out - 0.5), neighbour clamped at the border  (pyramid_noise_like, utils.py:122-133)
+__global__ void __launch_bounds__(256) bilinear_acc_kernel(const float* __restrict__ src, int64_t N, int h, int w,
+                                                           float* __restrict__ dst, int H, int W, float mul) {
+  const float rh = (float)h / (float)H, rw = (float)w / (float)W;
+  const int64_t total = N * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int64_t r = i / W;
+    const int y = (int)(r % H);
+    const int64_t n = r / H;
+    const float sy = fmaxf(rh * ((float)y + 0.5f) - 0.5f, 0.f), sx = fmaxf(rw * ((float)x + 0.5f) - 0.5f, 0.f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int yp = (y0 < h - 1) ? 1 : 0, xp = (x0 < w - 1) ? 1 : 0;
+    const float ly = sy - (float)y0, lx = sx - (float)x0;
+    const float* p = src + (n * h + y0) * w + x0;
+    const float v = (1.f - ly) * ((1.f - lx) * p[0] + lx * p[xp]) + ly * ((1.f - lx) * p[(size_t)yp * w] + lx * p[(size_t)yp * w + xp]);
+    dst[i] += mul * v;
+  }
+}
+
+__global__ void __launch_bounds__(256) sum_sumsq_kernel(const float* __restrict__ x, size_t n, double* __restrict__ out) {
+  double s = 0.0, q = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double v = (double)x[i];
+    s += v;
+    q += v * v;
+  }
+  __shared__ double s_s[256], s_q[256];
+  s_s[threadIdx.x] = s;
+  s_q[threadIdx.x] = q;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) {
+      s_s[threadIdx.x] += s_s[threadIdx.x + st];
+      s_q[threadIdx.x] += s_q[threadIdx.x + st];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    atomicAdd(out, s_s[0]);
+    atomicAdd(out + 1, s_q[0]);
+  }
+}
+
+// x /= std(x) (unbiased, torch.std), the moments taken from sums = (sum, sum of squares)
+__global__ void __launch_bounds__(256) scale_by_rstd_kernel(float* __restrict__ x, size_t n, const double* __restrict__ sums) {
+  const double mean = sums[0] / (double)n;
+  const double var = (sums[1] - (double)n * mean * mean) / (double)(n - 1);
+  const float sd = (float)sqrt(var);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = x[i] / sd;
+}
+
 int grid_for(size_t total, int per_block = 256, int waves = 16) {
   size_t blocks = (total + per_block - 1) / per_block;
   const size_t cap = (size_t)num_sms() * waves;
@@ -1077,6 +1130,28 @@ extern "C" int d3_pack_taps16(const float* w, int64_t w_pitch, int col0, int Cin
   a.out = static_cast<uint16_t*>(out);
   a.f16 = dtype16 == D3_DTYPE_F16;
   pack_taps_kernel<<<dim3(Cout / 32, Cin / 32, n_out_taps), 256, 0, static_cast<cudaStream_t>(stream_)>>>(a);
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
+extern "C" int d3_bilinear_upsample_acc(const float* src, int64_t planes, int h, int w, float* dst, int H, int W, float mul,
+                                        void* stream_) {
+  using namespace d3;
+  D3_REQUIRE(src && dst && planes > 0 && h > 0 && w > 0 && H > 0 && W > 0, "bilinear_upsample_acc: bad arguments");
+  bilinear_acc_kernel<<<grid_for((size_t)planes * H * W), 256, 0, static_cast<cudaStream_t>(stream_)>>>(src, planes, h, w, dst,
+                                                                                                      H, W, mul);
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
+extern "C" int d3_div_by_std(float* x, int64_t n, double* workspace2, void* stream_) {
+  using namespace d3;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  D3_REQUIRE(x && workspace2 && n > 1, "div_by_std: bad arguments");
+  D3_CHECK_CUDA(cudaMemsetAsync(workspace2, 0, 2 * sizeof(double), stream));
+  sum_sumsq_kernel<<<grid_for((size_t)n, 256 * 8, 8), 256, 0, stream>>>(x, (size_t)n, workspace2);
+  D3_LAUNCH_CHECK();
+  scale_by_rstd_kernel<<<grid_for((size_t)n, 256 * 4, 8), 256, 0, stream>>>(x, (size_t)n, workspace2);
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

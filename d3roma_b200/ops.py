@@ -896,6 +896,23 @@ def linear_small_bwd(x: torch.Tensor, w: Optional[torch.Tensor], dy: torch.Tenso
     return dx
 
 
+def bilinear_upsample_acc_(dst: torch.Tensor, src: torch.Tensor, mul: float) -> torch.Tensor:
+    """dst [B,C,H,W] += mul * Upsample(size=(H, W), mode="bilinear")(src [B,C,h,w]), fp32, in place."""
+    dst_, src = _f32c(dst, "dst"), _f32c(src, "src")
+    B, Cc, H, W = dst.shape
+    _lib.check(_lib.lib().d3_bilinear_upsample_acc(src.data_ptr(), B * Cc, src.shape[2], src.shape[3], dst_.data_ptr(), H, W,
+                                                   mul, _stream()))
+    return dst
+
+
+def div_by_std_(x: torch.Tensor) -> torch.Tensor:
+    """x /= x.std() (unbiased), in place."""
+    x = _f32c(x, "x")
+    ws = torch.empty(2, dtype=torch.float64, device=x.device)
+    _lib.check(_lib.lib().d3_div_by_std(x.data_ptr(), x.numel(), ws.data_ptr(), _stream()))
+    return x
+
+
 def sumsq(g: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     _lib.check(_lib.lib().d3_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream()))
     return out

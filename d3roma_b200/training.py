@@ -617,6 +617,24 @@ class UNetTrainer:
         return ls.sum() / n
 
 
+def pyramid_noise_like(x: torch.Tensor, discount: float = 0.9) -> torch.Tensor:
+    """``pyramid_noise_like`` of utils_d3roma/utils.py:122-133 (`noise_strategy: pyramid`, the setting of the pixel-space
+    training configs): the same random draws in the same order (``torch.randn_like`` on x's device, one
+    ``random.random()`` and one host ``torch.randn`` per level), the bilinear up-sampling + accumulation and the final
+    division by the standard deviation on the device kernels."""
+    import random
+    b, c, w, h = x.shape            # (the reference's own naming: w = rows, h = columns)
+    noise = torch.randn_like(x)
+    for i in range(10):
+        r = random.random() * 2 + 2
+        w, h = max(1, int(w / (r ** i))), max(1, int(h / (r ** i)))
+        noise_i = torch.randn(b, c, w, h).to(x)
+        ops.bilinear_upsample_acc_(noise, noise_i, discount ** i)
+        if w == 1 or h == 1:
+            break
+    return ops.div_by_std_(noise)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # train_step with the reference's signature (train.py:157-165)
 # ----------------------------------------------------------------------------------------------------------------------
@@ -644,8 +662,8 @@ def train_step(accelerator, config, model: UNetTrainer, optimizer, lr_scheduler,
         raise ValueError(f"loss type {config.loss_type} not supported")                    # :255-260
     if config.loss_type != model.loss_type:
         raise ValueError("config.loss_type differs from the UNetTrainer's loss_type")
-    if config.noise_strategy != "randn":
-        raise NotImplementedError                                                           # :263-269 ('pyramid' not built)
+    if config.noise_strategy not in ("randn", "pyramid"):
+        raise NotImplementedError                                                           # :263-269
     if config.cond_channels not in COND_ORDER:
         raise NotImplementedError                                                           # :283-297
     if config.prediction_type not in ("epsilon", "v_prediction", "sample"):
@@ -663,7 +681,10 @@ def train_step(accelerator, config, model: UNetTrainer, optimizer, lr_scheduler,
     normalized_disp, normalized_rgb, left_image, right_image, sim_disp = padder.pad(
         normalized_disp, normalized_rgb, left_image, right_image, sim_disp)
     mask = padder.pad_zero(mask)[0]
-    noise = torch.randn(normalized_disp.shape).to(normalized_disp.device)                    # :266 (host generator, as there)
+    if config.noise_strategy == "pyramid":                                                   # :263-264
+        noise = pyramid_noise_like(normalized_disp)
+    else:
+        noise = torch.randn(normalized_disp.shape).to(normalized_disp.device)                # :266 (host generator, as there)
     bs = noise.shape[0]
     timesteps, weights = t_sampler.sample(bs, noise.device)                                  # :261
     parts = {"rgb": normalized_rgb, "left": left_image, "right": right_image, "raw": sim_disp}

@@ -473,6 +473,12 @@ int d3_masked_loss_grad(const float* pred, const float* target, const float* mas
  * dx [n_rows][K] = (dy W) * act_in'(x) (dx NULL: skip; accumulate_dx: add to dx). */
 int d3_linear_small_bwd(const float* x, int n_rows, int K, int act_in, const float* w, int rows, const float* dy,
                         float* dw, float* db, float* dx, int accumulate_dx, void* stream);
+/* pyramid_noise_like (utils_d3roma/utils.py:122-133; `noise_strategy: pyramid` of the pixel-space training configs):
+ * dst[planes][H][W] += mul * nn.Upsample(size=(H, W), mode="bilinear")(src[planes][h][w]);  x /= x.std() (unbiased;
+ * workspace2: two doubles). */
+int d3_bilinear_upsample_acc(const float* src, int64_t planes, int h, int w, float* dst, int H, int W, float mul,
+                             void* stream);
+int d3_div_by_std(float* x, int64_t n, double* workspace2, void* stream);
 /* Optimizer (torch.optim.AdamW semantics, train.py:862; clip_grad_norm_ :518): out += sum g^2 (fp64);  one fused AdamW
  * step over a flat parameter buffer - gradients are multiplied by inv_loss_scale and by min(1, max_norm / (norm + 1e-6))
  * with norm = sqrt(*sumsq) * inv_loss_scale (sumsq NULL or max_norm <= 0: no clipping); the first n16 parameters are

@@ -225,3 +225,13 @@ def clamp_target_(x, mask, clip_range):
     x.clamp_(-clip_range, clip_range)
     mask.mul_((x.abs() < clip_range).all(dim=1, keepdim=True).float())
     return x, mask
+
+
+def bilinear_upsample_acc_(dst, src, mul):
+    dst += mul * F.interpolate(src, size=dst.shape[-2:], mode="bilinear")
+    return dst
+
+
+def div_by_std_(x):
+    x /= x.std()
+    return x

@@ -393,3 +393,26 @@ def test_train_step_reference_signature_on_gpu():
         losses.append(loss)
         assert info["t"].shape == (B,) and info["losses"]["loss"].shape == (B,) and math.isfinite(info["gradn"])
     assert losses[-1] < 0.8 * losses[0], losses
+
+
+def test_pyramid_noise_kernels():
+    """Bilinear up-sample + accumulate and the division by the standard deviation against torch on the same draws."""
+    import random
+    import torch.nn.functional as F
+    from d3roma_b200 import training
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for (h, w), (H, W) in (((7, 11), (64, 96)), ((1, 3), (384, 640)), ((96, 160), (384, 640)), ((5, 1), (33, 47))):
+        src = torch.randn((2, 3, h, w), generator=g, device="cuda")
+        dst = torch.randn((2, 3, H, W), generator=g, device="cuda")
+        want = dst + 0.81 * F.interpolate(src, size=(H, W), mode="bilinear")
+        ops.bilinear_upsample_acc_(dst, src, 0.81)
+        assert float((dst - want).abs().max()) < 2e-6
+    x = torch.randn((4, 1, 384, 640), generator=g, device="cuda") * 3 + 0.2
+    want = x / x.std()
+    assert float((ops.div_by_std_(x.clone()) - want).abs().max()) < 1e-5
+    z = torch.zeros(2, 1, 128, 160, device="cuda")
+    torch.manual_seed(4)
+    random.seed(4)
+    a = training.pyramid_noise_like(z)
+    assert a.shape == z.shape and abs(float(a.std()) - 1.0) < 1e-4 and bool(torch.isfinite(a).all())

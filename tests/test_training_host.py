@@ -223,3 +223,43 @@ def test_train_step_reference_signature(trainer_mod):
         assert max(float((sd[k] - v).abs().max()) for k, v in ref.state_dict().items()) < 3e-4
     with pytest.raises(NotImplementedError):
         trainer_mod.train_step(None, SimpleNamespace(ldm=True), tr, None, None, Sched, _Sampler(), None, **kw)
+
+
+def test_pyramid_noise_matches_reference(trainer_mod):
+    """``pyramid_noise_like`` (utils_d3roma/utils.py:122-133): the same random draws in the same order as the reference's
+    own function (imported from /root/reference when present; otherwise its restatement below)."""
+    import random
+    import torch.nn.functional as F
+    from tests._golden import HAVE_REF
+
+    def restated(x, discount=0.9):
+        b, c, w, h = x.shape
+        noise = torch.randn_like(x)
+        for i in range(10):
+            r = random.random() * 2 + 2
+            w, h = max(1, int(w / (r ** i))), max(1, int(h / (r ** i)))
+            noise += F.interpolate(torch.randn(b, c, w, h).to(x), size=x.shape[-2:], mode="bilinear") * discount ** i
+            if w == 1 or h == 1:
+                break
+        return noise / noise.std()
+
+    fn = restated
+    if HAVE_REF:
+        import sys
+        from oracle import diffusers_stub
+        diffusers_stub.install()
+        sys.path.insert(0, "/root/reference")
+        try:
+            from utils_d3roma.utils import pyramid_noise_like as fn   # the reference's own
+        finally:
+            sys.path.remove("/root/reference")
+    x = torch.zeros(2, 1, 64, 96)
+    for seed in (0, 1, 2):
+        torch.manual_seed(seed)
+        random.seed(seed)
+        want = fn(x)
+        torch.manual_seed(seed)
+        random.seed(seed)
+        got = trainer_mod.pyramid_noise_like(x)
+        assert float((got - want).abs().max()) < 1e-5
+        assert abs(float(got.std()) - 1.0) < 1e-5
