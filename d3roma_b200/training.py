@@ -668,8 +668,6 @@ def train_step(accelerator, config, model: UNetTrainer, optimizer, lr_scheduler,
         raise NotImplementedError                                                           # :283-297
     if config.prediction_type not in ("epsilon", "v_prediction", "sample"):
         raise NotImplementedError                                                           # :310-415 ('v_pred_depth' is LDM-only)
-    if "rgb" in config.cond_channels and getattr(config, "noise_rgb", False):
-        raise NotImplementedError("noise_rgb (train.py:271-276)")
     assert normalized_disp.shape[1] == config.depth_channels, "depth channel inconsistency"   # :181
     normalized_disp = normalized_disp.to(torch.float32).contiguous()
     mask = mask.to(torch.float32).contiguous()
@@ -687,7 +685,12 @@ def train_step(accelerator, config, model: UNetTrainer, optimizer, lr_scheduler,
         noise = torch.randn(normalized_disp.shape).to(normalized_disp.device)                # :266 (host generator, as there)
     bs = noise.shape[0]
     timesteps, weights = t_sampler.sample(bs, noise.device)                                  # :261
-    parts = {"rgb": normalized_rgb, "left": left_image, "right": right_image, "raw": sim_disp}
+    final_rgb = normalized_rgb
+    if "rgb" in config.cond_channels and getattr(config, "noise_rgb", False):               # :271-276
+        noise_rgb = torch.randn(normalized_rgb.shape).to(normalized_rgb.device)
+        noisy_rgb = noise_scheduler.add_noise(normalized_rgb, noise_rgb, timesteps)
+        final_rgb = ops.lincomb(0.5, normalized_rgb, 0.5, noisy_rgb)
+    parts = {"rgb": final_rgb, "left": left_image, "right": right_image, "raw": sim_disp}
     cond = torch.cat([parts[k] for k in COND_ORDER[config.cond_channels]], dim=1)
     if accelerator is not None:
         world = int(accelerator.num_processes)

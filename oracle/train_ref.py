@@ -78,6 +78,9 @@ def train_step_full(config, unet, optimizer, alphas_cumprod, t_sampler, normaliz
     mask = F.pad(mask, pads, mode="constant", value=0)
     noise = torch.randn(normalized_disp.shape)
     timesteps, weights = t_sampler.sample(noise.shape[0], noise.device)
+    if "rgb" in config.cond_channels and getattr(config, "noise_rgb", False):   # :271-276
+        noise_rgb = torch.randn(normalized_rgb.shape)
+        normalized_rgb = normalized_rgb * 0.5 + S.add_noise(normalized_rgb, noise_rgb, timesteps, alphas_cumprod) * 0.5
     parts = {"rgb": normalized_rgb, "left": left_image, "right": right_image, "raw": sim_disp}
     order = {"rgb": ("rgb",), "rgb+raw": ("rgb", "raw"), "left+right": ("left", "right"),
              "left+right+raw": ("left", "right", "raw"), "rgb+left+right": ("rgb", "left", "right"),

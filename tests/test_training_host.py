@@ -191,7 +191,7 @@ def test_train_step_reference_signature(trainer_mod):
     B, H, W = 2, 40, 48
     for cond_channels, cin, pt, lt in (("left+right+raw", 8, "sample", "mse"), ("rgb+raw", 5, "epsilon", "l1")):
         cfg = SimpleNamespace(ldm=False, loss_type=lt, noise_strategy="randn", cond_channels=cond_channels,
-                              prediction_type=pt, noise_rgb=False, depth_channels=1, clip_sample=True,
+                              prediction_type=pt, noise_rgb=cin == 5, depth_channels=1, clip_sample=True,
                               clip_sample_range=1.0, divis_by=32, clip_grad_norm=0.7)
         ref = make_unet(cin, 1, seed=4, sample_size=(64, 64))
         tr = trainer_mod.UNetTrainer(in_channels=cin, out_channels=1, lr=1e-3, loss_type=lt, device="cpu")
