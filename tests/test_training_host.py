@@ -2,8 +2,6 @@
 the C-ABI ops (tests/_emulated_train_ops.py) must reproduce autograd on the oracle UNet (oracle/train_ref.py) - tape
 order, gradient accumulation over skip / residual / shortcut branches, transposed and sub-pixel-phase weight packs of the
 data gradients, the parameter layout, gradient clipping and AdamW."""
-import copy
-
 import numpy as np
 import pytest
 import torch
