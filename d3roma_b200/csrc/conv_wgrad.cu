@@ -48,7 +48,7 @@ constexpr uint32_t kWgABytes = 2 * kBoxBytes;     // 128 output channels
 constexpr uint32_t kWgBBytes = 4 * kBoxBytes;     // up to 256 (tap, ci) columns
 constexpr uint32_t kWgStageBytes = kWgABytes + kWgBBytes;
 // halo form: 8 x 8 pixel tiles, x as (8 + 2) rows of 8 pixels per (kw, channel block) group, two groups per stage
-constexpr int kHaloStages = 5;
+constexpr int kHaloStages = 6;
 constexpr uint32_t kHaloBytes = 10 * 8 * 128;
 constexpr uint32_t kHaloStageBytes = kWgABytes + 2 * kHaloBytes;
 

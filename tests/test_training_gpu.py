@@ -41,6 +41,9 @@ WGRAD_CASES = [
     (2, 12, 20, 512, 512, 3, 1),
     (3, 32, 32, 128, 128, 3, 1),
     (2, 6, 10, 256, 256, 3, 1),
+    (1, 16, 16, 64, 128, 3, 1),      # halo form with an odd number of (kw, channel block) groups: last work item half full
+    (2, 8, 24, 192, 128, 3, 1),
+    (1, 16, 16, 64, 256, 3, 2),
 ]
 
 
