@@ -94,6 +94,37 @@ def eval_batch(config, pipeline, disable_bar=True, fxb=None, normalized_rgb=None
     return pred_un, rows, unc, err, out
 
 
+SPATIAL_KEYS = ("raw_disp", "normalized_disp", "sim_disp", "left_image", "right_image", "mask")
+
+
+@torch.no_grad()
+def eval_batch_coarse_to_fine(config, pipeline, batch: dict, disable_bar=True, generator=None):
+    """The ``config.coarse_to_fine`` branch of the evaluation loop (evaluate.py:362-398): the six spatial entries of the
+    batch are cut into four quadrants (the reference hard-codes 270 / 480, the half-way lines of its 540 x 960 frames;
+    here ``H // 2`` / ``W // 2``), every quadrant goes through ``eval_batch`` on its own, the predictions are stitched
+    back and the metric rows averaged over the quadrants.  Returns ``(pred_disps [B, H, W] numpy, disp_metrics [B, 5])``."""
+    import numpy as np
+    H, W = batch["raw_disp"].shape[2:]
+    hy, hx = H // 2, W // 2
+    cuts = ((slice(0, hy), slice(0, hx)), (slice(hy, H), slice(0, hx)), (slice(0, hy), slice(hx, W)),
+            (slice(hy, H), slice(hx, W)))                                          # j = 0..3 as in the reference
+    pred = np.empty((batch["raw_disp"].shape[0], H, W), dtype=np.float32)
+    rows = []
+    for ys, xs in cuts:
+        # the reference slices SPATIAL_KEYS only (its SceneFlow batches carry no full-size rgb / raw_depth the pipeline
+        # reads); every other [B, C, H, W] entry of the batch is cut the same way here
+        mini = {k: (v[:, :, ys, xs] if (k in SPATIAL_KEYS or (torch.is_tensor(v) and v.dim() == 4
+                                                             and tuple(v.shape[2:]) == (H, W))) and v is not None else v)
+                for k, v in batch.items()}
+        p, metrics, _, _, _ = eval_batch(config, pipeline, disable_bar, mini.get("fxb"), mini.get("normalized_rgb"),
+                                         mini.get("raw_disp"), mini.get("mask"), mini.get("left_image"),
+                                         mini.get("right_image"), mini.get("sim_disp"), mini.get("raw_depth"),
+                                         generator=generator)
+        pred[:, ys, xs] = p
+        rows.append(metrics[0])
+    return pred, np.mean(rows, axis=0)
+
+
 @torch.no_grad()
 def denoise_batch(pipeline, normalizer: Normalizer, *, rgb=None, left=None, right=None, sim_disp=None,
                   raw_depth=None, mask=None, cond_channels: str = "left+right+raw", depth_channels: int = 1,

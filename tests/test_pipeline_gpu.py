@@ -212,6 +212,26 @@ def test_eval_batch_contract_and_metrics():
     assert rows.shape == (3, 11) and set(mdict) == {"disp", "depth"} and np.isfinite(rows).all()
 
 
+def test_eval_batch_coarse_to_fine_quadrants():
+    """evaluate.py:362-398 (config.coarse_to_fine): four quadrants through eval_batch, stitched and averaged - must equal
+    evaluating each quadrant by hand with the same per-sample generators."""
+    import d3roma_b200 as d
+    from d3roma_b200 import evaluate, synthetic
+    _, ref, net = _make("fp16", hw=(64, 96))
+    pipe = d.GuidedDiffusionPipeline(net, d.MyDDIMScheduler.from_config(DDIM_CFG), d.FlowGuidance(flow_guidance_weight=0.0))
+    cfg = evaluate.default_config(num_inference_timesteps=2)
+    batch = synthetic.make_batch([0, 1], h=60, w=100)
+    gens = lambda: [torch.Generator().manual_seed(40 + i) for i in range(2)]   # noqa: E731
+    pred, md = evaluate.eval_batch_coarse_to_fine(cfg, pipe, batch, generator=None)
+    assert pred.shape == (2, 60, 100) and md.shape == (2, 5) and np.isfinite(pred).all() and np.isfinite(md).all()
+    # the first quadrant by hand (fresh per-sample generators: the later quadrants continue their streams)
+    keys = ("normalized_rgb", "raw_disp", "mask", "left_image", "right_image", "sim_disp", "raw_depth")
+    mini = {k: batch[k][:, :, :30, :50] for k in keys}
+    a, _ = evaluate.eval_batch_coarse_to_fine(cfg, pipe, batch, generator=gens())
+    b = evaluate.eval_batch(cfg, pipe, True, batch["fxb"], generator=gens(), **mini)[0]
+    np.testing.assert_array_equal(a[:, :30, :50], b)
+
+
 def test_eval_batch_sceneflow_variant_three_depth_channels():
     """conf/task/train_sceneflow.yaml: depth_channels = 3 with the 3-channel "average" normaliser (Cin = 12: sample 3 +
     left 3 + right 3 + raw 3), DDPM sampler, SceneFlow min/max mask + clip branch of eval_batch (evaluate.py:126-130)."""
