@@ -229,7 +229,7 @@ def test_eval_batch_coarse_to_fine_quadrants():
     mini = {k: batch[k][:, :, :30, :50] for k in keys}
     a, _ = evaluate.eval_batch_coarse_to_fine(cfg, pipe, batch, generator=gens())
     b = evaluate.eval_batch(cfg, pipe, True, batch["fxb"], generator=gens(), **mini)[0]
-    np.testing.assert_array_equal(a[:, :30, :50], b)
+    np.testing.assert_allclose(a[:, :30, :50], b, rtol=0, atol=2e-3)   # (statistics are summed with atomics)
 
 
 def test_eval_batch_sceneflow_variant_three_depth_channels():
