@@ -60,6 +60,16 @@ class WgradParams(C.Structure):
     ]
 
 
+class PackEntry(C.Structure):
+    """Mirror of ``d3_pack_entry``."""
+
+    _fields_ = [
+        ("w_offset", C.c_int64), ("w_pitch", C.c_int64), ("out_offset", C.c_int64),
+        ("col0", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32), ("n_out_taps", C.c_int32),
+        ("tap_map", C.c_int32 * 16),
+    ]
+
+
 class DDIMCoeffs(C.Structure):
     """Mirror of ``d3_ddim_coeffs``."""
 
@@ -192,6 +202,7 @@ def _declare(lib: C.CDLL) -> None:
         "d3_cast_f32_to_16": (i32, [vp, vp, i64, i32, vp]),
         "d3_gather_add": (i32, [vp, vp, vp, vp, i32, vp]),
         "d3_pack_taps16": (i32, [vp, i64, i32, i32, i32, C.POINTER(C.c_int32), i32, vp, i32, vp]),
+        "d3_pack_taps16_batched": (i32, [vp, vp, i32, i32, vp, vp, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here == header and library out of sync

@@ -547,12 +547,28 @@ __global__ void __launch_bounds__(256, 2) conv_out_bwd_kernel(const ConvOutBwdAr
   const int y1 = min(a.H, y0 + a.rows_per_block);
   const int npix = (y1 - y0) * a.W;
   const size_t plane = (size_t)a.H * a.W;
-  for (int pi = pslot; pi < npix; pi += 16) {
+  // software-pipelined over this thread's pixels: the activation vector of the next pixel is in flight while the current
+  // one is processed
+  int pi = pslot;
+  bool have = pi < npix;
+  uint4 h_next = make_uint4(0u, 0u, 0u, 0u);
+  if (have) {
+    const int yn = y0 + pi / a.W, xn = pi % a.W;
+    h_next = __ldg(reinterpret_cast<const uint4*>(a.h + (((size_t)b * a.H + yn) * a.W + xn) * a.pitch + vec * 8));
+  }
+  while (have) {
+    const uint4 h_cur = h_next;
     const int y = y0 + pi / a.W;
     const int x = pi % a.W;
     const size_t pix = ((size_t)b * a.H + y) * a.W + x;
+    pi += 16;
+    have = pi < npix;
+    if (have) {
+      const int yn = y0 + pi / a.W, xn = pi % a.W;
+      h_next = __ldg(reinterpret_cast<const uint4*>(a.h + (((size_t)b * a.H + yn) * a.W + xn) * a.pitch + vec * 8));
+    }
     float hv[8], av[8];
-    unpack8<DT>(__ldg(reinterpret_cast<const uint4*>(a.h + pix * a.pitch + vec * 8)), hv);
+    unpack8<DT>(h_cur, hv);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float z = fmaf(hv[k], sc[k], sh[k]);
@@ -564,23 +580,26 @@ __global__ void __launch_bounds__(256, 2) conv_out_bwd_kernel(const ConvOutBwdAr
     for (int d = 0; d < a.dc; ++d) {
       if (a.pass_d != 0 && d != a.pass_d) continue;
       const float* gp = a.dy + ((size_t)b * a.dc + d) * plane;
+      float g[9];
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         // forward: m[y][x] += w[t] * a[y + kh - 1][x + kw - 1]  =>  this pixel meets dy[y - kh + 1][x - kw + 1] through tap t
         const int yy = y - (t / 3) + 1, xx = x - (t % 3) + 1;
-        float g = 0.f;
-        if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) g = __ldg(gp + (size_t)yy * a.W + xx);
+        g[t] = (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) ? __ldg(gp + (size_t)yy * a.W + xx) : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
         if (a.pass_d == 0) {
           const float4 w0 = *reinterpret_cast<const float4*>(&s_w[(d * 9 + t) * 128 + vec * 8]);
           const float4 w1 = *reinterpret_cast<const float4*>(&s_w[(d * 9 + t) * 128 + vec * 8 + 4]);
-          dav[0] = fmaf(w0.x, g, dav[0]); dav[1] = fmaf(w0.y, g, dav[1]);
-          dav[2] = fmaf(w0.z, g, dav[2]); dav[3] = fmaf(w0.w, g, dav[3]);
-          dav[4] = fmaf(w1.x, g, dav[4]); dav[5] = fmaf(w1.y, g, dav[5]);
-          dav[6] = fmaf(w1.z, g, dav[6]); dav[7] = fmaf(w1.w, g, dav[7]);
+          dav[0] = fmaf(w0.x, g[t], dav[0]); dav[1] = fmaf(w0.y, g[t], dav[1]);
+          dav[2] = fmaf(w0.z, g[t], dav[2]); dav[3] = fmaf(w0.w, g[t], dav[3]);
+          dav[4] = fmaf(w1.x, g[t], dav[4]); dav[5] = fmaf(w1.y, g[t], dav[5]);
+          dav[6] = fmaf(w1.z, g[t], dav[6]); dav[7] = fmaf(w1.w, g[t], dav[7]);
         }
         if (d == a.pass_d) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(av[k], g, acc[t][k]);
+          for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(av[k], g[t], acc[t][k]);
         }
       }
     }
@@ -843,6 +862,45 @@ __global__ void __launch_bounds__(256) scale_by_rstd_kernel(float* __restrict__ 
   const double var = (sums[1] - (double)n * mean * mean) / (double)(n - 1);
   const float sd = (float)sqrt(var);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = x[i] / sd;
+}
+
+// All transposed weight packs of a model in ONE launch: a device table of entries (offsets into the fp32 master buffer
+// and into the 16-bit pack buffer) and the prefix sums of their 32 x 32 tile counts; a block finds its entry by binary
+// search.  (121 separate launches of pack_taps_kernel cost 1.5 ms per training step, all of it launch latency.)
+__global__ void __launch_bounds__(256) pack_taps_batched_kernel(const d3_pack_entry* __restrict__ entries,
+                                                                const int* __restrict__ tile_prefix, int n_entries,
+                                                                const float* __restrict__ w_base,
+                                                                uint16_t* __restrict__ out_base, int f16) {
+  __shared__ float tile[32][33];
+  const int tid = blockIdx.x;
+  int lo = 0, hi = n_entries - 1;
+  while (lo < hi) {                      // last entry whose first tile is <= tid
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_prefix[mid] <= tid) lo = mid; else hi = mid - 1;
+  }
+  const d3_pack_entry e = entries[lo];
+  int local = tid - tile_prefix[lo];
+  const int nco = e.Cout / 32, nci = e.Cin / 32;
+  const int cot = local % nco;
+  local /= nco;
+  const int cit = local % nci;
+  const int j = local / nci;
+  const int t = e.tap_map[j];
+  const int co0 = cot * 32, ci0 = cit * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* w = w_base + e.w_offset;
+  uint16_t* out = out_base + e.out_offset;
+  for (int r = ty; r < 32; r += 8) {
+    float v = 0.f;
+    if (t >= 0) v = w[(size_t)(co0 + r) * e.w_pitch + e.col0 + (size_t)t * e.Cin + ci0 + tx];
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const float v = tile[tx][r];
+    const size_t o = ((size_t)(ci0 + r) * e.n_out_taps + j) * e.Cout + co0 + tx;
+    out[o] = f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  }
 }
 
 int grid_for(size_t total, int per_block = 256, int waves = 16) {
@@ -1152,6 +1210,18 @@ extern "C" int d3_div_by_std(float* x, int64_t n, double* workspace2, void* stre
   sum_sumsq_kernel<<<grid_for((size_t)n, 256 * 8, 8), 256, 0, stream>>>(x, (size_t)n, workspace2);
   D3_LAUNCH_CHECK();
   scale_by_rstd_kernel<<<grid_for((size_t)n, 256 * 4, 8), 256, 0, stream>>>(x, (size_t)n, workspace2);
+  D3_LAUNCH_CHECK();
+  return D3_OK;
+}
+
+extern "C" int d3_pack_taps16_batched(const d3_pack_entry* entries_dev, const int32_t* tile_prefix_dev, int n_entries,
+                                      int total_tiles, const float* w_base, void* out_base, int dtype16, void* stream_) {
+  using namespace d3;
+  D3_REQUIRE(entries_dev && tile_prefix_dev && w_base && out_base && n_entries > 0 && total_tiles > 0,
+             "pack_taps16_batched: bad arguments");
+  D3_REQUIRE(dtype16 == D3_DTYPE_BF16 || dtype16 == D3_DTYPE_F16, "pack_taps16_batched: 16-bit dtypes only");
+  pack_taps_batched_kernel<<<total_tiles, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      entries_dev, tile_prefix_dev, n_entries, w_base, static_cast<uint16_t*>(out_base), dtype16 == D3_DTYPE_F16);
   D3_LAUNCH_CHECK();
   return D3_OK;
 }

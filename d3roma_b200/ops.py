@@ -943,3 +943,31 @@ def pack_taps16(w: torch.Tensor, col0: int, Cin: int, tap_map, out: torch.Tensor
     _lib.check(_lib.lib().d3_pack_taps16(w.data_ptr(), w.stride(0), col0, Cin, Cout, tm, len(tap_map), out.data_ptr(),
                                          _dt(out), _stream()))
     return out
+
+
+def make_pack_table(entries, device):
+    """Device-side table for ``pack_taps16_batched``: ``entries`` = [(w_offset, w_pitch, out_offset, col0, Cin, Cout,
+    tap_map)] (offsets in elements).  Returns (entries tensor (bytes), tile-prefix tensor, n_entries, total_tiles)."""
+    import numpy as np
+    arr = (_lib.PackEntry * len(entries))()
+    prefix, total = [], 0
+    for i, (wo, wp, oo, col0, cin, cout, tm) in enumerate(entries):
+        if cin % 32 or cout % 32 or not 1 <= len(tm) <= 16:
+            raise ValueError("make_pack_table: Cin / Cout must be multiples of 32, 1..16 output taps")
+        e = arr[i]
+        e.w_offset, e.w_pitch, e.out_offset = wo, wp, oo
+        e.col0, e.Cin, e.Cout, e.n_out_taps = col0, cin, cout, len(tm)
+        for j, t in enumerate(tm):
+            e.tap_map[j] = t
+        prefix.append(total)
+        total += (cout // 32) * (cin // 32) * len(tm)
+    raw = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).to(device)
+    pre = torch.tensor(prefix, dtype=torch.int32, device=device)
+    return raw, pre, len(entries), total
+
+
+def pack_taps16_batched(table, w_base: torch.Tensor, out_base: torch.Tensor) -> torch.Tensor:
+    raw, pre, n, total = table
+    _lib.check(_lib.lib().d3_pack_taps16_batched(raw.data_ptr(), pre.data_ptr(), n, total, w_base.data_ptr(),
+                                                 out_base.data_ptr(), _dt(out_base), _stream()))
+    return out_base

@@ -310,15 +310,19 @@ class UNetTrainer:
             total += _align(cin * len(tm) * cout)
         self._dg_buf = torch.zeros(total, dtype=self._adt, device=self.device)
         off = 0
+        table = []
         for key, name, col0, cin, cout, tm in ent:
             n = cin * len(tm) * cout
             self._dg[key] = self._dg_buf[off:off + n].view(cin, len(tm) * cout)
+            w_off, w_shape = self._layout[name]
+            table.append((w_off, w_shape[1], off, col0, cin, cout, tm))
             off = _align(off + n)
         self._dg_entries = ent
+        self._dg_table = ops.make_pack_table(table, self.device)
 
     def _refresh_dgrad_packs(self):
-        for key, name, col0, cin, cout, tm in self._dg_entries:
-            ops.pack_taps16(self.P(name), col0, cin, tm, self._dg[key])
+        """Every transposed weight pack from the fp32 master buffer, one launch (``d3_pack_taps16_batched``)."""
+        ops.pack_taps16_batched(self._dg_table, self._p, self._dg_buf)
 
     # ------------------------------------------------------------------ gradient bookkeeping
     # Every forward tensor collects the gradient contributions of its consumers as a list of pending 16-bit tensors

@@ -495,6 +495,18 @@ int d3_gather_add(const float* src, const int32_t* ia, const int32_t* ib, float*
  * (flipped taps for a stride-1 conv, the phase sub-sets of a stride-2 conv, the plain transpose for 1x1). */
 int d3_pack_taps16(const float* w, int64_t w_pitch, int col0, int Cin, int Cout, const int32_t* tap_map, int n_out_taps,
                    void* out, int dtype16, void* stream);
+/* The same for every pack of a model in one launch: `entries_dev` / `tile_prefix_dev` are DEVICE arrays (n_entries
+ * entries; tile_prefix[i] = number of 32 x 32 tiles, Cout/32 * Cin/32 * n_out_taps each, of the entries before i;
+ * total_tiles = their sum); offsets are in elements from w_base (fp32 master buffer) / out_base (16-bit pack buffer). */
+typedef struct d3_pack_entry {
+  int64_t w_offset;
+  int64_t w_pitch;
+  int64_t out_offset;
+  int32_t col0, Cin, Cout, n_out_taps;
+  int32_t tap_map[16];
+} d3_pack_entry;
+int d3_pack_taps16_batched(const d3_pack_entry* entries_dev, const int32_t* tile_prefix_dev, int n_entries, int total_tiles,
+                           const float* w_base, void* out_base, int dtype16, void* stream);
 
 #ifdef __cplusplus
 }

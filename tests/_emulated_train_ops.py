@@ -235,3 +235,15 @@ def bilinear_upsample_acc_(dst, src, mul):
 def div_by_std_(x):
     x /= x.std()
     return x
+
+
+def make_pack_table(entries, device):
+    return list(entries)
+
+
+def pack_taps16_batched(table, w_base, out_base):
+    for wo, wp, oo, col0, cin, cout, tm in table:
+        rows = cout
+        w = w_base[wo:wo + rows * wp].view(rows, wp)
+        pack_taps16(w, col0, cin, tm, out_base[oo:oo + cin * len(tm) * cout].view(cin, len(tm) * cout))
+    return out_base

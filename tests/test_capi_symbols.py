@@ -39,6 +39,7 @@ def test_struct_layouts_match_header():
     from d3roma_b200 import _lib
     text = (ROOT / "include" / "d3roma_b200.h").read_text()
     for cname, cls in (("d3_conv_params", _lib.ConvParams), ("d3_wgrad_params", _lib.WgradParams),
+                       ("d3_pack_entry", _lib.PackEntry),
                        ("d3_ddim_coeffs", _lib.DDIMCoeffs),
                        ("d3_ddpm_coeffs", _lib.DDPMCoeffs), ("d3_guidance_params", _lib.GuidanceParams)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), text, flags=re.S).group(1)
@@ -49,7 +50,7 @@ def test_struct_layouts_match_header():
             if not decl:
                 continue
             decl = re.sub(r"^(const\s+)?(void|float|double|int32_t|int64_t)\s*\*?", "", decl).strip()
-            fields += [f.strip().lstrip("*").strip() for f in decl.split(",")]
+            fields += [re.sub(r"\[\d+\]$", "", f.strip().lstrip("*").strip()) for f in decl.split(",")]
         assert fields == [f[0] for f in cls._fields_], (cname, fields)
 
 
