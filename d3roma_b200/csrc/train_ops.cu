@@ -525,7 +525,12 @@ __global__ void __launch_bounds__(256, 2) conv_out_bwd_kernel(const ConvOutBwdAr
     s_mean[threadIdx.x] = (float)mean;
     s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)a.eps));
   }
-  for (int i = threadIdx.x; i < a.dc * 9 * 128; i += 256) s_w[i] = a.w[i];
+  // weights staged as [d * 9 + t][half][vec][4]: the 16 channel-vector lanes of a pixel read consecutive 16-byte
+  // words (the straight [..][128] layout made every LDS.128 a 4-way bank conflict: ncu, 149 M conflicts per launch)
+  for (int i = threadIdx.x; i < a.dc * 9 * 128; i += 256) {
+    const int row = i >> 7, c = i & 127;
+    s_w[row * 128 + ((c >> 2) & 1) * 64 + (c >> 3) * 4 + (c & 3)] = a.w[i];
+  }
   for (int i = threadIdx.x; i < 9 * 128; i += 256) s_dw[i] = 0.f;
   __syncthreads();
   const int vec = threadIdx.x & 15;
@@ -590,8 +595,8 @@ __global__ void __launch_bounds__(256, 2) conv_out_bwd_kernel(const ConvOutBwdAr
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         if (a.pass_d == 0) {
-          const float4 w0 = *reinterpret_cast<const float4*>(&s_w[(d * 9 + t) * 128 + vec * 8]);
-          const float4 w1 = *reinterpret_cast<const float4*>(&s_w[(d * 9 + t) * 128 + vec * 8 + 4]);
+          const float4 w0 = *reinterpret_cast<const float4*>(&s_w[(d * 9 + t) * 128 + vec * 4]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&s_w[(d * 9 + t) * 128 + 64 + vec * 4]);
           dav[0] = fmaf(w0.x, g[t], dav[0]); dav[1] = fmaf(w0.y, g[t], dav[1]);
           dav[2] = fmaf(w0.z, g[t], dav[2]); dav[3] = fmaf(w0.w, g[t], dav[3]);
           dav[4] = fmaf(w1.x, g[t], dav[4]); dav[5] = fmaf(w1.y, g[t], dav[5]);
