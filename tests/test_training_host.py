@@ -261,3 +261,30 @@ def test_pyramid_noise_matches_reference(trainer_mod):
         got = trainer_mod.pyramid_noise_like(x)
         assert float((got - want).abs().max()) < 1e-5
         assert abs(float(got.std()) - 1.0) < 1e-5
+
+
+def test_gradient_accumulation_over_micro_batches(trainer_mod):
+    """``accelerator.accumulate`` (train.py:281): two forward / backward passes without ``zero_grad`` accumulate into the
+    flat gradient buffer - equal to autograd accumulating the same two losses."""
+    B, H, W, dc, cin = 1, 32, 32, 1, 8
+    ref = make_unet(cin, dc, seed=6, sample_size=(H, W))
+    tr = trainer_mod.UNetTrainer(in_channels=cin, out_channels=dc, device="cpu")
+    tr._adt = torch.float32
+    tr.load_state_dict(ref.state_dict())
+    ac = torch.cumprod(1 - S.make_betas("squaredcos_cap_v2", 128), 0)
+    ref.zero_grad(set_to_none=True)
+    tr.zero_grad()
+    for seed in (50, 51):
+        clean, cond, noise, t, mask, w = _inputs(B, H, W, dc, cin - dc, seed=seed)
+        noisy = S.add_noise(clean, noise, t, ac)
+        out = ref(torch.cat([noisy, cond], 1), t)
+        out = out.sample if hasattr(out, "sample") else out
+        ((out * mask - clean * mask) ** 2).mean().backward()           # grads accumulate in .grad
+        pred = tr.forward(noisy, cond, t)
+        dy, _ = E.masked_loss_grad(pred, clean, mask, None, grad_scale=1.0 / pred.numel(), dbias=tr.G("out.bias"))
+        tr.backward(dy, bias_grad_done=True)
+    got = tr.grad_dict()
+    gmax = max(float(p.grad.abs().max()) for p in ref.parameters())
+    for k, p in ref.named_parameters():
+        scale = max(float(p.grad.abs().max()), 1e-6 * gmax)
+        assert float((got[k] - p.grad).abs().max()) / scale < 2e-4, k
