@@ -27,8 +27,9 @@
 // of 4 x 256 + 1 x 128).
 //
 // One persistent CTA per SM: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue;
-// 4-stage smem ring of {dy 16 KB, x 32 KB}; two 256-column fp32 accumulators in TMEM (the epilogue of one work item runs
-// under the MMAs of the next).
+// generic form: 4-stage smem ring of {dy 16 KB, x 32 KB}, two 256-column fp32 accumulators in TMEM (the epilogue of one
+// work item runs under the MMAs of the next); halo form: 6 stages of {dy 16 KB, 2 x 10 KB halo blocks}, one 384-column
+// accumulator set.
 //
 // Replaces the weight half of aten::convolution_backward (cuDNN wgrad) in the training step of the reference
 // (/root/reference/train.py:157-538, `accelerator.backward(loss)` at :455).
