@@ -361,7 +361,12 @@ class UNetTrainer:
         return first
 
     # ------------------------------------------------------------------ forward pieces (each records its backward)
-    def _gn(self, x1: _Act, gname: str, bname: str, x2: Optional[_Act] = None, silu: bool = True, colsum=None):
+    def _gn(self, x1: _Act, gname: str, bname: str, x2: Optional[_Act] = None, silu: bool = True, colsum=None,
+            holder: Optional[dict] = None):
+        """GroupNorm(+SiLU) over ``x1`` (and ``x2``: the virtual concat of an up block).  ``holder``: a dict in which the
+        same resnet's conv2 backward leaves ``"dsc"``, the gradient its 1x1 shortcut sends to the (concatenated) input -
+        a dense tensor over exactly the channels of this GroupNorm's input, so it rides into dx as an addend instead of
+        being split and summed per source."""
         g, b = self.P(gname), self.P(bname)
         a = ops.groupnorm_silu(x1.t, x1.stats, g, b, x2=None if x2 is None else x2.t,
                                stats2=None if x2 is None else x2.stats, silu=silu)
@@ -370,13 +375,21 @@ class UNetTrainer:
             self._consume(x2.t)
         # the first consumer's backward runs last: with a single source its dx (+ everything pending) IS the total
         # gradient of x1, so the bias gradient of the conv that produced x1 (channel sums) is taken in the same pass
-        req = self._bias_req.get(id(x1.t)) if (first and x2 is None and colsum is None) else None
+        req = self._bias_req.get(id(x1.t)) if (first and colsum is None) else None
 
         def bwd():
             da = self._take(a)
-            addends = self._pending(x1.t, 3) if x2 is None else ()
+            extra = holder.pop("dsc", None) if holder else None
+            if x2 is None:
+                addends = self._pending(x1.t, 3 if extra is None else 2)
+            else:
+                addends = []
+            if extra is not None:
+                addends = list(addends) + [extra]
             cs = colsum
-            if req is not None:
+            # single source: dx + the addends is x1's total gradient.  Concat: true for the x1 part when the only other
+            # consumer of x1 was this resnet's shortcut (folded in through `extra`) - nothing else may be pending
+            if req is not None and (x2 is None or (extra is not None and id(x1.t) not in self._grads)):
                 cs, req["done"] = req["bg"], True
             dx = ops.groupnorm_silu_bwd(x1.t, x1.stats, g, b, da, x2=None if x2 is None else x2.t,
                                         stats2=None if x2 is None else x2.stats, silu=silu, addends=addends,
@@ -392,7 +405,7 @@ class UNetTrainer:
 
     def _conv(self, x: torch.Tensor, wname: str, bias: torch.Tensor, ksize: int, B: int, *, stride: int = 1, sc=(),
               residual: Optional[torch.Tensor] = None, want_stats: bool = True, bias_grad: Optional[torch.Tensor] = None,
-              need_dx: bool = True) -> _Act:
+              need_dx: bool = True, sc_holder: Optional[dict] = None) -> _Act:
         w = self.W16(wname)
         cout = w.shape[0]
         stats = self._arena.take(B, cout) if want_stats else None
@@ -431,10 +444,13 @@ class UNetTrainer:
             if sc:
                 csc = sum(s.shape[3] for s in sc)
                 dsc = ops.conv2d_igemm(dy, self._dg[wname + ".sc"], self._zero_bias[:csc], ksize=1)
-                o = 0
-                for s in sc:
-                    self._acc(s, dsc[..., o:o + s.shape[3]])
-                    o += s.shape[3]
+                if sc_holder is not None:
+                    sc_holder["dsc"] = dsc       # picked up by the resnet's norm1 backward (same channels, same order)
+                else:
+                    o = 0
+                    for s in sc:
+                        self._acc(s, dsc[..., o:o + s.shape[3]])
+                        o += s.shape[3]
             if residual is not None:
                 self._acc(residual, dy)
         self._tape.append(bwd)
@@ -443,16 +459,17 @@ class UNetTrainer:
     def _resnet(self, p: str, h: _Act, skip: Optional[_Act], cout: int, rows: torch.Tensor, B: int) -> _Act:
         o = self._temb_off[p]
         r = self.rows_total
-        a1 = self._gn(h, p + ".n1.g", p + ".n1.b", x2=skip)
+        cin = h.t.shape[3] + (0 if skip is None else skip.t.shape[3])
+        holder = {} if cin != cout else None
+        a1 = self._gn(h, p + ".n1.g", p + ".n1.b", x2=skip, holder=holder)
         h1 = self._conv(a1, p + ".w1", rows[:, o:o + cout], 3, B)
         # norm2's backward yields conv1's output gradient: its per-sample channel sums are the time-embedding gradient
         a2 = self._gn(h1, p + ".n2.g", p + ".n2.b", colsum=self._d_rows[:, o:o + cout])
-        cin = h.t.shape[3] + (0 if skip is None else skip.t.shape[3])
         b2 = self._derived[r + o:r + o + cout]
         bg = self.G("c2.b")[o:o + cout]
         if cin != cout:
             sc = [h.t] + ([] if skip is None else [skip.t])
-            return self._conv(a2, p + ".w2", b2, 3, B, sc=sc, bias_grad=bg)
+            return self._conv(a2, p + ".w2", b2, 3, B, sc=sc, bias_grad=bg, sc_holder=holder)
         return self._conv(a2, p + ".w2", b2, 3, B, residual=h.t, bias_grad=bg)
 
     def _attention(self, a: str, h: _Act, B: int) -> _Act:
