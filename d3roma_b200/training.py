@@ -50,6 +50,7 @@ class UNetTrainer:
         self._adt = torch.bfloat16 if compute_dtype == "bf16" else torch.float16
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.max_grad_norm, self.loss_scale, self.loss_type = max_grad_norm, float(loss_scale), loss_type
+        self.overlap_allreduce = True   # data parallel: all-reduce the up path's gradients under the down path's backward
         self.device = torch.device(device)
         self.step_count = 0
         self._specs = _resnet_specs()
@@ -58,6 +59,12 @@ class UNetTrainer:
         self._tape: List = []
         self._grads: Dict[int, tuple] = {}
         self._consumed, self._bias_req = set(), {}
+        self._tape_up_start = 0
+        self._early_done = False
+        self._early_reduce = None      # set by train_step for world_size > 1 (overlapped gradient all-reduce)
+        self._reduce_stream = None
+        self._early_work = None
+        self.overlapped_reductions = 0   # steps whose up-path gradients were reduced under the backward
 
     # ------------------------------------------------------------------ parameter layout
     def _build_layout(self):
@@ -74,11 +81,14 @@ class UNetTrainer:
 
         add("conv_in.w", 128, 128)
         rows = 0
+        self._up_range = [None, None]   # [start, end) of the up blocks' conv / attention weights in the flat buffers
         self._temb_off: Dict[str, int] = {}
         self._attn: List[Tuple[str, int]] = []
         for kind, i, j, cin_h, cin_s, cout, attn in self._specs:
             p = UNet2DModel._rprefix(kind, i, j)
             cin = cin_h + cin_s
+            if kind == "up" and self._up_range[0] is None:
+                self._up_range[0] = off
             add(p + ".w1", cout, 9 * cin)
             add(p + ".w2", cout, 9 * cout + (cin if cin != cout else 0))
             self._temb_off[p] = rows
@@ -88,6 +98,7 @@ class UNetTrainer:
                 add(a + ".wqkv", 3 * cout, cout)
                 add(a + ".wo", cout, cout)
                 self._attn.append((a, cout))
+        self._up_range[1] = off
         for i in range(5):
             c = BLOCK_OUT[i]
             add(f"down_blocks.{i}.downsamplers.0.conv.w", c, 9 * c)
@@ -536,6 +547,7 @@ class UNetTrainer:
             h = self._resnet(UNet2DModel._rprefix(kind, bi, bj), h, None, cout, rows, B)
             if attn:
                 h = self._attention(UNet2DModel._aprefix(kind, bi, bj), h, B)
+        self._tape_up_start = len(self._tape)     # closures from here on belong to the up path (they run FIRST in backward)
         for i in range(6):
             for j in range(3):
                 kind, bi, bj, cin_h, cin_s, cout, attn = next(it)
@@ -572,8 +584,10 @@ class UNetTrainer:
         da = ops.conv_out_bwd(h.t, h.stats, self.P("out.g"), self.P("out.b"), self.P("out.w"), d_out, self.G("out.w"))
         self._put(h.t, ops.groupnorm_silu_bwd(h.t, h.stats, self.P("out.g"), self.P("out.b"), da,
                                               dgamma=self.G("out.g"), dbeta=self.G("out.b")))
-        for fn in reversed(self._tape):
-            fn()
+        for idx in range(len(self._tape) - 1, -1, -1):
+            self._tape[idx]()
+            if idx == self._tape_up_start and self._early_reduce is not None:
+                self._early_reduce()              # the up path's weight gradients are final: start their all-reduce
         self._tape, self._grads, self._head = [], {}, None
         self._consumed, self._bias_req = set(), {}
         # time path: rows = Linear(SiLU(emb)); emb = Linear(SiLU(a1)); a1 = Linear(e0)
@@ -596,7 +610,20 @@ class UNetTrainer:
         gradients are first summed over the ranks (NCCL all-reduce) and averaged, as DDP does."""
         if world_size > 1:
             import torch.distributed as dist
-            dist.all_reduce(self._g)
+            if self._early_done:
+                # the up path's weights (59 % of the buffer) were reduced during the backward (side stream on the
+                # device, an asynchronous work handle on the host / gloo)
+                lo, hi = self._up_range
+                dist.all_reduce(self._g[:lo])
+                dist.all_reduce(self._g[hi:])
+                if self._early_work is not None:
+                    self._early_work.wait()
+                    self._early_work = None
+                else:
+                    torch.cuda.current_stream().wait_stream(self._reduce_stream)
+                self._early_done = False
+            else:
+                dist.all_reduce(self._g)
         self.step_count += 1
         self._sumsq.zero_()
         ops.sumsq(self._g, self._sumsq)
@@ -631,7 +658,27 @@ class UNetTrainer:
         dy, loss_sum = ops.masked_loss_grad(pred, target, None if mask is None else mask.contiguous(), w,
                                             l1=self.loss_type == "l1", grad_scale=self.loss_scale / n,
                                             dbias=self.G("out.bias"))
+        self._early_done = False
+        if world_size > 1 and self.overlap_allreduce:
+            import torch.distributed as dist
+            if pred.is_cuda and self._reduce_stream is None:
+                self._reduce_stream = torch.cuda.Stream(device=pred.device)
+
+            def early():
+                # every up-path closure has run: their weight gradients are complete while the whole down path is still
+                # to come - reduce them under the rest of the backward
+                up = self._g[self._up_range[0]:self._up_range[1]]
+                if pred.is_cuda:
+                    self._reduce_stream.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(self._reduce_stream):
+                        dist.all_reduce(up)
+                else:
+                    self._early_work = dist.all_reduce(up, async_op=True)
+                self._early_done = True
+                self.overlapped_reductions += 1
+            self._early_reduce = early
         self.backward(dy, bias_grad_done=True)
+        self._early_reduce = None
         self.optimizer_step(world_size)
         self.last_loss_sum = loss_sum          # fp64 [B]: sum of network_loss over each sample (train.py:422 `losses`)
         ls = loss_sum if w is None else loss_sum * w.double()

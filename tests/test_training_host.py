@@ -138,8 +138,11 @@ def _run_steps(training, shard, world):
     for step in range(2):
         clean, cond, noise, t, mask, w = (shard(x) for x in _inputs(B, H, W, dc, cin - dc, seed=20 + step))
         tr.train_step(clean, cond, noise, t, Sched, mask=mask, weights=w, prediction_type="epsilon", world_size=world)
+    # with more than one rank the up path's gradients are all-reduced while the down path's backward still runs
+    assert tr.overlapped_reductions == (2 if world > 1 else 0)
     sd = tr.state_dict()
-    keys = ["conv_in.weight", "mid_block.attentions.0.to_q.weight", "up_blocks.5.resnets.2.conv2.weight",
+    keys = ["conv_in.weight", "mid_block.attentions.0.to_q.weight", "up_blocks.5.resnets.2.conv2.weight", "up_blocks.0.resnets.0.conv1.weight",
+            "up_blocks.1.attentions.1.to_out.0.weight", "up_blocks.3.resnets.1.conv_shortcut.weight",
             "down_blocks.2.resnets.0.conv_shortcut.weight", "time_embedding.linear_2.bias", "conv_out.bias"]
     return {k: sd[k] for k in keys}
 
