@@ -691,9 +691,16 @@ __global__ void __launch_bounds__(256) cross_attention_small_kernel(const uint16
 
 // ---------------------------------------------------------------------------------------------------------------------
 // y[n][r] = act_out(bias[r] + sum_k w[r][k] * act_in(x[n][k])), fp32, n <= a few dozen rows.  One warp per output row r.
-// act: 0 none, 1 SiLU.
+// act: 0 none, 1 SiLU, 2 GELU (exact, erf: transformers' "gelu" of the CLIP text MLP), 3 quick GELU x * sigmoid(1.702 x).
 // ---------------------------------------------------------------------------------------------------------------------
-D3_DEVINL float act_f(float x, int act) { return act == 1 ? x / (1.0f + expf(-x)) : x; }
+D3_DEVINL float act_f(float x, int act) {
+  switch (act) {
+    case 1: return x / (1.0f + expf(-x));
+    case 2: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    case 3: return x / (1.0f + expf(-1.702f * x));
+    default: return x;
+  }
+}
 
 __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ x, int n_rows, int K,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
@@ -1059,6 +1066,7 @@ extern "C" int d3_cross_attention_small(const void* q, int q_pitch, const float*
 extern "C" int d3_linear_small(const float* x, int n_rows, int K, const float* w, const float* bias, int rows,
                                int act_in, int act_out, float* out, int out_stride, void* stream) {
   D3_REQUIRE(x && w && out && n_rows > 0 && rows > 0 && K % 4 == 0 && out_stride >= rows, "linear_small: bad arguments");
+  D3_REQUIRE(act_in >= 0 && act_in <= 3 && act_out >= 0 && act_out <= 3, "linear_small: activation code must be 0..3");
   const int blocks = ceil_div(rows * 32, 256);
   D3_CHECK_CUDA(launch_pdl(linear_small_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), x, n_rows,
                            K, w, bias, rows, act_in, act_out, out, out_stride));

@@ -1114,6 +1114,7 @@ extern "C" int d3_linear_small_bwd(const float* x, int n_rows, int K, int act_in
   using namespace d3;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   D3_REQUIRE(x && dy && n_rows > 0 && K > 0 && rows > 0, "linear_small_bwd: bad arguments");
+  D3_REQUIRE(act_in == 0 || act_in == 1, "linear_small_bwd: only identity / SiLU inputs have a backward (got %d)", act_in);
   if (dw != nullptr) {
     linear_bwd_w_kernel<<<(unsigned)(((size_t)rows * K + 255) / 256), 256, 0, stream>>>(x, act_in, dy, n_rows, K, rows, dw, db);
     D3_LAUNCH_CHECK();

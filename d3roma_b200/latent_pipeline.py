@@ -5,10 +5,12 @@ keys, RNG consumption and output semantics, over this package's scheduler kernel
 Networks: ``unet`` is ``d3roma_b200.UNet2DConditionModel`` and ``vae`` ``d3roma_b200.AutoencoderKL``
 (the SD-2.1 UNet / SD VAE architectures on the sm_100a kernels, ``unet_condition.py`` / ``autoencoder_kl.py``); any object
 with the same call surface works too (the loop only uses ``unet(x, t, ctx).sample`` and ``vae.encoder / quant_conv /
-post_quant_conv / decoder``, exactly what the reference touches, ``train.py:743-772, 821-833``).  The CLIP text encoder is
-NOT implemented: its only use on this path is the embedding of the empty prompt, a constant ``[1, 2, 1024]`` tensor that
-callers pass as ``empty_text_embed`` (the argument the reference provides for exactly that, custom_pipelines.py:229,
-299-301); when it is omitted, ``tokenizer`` / ``text_encoder`` must be the caller's own transformers objects.  This file is the reference's own part of
+post_quant_conv / decoder``, exactly what the reference touches, ``train.py:743-772, 821-833``).  ``text_encoder`` is
+``d3roma_b200.CLIPTextModel`` (``text_encoder.py``; fp32 kernels) or the caller's transformers object: its only use on
+this path is the embedding of the empty prompt, a constant ``[1, 2, 1024]`` tensor, which callers may also pass
+directly as ``empty_text_embed`` (the argument the reference provides for exactly that, custom_pipelines.py:229,
+299-301).  With ``tokenizer=None`` the package's encoder supplies the two token ids of ``""`` itself (the BPE tokenizer,
+host-side vocabulary files, is not rebuilt).  This file is the reference's own part of
 the path: the loop, its latent encode / decode conventions (``encode_rgb`` :47-59, ``encode_disp`` :35-45,
 ``__decode_depth`` :255-272), and the scheduler steps (``d3_sched_ddim_step`` / ``d3_sched_ddpm_step``) with the guidance
 hook wiring of :389-399.
@@ -113,6 +115,11 @@ class GuidedLatentDiffusionPipeline:
 
     def _encode_empty_text(self) -> torch.Tensor:
         """custom_pipelines.py:241-253: embedding of the empty prompt ([1, 2, 1024] for the SD-2.1 text encoder)."""
+        if self.tokenizer is None:
+            # d3roma_b200.CLIPTextModel knows the two token ids of "" (BOS, EOS); any other encoder needs its tokenizer
+            if not hasattr(self.text_encoder, "encode_empty_prompt"):
+                raise ValueError("GuidedLatentDiffusionPipeline: pass empty_text_embed, or a tokenizer with the text encoder")
+            return self.text_encoder.encode_empty_prompt()
         tok = self.tokenizer("", padding="do_not_pad", max_length=self.tokenizer.model_max_length, truncation=True,
                              return_tensors="pt")
         return self.text_encoder(tok.input_ids.to(self.text_encoder.device))[0]

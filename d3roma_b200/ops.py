@@ -401,7 +401,7 @@ def cross_attention_small(q: torch.Tensor, kc: torch.Tensor, vc: torch.Tensor) -
 
 def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act_in: int = 0,
                  act_out: int = 0) -> torch.Tensor:
-    """fp32 [n, K] x fp32 [rows, K]^T (+ bias) -> [n, rows]; act 0 = identity, 1 = SiLU."""
+    """fp32 [n, K] x fp32 [rows, K]^T (+ bias) -> [n, rows]; act 0 = identity, 1 = SiLU, 2 = GELU (erf), 3 = quick GELU."""
     n, K = x.shape
     rows = w.shape[0]
     if w.shape[1] != K or x.dtype != torch.float32 or w.dtype != torch.float32 or not (x.is_contiguous() and w.is_contiguous()):
@@ -409,6 +409,45 @@ def linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] 
     out = torch.empty((n, rows), dtype=torch.float32, device=x.device)
     _lib.check(_lib.lib().d3_linear_small(x.data_ptr(), n, K, w.data_ptr(), _ptr(bias), rows, act_in, act_out,
                                           out.data_ptr(), rows, _stream()))
+    return out
+
+
+def embed_tokens(ids: torch.Tensor, token_embedding: torch.Tensor, position_embedding: torch.Tensor) -> torch.Tensor:
+    """int64 [B, L] token ids -> fp32 [B*L, D]: token_embedding[id] + position_embedding[position]."""
+    if ids.dtype != torch.int64 or ids.dim() != 2 or not ids.is_contiguous():
+        raise ValueError("embed_tokens: contiguous int64 [B, L] ids expected")
+    B, L = ids.shape
+    V, D = token_embedding.shape
+    lo, hi = int(ids.min()), int(ids.max())
+    if lo < 0 or hi >= V:
+        raise IndexError(f"embed_tokens: token id out of range [0, {V}) (got {lo} .. {hi})")
+    out = torch.empty((B * L, D), dtype=torch.float32, device=ids.device)
+    _lib.check(_lib.lib().d3_embed_tokens(ids.data_ptr(), B * L, L, _f32c(token_embedding, "token_embedding").data_ptr(),
+                                          V, _f32c(position_embedding, "position_embedding").data_ptr(),
+                                          position_embedding.shape[0], D, out.data_ptr(), _stream()))
+    return out
+
+
+def layernorm_f32(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """LayerNorm over the rows of a contiguous fp32 [M, C] matrix."""
+    x = _f32c(x, "x")
+    M, C_ = x.shape
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().d3_layernorm_f32(x.data_ptr(), M, C_, _f32c(gamma, "gamma").data_ptr(),
+                                           _f32c(beta, "beta").data_ptr(), eps, out.data_ptr(), _stream()))
+    return out
+
+
+def causal_attention_f32(qkv: torch.Tensor, B: int, L: int, heads: int, scale: float) -> torch.Tensor:
+    """Fused fp32 [B*L, 3*D] rows (q | k | v) -> fp32 [B*L, D]: per-head softmax over the keys j <= i."""
+    qkv = _f32c(qkv, "qkv")
+    D = qkv.shape[1] // 3
+    if qkv.shape != (B * L, 3 * D) or D % heads:
+        raise ValueError("causal_attention_f32: qkv must be [B*L, 3*D] with D divisible by heads")
+    out = torch.empty((B * L, D), dtype=torch.float32, device=qkv.device)
+    es = qkv.element_size()
+    _lib.check(_lib.lib().d3_causal_attention_f32(qkv.data_ptr(), qkv.data_ptr() + D * es, qkv.data_ptr() + 2 * D * es,
+                                                  3 * D, B, L, heads, D // heads, scale, out.data_ptr(), D, _stream()))
     return out
 
 

@@ -374,10 +374,24 @@ int d3_attention_hd64_tc(const void* q, int q_pitch, const void* k, int k_pitch,
  * C = 64 * heads. */
 int d3_cross_attention_small(const void* q, int q_pitch, const float* kc, const float* vc, int B, int N, int L, int C,
                              void* out, int out_pitch, int dtype, void* stream);
-/* out[n][r] = act_out(bias[r] + sum_k w[r][k] * act_in(x[n][k])), fp32, act 0 = identity / 1 = SiLU: the time-embedding
- * MLP, all time_emb_proj layers stacked, the context key / value projections.  bias may be NULL; K % 4 == 0. */
+/* out[n][r] = act_out(bias[r] + sum_k w[r][k] * act_in(x[n][k])), fp32, act 0 = identity / 1 = SiLU / 2 = GELU (erf) /
+ * 3 = quick GELU: the time-embedding MLP, all time_emb_proj layers stacked, the context key / value projections, the
+ * Linear layers of the text encoder.  bias may be NULL; K % 4 == 0. */
 int d3_linear_small(const float* x, int n_rows, int K, const float* w, const float* bias, int rows, int act_in,
                     int act_out, float* out, int out_stride, void* stream);
+/* Text encoder of the latent pipeline (custom_pipelines.py:260-287 `__encode_empty_text`: tokenizer("") ->
+ * text_encoder(input_ids)[0]; transformers CLIPTextModel - embeddings, pre-LayerNorm transformer layers with a causal
+ * mask, final LayerNorm), fp32 throughout; its Linear layers are d3_linear_small calls.
+ *   d3_embed_tokens: out[n][:] = token_embedding[ids[n]][:] + position_embedding[n % seq_len][:]  (ids int64 on the device)
+ *   d3_layernorm_f32: LayerNorm over the rows of fp32 [M][C]
+ *   d3_causal_attention_f32: q / k / v fp32 rows of B*L tokens (row pitch `pitch`, head h at [h*head_dim, (h+1)*head_dim)):
+ *     out[i] = softmax_j<=i(q_i . k_j * scale) v_j per head; L <= 128. */
+int d3_embed_tokens(const int64_t* ids, int n, int seq_len, const float* token_embedding, int vocab,
+                    const float* position_embedding, int max_positions, int D, float* out, void* stream);
+int d3_layernorm_f32(const float* x, int64_t M, int C, const float* gamma, const float* beta, float eps, float* out,
+                     void* stream);
+int d3_causal_attention_f32(const float* q, const float* k, const float* v, int pitch, int B, int L, int heads,
+                            int head_dim, float scale, float* out, int out_pitch, void* stream);
 /* diffusers Timesteps(dim, flip_sin_to_cos, downscale_freq_shift): t fp32 [nt] -> out fp32 [nt][dim]. */
 int d3_timestep_sincos(const float* t, int nt, int dim, int flip_sin_to_cos, float freq_shift, float* out, void* stream);
 /* layout glue: fp32 NCHW [B,C,H,W] <-> channels [c_off, c_off + C) of a 16-bit NHWC tensor with pixel pitch `pitch`. */

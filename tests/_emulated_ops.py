@@ -141,3 +141,46 @@ def resize_nearest(x, Ho, Wo, Hbuf=None, Wbuf=None):
     out = x.new_zeros((B, Hbuf, Wbuf, C))
     out[:, :Ho, :Wo] = F.interpolate(x.float().permute(0, 3, 1, 2), size=(Ho, Wo), mode="nearest").permute(0, 2, 3, 1).to(x.dtype)
     return out
+
+
+# ---- text encoder (d3roma_b200/text_encoder.py) ----------------------------------------------------------------------
+def _act_small(x, code):
+    if code == 1:
+        return F.silu(x)
+    if code == 2:
+        return F.gelu(x)
+    if code == 3:
+        return x * torch.sigmoid(1.702 * x)
+    return x
+
+
+def linear_small(x, w, bias=None, act_in=0, act_out=0):  # noqa: F811  (supersedes the SiLU-only form above)
+    y = _act_small(x, act_in) @ w.t()
+    if bias is not None:
+        y = y + bias
+    return _act_small(y, act_out)
+
+
+def embed_tokens(ids, token_embedding, position_embedding):
+    B, L = ids.shape
+    return (token_embedding[ids] + position_embedding[:L][None]).reshape(B * L, -1)
+
+
+def layernorm_f32(x, gamma, beta, eps=1e-5):
+    return F.layer_norm(x, (x.shape[-1],), gamma, beta, eps)
+
+
+def causal_attention_f32(qkv, B, L, heads, scale):
+    D = qkv.shape[1] // 3
+    q, k, v = (t.reshape(B, L, heads, D // heads).transpose(1, 2) for t in qkv.split(D, dim=1))
+    s = q @ k.transpose(-1, -2) * scale + torch.full((L, L), float("-inf")).triu(1)
+    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * L, D)
+
+
+def lincomb(a, x, b=1.0, y=None, c=0.0, z=None):
+    out = a * x
+    if y is not None:
+        out = out + b * y
+    if z is not None:
+        out = out + c * z
+    return out
