@@ -174,6 +174,9 @@ def _declare(lib: C.CDLL) -> None:
         "d3_cross_attention_small": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp]),
         "d3_linear_small": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, vp, i32, vp]),
         "d3_timestep_sincos": (i32, [vp, i32, i32, i32, f32, vp, vp]),
+        "d3_ensemble_workspace_bytes": (C.c_size_t, []),
+        "d3_ensemble_objective": (i32, [vp, i32, i64, vp, vp, i32, vp, vp, vp]),
+        "d3_ensemble_reduce": (i32, [vp, i32, i64, vp, vp, i32, vp, vp, vp, vp]),
         "d3_embed_tokens": (i32, [vp, i32, i32, vp, i32, vp, i32, i32, vp, vp]),
         "d3_layernorm_f32": (i32, [vp, i64, i32, vp, vp, f32, vp, vp]),
         "d3_causal_attention_f32": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, i32, vp]),

@@ -51,8 +51,6 @@ def eval_batch(config, pipeline, disable_bar=True, fxb=None, normalized_rgb=None
     padder = InputPadder(image_shape, divis_by=config.divis_by)
     p_rgb, p_left, p_right, p_sim, p_raw = padder.pad(normalized_rgb, left_image, right_image, sim_disp, raw_depth)
     assert config.num_inference_rounds > 0, "num_inference_rounds should be greater than 0"
-    if getattr(config, "ensemble", False):
-        raise NotImplementedError("ensemble_depths (scipy optimisation, utils.py:346-460) is not implemented")
     preds, out = [], None
     denorm = functools.partial(denormalize, config)                            # evaluate.py:76
     for r in range(config.num_inference_rounds):
@@ -73,6 +71,8 @@ def eval_batch(config, pipeline, disable_bar=True, fxb=None, normalized_rgb=None
         out.images_sampled_prev = inter.clone()
         out.images_purturbed_pred_prev = inter.clone()
     pred_disps = torch.cat(preds, dim=1)                                       # [B, R*dc, H, W]
+    if getattr(config, "ensemble", False):                                     # evaluate.py:117-120
+        pred_disps = torch.stack([M.ensemble_depths(pred_disps[i])[0] for i in range(pred_disps.shape[0])]).unsqueeze(1)
     pred_un = denormalize(config, pred_disps, raw_disp, mask).mean(dim=1)      # [B, H, W]
     gt = raw_disp.squeeze(1)
     if config.eval_dataset[0] == "SceneFlow":                                  # evaluate.py:126-130

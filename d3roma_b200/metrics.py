@@ -93,3 +93,91 @@ class RANSAC:
 def metrics_to_dict(metrics_disp, metrics_depth):
     return {"disp": dict(zip(DISP_KEYS, np.array(metrics_disp).mean(0))),
             "depth": dict(zip(DEPTH_KEYS, np.array(metrics_depth).mean(0)))}
+
+
+_ENSEMBLE_OBJECTIVE = None      # tests/: a torch emulation of d3_ensemble_objective / d3_ensemble_reduce (host logic on CPU)
+_ENSEMBLE_REDUCE = None
+
+
+def _ens_objective(images: torch.Tensor, s: np.ndarray, t: np.ndarray, median: bool, ws: torch.Tensor,
+                   out3: torch.Tensor) -> torch.Tensor:
+    if _ENSEMBLE_OBJECTIVE is not None:
+        return _ENSEMBLE_OBJECTIVE(images, s, t, median)
+    n, P = images.shape[0], images[0].numel()
+    f = ctypes.POINTER(ctypes.c_float)
+    _lib.check(_lib.lib().d3_ensemble_objective(images.data_ptr(), n, P, s.ctypes.data_as(f), t.ctypes.data_as(f),
+                                                int(median), ws.data_ptr(), out3.data_ptr(), ops._stream()))
+    return out3
+
+
+def ensemble_depths(input_images: torch.Tensor, regularizer_strength: float = 0.02, max_iter: int = 2, tol: float = 1e-3,
+                    reduction: str = "median", max_res: int = None):
+    """``ensemble_depths`` of /root/reference/utils_d3roma/utils.py:28-120 (``config.ensemble``, evaluate.py:117-120):
+    ``input_images`` fp32 CUDA [n, H, W] (the R rounds of one sample) -> ``(aligned_images [H, W], uncertainty [H, W])``.
+
+    The host side is the reference's: the same initial guess (per-map 1 / (max - min) and -min / (max - min), float32), the
+    same ``scipy.optimize.minimize(closure, x, method="BFGS", tol=tol, options={"maxiter": max_iter, "disp": False})``
+    call with a closure that returns a float32 scalar.  The closure body (transform, pair distances, median / mean, near
+    and far error) is ONE kernel launch over the maps (``d3_ensemble_objective``) and 24 bytes back, the final prediction
+    (median + median absolute deviation, or mean + std, rescaled to [0, 1]) is ``d3_ensemble_reduce``.
+
+    Note on what the optimiser does: the iterate is float32, so scipy's forward differences (step ~1.5e-8 * |x|) fall
+    below its resolution; with the scipy versions that keep the float32 iterate (this image's among them) the gradient is
+    0 / 0 and BFGS returns the initial guess after 0 iterations - the result is then "min-max normalise every map,
+    reduce, min-max normalise again", and bit-exact parity with the reference holds (tests/golden/ensemble.npz).  With a
+    scipy that upcasts the iterate both implementations descend on the rounding noise of their float32 objectives."""
+    from scipy.optimize import minimize
+    if reduction not in ("mean", "median"):
+        raise ValueError(f"Unknown reduction method: {reduction}")
+    if max_res is not None:
+        # utils.py:48-52 calls torch.from_numpy on a tensor here and raises for every input
+        raise NotImplementedError("ensemble_depths: max_res is not supported (the reference's branch raises a TypeError)")
+    emulated = _ENSEMBLE_OBJECTIVE is not None
+    if input_images.dim() != 3:
+        raise ValueError("ensemble_depths: [n, H, W] expected")
+    images = input_images.to(torch.float32).contiguous() if emulated else ops._f32c(input_images, "input_images")
+    n = images.shape[0]
+    if not 1 <= n <= 32:
+        raise ValueError(f"ensemble_depths: 1 <= n <= 32 maps expected (got {n})")
+    median = reduction == "median"
+    P = images[0].numel()
+    dev = images.device
+    ws = out3 = None
+    if not emulated:
+        ws = torch.empty((_lib.lib().d3_ensemble_workspace_bytes(),), dtype=torch.uint8, device=dev)
+        out3 = torch.empty((3,), dtype=torch.float64, device=dev)
+    # init guess (utils.py:54-59), float32 like np.min / np.max of a float32 array
+    mm = (torch.stack([images.reshape(n, -1).min(1).values, images.reshape(n, -1).max(1).values], 1) if emulated
+          else ops.masked_minmax(images.reshape(n, -1))).cpu().numpy().astype(np.float32)
+    _min, _max = mm[:, 0], mm[:, 1]
+    s_init = (1.0 / (_max - _min)).reshape((-1, 1, 1))
+    t_init = (-1 * s_init.flatten() * _min.flatten()).reshape((-1, 1, 1))
+    x = np.concatenate([s_init, t_init]).reshape(-1).astype(np.float32)
+    n_pairs = n * (n - 1) // 2
+
+    def closure(x):                                   # utils.py:64-87
+        l = len(x)
+        s = np.ascontiguousarray(x[: int(l / 2)], dtype=np.float32)     # torch.from_numpy(s).to(dtype=float32)
+        t = np.ascontiguousarray(x[int(l / 2):], dtype=np.float32)
+        acc, lo, hi = (float(v) for v in _ens_objective(images, s, t, median, ws, out3).cpu())
+        with np.errstate(invalid="ignore", divide="ignore"):
+            sqrt_dist = np.float32(np.sqrt(np.float32(acc / (n_pairs * P)))) if n_pairs else np.float32(np.nan)
+        near_err = np.float32(abs(0.0 - lo))          # sqrt((0 - min(pred)) ** 2)
+        far_err = np.float32(abs(np.float32(1.0) - np.float32(hi)))
+        err = np.float32(sqrt_dist + np.float32((near_err + far_err) * np.float32(regularizer_strength)))
+        return np.asarray(err, dtype=np.float32)
+
+    res = minimize(closure, x, method="BFGS", tol=tol, options={"maxiter": max_iter, "disp": False})
+    x = res.x
+    l = len(x)
+    s = np.ascontiguousarray(x[: int(l / 2)], dtype=np.float32)
+    t = np.ascontiguousarray(x[int(l / 2):], dtype=np.float32)
+    if emulated:
+        return _ENSEMBLE_REDUCE(images, s, t, median)
+    aligned = torch.empty(images.shape[1:], dtype=torch.float32, device=dev)
+    uncertainty = torch.empty_like(aligned)
+    f = ctypes.POINTER(ctypes.c_float)
+    _lib.check(_lib.lib().d3_ensemble_reduce(images.data_ptr(), n, P, s.ctypes.data_as(f), t.ctypes.data_as(f),
+                                             int(median), ws.data_ptr(), aligned.data_ptr(), uncertainty.data_ptr(),
+                                             ops._stream()))
+    return aligned, uncertainty

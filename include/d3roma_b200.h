@@ -379,6 +379,19 @@ int d3_cross_attention_small(const void* q, int q_pitch, const float* kc, const 
  * Linear layers of the text encoder.  bias may be NULL; K % 4 == 0. */
 int d3_linear_small(const float* x, int n_rows, int K, const float* w, const float* bias, int rows, int act_in,
                     int act_out, float* out, int out_stride, void* stream);
+/* ensemble_depths (utils_d3roma/utils.py:28-120; `config.ensemble`, evaluate.py:117-120): n <= 32 maps [n][P] of one
+ * sample, per-map scale s and shift t (HOST arrays of n floats: the BFGS iterate of scipy lives on the host).
+ *   d3_ensemble_objective: one evaluation of the closure of utils.py:64-87: out3 (device, 3 doubles) =
+ *     { sum over pairs i < j and pixels of (v_i - v_j)^2,  min over pixels of pred,  max over pixels of pred },
+ *     v_i = x_i * s_i + t_i, pred = lower median (reduction 1) or mean (reduction 0) over the maps; deterministic.
+ *   d3_ensemble_reduce: utils.py:99-118: aligned [P] = median / mean of v, uncertainty [P] = median absolute deviation /
+ *     unbiased std, both rescaled with the aligned map's min and max: (aligned - min) / (max - min), uncertainty / (max - min).
+ * workspace: d3_ensemble_workspace_bytes() bytes of device scratch. */
+size_t d3_ensemble_workspace_bytes(void);
+int d3_ensemble_objective(const float* images, int n, int64_t P, const float* s_host, const float* t_host, int reduction,
+                          void* workspace, double* out3, void* stream);
+int d3_ensemble_reduce(const float* images, int n, int64_t P, const float* s_host, const float* t_host, int reduction,
+                       void* workspace, float* aligned, float* uncertainty, void* stream);
 /* Text encoder of the latent pipeline (custom_pipelines.py:260-287 `__encode_empty_text`: tokenizer("") ->
  * text_encoder(input_ids)[0]; transformers CLIPTextModel - embeddings, pre-LayerNorm transformer layers with a causal
  * mask, final LayerNorm), fp32 throughout; its Linear layers are d3_linear_small calls.

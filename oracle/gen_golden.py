@@ -639,11 +639,30 @@ def gen_ransac(store):
     store["den_out"] = _np(den)
 
 
+def gen_ensemble(store):
+    """ensemble_depths of the reference (utils_d3roma/utils.py:28-120) run unmodified on seeded stacks of maps
+    (oracle/ensemble_ref.make_inputs): odd / even counts (torch.median's lower median), identical maps (ties), both
+    reductions, a single pair."""
+    import warnings
+    from utils_d3roma.utils import ensemble_depths
+    from oracle.ensemble_ref import make_inputs
+    for tag, n, seed, ties, red in (("med5", 5, 0, False, "median"), ("med4", 4, 1, False, "median"),
+                                    ("med6t", 6, 2, True, "median"), ("mean3", 3, 3, False, "mean"),
+                                    ("mean5t", 5, 4, True, "mean"), ("med2", 2, 5, False, "median")):
+        x = make_inputs(n, seed=seed, ties=ties)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            aligned, unc = ensemble_depths(x.clone(), reduction=red)
+        store[f"{tag}/aligned"], store[f"{tag}/uncertainty"] = _np(aligned), _np(unc)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
     for name, fn in (("ddim", gen_ddim), ("ddpm", gen_ddpm), ("prepost", gen_prepost), ("guidance", gen_guidance),
-                     ("pipeline", gen_pipeline), ("guided", gen_guided), ("reproject", gen_reproject), ("piecewise", gen_piecewise), ("latent", gen_latent), ("latent_nets", gen_latent_nets), ("unet_oracle", gen_unet_oracle), ("postproc", gen_postproc), ("frontend", gen_frontend), ("ransac", gen_ransac)):
+                     ("pipeline", gen_pipeline), ("guided", gen_guided), ("reproject", gen_reproject), ("piecewise", gen_piecewise), ("latent", gen_latent), ("latent_nets", gen_latent_nets), ("unet_oracle", gen_unet_oracle), ("postproc", gen_postproc), ("frontend", gen_frontend), ("ransac", gen_ransac), ("ensemble", gen_ensemble)):
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:     # python oracle/gen_golden.py ensemble  -> only that fixture
+            continue
         store = {}
         with torch.no_grad():
             fn(store)

@@ -3,9 +3,11 @@ outputs (tests/golden/postproc.npz)."""
 from pathlib import Path
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import postproc_ref as P
+from tests._golden import SOURCES, load, same
 
 G = Path(__file__).parent / "golden"
 
@@ -48,3 +50,51 @@ def test_ransac_oracle_matches_reference_run():
     np.testing.assert_allclose(err.numpy(), g["best_error"], rtol=1e-6)
     np.testing.assert_array_equal(num.numpy(), g["best_num_inlier"])
     assert (g["best_num_inlier"] > 0).all()          # the problem is one where RANSAC does select models
+
+
+# ---------------------------------------------------------------------------------------------- ensemble_depths
+ENSEMBLE_CASES = (("med5", 5, 0, False, "median"), ("med4", 4, 1, False, "median"), ("med6t", 6, 2, True, "median"),
+                  ("mean3", 3, 3, False, "mean"), ("mean5t", 5, 4, True, "mean"), ("med2", 2, 5, False, "median"))
+
+
+@pytest.mark.parametrize("source", SOURCES)
+@pytest.mark.parametrize("tag,n,seed,ties,red", ENSEMBLE_CASES)
+def test_ensemble_depths_restatement(source, tag, n, seed, ties, red):
+    """oracle/ensemble_ref.py against the reference's own ensemble_depths (utils.py:28-120)."""
+    import warnings
+    from oracle import ensemble_ref as E
+    G = load("ensemble", source)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        aligned, unc, res = E.ensemble_depths(E.make_inputs(n, seed=seed, ties=ties), reduction=red)
+    assert same(aligned.numpy(), G[f"{tag}/aligned"], source, rtol=1e-6, atol=1e-6)
+    assert same(unc.numpy(), G[f"{tag}/uncertainty"], source, rtol=1e-6, atol=1e-6)
+    assert float(aligned.min()) == 0.0 and float(aligned.max()) == 1.0
+
+
+@pytest.mark.parametrize("tag,n,seed,ties,red", ENSEMBLE_CASES)
+def test_ensemble_depths_host_logic(monkeypatch, tag, n, seed, ties, red):
+    """d3roma_b200.metrics.ensemble_depths (initial guess, scipy call, closure arithmetic) with the two device entry
+    points swapped for the oracle's torch forms: the reference's result."""
+    import warnings
+    from d3roma_b200 import metrics
+    from oracle import ensemble_ref as E
+    calls = []
+
+    def objective(images, s, t, median):
+        calls.append(1)
+        return torch.tensor(E.objective(images, s, t, median), dtype=torch.float64)
+
+    monkeypatch.setattr(metrics, "_ENSEMBLE_OBJECTIVE", objective)
+    monkeypatch.setattr(metrics, "_ENSEMBLE_REDUCE", lambda images, s, t, median: E.reduce(images, s, t, median))
+    G = load("ensemble")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        aligned, unc = metrics.ensemble_depths(E.make_inputs(n, seed=seed, ties=ties), reduction=red)
+    assert len(calls) >= 1 + 2 * n                      # the value at x0 and one forward difference per variable
+    assert same(aligned.numpy(), G[f"{tag}/aligned"], rtol=1e-6, atol=1e-6)
+    assert same(unc.numpy(), G[f"{tag}/uncertainty"], rtol=1e-6, atol=1e-6)
+    with pytest.raises(ValueError):
+        metrics.ensemble_depths(E.make_inputs(3), reduction="mode")
+    with pytest.raises(NotImplementedError):
+        metrics.ensemble_depths(E.make_inputs(3), max_res=64)

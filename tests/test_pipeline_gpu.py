@@ -205,6 +205,14 @@ def test_eval_batch_contract_and_metrics():
     np.testing.assert_allclose(md, rmd, rtol=2e-5, atol=1e-6)
     np.testing.assert_allclose(mz, rmz, rtol=2e-5, atol=1e-6)
     np.testing.assert_allclose(err, np.abs(batch["raw_disp"].squeeze(1).numpy() - pred), rtol=1e-6, atol=1e-6)
+    # config.ensemble (evaluate.py:117-120): the rounds are aligned by ensemble_depths into ONE map per sample
+    import warnings
+    cfg_e = evaluate.default_config(num_inference_timesteps=2, num_inference_rounds=3, ensemble=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pred_e, (md_e, _), unc_e, _, _ = evaluate.eval_batch(cfg_e, pipe, True, **{k: batch[k] for k in keys})
+    assert pred_e.shape == (2, 60, 90) and unc_e is None and np.isfinite(pred_e).all() and np.isfinite(md_e).all()
+    assert pred_e.min() >= 0.0 and pred_e.max() <= 128.0 + 1e-3       # denormalised [0, 1] aligned maps
     # single-process distributed eval = same rows in global order
     from d3roma_b200 import distributed
     mdict, rows = distributed.run_distributed_eval(evaluate.default_config(num_inference_timesteps=2), pipe, 3, 2,

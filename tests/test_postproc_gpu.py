@@ -78,3 +78,86 @@ def test_ransac_and_safe_ssi_denormalize_match_reference_golden():
     # default permutation source: runs and returns a sane fit
     reg2 = RANSAC(n=0.1, k=10, d=0.2, t=0.6).fit(X, Y, Mk)
     assert torch.isfinite(reg2.best_fit).all() and (reg2.best_num_inlier > 0).all()
+
+
+# ---------------------------------------------------------------------------------------------- ensemble_depths
+ENSEMBLE_CASES = (("med5", 5, 0, False, "median"), ("med4", 4, 1, False, "median"), ("med6t", 6, 2, True, "median"),
+                  ("mean3", 3, 3, False, "mean"), ("mean5t", 5, 4, True, "mean"), ("med2", 2, 5, False, "median"))
+
+
+def _ens_call(name, images, s, t, median, *outs):
+    import ctypes
+    from d3roma_b200 import _lib, ops
+    f = ctypes.POINTER(ctypes.c_float)
+    ws = torch.empty((_lib.lib().d3_ensemble_workspace_bytes(),), dtype=torch.uint8, device="cuda")
+    s, t = np.ascontiguousarray(s, dtype=np.float32), np.ascontiguousarray(t, dtype=np.float32)
+    _lib.check(getattr(_lib.lib(), name)(images.data_ptr(), images.shape[0], images[0].numel(), s.ctypes.data_as(f),
+                                         t.ctypes.data_as(f), int(median), ws.data_ptr(), *[o.data_ptr() for o in outs],
+                                         ops._stream()))
+
+
+@pytest.mark.parametrize("n,hw,median", [(5, (24, 40), True), (4, (33, 17), True), (3, (24, 40), False),
+                                         (8, (360, 640), True), (32, (8, 9), True), (1, (5, 7), True), (7, (360, 640), False)])
+def test_ensemble_kernels_vs_oracle(n, hw, median):
+    """d3_ensemble_objective / d3_ensemble_reduce against the oracle's torch forms of the closure and of the final
+    prediction (utils.py:64-87, 99-118) for arbitrary scale / shift vectors."""
+    from oracle import ensemble_ref as E
+    x = E.make_inputs(n, hw=hw, seed=n)
+    rng = np.random.default_rng(n)
+    s, t = (0.5 + rng.random(n)).astype(np.float32), (rng.random(n) - 0.5).astype(np.float32)
+    xd = x.cuda()
+    out3 = torch.empty(3, dtype=torch.float64, device="cuda")
+    _ens_call("d3_ensemble_objective", xd, s, t, median, out3)
+    acc, lo, hi = E.objective(x, s, t, median)
+    got = out3.cpu().numpy()
+    assert abs(got[0] - acc) <= 1e-6 * max(acc, 1e-30)
+    if median:
+        assert got[1] == lo and got[2] == hi                    # the median is one of the inputs: exact
+    else:
+        assert abs(got[1] - lo) < 1e-6 and abs(got[2] - hi) < 1e-6
+    out3b = torch.empty(3, dtype=torch.float64, device="cuda")
+    _ens_call("d3_ensemble_objective", xd, s, t, median, out3b)
+    assert torch.equal(out3, out3b)                             # deterministic (BFGS differentiates it numerically)
+    if n == 1 and not median:
+        return
+    al, un = torch.empty(hw, device="cuda"), torch.empty(hw, device="cuda")
+    _ens_call("d3_ensemble_reduce", xd, s, t, median, al, un)
+    wal, wun = E.reduce(x, s, t, median)
+    if median:
+        assert torch.equal(al.cpu(), wal) and torch.equal(un.cpu(), wun)
+    else:
+        assert float((al.cpu() - wal).abs().max()) < 1e-6 and float((un.cpu() - wun).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("tag,n,seed,ties,red", ENSEMBLE_CASES)
+def test_ensemble_depths_vs_reference_golden(tag, n, seed, ties, red):
+    """d3roma_b200.metrics.ensemble_depths against the reference's own function (tests/golden/ensemble.npz)."""
+    import warnings
+    from d3roma_b200 import metrics
+    from oracle import ensemble_ref as E
+    z = np.load(G / "ensemble.npz")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        aligned, unc = metrics.ensemble_depths(E.make_inputs(n, seed=seed, ties=ties).cuda(), reduction=red)
+    assert aligned.is_cuda and aligned.shape == (24, 40)
+    tol = 0.0 if red == "median" else 1e-6
+    assert np.abs(aligned.cpu().numpy() - z[f"{tag}/aligned"]).max() <= tol
+    assert np.abs(unc.cpu().numpy() - z[f"{tag}/uncertainty"]).max() <= tol
+    with pytest.raises(ValueError):                                 # no CPU fallback
+        metrics.ensemble_depths(E.make_inputs(3))
+
+
+def test_ensemble_depths_recovers_common_map_at_full_size():
+    """Size-independent property at 360 x 640: n affine copies of one map align to that map rescaled to [0, 1] with zero
+    spread, whatever their scales and shifts."""
+    import warnings
+    from d3roma_b200 import metrics
+    g = torch.Generator().manual_seed(9)
+    base = torch.rand(360, 640, generator=g)
+    x = torch.stack([base * a + b for a, b in ((1.0, 0.0), (2.5, -1.0), (0.3, 4.0), (7.0, 0.5), (1.7, -3.0))]).cuda()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        aligned, unc = metrics.ensemble_depths(x)
+    want = (base - base.min()) / (base.max() - base.min())
+    assert float((aligned.cpu() - want).abs().max()) < 5e-6
+    assert float(unc.max()) < 5e-6
