@@ -80,3 +80,66 @@ class BaseOutput(OrderedDict):
 
     def to_tuple(self):
         return tuple(self[k] for k in self.keys())
+
+
+class PretrainedMixin:
+    """``save_pretrained`` / ``from_pretrained`` in the diffusers directory layout (``config.json`` +
+    ``diffusion_pytorch_model.safetensors`` or ``.bin``) for the network classes whose ``load_state_dict`` takes diffusers
+    key names.  The networks keep their weights in kernel layouts, so writing a checkpoint back needs the fp32
+    ``state_dict`` they were loaded from: set ``keep_state_dict = True`` before loading (``from_pretrained(...,
+    keep_state_dict=True)``) when ``save_pretrained`` / ``state_dict`` will be called."""
+
+    keep_state_dict = False
+    _sd_cpu = None
+    _weights_basename = "diffusion_pytorch_model"
+
+    def _remember_state_dict(self, sd):
+        self._sd_cpu = {k: v.detach().to("cpu", copy=True) for k, v in sd.items()} if self.keep_state_dict else None
+
+    def state_dict(self):
+        if self._sd_cpu is None:
+            raise RuntimeError(f"{type(self).__name__}.state_dict() needs keep_state_dict=True at load time")
+        return dict(self._sd_cpu)
+
+    def save_pretrained(self, path):
+        import json
+        import os
+        from safetensors.torch import save_file
+        sd = self.state_dict()
+        os.makedirs(path, exist_ok=True)
+        cfg = {k: (list(v) if isinstance(v, tuple) else v) for k, v in vars(self.config).items()}
+        cfg.update(_class_name=type(self).__name__, compute_dtype=self.compute_dtype)
+        with open(os.path.join(path, "config.json"), "w") as f:
+            json.dump(cfg, f, indent=2)
+        save_file({k: v.contiguous() for k, v in sd.items()}, os.path.join(path, self._weights_basename + ".safetensors"))
+
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None, compute_dtype=None, device="cuda", keep_state_dict=False, **overrides):
+        """``Class.from_pretrained("checkpoint/stable-diffusion/unet")`` / ``(..., subfolder="vae")`` (train.py:750, 830):
+        keys of ``config.json`` the class does not model are validated or ignored by its constructor; bookkeeping keys
+        (``_class_name``, ``_diffusers_version``, ``_name_or_path``) are dropped."""
+        import json
+        import os
+        if subfolder:
+            path = os.path.join(path, subfolder)
+        with open(os.path.join(path, "config.json")) as f:
+            cfg = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+        cfg.update(overrides)
+        if compute_dtype is not None:
+            cfg["compute_dtype"] = compute_dtype
+        net = cls(**cfg)
+        if device is not None:
+            net.to(device)
+        net.keep_state_dict = keep_state_dict
+        return net.load_state_dict(load_weights(path, cls._weights_basename))
+
+
+def load_weights(path, basename):
+    """``<basename>.safetensors`` when present, else ``<basename>.bin`` (torch pickle, tensors only)."""
+    import os
+    st = os.path.join(path, basename + ".safetensors")
+    if os.path.exists(st):
+        from safetensors.torch import load_file
+        return load_file(st)
+    import torch
+    return torch.load(os.path.join(path, basename + ".bin"), map_location="cpu", weights_only=True)

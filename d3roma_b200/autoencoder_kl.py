@@ -29,6 +29,7 @@ from typing import Dict, Optional, Sequence
 import torch
 
 from . import ops
+from ._config import PretrainedMixin
 from .unet import _Act, _StatsArena
 
 
@@ -63,7 +64,7 @@ class _Decoder:
         return self._o._decode(z)
 
 
-class AutoencoderKL:
+class AutoencoderKL(PretrainedMixin):
     def __init__(self, in_channels: int = 3, out_channels: int = 3, latent_channels: int = 4,
                  block_out_channels: Sequence[int] = (128, 256, 512, 512), layers_per_block: int = 2,
                  norm_num_groups: int = 32, scaling_factor: float = 0.18215, compute_dtype: str = "fp16", **unused):
@@ -185,6 +186,7 @@ class AutoencoderKL:
                 raise KeyError(f"unexpected keys in state_dict: {sorted(extra)[:5]} ...")
         self._loaded = True
         self._fold = {}
+        self._remember_state_dict(sd)
         return self
 
     def to(self, device=None, dtype=None):

@@ -93,13 +93,81 @@ class GuidedLatentDiffusionPipeline:
             if isinstance(m, torch.nn.Module):
                 for p in m.parameters():
                     return p.device
+            elif isinstance(getattr(m, "device", None), torch.device) and m.device.type == "cuda":
+                return m.device
         return torch.device("cuda", torch.cuda.current_device())
 
     def to(self, device):
         for m in (self.unet, self.vae, self.text_encoder):
-            if isinstance(m, torch.nn.Module):
+            if m is not None and hasattr(m, "to"):
                 m.to(device)
         return self
+
+    # ---- diffusers directory layout (train.py:682, 701 `pipeline.save_pretrained`; evaluate.py:313-314 / inference.py:72-73
+    # `GuidedLatentDiffusionPipeline.from_pretrained(path).to("cuda")`)
+    def save_pretrained(self, path):
+        """model_index.json + unet/ vae/ text_encoder/ scheduler/ guidance/ (tokenizer/ when it can save itself).  The
+        networks must have been loaded with ``keep_state_dict=True`` (they keep their weights in kernel layouts)."""
+        import json
+        import os
+        from ._config import save_config
+        os.makedirs(path, exist_ok=True)
+        index = {"_class_name": "GuidedLatentDiffusionPipeline"}
+        for name in ("unet", "vae", "text_encoder", "tokenizer"):
+            m = getattr(self, name)
+            if m is None or not hasattr(m, "save_pretrained"):
+                index[name] = [None, None]
+                continue
+            m.save_pretrained(os.path.join(path, name))
+            index[name] = [type(m).__module__.split(".")[0], type(m).__name__]
+        save_config(self.scheduler, os.path.join(path, "scheduler"), "scheduler_config.json")
+        index["scheduler"] = ["d3roma_b200", type(self.scheduler).__name__]
+        g = self.guidance
+        os.makedirs(os.path.join(path, "guidance"), exist_ok=True)
+        with open(os.path.join(path, "guidance", "config.json"), "w") as f:
+            json.dump({"_class_name": "FlowGuidance", "flow_guidance_weight": g.flow_guidance_weight,
+                       "perturb_start_ratio": getattr(g, "perturb_start_ratio", 0.0),
+                       "flow_guidance_mode": g.flow_guidance_mode}, f)
+        index["guidance"] = ["d3roma_b200", "FlowGuidance"]
+        with open(os.path.join(path, "model_index.json"), "w") as f:
+            json.dump(index, f, indent=2)
+
+    @classmethod
+    def from_pretrained(cls, path, compute_dtype=None, device="cuda", keep_state_dict=False, tokenizer=None):
+        """A pipeline directory as diffusers writes it for the reference (``unet/``, ``vae/``, ``text_encoder/``,
+        ``tokenizer/``, ``scheduler/``, ``guidance/``): the three networks on this package's kernels, the reference's
+        scheduler class named by ``scheduler_config.json``.  The tokenizer is the caller's (``tokenizer=``), or
+        ``transformers.CLIPTokenizer`` when that library and a ``tokenizer/`` folder are there, else ``None`` (the text
+        encoder then encodes the empty prompt from its two token ids).  A directory without ``text_encoder/`` gives a
+        pipeline that needs ``empty_text_embed``."""
+        import inspect
+        import os
+        from ._config import load_config
+        from .autoencoder_kl import AutoencoderKL
+        from .guidance import FlowGuidance
+        from .scheduler_ddim import MyDDIMScheduler
+        from .scheduler_ddpm import MyDDPMScheduler
+        from .text_encoder import CLIPTextModel
+        from .unet_condition import UNet2DConditionModel
+        kw = dict(compute_dtype=compute_dtype, device=device, keep_state_dict=keep_state_dict)
+        unet = UNet2DConditionModel.from_pretrained(os.path.join(path, "unet"), **kw)
+        vae = AutoencoderKL.from_pretrained(os.path.join(path, "vae"), **kw)
+        text_encoder = None
+        if os.path.exists(os.path.join(path, "text_encoder", "config.json")):
+            text_encoder = CLIPTextModel.from_pretrained(os.path.join(path, "text_encoder"), device=device)
+        if tokenizer is None and os.path.isdir(os.path.join(path, "tokenizer")):
+            try:
+                from transformers import CLIPTokenizer
+                tokenizer = CLIPTokenizer.from_pretrained(os.path.join(path, "tokenizer"))
+            except Exception:       # library or vocabulary files absent: the encoder knows the ids of ""
+                tokenizer = None
+        scfg = load_config(os.path.join(path, "scheduler"), "scheduler_config.json")
+        sched_cls = MyDDPMScheduler if "DDPM" in scfg.get("_class_name", "DDPM") else MyDDIMScheduler
+        gpath = os.path.join(path, "guidance", "config.json")
+        gcfg = load_config(os.path.join(path, "guidance"), "config.json") if os.path.exists(gpath) else {}
+        known = set(inspect.signature(FlowGuidance.__init__).parameters) - {"self", "camera"}
+        guidance = FlowGuidance(**{k: v for k, v in gcfg.items() if k in known})
+        return cls(unet, vae, tokenizer, text_encoder, sched_cls.from_config(scfg), guidance)
 
     def set_progress_bar_config(self, **kwargs):
         self._progress_bar_config = kwargs

@@ -133,6 +133,9 @@ class CLIPTextModel:
     def eval(self):
         return self
 
+    def parameters(self):           # train.py:827-828 freezes them (`param.requires_grad = False`)
+        return iter(self._w.values())
+
     def requires_grad_(self, flag: bool = False):
         return self
 

@@ -31,6 +31,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import ops
+from ._config import PretrainedMixin
 
 
 # Set ONLY by tests/test_ldm_host_logic.py, which swaps ``ops`` for torch emulations of the kernels to check the
@@ -67,7 +68,7 @@ def _p128(c: int) -> int:
     return (c + 127) // 128 * 128
 
 
-class UNet2DConditionModel:
+class UNet2DConditionModel(PretrainedMixin):
     def __init__(self, sample_size=64, in_channels: int = 4, out_channels: int = 4,
                  block_out_channels: Sequence[int] = (320, 640, 1280, 1280), layers_per_block: int = 2,
                  attention_head_dim: Sequence[int] = (5, 10, 20, 20), cross_attention_dim: int = 1024,
@@ -231,6 +232,7 @@ class UNet2DConditionModel:
         self._loaded = True
         self._ctx_cache = None
         self.reset_graphs()    # captured graphs hold raw pointers into the previous weight tensors
+        self._remember_state_dict(sd)
         return self
 
     def to(self, device=None, dtype=None):

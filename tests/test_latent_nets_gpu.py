@@ -90,3 +90,66 @@ def test_eval_batch_runs_the_latent_pipeline():
                                                sim, None)
     assert pred.shape == (B, H, W) and m5.shape == (B, 5) and m6.shape == (B, 6) and unc.shape == (B, H, W)
     assert np.isfinite(pred).all() and out.images_pred_orig.shape == (B, 2, H, W)
+
+
+def test_pipeline_directory_roundtrip_and_diffusers_style_checkpoints(tmp_path):
+    """``GuidedLatentDiffusionPipeline.from_pretrained(path).to("cuda")`` (evaluate.py:313-314, inference.py:72-73) on a
+    directory in the diffusers layout - written by ``save_pretrained`` here, with one network re-written the way
+    diffusers itself writes it (extra config keys, ``.bin`` weights) - and the text encoder supplying the embedding of
+    the empty prompt (no tokenizer, no ``empty_text_embed``)."""
+    import json
+    import d3roma_b200 as d
+    import d3roma_b200.autoencoder_kl as ak
+    import d3roma_b200.unet_condition as uc
+    from oracle import text_encoder_ref as T
+    from oracle.ldm_ref import make_cond_unet, make_vae
+    z = np.load(G / "latent_nets.npz")
+    cc, cin, cfg, n, plots = CASES["ddim_rgbraw"]
+    unet = uc.UNet2DConditionModel(in_channels=cin, **UCFG).to("cuda")
+    unet.keep_state_dict = True
+    unet.load_state_dict(make_cond_unet(in_channels=cin, seed=5, **UCFG).state_dict())
+    vae = ak.AutoencoderKL(**VCFG).to("cuda")
+    vae.keep_state_dict = True
+    vae_sd = make_vae(seed=11, **VCFG).state_dict()
+    vae.load_state_dict(vae_sd)
+    tcfg = dict(T.SMALL_TEXT, vocab_size=49408, eos_token_id=49407)      # 64 wide = the small UNet's cross_attention_dim
+    text = d.CLIPTextModel(**tcfg).to("cuda").load_state_dict(T.make_state_dict(tcfg, seed=21))
+    pipe = d.GuidedLatentDiffusionPipeline(unet, vae, None, text, d.MyDDIMScheduler.from_config(DDIM[cfg]),
+                                           d.FlowGuidance(flow_guidance_weight=0.0, flow_guidance_mode="gradient"))
+    rgb, sim = torch.from_numpy(z["rgb"]), torch.from_numpy(z["sim"])
+    run = lambda p: p(rgb, None, None, sim, None, None, num_inference_steps=n, num_intermediate_images=plots,  # noqa: E731
+                      cond_channels=cc, generator=torch.Generator().manual_seed(9)).images
+    want = run(pipe)
+    # the context really is the text encoder's output: the oracle's embedding through the explicit argument agrees
+    ete, _ = T.text_encoder_forward(T.make_state_dict(tcfg, seed=21), tcfg, torch.tensor([[49406, 49407]]))
+    via_arg = pipe(rgb, None, None, sim, None, None, empty_text_embed=ete, num_inference_steps=n,
+                   num_intermediate_images=plots, cond_channels=cc, generator=torch.Generator().manual_seed(9)).images
+    assert float((via_arg - want).abs().max()) <= 2e-3
+
+    root = tmp_path / "ldm_pipeline"
+    pipe.save_pretrained(root)
+    index = json.loads((root / "model_index.json").read_text())
+    assert index["unet"] == ["d3roma_b200", "UNet2DConditionModel"] and index["tokenizer"] == [None, None]
+    # rewrite the VAE folder the way diffusers does: bookkeeping + unmodelled config keys, torch-pickle weights
+    vcfg = json.loads((root / "vae" / "config.json").read_text())
+    vcfg.update(_diffusers_version="0.24.0", _name_or_path="stabilityai/sd-vae", act_fn="silu", sample_size=768,
+                down_block_types=["DownEncoderBlock2D"] * 4, up_block_types=["UpDecoderBlock2D"] * 4)
+    vcfg.pop("compute_dtype")
+    (root / "vae" / "config.json").write_text(json.dumps(vcfg))
+    (root / "vae" / "diffusion_pytorch_model.safetensors").unlink()
+    torch.save({k: v.clone() for k, v in vae_sd.items()}, root / "vae" / "diffusion_pytorch_model.bin")
+
+    again = d.GuidedLatentDiffusionPipeline.from_pretrained(str(root)).to("cuda")
+    assert type(again.scheduler).__name__ == "MyDDIMScheduler" and again.tokenizer is None
+    assert again.guidance.flow_guidance_mode == "gradient" and again.device.type == "cuda"
+    got = run(again)
+    assert float((got - want).abs().max()) <= 2e-3      # same weights, same kernels (statistics are summed with atomics)
+    with pytest.raises(RuntimeError):                    # loaded without keep_state_dict: nothing to write back
+        again.unet.save_pretrained(tmp_path / "nope")
+    # a directory without text_encoder/: the pipeline then needs empty_text_embed
+    import shutil
+    shutil.rmtree(root / "text_encoder")
+    bare = d.GuidedLatentDiffusionPipeline.from_pretrained(str(root))
+    assert bare.text_encoder is None
+    with pytest.raises((ValueError, AttributeError)):
+        run(bare)
