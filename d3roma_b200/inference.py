@@ -4,8 +4,9 @@
 Everything between the numpy arrays and the pipeline call — cv2.resize, HWC->CHW, ``(x/255-0.5)*2``, depth -> disparity,
 ``Normalizer.normalize``, the validity mask, the replicate padding the pixel-space UNet needs — is two kernels
 (``d3_frame_to_input``, ``d3_depth_to_input``); everything after it (unpad, denormalise, mean over rounds, disparity ->
-depth) stays on the device until the final copy.  Construction differs from the reference (no hydra / checkpoint path:
-pass the pipeline, camera and a config namespace), the methods do not.
+depth) stays on the device until the final copy.  Construction: pass a ready pipeline, camera and config namespace, or
+``D3RoMa.from_config(config, camera)`` which loads the pipeline from ``config.resume_pretrained`` like the reference's
+``_load_pipeline`` (inference.py:66-95; no hydra); the methods are the reference's.
 """
 from __future__ import annotations
 
@@ -86,6 +87,36 @@ class D3RoMa:
             resolution_hw = (h, w)
         self.resolution = tuple(resolution_hw)
         self.last_metrics = None
+
+    # ---- inference.py:66-95
+    @staticmethod
+    def load_pipeline(config, compute_dtype=None, device="cuda"):
+        """``D3RoMa._load_pipeline`` (inference.py:66-95): the pipeline class picked by ``config.ldm``, loaded from the
+        diffusers-layout directory ``config.resume_pretrained``, ``flow_guidance_mode`` taken from the config, the
+        sampler replaced by ``MyDDIMScheduler`` when ``config.sampler == "my_ddim"`` (same scheduler fields)."""
+        import os
+        from .latent_pipeline import GuidedLatentDiffusionPipeline
+        from .pipelines import GuidedDiffusionPipeline
+        from .scheduler_ddim import MyDDIMScheduler
+        path = f"{config.resume_pretrained}"
+        if not os.path.exists(path):
+            raise ValueError(f"patrained path not exists: {path}")          # (sic) inference.py:93
+        clazz = GuidedLatentDiffusionPipeline if getattr(config, "ldm", False) else GuidedDiffusionPipeline
+        pipeline = clazz.from_pretrained(path, compute_dtype=compute_dtype, device=device).to(device)
+        pipeline.guidance.flow_guidance_mode = config.flow_guidance_mode
+        if getattr(config, "sampler", None) == "my_ddim":
+            pipeline.scheduler = MyDDIMScheduler.from_config(dict(
+                beta_schedule=config.beta_schedule, beta_start=config.beta_start, beta_end=config.beta_end,
+                clip_sample=config.clip_sample, num_train_timesteps=config.num_train_timesteps,
+                prediction_type=config.prediction_type, set_alpha_to_one=False, skip_prk_steps=True, steps_offset=1,
+                trained_betas=None))
+        return pipeline
+
+    @classmethod
+    def from_config(cls, config, camera: Camera, compute_dtype=None, device="cuda"):
+        """The reference's constructor path (inference.py:40-64) without hydra: ``config`` carries the fields of the
+        task YAML (``resume_pretrained``, ``ldm``, ``sampler``, scheduler and normaliser fields)."""
+        return cls(cls.load_pipeline(config, compute_dtype, device), camera, config)
 
     # ---- inference.py:97-135
     @torch.no_grad()

@@ -95,6 +95,36 @@ def test_d3roma_infer_matches_reference_flow():
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
 
 
+def test_d3roma_from_config_loads_the_saved_pipeline(tmp_path):
+    """D3RoMa.from_config = the reference's constructor path (inference.py:40-95): pipeline directory named by
+    config.resume_pretrained, class picked by config.ldm, my_ddim sampler override, guidance mode from the config."""
+    import d3roma_b200 as d
+    from d3roma_b200 import evaluate
+    from d3roma_b200.inference import D3RoMa
+    from d3roma_b200.weights import random_init_state_dict
+    net = d.UNet2DModel(sample_size=(64, 96), in_channels=8, out_channels=1, compute_dtype="fp16").to("cuda")
+    net.load_state_dict(random_init_state_dict(8, 1, seed=0))
+    ddpm = d.MyDDPMScheduler.from_config(dict(beta_schedule="squaredcos_cap_v2", num_train_timesteps=128,
+                                              prediction_type="sample"))
+    d.GuidedDiffusionPipeline(net, ddpm, d.FlowGuidance(flow_guidance_weight=0.0)).save_pretrained(tmp_path / "ckpt")
+    cfg = evaluate.default_config(num_inference_timesteps=2, camera_resolution="90x60", ldm=False,
+                                  resume_pretrained=str(tmp_path / "ckpt"), flow_guidance_mode="gradient",
+                                  sampler="my_ddim", beta_schedule="squaredcos_cap_v2", beta_start=1e-4, beta_end=2e-2,
+                                  clip_sample=True, num_train_timesteps=128, prediction_type="sample")
+    eng = D3RoMa.from_config(cfg, d.SIM_CAMERA)
+    assert type(eng.pipeline.scheduler).__name__ == "MyDDIMScheduler" and eng.pipeline.scheduler.config.steps_offset == 1
+    assert eng.pipeline.guidance.flow_guidance_mode == "gradient"
+    rng = np.random.default_rng(4)
+    rgb = rng.integers(0, 256, (60, 90, 3), dtype=np.uint8)
+    gray = rng.integers(0, 256, (60, 90), dtype=np.uint8)
+    depth = (rng.random((60, 90)) + 0.3).astype(np.float32)
+    got = eng.infer(gray, gray, depth, rgb)
+    assert got.shape == (60, 90) and np.isfinite(got).all()
+    cfg.resume_pretrained = str(tmp_path / "missing")
+    with pytest.raises(ValueError):
+        D3RoMa.from_config(cfg, d.SIM_CAMERA)
+
+
 def test_depth_to_rgb_frame_reprojection_bit_exact_vs_reference_and_oracle():
     """DepthCamera.transform_depth_to_rgb_frame / transform_cropped_depth_to_rgb_frame (utils_d3roma/camera.py:610-701)
     on the device: bit-identical to the reference camera object's outputs (tests/golden/reproject.npz, including numpy's
