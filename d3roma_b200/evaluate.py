@@ -94,6 +94,33 @@ def eval_batch(config, pipeline, disable_bar=True, fxb=None, normalized_rgb=None
     return pred_un, rows, unc, err, out
 
 
+@torch.no_grad()
+def evaluate_intermediate_metrics(config, fxb, intermediates, gt_disps, gt_masks, gt_indexes=None):
+    """``evaluate_intermediate_metrics`` of /root/reference/evaluate.py:28-57: the metric rows of every plotted step's
+    predicted x0 (``intermediates.images_pred_orig`` [B, N, H, W], already denormalised by ``eval_batch``) against the
+    ground truth -> ``(disp_metrics [B, N, 5], depth_metrics [B, N, 6])`` numpy.  One reduction kernel over the B*N maps;
+    nothing but the rows leaves the device.  Reference quirk kept: ``fxb.view(B, 1).repeat(B, N, 1)`` flattens to
+    ``fxb[i % B]`` for map i = b*N + n (not ``fxb[b]``) - identical whenever the batch shares one camera."""
+    dev = intermediates.images_pred_orig.device
+    pred = intermediates.images_pred_orig.to(torch.float32)
+    B, N, H, W = pred.shape
+    gt = gt_disps.to(dev, torch.float32).repeat(1, N, 1, 1)
+    m = gt_masks.to(dev).repeat(1, N, 1, 1).bool()
+    if config.eval_dataset[0] == "SceneFlow":
+        scale = 960. / float(config.camera_resolution.split("x")[0])
+        lo, hi = 0.5 / scale, 192.0 / scale
+        m = (pred >= lo) & (pred < hi) & m
+        pred = pred.clamp(lo, hi)
+    else:
+        pred = pred.clamp(min=0.25)                                            # prevent 0 disparities (:47)
+    fx = None
+    if fxb is not None:
+        fx = torch.as_tensor(fxb).reshape(-1).to(dev, torch.float64)[torch.arange(B * N, device=dev) % B]
+    rows = M.compute_errors_device(gt.reshape(-1, H, W).contiguous(), pred.reshape(-1, H, W).contiguous(),
+                                   m.reshape(-1, H, W).contiguous(), fx).cpu().numpy()
+    return rows[:, :5].reshape(B, N, 5), rows[:, 5:].reshape(B, N, 6)
+
+
 SPATIAL_KEYS = ("raw_disp", "normalized_disp", "sim_disp", "left_image", "right_image", "mask")
 
 

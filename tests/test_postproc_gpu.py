@@ -161,3 +161,35 @@ def test_ensemble_depths_recovers_common_map_at_full_size():
     want = (base - base.min()) / (base.max() - base.min())
     assert float((aligned.cpu() - want).abs().max()) < 5e-6
     assert float(unc.max()) < 5e-6
+
+
+@pytest.mark.parametrize("dataset", ["synthetic", "SceneFlow"])
+def test_evaluate_intermediate_metrics_vs_oracle(dataset):
+    """evaluate.py:28-57: metric rows of the plotted x0 estimates, against the oracle's compute_errors over the same
+    maps prepared the reference's way (including its fxb[i % B] indexing)."""
+    from types import SimpleNamespace
+    from d3roma_b200 import evaluate
+    from oracle import postproc_ref as P
+    g = torch.Generator().manual_seed(13)
+    B, N, H, W = 3, 4, 40, 56
+    gt = torch.rand(B, 1, H, W, generator=g) * 60 + 1
+    mask = (torch.rand(B, 1, H, W, generator=g) > 0.3).float()
+    pred = gt.repeat(1, N, 1, 1) + torch.randn(B, N, H, W, generator=g) * 3
+    pred[0, 1, :4] = -2.0                                     # clamped to 0.25 / the SceneFlow floor
+    fxb = torch.tensor([24.5, 30.0, 18.0])
+    cfg = evaluate.default_config(eval_dataset=[dataset], camera_resolution="480x270")
+    md, mz = evaluate.evaluate_intermediate_metrics(cfg, fxb.cuda(), SimpleNamespace(images_pred_orig=pred.cuda()),
+                                                    gt.cuda(), mask.cuda(), None)
+    assert md.shape == (B, N, 5) and mz.shape == (B, N, 6)
+    p, m = pred.clone(), mask.repeat(1, N, 1, 1).bool()
+    if dataset == "SceneFlow":
+        lo, hi = 0.5 / 2.0, 192.0 / 2.0
+        m = (p >= lo) & (p < hi) & m
+        p = p.clamp(lo, hi)
+    else:
+        p = p.clamp(min=0.25)
+    fx = fxb.view(B, 1).repeat(B, N, 1).view(-1, 1).numpy()
+    rd, rz = P.compute_errors_disp(gt.repeat(1, N, 1, 1).view(-1, H, W).numpy(), p.view(-1, H, W).numpy(),
+                                   m.view(-1, H, W).numpy(), fx[:, 0])
+    np.testing.assert_allclose(md.reshape(-1, 5), rd, rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(mz.reshape(-1, 6), rz, rtol=2e-5, atol=1e-6)
