@@ -398,11 +398,26 @@ def run_gpu_arm(args):
     gt_disp = d.prepost.depth_to_disp(depth_h.to(dev), cam.fxb).view(Bp, H0, W0) if want_rows else None
     fxb_t = torch.full((Bp,), float(cam.fxb), device=dev) if want_rows else None
 
+    peer = None
+    if world > 1 and args.gather == "peer":
+        from d3roma_b200.distributed import PeerGather
+        regions = {"disp": ((Bp, 1, H0, W0), torch.float32)}
+        if want_rows:
+            regions["rows"] = ((Bp, 11), torch.float64)
+        peer = PeerGather(regions, rank=rank, world=world)
+
     def one_step():
         cond.mul_(1.0)   # a new batch every step: the per-loop conditioning term of conv_in is recomputed, not cached
         img = pipe.sample_from(x_T, cond, n_steps, left_images=left_d if guided else None,
                                right_images=right_d if guided else None,
                                denorm=normalizer.denormalize if guided else None)
+        if peer is not None:
+            # the exchange is part of the last kernel: denormalise + stores into every rank's gather buffer over NVLink
+            peer.denormalize_into(padder.unpad(img), normalizer)
+            if want_rows:
+                mine = peer._local_slot("disp")
+                peer.push(M.compute_errors_device(gt_disp, mine[:, 0], gt_disp > 0, fxb_t), "rows")
+            return peer.finish()["disp"]
         disp = normalizer.denormalize(padder.unpad(img))
         rows = None
         if want_rows:   # distributed_evaluate.py:153-163: per-sample metric rows gathered with the maps
@@ -488,6 +503,10 @@ def run_gpu_arm(args):
                     "steps": n_e2e, "api": "d3roma_b200.evaluate.denoise_batch -> GuidedDiffusionPipeline.__call__"},
             "gpu_launches": launches,
         }
+        if world > 1:
+            line["config"]["gather"] = ("stores into NVLink peer memory fused into the denormalise kernel + flag handshake "
+                                        "(d3roma_b200.distributed.PeerGather)" if peer is not None else
+                                        "NCCL all_gather_into_tensor after the loop")
         if unet_tf is not None and dtype != "fp32":
             line["unet"] = {"algorithmic_tflops": unet_tf, "peak": peaks["tf_sust"],
                             "frac_of_sustained_peak": unet_tf / peaks["tf_sust"], "gflop_per_sample_step": gflop,
@@ -503,6 +522,8 @@ def run_gpu_arm(args):
             line["cpu_baseline"] = {"value": maps_cpu, "unit": "maps/s", "cores": threads, "kind": "port",
                                     "sample": CPU_SAMPLE + f" (3 timed steps of {sec_cpu:.2f} s)"}
         emit(line)
+    if peer is not None:
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -927,6 +948,9 @@ def main():
     ap.add_argument("--impl", default="d3roma_b200", choices=["d3roma_b200", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS) + ["ldm", "train"])
     ap.add_argument("--dtype", default=None, choices=["fp16", "bf16"])
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
+                    help="output gather of the N > 1 runs: NCCL all_gather_into_tensor after the loop, or stores into NVLink "
+                         "peer memory fused into the denormalise kernel (d3roma_b200.distributed.PeerGather)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     args = ap.parse_args()

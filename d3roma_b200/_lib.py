@@ -174,6 +174,14 @@ def _declare(lib: C.CDLL) -> None:
         "d3_cross_attention_small": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp]),
         "d3_linear_small": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, vp, i32, vp]),
         "d3_timestep_sincos": (i32, [vp, i32, i32, i32, f32, vp, vp]),
+        "d3_peer_alloc": (i32, [C.c_size_t, C.POINTER(vp), vp]),
+        "d3_peer_open": (i32, [vp, C.POINTER(vp)]),
+        "d3_peer_close": (i32, [vp]),
+        "d3_peer_free": (i32, [vp]),
+        "d3_denormalize_gather": (i32, [vp, i64, i64, i32, f32, f32, f32, f32, C.POINTER(vp), i32, i64, vp]),
+        "d3_peer_push": (i32, [vp, C.c_size_t, C.POINTER(vp), i32, C.c_size_t, vp]),
+        "d3_peer_signal": (i32, [C.POINTER(vp), i32, i32, C.c_uint32, vp]),
+        "d3_peer_wait": (i32, [vp, i32, C.c_uint32, vp]),
         "d3_ensemble_workspace_bytes": (C.c_size_t, []),
         "d3_ensemble_objective": (i32, [vp, i32, i64, vp, vp, i32, vp, vp, vp]),
         "d3_ensemble_reduce": (i32, [vp, i32, i64, vp, vp, i32, vp, vp, vp, vp]),

@@ -106,3 +106,148 @@ def run_distributed_eval(config, pipeline, n_total: int, batch_size: int, make_b
     local = torch.cat(rows) if rows else torch.zeros((0, 11), dtype=torch.float64, device=device)
     allrows = all_gather_variable(local, n_total, rank, world).cpu().numpy()
     return metrics.metrics_to_dict(allrows[:, :5], allrows[:, 5:]), allrows
+
+
+class _DevicePtr:
+    """A raw device allocation exposed through the CUDA array interface so that torch can view it without copying."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerGather:
+    """The output all-gather of the evaluation sweep (distributed_evaluate.py:162-163) as stores into NVLink peer memory
+    issued by the LAST KERNEL of the loop, instead of an NCCL call after it (csrc/peer_gather.cu).
+
+    Every rank allocates ``2 x world x slot`` bytes (double-buffered by epoch) plus a flag array through the library
+    (``d3_peer_alloc``), the CUDA IPC handles are exchanged ONCE with ``dist.all_gather_object``, peers are mapped with
+    ``d3_peer_open``.  Per step: ``denormalize_into(y, normalizer)`` (``Normalizer.denormalize`` fused with the stores
+    into every rank's buffer) and / or ``push(tensor, region)``, then ``finish()`` = signal + wait, which returns this
+    rank's gathered views.  Regions: name -> (per-rank shape, dtype).  No NCCL call, no host synchronisation per step.
+    """
+
+    _FLAG_BYTES = 256
+
+    def __init__(self, regions: dict, rank: Optional[int] = None, world: Optional[int] = None, group=None, device=None):
+        import ctypes as C
+        from . import _lib
+        self._lib, self._C = _lib, C
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        if not 1 <= self.world <= 16:
+            raise ValueError("PeerGather: 1 <= world <= 16 ranks of one NVLink domain")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._regions, off = {}, 0
+        for name, (shape, dtype) in regions.items():
+            nbytes = int(torch.empty((), dtype=dtype).element_size())
+            for s in shape:
+                nbytes *= int(s)
+            slot = (nbytes + 255) // 256 * 256
+            self._regions[name] = (tuple(shape), dtype, nbytes, slot, off)
+            off += slot * self.world
+        self._parity_bytes = off
+        self._flag_off = 2 * off
+        total = self._flag_off + self._FLAG_BYTES
+        ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().d3_peer_alloc(total, C.byref(ptr), handle))
+        self._own = ptr.value
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(handle), group=group)
+        else:
+            handles[0] = bytes(handle)
+        self._bases, self._opened = [], []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self._bases.append(self._own)
+                continue
+            p = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().d3_peer_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(p)))
+            self._bases.append(p.value)
+            self._opened.append(p.value)
+        self._raw = _DevicePtr(self._own, total)
+        self._local = torch.as_tensor(self._raw, device=self.device)         # uint8 view of this rank's whole buffer
+        self.epoch = 0
+        self._pushed = False
+        if self.world > 1:
+            dist.barrier(group=group)          # every rank has mapped every buffer before the first store
+
+    def _ptr_array(self, byte_offset: int):
+        C = self._C
+        return (C.c_void_p * self.world)(*[b + byte_offset for b in self._bases])
+
+    def _stream(self):
+        return self._C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _begin(self):
+        if not self._pushed:
+            self.epoch += 1
+            self._pushed = True
+        return (self.epoch & 1) * self._parity_bytes
+
+    def denormalize_into(self, y: torch.Tensor, normalizer, region: str = "disp") -> None:
+        """``normalizer.denormalize(y)`` ("average" mode, utils.py:252-273) for this rank's maps ``y [n, R*num_chs, H, W]``
+        written straight into slot ``rank`` of every rank's buffer."""
+        shape, dtype, nbytes, slot, off = self._regions[region]
+        if dtype != torch.float32 or normalizer.ssi or normalizer.mode != "average":
+            raise NotImplementedError("denormalize_into: fp32 maps, non-SSI 'average' normaliser")
+        if not (y.is_cuda and y.dtype == torch.float32 and y.is_contiguous()):
+            raise ValueError("denormalize_into: contiguous fp32 CUDA tensor expected (no CPU fallback)")
+        nc = int(normalizer.num_chs)
+        NR, HW = y.shape[0] * (y.shape[1] // nc), y.shape[2] * y.shape[3]
+        if NR * HW * 4 != nbytes:
+            raise ValueError(f"denormalize_into: result has {NR * HW} elements, region {region!r} holds {nbytes // 4}")
+        base = self._begin() + off + self.rank * slot
+        self._lib.check(self._lib.lib().d3_denormalize_gather(
+            y.data_ptr(), NR, HW, nc, float(normalizer.ch_bounds[0]), float(normalizer.ch_gammas[0]),
+            float(normalizer.t), float(normalizer.s), self._ptr_array(0), self.world, base // 4, self._stream()))
+
+    def push(self, x: torch.Tensor, region: str) -> None:
+        """Final bytes (e.g. the fp64 [n, 11] metric rows) into slot ``rank`` of every rank's buffer."""
+        shape, dtype, nbytes, slot, off = self._regions[region]
+        if not (x.is_cuda and x.dtype == dtype and x.is_contiguous() and x.numel() * x.element_size() == nbytes):
+            raise ValueError(f"push: contiguous CUDA tensor of shape {shape} / {dtype} expected")
+        base = self._begin() + off + self.rank * slot
+        self._lib.check(self._lib.lib().d3_peer_push(x.data_ptr(), nbytes, self._ptr_array(0), self.world, base,
+                                                     self._stream()))
+
+    def _local_slot(self, region: str) -> torch.Tensor:
+        """This rank's own slot of the epoch being pushed (its copy in the local buffer): valid in stream order after
+        ``denormalize_into`` / ``push`` - lets later kernels of the step (the metric rows) read the result in place."""
+        shape, dtype, nbytes, slot, off = self._regions[region]
+        base = (self.epoch & 1) * self._parity_bytes + off + self.rank * slot
+        return self._local[base:base + nbytes].view(dtype).view(shape)
+
+    def finish(self) -> dict:
+        """Signal every peer that this rank's slots of the epoch are complete, wait (on the stream) for all of theirs,
+        return ``{region: [world, *shape] view}`` of this rank's buffer - valid until the epoch after next is pushed."""
+        if not self._pushed:
+            raise RuntimeError("PeerGather.finish() without a push")
+        lib, st = self._lib.lib(), self._stream()
+        self._lib.check(lib.d3_peer_signal(self._ptr_array(self._flag_off), self.world, self.rank, self.epoch, st))
+        self._lib.check(lib.d3_peer_wait(self._own + self._flag_off, self.world, self.epoch, st))
+        self._pushed = False
+        par = (self.epoch & 1) * self._parity_bytes
+        out = {}
+        for name, (shape, dtype, nbytes, slot, off) in self._regions.items():
+            rows = self._local[par + off:par + off + slot * self.world].view(self.world, slot)[:, :nbytes]
+            out[name] = rows.view(dtype).view((self.world,) + shape) if slot == nbytes else \
+                rows.contiguous().view(dtype).view((self.world,) + shape)
+        return out
+
+    def close(self, group=None):
+        """Unmap the peers and free the buffer; collective (nobody may still be storing into a freed buffer)."""
+        if self._own is None:
+            return
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=group)
+        for p in self._opened:
+            self._lib.check(self._lib.lib().d3_peer_close(p))
+        self._local = self._raw = None
+        if self.world > 1:
+            dist.barrier(group=group)
+        self._lib.check(self._lib.lib().d3_peer_free(self._own))
+        self._own, self._opened, self._bases = None, [], []

@@ -379,6 +379,25 @@ int d3_cross_attention_small(const void* q, int q_pitch, const float* kc, const 
  * Linear layers of the text encoder.  bias may be NULL; K % 4 == 0. */
 int d3_linear_small(const float* x, int n_rows, int K, const float* w, const float* bias, int rows, int act_in,
                     int act_out, float* out, int out_stride, void* stream);
+/* Output gather over NVLink peer memory (distributed_evaluate.py:162-163 `gather_for_metrics` of the predicted maps and
+ * metric rows).  One process per GPU: d3_peer_alloc makes this rank's gather buffer (cudaMalloc, zeroed) and
+ * its 64-byte CUDA IPC handle; the handles are exchanged by the host (torch.distributed) and d3_peer_open maps a peer's
+ * buffer into this process (peer access over NVLink).  Per step:
+ *   d3_denormalize_gather: Normalizer.denormalize (utils.py:252-273, as d3_denormalize_disp) with every value stored at
+ *     element dst_elem_offset + i of EACH of the n_dst buffers (dst_bases: HOST array of device pointers, own buffer
+ *     included) - the exchange is part of the last kernel of the loop;
+ *   d3_peer_push: the same multi-destination store for final bytes (metric rows);
+ *   d3_peer_signal: flag word `slot` of every peer's flag array := epoch (release, system scope), launched after the stores;
+ *   d3_peer_wait: returns (in stream order) when the n local flag words are >= epoch; traps after ~20 s without a peer. */
+int d3_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int d3_peer_open(const unsigned char* handle64, void** ptr);
+int d3_peer_close(void* ptr);
+int d3_peer_free(void* ptr);
+int d3_denormalize_gather(const float* y, int64_t NR, int64_t HW, int num_chs, float bound, float gamma, float t, float s,
+                          void* const* dst_bases, int n_dst, int64_t dst_elem_offset, void* stream);
+int d3_peer_push(const void* src, size_t bytes, void* const* dst_bases, int n_dst, size_t dst_byte_offset, void* stream);
+int d3_peer_signal(void* const* flag_bases, int n_dst, int slot, uint32_t epoch, void* stream);
+int d3_peer_wait(const uint32_t* local_flags, int n, uint32_t epoch, void* stream);
 /* ensemble_depths (utils_d3roma/utils.py:28-120; `config.ensemble`, evaluate.py:117-120): n <= 32 maps [n][P] of one
  * sample, per-map scale s and shift t (HOST arrays of n floats: the BFGS iterate of scipy lives on the host).
  *   d3_ensemble_objective: one evaluation of the closure of utils.py:64-87: out3 (device, 3 doubles) =

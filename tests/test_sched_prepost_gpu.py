@@ -177,3 +177,39 @@ def test_guidance_gradient_vs_reference_and_oracle():
                                x0 - 0.01 * fg.grad(x0, l, r), rtol=1e-5, atol=1e-5)
     with pytest.raises(NotImplementedError):
         FlowGuidance().perturb(x0, 5, None, None)
+
+
+def test_peer_gather_single_rank_equals_denormalize():
+    """d3roma_b200.distributed.PeerGather on one rank (the kernels and the buffer plumbing of the multi-GPU output gather;
+    the cross-rank form is tools/check_peer_gather.py under torchrun): Normalizer.denormalize fused with the store into
+    the gather buffer is bit-identical to Normalizer.denormalize, pushes land in their region, epochs alternate buffers."""
+    import d3roma_b200 as d
+    from d3roma_b200.distributed import PeerGather
+    norm = d.Normalizer(ssi=False, mode="average", num_chs=1, ch_bounds=[128.], ch_gammas=[1.], t=0.5, s=2.0)
+    pg = PeerGather({"disp": ((3, 1, 20, 36), torch.float32), "rows": ((3, 11), torch.float64)}, rank=0, world=1)
+    g = torch.Generator().manual_seed(2)
+    seen = []
+    for epoch in range(3):
+        y = (torch.rand(3, 1, 20, 36, generator=g) * 2 - 1).cuda()
+        rows = torch.rand(3, 11, generator=g, dtype=torch.float64).cuda()
+        pg.denormalize_into(y, norm)
+        assert torch.equal(pg._local_slot("disp"), norm.denormalize(y))
+        pg.push(rows, "rows")
+        out = pg.finish()
+        assert out["disp"].shape == (1, 3, 1, 20, 36) and out["rows"].shape == (1, 3, 11)
+        assert torch.equal(out["disp"][0], norm.denormalize(y)) and torch.equal(out["rows"][0], rows)
+        seen.append((out["disp"], norm.denormalize(y)))
+        if epoch:
+            assert torch.equal(seen[-2][0], seen[-2][1])            # the previous epoch's buffer is untouched
+    with pytest.raises(RuntimeError):
+        pg.finish()
+    with pytest.raises(ValueError):
+        pg.push(torch.zeros(2, 11, dtype=torch.float64).cuda(), "rows")
+    pg.close()
+    # two gamma-corrected channels averaged (the general form of the "average" mode)
+    norm2 = d.Normalizer(ssi=False, mode="average", num_chs=2, ch_bounds=[64.], ch_gammas=[0.5], t=0.5, s=2.0)
+    pg2 = PeerGather({"disp": ((2, 1, 8, 12), torch.float32)}, rank=0, world=1)
+    y2 = (torch.rand(2, 2, 8, 12, generator=g) * 2 - 1).cuda()
+    pg2.denormalize_into(y2, norm2)
+    assert torch.equal(pg2.finish()["disp"][0], norm2.denormalize(y2))
+    pg2.close()
