@@ -198,7 +198,7 @@ def test_peer_gather_single_rank_equals_denormalize():
         out = pg.finish()
         assert out["disp"].shape == (1, 3, 1, 20, 36) and out["rows"].shape == (1, 3, 11)
         assert torch.equal(out["disp"][0], norm.denormalize(y)) and torch.equal(out["rows"][0], rows)
-        seen.append((out["disp"], norm.denormalize(y)))
+        seen.append((out["disp"][0], norm.denormalize(y)))
         if epoch:
             assert torch.equal(seen[-2][0], seen[-2][1])            # the previous epoch's buffer is untouched
     with pytest.raises(RuntimeError):
