@@ -50,16 +50,8 @@ def _worker(rank, world, port, n, q):
 
 @pytest.mark.parametrize("world,n", [(2, 7), (3, 8), (2, 1)])
 def test_sharded_eval_gathers_in_global_order(world, n):
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    results = dict(q.get(timeout=120) for _ in range(world))
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    from tests._util import run_ranks
+    results = dict(run_ranks(_worker, world, (n,)))
     want = _expected(n)
     for r in range(world):
         assert torch.equal(results[r], want), f"rank {r}"
@@ -103,18 +95,10 @@ def test_distributed_eval_metric_rows_independent_of_world_size():
     """distributed_evaluate.py:153-163: the gathered [N, 5] + [N, 6] fp64 metric rows come back in global sample order and
     are the same at world_size 1 and 2."""
     import numpy as np
-    ctx = mp.get_context("spawn")
+    from tests._util import run_ranks
     got = {}
     for world in (1, 2):
-        q = ctx.Queue()
-        port = _free_port()
-        procs = [ctx.Process(target=_eval_worker, args=(r, world, port, 5, q)) for r in range(world)]
-        for p in procs:
-            p.start()
-        res = [q.get(timeout=120) for _ in range(world)]
-        for p in procs:
-            p.join(timeout=60)
-            assert p.exitcode == 0
+        res = run_ranks(_eval_worker, world, (5,))
         for _, rows, keys in res:
             assert rows.shape == (5, 11) and rows.dtype == np.float64 and keys == ["depth", "disp"]
         got[world] = res

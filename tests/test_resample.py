@@ -1,6 +1,5 @@
 """Timestep samplers (d3roma_b200/resample.py) against the reference's own module (core/resample.py, imported live when
 /root/reference is present), stand-alone properties, and the cross-rank loss exchange over gloo (world size 2)."""
-import socket
 import sys
 
 import numpy as np
@@ -84,19 +83,8 @@ def _worker(rank, world, port, q):
 
 
 def test_update_with_local_losses_over_gloo():
-    import torch.multiprocessing as mp
-    with socket.socket() as sk:
-        sk.bind(("127.0.0.1", 0))
-        port = sk.getsockname()[1]
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    got = dict((r, (c, h)) for r, c, h in (q.get(timeout=120) for _ in range(2)))
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    from tests._util import run_ranks
+    got = dict((r, (c, h)) for r, c, h in run_ranks(_worker, 2))
     # what one process would hold after the same updates in rank order
     want = R.LossSecondMomentResampler(16, history_per_term=2)
     gens = [torch.Generator().manual_seed(r) for r in range(2)]

@@ -117,8 +117,7 @@ def _ddp_worker(rank, world, port, q):
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     out = _run_steps(training, lambda x: x[rank::world], world)
-    if rank == 0:
-        q.put({k: v.numpy() for k, v in out.items()})
+    q.put({k: v.numpy() for k, v in out.items()})      # every rank reports (ranks hold identical parameters)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -150,21 +149,9 @@ def _run_steps(training, shard, world):
 def test_data_parallel_matches_global_batch(trainer_mod):
     """world_size 2 over gloo: each rank takes every second sample, gradients are all-reduced and averaged before
     clipping / AdamW - the parameters after two steps equal those of one process training on the whole batch."""
-    import socket
-    import torch.multiprocessing as mp
+    from tests._util import run_ranks
     want = _run_steps(trainer_mod, lambda x: x, 1)
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    got = q.get(timeout=600)
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    got = run_ranks(_ddp_worker, 2, timeout=600)[0]
     for k, v in want.items():
         assert float(np.abs(got[k] - v.numpy()).max()) < 2e-5, k
 
