@@ -30,20 +30,32 @@ struct EnsArgs {
   float s[kEnsMaxN], t[kEnsMaxN];
 };
 
+// The kernels are instantiated for every map count up to 8 (NT = n: loops unroll, the per-pixel values live in
+// registers) and once generically (NT = 0: runtime n <= 32, values in local memory).
+template <int NT>
+D3_DEVINL int count_of(int n) { return NT ? NT : n; }
+
 // lower median of v[0..n) (torch.median: the element of rank (n - 1) / 2), by rank counting - no data movement
-D3_DEVINL float lower_median(const float* v, int n) {
+template <int NT>
+D3_DEVINL float lower_median(const float* v, int n_rt) {
+  const int n = count_of<NT>(n_rt);
   const int k = (n - 1) >> 1;
   float med = v[0];
+#pragma unroll
   for (int i = 0; i < n; ++i) {
     int rank = 0;
+#pragma unroll
     for (int j = 0; j < n; ++j) rank += (v[j] < v[i]) || (v[j] == v[i] && j < i);
     if (rank == k) med = v[i];
   }
   return med;
 }
 
-D3_DEVINL float mean_of(const float* v, int n) {
+template <int NT>
+D3_DEVINL float mean_of(const float* v, int n_rt) {
+  const int n = count_of<NT>(n_rt);
   float a = v[0];
+#pragma unroll
   for (int i = 1; i < n; ++i) a = __fadd_rn(a, v[i]);   // torch's outer-dimension reduction adds the rows in order
   return __fdiv_rn(a, (float)n);
 }
@@ -71,44 +83,55 @@ D3_DEVINL void block_partials(double sum, float mn, float mx, double* __restrict
   }
 }
 
+template <int NT>
 __global__ void __launch_bounds__(kEnsThreads) ensemble_objective_kernel(const EnsArgs a, double* __restrict__ partial) {
-  float v[kEnsMaxN];
+  float v[NT ? NT : kEnsMaxN];
+  const int n = count_of<NT>(a.n);
   double sum = 0.0;
   float mn = INFINITY, mx = -INFINITY;
   for (int64_t p = (int64_t)blockIdx.x * kEnsThreads + threadIdx.x; p < a.P; p += (int64_t)gridDim.x * kEnsThreads) {
-    for (int i = 0; i < a.n; ++i) v[i] = __fadd_rn(__fmul_rn(__ldg(a.images + (size_t)i * a.P + p), a.s[i]), a.t[i]);
-    for (int i = 0; i < a.n; ++i)
-      for (int j = i + 1; j < a.n; ++j) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) v[i] = __fadd_rn(__fmul_rn(__ldg(a.images + (size_t)i * a.P + p), a.s[i]), a.t[i]);
+#pragma unroll
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+      for (int j = i + 1; j < n; ++j) {
         const double d = (double)__fsub_rn(v[i], v[j]);    // the fp32 difference of the reference, squared and summed in fp64
         sum = fma(d, d, sum);
       }
-    const float pred = a.median ? lower_median(v, a.n) : mean_of(v, a.n);
+    const float pred = a.median ? lower_median<NT>(v, n) : mean_of<NT>(v, n);
     mn = fminf(mn, pred);
     mx = fmaxf(mx, pred);
   }
   block_partials(sum, mn, mx, partial);
 }
 
+template <int NT>
 __global__ void __launch_bounds__(kEnsThreads) ensemble_reduce_kernel(const EnsArgs a, float* __restrict__ aligned,
                                                                      float* __restrict__ uncertainty,
                                                                      double* __restrict__ partial) {
-  float v[kEnsMaxN], dev[kEnsMaxN];
+  float v[NT ? NT : kEnsMaxN], dev[NT ? NT : kEnsMaxN];
+  const int n = count_of<NT>(a.n);
   float mn = INFINITY, mx = -INFINITY;
   for (int64_t p = (int64_t)blockIdx.x * kEnsThreads + threadIdx.x; p < a.P; p += (int64_t)gridDim.x * kEnsThreads) {
-    for (int i = 0; i < a.n; ++i) v[i] = __fadd_rn(__fmul_rn(__ldg(a.images + (size_t)i * a.P + p), a.s[i]), a.t[i]);
+#pragma unroll
+    for (int i = 0; i < n; ++i) v[i] = __fadd_rn(__fmul_rn(__ldg(a.images + (size_t)i * a.P + p), a.s[i]), a.t[i]);
     float al, un;
     if (a.median) {
-      al = lower_median(v, a.n);
-      for (int i = 0; i < a.n; ++i) dev[i] = fabsf(__fsub_rn(v[i], al));
-      un = lower_median(dev, a.n);
+      al = lower_median<NT>(v, n);
+#pragma unroll
+      for (int i = 0; i < n; ++i) dev[i] = fabsf(__fsub_rn(v[i], al));
+      un = lower_median<NT>(dev, n);
     } else {
-      al = mean_of(v, a.n);
+      al = mean_of<NT>(v, n);
       // torch.std(dim=0): unbiased; two-pass in fp64 here (torch runs Welford's update: equal to within an ulp or two)
       double m = 0.0, q = 0.0;
-      for (int i = 0; i < a.n; ++i) m += (double)v[i];
-      m /= (double)a.n;
-      for (int i = 0; i < a.n; ++i) { const double d = (double)v[i] - m; q += d * d; }
-      un = a.n > 1 ? (float)sqrt(q / (double)(a.n - 1)) : __int_as_float(0x7fc00000);
+#pragma unroll
+      for (int i = 0; i < n; ++i) m += (double)v[i];
+      m /= (double)n;
+#pragma unroll
+      for (int i = 0; i < n; ++i) { const double d = (double)v[i] - m; q += d * d; }
+      un = n > 1 ? (float)sqrt(q / (double)(n - 1)) : __int_as_float(0x7fc00000);
     }
     aligned[p] = al;
     uncertainty[p] = un;
@@ -175,7 +198,12 @@ extern "C" int d3_ensemble_objective(const float* images, int n, int64_t P, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int blocks = ens_blocks(P);
   double* partial = static_cast<double*>(workspace);
-  ensemble_objective_kernel<<<blocks, kEnsThreads, 0, st>>>(a, partial);
+  switch (n) {
+#define D3_ENS_CASE(N) case N: ensemble_objective_kernel<N><<<blocks, kEnsThreads, 0, st>>>(a, partial); break;
+    D3_ENS_CASE(1) D3_ENS_CASE(2) D3_ENS_CASE(3) D3_ENS_CASE(4) D3_ENS_CASE(5) D3_ENS_CASE(6) D3_ENS_CASE(7) D3_ENS_CASE(8)
+#undef D3_ENS_CASE
+    default: ensemble_objective_kernel<0><<<blocks, kEnsThreads, 0, st>>>(a, partial);
+  }
   D3_LAUNCH_CHECK();
   ensemble_finalize_kernel<<<1, kEnsThreads, 0, st>>>(partial, blocks, out3);
   D3_LAUNCH_CHECK();
@@ -191,7 +219,12 @@ extern "C" int d3_ensemble_reduce(const float* images, int n, int64_t P, const f
   const int blocks = ens_blocks(P);
   double* partial = static_cast<double*>(workspace);
   double* out3 = partial + (size_t)kEnsMaxBlocks * 3;
-  ensemble_reduce_kernel<<<blocks, kEnsThreads, 0, st>>>(a, aligned, uncertainty, partial);
+  switch (n) {
+#define D3_ENS_CASE(N) case N: ensemble_reduce_kernel<N><<<blocks, kEnsThreads, 0, st>>>(a, aligned, uncertainty, partial); break;
+    D3_ENS_CASE(1) D3_ENS_CASE(2) D3_ENS_CASE(3) D3_ENS_CASE(4) D3_ENS_CASE(5) D3_ENS_CASE(6) D3_ENS_CASE(7) D3_ENS_CASE(8)
+#undef D3_ENS_CASE
+    default: ensemble_reduce_kernel<0><<<blocks, kEnsThreads, 0, st>>>(a, aligned, uncertainty, partial);
+  }
   D3_LAUNCH_CHECK();
   ensemble_finalize_kernel<<<1, kEnsThreads, 0, st>>>(partial, blocks, out3);
   D3_LAUNCH_CHECK();

@@ -52,6 +52,24 @@ __global__ void __launch_bounds__(256) denormalize_gather_kernel(const float* __
   }
 }
 
+// num_chs == 1: elementwise, four values per thread, 16-byte loads and (local + NVLink) stores
+__global__ void __launch_bounds__(256) denormalize_gather_vec4_kernel(const float4* __restrict__ y, int64_t n4, float bound,
+                                                                     float gamma, float t, float s, const PeerPtrs dst,
+                                                                     int64_t dst_off4) {
+  const float inv_gamma = 1.0f / gamma;
+  auto f = [&](float x) {
+    float v = __fadd_rn(__fdiv_rn(x, s), t);
+    if (gamma != 1.0f) v = powf(v, inv_gamma);
+    return __fadd_rn(0.f, __fmul_rn(v, bound));
+  };
+  D3_GRID_STRIDE(i, n4) {
+    const float4 a = __ldcs(y + i);
+    const float4 z = make_float4(f(a.x), f(a.y), f(a.z), f(a.w));
+#pragma unroll 4
+    for (int k = 0; k < dst.n; ++k) static_cast<float4*>(dst.p[k])[dst_off4 + i] = z;
+  }
+}
+
 // 16-byte vectors when everything is aligned, bytes otherwise
 __global__ void __launch_bounds__(256) peer_push_kernel(const unsigned char* __restrict__ src, size_t bytes,
                                                        const PeerPtrs dst, size_t dst_off, int vec) {
@@ -149,6 +167,16 @@ extern "C" int d3_denormalize_gather(const float* y, int64_t NR, int64_t HW, int
   PeerPtrs pp;
   if (int rc = fill_ptrs(pp, dst_bases, n_dst, "denormalize_gather")) return rc;
   if (NR * HW == 0) return D3_OK;
+  bool vec = num_chs == 1 && (NR * HW) % 4 == 0 && dst_elem_offset % 4 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0;
+  for (int k = 0; k < n_dst; ++k) vec = vec && reinterpret_cast<uintptr_t>(dst_bases[k]) % 16 == 0;
+  if (vec) {
+    const int64_t n4 = NR * HW / 4, w4 = (n4 + 255) / 256;
+    const int b4 = (int)(w4 < (int64_t)num_sms() * 16 ? w4 : (int64_t)num_sms() * 16);
+    denormalize_gather_vec4_kernel<<<b4, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(y), n4, bound, gamma, t, s, pp, dst_elem_offset / 4);
+    D3_LAUNCH_CHECK();
+    return D3_OK;
+  }
   const int64_t want = (NR * HW + 255) / 256;
   const int blocks = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
   denormalize_gather_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, NR, HW, num_chs, bound, gamma, t, s,

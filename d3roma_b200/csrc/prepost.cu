@@ -60,6 +60,23 @@ __global__ void denormalize_disp_kernel(const float* __restrict__ y, int64_t NR,
   }
 }
 
+// num_chs == 1 (every pixel-space config): purely elementwise - four maps values per thread, 16-byte loads and stores,
+// no index division; the arithmetic (and its rounding sequence) is that of denormalize_disp_kernel.
+__global__ void __launch_bounds__(256) denormalize_disp_vec4_kernel(const float4* __restrict__ y, int64_t n4, float bound,
+                                                                   float gamma, float t, float s,
+                                                                   float4* __restrict__ out) {
+  const float inv_gamma = 1.0f / gamma;
+  auto f = [&](float x) {
+    float v = __fadd_rn(__fdiv_rn(x, s), t);
+    if (gamma != 1.0f) v = powf(v, inv_gamma);
+    return __fadd_rn(0.f, __fmul_rn(v, bound));
+  };
+  D3_GRID_STRIDE(i, n4) {
+    const float4 a = __ldcs(y + i);
+    out[i] = make_float4(f(a.x), f(a.y), f(a.z), f(a.w));
+  }
+}
+
 // Normalizer "piecewise" mode (utils_d3roma/utils.py:198-229): the disparity is split over up to 3 channels, channel c
 // covering the range [sum_{j<c} bound_j, sum_{j<=c} bound_j):
 //   ch0 = min(x, b0) / b0, res0 = (ch0 < 1) ? 0 : x - b0;  ch1 = min(res0, b1) / b1, res1 = (ch1 < 1) ? 0 : res0 - b1; ...
@@ -197,6 +214,14 @@ extern "C" int d3_denormalize_disp(const float* y, int64_t NR, int64_t HW, int n
                                    float t, float s, float* out, void* stream) {
   D3_REQUIRE(y && out && num_chs >= 1 && bound > 0.f && gamma > 0.f && s != 0.f, "denormalize_disp: bad arguments");
   if (NR * HW == 0) return D3_OK;
+  if (num_chs == 1 && (NR * HW) % 4 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0 &&
+      reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+    const int64_t n4 = NR * HW / 4;
+    denormalize_disp_vec4_kernel<<<ew_blocks(n4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(y), n4, bound, gamma, t, s, reinterpret_cast<float4*>(out));
+    D3_LAUNCH_CHECK();
+    return D3_OK;
+  }
   denormalize_disp_kernel<<<ew_blocks(NR * HW), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, NR, HW, num_chs,
                                                                                            bound, gamma, t, s, out);
   D3_LAUNCH_CHECK();

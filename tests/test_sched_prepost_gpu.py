@@ -213,3 +213,23 @@ def test_peer_gather_single_rank_equals_denormalize():
     pg2.denormalize_into(y2, norm2)
     assert torch.equal(pg2.finish()["disp"][0], norm2.denormalize(y2))
     pg2.close()
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 20, 36), (1, 1, 5, 7), (3, 1, 9, 11), (16, 1, 360, 640)])
+@pytest.mark.parametrize("gamma", [1.0, 0.5])
+def test_denormalize_vector_and_scalar_paths_agree_with_torch(shape, gamma):
+    """Normalizer.denormalize, one channel: the 16-byte path (element count divisible by 4) and the scalar path give
+    torch's result for ``(y / s + t) ** (1 / gamma) * bound`` - bit for bit at gamma = 1."""
+    import d3roma_b200 as d
+    norm = d.Normalizer(ssi=False, mode="average", num_chs=1, ch_bounds=[128.], ch_gammas=[gamma], t=0.5, s=2.0)
+    y = (torch.rand(shape, generator=torch.Generator().manual_seed(sum(shape))) * 2 - 1).cuda()
+    got = norm.denormalize(y)
+    want = (y / 2.0 + 0.5)
+    if gamma == 1.0:
+        assert torch.equal(got, want * 128.0)
+    else:
+        assert torch.allclose(got, want.pow(1.0 / gamma) * 128.0, rtol=2e-6, atol=1e-5)
+    # an unaligned view (storage offset of one element) takes the scalar path and gives the same values
+    buf = torch.empty(y.numel() + 1, device="cuda")
+    buf[1:] = y.reshape(-1)
+    assert torch.equal(norm.denormalize(buf[1:].view(shape)), got)
