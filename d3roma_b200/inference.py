@@ -6,7 +6,9 @@ Everything between the numpy arrays and the pipeline call — cv2.resize, HWC->C
 (``d3_frame_to_input``, ``d3_depth_to_input``); everything after it (unpad, denormalise, mean over rounds, disparity ->
 depth) stays on the device until the final copy.  Construction: pass a ready pipeline, camera and config namespace, or
 ``D3RoMa.from_config(config, camera)`` which loads the pipeline from ``config.resume_pretrained`` like the reference's
-``_load_pipeline`` (inference.py:66-95; no hydra); the methods are the reference's.
+``_load_pipeline`` (inference.py:66-95; no hydra); the public methods (``infer``, ``infer_with_rgb_raw``) are the
+reference's.  The internal ``run_pipeline`` takes the RAW frames and depth (the reference's takes tensors its callers
+preprocessed, inference.py:191) because resize / normalise / pad are fused into the two kernels above.
 """
 from __future__ import annotations
 

@@ -78,3 +78,59 @@ def test_train_step_signature():
     assert ours == theirs
     assert [p.name for p in sig.parameters.values() if p.default is None] == theirs[-n_def:]
     assert fn.args.kwarg is not None and any(p.kind == p.VAR_KEYWORD for p in sig.parameters.values())
+
+
+def _ast_args(path, name, cls=None):
+    """Positional argument names (and the literal defaults of the trailing ones) of a function read from source."""
+    import ast
+    tree = ast.parse(path.read_text())
+    scope = tree
+    if cls is not None:
+        scope = next(n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == cls)
+    fn = next(n for n in ast.walk(scope) if isinstance(n, ast.FunctionDef) and n.name == name)
+    defaults = [ast.literal_eval(d) for d in fn.args.defaults]
+    return [a.arg for a in fn.args.args], defaults
+
+
+def test_evaluation_side_signatures(ref_modules):
+    """eval_batch / evaluate_intermediate_metrics (evaluate.py imports hydra: read with ast), ensemble_depths,
+    compute_errors, compute_scale_and_shift, metrics_to_dict (utils_d3roma/utils.py: imported)."""
+    from d3roma_b200 import evaluate, metrics
+    ru = ref_modules["utils"]
+    for name in ("ensemble_depths", "compute_errors", "compute_scale_and_shift", "metrics_to_dict"):
+        assert _params(getattr(metrics, name)) == _params(getattr(ru, name)), name
+    for name in ("eval_batch", "evaluate_intermediate_metrics", "denormalize"):
+        theirs, defaults = _ast_args(REF / "evaluate.py", name)
+        sig = inspect.signature(getattr(evaluate, name))
+        ours = [p.name for p in sig.parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]
+        assert ours[:len(theirs)] == theirs, name             # ours may add trailing keyword options (generator, as_numpy)
+        extra = ours[len(theirs):]
+        assert all(sig.parameters[e].default is not inspect.Parameter.empty for e in extra), (name, extra)
+
+
+def test_latent_pipeline_text_encoder_and_sampler_signatures(ref_modules):
+    import d3roma_b200 as d
+    from d3roma_b200 import resample
+    rp = ref_modules["pipelines"].GuidedLatentDiffusionPipeline
+    assert _params(d.GuidedLatentDiffusionPipeline.__init__) == _params(rp.__init__)
+    assert _params(d.GuidedLatentDiffusionPipeline.__call__) == _params(rp.__call__)
+    sys.path.insert(0, str(REF))
+    try:
+        from core import resample as ref_resample
+    finally:
+        sys.path.remove(str(REF))
+    assert _params(resample.create_named_schedule_sampler) == _params(ref_resample.create_named_schedule_sampler)
+    for cls in ("UniformSampler", "SNRSampler", "LossSecondMomentResampler"):
+        assert _params(getattr(resample, cls).__init__) == _params(getattr(ref_resample, cls).__init__), cls
+    for name in ("sample", "weights"):
+        assert _params(getattr(resample.ScheduleSampler, name)) == _params(getattr(ref_resample.ScheduleSampler, name))
+    for name in ("update_with_local_losses", "update_with_all_losses"):
+        assert _params(getattr(resample.LossAwareSampler, name)) == _params(getattr(ref_resample.LossAwareSampler, name))
+    # the front end's methods (inference.py needs hydra: ast)
+    from d3roma_b200.inference import D3RoMa
+    # (run_pipeline is internal on both sides: the reference's takes preprocessed tensors, ours the raw frames, because the
+    # preprocessing is fused into two kernels)
+    for name in ("infer", "infer_with_rgb_raw"):
+        theirs, _ = _ast_args(REF / "inference.py", name, cls="D3RoMa")
+        ours = [p.name for p in inspect.signature(getattr(D3RoMa, name)).parameters.values()]
+        assert ours == theirs, name
