@@ -23,6 +23,7 @@
 #ifndef D3ROMA_B200_H
 #define D3ROMA_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
