@@ -61,3 +61,64 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     import pytest
     with pytest.raises(_lib.D3Error):
         _lib.lib()
+
+
+def test_ctypes_argument_counts_match_header_prototypes():
+    """Every ctypes binding in _lib.py takes exactly as many arguments as the header's prototype declares (a mismatch
+    would only show up as garbage arguments on the GPU)."""
+    from d3roma_b200 import _lib
+    l = _lib.lib()
+    text = (ROOT / "include" / "d3roma_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"\s+", " ", text)
+    protos = re.findall(r"\b(d3_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", text)
+    assert len(protos) >= 90
+    checked = 0
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        fn = getattr(l, name)
+        if fn.argtypes is None:
+            assert n == 0, f"{name}: {n} parameters in the header but no argtypes bound"
+            continue
+        assert len(fn.argtypes) == n, f"{name}: header declares {n} parameters, ctypes binds {len(fn.argtypes)}"
+        checked += 1
+    assert checked >= 85
+
+
+def test_ctypes_argument_types_match_header_prototypes():
+    """Scalar classes of every bound argument (pointer / float / double / 32-bit / 64-bit / size_t) against the header."""
+    import ctypes as C
+    from d3roma_b200 import _lib
+    l = _lib.lib()
+    text = (ROOT / "include" / "d3roma_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"\s+", " ", text)
+
+    def header_class(param: str) -> str:
+        if "*" in param or "[" in param:
+            return "ptr"
+        for tok, cls in (("double", "f64"), ("float", "f32"), ("int64_t", "i64"), ("size_t", "size"), ("uint32_t", "u32"),
+                         ("int32_t", "i32"), ("int", "i32")):
+            if re.search(r"\b%s\b" % tok, param):
+                return cls
+        raise AssertionError(f"unclassified parameter {param!r}")
+
+    def ctypes_class(t) -> str:
+        if t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or issubclass(t, C._Pointer) or issubclass(t, C.Array):
+            return "ptr"
+        return {C.c_float: "f32", C.c_double: "f64", C.c_int64: "i64", C.c_size_t: "size", C.c_uint32: "u32",
+                C.c_int32: "i32", C.c_int: "i32"}[t]
+
+    same_width = {("size", "i64"), ("i64", "size")}            # LP64: both are 64-bit integers in the same register class
+    bad = []
+    for name, params in re.findall(r"\b(d3_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", text):
+        fn = getattr(l, name)
+        if fn.argtypes is None:
+            continue
+        want = [] if params.strip() in ("", "void") else [header_class(p.strip()) for p in params.split(",")]
+        got = [ctypes_class(t) for t in fn.argtypes]
+        for i, (w, g) in enumerate(zip(want, got)):
+            if w != g and (w, g) not in same_width:
+                bad.append(f"{name} arg {i}: header {w}, ctypes {g}")
+    assert not bad, bad
