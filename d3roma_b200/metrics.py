@@ -137,8 +137,11 @@ def ensemble_depths(input_images: torch.Tensor, regularizer_strength: float = 0.
         raise ValueError("ensemble_depths: [n, H, W] expected")
     images = input_images.to(torch.float32).contiguous() if emulated else ops._f32c(input_images, "input_images")
     n = images.shape[0]
-    if not 1 <= n <= 32:
-        raise ValueError(f"ensemble_depths: 1 <= n <= 32 maps expected (got {n})")
+    if n < 2:
+        # the reference's closure concatenates the pair differences of torch.combinations: with one map the list is empty
+        raise RuntimeError("torch.cat(): expected a non-empty list of Tensors (ensemble_depths needs at least two maps)")
+    if n > 32:
+        raise ValueError(f"ensemble_depths: at most 32 maps (got {n})")
     median = reduction == "median"
     P = images[0].numel()
     dev = images.device
@@ -160,8 +163,7 @@ def ensemble_depths(input_images: torch.Tensor, regularizer_strength: float = 0.
         s = np.ascontiguousarray(x[: int(l / 2)], dtype=np.float32)     # torch.from_numpy(s).to(dtype=float32)
         t = np.ascontiguousarray(x[int(l / 2):], dtype=np.float32)
         acc, lo, hi = (float(v) for v in _ens_objective(images, s, t, median, ws, out3).cpu())
-        with np.errstate(invalid="ignore", divide="ignore"):
-            sqrt_dist = np.float32(np.sqrt(np.float32(acc / (n_pairs * P)))) if n_pairs else np.float32(np.nan)
+        sqrt_dist = np.float32(np.sqrt(np.float32(acc / (n_pairs * P))))
         near_err = np.float32(abs(0.0 - lo))          # sqrt((0 - min(pred)) ** 2)
         far_err = np.float32(abs(np.float32(1.0) - np.float32(hi)))
         err = np.float32(sqrt_dist + np.float32((near_err + far_err) * np.float32(regularizer_strength)))

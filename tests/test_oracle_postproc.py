@@ -98,3 +98,5 @@ def test_ensemble_depths_host_logic(monkeypatch, tag, n, seed, ties, red):
         metrics.ensemble_depths(E.make_inputs(3), reduction="mode")
     with pytest.raises(NotImplementedError):
         metrics.ensemble_depths(E.make_inputs(3), max_res=64)
+    with pytest.raises(RuntimeError):                   # one map: the reference's torch.cat of an empty list
+        metrics.ensemble_depths(E.make_inputs(1))
