@@ -8,7 +8,9 @@ One "step" = one pass of the hot path over one batch.  The default workload is B
 left+right+raw variant, 16 stereo pairs per GPU at 360x640 (computed at the padded 384x640 like the reference's eval
 path), 10 DDIM steps, in the fp16-operand mode (the mode that meets the north-star per-step tolerance; `--dtype bf16`
 times the secondary bf16 mode).  For N > 1 the driver launches this under torchrun; independent stereo pairs are
-sharded by rank (weak scaling) and the final disparity maps are all-gathered over NCCL inside the timed step.
+sharded by rank (weak scaling) and the final disparity maps are all-gathered inside the timed step: over NCCL by
+default, or (`--gather peer`) as stores into NVLink peer memory issued by the denormalise kernel itself
+(d3roma_b200.distributed.PeerGather; `config.gather` names what ran).
 
 Other BASELINE configs (parity-test cases made measurable; `config.workload` names what ran):
   c1  1 pair, DDIM 10 (configs[0] on the GPU: the B = 1 latency case)
