@@ -15,7 +15,10 @@ published diffusers module structure (ResnetBlock2D, Transformer2DModel with ``u
 BasicTransformerBlock = LayerNorm/self-attn/LayerNorm/cross-attn/LayerNorm/GEGLU-FF, Downsample2D / Upsample2D,
 UNetMidBlock2D(CrossAttn), DownEncoderBlock2D / UpDecoderBlock2D) with diffusers' parameter names, and is gated by the
 published parameter counts: 865 910 724 (SD-2.1 UNet, in_channels 4) and 83 653 863 (SD VAE) - see
-tests/test_oracle_ldm.py.  Reduced-width instances of the same modules are what the GPU parity tests compare against.
+tests/test_oracle_ldm.py.  For the VAE there is an independent second source as well: transformers' ports of the original
+latent-diffusion autoencoder (ChameleonVQVAEEncoder, JanusVQVAE* blocks) agree with the encoder as a whole and with the
+decoder's blocks when given the same weights (tests/test_oracle_ldm_crosscheck.py).  Reduced-width instances of the same
+modules are what the GPU parity tests compare against.
 """
 from __future__ import annotations
 
