@@ -101,3 +101,37 @@ def test_vae_decoder_blocks_match_the_original_ldm_block_ports():
                             "conv.bias": sd["up_blocks.0.upsamplers.0.conv.bias"]}, strict=True)
         h = torch.randn(1, 128, 7, 9, generator=g)
         assert float((dec.up_blocks[0].upsamplers[0](h) - up(h)).abs().max()) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------- pixel-space UNet pieces
+def test_timestep_embedding_matches_the_adm_form():
+    """oracle/unet_ref.timestep_embedding (diffusers ``Timesteps(flip_sin_to_cos=True, downscale_freq_shift=0)``, SURVEY
+    A.2) against an independent implementation of the ADM / improved-DDPM ``timestep_embedding`` that ships with
+    torchtitan's FLUX model (cos | sin, frequencies ``exp(-ln(1e4) i / half)``)."""
+    layers = pytest.importorskip("torchtitan.experiments.flux.model.layers")
+    from oracle.unet_ref import timestep_embedding
+    t = torch.tensor([0.0, 1.0, 13.0, 109.0, 127.0, 999.0])
+    want = layers.timestep_embedding(t, 128, time_factor=1.0)
+    got = timestep_embedding(t, 128)
+    assert got.shape == want.shape == (6, 128)
+    assert float((got - want).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("C,hw", [(256, (6, 10)), (512, (3, 5))])
+def test_attention_block_matches_torch_multihead_attention(C, hw):
+    """The restated attention block (heads of 8 channels, 1/sqrt(8) scaling, GroupNorm before, residual after) against
+    ``torch.nn.MultiheadAttention`` with the same projections: head split convention, scaling and softmax axis."""
+    from oracle.unet_ref import Attention
+    torch.manual_seed(3)
+    blk = Attention(C).eval()
+    mha = torch.nn.MultiheadAttention(C, C // 8, batch_first=True).eval()
+    with torch.no_grad():
+        mha.in_proj_weight.copy_(torch.cat([blk.to_q.weight, blk.to_k.weight, blk.to_v.weight]))
+        mha.in_proj_bias.copy_(torch.cat([blk.to_q.bias, blk.to_k.bias, blk.to_v.bias]))
+        mha.out_proj.weight.copy_(blk.to_out[0].weight)
+        mha.out_proj.bias.copy_(blk.to_out[0].bias)
+        x = torch.randn(2, C, *hw)
+        y = blk.group_norm(x.view(2, C, -1)).transpose(1, 2)
+        want = mha(y, y, y, need_weights=False)[0].transpose(1, 2).reshape(2, C, *hw) + x
+        got = blk(x)
+    assert float((got - want).abs().max()) < 2e-5
