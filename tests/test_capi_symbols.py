@@ -122,3 +122,21 @@ def test_ctypes_argument_types_match_header_prototypes():
             if w != g and (w, g) not in same_width:
                 bad.append(f"{name} arg {i}: header {w}, ctypes {g}")
     assert not bad, bad
+
+
+def test_every_exported_entry_point_is_declared_in_the_header():
+    """The reverse direction: no ``d3_*`` function leaves the library without a prototype (and its reference citation)
+    in include/d3roma_b200.h."""
+    import shutil
+    import subprocess
+    from d3roma_b200 import _lib
+    nm = shutil.which("nm")
+    if nm is None:
+        import pytest
+        pytest.skip("nm not available")
+    out = subprocess.run([nm, "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = sorted({line.split()[-1] for line in out.splitlines() if line.split() and line.split()[-1].startswith("d3_")
+                       and line.split()[-2] in ("T", "t")})
+    assert len(exported) >= 90
+    undeclared = [s for s in exported if s not in set(_declared())]
+    assert not undeclared, undeclared
